@@ -1,0 +1,298 @@
+"""ctypes binding of the CPU oracle (oracle/gen_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's CPU legs; never from the
+product package under gen.jl_b200/.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+if _HERE not in sys.path:
+    sys.path.insert(0, _HERE)
+import build as _build  # noqa: E402
+
+MODEL_LGSSM, MODEL_SV, MODEL_BEARINGS, MODEL_HMM, MODEL_BLR = 1, 2, 3, 4, 5
+PROPOSAL_DEFAULT, PROPOSAL_AFFINE_NORMAL, PROPOSAL_CATEGORICAL_TABLE = 0, 1, 2
+RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL = 0, 1, 2
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+_u64p = C.POINTER(C.c_uint64)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = _build.build()
+        L = C.CDLL(path)
+        d, i, i64, u64, u32, vp = C.c_double, C.c_int, C.c_int64, C.c_uint64, C.c_uint32, C.c_void_p
+        sig = {
+            "go_logpdf_normal": (d, [d, d, d]),
+            "go_logpdf_gamma": (d, [d, d, d]),
+            "go_logpdf_bernoulli": (d, [i, d]),
+            "go_logpdf_categorical": (d, [i64, _dp, i64]),
+            "go_logpdf_mvnormal": (d, [_dp, _dp, _dp, i]),
+            "go_random_normal": (d, [d, d, d]),
+            "go_random_bernoulli": (i, [d, d]),
+            "go_random_categorical": (i64, [_dp, i64, d]),
+            "go_random_gamma_philox": (d, [d, d, u64, u64, u32]),
+            "go_logsumexp": (d, [_dp, i64]),
+            "go_logsumexp2": (d, [d, d]),
+            "go_effective_sample_size": (d, [_dp, i64]),
+            "go_normalize_weights": (d, [_dp, i64, _dp]),
+            "go_philox4x32_10": (None, [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
+            "go_philox_normals": (None, [u64, u32, i64, i64, i, _dp]),
+            "go_philox_uniforms": (None, [u64, u32, i64, i64, i, _dp]),
+            "go_philox_resample_u0": (u32, [u64, u32]),
+            "go_philox_multinomial_u64": (None, [u64, u32, i64, i64, _u64p]),
+            "go_dexp": (d, [d]),
+            "go_quant_bits": (i, [i64]),
+            "go_quantize": (u64, [d, i]),
+            "go_quantized_weights": (u64, [_dp, i64, d, i, _u64p]),
+            "go_resample_systematic": (i, [_dp, i64, u32, _i64p]),
+            "go_resample_multinomial": (i, [_dp, i64, _u64p, _i64p]),
+            "go_resample_residual": (i, [_dp, i64, u32, _i64p]),
+            "go_kalman_logml": (d, [d, d, d, d, d, _dp, i]),
+            "go_hmm_forward": (d, [_dp, _dp, _dp, i, i, _i64p, i]),
+            "go_blr_log_evidence": (d, [_dp, _dp, i, i, d]),
+            "go_model_state_dim": (i, [i, _dp]),
+            "go_model_num_normals": (i, [i, _dp, i, i]),
+            "go_model_num_uniforms": (i, [i, _dp, i, i]),
+            "go_model_num_obs": (i, [i, _dp]),
+            "go_set_threads": (None, [i]),
+            "go_get_max_threads": (i, []),
+            "go_pf_init": (vp, [i, _dp, i, i64, u64, _dp, i, _dp, _dp, _dp]),
+            "go_pf_step": (i, [vp, _dp, i, _dp, _dp, _dp, _dp]),
+            "go_pf_maybe_resample": (i, [vp, d, i, i, u32, _u64p, _dp]),
+            "go_pf_log_ml_estimate": (d, [vp]),
+            "go_pf_log_weights": (_dp, [vp]),
+            "go_pf_parents": (_i64p, [vp]),
+            "go_pf_state": (_dp, [vp, i]),
+            "go_pf_log_ml_est_field": (d, [vp]),
+            "go_pf_num_particles": (i64, [vp]),
+            "go_pf_step_index": (i, [vp]),
+            "go_pf_copy": (vp, [vp]),
+            "go_pf_set_log_weights": (None, [vp, _dp]),
+            "go_pf_free": (None, [vp]),
+            "go_importance_sampling": (d, [i, _dp, i, i64, u64, _dp, i, _dp, _dp, _dp, _dp, C.POINTER(vp)]),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    """float64 C-contiguous array -> (keepalive, pointer); None -> NULL."""
+    if a is None:
+        return None, None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def logsumexp(a):
+    a, p = _d(a)
+    return lib().go_logsumexp(p, a.size)
+
+
+def effective_sample_size(lognormw):
+    a, p = _d(lognormw)
+    return lib().go_effective_sample_size(p, a.size)
+
+
+def normalize_weights(logw):
+    a, p = _d(logw)
+    out = np.empty_like(a)
+    lse = lib().go_normalize_weights(p, a.size, out.ctypes.data_as(_dp))
+    return lse, out
+
+
+def logpdf_categorical(x, probs):
+    a, p = _d(probs)
+    return lib().go_logpdf_categorical(int(x), p, a.size)
+
+
+def logpdf_mvnormal(x, mu, cov):
+    xa, xp = _d(x)
+    ma, mp = _d(mu)
+    ca, cp = _d(cov)
+    return lib().go_logpdf_mvnormal(xp, mp, cp, xa.size)
+
+
+def philox(ctr, key):
+    u32 = C.c_uint32
+    c = (u32 * 4)(*ctr)
+    k = (u32 * 2)(*key)
+    o = (u32 * 4)()
+    lib().go_philox4x32_10(c, k, o)
+    return list(o)
+
+
+def philox_normals(seed, step, pid0, n, ndraw):
+    out = np.empty((ndraw, n), dtype=np.float64)
+    lib().go_philox_normals(seed, step, pid0, n, ndraw, out.ctypes.data_as(_dp))
+    return out
+
+
+def philox_uniforms(seed, step, pid0, n, ndraw):
+    out = np.empty((ndraw, n), dtype=np.float64)
+    lib().go_philox_uniforms(seed, step, pid0, n, ndraw, out.ctypes.data_as(_dp))
+    return out
+
+
+def philox_multinomial_u64(seed, step, k0, n):
+    out = np.empty(n, dtype=np.uint64)
+    lib().go_philox_multinomial_u64(seed, step, k0, n, out.ctypes.data_as(_u64p))
+    return out
+
+
+def quantized_weights(logw, b=None, m=None):
+    a, p = _d(logw)
+    if m is None:
+        m = float(np.max(a))
+    if b is None:
+        b = lib().go_quant_bits(a.size)
+    q = np.empty(a.size, dtype=np.uint64)
+    tot = lib().go_quantized_weights(p, a.size, m, b, q.ctypes.data_as(_u64p))
+    return q, tot
+
+
+def resample(kind, logw, u0=0, u64s=None):
+    """0-based ancestors (int64) by the integer-CDF spec; raises if all weights are -inf."""
+    a, p = _d(logw)
+    anc = np.empty(a.size, dtype=np.int64)
+    ap = anc.ctypes.data_as(_i64p)
+    if kind == RESAMPLE_SYSTEMATIC:
+        rc = lib().go_resample_systematic(p, a.size, u0, ap)
+    elif kind == RESAMPLE_RESIDUAL:
+        rc = lib().go_resample_residual(p, a.size, u0, ap)
+    else:
+        u = np.ascontiguousarray(u64s, dtype=np.uint64)
+        rc = lib().go_resample_multinomial(p, a.size, u.ctypes.data_as(_u64p), ap)
+    if rc != 0:
+        raise ValueError("oracle resample failed rc=%d" % rc)
+    return anc
+
+
+def kalman_logml(m0, s0, a, q, r, y):
+    ya, yp = _d(y)
+    return lib().go_kalman_logml(m0, s0, a, q, r, yp, ya.size)
+
+
+def hmm_forward(prior, emission_MxK, transition_KxK, obs):
+    """emission_MxK[x-1, z-1] = p(x|z); transition_KxK[z-1, prev-1] = p(z|prev) (Gen test layout)."""
+    pr, prp = _d(prior)
+    em, emp = _d(np.asfortranarray(emission_MxK).ravel(order="F"))
+    tr, trp = _d(np.asfortranarray(transition_KxK).ravel(order="F"))
+    o = np.ascontiguousarray(obs, dtype=np.int64)
+    M, K = np.shape(emission_MxK)
+    return lib().go_hmm_forward(prp, emp, trp, K, M, o.ctypes.data_as(_i64p), o.size)
+
+
+def blr_log_evidence(X, y, sigma):
+    Xa, Xp = _d(X)
+    ya, yp = _d(y)
+    n, D = Xa.shape
+    return lib().go_blr_log_evidence(Xp, yp, n, D, sigma)
+
+
+class OraclePF:
+    """Python handle on go_pf_t (mirrors Gen's ParticleFilterState fields)."""
+
+    def __init__(self, ptr, kind, params):
+        self._p = ptr
+        self.kind = kind
+        self.params = np.ascontiguousarray(params, dtype=np.float64)
+        self.S = lib().go_model_state_dim(kind, self.params.ctypes.data_as(_dp))
+
+    @classmethod
+    def init(cls, kind, params, n, obs, seed=0, proposal_kind=0, pargs=None, normals=None, uniforms=None):
+        pa, pp = _d(params)
+        oa, op = _d(obs)
+        ga, gp = _d(pargs)
+        na, np_ = _d(normals)
+        ua, up = _d(uniforms)
+        ptr = lib().go_pf_init(kind, pp, pa.size, n, seed, op, proposal_kind, gp, np_, up)
+        if not ptr:
+            raise ValueError("go_pf_init failed")
+        return cls(ptr, kind, pa)
+
+    def step(self, obs, proposal_kind=0, pargs=None, normals=None, uniforms=None):
+        oa, op = _d(obs)
+        ga, gp = _d(pargs)
+        na, np_ = _d(normals)
+        ua, up = _d(uniforms)
+        incr = np.empty(self.n, dtype=np.float64)
+        rc = lib().go_pf_step(self._p, op, proposal_kind, gp, np_, up, incr.ctypes.data_as(_dp))
+        assert rc == 0
+        return incr
+
+    def maybe_resample(self, ess_threshold=None, kind=RESAMPLE_SYSTEMATIC, u0=None, u64s=None):
+        if ess_threshold is None:
+            ess_threshold = self.n / 2
+        ess = C.c_double()
+        up = None
+        if u64s is not None:
+            u64s = np.ascontiguousarray(u64s, dtype=np.uint64)
+            up = u64s.ctypes.data_as(_u64p)
+        rc = lib().go_pf_maybe_resample(self._p, float(ess_threshold), kind, 0 if u0 is None else 1,
+                                        0 if u0 is None else int(u0), up, C.byref(ess))
+        if rc < 0:
+            raise ValueError("oracle resample failed rc=%d" % rc)
+        self.last_ess = ess.value
+        return bool(rc)
+
+    @property
+    def n(self):
+        return lib().go_pf_num_particles(self._p)
+
+    @property
+    def log_weights(self):
+        return np.ctypeslib.as_array(lib().go_pf_log_weights(self._p), shape=(self.n,)).copy()
+
+    @log_weights.setter
+    def log_weights(self, lw):
+        a, p = _d(lw)
+        assert a.size == self.n
+        lib().go_pf_set_log_weights(self._p, p)
+
+    @property
+    def parents(self):
+        return np.ctypeslib.as_array(lib().go_pf_parents(self._p), shape=(self.n,)).copy()
+
+    @property
+    def log_ml_est(self):
+        return lib().go_pf_log_ml_est_field(self._p)
+
+    def state(self, field):
+        return np.ctypeslib.as_array(lib().go_pf_state(self._p, field), shape=(self.n,)).copy()
+
+    def log_ml_estimate(self):
+        return lib().go_pf_log_ml_estimate(self._p)
+
+    def copy(self):
+        return OraclePF(lib().go_pf_copy(self._p), self.kind, self.params)
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib().go_pf_free(self._p)
+            self._p = None
+
+
+def importance_sampling(kind, params, n, obs, seed=0, proposal_kind=0, pargs=None, normals=None, uniforms=None):
+    pa, pp = _d(params)
+    oa, op = _d(obs)
+    ga, gp = _d(pargs)
+    na, np_ = _d(normals)
+    ua, up = _d(uniforms)
+    out = np.empty(n, dtype=np.float64)
+    ptr = C.c_void_p()
+    lml = lib().go_importance_sampling(kind, pp, pa.size, n, seed, op, proposal_kind, gp, np_, up,
+                                       out.ctypes.data_as(_dp), C.byref(ptr))
+    return OraclePF(ptr.value, kind, pa), out, lml
