@@ -1,0 +1,507 @@
+"""Host-side mirror of Gen.jl's particle-filter / importance-sampling interface over libgenb200.
+
+Julia is not available in this image, so this module plays the role of the `GenB200.jl` glue
+(INTEGRATION.md): the same function names, argument order, return values and error behaviour as
+src/inference/particle_filter.jl and src/inference/importance.jl of the reference, with Julia's
+trailing `!` spelled as a trailing underscore.  Every call goes through the C ABI
+(include/genb200.h); nothing here computes on the host.
+
+    state = initialize_particle_filter(model, (0,), obs0, N)
+    for t in 1..T:
+        maybe_resample_(state, ess_threshold=N/2)
+        particle_filter_step_(state, (t,), (UnknownChange,), obs_t)
+    log_ml_estimate(state)
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+
+UnknownChange = "UnknownChange"
+NoChange = "NoChange"
+
+_RESAMPLERS = {"multinomial": L.RESAMPLE_MULTINOMIAL, "systematic": L.RESAMPLE_SYSTEMATIC,
+               "residual": L.RESAMPLE_RESIDUAL}
+_DTYPES = {"f64": L.F64, "float64": L.F64, "fp64": L.F64, np.float64: L.F64,
+           "f32": L.F32, "float32": L.F32, "fp32": L.F32, np.float32: L.F32}
+
+
+def _darr(a):
+    if a is None:
+        return None, None, 0
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+    return a, a.ctypes.data_as(L.dp), a.size
+
+
+def _flatten_obs(obs):
+    """Observations cross the boundary as a flat Float64 vector in the model's fixed slot order
+    (SURVEY.md section 8b).  Accepts a scalar, a sequence, or a choicemap-like dict (values in
+    insertion order, e.g. {("chain", t, "z"): z_t})."""
+    if isinstance(obs, dict):
+        obs = list(obs.values())
+    return np.atleast_1d(np.asarray(obs, dtype=np.float64)).reshape(-1)
+
+
+class DeviceModel:
+    """A generative function of the supported class (replaces a GenerativeFunction object)."""
+
+    def __init__(self, kind, params, name):
+        self.kind = kind
+        self.name = name
+        self.params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1)
+        h = C.c_void_p()
+        L.check(L.lib().gb_model_create(kind, self.params.ctypes.data_as(L.dp), self.params.size, C.byref(h)))
+        self._h = h
+
+    @property
+    def state_dim(self):
+        return L.lib().gb_model_state_dim(self._h)
+
+    @property
+    def num_obs(self):
+        return L.lib().gb_model_num_obs(self._h)
+
+    def num_normals(self, is_init, proposal_kind=0):
+        return L.lib().gb_model_num_normals(self._h, proposal_kind, int(is_init))
+
+    def num_uniforms(self, is_init, proposal_kind=0):
+        return L.lib().gb_model_num_uniforms(self._h, proposal_kind, int(is_init))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                L.lib().gb_model_free(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+def lgssm_model(m0=0.0, s0=1.0, a=0.9, q=0.5, r=1.0):
+    """x0 ~ normal(m0, s0); x_t ~ normal(a x_{t-1}, q); y_t ~ normal(x_t, r)  via Unfold (cfg 1)."""
+    return DeviceModel(L.MODEL_LGSSM, [m0, s0, a, q, r], "lgssm")
+
+
+def sv_model(mu=-1.0, phi=0.95, sigma=0.25):
+    """h0 ~ normal(mu, sigma/sqrt(1-phi^2)); h_t ~ normal(mu + phi (h-mu), sigma); y ~ normal(0, exp(h/2))."""
+    return DeviceModel(L.MODEL_SV, [mu, phi, sigma, sigma / math.sqrt(1.0 - phi * phi)], "sv")
+
+
+def bearings_model(x0=(0.01, 0.01), y0=(0.95, 0.01), vx0=(0.002, 0.01), vy0=(-0.013, 0.01),
+                   velocity_var=1e-6, measurement_noise=0.005):
+    """The tutorial's bearings-only tracker (docs/src/tutorials/smc.md:607-661)."""
+    return DeviceModel(L.MODEL_BEARINGS, [*x0, *y0, *vx0, *vy0, velocity_var, measurement_noise], "bearings")
+
+
+def hmm_model(prior, transition, emission):
+    """Discrete HMM in the layout of test/inference/particle_filter.jl:52-78:
+    transition[z, prev_z] = p(z | prev_z), emission[x, z] = p(x | z) (columns are distributions)."""
+    prior = np.asarray(prior, dtype=np.float64)
+    tr = np.asarray(transition, dtype=np.float64)
+    em = np.asarray(emission, dtype=np.float64)
+    K, M = prior.size, em.shape[0]
+    assert tr.shape == (K, K) and em.shape == (M, K)
+    p = np.concatenate([[K, M], prior, tr.ravel(order="F"), em.ravel(order="F")])
+    return DeviceModel(L.MODEL_HMM, p, "hmm")
+
+
+def blr_model(X, sigma):
+    """w ~ Map(normal)(0, 1) (D weights); y_j ~ normal(x_j . w, sigma)  (cfg 4)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    n, D = X.shape
+    return DeviceModel(L.MODEL_BLR, np.concatenate([[D, n, sigma], X.ravel()]), "blr")
+
+
+class AffineNormalProposal:
+    """x ~ normal(c0 + c1 * x_prev, std): proposal_args = (c0, c1, std)."""
+    kind = L.PROPOSAL_AFFINE_NORMAL
+
+
+class CategoricalTableProposal:
+    """z ~ categorical(table[:, prev_z]): proposal_args = (table,) with K probs at t=0, K x K after."""
+    kind = L.PROPOSAL_CATEGORICAL_TABLE
+
+
+def _proposal(proposal, proposal_args):
+    if proposal is None:
+        return L.PROPOSAL_DEFAULT, None
+    kind = proposal.kind
+    if kind == L.PROPOSAL_CATEGORICAL_TABLE:
+        tab = np.asarray(proposal_args[0], dtype=np.float64)
+        return kind, tab.ravel(order="F") if tab.ndim == 2 else tab
+    return kind, np.asarray(proposal_args, dtype=np.float64)
+
+
+class DeviceTraces:
+    """Lazy view of the traces of a device particle store: columns are copied to the host on access."""
+
+    def __init__(self, state):
+        self._state = state
+
+    def __len__(self):
+        return self._state.num_particles
+
+    def column(self, field):
+        return self._state.get_state(field)
+
+    def __getitem__(self, i):
+        return tuple(self.column(f)[i] for f in range(self._state.state_dim))
+
+
+class DeviceParticleFilterState:
+    """ParticleFilterState (particle_filter.jl:35-41) held as SoA columns in HBM."""
+
+    def __init__(self, handle, model, dtype):
+        self._h = handle
+        self.model = model
+        self.dtype = dtype
+        self.resampler = "multinomial"
+        self._last_t = None   # the model's time argument (extend-by-one check)
+
+    # -- fields of the reference struct, materialised lazily --
+    @property
+    def num_particles(self):
+        nl, ng = C.c_int64(), C.c_int64()
+        L.check(L.lib().gb_pf_num_particles(self._h, C.byref(nl), C.byref(ng)))
+        return nl.value
+
+    @property
+    def state_dim(self):
+        return self.model.state_dim
+
+    @property
+    def log_weights(self):
+        return get_log_weights(self)
+
+    @log_weights.setter
+    def log_weights(self, lw):
+        a, p, n = _darr(lw)
+        if n != self.num_particles:
+            raise ValueError("log_weights has the wrong length")
+        L.check(L.lib().gb_pf_set_log_weights(self._h, p))
+
+    @property
+    def parents(self):
+        out = np.empty(self.num_particles, dtype=np.int64)
+        L.check(L.lib().gb_pf_get_parents(self._h, out.ctypes.data_as(L.i64p)))
+        return out
+
+    @property
+    def log_ml_est(self):
+        v = C.c_double()
+        L.check(L.lib().gb_pf_get_log_ml_est(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def traces(self):
+        return DeviceTraces(self)
+
+    @property
+    def step_index(self):
+        v = C.c_int()
+        L.check(L.lib().gb_pf_step_index(self._h, C.byref(v)))
+        return v.value
+
+    def get_state(self, field):
+        out = np.empty(self.num_particles, dtype=np.float64)
+        L.check(L.lib().gb_pf_get_state(self._h, field, out.ctypes.data_as(L.dp)))
+        return out
+
+    def ess(self):
+        e, l = C.c_double(), C.c_double()
+        L.check(L.lib().gb_pf_get_ess(self._h, C.byref(e), C.byref(l)))
+        return e.value
+
+    # -- validation mode (pre-drawn noise; Gen has no RNG hook) --
+    def set_noise(self, normals=None, uniforms=None):
+        n = self.num_particles
+        na = None if normals is None else np.ascontiguousarray(normals, dtype=np.float64).reshape(-1, n)
+        ua = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64).reshape(-1, n)
+        L.check(L.lib().gb_pf_set_noise(
+            self._h, None if na is None else na.ctypes.data_as(L.dp), 0 if na is None else na.shape[0],
+            None if ua is None else ua.ctypes.data_as(L.dp), 0 if ua is None else ua.shape[0]))
+
+    def set_resample_noise(self, u0=None, u64s=None):
+        up = None
+        if u64s is not None:
+            u64s = np.ascontiguousarray(u64s, dtype=np.uint64)
+            up = u64s.ctypes.data_as(L.u64p)
+        L.check(L.lib().gb_pf_set_resample_noise(self._h, 0 if u0 is None else 1, 0 if u0 is None else int(u0), up))
+
+    def set_lazy_gather(self, lazy):
+        L.check(L.lib().gb_pf_set_lazy_gather(self._h, int(bool(lazy))))
+
+    def set_stream(self, cuda_stream):
+        L.check(L.lib().gb_pf_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        L.check(L.lib().gb_pf_sync(self._h))
+
+    def enable_timing(self, on=True):
+        L.check(L.lib().gb_pf_enable_timing(self._h, int(on)))
+
+    def get_timing(self):
+        ms = (C.c_double * L.K_COUNT)()
+        ln = (C.c_int64 * L.K_COUNT)()
+        L.check(L.lib().gb_pf_get_timing(self._h, ms, ln))
+        return {L.lib().gb_kernel_name(k).decode(): (ms[k], ln[k]) for k in range(L.K_COUNT)}
+
+    # Base.copy (particle_filter.jl:43-51)
+    def copy(self):
+        h = C.c_void_p()
+        L.check(L.lib().gb_pf_clone(self._h, C.byref(h)))
+        c = DeviceParticleFilterState(h, self.model, self.dtype)
+        c.resampler = self.resampler
+        c._last_t = self._last_t
+        return c
+
+    __copy__ = copy
+
+    # Base.:(==) (particle_filter.jl:52-58)
+    def __eq__(self, other):
+        if not isinstance(other, DeviceParticleFilterState):
+            return NotImplemented
+        if self.num_particles != other.num_particles or self.log_ml_est != other.log_ml_est:
+            return False
+        if not np.array_equal(self.log_weights, other.log_weights) or not np.array_equal(self.parents, other.parents):
+            return False
+        return all(np.array_equal(self.get_state(f), other.get_state(f)) for f in range(self.state_dim))
+
+    __hash__ = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                L.lib().gb_pf_free(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+def initialize_particle_filter(model, model_args, observations, *rest, dtype="f64", seed=0):
+    """initialize_particle_filter(model, model_args, observations[, proposal, proposal_args], num_particles)
+    (particle_filter.jl:118-134, :142-154)."""
+    if len(rest) == 1:
+        proposal, proposal_args, num_particles = None, (), rest[0]
+    elif len(rest) == 3:
+        proposal, proposal_args, num_particles = rest
+    else:
+        raise TypeError("initialize_particle_filter(model, model_args, observations, [proposal, proposal_args,] num_particles)")
+    obs = _flatten_obs(observations)
+    pk, pargs = _proposal(proposal, proposal_args)
+    pa, pp, npa = _darr(pargs)
+    h = C.c_void_p()
+    dt = _DTYPES[dtype]
+    L.check(L.lib().gb_pf_initialize(model._h, int(num_particles), dt, int(seed), obs.ctypes.data_as(L.dp), obs.size,
+                                     pk, pp, npa, C.byref(h)))
+    st = DeviceParticleFilterState(h, model, dt)
+    if len(model_args) >= 1 and isinstance(model_args[0], (int, np.integer)):
+        st._last_t = int(model_args[0])
+    return st
+
+
+def create_particle_filter(model, num_particles, dtype="f64", seed=0, n_global=None, pid_offset=0):
+    """Allocate an empty store (validation mode needs the handle before `generate` to inject noise)."""
+    h = C.c_void_p()
+    dt = _DTYPES[dtype]
+    ng = int(num_particles) if n_global is None else int(n_global)
+    L.check(L.lib().gb_pf_create(model._h, int(num_particles), ng, int(pid_offset), dt, int(seed), C.byref(h)))
+    return DeviceParticleFilterState(h, model, dt)
+
+
+def generate_(state, observations, proposal=None, proposal_args=()):
+    """The t = 0 `generate` sweep of initialize_particle_filter on an allocated store."""
+    obs = _flatten_obs(observations)
+    pk, pargs = _proposal(proposal, proposal_args)
+    pa, pp, npa = _darr(pargs)
+    L.check(L.lib().gb_pf_generate(state._h, obs.ctypes.data_as(L.dp), obs.size, pk, pp, npa))
+    return state
+
+
+def particle_filter_step_(state, new_args, argdiffs, observations, proposal=None, proposal_args=(), return_incr=True):
+    """particle_filter_step!(state, new_args, argdiffs, observations[, proposal, proposal_args])
+    -> (log_incremental_weights,)   (particle_filter.jl:186-208, :217-240).
+    Only extend-by-one is supported: new_args must be (t,) with t = previous t + 1; anything else would
+    produce a non-empty discard, which the reference rejects (:227-229)."""
+    if len(new_args) >= 1 and new_args[0] is not None and state._last_t is not None:
+        if int(new_args[0]) != state._last_t + 1:
+            raise L.GenB200Error(L.ESTATE, "Choices were updated or deleted inside particle filter step "
+                                 "(only extension by one time step is supported)")
+    obs = _flatten_obs(observations)
+    pk, pargs = _proposal(proposal, proposal_args)
+    pa, pp, npa = _darr(pargs)
+    incr = np.empty(state.num_particles, dtype=np.float64) if return_incr else None
+    L.check(L.lib().gb_pf_step(state._h, obs.ctypes.data_as(L.dp), obs.size, pk, pp, npa,
+                               None if incr is None else incr.ctypes.data_as(L.dp)))
+    if len(new_args) >= 1 and new_args[0] is not None:
+        state._last_t = int(new_args[0])
+    return (incr,)
+
+
+def maybe_resample_(state, ess_threshold=None, verbose=False, resampler=None):
+    """maybe_resample!(state; ess_threshold=num_particles/2, verbose=false) -> Bool (particle_filter.jl:249-275).
+    `resampler` in {"multinomial" (reference semantics), "systematic", "residual"}."""
+    n = state.num_particles
+    thr = n / 2 if ess_threshold is None else float(ess_threshold)
+    kind = _RESAMPLERS[resampler or state.resampler]
+    did = C.c_int()
+    if verbose:
+        print("effective sample size: %s, doing resample: %s" % (state.ess(), state.ess() < thr))
+    L.check(L.lib().gb_pf_maybe_resample(state._h, thr, kind, C.byref(did)))
+    return bool(did.value)
+
+
+def log_ml_estimate(state):
+    """particle_filter.jl:91-94."""
+    v = C.c_double()
+    L.check(L.lib().gb_pf_log_ml_estimate(state._h, C.byref(v)))
+    return v.value
+
+
+def get_log_weights(state):
+    """particle_filter.jl:82-84 (unnormalised log weights)."""
+    out = np.empty(state.num_particles, dtype=np.float64)
+    L.check(L.lib().gb_pf_get_log_weights(state._h, out.ctypes.data_as(L.dp)))
+    return out
+
+
+def get_traces(state):
+    """particle_filter.jl:70-73."""
+    return state.traces
+
+
+def importance_sampling(model, model_args, observations, *rest, verbose=False, dtype="f64", seed=0,
+                        normals=None, uniforms=None, return_traces=True):
+    """(traces, log_norm_weights, lml_est) = importance_sampling(model, model_args, observations,
+    [proposal, proposal_args,] num_samples)   (importance.jl:20-59)."""
+    if len(rest) == 1:
+        proposal, proposal_args, n = None, (), rest[0]
+    elif len(rest) == 3:
+        proposal, proposal_args, n = rest
+    else:
+        raise TypeError("importance_sampling(model, model_args, observations, [proposal, proposal_args,] num_samples)")
+    n = int(n)
+    obs = _flatten_obs(observations)
+    pk, pargs = _proposal(proposal, proposal_args)
+    pa, pp, npa = _darr(pargs)
+    na = None if normals is None else np.ascontiguousarray(normals, dtype=np.float64).reshape(-1, n)
+    ua = None if uniforms is None else np.ascontiguousarray(uniforms, dtype=np.float64).reshape(-1, n)
+    lnw = np.empty(n, dtype=np.float64)
+    lml = C.c_double()
+    h = C.c_void_p()
+    dt = _DTYPES[dtype]
+    L.check(L.lib().gb_importance_sampling(
+        model._h, n, dt, int(seed), obs.ctypes.data_as(L.dp), obs.size, pk, pp, npa,
+        None if na is None else na.ctypes.data_as(L.dp), 0 if na is None else na.shape[0],
+        None if ua is None else ua.ctypes.data_as(L.dp), 0 if ua is None else ua.shape[0],
+        lnw.ctypes.data_as(L.dp), C.byref(lml), C.byref(h) if return_traces else None))
+    traces = DeviceParticleFilterState(h, model, dt).traces if return_traces else None
+    return traces, lnw, lml.value
+
+
+# ---- raw-array entries (config 5) and the distribution kernels ----
+def resample(logw, kind="systematic", u0=0, u64s=None, dtype="f64", seed=0, step=0):
+    """0-based ancestors of N log weights by the engine's resampling kernels."""
+    a, p, n = _darr(logw)
+    out = np.empty(n, dtype=np.int64)
+    up = None
+    if u64s is not None:
+        u64s = np.ascontiguousarray(u64s, dtype=np.uint64)
+        up = u64s.ctypes.data_as(L.u64p)
+    L.check(L.lib().gb_resample(p, n, _DTYPES[dtype], _RESAMPLERS[kind], int(u0), up, int(seed), int(step),
+                                out.ctypes.data_as(L.i64p)))
+    return out
+
+
+def logsumexp(arr, dtype="f64"):
+    """inference.jl:3-6 on the device."""
+    a, p, n = _darr(arr)
+    v = C.c_double()
+    L.check(L.lib().gb_logsumexp(p, n, _DTYPES[dtype], C.byref(v), None))
+    return v.value
+
+
+def effective_sample_size_from_logw(arr, dtype="f64"):
+    """particle_filter.jl:3-12 (normalize_weights + effective_sample_size) on the device."""
+    a, p, n = _darr(arr)
+    lse, ess = C.c_double(), C.c_double()
+    L.check(L.lib().gb_logsumexp(p, n, _DTYPES[dtype], C.byref(lse), C.byref(ess)))
+    return ess.value
+
+
+_DISTS = {"normal": L.DIST_NORMAL, "gamma": L.DIST_GAMMA, "bernoulli": L.DIST_BERNOULLI,
+          "categorical": L.DIST_CATEGORICAL, "mvnormal": L.DIST_MVNORMAL}
+
+
+def logpdf(dist, x, a, b=None, dtype="f64"):
+    """Batched logpdf(dist, x, args...) (modeling_library.jl:22).  normal(mu, std), gamma(shape, scale),
+    bernoulli(p), categorical(probs), mvnormal(mu, cov)."""
+    k = _DISTS[dist]
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+    if k == L.DIST_MVNORMAL:
+        ln = a.size
+        n = x.size // ln
+        ast = bst = 0
+    elif k == L.DIST_CATEGORICAL:
+        ln, n, ast, bst = a.size, x.size, 0, 0
+    else:
+        ln, n = 0, x.size
+        ast = 0 if a.size == 1 else 1
+        bst = 0 if (bb is None or bb.size == 1) else 1
+    out = np.empty(n, dtype=np.float64)
+    L.check(L.lib().gb_dist_logpdf(k, _DTYPES[dtype], n, x.ctypes.data_as(L.dp), a.ctypes.data_as(L.dp), ast,
+                                   None if bb is None else bb.ctypes.data_as(L.dp), bst, ln, out.ctypes.data_as(L.dp)))
+    return out
+
+
+def random(dist, n, a, b=None, dtype="f64", seed=0, step=0):
+    """n draws of random(dist, args...) (modeling_library.jl:15) from the engine's Philox stream."""
+    k = _DISTS[dist]
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+    if k in (L.DIST_MVNORMAL, L.DIST_CATEGORICAL):
+        ln, ast, bst = a.size, 0, 0
+    else:
+        ln = 0
+        ast = 0 if a.size == 1 else 1
+        bst = 0 if (bb is None or bb.size == 1) else 1
+    out = np.empty(n * (ln if k == L.DIST_MVNORMAL else 1), dtype=np.float64)
+    L.check(L.lib().gb_dist_random(k, _DTYPES[dtype], n, a.ctypes.data_as(L.dp), ast,
+                                   None if bb is None else bb.ctypes.data_as(L.dp), bst, ln, int(seed), int(step),
+                                   out.ctypes.data_as(L.dp)))
+    return out.reshape(n, ln) if k == L.DIST_MVNORMAL else out
+
+
+def philox_normals(seed, step, pid0, n, ndraw, dtype="f64"):
+    out = np.empty((ndraw, n), dtype=np.float64)
+    L.check(L.lib().gb_philox_normals(int(seed), int(step), int(pid0), int(n), int(ndraw), _DTYPES[dtype],
+                                      out.ctypes.data_as(L.dp)))
+    return out
+
+
+def philox_uniforms(seed, step, pid0, n, ndraw, dtype="f64"):
+    out = np.empty((ndraw, n), dtype=np.float64)
+    L.check(L.lib().gb_philox_uniforms(int(seed), int(step), int(pid0), int(n), int(ndraw), _DTYPES[dtype],
+                                       out.ctypes.data_as(L.dp)))
+    return out
+
+
+def philox_resample_u0(seed, step):
+    return int(L.lib().gb_philox_resample_u0(int(seed), int(step)))
+
+
+def philox_multinomial_u64(seed, step, k0, n):
+    out = np.empty(n, dtype=np.uint64)
+    L.check(L.lib().gb_philox_multinomial_u64(int(seed), int(step), int(k0), int(n), out.ctypes.data_as(L.u64p)))
+    return out
+
+
+def device_count():
+    c = C.c_int()
+    L.check(L.lib().gb_device_count(C.byref(c)))
+    return c.value

@@ -1,0 +1,302 @@
+// common.cuh -- shared device/host helpers of libgenb200 (sm_100a).
+//
+// Compiled with -fmad=false: Julia never contracts `mu + std * randn()` (normal.jl:128), so every
+// a*b+c written in this tree stays two roundings; where a fused multiply-add is wanted it is written
+// as fma() explicitly.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+
+#define GB_HD __host__ __device__ __forceinline__
+#define GB_D __device__ __forceinline__
+
+namespace gb {
+
+constexpr int kBlock = 256;          // threads per CTA for every streaming kernel
+constexpr int kTile = 2048;          // particles per scan tile (kBlock * kItems)
+constexpr int kItems = kTile / kBlock;
+constexpr int kChunk = 4 * kTile;    // output slots one ancestors CTA fills before overflow CTAs take over
+constexpr double kLog2Pi = 1.8378770664093454835606594728112;  // log(2*pi)
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10.  Counter = (pid_lo, pid_hi, step, kind<<24 | idx), key = seed: a draw is a pure
+// function of (seed, step, global particle id, draw index) and so independent of sharding and of the
+// launch geometry.  Same integer spec as the oracle (oracle/gen_oracle.c go_philox4x32_10).
+// ------------------------------------------------------------------------------------------
+enum { PK_NORMAL = 1, PK_UNIFORM = 2, PK_RESAMPLE = 3, PK_MULTI = 4, PK_GAMMA = 5 };
+
+struct U4 { uint32_t x, y, z, w; };
+
+GB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+GB_HD U4 philox4x32_10(U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    U4 n;
+    n.x = hi1 ^ c.y ^ k0;
+    n.y = lo1;
+    n.z = hi0 ^ c.w ^ k1;
+    n.w = lo0;
+    c = n;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+GB_HD U4 philox_block(uint64_t seed, uint64_t pid, uint32_t step, uint32_t kind, uint32_t idx) {
+  U4 c = {(uint32_t)pid, (uint32_t)(pid >> 32), step, (kind << 24) | (idx & 0xFFFFFFu)};
+  return philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// 52-bit uniform strictly inside (0,1); exact in fp64
+GB_HD double u52(uint32_t hi, uint32_t lo) {
+  uint64_t v = (((uint64_t)hi << 32) | lo) >> 12;
+  return ((double)v + 0.5) * 0x1p-52;
+}
+// 24-bit uniform strictly inside (0,1); exact in fp32
+GB_HD float u24(uint32_t w) { return ((float)(w >> 8) + 0.5f) * 0x1p-24f; }
+
+// fp64 noise: one Philox block -> one Box-Muller pair (oracle: philox_normal_pair)
+GB_D void philox_normal_pair(uint64_t seed, uint64_t pid, uint32_t step, uint32_t pair, double &n0, double &n1) {
+  U4 w = philox_block(seed, pid, step, PK_NORMAL, pair);
+  double u1 = u52(w.x, w.y), u2 = u52(w.z, w.w);
+  double r = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+// fp32 noise: the same block and the same 52-bit uniforms, transformed in single precision
+GB_D void philox_normal_pair(uint64_t seed, uint64_t pid, uint32_t step, uint32_t pair, float &n0, float &n1) {
+  U4 w = philox_block(seed, pid, step, PK_NORMAL, pair);
+  float u1 = u24(w.x), u2 = u24(w.z);
+  float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+GB_D void philox_uniform_pair(uint64_t seed, uint64_t pid, uint32_t step, uint32_t pair, double &a, double &b) {
+  U4 w = philox_block(seed, pid, step, PK_UNIFORM, pair);
+  a = u52(w.x, w.y);
+  b = u52(w.z, w.w);
+}
+GB_D void philox_uniform_pair(uint64_t seed, uint64_t pid, uint32_t step, uint32_t pair, float &a, float &b) {
+  double x, y;
+  philox_uniform_pair(seed, pid, step, pair, x, y);
+  a = (float)x;
+  b = (float)y;
+  // (float)u52 can round up to 1.0f; keep the draw inside [0,1)
+  a = a >= 1.0f ? 0x1.fffffep-1f : a;
+  b = b >= 1.0f ? 0x1.fffffep-1f : b;
+}
+
+// ------------------------------------------------------------------------------------------
+// Integer-CDF weight quantisation (oracle go_dexp/go_quantize).  Only rint,
+// fma, * and exact power-of-two scaling are used, so host gcc and device produce identical bits.
+// ------------------------------------------------------------------------------------------
+GB_HD double dmul(double a, double b) {
+#ifdef __CUDA_ARCH__
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+GB_HD double dexp_parts(double x, int &kout) {
+  double kd = rint(dmul(x, 1.4426950408889634074));
+  double r = fma(kd, -6.93147180369123816490e-01, x);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = 1.0 / 6227020800.0;
+  p = fma(p, r, 1.0 / 479001600.0);
+  p = fma(p, r, 1.0 / 39916800.0);
+  p = fma(p, r, 1.0 / 3628800.0);
+  p = fma(p, r, 1.0 / 362880.0);
+  p = fma(p, r, 1.0 / 40320.0);
+  p = fma(p, r, 1.0 / 5040.0);
+  p = fma(p, r, 1.0 / 720.0);
+  p = fma(p, r, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  kout = (int)kd;
+  return p;
+}
+GB_HD double pow2i(int e) {
+  uint64_t bits = (uint64_t)(e + 1023) << 52;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)bits);
+#else
+  double d;
+  memcpy(&d, &bits, 8);
+  return d;
+#endif
+}
+// floor(exp(x) * 2^b) for x = lw - max <= 0; NaN / -Inf / tiny -> 0
+GB_HD uint64_t quantize(double x, int b) {
+  if (!(x > -708.0)) return 0;
+  if (x > 0.0) x = 0.0;
+  int k;
+  double p = dexp_parts(x, k);
+  int e = k + b;
+  if (e < 0) return 0;
+  return (uint64_t)dmul(p, pow2i(e));
+}
+inline __host__ int quant_bits(int64_t n) {
+  int lg = 0;
+  while (((int64_t)1 << lg) < n) lg++;
+  int b = 62 - lg;
+  return b > 52 ? 52 : b;
+}
+
+// ------------------------------------------------------------------------------------------
+// 128 / 64 -> 64 bit floor division via a double reciprocal and exact integer correction.
+// Requires d >= 1 and floor(a / d) < 2^63.
+// ------------------------------------------------------------------------------------------
+GB_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((u128)a * b) >> 64);
+#endif
+}
+GB_HD double u128_to_double(uint64_t hi, uint64_t lo) {
+  // round-to-nearest of each half is enough: the estimate is corrected exactly below
+  return (double)hi * 18446744073709551616.0 + (double)lo;
+}
+GB_HD uint64_t div128_64(uint64_t ahi, uint64_t alo, uint64_t d, double dinv) {
+  // first estimate: relative error ~2^-50, i.e. up to ~2^13 units when the quotient is ~2^63
+  double qd = u128_to_double(ahi, alo) * dinv;
+  uint64_t q = qd >= 9223372036854775807.0 ? 0x7FFFFFFFFFFFFFFFull : (uint64_t)qd;
+  // remainder r = a - q*d as a signed 128-bit number (|r| < 2^14 * d < 2^77)
+  uint64_t plo = q * d, phi = mulhi64(q, d);
+  uint64_t rlo = alo - plo;
+  int64_t rhi = (int64_t)(ahi - phi - (alo < plo ? 1 : 0));
+  // second estimate on the (small) remainder
+  double rd = (double)rhi * 18446744073709551616.0 + (double)rlo;
+  int64_t dq = (int64_t)(rd * dinv);
+  q += (uint64_t)dq;
+  // r -= dq * d  (dq*d fits in signed 128)
+  {
+    uint64_t m = dq < 0 ? (uint64_t)(-dq) : (uint64_t)dq;
+    uint64_t mlo = m * d, mhi = mulhi64(m, d);
+    if (dq >= 0) {
+      uint64_t nlo = rlo - mlo;
+      rhi = rhi - (int64_t)mhi - (rlo < mlo ? 1 : 0);
+      rlo = nlo;
+    } else {
+      uint64_t nlo = rlo + mlo;
+      rhi = rhi + (int64_t)mhi + (nlo < rlo ? 1 : 0);
+      rlo = nlo;
+    }
+  }
+  // final exact fix-up (a couple of iterations at most)
+  while (rhi < 0) {
+    uint64_t nlo = rlo + d;
+    rhi += (nlo < rlo ? 1 : 0);
+    rlo = nlo;
+    q--;
+  }
+  while (rhi > 0 || rlo >= d) {
+    uint64_t nlo = rlo - d;
+    rhi -= (rlo < d ? 1 : 0);
+    rlo = nlo;
+    q++;
+  }
+  return q;
+}
+
+// Parameters of one systematic sweep over an integer CDF.
+//   regular  (Appendix B "systematic"): tau_k = floor((k*2^32 + u0) * Q / (nslots * 2^32))
+//   residual (Appendix B "residual")  : tau_k = floor((k*2^32 + u0) * Q / 2^32)   (CDF of N*q - c*Q)
+struct SweepParams {
+  uint64_t q_total;   // Q_N
+  double q_inv;       // 1.0 / (double)Q_N
+  uint64_t dscale;    // nslots << 32 (regular) ; unused for residual
+  uint32_t u0;
+};
+// number of slots k with tau_k < C  (regular sweep; C <= Q_N < 2^62, dscale < 2^63)
+GB_HD int64_t slots_below(uint64_t C, const SweepParams &sp) {
+  if (C == 0) return 0;
+  // A = C * dscale - 1
+  uint64_t alo = C * sp.dscale, ahi = mulhi64(C, sp.dscale);
+  ahi -= (alo == 0 ? 1 : 0);
+  alo -= 1;
+  uint64_t X = div128_64(ahi, alo, sp.q_total, sp.q_inv);
+  if (X < sp.u0) return 0;
+  return (int64_t)((X - sp.u0) >> 32) + 1;
+}
+// residual sweep: C is a 128-bit CDF value (< 2^92): A = (C << 32) - 1
+GB_HD int64_t slots_below_residual(uint64_t chi, uint64_t clo, const SweepParams &sp) {
+  if ((chi | clo) == 0) return 0;
+  uint64_t ahi = (chi << 32) | (clo >> 32), alo = clo << 32;
+  ahi -= (alo == 0 ? 1 : 0);
+  alo -= 1;
+  uint64_t X = div128_64(ahi, alo, sp.q_total, sp.q_inv);
+  if (X < sp.u0) return 0;
+  return (int64_t)((X - sp.u0) >> 32) + 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// online log-sum-exp triple (m, s1 = sum exp(lw-m), s2 = sum exp(2(lw-m)))
+// (inference.jl:3-6 and particle_filter.jl:3-12 in one pass: lse = m + log s1, ess = s1^2 / s2)
+// ------------------------------------------------------------------------------------------
+struct Lse3 { double m, s1, s2; };
+GB_HD Lse3 lse3_empty() { return Lse3{-INFINITY, 0.0, 0.0}; }
+GB_D void lse3_push(Lse3 &a, double lw) {
+  if (lw == -INFINITY || lw != lw) {
+    if (lw != lw) { a.m = lw; }  // NaN poisons the max exactly like Julia's maximum()
+    return;
+  }
+  double d = lw - a.m;
+  double e = exp(-fabs(d));   // a.m == -inf: d = +inf, e = 0
+  double e2 = e * e;
+  if (d > 0.0) {
+    a.s1 = a.s1 * e + 1.0;
+    a.s2 = a.s2 * e2 + 1.0;
+    a.m = lw;
+  } else {
+    a.s1 += e;
+    a.s2 += e2;
+  }
+}
+GB_D Lse3 lse3_merge(const Lse3 &a, const Lse3 &b) {
+  if (a.m != a.m) return a;
+  if (b.m != b.m) return b;
+  if (b.m == -INFINITY) return a;
+  if (a.m == -INFINITY) return b;
+  double m = fmax(a.m, b.m);
+  double ea = exp(a.m - m), eb = exp(b.m - m);
+  return Lse3{m, a.s1 * ea + b.s1 * eb, a.s2 * ea * ea + b.s2 * eb * eb};
+}
+GB_D Lse3 lse3_warp_reduce(Lse3 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Lse3 w;
+    w.m = __shfl_xor_sync(0xffffffffu, v.m, o);
+    w.s1 = __shfl_xor_sync(0xffffffffu, v.s1, o);
+    w.s2 = __shfl_xor_sync(0xffffffffu, v.s2, o);
+    v = lse3_merge(v, w);
+  }
+  return v;
+}
+
+// streaming (read-once / write-once) global accesses: keep the 126 MB L2 for data that is re-read
+template <typename T> GB_D T ld_stream(const T *p) { return __ldcs(p); }
+template <typename T> GB_D void st_stream(T *p, T v) { __stcs(p, v); }
+
+}  // namespace gb

@@ -1,0 +1,105 @@
+// dist.cuh -- device logpdf / random of Gen's built-in distributions on the hot path
+// (src/modeling_library/distributions/{normal,gamma,bernoulli,categorical,mvnormal}.jl).
+// Templated on the arithmetic type R (double = reference precision, float = fp32 mode).
+#pragma once
+#include "common.cuh"
+
+namespace gb {
+
+template <typename R> struct Math;
+template <> struct Math<double> {
+  static GB_D double log_(double x) { return log(x); }
+  static GB_D double exp_(double x) { return exp(x); }
+  static GB_D double sqrt_(double x) { return sqrt(x); }
+  static GB_D double atan2_(double y, double x) { return atan2(y, x); }
+  static GB_D double lgamma_(double x) { return lgamma(x); }
+  static GB_D double pow_(double x, double y) { return pow(x, y); }
+  static GB_D double neg_inf() { return -INFINITY; }
+  static GB_D double log2pi() { return kLog2Pi; }
+};
+template <> struct Math<float> {
+  static GB_D float log_(float x) { return logf(x); }
+  static GB_D float exp_(float x) { return expf(x); }
+  static GB_D float sqrt_(float x) { return sqrtf(x); }
+  static GB_D float atan2_(float y, float x) { return atan2f(y, x); }
+  static GB_D float lgamma_(float x) { return lgammaf(x); }
+  static GB_D float pow_(float x, float y) { return powf(x, y); }
+  static GB_D float neg_inf() { return -INFINITY; }
+  static GB_D float log2pi() { return (float)kLog2Pi; }
+};
+
+// normal.jl:56-59:  z = (x - mu) / std;  -(abs2(z) + log(2pi))/2 - log(std)
+template <typename R> GB_D R logpdf_normal(R x, R mu, R std) {
+  R z = (x - mu) / std;
+  return -(z * z + Math<R>::log2pi()) / R(2) - Math<R>::log_(std);
+}
+// same with log(std) hoisted by the caller (std is a per-step constant on the hot path)
+template <typename R> GB_D R logpdf_normal_ls(R x, R mu, R std, R log_std) {
+  R z = (x - mu) / std;
+  return -(z * z + Math<R>::log2pi()) / R(2) - log_std;
+}
+// normal.jl:128:  mu + std * randn()   (two roundings: -fmad=false)
+template <typename R> GB_D R random_normal(R mu, R std, R eps) { return mu + std * eps; }
+
+// gamma.jl:10-16
+template <typename R> GB_D R logpdf_gamma(R x, R shape, R scale) {
+  if (x > R(0))
+    return (shape - R(1)) * Math<R>::log_(x) - (x / scale) - shape * Math<R>::log_(scale) - Math<R>::lgamma_(shape);
+  return Math<R>::neg_inf();
+}
+// bernoulli.jl:10-12 / :19
+template <typename R> GB_D R logpdf_bernoulli(bool x, R p) { return x ? Math<R>::log_(p) : Math<R>::log_(R(1) - p); }
+template <typename R> GB_D bool random_bernoulli(R p, R u) { return u < p; }
+// categorical.jl:10-12 (x is 1-based); probs are always fp64 tables
+template <typename R> GB_D R logpdf_categorical(long long x, const double *__restrict__ probs, int len) {
+  return (x > 0 && x <= len) ? Math<R>::log_((R)__ldg(probs + (x - 1))) : Math<R>::neg_inf();
+}
+// categorical.jl:20-22: single draw = inverse-CDF linear scan (oracle go_random_categorical)
+template <typename R> GB_D long long random_categorical(const double *__restrict__ probs, int len, R u) {
+  double c = 0.0;
+  for (int i = 0; i < len; i++) {
+    c += __ldg(probs + i);
+    if ((double)u < c) return i + 1;
+  }
+  return len;
+}
+// gamma.jl:29-31 -> Marsaglia-Tsang on the engine's Philox stream (oracle go_random_gamma_philox)
+template <typename R> GB_D R random_gamma_philox(R shape, R scale, uint64_t seed, uint64_t pid, uint32_t step) {
+  double sh = (double)shape;
+  double a = sh < 1.0 ? sh + 1.0 : sh;
+  double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d), g = d;
+  for (uint32_t i = 0; i < 64; i++) {
+    U4 w = philox_block(seed, pid, step, PK_GAMMA, 2 * i);
+    U4 w2 = philox_block(seed, pid, step, PK_GAMMA, 2 * i + 1);
+    double u1 = u52(w.x, w.y), u2 = u52(w.z, w.w);
+    double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    double u = u52(w2.x, w2.y);
+    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) { g = d * v; break; }
+  }
+  if (sh < 1.0) {
+    U4 w = philox_block(seed, pid, step, PK_GAMMA, 0xFFFFFFu);
+    g *= pow(u52(w.z, w.w), 1.0 / sh);
+  }
+  return (R)(g * (double)scale);
+}
+
+// mvnormal.jl:12-16: the covariance is shared by all particles, so it is factored ONCE (host, in
+// fp64) instead of once per call as the reference does; the kernel consumes L (row-major lower
+// Cholesky factor, k*k doubles) and logdet:  -(k log 2pi + logdet + |L^-1 (x-mu)|^2) / 2
+template <typename R, int KMAX>
+GB_D R logpdf_mvnormal_chol(const R *x, const double *__restrict__ mu, const double *__restrict__ L, double logdet, int k) {
+  R z[KMAX];
+  R quad = R(0);
+  for (int i = 0; i < k; i++) {
+    R s = x[i] - (R)__ldg(mu + i);
+    for (int p = 0; p < i; p++) s -= (R)__ldg(L + i * k + p) * z[p];
+    z[i] = s / (R)__ldg(L + i * k + i);
+    quad += z[i] * z[i];
+  }
+  return -(R(k) * Math<R>::log2pi() + (R)logdet + quad) / R(2);
+}
+
+}  // namespace gb

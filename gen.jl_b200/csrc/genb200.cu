@@ -1,0 +1,1351 @@
+// genb200.cu -- C ABI (include/genb200.h) over the sm_100a kernels: the device-resident
+// structure-of-arrays ParticleFilterState (particle_filter.jl:35-41) and Gen's particle-filter /
+// importance-sampling entry points for the supported model class.
+//
+// There is no CPU fallback anywhere in this file: every compute entry needs a CUDA device and
+// fails with GB_ENOGPU otherwise.
+#include "../../include/genb200.h"
+#include "kernels_resample.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace gb;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? GB_ENOGPU : GB_ECUDA, \
+                  std::string(#call) + ": " + cudaGetErrorString(e__));                            \
+  } while (0)
+#define REQ(cond, msg)                          \
+  do {                                          \
+    if (!(cond)) return fail(GB_EINVAL, msg);   \
+  } while (0)
+
+extern "C" const char *gb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *gb_version(void) { return "genb200 0.1 (sm_100a)"; }
+
+static int require_gpu() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(GB_ENOGPU, "no CUDA device: libgenb200 has no CPU fallback");
+  }
+  return GB_OK;
+}
+extern "C" int gb_device_count(int *count) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  *count = n;
+  return GB_OK;
+}
+extern "C" int gb_set_device(int device) {
+  int rc = require_gpu();
+  if (rc) return rc;
+  CK(cudaSetDevice(device));
+  return GB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// models
+// ------------------------------------------------------------------------------------------
+struct gb_model {
+  int kind = 0;
+  std::vector<double> params;
+  int S = 0, nobs = 1, K = 0, M = 0, D = 0;
+};
+
+static int model_state_dim(int kind, const double *p) {
+  switch (kind) {
+    case MODEL_LGSSM: case MODEL_SV: case MODEL_HMM: return 1;
+    case MODEL_BEARINGS: return 4;
+    case MODEL_BLR: return (int)p[0];
+  }
+  return -1;
+}
+static int model_num_normals(int kind, const double *p, int is_init) {
+  switch (kind) {
+    case MODEL_LGSSM: case MODEL_SV: return 1;
+    case MODEL_BEARINGS: return is_init ? 4 : 2;
+    case MODEL_HMM: return 0;
+    case MODEL_BLR: return is_init ? (int)p[0] : 0;
+  }
+  return 0;
+}
+static int model_num_uniforms(int kind) { return kind == MODEL_HMM ? 1 : 0; }
+
+extern "C" int gb_model_create(int kind, const double *params, int nparams, gb_model_t **out) {
+  REQ(out && params && nparams > 0, "gb_model_create: null argument");
+  int need = 0;
+  switch (kind) {
+    case MODEL_LGSSM: need = 5; break;
+    case MODEL_SV: need = 4; break;
+    case MODEL_BEARINGS: need = 10; break;
+    case MODEL_HMM: {
+      REQ(nparams >= 2, "HMM params: [K, M, prior, transition, emission]");
+      int K = (int)params[0], M = (int)params[1];
+      REQ(K >= 1 && K <= 1024 && M >= 1 && M <= 1024, "HMM: K, M must be in 1..1024");
+      need = 2 + K + K * K + M * K;
+      break;
+    }
+    case MODEL_BLR: {
+      REQ(nparams >= 3, "BLR params: [D, n, sigma, X]");
+      int D = (int)params[0], n = (int)params[1];
+      if (!(D >= 1 && D <= kBlrMax && n >= 1 && n <= kBlrMax))
+        return fail(GB_EUNSUPPORTED, "BLR: D and n must be in 1..64");
+      need = 3 + n * D;
+      break;
+    }
+    default:
+      return fail(GB_EUNSUPPORTED, "gb_model_create: model kind outside the supported class");
+  }
+  REQ(nparams == need, "gb_model_create: wrong number of parameters for this model kind");
+  gb_model *m = new gb_model;
+  m->kind = kind;
+  m->params.assign(params, params + nparams);
+  m->S = model_state_dim(kind, params);
+  if (kind == MODEL_HMM) { m->K = (int)params[0]; m->M = (int)params[1]; }
+  if (kind == MODEL_BLR) { m->D = (int)params[0]; m->nobs = (int)params[1]; }
+  *out = m;
+  return GB_OK;
+}
+extern "C" void gb_model_free(gb_model_t *m) { delete m; }
+extern "C" int gb_model_state_dim(const gb_model_t *m) { return m ? m->S : -1; }
+extern "C" int gb_model_num_obs(const gb_model_t *m) { return m ? m->nobs : -1; }
+extern "C" int gb_model_num_normals(const gb_model_t *m, int, int is_init) {
+  return m ? model_num_normals(m->kind, m->params.data(), is_init) : -1;
+}
+extern "C" int gb_model_num_uniforms(const gb_model_t *m, int, int) { return m ? model_num_uniforms(m->kind) : -1; }
+
+// ------------------------------------------------------------------------------------------
+// particle store
+// ------------------------------------------------------------------------------------------
+enum WState { W_STATS = 0, W_ZERO = 1, W_DIRTY = 2 };
+
+struct TimedLaunch { int k; cudaEvent_t a, b; };
+
+struct gb_pf {
+  gb_model model;
+  int dtype = GB_F64;
+  size_t esz = 8;
+  long long n = 0, n_global = 0, pid_offset = 0, ld = 0;
+  uint64_t seed = 0;
+  int step = 0;
+  int S = 0;
+  void *state[2] = {nullptr, nullptr};
+  int cur = 0;
+  void *logw = nullptr, *incr = nullptr;
+  int *anc = nullptr;             // local ancestors of the last resample (n entries, padded)
+  bool anc_valid = false;
+  bool pending_gather = false;    // resample decided, rows not moved yet (lazy gather)
+  bool lazy = true;
+  long long *parents64 = nullptr; // global 1-based parents (sharded path)
+  bool parents64_valid = false;
+  double log_ml_est = 0.0;
+  int wstate = W_DIRTY;
+  Lse3 *partials = nullptr;
+  unsigned int *ticket = nullptr;
+  WeightStats *d_stats = nullptr, *h_stats = nullptr;
+  // validation noise
+  double *d_normals = nullptr, *d_uniforms = nullptr;
+  int nn_set = 0, nu_set = 0, nn_cap = 0, nu_cap = 0;
+  bool use_u0 = false;
+  uint32_t u0 = 0;
+  uint64_t *d_u64 = nullptr;
+  bool u64_set = false;
+  // resampling workspace
+  long long ntiles = 0;
+  uint64_t *tile_q = nullptr, *tile_c = nullptr;
+  U128 *tile_r = nullptr;
+  long long *tile_slot = nullptr;
+  ResamplePlan *d_plan = nullptr, *h_plan = nullptr;
+  uint64_t *cdf = nullptr;
+  int *off_anc = nullptr;         // sharded: ancestors of the shard's offspring range
+  long long off_cap = 0, off_lo = 0, off_hi = 0;
+  double *d_tab = nullptr, *d_ptab = nullptr;
+  int ptab_cap = 0;
+  cudaStream_t stream = 0;
+  int num_sms = 148;
+  // instrumentation
+  bool timing = false;
+  std::vector<TimedLaunch> pending;
+  std::vector<cudaEvent_t> pool;
+  double ms[GB_K_COUNT] = {0};
+  long long launches[GB_K_COUNT] = {0};
+};
+
+static const char *kKernelNames[GB_K_COUNT] = {"step(propose+weight+lse)", "lse_finalize", "qtotal", "tilescan",
+                                               "ancestors", "gather", "misc"};
+extern "C" const char *gb_kernel_name(int k) { return (k >= 0 && k < GB_K_COUNT) ? kKernelNames[k] : "?"; }
+
+static cudaEvent_t get_event(gb_pf *pf) {
+  if (!pf->pool.empty()) { cudaEvent_t e = pf->pool.back(); pf->pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+struct LaunchScope {
+  gb_pf *pf; int k; cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(gb_pf *p, int kid) : pf(p), k(kid) {
+    pf->launches[k]++;
+    if (pf->timing) { a = get_event(pf); b = get_event(pf); cudaEventRecord(a, pf->stream); }
+  }
+  ~LaunchScope() {
+    if (pf->timing) { cudaEventRecord(b, pf->stream); pf->pending.push_back({k, a, b}); }
+  }
+};
+#define LAUNCH(pf, kid, ...)      \
+  do {                            \
+    LaunchScope ls__(pf, kid);    \
+    __VA_ARGS__;                  \
+  } while (0)
+
+static std::unordered_map<const void *, int> g_occ;
+template <typename F> static int grid_for(gb_pf *pf, F kernel, long long work_items, int block) {
+  const void *key = (const void *)kernel;
+  auto it = g_occ.find(key);
+  int occ;
+  if (it == g_occ.end()) {
+    occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) occ = 1;
+    g_occ[key] = occ;
+  } else occ = it->second;
+  long long blocks = (work_items + block - 1) / block;
+  long long cap = (long long)pf->num_sms * occ;
+  if (blocks < 1) blocks = 1;
+  return (int)std::min(blocks, cap);
+}
+
+static void pf_release(gb_pf *pf) {
+  if (!pf) return;
+  cudaFree(pf->state[0]); cudaFree(pf->state[1]); cudaFree(pf->logw); cudaFree(pf->incr); cudaFree(pf->anc);
+  cudaFree(pf->parents64); cudaFree(pf->partials); cudaFree(pf->ticket); cudaFree(pf->d_stats);
+  cudaFreeHost(pf->h_stats); cudaFree(pf->d_normals); cudaFree(pf->d_uniforms); cudaFree(pf->d_u64);
+  cudaFree(pf->tile_q); cudaFree(pf->tile_c); cudaFree(pf->tile_r); cudaFree(pf->tile_slot); cudaFree(pf->d_plan);
+  cudaFreeHost(pf->h_plan); cudaFree(pf->cdf); cudaFree(pf->off_anc); cudaFree(pf->d_tab); cudaFree(pf->d_ptab);
+  for (auto &t : pf->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (auto e : pf->pool) cudaEventDestroy(e);
+  delete pf;
+}
+extern "C" void gb_pf_free(gb_pf_t *pf) { pf_release(pf); }
+
+static const int kMaxPartials = 148 * 16 + 64;
+
+extern "C" int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_global, int64_t pid_offset, int dtype,
+                            uint64_t seed, gb_pf_t **out) {
+  REQ(m && out, "gb_pf_create: null argument");
+  REQ(n_local >= 1 && n_global >= n_local && pid_offset >= 0 && pid_offset + n_local <= n_global,
+      "gb_pf_create: bad particle counts");
+  REQ(n_global < ((int64_t)1 << 31), "gb_pf_create: at most 2^31-1 particles");
+  REQ(dtype == GB_F64 || dtype == GB_F32, "gb_pf_create: dtype must be GB_F64 or GB_F32");
+  int rc = require_gpu();
+  if (rc) return rc;
+  gb_pf *pf = new gb_pf;
+  pf->model = *m;
+  pf->dtype = dtype;
+  pf->esz = dtype == GB_F64 ? 8 : 4;
+  pf->n = n_local; pf->n_global = n_global; pf->pid_offset = pid_offset;
+  pf->ld = ((n_local + kTile - 1) / kTile) * kTile;
+  pf->seed = seed;
+  pf->S = m->S;
+  pf->ntiles = pf->ld / kTile;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&pf->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  auto A = [&](void **p, size_t bytes, bool zero) -> cudaError_t {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess && zero) e = cudaMemset(*p, 0, bytes);
+    return e;
+  };
+  cudaError_t e = cudaSuccess;
+  size_t col = (size_t)pf->ld * pf->esz;
+  if (e == cudaSuccess) e = A(&pf->state[0], col * pf->S, true);
+  if (e == cudaSuccess) e = A(&pf->state[1], col * pf->S, true);
+  if (e == cudaSuccess) e = A(&pf->logw, col, true);
+  if (e == cudaSuccess) e = A(&pf->incr, col, true);
+  if (e == cudaSuccess) e = A((void **)&pf->anc, (size_t)pf->ld * 4, true);
+  if (e == cudaSuccess) e = A((void **)&pf->partials, sizeof(Lse3) * kMaxPartials, true);
+  if (e == cudaSuccess) e = A((void **)&pf->ticket, 64, true);
+  if (e == cudaSuccess) e = A((void **)&pf->d_stats, sizeof(WeightStats), true);
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&pf->h_stats, sizeof(WeightStats));
+  if (e == cudaSuccess) e = A((void **)&pf->tile_q, (size_t)(pf->ntiles + 1) * 8, true);
+  if (e == cudaSuccess) e = A((void **)&pf->tile_slot, (size_t)(pf->ntiles + 1) * 8, true);
+  if (e == cudaSuccess) e = A((void **)&pf->d_plan, sizeof(ResamplePlan), true);
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&pf->h_plan, sizeof(ResamplePlan));
+  if (e == cudaSuccess && m->kind == MODEL_HMM) {
+    size_t nt = m->params.size() - 2;
+    e = A((void **)&pf->d_tab, nt * 8, false);
+    if (e == cudaSuccess) e = cudaMemcpy(pf->d_tab, m->params.data() + 2, nt * 8, cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {
+    std::string msg = std::string("gb_pf_create: ") + cudaGetErrorString(e);
+    pf_release(pf);
+    cudaGetLastError();
+    return fail(GB_ECUDA, msg);
+  }
+  *out = pf;
+  return GB_OK;
+}
+
+extern "C" int gb_pf_set_stream(gb_pf_t *pf, void *s) { REQ(pf, "null handle"); pf->stream = (cudaStream_t)s; return GB_OK; }
+extern "C" int gb_pf_sync(gb_pf_t *pf) { REQ(pf, "null handle"); CK(cudaStreamSynchronize(pf->stream)); return GB_OK; }
+extern "C" int gb_pf_set_lazy_gather(gb_pf_t *pf, int lazy) { REQ(pf, "null handle"); pf->lazy = lazy != 0; return GB_OK; }
+extern "C" int gb_pf_num_particles(const gb_pf_t *pf, int64_t *nl, int64_t *ng) {
+  REQ(pf, "null handle");
+  if (nl) *nl = pf->n;
+  if (ng) *ng = pf->n_global;
+  return GB_OK;
+}
+extern "C" int gb_pf_step_index(const gb_pf_t *pf, int *step) { REQ(pf && step, "null argument"); *step = pf->step; return GB_OK; }
+
+extern "C" int gb_pf_enable_timing(gb_pf_t *pf, int on) { REQ(pf, "null handle"); pf->timing = on != 0; return GB_OK; }
+extern "C" int gb_pf_get_timing(gb_pf_t *pf, double *ms, int64_t *launches) {
+  REQ(pf, "null handle");
+  CK(cudaStreamSynchronize(pf->stream));
+  for (auto &t : pf->pending) {
+    float f = 0.f;
+    cudaEventElapsedTime(&f, t.a, t.b);
+    pf->ms[t.k] += f;
+    pf->pool.push_back(t.a);
+    pf->pool.push_back(t.b);
+  }
+  pf->pending.clear();
+  for (int k = 0; k < GB_K_COUNT; k++) {
+    if (ms) ms[k] = pf->ms[k];
+    if (launches) launches[k] = pf->launches[k];
+    pf->ms[k] = 0;
+    pf->launches[k] = 0;
+  }
+  return GB_OK;
+}
+
+// upload [nd][n] host doubles into a [nd][ld] device buffer
+static int upload_rows(gb_pf *pf, double **dbuf, int *cap, const double *src, int nd) {
+  if (nd > *cap) {
+    cudaFree(*dbuf);
+    *dbuf = nullptr;
+    CK(cudaMalloc((void **)dbuf, (size_t)nd * pf->ld * 8));
+    CK(cudaMemsetAsync(*dbuf, 0, (size_t)nd * pf->ld * 8, pf->stream));
+    *cap = nd;
+  }
+  CK(cudaMemcpy2DAsync(*dbuf, (size_t)pf->ld * 8, src, (size_t)pf->n * 8, (size_t)pf->n * 8, nd, cudaMemcpyHostToDevice,
+                       pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));   // the host buffer is pageable and caller-owned
+  return GB_OK;
+}
+extern "C" int gb_pf_set_noise(gb_pf_t *pf, const double *normals, int nn, const double *uniforms, int nu) {
+  REQ(pf, "null handle");
+  pf->nn_set = pf->nu_set = 0;
+  if (normals && nn > 0) {
+    int rc = upload_rows(pf, &pf->d_normals, &pf->nn_cap, normals, nn);
+    if (rc) return rc;
+    pf->nn_set = nn;
+  }
+  if (uniforms && nu > 0) {
+    int rc = upload_rows(pf, &pf->d_uniforms, &pf->nu_cap, uniforms, nu);
+    if (rc) return rc;
+    pf->nu_set = nu;
+  }
+  return GB_OK;
+}
+extern "C" int gb_pf_set_resample_noise(gb_pf_t *pf, int use_u0, uint32_t u0, const uint64_t *u64s) {
+  REQ(pf, "null handle");
+  pf->use_u0 = use_u0 != 0;
+  pf->u0 = u0;
+  pf->u64_set = false;
+  if (u64s) {
+    if (!pf->d_u64) CK(cudaMalloc((void **)&pf->d_u64, (size_t)pf->ld * 8));
+    CK(cudaMemcpyAsync(pf->d_u64, u64s, (size_t)pf->n * 8, cudaMemcpyHostToDevice, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    pf->u64_set = true;
+  }
+  return GB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// step / generate dispatch
+// ------------------------------------------------------------------------------------------
+template <typename R, int KIND, int PK, bool INIT>
+static int launch_step_t(gb_pf *pf, const StepArgs &a, bool predrawn, bool gather) {
+  constexpr int V = VecOf<R>::V;
+  const long long nvec = (pf->n + V - 1) / V;
+#define GO(PD, GA)                                                                         \
+  {                                                                                        \
+    auto kern = step_kernel<R, KIND, PK, INIT, PD, GA>;                                    \
+    int grid = grid_for(pf, kern, nvec, kBlock);                                           \
+    LAUNCH(pf, GB_K_STEP, kern<<<grid, kBlock, 0, pf->stream>>>(a));                       \
+  }
+  if (INIT) {
+    if (predrawn) GO(true, false) else GO(false, false)
+  } else {
+    if (predrawn) { if (gather) GO(true, true) else GO(true, false) }
+    else { if (gather) GO(false, true) else GO(false, false) }
+  }
+#undef GO
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+template <typename R, bool INIT>
+static int launch_step_k(gb_pf *pf, const StepArgs &a, int pk, bool predrawn, bool gather) {
+  switch (pf->model.kind) {
+    case MODEL_LGSSM:
+      if (pk == PROPOSAL_AFFINE_NORMAL) return launch_step_t<R, MODEL_LGSSM, PROPOSAL_AFFINE_NORMAL, INIT>(pf, a, predrawn, gather);
+      if (pk == PROPOSAL_DEFAULT) return launch_step_t<R, MODEL_LGSSM, PROPOSAL_DEFAULT, INIT>(pf, a, predrawn, gather);
+      break;
+    case MODEL_SV:
+      if (pk == PROPOSAL_DEFAULT) return launch_step_t<R, MODEL_SV, PROPOSAL_DEFAULT, INIT>(pf, a, predrawn, gather);
+      break;
+    case MODEL_BEARINGS:
+      if (pk == PROPOSAL_DEFAULT) return launch_step_t<R, MODEL_BEARINGS, PROPOSAL_DEFAULT, INIT>(pf, a, predrawn, gather);
+      break;
+    case MODEL_HMM:
+      if (pk == PROPOSAL_CATEGORICAL_TABLE) return launch_step_t<R, MODEL_HMM, PROPOSAL_CATEGORICAL_TABLE, INIT>(pf, a, predrawn, gather);
+      if (pk == PROPOSAL_DEFAULT) return launch_step_t<R, MODEL_HMM, PROPOSAL_DEFAULT, INIT>(pf, a, predrawn, gather);
+      break;
+  }
+  return fail(GB_EUNSUPPORTED, "this proposal kind is not supported for this model kind");
+}
+
+static int fill_model_params(gb_pf *pf, ModelParams &mp, const double *obs, int nobs, int pk, const double *pargs,
+                             int npargs, bool init) {
+  memset(&mp, 0, sizeof(mp));
+  const gb_model &m = pf->model;
+  REQ(obs && nobs >= 1, "observation vector is required");
+  mp.obs0 = obs[0];
+  mp.K = m.K; mp.M = m.M;
+  if (m.kind == MODEL_HMM) {
+    mp.tab = pf->d_tab;
+    REQ(obs[0] >= 1 && obs[0] <= m.M, "HMM observation outside 1..M");
+  } else {
+    for (size_t i = 0; i < m.params.size() && i < 12; i++) mp.p[i] = m.params[i];
+  }
+  if (pk == PROPOSAL_AFFINE_NORMAL) {
+    REQ(m.kind == MODEL_LGSSM, "affine-normal proposal is defined for the LGSSM model only");
+    REQ(pargs && npargs == 3, "affine-normal proposal takes pargs = [c0, c1, std]");
+    for (int i = 0; i < 3; i++) mp.pa[i] = pargs[i];
+  } else if (pk == PROPOSAL_CATEGORICAL_TABLE) {
+    REQ(m.kind == MODEL_HMM, "categorical-table proposal is defined for the HMM model only");
+    int need = init ? m.K : m.K * m.K;
+    REQ(pargs && npargs == need, "categorical-table proposal: K probabilities at t=0, K*K afterwards");
+    if (pf->ptab_cap < need) {
+      cudaFree(pf->d_ptab);
+      pf->d_ptab = nullptr;
+      CK(cudaMalloc((void **)&pf->d_ptab, (size_t)m.K * m.K * 8));
+      pf->ptab_cap = m.K * m.K;
+    }
+    CK(cudaMemcpyAsync(pf->d_ptab, pargs, (size_t)need * 8, cudaMemcpyHostToDevice, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    mp.ptab = pf->d_ptab;
+  } else {
+    REQ(pk == PROPOSAL_DEFAULT, "unknown proposal kind");
+  }
+  return GB_OK;
+}
+
+static int check_noise(gb_pf *pf, bool init, bool *predrawn) {
+  const gb_model &m = pf->model;
+  int nn = model_num_normals(m.kind, m.params.data(), init), nu = model_num_uniforms(m.kind);
+  *predrawn = (pf->nn_set > 0 || pf->nu_set > 0);
+  if (*predrawn) {
+    REQ(pf->nn_set >= nn && pf->nu_set >= nu, "gb_pf_set_noise: fewer pre-drawn rows than this call consumes");
+  }
+  return GB_OK;
+}
+
+static int blr_generate(gb_pf *pf, const double *obs, int nobs, bool predrawn);
+
+extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, const double *pargs, int npargs) {
+  REQ(pf, "null handle");
+  REQ(nobs == pf->model.nobs, "gb_pf_generate: wrong number of observations");
+  bool predrawn;
+  int rc = check_noise(pf, true, &predrawn);
+  if (rc) return rc;
+  pf->step = 0;
+  pf->log_ml_est = 0.0;               // particle_filter.jl:133,153
+  pf->anc_valid = pf->parents64_valid = pf->pending_gather = false;   // parents = collect(1:N)
+  if (pf->model.kind == MODEL_BLR) {
+    REQ(pk == PROPOSAL_DEFAULT, "BLR supports the default proposal only");
+    rc = blr_generate(pf, obs, nobs, predrawn);
+  } else {
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    rc = fill_model_params(pf, a.mp, obs, nobs, pk, pargs, npargs, true);
+    if (rc) return rc;
+    a.state_in = nullptr;
+    a.state_out = pf->state[pf->cur ^ 1];
+    a.logw = pf->logw; a.incr = pf->incr;
+    a.normals = pf->d_normals; a.uniforms = pf->d_uniforms;
+    a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
+    a.seed = pf->seed; a.step = 0;
+    a.partials = pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
+    rc = pf->dtype == GB_F64 ? launch_step_k<double, true>(pf, a, pk, predrawn, false)
+                             : launch_step_k<float, true>(pf, a, pk, predrawn, false);
+  }
+  if (rc) return rc;
+  pf->cur ^= 1;
+  pf->wstate = W_STATS;
+  pf->nn_set = pf->nu_set = 0;
+  return GB_OK;
+}
+
+extern "C" int gb_pf_initialize(const gb_model_t *m, int64_t n, int dtype, uint64_t seed, const double *obs, int nobs,
+                                int pk, const double *pargs, int npargs, gb_pf_t **out) {
+  gb_pf_t *pf = nullptr;
+  int rc = gb_pf_create(m, n, n, 0, dtype, seed, &pf);
+  if (rc) return rc;
+  rc = gb_pf_generate(pf, obs, nobs, pk, pargs, npargs);
+  if (rc) { pf_release(pf); return rc; }
+  *out = pf;
+  return GB_OK;
+}
+
+extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, const double *pargs, int npargs,
+                          double *incr_out) {
+  REQ(pf, "null handle");
+  REQ(pf->model.kind != MODEL_BLR, "the BLR model has no sequential structure (importance sampling only)");
+  REQ(nobs == pf->model.nobs, "gb_pf_step: wrong number of observations");
+  bool predrawn;
+  int rc = check_noise(pf, false, &predrawn);
+  if (rc) return rc;
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  rc = fill_model_params(pf, a.mp, obs, nobs, pk, pargs, npargs, false);
+  if (rc) return rc;
+  a.state_in = pf->state[pf->cur];
+  a.state_out = pf->state[pf->cur ^ 1];
+  a.logw = pf->logw; a.incr = pf->incr;
+  a.anc = pf->anc;
+  a.normals = pf->d_normals; a.uniforms = pf->d_uniforms;
+  a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
+  a.seed = pf->seed; a.step = (unsigned)(pf->step + 1);
+  a.partials = pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
+  const bool gather = pf->pending_gather;
+  rc = pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, pk, predrawn, gather)
+                           : launch_step_k<float, false>(pf, a, pk, predrawn, gather);
+  if (rc) return rc;
+  pf->step += 1;
+  pf->cur ^= 1;                       // particle_filter.jl:203-205, :234-237 (swap traces/new_traces)
+  pf->pending_gather = false;
+  pf->wstate = W_STATS;
+  pf->nn_set = pf->nu_set = 0;
+  if (incr_out) {
+    if (pf->dtype == GB_F64) {
+      CK(cudaMemcpyAsync(incr_out, pf->incr, (size_t)pf->n * 8, cudaMemcpyDeviceToHost, pf->stream));
+      CK(cudaStreamSynchronize(pf->stream));
+    } else {
+      std::vector<float> tmp(pf->n);
+      CK(cudaMemcpyAsync(tmp.data(), pf->incr, (size_t)pf->n * 4, cudaMemcpyDeviceToHost, pf->stream));
+      CK(cudaStreamSynchronize(pf->stream));
+      for (long long i = 0; i < pf->n; i++) incr_out[i] = tmp[i];
+    }
+  }
+  return GB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// weights: stats, materialisation
+// ------------------------------------------------------------------------------------------
+static int run_gather(gb_pf *pf) {   // materialise a deferred resample gather
+  if (!pf->pending_gather) return GB_OK;
+  const long long nvec = pf->dtype == GB_F64 ? (pf->n + 1) / 2 : (pf->n + 3) / 4;
+  if (pf->dtype == GB_F64) {
+    auto kern = gather_kernel<double>;
+    int grid = grid_for(pf, kern, nvec, kBlock);
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)pf->state[pf->cur], (double *)pf->state[pf->cur ^ 1],
+                                                                   pf->ld, pf->S, pf->anc, pf->n, (double *)pf->logw));
+  } else {
+    auto kern = gather_kernel<float>;
+    int grid = grid_for(pf, kern, nvec, kBlock);
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)pf->state[pf->cur], (float *)pf->state[pf->cur ^ 1],
+                                                                   pf->ld, pf->S, pf->anc, pf->n, (float *)pf->logw));
+  }
+  CK(cudaGetLastError());
+  pf->cur ^= 1;                       // particle_filter.jl:270-272
+  pf->pending_gather = false;
+  return GB_OK;
+}
+
+// make h_stats describe the current log weights
+static int ensure_stats(gb_pf *pf) {
+  if (pf->wstate == W_ZERO) {
+    // all log weights are exactly 0.0: logsumexp = 0 + log(N_local)
+    pf->h_stats->m = 0.0; pf->h_stats->s1 = (double)pf->n; pf->h_stats->s2 = (double)pf->n;
+    pf->h_stats->lse = log((double)pf->n); pf->h_stats->ess = (double)pf->n;
+    return GB_OK;
+  }
+  if (pf->wstate == W_DIRTY) {
+    if (pf->dtype == GB_F64) {
+      auto kern = lse_kernel<double>;
+      int grid = grid_for(pf, kern, pf->n, kBlock);
+      LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)pf->logw, pf->n, pf->partials, pf->ticket, pf->d_stats));
+    } else {
+      auto kern = lse_kernel<float>;
+      int grid = grid_for(pf, kern, pf->n, kBlock);
+      LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)pf->logw, pf->n, pf->partials, pf->ticket, pf->d_stats));
+    }
+    CK(cudaGetLastError());
+    pf->wstate = W_STATS;
+  }
+  CK(cudaMemcpyAsync(pf->h_stats, pf->d_stats, sizeof(WeightStats), cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));
+  return GB_OK;
+}
+
+extern "C" int gb_pf_weight_partials(gb_pf_t *pf, double *m, double *s1, double *s2) {
+  REQ(pf && m && s1 && s2, "null argument");
+  int rc = ensure_stats(pf);
+  if (rc) return rc;
+  *m = pf->h_stats->m; *s1 = pf->h_stats->s1; *s2 = pf->h_stats->s2;
+  return GB_OK;
+}
+extern "C" int gb_pf_get_ess(gb_pf_t *pf, double *ess, double *lse) {
+  REQ(pf, "null handle");
+  int rc = ensure_stats(pf);
+  if (rc) return rc;
+  if (ess) *ess = pf->h_stats->ess;
+  if (lse) *lse = pf->h_stats->lse;
+  return GB_OK;
+}
+extern "C" int gb_pf_log_ml_estimate(gb_pf_t *pf, double *out) {
+  REQ(pf && out, "null argument");
+  REQ(pf->n == pf->n_global, "gb_pf_log_ml_estimate: sharded filters combine partials on the host (sharded.py)");
+  int rc = ensure_stats(pf);
+  if (rc) return rc;
+  // particle_filter.jl:93: log_ml_est + logsumexp(log_weights) - log(num_particles)
+  *out = pf->log_ml_est + pf->h_stats->lse - log((double)pf->n_global);
+  return GB_OK;
+}
+extern "C" int gb_pf_get_log_ml_est(gb_pf_t *pf, double *out) { REQ(pf && out, "null argument"); *out = pf->log_ml_est; return GB_OK; }
+
+template <typename R> static int fill_dev(gb_pf *pf, R *p, long long n, R v) {
+  auto kern = fill_kernel<R>;
+  int grid = grid_for(pf, kern, n, kBlock);
+  LAUNCH(pf, GB_K_MISC, kern<<<grid, kBlock, 0, pf->stream>>>(p, n, v));
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+// deferred state -> the arrays really hold what the API says they hold
+static int materialize(gb_pf *pf) {
+  bool was_pending = pf->pending_gather;
+  int rc = run_gather(pf);   // also zeroes logw
+  if (rc) return rc;
+  (void)was_pending;
+  return GB_OK;
+}
+
+static int copy_out(gb_pf *pf, const void *dsrc, double *out, long long n) {
+  if (pf->dtype == GB_F64) {
+    CK(cudaMemcpyAsync(out, dsrc, (size_t)n * 8, cudaMemcpyDeviceToHost, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+  } else {
+    std::vector<float> tmp(n);
+    CK(cudaMemcpyAsync(tmp.data(), dsrc, (size_t)n * 4, cudaMemcpyDeviceToHost, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    for (long long i = 0; i < n; i++) out[i] = tmp[i];
+  }
+  return GB_OK;
+}
+extern "C" int gb_pf_get_log_weights(gb_pf_t *pf, double *out) {
+  REQ(pf && out, "null argument");
+  int rc = materialize(pf);
+  if (rc) return rc;
+  return copy_out(pf, pf->logw, out, pf->n);
+}
+extern "C" int gb_pf_set_log_weights(gb_pf_t *pf, const double *in) {
+  REQ(pf && in, "null argument");
+  int rc = materialize(pf);
+  if (rc) return rc;
+  if (pf->dtype == GB_F64) {
+    CK(cudaMemcpyAsync(pf->logw, in, (size_t)pf->n * 8, cudaMemcpyHostToDevice, pf->stream));
+  } else {
+    std::vector<float> tmp(pf->n);
+    for (long long i = 0; i < pf->n; i++) tmp[i] = (float)in[i];
+    CK(cudaMemcpyAsync(pf->logw, tmp.data(), (size_t)pf->n * 4, cudaMemcpyHostToDevice, pf->stream));
+  }
+  CK(cudaStreamSynchronize(pf->stream));
+  pf->wstate = W_DIRTY;
+  return GB_OK;
+}
+extern "C" int gb_pf_get_state(gb_pf_t *pf, int field, double *out) {
+  REQ(pf && out, "null argument");
+  REQ(field >= 0 && field < pf->S, "gb_pf_get_state: field out of range");
+  int rc = materialize(pf);
+  if (rc) return rc;
+  return copy_out(pf, (const char *)pf->state[pf->cur] + (size_t)field * pf->ld * pf->esz, out, pf->n);
+}
+extern "C" int gb_pf_get_parents(gb_pf_t *pf, int64_t *out) {
+  REQ(pf && out, "null argument");
+  if (!pf->parents64) CK(cudaMalloc((void **)&pf->parents64, (size_t)pf->ld * 8));
+  if (!pf->parents64_valid) {
+    if (pf->anc_valid) {
+      int grid = grid_for(pf, parents_from_anc_kernel, pf->n, kBlock);
+      LAUNCH(pf, GB_K_MISC, parents_from_anc_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->anc, pf->parents64, pf->n, pf->pid_offset));
+    } else {
+      int grid = grid_for(pf, iota_parents_kernel, pf->n, kBlock);
+      LAUNCH(pf, GB_K_MISC, iota_parents_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->parents64, pf->n, pf->pid_offset));
+    }
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(out, pf->parents64, (size_t)pf->n * 8, cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));
+  return GB_OK;
+}
+
+extern "C" int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out) {
+  REQ(pf && out, "null argument");
+  int rc = materialize(pf);
+  if (rc) return rc;
+  rc = ensure_stats(pf);
+  if (rc) return rc;
+  gb_pf_t *c = nullptr;
+  rc = gb_pf_create(&pf->model, pf->n, pf->n_global, pf->pid_offset, pf->dtype, pf->seed, &c);
+  if (rc) return rc;
+  c->stream = pf->stream;
+  c->lazy = pf->lazy;
+  c->step = pf->step;
+  c->log_ml_est = pf->log_ml_est;
+  c->wstate = pf->wstate;
+  c->anc_valid = pf->anc_valid;
+  size_t col = (size_t)pf->ld * pf->esz;
+  cudaError_t e = cudaMemcpyAsync(c->state[c->cur], pf->state[pf->cur], col * pf->S, cudaMemcpyDeviceToDevice, pf->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->logw, pf->logw, col, cudaMemcpyDeviceToDevice, pf->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->incr, pf->incr, col, cudaMemcpyDeviceToDevice, pf->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->anc, pf->anc, (size_t)pf->ld * 4, cudaMemcpyDeviceToDevice, pf->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_stats, pf->d_stats, sizeof(WeightStats), cudaMemcpyDeviceToDevice, pf->stream);
+  if (e == cudaSuccess && pf->parents64_valid) {
+    e = cudaMalloc((void **)&c->parents64, (size_t)pf->ld * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->parents64, pf->parents64, (size_t)pf->ld * 8, cudaMemcpyDeviceToDevice, pf->stream);
+    c->parents64_valid = true;
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
+  if (e != cudaSuccess) { pf_release(c); return fail(GB_ECUDA, std::string("gb_pf_clone: ") + cudaGetErrorString(e)); }
+  *out = c;
+  return GB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// resampling
+// ------------------------------------------------------------------------------------------
+static int ensure_residual_ws(gb_pf *pf) {
+  if (!pf->tile_c) CK(cudaMalloc((void **)&pf->tile_c, (size_t)(pf->ntiles + 1) * 8));
+  if (!pf->tile_r) CK(cudaMalloc((void **)&pf->tile_r, (size_t)(pf->ntiles + 1) * sizeof(U128)));
+  return GB_OK;
+}
+
+template <typename R, int SWEEP>
+static int launch_qtotal(gb_pf *pf, const void *logw, double m, int bits, uint64_t q_total) {
+  auto kern = qtotal_kernel<R, SWEEP>;
+  int grid = grid_for(pf, kern, pf->ntiles * kBlock, kBlock);
+  LAUNCH(pf, GB_K_QTOTAL, kern<<<grid, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->n_global, q_total,
+                                                                 pf->tile_q, pf->tile_c, pf->tile_r));
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+template <int SWEEP>
+static int launch_tilescan(gb_pf *pf, uint64_t q_offset, uint64_t q_total, uint32_t u0, int write) {
+  LAUNCH(pf, GB_K_TILESCAN, tilescan_kernel<SWEEP><<<1, 1024, 0, pf->stream>>>(pf->ntiles, pf->tile_q, pf->tile_c, pf->tile_r,
+                                                                                pf->tile_slot, pf->d_plan, q_offset, q_total,
+                                                                                pf->n_global, u0, write));
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+template <typename R, int SWEEP>
+static int launch_ancestors(gb_pf *pf, const void *logw, double m, int bits, long long over_base, long long n_over,
+                            int *anc, long long anc_base) {
+  auto kern = ancestors_kernel<R, SWEEP>;
+  long long grid = pf->ntiles + n_over;
+  LAUNCH(pf, GB_K_ANCESTORS, kern<<<(unsigned)grid, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->tile_q, pf->tile_c,
+                                                                              pf->tile_r, pf->tile_slot, pf->d_plan, pf->ntiles,
+                                                                              over_base, anc, anc_base, pf->cdf));
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+static int fetch_plan(gb_pf *pf) {
+  CK(cudaMemcpyAsync(pf->h_plan, pf->d_plan, sizeof(ResamplePlan), cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));
+  return GB_OK;
+}
+
+// ancestors (local, 0-based int32) of all n slots of a single-shard filter into pf->anc
+template <typename R>
+static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, uint32_t u0, const uint64_t *d_u64,
+                             uint64_t seed, uint32_t step, int *anc) {
+  const int bits = quant_bits(pf->n_global);
+  const long long n_over = (pf->n_global + kChunk - 1) / kChunk;
+  int rc;
+  if (kind == GB_RESAMPLE_SYSTEMATIC) {
+    if ((rc = launch_qtotal<R, SWEEP_SYSTEMATIC>(pf, logw, m, bits, 0))) return rc;
+    if ((rc = launch_tilescan<SWEEP_SYSTEMATIC>(pf, 0, 0, u0, 1))) return rc;
+    return launch_ancestors<R, SWEEP_SYSTEMATIC>(pf, logw, m, bits, 0, n_over, anc, 0);
+  }
+  if (kind == GB_RESAMPLE_RESIDUAL) {
+    if ((rc = ensure_residual_ws(pf))) return rc;
+    if ((rc = launch_qtotal<R, SWEEP_SYSTEMATIC>(pf, logw, m, bits, 0))) return rc;
+    if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, u0, 0))) return rc;    // totals only -> plan.sp.q_total
+    if ((rc = fetch_plan(pf))) return rc;
+    const uint64_t qn = pf->h_plan->sp.q_total;
+    if ((rc = launch_qtotal<R, SWEEP_RESIDUAL>(pf, logw, m, bits, qn))) return rc;
+    if ((rc = launch_tilescan<SWEEP_RESIDUAL>(pf, 0, qn, u0, 1))) return rc;
+    return launch_ancestors<R, SWEEP_RESIDUAL>(pf, logw, m, bits, 0, n_over, anc, 0);
+  }
+  if (kind == GB_RESAMPLE_MULTINOMIAL) {
+    if (!pf->cdf) CK(cudaMalloc((void **)&pf->cdf, (size_t)pf->ld * 8));
+    if ((rc = launch_qtotal<R, SWEEP_SYSTEMATIC>(pf, logw, m, bits, 0))) return rc;
+    if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, u0, 1))) return rc;
+    if ((rc = launch_ancestors<R, SWEEP_CDF>(pf, logw, m, bits, 0, 0, anc, 0))) return rc;
+    int grid = grid_for(pf, multinomial_kernel, pf->n, kBlock);
+    LAUNCH(pf, GB_K_ANCESTORS, multinomial_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->cdf, pf->tile_q, pf->ntiles, pf->n, pf->d_plan,
+                                                                                   d_u64, seed, step, pf->n, anc));
+    CK(cudaGetLastError());
+    return GB_OK;
+  }
+  return fail(GB_EINVAL, "unknown resampler kind");
+}
+
+extern "C" int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind, int *did) {
+  REQ(pf && did, "null argument");
+  REQ(pf->n == pf->n_global, "gb_pf_maybe_resample: single shard only; sharded filters use the gb_pf_* pieces");
+  *did = 0;
+  int rc = ensure_stats(pf);          // particle_filter.jl:254-255
+  if (rc) return rc;
+  const double ess = pf->h_stats->ess, lse = pf->h_stats->lse, m = pf->h_stats->m;
+  const bool do_resample = ess < ess_threshold;   // :256 (strict; NaN compares false)
+  if (!do_resample) return GB_OK;
+  if ((rc = materialize(pf))) return rc;          // two deferred gathers cannot be chained
+  // (W_ZERO with nothing pending: the array was really zeroed by the gather / commit that set it)
+  // resampling randomness is keyed by the index of the step that produced the weights
+  const uint32_t u0 = pf->use_u0 ? pf->u0 : philox_block(pf->seed, 0, (uint32_t)pf->step, PK_RESAMPLE, 0).x;
+  const uint64_t *d_u64 = pf->u64_set ? pf->d_u64 : nullptr;
+  rc = pf->dtype == GB_F64 ? compute_ancestors<double>(pf, pf->logw, m, kind, u0, d_u64, pf->seed, (uint32_t)pf->step, pf->anc)
+                           : compute_ancestors<float>(pf, pf->logw, m, kind, u0, d_u64, pf->seed, (uint32_t)pf->step, pf->anc);
+  if (rc) return rc;
+  pf->log_ml_est += lse - log((double)pf->n_global);   // :263
+  pf->anc_valid = true;
+  pf->parents64_valid = false;
+  pf->pending_gather = true;
+  pf->wstate = W_ZERO;                                  // :266
+  pf->use_u0 = false;
+  pf->u64_set = false;
+  if (!pf->lazy && (rc = run_gather(pf))) return rc;    // :264-272
+  *did = 1;
+  return GB_OK;
+}
+
+// ---- sharded pieces ----
+extern "C" int gb_pf_quantized_total(gb_pf_t *pf, double m_global, int bits, uint64_t *q_local) {
+  REQ(pf && q_local, "null argument");
+  int rc = materialize(pf);
+  if (rc) return rc;
+  rc = pf->dtype == GB_F64 ? launch_qtotal<double, SWEEP_SYSTEMATIC>(pf, pf->logw, m_global, bits, 0)
+                           : launch_qtotal<float, SWEEP_SYSTEMATIC>(pf, pf->logw, m_global, bits, 0);
+  if (rc) return rc;
+  if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, 0, 0))) return rc;   // totals only
+  if ((rc = fetch_plan(pf))) return rc;
+  *q_local = pf->h_plan->sp.q_total;
+  return GB_OK;
+}
+extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits, uint64_t q_offset, uint64_t q_total,
+                                          uint32_t u0, int64_t *slot_lo, int64_t *slot_hi) {
+  REQ(pf && slot_lo && slot_hi, "null argument");
+  REQ(q_total > 0, "gb_pf_systematic_offspring: zero total weight");
+  int rc;
+  // tile_q still holds the per-tile totals written by gb_pf_quantized_total
+  if ((rc = launch_tilescan<SWEEP_SYSTEMATIC>(pf, q_offset, q_total, u0, 1))) return rc;
+  if ((rc = fetch_plan(pf))) return rc;
+  const long long lo = pf->h_plan->slot_lo, hi = pf->h_plan->slot_hi;
+  const long long cnt = hi - lo;
+  if (cnt > pf->off_cap) {
+    cudaFree(pf->off_anc);
+    pf->off_anc = nullptr;
+    long long cap = ((cnt + kTile - 1) / kTile) * kTile;
+    CK(cudaMalloc((void **)&pf->off_anc, (size_t)cap * 4));
+    pf->off_cap = cap;
+  }
+  if (cnt > 0) {
+    const long long n_over = (cnt + kChunk - 1) / kChunk;
+    rc = pf->dtype == GB_F64
+             ? launch_ancestors<double, SWEEP_SYSTEMATIC>(pf, pf->logw, m_global, bits, lo, n_over, pf->off_anc, lo)
+             : launch_ancestors<float, SWEEP_SYSTEMATIC>(pf, pf->logw, m_global, bits, lo, n_over, pf->off_anc, lo);
+    if (rc) return rc;
+  }
+  pf->off_lo = lo; pf->off_hi = hi;
+  *slot_lo = lo; *slot_hi = hi;
+  return GB_OK;
+}
+extern "C" int gb_pf_export_offspring(gb_pf_t *pf, int64_t k_lo, int64_t k_hi, void *dev_rows, void *dev_parents) {
+  REQ(pf && dev_rows && dev_parents, "null argument");
+  REQ(k_lo >= pf->off_lo && k_hi <= pf->off_hi && k_lo <= k_hi, "gb_pf_export_offspring: slots outside the shard's offspring range");
+  const long long cnt = k_hi - k_lo;
+  if (cnt == 0) return GB_OK;
+  const int *anc = pf->off_anc + (k_lo - pf->off_lo);
+  if (pf->dtype == GB_F64) {
+    auto kern = export_kernel<double>;
+    int grid = grid_for(pf, kern, cnt, kBlock);
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)pf->state[pf->cur], pf->ld, pf->S, anc, cnt,
+                                                                   (double *)dev_rows, (long long *)dev_parents, pf->pid_offset));
+  } else {
+    auto kern = export_kernel<float>;
+    int grid = grid_for(pf, kern, cnt, kBlock);
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)pf->state[pf->cur], pf->ld, pf->S, anc, cnt,
+                                                                   (float *)dev_rows, (long long *)dev_parents, pf->pid_offset));
+  }
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+extern "C" int gb_pf_import_rows(gb_pf_t *pf, int64_t dst_lo, int64_t count, const void *dev_rows, const void *dev_parents) {
+  REQ(pf && dev_rows && dev_parents, "null argument");
+  REQ(dst_lo >= 0 && count >= 0 && dst_lo + count <= pf->n, "gb_pf_import_rows: destination outside the shard");
+  if (count == 0) return GB_OK;
+  if (!pf->parents64) CK(cudaMalloc((void **)&pf->parents64, (size_t)pf->ld * 8));
+  if (pf->dtype == GB_F64) {
+    auto kern = import_kernel<double>;
+    int grid = grid_for(pf, kern, count, kBlock);
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((double *)pf->state[pf->cur ^ 1], pf->ld, pf->S, dst_lo, count,
+                                                                   (const double *)dev_rows, (const long long *)dev_parents, pf->parents64));
+  } else {
+    auto kern = import_kernel<float>;
+    int grid = grid_for(pf, kern, count, kBlock);
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((float *)pf->state[pf->cur ^ 1], pf->ld, pf->S, dst_lo, count,
+                                                                   (const float *)dev_rows, (const long long *)dev_parents, pf->parents64));
+  }
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+extern "C" int gb_pf_commit_resample(gb_pf_t *pf, double log_ml_increment) {
+  REQ(pf, "null handle");
+  pf->cur ^= 1;
+  pf->log_ml_est += log_ml_increment;
+  pf->wstate = W_ZERO;
+  pf->anc_valid = false;
+  pf->parents64_valid = true;
+  pf->pending_gather = false;
+  int rc = pf->dtype == GB_F64 ? fill_dev<double>(pf, (double *)pf->logw, pf->ld, 0.0) : fill_dev<float>(pf, (float *)pf->logw, pf->ld, 0.f);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// importance sampling
+// ------------------------------------------------------------------------------------------
+static int blr_generate(gb_pf *pf, const double *obs, int nobs, bool predrawn) {
+  const gb_model &m = pf->model;
+  std::vector<double> X((size_t)kBlrMax * kBlrMax, 0.0), y(kBlrMax, 0.0);
+  for (int j = 0; j < m.nobs; j++)
+    for (int d = 0; d < m.D; d++) X[(size_t)j * kBlrMax + d] = m.params[3 + (size_t)j * m.D + d];
+  for (int j = 0; j < nobs; j++) y[j] = obs[j];
+  CK(cudaMemcpyToSymbolAsync(c_blr_X, X.data(), X.size() * 8, 0, cudaMemcpyHostToDevice, pf->stream));
+  CK(cudaMemcpyToSymbolAsync(c_blr_y, y.data(), y.size() * 8, 0, cudaMemcpyHostToDevice, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));
+  BlrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.state_out = pf->state[pf->cur ^ 1];
+  a.logw = pf->logw;
+  a.normals = pf->d_normals;
+  a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
+  a.seed = pf->seed; a.D = m.D; a.nobs = m.nobs; a.sigma = m.params[2];
+  a.partials = pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
+#define GO(R, PD)                                                                   \
+  {                                                                                 \
+    auto kern = blr_generate_kernel<R, PD>;                                         \
+    int grid = grid_for(pf, kern, pf->n, 128);                                      \
+    LAUNCH(pf, GB_K_STEP, kern<<<grid, 128, 0, pf->stream>>>(a));                   \
+  }
+  if (pf->dtype == GB_F64) { if (predrawn) GO(double, true) else GO(double, false) }
+  else { if (predrawn) GO(float, true) else GO(float, false) }
+#undef GO
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+
+extern "C" int gb_importance_sampling(const gb_model_t *m, int64_t n, int dtype, uint64_t seed, const double *obs, int nobs,
+                                      int pk, const double *pargs, int npargs, const double *normals, int nn,
+                                      const double *uniforms, int nu, double *lognormw_out, double *lml_out, gb_pf_t **pf_out) {
+  REQ(m && lml_out, "null argument");
+  gb_pf_t *pf = nullptr;
+  int rc = gb_pf_create(m, n, n, 0, dtype, seed, &pf);
+  if (rc) return rc;
+  if ((normals && nn > 0) || (uniforms && nu > 0)) rc = gb_pf_set_noise(pf, normals, nn, uniforms, nu);
+  if (!rc) rc = gb_pf_generate(pf, obs, nobs, pk, pargs, npargs);    // importance.jl:28-31, :48-54
+  if (!rc) rc = ensure_stats(pf);                                    // :32, :55
+  if (rc) { pf_release(pf); return rc; }
+  *lml_out = pf->h_stats->lse - log((double)n);                      // :33, :56
+  if (lognormw_out) {                                                // :34, :57
+    double *d_out = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_out, (size_t)n * 8);
+    if (e != cudaSuccess) { pf_release(pf); return fail(GB_ECUDA, cudaGetErrorString(e)); }
+    if (dtype == GB_F64) {
+      auto kern = normalize_kernel<double>;
+      int grid = grid_for(pf, kern, n, kBlock);
+      LAUNCH(pf, GB_K_MISC, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)pf->logw, n, pf->d_stats, d_out));
+    } else {
+      auto kern = normalize_kernel<float>;
+      int grid = grid_for(pf, kern, n, kBlock);
+      LAUNCH(pf, GB_K_MISC, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)pf->logw, n, pf->d_stats, d_out));
+    }
+    e = cudaMemcpyAsync(lognormw_out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, pf->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) { pf_release(pf); return fail(GB_ECUDA, cudaGetErrorString(e)); }
+  }
+  if (pf_out) *pf_out = pf; else pf_release(pf);
+  return GB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// raw-array resampling / logsumexp (config 5 microbenchmark)
+// ------------------------------------------------------------------------------------------
+struct RawWs {       // per-thread cached workspace: a gb_pf shell without particle columns
+  gb_pf *pf = nullptr;
+  long long n = 0;
+  int dtype = -1;
+};
+static thread_local RawWs g_raw;
+
+static int raw_workspace(long long n, int dtype, cudaStream_t stream, gb_pf **out) {
+  if (g_raw.pf && g_raw.n == n && g_raw.dtype == dtype) { g_raw.pf->stream = stream; *out = g_raw.pf; return GB_OK; }
+  if (g_raw.pf) { pf_release(g_raw.pf); g_raw.pf = nullptr; }
+  int rc = require_gpu();
+  if (rc) return rc;
+  REQ(n >= 1 && n < ((int64_t)1 << 31), "raw resampling: 1 <= n < 2^31");
+  gb_pf *pf = new gb_pf;
+  pf->dtype = dtype; pf->esz = dtype == GB_F64 ? 8 : 4;
+  pf->n = pf->n_global = n; pf->ld = ((n + kTile - 1) / kTile) * kTile; pf->ntiles = pf->ld / kTile;
+  pf->stream = stream;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&pf->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaError_t e = cudaMalloc((void **)&pf->partials, sizeof(Lse3) * kMaxPartials);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->ticket, 64);
+  if (e == cudaSuccess) e = cudaMemset(pf->ticket, 0, 64);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->d_stats, sizeof(WeightStats));
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&pf->h_stats, sizeof(WeightStats));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->tile_q, (size_t)(pf->ntiles + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->tile_slot, (size_t)(pf->ntiles + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->d_plan, sizeof(ResamplePlan));
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&pf->h_plan, sizeof(ResamplePlan));
+  if (e != cudaSuccess) { pf_release(pf); return fail(GB_ECUDA, std::string("raw workspace: ") + cudaGetErrorString(e)); }
+  g_raw.pf = pf; g_raw.n = n; g_raw.dtype = dtype;
+  *out = pf;
+  return GB_OK;
+}
+
+// max + sums of a raw device array -> ws->h_stats
+static int raw_stats(gb_pf *ws, const void *dev_logw) {
+  if (ws->dtype == GB_F64) {
+    auto kern = lse_kernel<double>;
+    int grid = grid_for(ws, kern, ws->n, kBlock);
+    LAUNCH(ws, GB_K_FINALIZE, kern<<<grid, kBlock, 0, ws->stream>>>((const double *)dev_logw, ws->n, ws->partials, ws->ticket, ws->d_stats));
+  } else {
+    auto kern = lse_kernel<float>;
+    int grid = grid_for(ws, kern, ws->n, kBlock);
+    LAUNCH(ws, GB_K_FINALIZE, kern<<<grid, kBlock, 0, ws->stream>>>((const float *)dev_logw, ws->n, ws->partials, ws->ticket, ws->d_stats));
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ws->h_stats, ws->d_stats, sizeof(WeightStats), cudaMemcpyDeviceToHost, ws->stream));
+  CK(cudaStreamSynchronize(ws->stream));
+  return GB_OK;
+}
+
+// NOTE: dev_logw must be padded to a multiple of 2048 elements (the engine's own arrays are); the
+// host-buffer entry below takes care of that, device callers allocate round_up(n, 2048) elements.
+extern "C" int gb_resample_device(const void *dev_logw, int64_t n, int dtype, int kind, uint32_t u0, const void *dev_u64,
+                                  uint64_t seed, uint32_t step, void *dev_anc, void *cuda_stream) {
+  REQ(dev_logw && dev_anc, "null argument");
+  REQ(dtype == GB_F64 || dtype == GB_F32, "bad dtype");
+  gb_pf *ws = nullptr;
+  int rc = raw_workspace(n, dtype, (cudaStream_t)cuda_stream, &ws);
+  if (rc) return rc;
+  if ((rc = raw_stats(ws, dev_logw))) return rc;
+  const double m = ws->h_stats->m;
+  if (!(m > -INFINITY)) return fail(GB_ESTATE, "gb_resample: all log weights are -Inf or NaN");
+  return dtype == GB_F64 ? compute_ancestors<double>(ws, dev_logw, m, kind, u0, (const uint64_t *)dev_u64, seed, step, (int *)dev_anc)
+                         : compute_ancestors<float>(ws, dev_logw, m, kind, u0, (const uint64_t *)dev_u64, seed, step, (int *)dev_anc);
+}
+
+extern "C" int gb_resample(const double *logw, int64_t n, int dtype, int kind, uint32_t u0, const uint64_t *u64s,
+                           uint64_t seed, uint32_t step, int64_t *anc_out) {
+  REQ(logw && anc_out && n >= 1, "null argument");
+  int rc = require_gpu();
+  if (rc) return rc;
+  const long long ld = ((n + kTile - 1) / kTile) * kTile;
+  const size_t esz = dtype == GB_F64 ? 8 : 4;
+  void *d_lw = nullptr;
+  int *d_anc = nullptr;
+  uint64_t *d_u = nullptr;
+  std::vector<float> tmpf;
+  std::vector<int> anc32(n);
+  cudaError_t e = cudaMalloc(&d_lw, (size_t)ld * esz);
+  if (e == cudaSuccess) e = cudaMemset(d_lw, 0xFF, (size_t)ld * esz);   // padding = NaN, masked by index anyway
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_anc, (size_t)ld * 4);
+  if (e == cudaSuccess && u64s) {
+    e = cudaMalloc((void **)&d_u, (size_t)ld * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(d_u, u64s, (size_t)n * 8, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) {
+    if (dtype == GB_F64) e = cudaMemcpy(d_lw, logw, (size_t)n * 8, cudaMemcpyHostToDevice);
+    else {
+      tmpf.resize(n);
+      for (long long i = 0; i < n; i++) tmpf[i] = (float)logw[i];
+      e = cudaMemcpy(d_lw, tmpf.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
+    }
+  }
+  rc = GB_OK;
+  if (e != cudaSuccess) rc = fail(GB_ECUDA, std::string("gb_resample: ") + cudaGetErrorString(e));
+  if (!rc) rc = gb_resample_device(d_lw, n, dtype, kind, u0, d_u, seed, step, d_anc, nullptr);
+  if (!rc) {
+    e = cudaMemcpy(anc32.data(), d_anc, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(GB_ECUDA, std::string("gb_resample: ") + cudaGetErrorString(e));
+  }
+  cudaFree(d_lw); cudaFree(d_anc); cudaFree(d_u);
+  if (rc) return rc;
+  for (long long i = 0; i < n; i++) anc_out[i] = anc32[i];
+  return GB_OK;
+}
+
+extern "C" int gb_logsumexp(const double *a, int64_t n, int dtype, double *lse_out, double *ess_out) {
+  REQ(a && n >= 1, "null argument");
+  gb_pf *ws = nullptr;
+  int rc = raw_workspace(n, dtype, nullptr, &ws);
+  if (rc) return rc;
+  void *d = nullptr;
+  const size_t esz = dtype == GB_F64 ? 8 : 4;
+  CK(cudaMalloc(&d, (size_t)n * esz));
+  cudaError_t e;
+  if (dtype == GB_F64) e = cudaMemcpy(d, a, (size_t)n * 8, cudaMemcpyHostToDevice);
+  else {
+    std::vector<float> t(n);
+    for (long long i = 0; i < n; i++) t[i] = (float)a[i];
+    e = cudaMemcpy(d, t.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) { cudaFree(d); return fail(GB_ECUDA, cudaGetErrorString(e)); }
+  rc = raw_stats(ws, d);
+  cudaFree(d);
+  if (rc) return rc;
+  if (lse_out) *lse_out = ws->h_stats->lse;
+  if (ess_out) *ess_out = ws->h_stats->ess;
+  return GB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// noise export + host-side integer helpers
+// ------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(kBlock) noise_kernel(unsigned long long seed, unsigned int step, long long pid0, long long n,
+                                                       int ndraw, int uniform, double *__restrict__ out) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
+    for (int d = 0; d < ndraw; d += 2) {
+      R a, b;
+      if (uniform) philox_uniform_pair(seed, (unsigned long long)(pid0 + i), step, (unsigned)(d / 2), a, b);
+      else philox_normal_pair(seed, (unsigned long long)(pid0 + i), step, (unsigned)(d / 2), a, b);
+      out[(long long)d * n + i] = (double)a;
+      if (d + 1 < ndraw) out[(long long)(d + 1) * n + i] = (double)b;
+    }
+}
+static int export_noise(uint64_t seed, uint32_t step, int64_t pid0, int64_t n, int ndraw, int dtype, int uniform, double *out) {
+  REQ(out && n >= 1 && ndraw >= 1, "bad argument");
+  int rc = require_gpu();
+  if (rc) return rc;
+  double *d = nullptr;
+  CK(cudaMalloc((void **)&d, (size_t)n * ndraw * 8));
+  int grid = (int)std::min<long long>((n + kBlock - 1) / kBlock, 148 * 8);
+  if (dtype == GB_F64) noise_kernel<double><<<grid, kBlock>>>(seed, step, pid0, n, ndraw, uniform, d);
+  else noise_kernel<float><<<grid, kBlock>>>(seed, step, pid0, n, ndraw, uniform, d);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(out, d, (size_t)n * ndraw * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(GB_ECUDA, std::string("noise export: ") + cudaGetErrorString(e));
+  return GB_OK;
+}
+extern "C" int gb_philox_normals(uint64_t seed, uint32_t step, int64_t pid0, int64_t n, int ndraw, int dtype, double *out) {
+  return export_noise(seed, step, pid0, n, ndraw, dtype, 0, out);
+}
+extern "C" int gb_philox_uniforms(uint64_t seed, uint32_t step, int64_t pid0, int64_t n, int ndraw, int dtype, double *out) {
+  return export_noise(seed, step, pid0, n, ndraw, dtype, 1, out);
+}
+extern "C" uint32_t gb_philox_resample_u0(uint64_t seed, uint32_t step) { return philox_block(seed, 0, step, PK_RESAMPLE, 0).x; }
+extern "C" int gb_philox_multinomial_u64(uint64_t seed, uint32_t step, int64_t k0, int64_t n, uint64_t *out) {
+  REQ(out, "null argument");
+  for (int64_t i = 0; i < n; i++) {   // integer-only: identical on host and device
+    U4 w = philox_block(seed, (uint64_t)(k0 + i), step, PK_MULTI, 0);
+    out[i] = ((uint64_t)w.x << 32) | w.y;
+  }
+  return GB_OK;
+}
+extern "C" int gb_quant_bits(int64_t n_global) { return quant_bits(n_global); }
+
+// host-side evaluation of the exact-integer helpers the kernels use (so the CPU test-suite can check
+// them against Python big integers without a GPU); not part of the product path
+extern "C" int64_t gb_selftest_slots_below(uint64_t C, int64_t nslots, uint64_t q_total, uint32_t u0) {
+  SweepParams sp;
+  sp.q_total = q_total; sp.q_inv = 1.0 / (double)q_total; sp.dscale = (uint64_t)nslots << 32; sp.u0 = u0;
+  return slots_below(C, sp);
+}
+extern "C" int64_t gb_selftest_slots_below_residual(uint64_t chi, uint64_t clo, uint64_t q_total, uint32_t u0) {
+  SweepParams sp;
+  sp.q_total = q_total; sp.q_inv = 1.0 / (double)q_total; sp.dscale = 0; sp.u0 = u0;
+  return slots_below_residual(chi, clo, sp);
+}
+extern "C" uint64_t gb_selftest_div128(uint64_t ahi, uint64_t alo, uint64_t d) { return div128_64(ahi, alo, d, 1.0 / (double)d); }
+extern "C" uint64_t gb_selftest_quantize(double x, int bits) { return quantize(x, bits); }
+extern "C" void gb_selftest_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  U4 r = philox4x32_10(U4{ctr[0], ctr[1], ctr[2], ctr[3]}, key[0], key[1]);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// ------------------------------------------------------------------------------------------
+// batched distribution kernels
+// ------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(kBlock) dist_logpdf_kernel(int dist, long long n, const double *__restrict__ x, const double *__restrict__ a,
+                                                             int as, const double *__restrict__ b, int bs, int len, double logdet,
+                                                             double *__restrict__ out) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+    R r;
+    switch (dist) {
+      case GB_DIST_NORMAL: r = logpdf_normal<R>((R)x[i], (R)a[i * as], (R)b[i * bs]); break;
+      case GB_DIST_GAMMA: r = logpdf_gamma<R>((R)x[i], (R)a[i * as], (R)b[i * bs]); break;
+      case GB_DIST_BERNOULLI: r = logpdf_bernoulli<R>(x[i] != 0.0, (R)a[i * as]); break;
+      case GB_DIST_CATEGORICAL: r = logpdf_categorical<R>((long long)x[i], a, len); break;
+      default: {
+        R xv[kBlrMax];
+        for (int k = 0; k < len; k++) xv[k] = (R)x[i * len + k];
+        r = logpdf_mvnormal_chol<R, kBlrMax>(xv, a, b, logdet, len);
+      }
+    }
+    out[i] = (double)r;
+  }
+}
+template <typename R>
+__global__ void __launch_bounds__(kBlock) dist_random_kernel(int dist, long long n, const double *__restrict__ a, int as,
+                                                             const double *__restrict__ b, int bs, int len, unsigned long long seed,
+                                                             unsigned int step, double *__restrict__ out) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+    const unsigned long long pid = (unsigned long long)i;
+    switch (dist) {
+      case GB_DIST_NORMAL: {
+        R e0, e1;
+        philox_normal_pair(seed, pid, step, 0u, e0, e1);
+        out[i] = (double)random_normal<R>((R)a[i * as], (R)b[i * bs], e0);
+        break;
+      }
+      case GB_DIST_GAMMA: out[i] = (double)random_gamma_philox<R>((R)a[i * as], (R)b[i * bs], seed, pid, step); break;
+      case GB_DIST_BERNOULLI: {
+        R u0, u1;
+        philox_uniform_pair(seed, pid, step, 0u, u0, u1);
+        out[i] = random_bernoulli<R>((R)a[i * as], u0) ? 1.0 : 0.0;
+        break;
+      }
+      case GB_DIST_CATEGORICAL: {
+        R u0, u1;
+        philox_uniform_pair(seed, pid, step, 0u, u0, u1);
+        out[i] = (double)random_categorical<R>(a, len, u0);
+        break;
+      }
+      default: {   // mvnormal.jl:30-33: mu + L * randn(k)
+        R eps[kBlrMax];
+        for (int k = 0; k < len; k += 2) {
+          R e0, e1;
+          philox_normal_pair(seed, pid, step, (unsigned)(k / 2), e0, e1);
+          eps[k] = e0;
+          if (k + 1 < len) eps[k + 1] = e1;
+        }
+        for (int r = 0; r < len; r++) {
+          R s = (R)a[r];
+          for (int c = 0; c <= r; c++) s += (R)b[r * len + c] * eps[c];
+          out[i * len + r] = (double)s;
+        }
+      }
+    }
+  }
+}
+
+// lower Cholesky factor (row-major) of a symmetric positive definite matrix; returns logdet
+static bool host_cholesky(const double *cov, int k, std::vector<double> &L, double *logdet) {
+  L.assign((size_t)k * k, 0.0);
+  double ld = 0.0;
+  for (int j = 0; j < k; j++) {
+    double d = cov[j * k + j];
+    for (int p = 0; p < j; p++) d -= L[j * k + p] * L[j * k + p];
+    if (!(d > 0.0)) return false;
+    d = sqrt(d);
+    L[j * k + j] = d;
+    ld += 2.0 * log(d);
+    for (int i = j + 1; i < k; i++) {
+      double s = cov[i * k + j];
+      for (int p = 0; p < j; p++) s -= L[i * k + p] * L[j * k + p];
+      L[i * k + j] = s / d;
+    }
+  }
+  *logdet = ld;
+  return true;
+}
+
+static int dist_common(int dist, int dtype, int64_t n, const double *x, const double *a, int as, const double *b, int bs, int len,
+                       bool random, uint64_t seed, uint32_t step, double *out) {
+  REQ(out && n >= 1, "bad argument");
+  REQ(dist >= GB_DIST_NORMAL && dist <= GB_DIST_MVNORMAL, "unknown distribution");
+  int rc = require_gpu();
+  if (rc) return rc;
+  const bool vec = dist == GB_DIST_MVNORMAL;
+  if (dist == GB_DIST_CATEGORICAL || vec) REQ(len >= 1 && (!vec || len <= kBlrMax), "len out of range (mvnormal: k <= 64)");
+  size_t nx = (size_t)n * (vec ? len : 1);
+  size_t na = (dist == GB_DIST_CATEGORICAL || vec) ? (size_t)len : (as ? (size_t)n : 1);
+  size_t nb = vec ? (size_t)len * len : (b ? (bs ? (size_t)n : 1) : 0);
+  std::vector<double> L;
+  double logdet = 0.0;
+  const double *bsrc = b;
+  if (vec) {
+    REQ(b, "mvnormal needs a covariance");
+    if (!host_cholesky(b, len, L, &logdet)) return fail(GB_EINVAL, "mvnormal: covariance is not positive definite");
+    bsrc = L.data();
+  }
+  double *dx = nullptr, *da = nullptr, *db = nullptr, *dout = nullptr;
+  cudaError_t e = cudaSuccess;
+  size_t nout = random ? nx : (size_t)n;
+  if (!random) { e = cudaMalloc((void **)&dx, nx * 8); if (e == cudaSuccess) e = cudaMemcpy(dx, x, nx * 8, cudaMemcpyHostToDevice); }
+  if (e == cudaSuccess) e = cudaMalloc((void **)&da, na * 8);
+  if (e == cudaSuccess) e = cudaMemcpy(da, a, na * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nb) { e = cudaMalloc((void **)&db, nb * 8); if (e == cudaSuccess) e = cudaMemcpy(db, bsrc, nb * 8, cudaMemcpyHostToDevice); }
+  if (e == cudaSuccess) e = cudaMalloc((void **)&dout, nout * 8);
+  if (e == cudaSuccess) {
+    int grid = (int)std::min<long long>((n + kBlock - 1) / kBlock, 148 * 8);
+    const int as_ = (dist == GB_DIST_CATEGORICAL || vec) ? 0 : (as ? 1 : 0), bs_ = vec ? 0 : (bs ? 1 : 0);
+    const double *dbb = db ? db : da;   // bernoulli / categorical have no second parameter
+    if (random) {
+      if (dtype == GB_F64) dist_random_kernel<double><<<grid, kBlock>>>(dist, n, da, as_, dbb, bs_, len, seed, step, dout);
+      else dist_random_kernel<float><<<grid, kBlock>>>(dist, n, da, as_, dbb, bs_, len, seed, step, dout);
+    } else {
+      if (dtype == GB_F64) dist_logpdf_kernel<double><<<grid, kBlock>>>(dist, n, dx, da, as_, dbb, bs_, len, logdet, dout);
+      else dist_logpdf_kernel<float><<<grid, kBlock>>>(dist, n, dx, da, as_, dbb, bs_, len, logdet, dout);
+    }
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, nout * 8, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(da); cudaFree(db); cudaFree(dout);
+  if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_dist: ") + cudaGetErrorString(e));
+  return GB_OK;
+}
+extern "C" int gb_dist_logpdf(int dist, int dtype, int64_t n, const double *x, const double *a, int as, const double *b, int bs,
+                              int len, double *out) {
+  REQ(x && a, "null argument");
+  return dist_common(dist, dtype, n, x, a, as, b, bs, len, false, 0, 0, out);
+}
+extern "C" int gb_dist_random(int dist, int dtype, int64_t n, const double *a, int as, const double *b, int bs, int len,
+                              uint64_t seed, uint32_t step, double *out) {
+  REQ(a, "null argument");
+  return dist_common(dist, dtype, n, nullptr, a, as, b, bs, len, true, seed, step, out);
+}

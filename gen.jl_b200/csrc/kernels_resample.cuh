@@ -1,0 +1,522 @@
+// kernels_resample.cuh -- K4/K5: the resampling half of maybe_resample! (particle_filter.jl:249-275).
+//
+// The reference draws N multinomial ancestors with Distributions.jl's alias sampler
+// (particle_filter.jl:261-262).  Here all three resamplers (multinomial, systematic, residual) are
+// sweeps over an exact INTEGER CDF of fixed-point weights q_i = floor(exp(lw_i - max) * 2^b)
+// (SURVEY.md Appendix B), so ancestors are a pure function of (log weights, uniforms): independent of
+// the tiling, of the launch geometry and of how particles are sharded over GPUs, and bit-identical to
+// the sequential oracle.
+//
+// Passes (all HBM-streaming, tiles of kTile = 2048 particles, 256 threads x 8 items):
+//   qtotal    : read lw            -> per-tile sum of q                       (E bytes / particle)
+//   tilescan  : per-tile sums      -> exclusive tile CDF + first output slot of every tile (tiny)
+//   ancestors : read lw, block scan, per-particle offspring range by exact 128/64-bit division,
+//               merge-path style fill of the tile's output slots            (E + 4 bytes / particle)
+//   gather    : read ancestors + ancestor rows (monotone => near-coalesced), write rows, zero lw
+#pragma once
+#include "kernels_step.cuh"
+
+namespace gb {
+
+struct U128 { uint64_t lo, hi; };
+GB_HD U128 u128_add(U128 a, U128 b) {
+  U128 r;
+  r.lo = a.lo + b.lo;
+  r.hi = a.hi + b.hi + (r.lo < a.lo ? 1 : 0);
+  return r;
+}
+GB_HD U128 u128_make(uint64_t lo) { return U128{lo, 0}; }
+
+enum { SWEEP_SYSTEMATIC = 0, SWEEP_RESIDUAL = 1, SWEEP_CDF = 2 };
+
+// Everything the ancestors pass needs to know about the global sweep; written by tilescan.
+struct ResamplePlan {
+  SweepParams sp;
+  uint64_t q_offset;     // integer CDF mass of the shards before this one
+  long long slot_lo;     // first / one-past-last global output slot filled by this shard's particles
+  long long slot_hi;
+  long long n_global;
+};
+
+template <typename R> GB_D void load_items(const R *__restrict__ logw, long long base, long long n, double (&lw)[kItems]);
+template <> GB_D void load_items<double>(const double *__restrict__ logw, long long base, long long n, double (&lw)[kItems]) {
+  const long long i0 = base + (long long)threadIdx.x * kItems;
+#pragma unroll
+  for (int j = 0; j < kItems; j += 2) {
+    // arrays are padded to a multiple of kTile elements, so the vector load is always in bounds
+    double2 v = __ldcs(reinterpret_cast<const double2 *>(logw + i0 + j));
+    lw[j] = (i0 + j < n) ? v.x : -INFINITY;
+    lw[j + 1] = (i0 + j + 1 < n) ? v.y : -INFINITY;
+  }
+}
+template <> GB_D void load_items<float>(const float *__restrict__ logw, long long base, long long n, double (&lw)[kItems]) {
+  const long long i0 = base + (long long)threadIdx.x * kItems;
+#pragma unroll
+  for (int j = 0; j < kItems; j += 4) {
+    float4 v = __ldcs(reinterpret_cast<const float4 *>(logw + i0 + j));
+    lw[j] = (i0 + j < n) ? (double)v.x : -INFINITY;
+    lw[j + 1] = (i0 + j + 1 < n) ? (double)v.y : -INFINITY;
+    lw[j + 2] = (i0 + j + 2 < n) ? (double)v.z : -INFINITY;
+    lw[j + 3] = (i0 + j + 3 < n) ? (double)v.w : -INFINITY;
+  }
+}
+
+// ---- 64-bit / 128-bit block primitives built on warp shuffles ----
+GB_D uint64_t shfl_up_u64(uint64_t v, int d) {
+  uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d);
+  uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), d);
+  return ((uint64_t)hi << 32) | lo;
+}
+GB_D uint64_t shfl_u64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+  uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
+// exclusive block scan of one U128 per thread; returns the exclusive prefix, *total = block sum
+GB_D U128 block_exclusive_scan(U128 v, U128 *s_warp /* kBlock/32 + 1 */, U128 *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  U128 inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    U128 o;
+    o.lo = shfl_up_u64(inc.lo, d);
+    o.hi = shfl_up_u64(inc.hi, d);
+    if (lane >= d) inc = u128_add(inc, o);
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    U128 w = lane < kBlock / 32 ? s_warp[lane] : U128{0, 0};
+    U128 winc = w;
+#pragma unroll
+    for (int d = 1; d < kBlock / 32; d <<= 1) {
+      U128 o;
+      o.lo = shfl_up_u64(winc.lo, d);
+      o.hi = shfl_up_u64(winc.hi, d);
+      if (lane >= d) winc = u128_add(winc, o);
+    }
+    if (lane < kBlock / 32) {
+      // exclusive warp offset = inclusive - own
+      U128 ex;
+      ex.lo = winc.lo - w.lo;
+      ex.hi = winc.hi - w.hi - (winc.lo < w.lo ? 1 : 0);
+      s_warp[lane] = ex;
+    }
+    if (lane == kBlock / 32 - 1) s_warp[kBlock / 32] = winc;
+  }
+  __syncthreads();
+  U128 woff = s_warp[warp];
+  *total = s_warp[kBlock / 32];
+  U128 ex;
+  ex.lo = inc.lo - v.lo;
+  ex.hi = inc.hi - v.hi - (inc.lo < v.lo ? 1 : 0);
+  return u128_add(woff, ex);
+}
+// 64-bit flavour (systematic / multinomial CDF never exceeds 2^62)
+GB_D uint64_t block_exclusive_scan(uint64_t v, uint64_t *s_warp /* kBlock/32 + 1 */, uint64_t *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t o = shfl_up_u64(inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t w = lane < kBlock / 32 ? s_warp[lane] : 0;
+    uint64_t winc = w;
+#pragma unroll
+    for (int d = 1; d < kBlock / 32; d <<= 1) {
+      uint64_t o = shfl_up_u64(winc, d);
+      if (lane >= d) winc += o;
+    }
+    if (lane < kBlock / 32) s_warp[lane] = winc - w;
+    if (lane == kBlock / 32 - 1) s_warp[kBlock / 32] = winc;
+  }
+  __syncthreads();
+  *total = s_warp[kBlock / 32];
+  return s_warp[warp] + (inc - v);
+}
+
+// residual resampling: deterministic copies c = floor(N q / Q) and residual mass r = N q - c Q
+GB_D void residual_split(uint64_t q, long long n_global, uint64_t q_total, uint64_t &c, uint64_t &r) {
+  uint64_t nq = (uint64_t)n_global * q;   // <= 2^62 by the choice of the quantisation width
+  c = nq / q_total;
+  r = nq - c * q_total;
+}
+
+// ---- K4a: per-tile totals ----
+template <typename R, int SWEEP>
+__global__ void __launch_bounds__(kBlock) qtotal_kernel(const R *__restrict__ logw, long long n, double m, int bits,
+                                                        long long n_global, uint64_t q_total,
+                                                        uint64_t *__restrict__ tile_q, uint64_t *__restrict__ tile_c,
+                                                        U128 *__restrict__ tile_r) {
+  __shared__ U128 s_warp[kBlock / 32 + 1];
+  __shared__ uint64_t s_warp64[kBlock / 32 + 1];
+  const long long ntiles = (n + kTile - 1) / kTile;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    double lw[kItems];
+    load_items<R>(logw, tile * kTile, n, lw);
+    uint64_t sq = 0, sc = 0;
+    U128 sr = {0, 0};
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+      uint64_t q = quantize(lw[j] - m, bits);
+      if (SWEEP == SWEEP_RESIDUAL) {
+        uint64_t c, r;
+        residual_split(q, n_global, q_total, c, r);
+        sc += c;
+        sr = u128_add(sr, u128_make(r));
+      } else {
+        sq += q;
+      }
+    }
+    // block reduction through the scan helper (total only)
+    if (SWEEP == SWEEP_RESIDUAL) {
+      U128 tot, tot2;
+      block_exclusive_scan(sr, s_warp, &tot);
+      __syncthreads();
+      block_exclusive_scan(u128_make(sc), s_warp, &tot2);
+      if (threadIdx.x == 0) { tile_r[tile] = tot; tile_c[tile] = tot2.lo; }
+    } else {
+      uint64_t tot;
+      block_exclusive_scan(sq, s_warp64, &tot);
+      if (threadIdx.x == 0) tile_q[tile] = tot;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- tilescan: exclusive scan of the tile totals + first output slot of every tile ----
+// One CTA of 1024 threads (ntiles <= 2^31 / 2048 = 2^20, i.e. at most 1024 entries per thread).
+// tile_q/tile_c/tile_r are overwritten with their exclusive prefixes (ntiles + 1 entries each);
+// tile_slot[i] = first global output slot produced by tile i (ntiles + 1 entries).
+template <int SWEEP>
+__global__ void __launch_bounds__(1024) tilescan_kernel(long long ntiles, uint64_t *tile_q, uint64_t *tile_c, U128 *tile_r,
+                                                        long long *tile_slot, ResamplePlan *plan, uint64_t q_offset,
+                                                        uint64_t q_total_given, long long n_global, uint32_t u0, int write) {
+  __shared__ U128 s_part[1024 / 32 + 1];
+  __shared__ U128 s_part2[1024 / 32 + 1];
+  __shared__ SweepParams s_sp;
+  const int T = 1024;
+  const long long per = (ntiles + T - 1) / T;
+  const long long lo = (long long)threadIdx.x * per, hi = lo + per < ntiles ? lo + per : ntiles;
+  U128 a = {0, 0};
+  uint64_t ac = 0;
+  for (long long i = lo; i < hi; i++) {
+    if (SWEEP == SWEEP_RESIDUAL) { a = u128_add(a, tile_r[i]); ac += tile_c[i]; }
+    else a = u128_add(a, u128_make(tile_q[i]));
+  }
+  // block scan over 1024 thread sums (two-level: warp shuffles + shared)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto scan1024 = [&](U128 v, U128 *sh, U128 *total) -> U128 {
+    U128 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      U128 o;
+      o.lo = shfl_up_u64(inc.lo, d);
+      o.hi = shfl_up_u64(inc.hi, d);
+      if (lane >= d) inc = u128_add(inc, o);
+    }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      U128 w = sh[lane];
+      U128 winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        U128 o;
+        o.lo = shfl_up_u64(winc.lo, d);
+        o.hi = shfl_up_u64(winc.hi, d);
+        if (lane >= d) winc = u128_add(winc, o);
+      }
+      U128 ex;
+      ex.lo = winc.lo - w.lo;
+      ex.hi = winc.hi - w.hi - (winc.lo < w.lo ? 1 : 0);
+      sh[lane] = ex;
+      if (lane == 31) sh[32] = winc;
+    }
+    __syncthreads();
+    *total = sh[32];
+    U128 ex;
+    ex.lo = inc.lo - v.lo;
+    ex.hi = inc.hi - v.hi - (inc.lo < v.lo ? 1 : 0);
+    return u128_add(sh[warp], ex);
+  };
+  U128 tot, totc;
+  U128 ex = scan1024(a, s_part, &tot);
+  U128 exc = scan1024(u128_make(ac), s_part2, &totc);
+  if (threadIdx.x == 0) {
+    SweepParams sp;
+    if (SWEEP == SWEEP_RESIDUAL) sp.q_total = q_total_given;           // Q_N of the quantised weights
+    else sp.q_total = q_total_given ? q_total_given : tot.lo;          // single shard: Q_N = local total
+    sp.q_inv = 1.0 / (double)sp.q_total;
+    sp.dscale = (uint64_t)n_global << 32;
+    sp.u0 = u0;
+    s_sp = sp;
+  }
+  __syncthreads();
+  const SweepParams sp = s_sp;
+  auto slot_of = [&](const U128 &r, uint64_t c) -> long long {
+    if (SWEEP == SWEEP_RESIDUAL) return (long long)c + slots_below_residual(r.hi, r.lo, sp);
+    if (SWEEP == SWEEP_SYSTEMATIC) return slots_below(q_offset + r.lo, sp);
+    return 0;
+  };
+  if (write) {
+    U128 run = ex;
+    uint64_t runc = exc.lo;
+    for (long long i = lo; i < hi; i++) {
+      U128 val;
+      uint64_t valc = 0;
+      if (SWEEP == SWEEP_RESIDUAL) { val = tile_r[i]; valc = tile_c[i]; tile_r[i] = run; tile_c[i] = runc; }
+      else { val = u128_make(tile_q[i]); tile_q[i] = (SWEEP == SWEEP_CDF ? q_offset : 0) + run.lo; }
+      tile_slot[i] = slot_of(run, runc);
+      run = u128_add(run, val);
+      runc += valc;
+    }
+    if (threadIdx.x == 0) {
+      if (SWEEP == SWEEP_RESIDUAL) { tile_r[ntiles] = tot; tile_c[ntiles] = totc.lo; }
+      else tile_q[ntiles] = (SWEEP == SWEEP_CDF ? q_offset : 0) + tot.lo;
+      tile_slot[ntiles] = slot_of(tot, totc.lo);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    plan->sp = sp;
+    plan->q_offset = q_offset;
+    plan->n_global = n_global;
+    if (SWEEP == SWEEP_SYSTEMATIC) {
+      plan->slot_lo = slots_below(q_offset, sp);
+      plan->slot_hi = slots_below(q_offset + tot.lo, sp);
+    } else if (SWEEP == SWEEP_RESIDUAL) {
+      plan->slot_lo = 0;
+      plan->slot_hi = (long long)totc.lo + slots_below_residual(tot.hi, tot.lo, sp);
+    } else {
+      plan->slot_lo = 0;
+      plan->slot_hi = n_global;
+    }
+  }
+}
+
+// ---- K4b: per-tile scan -> offspring ranges -> ancestor fill ----
+// CTAs [0, ntiles) own one input tile each and fill at most kChunk of its output slots; CTAs
+// [ntiles, ntiles + n_over) own one kChunk-aligned range of output slots each and fill the part of it
+// that belongs to a heavy tile's overflow (at most one tile per range), so a degenerate weight vector
+// (one particle taking every slot) is still spread over the whole GPU.
+template <typename R, int SWEEP>
+__global__ void __launch_bounds__(kBlock) ancestors_kernel(const R *__restrict__ logw, long long n, double m, int bits,
+                                                           const uint64_t *__restrict__ tile_q,
+                                                           const uint64_t *__restrict__ tile_c,
+                                                           const U128 *__restrict__ tile_r,
+                                                           const long long *__restrict__ tile_slot,
+                                                           const ResamplePlan *__restrict__ plan, long long ntiles,
+                                                           long long over_base, int *__restrict__ anc, long long anc_base,
+                                                           uint64_t *__restrict__ cdf_out) {
+  __shared__ U128 s_warp[kBlock / 32 + 1];
+  __shared__ uint64_t s_warp64[kBlock / 32 + 1];
+  __shared__ uint32_t s_kend[kTile];
+  __shared__ long long s_tile, s_lo, s_hi;
+  const SweepParams sp = plan->sp;
+  const uint64_t q_offset = plan->q_offset;
+  const long long n_global = plan->n_global;
+
+  if (threadIdx.x == 0) {
+    long long tile, lo, hi;
+    if ((long long)blockIdx.x < ntiles) {
+      tile = blockIdx.x;
+      lo = tile_slot[tile];
+      hi = tile_slot[tile + 1];
+      if (hi > lo + kChunk) hi = lo + kChunk;
+    } else {
+      const long long a0 = over_base + ((long long)blockIdx.x - ntiles) * kChunk;
+      // tile whose slot range contains a0: last i with tile_slot[i] <= a0
+      long long l = 0, h = ntiles;      // invariant: tile_slot[l] <= a0 (or l == 0), tile_slot[h] > a0 (or h == ntiles)
+      if (a0 < tile_slot[0] || a0 >= tile_slot[ntiles]) { tile = 0; lo = hi = 0; }
+      else {
+        while (h - l > 1) {
+          long long mid = (l + h) >> 1;
+          if (tile_slot[mid] <= a0) l = mid; else h = mid;
+        }
+        tile = l;
+        lo = tile_slot[tile] + kChunk;
+        if (lo < a0) lo = a0;
+        hi = tile_slot[tile + 1];
+        if (hi > a0 + kChunk) hi = a0 + kChunk;
+      }
+    }
+    s_tile = tile; s_lo = lo; s_hi = hi;
+  }
+  __syncthreads();
+  const long long tile = s_tile, lo = s_lo, hi = s_hi;
+  if (SWEEP != SWEEP_CDF && lo >= hi) return;
+
+  double lw[kItems];
+  load_items<R>(logw, tile * kTile, n, lw);
+  const long long slot0 = tile_slot[tile];
+  if (SWEEP == SWEEP_RESIDUAL) {
+    uint64_t c[kItems];
+    U128 r[kItems];
+    uint64_t tc = 0;
+    U128 tr = {0, 0};
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+      uint64_t q = quantize(lw[j] - m, bits), rr;
+      residual_split(q, n_global, sp.q_total, c[j], rr);
+      tc += c[j];
+      tr = u128_add(tr, u128_make(rr));
+      c[j] = tc;
+      r[j] = tr;
+    }
+    U128 dummy;
+    uint64_t dummy64;
+    U128 exr = block_exclusive_scan(tr, s_warp, &dummy);
+    uint64_t exc = block_exclusive_scan(tc, s_warp64, &dummy64);
+    const U128 base_r = u128_add(tile_r[tile], exr);
+    const uint64_t base_c = tile_c[tile] + exc;
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+      U128 C = u128_add(base_r, r[j]);
+      long long kend = (long long)(base_c + c[j]) + slots_below_residual(C.hi, C.lo, sp);
+      s_kend[threadIdx.x * kItems + j] = (uint32_t)(kend - slot0);
+    }
+  } else {
+    uint64_t c[kItems];
+    uint64_t t = 0;
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+      t += quantize(lw[j] - m, bits);
+      c[j] = t;
+    }
+    uint64_t dummy64;
+    uint64_t ex = block_exclusive_scan(t, s_warp64, &dummy64);
+    const uint64_t base = tile_q[tile] + ex + (SWEEP == SWEEP_CDF ? 0 : q_offset);
+    if (SWEEP == SWEEP_CDF) {
+      // multinomial: materialise the inclusive integer CDF (tile_q already carries q_offset)
+      const long long i0 = tile * kTile + (long long)threadIdx.x * kItems;
+#pragma unroll
+      for (int j = 0; j < kItems; j++) cdf_out[i0 + j] = base + c[j];
+      return;
+    }
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+      long long kend = slots_below(base + c[j], sp);
+      s_kend[threadIdx.x * kItems + j] = (uint32_t)(kend - slot0);
+    }
+  }
+  __syncthreads();
+  // merge-path fill: slot k belongs to the first particle whose offspring range ends beyond k
+  const int base_particle = (int)(tile * kTile);
+  for (long long k = lo + threadIdx.x; k < hi; k += kBlock) {
+    const uint32_t rel = (uint32_t)(k - slot0);
+    int l = 0, h = kTile - 1;   // smallest j with s_kend[j] > rel (exists: s_kend[kTile-1] = tile slot count > rel)
+    while (l < h) {
+      int mid = (l + h) >> 1;
+      if (s_kend[mid] > rel) h = mid; else l = mid + 1;
+    }
+    anc[k - anc_base] = base_particle + l;
+  }
+}
+
+// ---- multinomial (reference semantics: N iid categorical draws in slot order) ----
+// tau_k = floor(U_k * Q_N / 2^64); ancestor = first particle whose inclusive CDF exceeds tau_k.
+// Two-level search: tile table (L2 resident), then the tile's 2048 CDF entries.
+__global__ void __launch_bounds__(kBlock) multinomial_kernel(const uint64_t *__restrict__ cdf, const uint64_t *__restrict__ tile_q,
+                                                             long long ntiles, long long n, const ResamplePlan *__restrict__ plan,
+                                                             const uint64_t *__restrict__ u64s, unsigned long long seed,
+                                                             unsigned int step, long long nslots, int *__restrict__ anc) {
+  const uint64_t qn = plan->sp.q_total;
+  for (long long k = (long long)blockIdx.x * kBlock + threadIdx.x; k < nslots; k += (long long)gridDim.x * kBlock) {
+    uint64_t u;
+    if (u64s) u = u64s[k];
+    else {
+      U4 w = philox_block(seed, (uint64_t)k, step, PK_MULTI, 0);
+      u = ((uint64_t)w.x << 32) | w.y;
+    }
+    const uint64_t tau = mulhi64(u, qn);
+    // last tile whose exclusive prefix is <= tau
+    long long l = 0, h = ntiles;
+    while (h - l > 1) {
+      long long mid = (l + h) >> 1;
+      if (__ldg(tile_q + mid) <= tau) l = mid; else h = mid;
+    }
+    long long a = l * kTile, b = a + kTile - 1;
+    if (b > n - 1) b = n - 1;
+    while (a < b) {
+      long long mid = (a + b) >> 1;
+      if (__ldg(cdf + mid) > tau) b = mid; else a = mid + 1;
+    }
+    anc[k] = (int)a;
+  }
+}
+
+// ---- K5: resampled trace gather (particle_filter.jl:264-267) ----
+template <typename R>
+__global__ void __launch_bounds__(kBlock) gather_kernel(const R *__restrict__ sin, R *__restrict__ sout, long long ld, int S,
+                                                        const int *__restrict__ anc, long long n, R *__restrict__ logw) {
+  constexpr int V = VecOf<R>::V;
+  const long long nvec = (n + V - 1) / V;
+  for (long long iv = (long long)blockIdx.x * kBlock + threadIdx.x; iv < nvec; iv += (long long)gridDim.x * kBlock) {
+    const long long i0 = iv * V;
+    int src[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) src[v] = (i0 + v < n) ? __ldcs(anc + i0 + v) : 0;
+    for (int s = 0; s < S; s++) {
+      R val[V];
+#pragma unroll
+      for (int v = 0; v < V; v++) val[v] = __ldg(sin + (long long)s * ld + src[v]);
+      vstore<R>(sout + (long long)s * ld + i0, val);
+    }
+    if (logw) {
+      R z[V];
+#pragma unroll
+      for (int v = 0; v < V; v++) z[v] = R(0);
+      vstore_keep<R>(logw + i0, z);
+    }
+  }
+}
+
+// gather for the sharded path: rows of slots [0, count) (ancestors anc[0..count)) into a compact
+// [S][count] buffer + int64 global parent ids
+template <typename R>
+__global__ void __launch_bounds__(kBlock) export_kernel(const R *__restrict__ sin, long long ld, int S, const int *__restrict__ anc,
+                                                        long long count, R *__restrict__ rows, long long *__restrict__ parents,
+                                                        long long pid_offset) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < count; i += (long long)gridDim.x * kBlock) {
+    const int src = __ldcs(anc + i);
+    for (int s = 0; s < S; s++) rows[(long long)s * count + i] = __ldg(sin + (long long)s * ld + src);
+    parents[i] = pid_offset + src + 1;   // Gen's parents are 1-based
+  }
+}
+template <typename R>
+__global__ void __launch_bounds__(kBlock) import_kernel(R *__restrict__ sout, long long ld, int S, long long dst_lo, long long count,
+                                                        const R *__restrict__ rows, const long long *__restrict__ parents_in,
+                                                        long long *__restrict__ parents) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < count; i += (long long)gridDim.x * kBlock) {
+    for (int s = 0; s < S; s++) sout[(long long)s * ld + dst_lo + i] = rows[(long long)s * count + i];
+    parents[dst_lo + i] = parents_in[i];
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kBlock) fill_kernel(R *__restrict__ p, long long n, R v) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) p[i] = v;
+}
+__global__ void __launch_bounds__(kBlock) iota_parents_kernel(long long *__restrict__ p, long long n, long long base) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) p[i] = base + i + 1;
+}
+__global__ void __launch_bounds__(kBlock) parents_from_anc_kernel(const int *__restrict__ anc, long long *__restrict__ p, long long n,
+                                                                  long long base) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
+    p[i] = base + anc[i] + 1;
+}
+template <typename R>
+__global__ void __launch_bounds__(kBlock) convert_out_kernel(const R *__restrict__ in, double *__restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) out[i] = (double)in[i];
+}
+template <typename R>
+__global__ void __launch_bounds__(kBlock) convert_in_kernel(const double *__restrict__ in, R *__restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) out[i] = (R)in[i];
+}
+
+}  // namespace gb

@@ -1,0 +1,178 @@
+/*
+ * genb200.h -- C ABI of libgenb200.so: the B200 (sm_100a) particle inference engine that sits
+ * behind Gen.jl's particle-filter / importance-sampling API.
+ *
+ * This is the `ccall` target of the Julia glue and of the Python ctypes host
+ * mirror in gen.jl_b200/.  Plain pointers and sizes only; every entry returns 0 on success or a
+ * non-zero GB_E* code with the message available from gb_last_error() (thread local), which
+ * replaces Julia's `error(...)` (src/inference/particle_filter.jl:227-229).  There is NO CPU
+ * fallback: every compute entry fails with GB_ENOGPU when no sm_100 device is usable.
+ *
+ * All file:line citations are relative to the reference checkout (probcomp/Gen.jl v0.4.8).
+ * Unless a parameter is documented as a DEVICE pointer it is a HOST pointer owned by the caller;
+ * the engine copies in/out.  Handles are not thread safe (one caller thread per handle).
+ */
+#ifndef GENB200_H
+#define GENB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { GB_OK = 0, GB_EINVAL = 1, GB_ENOGPU = 2, GB_ECUDA = 3, GB_EUNSUPPORTED = 4, GB_ESTATE = 5 };
+
+/* Supported model class: Unfold / Map / static-IR programs whose random
+ * choices are built-in distributions.  `params` layouts:
+ *   GB_MODEL_LGSSM    [m0, s0, a, q, r]            x0~normal(m0,s0); x_t~normal(a*x,q); y_t~normal(x_t,r)
+ *   GB_MODEL_SV       [mu, phi, sigma, sd0]        h0~normal(mu,sd0); h_t~normal(mu+phi*(h-mu),sigma); y~normal(0,exp(h/2))
+ *   GB_MODEL_BEARINGS [x0mu,x0sd,y0mu,y0sd,vx0mu,vx0sd,vy0mu,vy0sd, velocity_var, measurement_noise]
+ *                     (docs/src/tutorials/smc.md:607-661)
+ *   GB_MODEL_HMM      [K, M, prior[K], transition[K*K] (column = previous z), emission[M*K] (column = z)]
+ *                     (test/inference/particle_filter.jl:52-78; categorical choices, 1-based)
+ *   GB_MODEL_BLR      [D, n, sigma, X[n*D] row-major]   w~Map(normal)(0,1); y_j~normal(x_j.w, sigma)
+ */
+enum { GB_MODEL_LGSSM = 1, GB_MODEL_SV = 2, GB_MODEL_BEARINGS = 3, GB_MODEL_HMM = 4, GB_MODEL_BLR = 5 };
+/* Custom proposals (particle_filter.jl:118-134, :186-208; trace_translators.jl:836-856):
+ *   GB_PROPOSAL_AFFINE_NORMAL     pargs = [c0, c1, std]: x ~ normal(c0 + c1*x_prev, std)   (c1 unused at t=0)
+ *   GB_PROPOSAL_CATEGORICAL_TABLE pargs = K probs at t=0, K*K (column = previous z) afterwards */
+enum { GB_PROPOSAL_DEFAULT = 0, GB_PROPOSAL_AFFINE_NORMAL = 1, GB_PROPOSAL_CATEGORICAL_TABLE = 2 };
+/* particle_filter.jl:261-262 is multinomial; systematic / residual are the north-star extensions
+ * (exact integer-CDF definitions shared with the oracle). */
+enum { GB_RESAMPLE_MULTINOMIAL = 0, GB_RESAMPLE_SYSTEMATIC = 1, GB_RESAMPLE_RESIDUAL = 2 };
+enum { GB_F64 = 0, GB_F32 = 1 };
+/* distributions for the batched logpdf/random entries (modeling_library/distributions/*.jl) */
+enum { GB_DIST_NORMAL = 1, GB_DIST_GAMMA = 2, GB_DIST_BERNOULLI = 3, GB_DIST_CATEGORICAL = 4, GB_DIST_MVNORMAL = 5 };
+
+typedef struct gb_model gb_model_t;
+typedef struct gb_pf gb_pf_t;
+
+const char *gb_last_error(void);
+const char *gb_version(void);
+int gb_device_count(int *count);              /* 0 devices => *count = 0, returns GB_OK */
+int gb_set_device(int device);
+
+/* ---- model handles (replace GenerativeFunction objects of the supported class) ---- */
+int gb_model_create(int kind, const double *params, int nparams, gb_model_t **out);
+void gb_model_free(gb_model_t *m);
+int gb_model_state_dim(const gb_model_t *m);
+int gb_model_num_obs(const gb_model_t *m);
+int gb_model_num_normals(const gb_model_t *m, int proposal_kind, int is_init);
+int gb_model_num_uniforms(const gb_model_t *m, int proposal_kind, int is_init);
+
+/* ---- ParticleFilterState (particle_filter.jl:35-41) as a device-resident SoA store ---- */
+/* Allocate a shard of n_local particles with global ids [pid_offset, pid_offset+n_local) of an
+ * n_global-particle filter (single GPU: n_local == n_global, pid_offset == 0). */
+int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_global, int64_t pid_offset, int dtype,
+                 uint64_t seed, gb_pf_t **out);
+/* Validation mode: pre-drawn noise [nd][n_local] consumed by the NEXT generate/step call in place
+ * of the Philox stream (Gen has no RNG hook).  NULL / 0 clears. */
+int gb_pf_set_noise(gb_pf_t *pf, const double *normals, int n_normals, const double *uniforms, int n_uniforms);
+/* initialize_particle_filter (particle_filter.jl:118-134, :142-154): generate at t = 0. */
+int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int proposal_kind, const double *pargs, int npargs);
+/* create + generate in one call (the usual entry) */
+int gb_pf_initialize(const gb_model_t *m, int64_t n, int dtype, uint64_t seed, const double *obs, int nobs,
+                     int proposal_kind, const double *pargs, int npargs, gb_pf_t **out);
+/* particle_filter_step! (particle_filter.jl:186-208, :217-240), extend-by-one only (the reference's
+ * non-empty-discard error, :227-229, is unreachable by construction).  incr_out (n_local doubles,
+ * may be NULL) receives the log incremental weights the reference returns. */
+int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int proposal_kind, const double *pargs, int npargs,
+               double *incr_out);
+/* maybe_resample! (particle_filter.jl:249-275).  Single shard only (n_local == n_global).
+ * Resampling randomness: Philox(seed, step) unless gb_pf_set_resample_noise was called. */
+int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind, int *did_resample);
+/* validation mode for the resampler: u0 for systematic/residual, n u64 for multinomial (NULL clears) */
+int gb_pf_set_resample_noise(gb_pf_t *pf, int use_u0, uint32_t u0, const uint64_t *u64s);
+int gb_pf_log_ml_estimate(gb_pf_t *pf, double *out);                 /* particle_filter.jl:91-94 */
+int gb_pf_get_log_weights(gb_pf_t *pf, double *out_n);               /* :82-84 (unnormalised) */
+int gb_pf_set_log_weights(gb_pf_t *pf, const double *in_n);          /* tests poke .log_weights (:176-197) */
+int gb_pf_get_parents(gb_pf_t *pf, int64_t *out_n);                  /* :40, 1-based, global ids */
+int gb_pf_get_state(gb_pf_t *pf, int field, double *out_n);          /* column `field` of the traces */
+int gb_pf_get_log_ml_est(gb_pf_t *pf, double *out);                  /* the .log_ml_est field (:39) */
+int gb_pf_get_ess(gb_pf_t *pf, double *ess_out, double *lse_out);    /* particle_filter.jl:3-12 */
+int gb_pf_num_particles(const gb_pf_t *pf, int64_t *n_local, int64_t *n_global);
+int gb_pf_step_index(const gb_pf_t *pf, int *step);
+int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out);                         /* Base.copy (:43-51) */
+void gb_pf_free(gb_pf_t *pf);
+/* 0 = eager gather inside maybe_resample!, 1 (default) = the resampled-trace gather is deferred and
+ * fused into the next particle_filter_step! (materialised on any read of the state). */
+int gb_pf_set_lazy_gather(gb_pf_t *pf, int lazy);
+/* All launches of this handle go to `cuda_stream` (a cudaStream_t; NULL = legacy default stream). */
+int gb_pf_set_stream(gb_pf_t *pf, void *cuda_stream);
+int gb_pf_sync(gb_pf_t *pf);
+
+/* ---- sharded (one process per GPU) pieces of maybe_resample!; the host glue runs the collectives
+ *      between them (gen.jl_b200/sharded.py).  All scalars are host values. ---- */
+/* local online log-sum-exp partials of the shard: m = max, s1 = sum exp(lw-m), s2 = sum exp(2(lw-m)) */
+int gb_pf_weight_partials(gb_pf_t *pf, double *m, double *s1, double *s2);
+/* local total of the integer-quantised weights floor(exp(lw - m_global) * 2^bits) */
+int gb_pf_quantized_total(gb_pf_t *pf, double m_global, int bits, uint64_t *q_local);
+/* Offspring of this shard's particles under global-prefix systematic resampling: the shard's
+ * particles fill the global slot range [*slot_lo, *slot_hi).  Ancestors (global ids) for that range
+ * are kept in the handle for gb_pf_export_offspring. */
+int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits, uint64_t q_offset, uint64_t q_total,
+                               uint32_t u0, int64_t *slot_lo, int64_t *slot_hi);
+/* Gather rows for global slots [k_lo, k_hi) (inside the shard's offspring range) into DEVICE buffers:
+ * dev_rows = S columns of (k_hi-k_lo) elements of the filter dtype, dev_parents = int64 global ids. */
+int gb_pf_export_offspring(gb_pf_t *pf, int64_t k_lo, int64_t k_hi, void *dev_rows, void *dev_parents);
+/* Install rows for local slots [dst_lo, dst_lo+count) of the NEW trace buffer from DEVICE buffers of
+ * the same layout; gb_pf_commit_resample then swaps buffers, zeroes the log weights and adds
+ * log_ml_increment to log_ml_est (particle_filter.jl:263-272). */
+int gb_pf_import_rows(gb_pf_t *pf, int64_t dst_lo, int64_t count, const void *dev_rows, const void *dev_parents);
+int gb_pf_commit_resample(gb_pf_t *pf, double log_ml_increment);
+
+/* ---- importance_sampling (importance.jl:20-59) ---- */
+/* lognormw_out: n doubles (may be NULL); lml_out: log ML estimate; pf_out (may be NULL) receives the
+ * particle store (traces + unnormalised log weights).  normals/uniforms: validation noise or NULL. */
+int gb_importance_sampling(const gb_model_t *m, int64_t n, int dtype, uint64_t seed, const double *obs, int nobs,
+                           int proposal_kind, const double *pargs, int npargs, const double *normals,
+                           int n_normals, const double *uniforms, int n_uniforms, double *lognormw_out,
+                           double *lml_out, gb_pf_t **pf_out);
+
+/* ---- resampling on raw log-weight arrays (config 5 microbenchmark; same kernels as maybe_resample!) ----
+ * Host-buffer form: ancestors are 0-based int64. u64s only for multinomial (NULL => Philox(seed, step)). */
+int gb_resample(const double *logw, int64_t n, int dtype, int kind, uint32_t u0, const uint64_t *u64s,
+                uint64_t seed, uint32_t step, int64_t *anc_out);
+/* Device-resident form for benchmarking: dev_logw (n elements of dtype), dev_anc (n int32), dev_u64
+ * (n uint64 or NULL).  Workspace is cached per thread.  Asynchronous on cuda_stream. */
+int gb_resample_device(const void *dev_logw, int64_t n, int dtype, int kind, uint32_t u0, const void *dev_u64,
+                       uint64_t seed, uint32_t step, void *dev_anc, void *cuda_stream);
+/* logsumexp / ESS of a raw array (inference.jl:3-6, particle_filter.jl:3-12) */
+int gb_logsumexp(const double *a, int64_t n, int dtype, double *lse_out, double *ess_out);
+
+/* ---- batched distribution kernels (modeling_library/distributions/{normal,gamma,bernoulli,
+ *      categorical,mvnormal}.jl logpdf + random) ----
+ * x, a, b: n elements each (a/b broadcast when a_stride/b_stride == 0).  categorical: a = probs[len],
+ * x integer-valued; mvnormal: x is [n][k] row-major, a = mu[k], b = cov[k*k], k = len. */
+int gb_dist_logpdf(int dist, int dtype, int64_t n, const double *x, const double *a, int a_stride, const double *b,
+                   int b_stride, int len, double *out);
+/* draws n values with the engine's Philox stream (seed, step, pid = 0..n-1) */
+int gb_dist_random(int dist, int dtype, int64_t n, const double *a, int a_stride, const double *b, int b_stride,
+                   int len, uint64_t seed, uint32_t step, double *out);
+
+/* ---- the engine's counter-based noise, exported so the oracle can consume identical draws ---- */
+int gb_philox_normals(uint64_t seed, uint32_t step, int64_t pid0, int64_t n, int ndraw, int dtype, double *out);
+int gb_philox_uniforms(uint64_t seed, uint32_t step, int64_t pid0, int64_t n, int ndraw, int dtype, double *out);
+uint32_t gb_philox_resample_u0(uint64_t seed, uint32_t step);         /* host-side integer, no GPU */
+int gb_philox_multinomial_u64(uint64_t seed, uint32_t step, int64_t k0, int64_t n, uint64_t *out);
+int gb_quant_bits(int64_t n_global);                                   /* host-side, no GPU */
+
+/* ---- instrumentation for bench.py: per-kernel CUDA-event timings on the handle's stream ---- */
+enum { GB_K_STEP = 0, GB_K_FINALIZE = 1, GB_K_QTOTAL = 2, GB_K_TILESCAN = 3, GB_K_ANCESTORS = 4, GB_K_GATHER = 5,
+       GB_K_MISC = 6, GB_K_COUNT = 7 };
+int gb_pf_enable_timing(gb_pf_t *pf, int on);
+/* ms[GB_K_COUNT], launches[GB_K_COUNT]; resets the accumulators */
+int gb_pf_get_timing(gb_pf_t *pf, double *ms, int64_t *launches);
+const char *gb_kernel_name(int k);
+
+/* ---- internal test hooks: HOST-side evaluation of the exact-integer helpers the kernels use, so the
+ *      CPU-only test suite can check them against Python big integers (not part of the product path) ---- */
+int64_t gb_selftest_slots_below(uint64_t C, int64_t nslots, uint64_t q_total, uint32_t u0);
+int64_t gb_selftest_slots_below_residual(uint64_t chi, uint64_t clo, uint64_t q_total, uint32_t u0);
+uint64_t gb_selftest_div128(uint64_t ahi, uint64_t alo, uint64_t d);
+uint64_t gb_selftest_quantize(double x, int bits);
+void gb_selftest_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

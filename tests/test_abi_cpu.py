@@ -1,0 +1,161 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol include/genb200.h declares,
+fails loudly without a GPU (no CPU fallback), and its exact-integer helpers (the host-side instances
+of the device functions) agree with Python big integers and with the oracle."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "genb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(g):
+    from genb200 import _lib as L
+    lib = C.CDLL(g.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 50
+    for name in names:
+        assert hasattr(lib, name), "libgenb200.so does not export %s" % name
+        assert name in L.SIGNATURES, "ctypes binding is missing %s" % name
+    assert sorted(L.SIGNATURES) == names
+
+
+def test_no_cpu_fallback(g):
+    """Without a GPU every compute entry must fail with GB_ENOGPU -- never compute on the host."""
+    if g.device_count() > 0:
+        pytest.skip("GPU present")
+    from genb200 import _lib as L
+    m = g.lgssm_model()
+    with pytest.raises(g.GenB200Error) as ei:
+        g.initialize_particle_filter(m, (0,), 0.3, 100)
+    assert ei.value.code == L.ENOGPU
+    with pytest.raises(g.GenB200Error):
+        g.resample(np.zeros(10))
+    with pytest.raises(g.GenB200Error):
+        g.logpdf("normal", [0.0], [0.0], [1.0])
+    with pytest.raises(g.GenB200Error):
+        g.importance_sampling(m, (0,), 0.3, 10)
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gen.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                for line in open(os.path.join(dirpath, f)):
+                    if re.search(r"#\s*include|\bimport\b|CDLL|dlopen|sys\.path", line):
+                        assert "oracle" not in line.lower(), (f, line)
+
+
+def test_model_validation(g):
+    from genb200 import _lib as L
+    with pytest.raises(g.GenB200Error) as ei:
+        g.DeviceModel(99, [1.0], "bogus")
+    assert ei.value.code == L.EUNSUPPORTED
+    with pytest.raises(g.GenB200Error):
+        g.DeviceModel(L.MODEL_LGSSM, [1.0, 2.0], "short")
+    m = g.bearings_model()
+    assert m.state_dim == 4 and m.num_obs == 1 and m.num_normals(True) == 4 and m.num_normals(False) == 2
+    h = g.hmm_model([0.5, 0.5], np.eye(2), np.eye(2))
+    assert h.state_dim == 1 and h.num_uniforms(False) == 1
+
+
+def test_philox_matches_oracle_and_known_answer(g, O):
+    from genb200 import _lib as L
+    lib = L.lib()
+    # Random123 known-answer vectors for philox4x32-10
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kats:
+        c = (C.c_uint32 * 4)(*ctr)
+        k = (C.c_uint32 * 2)(*key)
+        o = (C.c_uint32 * 4)()
+        lib.gb_selftest_philox(c, k, o)
+        assert tuple(o) == exp
+        assert tuple(O.philox(ctr, key)) == exp
+    rnd = random.Random(1)
+    for _ in range(200):
+        seed, step = rnd.getrandbits(64), rnd.getrandbits(32)
+        assert lib.gb_philox_resample_u0(seed, step) == O.lib().go_philox_resample_u0(seed, step)
+    a = g.philox_multinomial_u64(12345, 7, 1000, 257)
+    assert np.array_equal(a, O.philox_multinomial_u64(12345, 7, 1000, 257))
+
+
+def test_quantize_matches_oracle(g, O):
+    from genb200 import _lib as L
+    lib = L.lib()
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([-np.abs(rng.standard_normal(2000)) * 10, [-0.0, 0.0, -1e-300, -707.9, -708.0, -709.0, -1e9,
+                                                                    -np.inf, np.nan, 1.0]])
+    for b in (31, 35, 42, 52):
+        for x in xs:
+            assert lib.gb_selftest_quantize(float(x), b) == O.lib().go_quantize(float(x), b), (x, b)
+    for n in (1, 2, 3, 1000, 10 ** 6, 10 ** 8, 2 ** 30, 2 ** 31 - 1):
+        assert lib.gb_quant_bits(n) == O.lib().go_quant_bits(n)
+
+
+def test_div128_exact(g):
+    from genb200 import _lib as L
+    lib = L.lib()
+    rnd = random.Random(7)
+    for _ in range(20000):
+        dbits = rnd.randint(31, 62)
+        d = rnd.getrandbits(dbits) | (1 << (dbits - 1))
+        qbits = rnd.randint(1, 62)
+        q = rnd.getrandbits(qbits)
+        r = rnd.randrange(d) if rnd.random() < 0.8 else rnd.choice([0, d - 1])
+        a = q * d + r
+        assert lib.gb_selftest_div128(a >> 64, a & (2 ** 64 - 1), d) == q, (a, d)
+
+
+def test_slots_below_matches_bigint_definition(g):
+    """#{k : floor((k 2^32 + u0) Q / (N 2^32)) < C} -- the device's closed form vs brute force / big ints."""
+    from genb200 import _lib as L
+    lib = L.lib()
+    rnd = random.Random(3)
+    # brute force on small N
+    for _ in range(300):
+        n = rnd.randint(1, 40)
+        Q = rnd.getrandbits(rnd.randint(32, 62)) | (1 << 31)
+        u0 = rnd.getrandbits(32)
+        taus = [((k << 32) + u0) * Q // (n << 32) for k in range(n)]
+        for C_ in [0, 1, Q, Q // 2, Q - 1] + [rnd.randrange(Q + 1) for _ in range(10)] + taus[:5] + [t + 1 for t in taus[:5]]:
+            C_ = min(C_, Q)
+            assert lib.gb_selftest_slots_below(C_, n, Q, u0) == sum(1 for t in taus if t < C_)
+    # closed form with big ints on large N
+    for _ in range(5000):
+        n = rnd.randint(1, 2 ** 31 - 1)
+        lg = max(0, (n - 1).bit_length())
+        Q = rnd.randrange(1 << 31, (1 << 62) + 1 if lg == 0 else (n << (62 - lg)) + 1)
+        Q = min(Q, 1 << 62)
+        u0 = rnd.getrandbits(32)
+        C_ = rnd.randrange(Q + 1)
+        if C_ == 0:
+            exp = 0
+        else:
+            X = (C_ * (n << 32) - 1) // Q
+            exp = 0 if X < u0 else ((X - u0) >> 32) + 1
+        assert lib.gb_selftest_slots_below(C_, n, Q, u0) == exp
+    # residual sweep: tau_k = floor((k 2^32 + u0) Q / 2^32), C up to R*Q < 2^93
+    for _ in range(5000):
+        Q = rnd.getrandbits(rnd.randint(32, 62)) | (1 << 31)
+        R = rnd.randint(1, 2 ** 31 - 1)
+        C_ = rnd.randrange(R * Q + 1)
+        u0 = rnd.getrandbits(32)
+        if C_ == 0:
+            exp = 0
+        else:
+            X = ((C_ << 32) - 1) // Q
+            exp = 0 if X < u0 else ((X - u0) >> 32) + 1
+        assert lib.gb_selftest_slots_below_residual(C_ >> 64, C_ & (2 ** 64 - 1), Q, u0) == exp

@@ -1,0 +1,476 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): ancestor indices and resampled states bit-exact on shared pre-drawn
+noise; log weights / log-ML within 1e-10 relative in fp64 and 1e-5 in fp32; log-ML also against the
+exact Kalman / HMM-forward values.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import fixtures as F
+
+pytestmark = pytest.mark.gpu
+
+RTOL64, RTOL32 = 1e-10, 1e-5
+
+
+def close(a, b, rtol):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.all(np.abs(a - b) <= rtol * np.maximum(1.0, np.abs(b)) + 0.0) or np.array_equal(a, b)
+
+
+def okind(O, name):
+    return {"multinomial": O.RESAMPLE_MULTINOMIAL, "systematic": O.RESAMPLE_SYSTEMATIC, "residual": O.RESAMPLE_RESIDUAL}[name]
+
+
+# ---------------------------------------------------------------------------------------------
+# noise, distributions, logsumexp
+# ---------------------------------------------------------------------------------------------
+def test_philox_noise_matches_oracle_spec(g, O):
+    a = g.philox_normals(99, 3, 1000, 5000, 4)
+    b = O.philox_normals(99, 3, 1000, 5000, 4)
+    assert np.max(np.abs(a - b)) < 1e-13            # same integers, libm-level differences only
+    assert abs(a.mean()) < 0.03 and abs(a.std() - 1) < 0.03
+    u = g.philox_uniforms(99, 3, 1000, 5000, 2)
+    assert np.array_equal(u, O.philox_uniforms(99, 3, 1000, 5000, 2))   # exact: integer -> fp64
+    f = g.philox_normals(99, 3, 0, 200000, 2, dtype="f32")
+    assert abs(f.mean()) < 0.01 and abs(f.std() - 1) < 0.01 and np.all(np.isfinite(f))
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 2e-5)])
+def test_distribution_logpdfs(g, O, dtype, tol):
+    rng = np.random.default_rng(0)
+    n = 4096
+    L = O.lib()
+    x, mu, sd = rng.standard_normal(n) * 3, rng.standard_normal(n), np.exp(rng.standard_normal(n))
+    ref = np.array([L.go_logpdf_normal(*t) for t in zip(x, mu, sd)])
+    assert close(g.logpdf("normal", x, mu, sd, dtype=dtype), ref, tol)
+    if dtype == "f64":
+        assert g.logpdf("normal", [1e13], [0.0], [1.0])[0] == -5e25          # distributions.jl:109
+    xs, k, th = np.exp(rng.standard_normal(n)), np.exp(rng.standard_normal(n)), np.exp(rng.standard_normal(n))
+    xs[:5] = [-1.0, 0.0, -3.0, 1.0, 2.0]
+    ref = np.array([L.go_logpdf_gamma(*t) for t in zip(xs, k, th)])
+    got = g.logpdf("gamma", xs, k, th, dtype=dtype)
+    assert np.all(got[:3] == -np.inf) and close(got[3:], ref[3:], tol * 10)   # distributions.jl:73
+    xb, p = (rng.random(n) < 0.5).astype(float), rng.random(n) * 0.98 + 0.01
+    ref = np.array([L.go_logpdf_bernoulli(int(a), b) for a, b in zip(xb, p)])
+    assert close(g.logpdf("bernoulli", xb, p, dtype=dtype), ref, tol)
+    probs = np.array([0.2, 0.3, 0.5])
+    xc = np.array([-1, 0, 1, 2, 3, 4], dtype=float)
+    got = g.logpdf("categorical", xc, probs, dtype=dtype)
+    assert got[0] == -np.inf and got[1] == -np.inf and got[5] == -np.inf       # distributions.jl:50
+    assert close(got[2:5], np.log(probs), tol)
+    kdim = 7
+    A = rng.standard_normal((kdim, kdim))
+    cov = A @ A.T + kdim * np.eye(kdim)
+    m = rng.standard_normal(kdim)
+    xv = rng.standard_normal((257, kdim))
+    ref = np.array([O.logpdf_mvnormal(r, m, cov) for r in xv])
+    assert close(g.logpdf("mvnormal", xv, m, cov, dtype=dtype), ref, tol * 10)
+
+
+def test_distribution_samplers(g, O):
+    n = 200000
+    a = g.random("normal", n, [1.5], [2.0], seed=5)
+    assert abs(a.mean() - 1.5) < 0.03 and abs(a.std() - 2.0) < 0.03
+    # normal = mu + std * eps with the exported Philox eps (normal.jl:128), bit exact
+    eps = g.philox_normals(5, 0, 0, n, 1)[0]
+    assert np.array_equal(a, 1.5 + 2.0 * eps)
+    b = g.random("bernoulli", n, [0.3], seed=6)
+    assert abs(b.mean() - 0.3) < 0.01
+    u = g.philox_uniforms(6, 0, 0, n, 1)[0]
+    assert np.array_equal(b, (u < 0.3).astype(float))                          # bernoulli.jl:19
+    c = g.random("categorical", n, [0.2, 0.3, 0.5], seed=7)
+    assert np.all((c >= 1) & (c <= 3))                                         # distributions.jl:46-47
+    assert np.allclose(np.bincount(c.astype(int), minlength=4)[1:] / n, [0.2, 0.3, 0.5], atol=0.01)
+    u = g.philox_uniforms(7, 0, 0, n, 1)[0]
+    L = O.lib()
+    pr = np.array([0.2, 0.3, 0.5])
+    ref = np.array([L.go_random_categorical(pr.ctypes.data_as(O._dp), 3, x) for x in u[:2000]])
+    assert np.array_equal(c[:2000], ref)
+    gm = g.random("gamma", n, [2.5], [1.5], seed=8)
+    assert np.all(gm > 0) and abs(gm.mean() - 2.5 * 1.5) < 0.05 and abs(gm.var() - 2.5 * 1.5 ** 2) < 0.2
+    ref = np.array([L.go_random_gamma_philox(2.5, 1.5, 8, i, 0) for i in range(500)])
+    assert np.allclose(gm[:500], ref, rtol=1e-12)
+    gs = g.random("gamma", n, [0.4], [2.0], seed=9)
+    assert np.all(gs > 0) and abs(gs.mean() - 0.8) < 0.03                      # shape < 1 branch
+    cov = np.array([[2.0, 0.6], [0.6, 1.0]])
+    mv = g.random("mvnormal", n, [1.0, -1.0], cov, seed=10)
+    assert np.allclose(mv.mean(axis=0), [1.0, -1.0], atol=0.02) and np.allclose(np.cov(mv.T), cov, atol=0.03)
+
+
+@pytest.mark.parametrize("n", [1, 4, 1000, 300001])
+def test_logsumexp_and_ess(g, O, n):
+    rng = np.random.default_rng(n)
+    a = 5.0 * rng.standard_normal(n) - 700.0
+    lse = g.logsumexp(a)
+    assert abs(lse - O.logsumexp(a)) <= RTOL64 * abs(O.logsumexp(a))
+    _, lnw = O.normalize_weights(a)
+    ess = g.effective_sample_size_from_logw(a)
+    assert abs(ess - O.effective_sample_size(lnw)) <= 1e-9 * ess
+    assert g.logsumexp(np.full(n, -np.inf)) == -np.inf                          # inference.jl:5
+    if n == 4:
+        # test/inference/importance_sampling.jl:21: logsumexp(log_norm_weights) ~ 0 @ 1e-14
+        assert abs(g.logsumexp(lnw)) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------------
+# resampling kernels on raw weights (config 5 shapes)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 7, 2047, 2048, 2049, 8192, 8193, 100003, 1 << 20])
+@pytest.mark.parametrize("shape", ["normal", "equal", "onehot"])
+def test_resamplers_bit_exact(g, O, n, shape):
+    lw = F.resample_logw(n, shape)
+    if shape == "onehot" and n > 3:
+        lw = np.roll(lw, n // 3)           # the heavy particle in the middle of a tile
+    rng = np.random.default_rng(n)
+    u0 = int(rng.integers(0, 2 ** 32))
+    for kind in ("systematic", "residual"):
+        got = g.resample(lw, kind, u0=u0)
+        exp = O.resample(okind(O, kind), lw, u0=u0)
+        assert np.array_equal(got, exp), (kind, np.flatnonzero(got != exp)[:5])
+    us = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+    got = g.resample(lw, "multinomial", u64s=us)
+    assert np.array_equal(got, O.resample(O.RESAMPLE_MULTINOMIAL, lw, u64s=us))
+    # Philox-keyed multinomial uniforms are integer-exact on both sides
+    got = g.resample(lw, "multinomial", seed=17, step=3)
+    assert np.array_equal(got, O.resample(O.RESAMPLE_MULTINOMIAL, lw, u64s=O.philox_multinomial_u64(17, 3, 0, n)))
+
+
+@pytest.mark.parametrize("n", [5, 4099, 1 << 18])
+def test_resamplers_fp32_weights(g, O, n):
+    lw = F.resample_logw(n, "normal").astype(np.float32).astype(np.float64)
+    for kind in ("systematic", "residual"):
+        assert np.array_equal(g.resample(lw, kind, u0=77, dtype="f32"), O.resample(okind(O, kind), lw, u0=77))
+
+
+def test_resampler_edge_weights(g, O):
+    n = 5000
+    lw = F.resample_logw(n, "normal")
+    lw[::3] = -np.inf                       # zero-weight particles never get offspring
+    lw[10] = -800.0                         # below the quantisation floor
+    got = g.resample(lw, "systematic", u0=5)
+    assert np.array_equal(got, O.resample(O.RESAMPLE_SYSTEMATIC, lw, u0=5))
+    assert not np.any(np.isin(got, np.arange(0, n, 3)))
+    with pytest.raises(g.GenB200Error):
+        g.resample(np.full(100, -np.inf), "systematic")
+    # extreme u0 values
+    for u0 in (0, 2 ** 32 - 1):
+        assert np.array_equal(g.resample(lw, "systematic", u0=u0), O.resample(O.RESAMPLE_SYSTEMATIC, lw, u0=u0))
+        assert np.array_equal(g.resample(lw, "residual", u0=u0), O.resample(O.RESAMPLE_RESIDUAL, lw, u0=u0))
+
+
+def test_resampler_properties_large(g):
+    """Size-independent properties at a size the sequential oracle is too slow for."""
+    n = 10 ** 7
+    lw = F.resample_logw(n, "normal")
+    w = np.exp(lw - lw.max())
+    w /= w.sum()
+    for kind in ("systematic", "residual"):
+        anc = g.resample(lw, kind, u0=123456789)
+        assert anc.min() >= 0 and anc.max() < n and np.all(np.diff(anc) >= 0)           # sortedness
+        cnt = np.bincount(anc, minlength=n)
+        assert cnt.sum() == n
+        assert np.max(np.abs(cnt - n * w)) < 1.0 + 1e-3                                  # |offspring - N w| < 1
+    anc = g.resample(lw, "multinomial", seed=1, step=2)
+    cnt = np.bincount(anc, minlength=n)
+    top = np.argsort(w)[-1000:]
+    assert abs(cnt[top].sum() - n * w[top].sum()) < 6 * math.sqrt(n * w[top].sum())     # unbiased counts
+    # idempotence: resampling equal weights with systematic is the identity permutation
+    assert np.array_equal(g.resample(np.zeros(n), "systematic", u0=999), np.arange(n))
+
+
+# ---------------------------------------------------------------------------------------------
+# particle filter: validation mode (pre-drawn noise), all models
+# ---------------------------------------------------------------------------------------------
+def model_zoo(g, O):
+    return {
+        "lgssm": (g.lgssm_model(**F.LGSSM), O.MODEL_LGSSM, F.lgssm_params(), F.lgssm_series(12), None, None),
+        "lgssm_affine": (g.lgssm_model(**F.LGSSM), O.MODEL_LGSSM, F.lgssm_params(), F.lgssm_series(12),
+                         g.AffineNormalProposal(), O.PROPOSAL_AFFINE_NORMAL),
+        "sv": (g.sv_model(**F.SV), O.MODEL_SV, F.sv_params(), F.sv_series(12), None, None),
+        "bearings": (g.bearings_model(), O.MODEL_BEARINGS, F.BEARINGS_PARAMS, F.bearings_series(12), None, None),
+        "hmm": (g.hmm_model(F.HMM_PRIOR, F.HMM_TRANSITION, F.HMM_EMISSION), O.MODEL_HMM, F.hmm_params(),
+                np.array([1, 1, 2, 3, 3, 1, 2, 2, 1, 3, 1, 2], dtype=float), None, None),
+        "hmm_table": (g.hmm_model(F.HMM_PRIOR, F.HMM_TRANSITION, F.HMM_EMISSION), O.MODEL_HMM, F.hmm_params(),
+                      np.array([1, 1, 2, 3, 3, 1, 2, 2, 1, 3, 1, 2], dtype=float),
+                      g.CategoricalTableProposal(), O.PROPOSAL_CATEGORICAL_TABLE),
+    }
+
+
+def proposal_args(name, t, obs, ys):
+    """(engine proposal_args, oracle pargs) for step t."""
+    if name == "lgssm_affine":
+        # locally optimal Gaussian proposal for the LGSSM: precision-weighted mean of prior and likelihood
+        a, q, r = F.LGSSM["a"], F.LGSSM["q"], F.LGSSM["r"]
+        s0 = F.LGSSM["s0"]
+        pv = (s0 if t == 0 else q) ** 2
+        k = pv / (pv + r * r)
+        c0, c1, sd = k * obs, (0.0 if t == 0 else (1 - k) * a), math.sqrt((1 - k) * pv)
+        return (c0, c1, sd), [c0, c1, sd]
+    if name == "hmm_table":
+        tab = F.hmm_init_proposal(int(obs)) if t == 0 else F.hmm_step_proposal(int(obs))
+        return (tab,), tab.ravel(order="F")
+    return (), None
+
+
+@pytest.mark.parametrize("name", ["lgssm", "lgssm_affine", "sv", "bearings", "hmm", "hmm_table"])
+@pytest.mark.parametrize("resampler", ["systematic", "residual", "multinomial"])
+@pytest.mark.parametrize("lazy", [True, False])
+def test_pf_predrawn_noise_bit_exact(g, O, name, resampler, lazy):
+    model, okind_m, params, ys, prop, opk = model_zoo(g, O)[name]
+    n = 3001                                   # ragged: not a multiple of the vector width or the tile
+    rng = np.random.default_rng(hash((name, resampler)) % 2 ** 32)
+    nn0, nu0 = model.num_normals(True), model.num_uniforms(True)
+    nn1, nu1 = model.num_normals(False), model.num_uniforms(False)
+    st = g.create_particle_filter(model, n)
+    st.set_lazy_gather(lazy)
+    eps, us = rng.standard_normal((max(nn0, 1), n)), rng.random((max(nu0, 1), n))
+    pa, opa = proposal_args(name, 0, ys[0], ys)
+    st.set_noise(eps if nn0 else None, us if nu0 else None)
+    g.generate_(st, ys[0], prop, pa)
+    ref = O.OraclePF.init(okind_m, params, n, [ys[0]], proposal_kind=opk or 0, pargs=opa,
+                          normals=eps if nn0 else None, uniforms=us if nu0 else None)
+    assert close(st.log_weights, ref.log_weights, RTOL64)
+    nres = 0
+    for t in range(1, len(ys)):
+        u0 = int(rng.integers(0, 2 ** 32))
+        u64 = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
+        thr = n if t % 3 else n / 2            # mix "always" and ESS-triggered resampling
+        st.set_resample_noise(u0=u0, u64s=u64 if resampler == "multinomial" else None)
+        did = g.maybe_resample_(st, ess_threshold=thr, resampler=resampler)
+        did_ref = ref.maybe_resample(ess_threshold=thr, kind=okind(O, resampler), u0=u0, u64s=u64)
+        assert did == did_ref
+        nres += did
+        if t % 4 == 0:                         # reading between resample and step forces materialisation
+            assert np.array_equal(st.parents, ref.parents)
+            assert np.array_equal(st.get_state(0), ref.state(0))
+            assert np.array_equal(st.log_weights, ref.log_weights)
+        eps, us = rng.standard_normal((max(nn1, 1), n)), rng.random((max(nu1, 1), n))
+        pa, opa = proposal_args(name, t, ys[t], ys)
+        st.set_noise(eps if nn1 else None, us if nu1 else None)
+        incr, = g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], prop, pa)
+        incr_ref = ref.step([ys[t]], proposal_kind=opk or 0, pargs=opa, normals=eps if nn1 else None,
+                            uniforms=us if nu1 else None)
+        assert len(incr) == n                                                    # particle_filter.jl test :137
+        assert close(incr, incr_ref, RTOL64)
+        for f in range(model.state_dim):
+            assert np.array_equal(st.get_state(f), ref.state(f)), (t, f)         # resampled states bit-exact
+        assert close(st.log_weights, ref.log_weights, RTOL64)
+        assert abs(st.log_ml_est - ref.log_ml_est) <= RTOL64 * max(1.0, abs(ref.log_ml_est))
+    assert nres >= 3
+    assert np.array_equal(st.parents, ref.parents)                               # ancestors bit-exact (1-based)
+    lml, lml_ref = g.log_ml_estimate(st), ref.log_ml_estimate()
+    assert abs(lml - lml_ref) <= RTOL64 * max(1.0, abs(lml_ref))
+
+
+@pytest.mark.parametrize("name", ["lgssm", "sv", "bearings", "hmm"])
+def test_pf_philox_mode_matches_oracle_on_exported_noise(g, O, name):
+    """Production mode: the engine draws from its counter-based Philox stream; the same draws, exported
+    through the ABI, are replayed through the oracle."""
+    model, okind_m, params, ys, _, _ = model_zoo(g, O)[name]
+    n, seed = 50000, 4242
+    st = g.initialize_particle_filter(model, (0,), ys[0], n, seed=seed)
+    nn0, nu0 = model.num_normals(True), model.num_uniforms(True)
+    nn1, nu1 = model.num_normals(False), model.num_uniforms(False)
+    ref = O.OraclePF.init(okind_m, params, n, [ys[0]],
+                          normals=g.philox_normals(seed, 0, 0, n, nn0) if nn0 else None,
+                          uniforms=g.philox_uniforms(seed, 0, 0, n, nu0) if nu0 else None)
+    for t in range(1, 8):
+        did = g.maybe_resample_(st, resampler="systematic")
+        did_ref = ref.maybe_resample(kind=O.RESAMPLE_SYSTEMATIC, u0=g.philox_resample_u0(seed, t - 1))
+        assert did == did_ref
+        g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t])
+        ref.step([ys[t]], normals=g.philox_normals(seed, t, 0, n, nn1) if nn1 else None,
+                 uniforms=g.philox_uniforms(seed, t, 0, n, nu1) if nu1 else None)
+    for f in range(model.state_dim):
+        assert np.array_equal(st.get_state(f), ref.state(f))
+    assert np.array_equal(st.parents, ref.parents)
+    assert close(st.log_weights, ref.log_weights, RTOL64)
+    assert abs(g.log_ml_estimate(st) - ref.log_ml_estimate()) <= RTOL64 * abs(ref.log_ml_estimate())
+
+
+@pytest.mark.parametrize("name", ["lgssm", "sv", "bearings"])
+def test_pf_fp32_mode(g, O, name):
+    """fp32 store and arithmetic: log weights / log-ML within 1e-5 relative of the fp64 oracle on the
+    same (fp32-representable) noise, resampling forced to follow the oracle's ancestors."""
+    model, okind_m, params, ys, _, _ = model_zoo(g, O)[name]
+    n = 20000
+    rng = np.random.default_rng(3)
+    nn0, nn1 = model.num_normals(True), model.num_normals(False)
+    st = g.create_particle_filter(model, n, dtype="f32")
+    eps = rng.standard_normal((nn0, n)).astype(np.float32).astype(np.float64)
+    st.set_noise(eps)
+    g.generate_(st, ys[0])
+    ref = O.OraclePF.init(okind_m, params, n, [ys[0]], normals=eps)
+    assert close(st.log_weights, ref.log_weights, RTOL32 * 20)
+    for t in range(1, 6):
+        # keep both sides on the same ancestors: feed the engine's fp32 log weights to the oracle
+        ref.log_weights = st.log_weights
+        st.set_resample_noise(u0=1234 + t)
+        did = g.maybe_resample_(st, ess_threshold=n, resampler="systematic")
+        did_ref = ref.maybe_resample(ess_threshold=n, kind=O.RESAMPLE_SYSTEMATIC, u0=1234 + t)
+        assert did and did_ref
+        assert np.array_equal(st.parents, ref.parents)                          # integer CDF: exact in fp32 too
+        eps = rng.standard_normal((nn1, n)).astype(np.float32).astype(np.float64)
+        st.set_noise(eps)
+        incr, = g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t])
+        incr_ref = ref.step([ys[t]], normals=eps)
+        # per-particle weights: fp32 state error is amplified by the likelihood's curvature
+        assert np.max(np.abs(incr - incr_ref) / np.maximum(1.0, np.abs(incr_ref))) < 2e-3
+        lml, lml_ref = g.log_ml_estimate(st), ref.log_ml_estimate()
+        assert abs(lml - lml_ref) <= RTOL32 * max(1.0, abs(lml_ref)) * 10
+        # resync the oracle's state so errors do not compound through the nonlinear dynamics
+        for f in range(model.state_dim):
+            s = st.get_state(f)
+            np.ctypeslib.as_array(O.lib().go_pf_state(ref._p, f), shape=(n,))[:] = s
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own end-to-end tests
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("custom", [True, False])
+@pytest.mark.parametrize("resampler", ["multinomial", "systematic", "residual"])
+def test_reference_hmm_particle_filter(g, custom, resampler):
+    """test/inference/particle_filter.jl:96-170: N = 20000, ess_threshold = N, atol = 0.02 against the
+    HMM forward algorithm (-4.87645083351704)."""
+    model = g.hmm_model(F.HMM_PRIOR, F.HMM_TRANSITION, F.HMM_EMISSION)
+    n, obs = 20000, F.HMM_OBS
+    prop = g.CategoricalTableProposal() if custom else None
+    if custom:
+        st = g.initialize_particle_filter(model, (1,), {"x_init": obs[0]}, prop, (F.hmm_init_proposal(obs[0]),), n, seed=1)
+    else:
+        st = g.initialize_particle_filter(model, (1,), {"x_init": obs[0]}, n, seed=1)
+    for T in range(2, len(obs) + 1):
+        g.maybe_resample_(st, ess_threshold=n, resampler=resampler)
+        pargs = (F.hmm_step_proposal(obs[T - 1]),) if custom else ()
+        incr, = g.particle_filter_step_(st, (T,), (g.UnknownChange,), {("chain", T - 1, "x"): obs[T - 1]}, prop, pargs)
+        assert len(incr) == n
+    assert abs(g.log_ml_estimate(st) - F.HMM_EXPECTED_LOG_ML) < 0.02
+    z = st.get_state(0)
+    assert np.all((z >= 1) & (z <= 3))
+
+
+def test_non_extension_step_is_an_error(g):
+    # particle_filter.jl:227-229: a step that would touch existing choices is rejected
+    st = g.initialize_particle_filter(g.lgssm_model(), (0,), 0.1, 100)
+    g.particle_filter_step_(st, (1,), (g.UnknownChange,), 0.2)
+    with pytest.raises(g.GenB200Error):
+        g.particle_filter_step_(st, (1,), (g.UnknownChange,), 0.2)
+    with pytest.raises(g.GenB200Error):
+        g.particle_filter_step_(st, (5,), (g.UnknownChange,), 0.2)
+
+
+def test_kalman_exact_log_ml(g, O):
+    """cfg 1: N = 1000, T = 100, systematic resampling, 32 filter seeds vs the exact Kalman log-ML."""
+    ys = F.lgssm_series(101)
+    kf = O.kalman_logml(F.LGSSM["m0"], F.LGSSM["s0"], F.LGSSM["a"], F.LGSSM["q"], F.LGSSM["r"], ys)
+    model = g.lgssm_model(**F.LGSSM)
+    ests = []
+    for seed in range(32):
+        st = g.initialize_particle_filter(model, (0,), ys[0], 1000, seed=seed)
+        for t in range(1, len(ys)):
+            g.maybe_resample_(st, resampler="systematic")
+            g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+        ests.append(g.log_ml_estimate(st))
+    ests = np.array(ests)
+    se = ests.std(ddof=1) / math.sqrt(len(ests))
+    # E[log Z_hat] <= log Z (Jensen): allow the O(var/2) bias on top of 4 standard errors
+    assert abs(ests.mean() - kf) < 4 * se + 0.5 * ests.var() + 0.02, (ests.mean(), kf, se)
+    # a large filter is very close
+    st = g.initialize_particle_filter(model, (0,), ys[0], 1 << 20, seed=99)
+    for t in range(1, len(ys)):
+        g.maybe_resample_(st, resampler="systematic")
+        g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+    assert abs(g.log_ml_estimate(st) - kf) < 0.02
+
+
+# ---------------------------------------------------------------------------------------------
+# importance sampling
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [("f64", RTOL64), ("f32", 2e-4)])
+def test_importance_sampling_blr(g, O, dtype, tol):
+    X, y, sigma = F.blr_problem(D=64, n=64)
+    n = 4096
+    rng = np.random.default_rng(8)
+    eps = rng.standard_normal((64, n))
+    if dtype == "f32":
+        eps = eps.astype(np.float32).astype(np.float64)
+    model = g.blr_model(X, sigma)
+    traces, lnw, lml = g.importance_sampling(model, (X,), y, n, dtype=dtype, normals=eps)
+    pf, lnw_ref, lml_ref = O.importance_sampling(O.MODEL_BLR, F.blr_params(X, sigma), n, y, normals=eps)
+    assert len(traces) == n and len(lnw) == n
+    if dtype == "f64":
+        assert abs(g.logsumexp(lnw)) < 1e-12                                    # importance_sampling.jl:21
+        for d in (0, 17, 63):
+            assert np.array_equal(traces.column(d), pf.state(d))
+        assert close(lnw, lnw_ref, 1e-9)
+    assert abs(lml - lml_ref) <= tol * abs(lml_ref)
+
+
+def test_importance_sampling_small_models(g, O):
+    # test/inference/importance_sampling.jl:18-34 shapes (N = 4), default and custom proposal
+    m = g.lgssm_model(**F.LGSSM)
+    for prop, pargs, opk, opa in [(None, (), 0, None), (g.AffineNormalProposal(), (0.1, 0.0, 0.8), O.PROPOSAL_AFFINE_NORMAL, [0.1, 0.0, 0.8])]:
+        eps = np.random.default_rng(1).standard_normal((1, 4))
+        args = (m, (0,), 0.3) + ((prop, pargs, 4) if prop else (4,))
+        traces, lnw, lml = g.importance_sampling(*args, normals=eps)
+        pf, lnw_ref, lml_ref = O.importance_sampling(O.MODEL_LGSSM, F.lgssm_params(), 4, [0.3], proposal_kind=opk, pargs=opa, normals=eps)
+        assert len(traces) == 4 and len(lnw) == 4 and not math.isnan(lml)
+        assert abs(g.logsumexp(lnw)) < 1e-14
+        assert close(lnw, lnw_ref, RTOL64) and abs(lml - lml_ref) < 1e-12
+        assert np.array_equal(traces.column(0), pf.state(0))
+
+
+def test_importance_sampling_conjugate_evidence(g, O):
+    # low-dimensional problem where prior importance sampling converges: exact conjugate evidence
+    X, y, sigma = F.blr_problem(D=3, n=8, sigma=1.0)
+    exact = O.blr_log_evidence(X, y, sigma)
+    _, _, lml = g.importance_sampling(g.blr_model(X, sigma), (X,), y, 2_000_000, seed=5, return_traces=False)
+    assert abs(lml - exact) < 0.05, (lml, exact)
+
+
+# ---------------------------------------------------------------------------------------------
+# ParticleFilterState semantics
+# ---------------------------------------------------------------------------------------------
+def test_pf_state_copy_and_fields(g):
+    # test/inference/particle_filter.jl:172-198
+    m = g.lgssm_model()
+    st = g.initialize_particle_filter(m, (0,), 0.1, 1000, seed=3)
+    assert np.array_equal(st.parents, np.arange(1, 1001)) and st.log_ml_est == 0.0
+    c = st.copy()
+    assert c == st and c is not st
+    g.particle_filter_step_(st, (1,), (g.UnknownChange,), 0.2)
+    assert not (c == st)
+    lw = np.linspace(-3, 0, 1000)
+    c.log_weights = lw
+    assert np.array_equal(c.log_weights, lw)
+    assert abs(g.log_ml_estimate(c) - (math.log(np.exp(lw).sum()) - math.log(1000))) < 1e-12
+    # lazily gathered state is materialised by copy()
+    g.maybe_resample_(st, ess_threshold=1000, resampler="systematic")
+    c2 = st.copy()
+    assert c2 == st and np.all(c2.log_weights == 0.0)
+    assert st.log_ml_est != 0.0 and c2.log_ml_est == st.log_ml_est
+
+
+def test_all_minus_inf_weights(g):
+    # SURVEY.md section 8a edge semantics: lse = -Inf, ESS = NaN, no resample, log_ml_estimate = -Inf
+    st = g.initialize_particle_filter(g.lgssm_model(), (0,), 0.1, 64)
+    st.log_weights = np.full(64, -np.inf)
+    assert g.maybe_resample_(st, ess_threshold=64) is False
+    assert g.log_ml_estimate(st) == -np.inf
+    assert np.array_equal(st.parents, np.arange(1, 65))
+
+
+def test_determinism(g):
+    def run():
+        st = g.initialize_particle_filter(g.bearings_model(), (0,), 1.56, 100000, seed=11)
+        zs = F.bearings_series(6)
+        for t in range(1, 6):
+            g.maybe_resample_(st, resampler="systematic")
+            g.particle_filter_step_(st, (t,), (g.UnknownChange,), zs[t])
+        return st.get_state(0), st.log_weights, st.parents
+    a, b = run(), run()
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
