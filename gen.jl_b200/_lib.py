@@ -59,8 +59,8 @@ SIGNATURES = {
     "gb_pf_set_lazy_gather": (i, [vp, i]),
     "gb_pf_set_stream": (i, [vp, vp]),
     "gb_pf_sync": (i, [vp]),
-    "gb_pf_weight_partials": (i, [vp, dp, dp, dp]),
-    "gb_pf_quantized_total": (i, [vp, d, i, u64p]),
+    "gb_pf_weight_max": (i, [vp, dp]),
+    "gb_pf_weight_sums": (i, [vp, d, i, dp, dp, u64p]),
     "gb_pf_systematic_offspring": (i, [vp, d, i, u64, u64, u32, i64p, i64p]),
     "gb_pf_export_offspring": (i, [vp, i64, i64, vp, vp]),
     "gb_pf_import_rows": (i, [vp, i64, i64, vp, vp]),
@@ -83,6 +83,7 @@ SIGNATURES = {
     "gb_selftest_slots_below_residual": (i64, [u64, u64, u64, u32]),
     "gb_selftest_div128": (u64, [u64, u64, u64]),
     "gb_selftest_quantize": (u64, [d, i]),
+    "gb_selftest_math": (d, [i, d, d]),
     "gb_selftest_philox": (None, [u32p, u32p, u32p]),
 }
 

@@ -69,26 +69,6 @@ GB_HD double u52(uint32_t hi, uint32_t lo) {
 // 24-bit uniform strictly inside (0,1); exact in fp32
 GB_HD float u24(uint32_t w) { return ((float)(w >> 8) + 0.5f) * 0x1p-24f; }
 
-// fp64 noise: one Philox block -> one Box-Muller pair (oracle: philox_normal_pair)
-GB_D void philox_normal_pair(uint64_t seed, uint64_t pid, uint32_t step, uint32_t pair, double &n0, double &n1) {
-  U4 w = philox_block(seed, pid, step, PK_NORMAL, pair);
-  double u1 = u52(w.x, w.y), u2 = u52(w.z, w.w);
-  double r = sqrt(-2.0 * log(u1));
-  double s, c;
-  sincospi(2.0 * u2, &s, &c);
-  n0 = r * c;
-  n1 = r * s;
-}
-// fp32 noise: the same block and the same 52-bit uniforms, transformed in single precision
-GB_D void philox_normal_pair(uint64_t seed, uint64_t pid, uint32_t step, uint32_t pair, float &n0, float &n1) {
-  U4 w = philox_block(seed, pid, step, PK_NORMAL, pair);
-  float u1 = u24(w.x), u2 = u24(w.z);
-  float r = sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  sincospif(2.0f * u2, &s, &c);
-  n0 = r * c;
-  n1 = r * s;
-}
 GB_D void philox_uniform_pair(uint64_t seed, uint64_t pid, uint32_t step, uint32_t pair, double &a, double &b) {
   U4 w = philox_block(seed, pid, step, PK_UNIFORM, pair);
   a = u52(w.x, w.y);
@@ -227,6 +207,7 @@ struct SweepParams {
   uint64_t q_total;   // Q_N
   double q_inv;       // 1.0 / (double)Q_N
   uint64_t dscale;    // nslots << 32 (regular) ; unused for residual
+  double ratio;       // (double)nslots / (double)Q_N: slots per unit of integer CDF mass
   uint32_t u0;
 };
 // number of slots k with tau_k < C  (regular sweep; C <= Q_N < 2^62, dscale < 2^63)
@@ -239,6 +220,16 @@ GB_HD int64_t slots_below(uint64_t C, const SweepParams &sp) {
   uint64_t X = div128_64(ahi, alo, sp.q_total, sp.q_inv);
   if (X < sp.u0) return 0;
   return (int64_t)((X - sp.u0) >> 32) + 1;
+}
+// Same count through a double-precision estimate, falling back to the exact division only when the
+// estimate lands within 2^-17 slots of a slot boundary (probability ~1.5e-5 per call): slot coordinate
+// y = (C*D/Q - u0) / 2^32, count = ceil(y) for y > 0.  |estimate - y| <= y * 2^-50 <= 2^-19.
+GB_HD int64_t slots_below_fast(uint64_t C, const SweepParams &sp) {
+  const double y = fma((double)C, sp.ratio, -(double)sp.u0 * 0x1p-32);
+  const double c = ceil(y);
+  if (y < -0x1p-17) return 0;
+  if (c - y > 0x1p-17 && y - (c - 1.0) > 0x1p-17) return (int64_t)c;
+  return slots_below(C, sp);
 }
 // residual sweep: C is a 128-bit CDF value (< 2^92): A = (C << 32) - 1
 GB_HD int64_t slots_below_residual(uint64_t chi, uint64_t clo, const SweepParams &sp) {

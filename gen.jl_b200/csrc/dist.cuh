@@ -2,12 +2,16 @@
 // (src/modeling_library/distributions/{normal,gamma,bernoulli,categorical,mvnormal}.jl).
 // Templated on the arithmetic type R (double = reference precision, float = fp32 mode).
 #pragma once
-#include "common.cuh"
+#include "gbmath.cuh"
 
 namespace gb {
 
 template <typename R> struct Math;
 template <> struct Math<double> {
+  // hot-loop versions (csrc/gbmath.cuh): constant-bank coefficients + shared-memory tables
+  static GB_D double log_t(double x, const MathTables &T) { return gb_log(x, T); }
+  static GB_D double exp_t(double x) { return gb_exp(x); }
+  static GB_D double atan2_t(double y, double x, const MathTables &T) { return gb_atan2(y, x, T); }
   static GB_D double log_(double x) { return log(x); }
   static GB_D double exp_(double x) { return exp(x); }
   static GB_D double sqrt_(double x) { return sqrt(x); }
@@ -18,6 +22,9 @@ template <> struct Math<double> {
   static GB_D double log2pi() { return kLog2Pi; }
 };
 template <> struct Math<float> {
+  static GB_D float log_t(float x, const MathTables &) { return logf(x); }
+  static GB_D float exp_t(float x) { return expf(x); }
+  static GB_D float atan2_t(float y, float x, const MathTables &) { return atan2f(y, x); }
   static GB_D float log_(float x) { return logf(x); }
   static GB_D float exp_(float x) { return expf(x); }
   static GB_D float sqrt_(float x) { return sqrtf(x); }
@@ -38,6 +45,13 @@ template <typename R> GB_D R logpdf_normal_ls(R x, R mu, R std, R log_std) {
   R z = (x - mu) / std;
   return -(z * z + Math<R>::log2pi()) / R(2) - log_std;
 }
+// hot-loop form: z = (x - mu) * (1/std) with the reciprocal hoisted by the caller.  Differs from the
+// reference's division by <= 1 ulp of z, far inside the 1e-10 log-weight tolerance; the state arithmetic
+// (random_normal) is untouched, so resampled states stay bit-exact.
+template <typename R> GB_D R logpdf_normal_fast(R x, R mu, R inv_std, R log_std) {
+  R z = (x - mu) * inv_std;
+  return -(z * z + Math<R>::log2pi()) / R(2) - log_std;
+}
 // normal.jl:128:  mu + std * randn()   (two roundings: -fmad=false)
 template <typename R> GB_D R random_normal(R mu, R std, R eps) { return mu + std * eps; }
 
@@ -53,6 +67,11 @@ template <typename R> GB_D bool random_bernoulli(R p, R u) { return u < p; }
 // categorical.jl:10-12 (x is 1-based); probs are always fp64 tables
 template <typename R> GB_D R logpdf_categorical(long long x, const double *__restrict__ probs, int len) {
   return (x > 0 && x <= len) ? Math<R>::log_((R)__ldg(probs + (x - 1))) : Math<R>::neg_inf();
+}
+template <typename R> GB_D R logpdf_categorical_t(long long x, const double *__restrict__ probs, int len, const MathTables &T) {
+  if (!(x > 0 && x <= len)) return Math<R>::neg_inf();
+  const double p = __ldg(probs + (x - 1));
+  return p > 0x1p-1000 ? Math<R>::log_t((R)p, T) : Math<R>::log_((R)p);   // log(0) = -Inf via libm
 }
 // categorical.jl:20-22: single draw = inverse-CDF linear scan (oracle go_random_categorical)
 template <typename R> GB_D long long random_categorical(const double *__restrict__ probs, int len, R u) {

@@ -5,6 +5,7 @@
 // There is no CPU fallback anywhere in this file: every compute entry needs a CUDA device and
 // fails with GB_ENOGPU otherwise.
 #include "../../include/genb200.h"
+#include "gbmath.cuh"
 #include "kernels_resample.cuh"
 
 #include <algorithm>
@@ -135,7 +136,10 @@ extern "C" int gb_model_num_uniforms(const gb_model_t *m, int, int) { return m ?
 // ------------------------------------------------------------------------------------------
 // particle store
 // ------------------------------------------------------------------------------------------
-enum WState { W_STATS = 0, W_ZERO = 1, W_DIRTY = 2 };
+// what is known about the current log weights
+//   W_STATS: h_stats (m, s1, s2, lse, ess, q_total) valid on the host     W_MAX: d_stats->m valid on the device
+//   W_ZERO : all log weights are exactly 0.0 (just resampled)             W_DIRTY: nothing known
+enum WState { W_STATS = 0, W_ZERO = 1, W_DIRTY = 2, W_MAX = 3 };
 
 struct TimedLaunch { int k; cudaEvent_t a, b; };
 
@@ -158,7 +162,8 @@ struct gb_pf {
   bool parents64_valid = false;
   double log_ml_est = 0.0;
   int wstate = W_DIRTY;
-  Lse3 *partials = nullptr;
+  double2 *partials = nullptr;     // per-CTA partials (running max as double, or (s1, s2))
+  bool tiles_valid = false;        // tile_q / super_q hold the quantised mass of the current weights w.r.t. h_stats->m
   unsigned int *ticket = nullptr;
   WeightStats *d_stats = nullptr, *h_stats = nullptr;
   // validation noise
@@ -173,6 +178,10 @@ struct gb_pf {
   uint64_t *tile_q = nullptr, *tile_c = nullptr;
   U128 *tile_r = nullptr;
   long long *tile_slot = nullptr;
+  unsigned long long *super_q = nullptr, *super_excl = nullptr;
+  long long nsuper = 0;
+  OverflowEntry *oflow = nullptr;
+  unsigned int *oflow_count = nullptr;
   ResamplePlan *d_plan = nullptr, *h_plan = nullptr;
   uint64_t *cdf = nullptr;
   int *off_anc = nullptr;         // sharded: ancestors of the shard's offspring range
@@ -189,8 +198,8 @@ struct gb_pf {
   long long launches[GB_K_COUNT] = {0};
 };
 
-static const char *kKernelNames[GB_K_COUNT] = {"step(propose+weight+lse)", "lse_finalize", "qtotal", "tilescan",
-                                               "ancestors", "gather", "misc"};
+static const char *kKernelNames[GB_K_COUNT] = {"step(gather+propose+weight+max)", "weight_stats(lse+ess+qtotals)", "qtotal(residual)",
+                                               "tilescan", "ancestors", "gather", "misc"};
 extern "C" const char *gb_kernel_name(int k) { return (k >= 0 && k < GB_K_COUNT) ? kKernelNames[k] : "?"; }
 
 static cudaEvent_t get_event(gb_pf *pf) {
@@ -236,6 +245,7 @@ static void pf_release(gb_pf *pf) {
   cudaFree(pf->state[0]); cudaFree(pf->state[1]); cudaFree(pf->logw); cudaFree(pf->incr); cudaFree(pf->anc);
   cudaFree(pf->parents64); cudaFree(pf->partials); cudaFree(pf->ticket); cudaFree(pf->d_stats);
   cudaFreeHost(pf->h_stats); cudaFree(pf->d_normals); cudaFree(pf->d_uniforms); cudaFree(pf->d_u64);
+  cudaFree(pf->super_q); cudaFree(pf->super_excl); cudaFree(pf->oflow); cudaFree(pf->oflow_count);
   cudaFree(pf->tile_q); cudaFree(pf->tile_c); cudaFree(pf->tile_r); cudaFree(pf->tile_slot); cudaFree(pf->d_plan);
   cudaFreeHost(pf->h_plan); cudaFree(pf->cdf); cudaFree(pf->off_anc); cudaFree(pf->d_tab); cudaFree(pf->d_ptab);
   for (auto &t : pf->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -245,6 +255,17 @@ static void pf_release(gb_pf *pf) {
 extern "C" void gb_pf_free(gb_pf_t *pf) { pf_release(pf); }
 
 static const int kMaxPartials = 148 * 16 + 64;
+
+// workspace of the systematic pipeline: super-tile totals / prefixes and the overflow queue
+static cudaError_t alloc_sys_workspace(gb_pf *pf) {
+  pf->nsuper = (pf->ntiles + kSuper - 1) / kSuper;
+  cudaError_t e = cudaMalloc((void **)&pf->super_q, (size_t)(pf->nsuper + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->super_excl, (size_t)(pf->nsuper + 1) * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->oflow, (size_t)(pf->n_global / kChunk + 2) * sizeof(OverflowEntry));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->oflow_count, 64);
+  if (e == cudaSuccess) e = cudaMemset(pf->oflow_count, 0, 64);
+  return e;
+}
 
 extern "C" int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_global, int64_t pid_offset, int dtype,
                             uint64_t seed, gb_pf_t **out) {
@@ -279,7 +300,7 @@ extern "C" int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_glob
   if (e == cudaSuccess) e = A(&pf->logw, col, true);
   if (e == cudaSuccess) e = A(&pf->incr, col, true);
   if (e == cudaSuccess) e = A((void **)&pf->anc, (size_t)pf->ld * 4, true);
-  if (e == cudaSuccess) e = A((void **)&pf->partials, sizeof(Lse3) * kMaxPartials, true);
+  if (e == cudaSuccess) e = A((void **)&pf->partials, sizeof(double2) * kMaxPartials, true);
   if (e == cudaSuccess) e = A((void **)&pf->ticket, 64, true);
   if (e == cudaSuccess) e = A((void **)&pf->d_stats, sizeof(WeightStats), true);
   if (e == cudaSuccess) e = cudaMallocHost((void **)&pf->h_stats, sizeof(WeightStats));
@@ -287,6 +308,7 @@ extern "C" int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_glob
   if (e == cudaSuccess) e = A((void **)&pf->tile_slot, (size_t)(pf->ntiles + 1) * 8, true);
   if (e == cudaSuccess) e = A((void **)&pf->d_plan, sizeof(ResamplePlan), true);
   if (e == cudaSuccess) e = cudaMallocHost((void **)&pf->h_plan, sizeof(ResamplePlan));
+  if (e == cudaSuccess) e = alloc_sys_workspace(pf);
   if (e == cudaSuccess && m->kind == MODEL_HMM) {
     size_t nt = m->params.size() - 2;
     e = A((void **)&pf->d_tab, nt * 8, false);
@@ -492,13 +514,14 @@ extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, 
     a.normals = pf->d_normals; a.uniforms = pf->d_uniforms;
     a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
     a.seed = pf->seed; a.step = 0;
-    a.partials = pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
+    a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
     rc = pf->dtype == GB_F64 ? launch_step_k<double, true>(pf, a, pk, predrawn, false)
                              : launch_step_k<float, true>(pf, a, pk, predrawn, false);
   }
   if (rc) return rc;
   pf->cur ^= 1;
-  pf->wstate = W_STATS;
+  pf->wstate = W_MAX;
+  pf->tiles_valid = false;
   pf->nn_set = pf->nu_set = 0;
   return GB_OK;
 }
@@ -533,7 +556,7 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
   a.normals = pf->d_normals; a.uniforms = pf->d_uniforms;
   a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
   a.seed = pf->seed; a.step = (unsigned)(pf->step + 1);
-  a.partials = pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
+  a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
   const bool gather = pf->pending_gather;
   rc = pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, pk, predrawn, gather)
                            : launch_step_k<float, false>(pf, a, pk, predrawn, gather);
@@ -541,7 +564,8 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
   pf->step += 1;
   pf->cur ^= 1;                       // particle_filter.jl:203-205, :234-237 (swap traces/new_traces)
   pf->pending_gather = false;
-  pf->wstate = W_STATS;
+  pf->wstate = W_MAX;
+  pf->tiles_valid = false;
   pf->nn_set = pf->nu_set = 0;
   if (incr_out) {
     if (pf->dtype == GB_F64) {
@@ -560,6 +584,8 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
 // ------------------------------------------------------------------------------------------
 // weights: stats, materialisation
 // ------------------------------------------------------------------------------------------
+static int run_gather(gb_pf *pf);
+static int materialize_pending(gb_pf *pf) { return run_gather(pf); }
 static int run_gather(gb_pf *pf) {   // materialise a deferred resample gather
   if (!pf->pending_gather) return GB_OK;
   const long long nvec = pf->dtype == GB_F64 ? (pf->n + 1) / 2 : (pf->n + 3) / 4;
@@ -577,40 +603,83 @@ static int run_gather(gb_pf *pf) {   // materialise a deferred resample gather
   CK(cudaGetLastError());
   pf->cur ^= 1;                       // particle_filter.jl:270-272
   pf->pending_gather = false;
+  pf->tiles_valid = false;
   return GB_OK;
 }
 
+// d_stats->m = max of the log weights (device side)
+static int ensure_max(gb_pf *pf, const void *logw) {
+  if (pf->wstate != W_DIRTY) return GB_OK;
+  if (pf->dtype == GB_F64) {
+    auto kern = max_kernel<double>;
+    int grid = grid_for(pf, kern, pf->n, kBlock);
+    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)logw, pf->n, (double *)pf->partials, pf->ticket, pf->d_stats));
+  } else {
+    auto kern = max_kernel<float>;
+    int grid = grid_for(pf, kern, pf->n, kBlock);
+    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)logw, pf->n, (double *)pf->partials, pf->ticket, pf->d_stats));
+  }
+  CK(cudaGetLastError());
+  pf->wstate = W_MAX;
+  return GB_OK;
+}
+// one pass over the log weights: (s1, s2) w.r.t. the reference max + quantised tile / super-tile totals;
+// the reference max is read from d_stats->m (from_device) or passed by value (sharded: global max)
+static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_device) {
+  const int bits = quant_bits(pf->n_global);
+  CK(cudaMemsetAsync(pf->super_q, 0, (size_t)(pf->nsuper + 1) * 8, pf->stream));
+  if (pf->dtype == GB_F64) {
+    auto kern = wstats_kernel<double>;
+    int grid = grid_for(pf, kern, pf->ntiles * kBlock, kBlock);
+    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)logw, pf->n, m_arg, from_device ? 1 : 0, bits, pf->tile_q,
+                                                                     pf->super_q, pf->partials, pf->ticket, pf->d_stats));
+  } else {
+    auto kern = wstats_kernel<float>;
+    int grid = grid_for(pf, kern, pf->ntiles * kBlock, kBlock);
+    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)logw, pf->n, m_arg, from_device ? 1 : 0, bits, pf->tile_q,
+                                                                     pf->super_q, pf->partials, pf->ticket, pf->d_stats));
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(pf->h_stats, pf->d_stats, sizeof(WeightStats), cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));
+  pf->tiles_valid = true;
+  return GB_OK;
+}
 // make h_stats describe the current log weights
 static int ensure_stats(gb_pf *pf) {
+  if (pf->wstate == W_STATS) return GB_OK;
   if (pf->wstate == W_ZERO) {
     // all log weights are exactly 0.0: logsumexp = 0 + log(N_local)
     pf->h_stats->m = 0.0; pf->h_stats->s1 = (double)pf->n; pf->h_stats->s2 = (double)pf->n;
     pf->h_stats->lse = log((double)pf->n); pf->h_stats->ess = (double)pf->n;
     return GB_OK;
   }
-  if (pf->wstate == W_DIRTY) {
-    if (pf->dtype == GB_F64) {
-      auto kern = lse_kernel<double>;
-      int grid = grid_for(pf, kern, pf->n, kBlock);
-      LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)pf->logw, pf->n, pf->partials, pf->ticket, pf->d_stats));
-    } else {
-      auto kern = lse_kernel<float>;
-      int grid = grid_for(pf, kern, pf->n, kBlock);
-      LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)pf->logw, pf->n, pf->partials, pf->ticket, pf->d_stats));
-    }
-    CK(cudaGetLastError());
-    pf->wstate = W_STATS;
-  }
-  CK(cudaMemcpyAsync(pf->h_stats, pf->d_stats, sizeof(WeightStats), cudaMemcpyDeviceToHost, pf->stream));
-  CK(cudaStreamSynchronize(pf->stream));
+  int rc = ensure_max(pf, pf->logw);
+  if (rc) return rc;
+  if ((rc = run_wstats(pf, pf->logw, 0.0, true))) return rc;
+  pf->wstate = W_STATS;
   return GB_OK;
 }
 
-extern "C" int gb_pf_weight_partials(gb_pf_t *pf, double *m, double *s1, double *s2) {
-  REQ(pf && m && s1 && s2, "null argument");
-  int rc = ensure_stats(pf);
+extern "C" int gb_pf_weight_max(gb_pf_t *pf, double *m_local) {
+  REQ(pf && m_local, "null argument");
+  if (pf->wstate == W_ZERO) { *m_local = 0.0; return GB_OK; }
+  if (pf->wstate == W_STATS) { *m_local = pf->h_stats->m; return GB_OK; }
+  int rc = ensure_max(pf, pf->logw);
   if (rc) return rc;
-  *m = pf->h_stats->m; *s1 = pf->h_stats->s1; *s2 = pf->h_stats->s2;
+  CK(cudaMemcpyAsync(&pf->h_stats->m, &pf->d_stats->m, sizeof(double), cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));
+  *m_local = pf->h_stats->m;
+  return GB_OK;
+}
+extern "C" int gb_pf_weight_sums(gb_pf_t *pf, double m_ref, int bits, double *s1, double *s2, uint64_t *q_local) {
+  REQ(pf && s1 && s2 && q_local, "null argument");
+  REQ(bits == quant_bits(pf->n_global), "gb_pf_weight_sums: bits must be gb_quant_bits(n_global)");
+  int rc = materialize_pending(pf);
+  if (rc) return rc;
+  if ((rc = run_wstats(pf, pf->logw, m_ref, false))) return rc;
+  if (pf->wstate != W_ZERO) pf->wstate = W_STATS;    // h_stats now refers to m_ref (>= the local max)
+  *s1 = pf->h_stats->s1; *s2 = pf->h_stats->s2; *q_local = pf->h_stats->q_total;
   return GB_OK;
 }
 extern "C" int gb_pf_get_ess(gb_pf_t *pf, double *ess, double *lse) {
@@ -679,6 +748,7 @@ extern "C" int gb_pf_set_log_weights(gb_pf_t *pf, const double *in) {
   }
   CK(cudaStreamSynchronize(pf->stream));
   pf->wstate = W_DIRTY;
+  pf->tiles_valid = false;
   return GB_OK;
 }
 extern "C" int gb_pf_get_state(gb_pf_t *pf, int field, double *out) {
@@ -781,7 +851,28 @@ static int fetch_plan(gb_pf *pf) {
   return GB_OK;
 }
 
-// ancestors (local, 0-based int32) of all n slots of a single-shard filter into pf->anc
+// systematic pipeline after wstats: superscan -> ancestors -> overflow.  Fills anc[k - anc_base] for the
+// shard's offspring slots; single shard: q_offset = 0, q_total = 0 (= the local total), anc_base = 0.
+template <typename R>
+static int launch_systematic(gb_pf *pf, const void *logw, double m, uint64_t q_offset, uint64_t q_total, uint32_t u0,
+                             int *anc, long long anc_base) {
+  const int bits = quant_bits(pf->n_global);
+  LAUNCH(pf, GB_K_TILESCAN, superscan_kernel<<<1, 1024, 0, pf->stream>>>(pf->nsuper, pf->super_q, pf->super_excl, pf->d_plan, q_offset,
+                                                                          q_total, pf->n_global, u0, pf->oflow_count));
+  CK(cudaGetLastError());
+  auto kern = ancestors_sys_kernel<R>;
+  LAUNCH(pf, GB_K_ANCESTORS, kern<<<(unsigned)pf->ntiles, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->tile_q, pf->super_excl,
+                                                                                    pf->d_plan, anc, anc_base, pf->oflow, pf->oflow_count));
+  CK(cudaGetLastError());
+  auto okern = overflow_sys_kernel<R>;
+  LAUNCH(pf, GB_K_ANCESTORS, okern<<<pf->num_sms * 4, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->d_plan, anc, anc_base,
+                                                                                pf->oflow, pf->oflow_count));
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+
+// ancestors (local, 0-based int32) of all n slots of a single-shard filter into anc.
+// Requires h_stats (m) and, for systematic, valid tile totals (run_wstats).
 template <typename R>
 static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, uint32_t u0, const uint64_t *d_u64,
                              uint64_t seed, uint32_t step, int *anc) {
@@ -789,23 +880,22 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
   const long long n_over = (pf->n_global + kChunk - 1) / kChunk;
   int rc;
   if (kind == GB_RESAMPLE_SYSTEMATIC) {
-    if ((rc = launch_qtotal<R, SWEEP_SYSTEMATIC>(pf, logw, m, bits, 0))) return rc;
-    if ((rc = launch_tilescan<SWEEP_SYSTEMATIC>(pf, 0, 0, u0, 1))) return rc;
-    return launch_ancestors<R, SWEEP_SYSTEMATIC>(pf, logw, m, bits, 0, n_over, anc, 0);
+    if (!pf->tiles_valid && (rc = run_wstats(pf, logw, m, false))) return rc;
+    return launch_systematic<R>(pf, logw, m, 0, 0, u0, anc, 0);
   }
   if (kind == GB_RESAMPLE_RESIDUAL) {
     if ((rc = ensure_residual_ws(pf))) return rc;
-    if ((rc = launch_qtotal<R, SWEEP_SYSTEMATIC>(pf, logw, m, bits, 0))) return rc;
-    if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, u0, 0))) return rc;    // totals only -> plan.sp.q_total
-    if ((rc = fetch_plan(pf))) return rc;
-    const uint64_t qn = pf->h_plan->sp.q_total;
+    if (!pf->tiles_valid && (rc = run_wstats(pf, logw, m, false))) return rc;
+    const uint64_t qn = pf->h_stats->q_total;
+    pf->tiles_valid = false;   // tile_q is about to be overwritten by the residual tile scan
     if ((rc = launch_qtotal<R, SWEEP_RESIDUAL>(pf, logw, m, bits, qn))) return rc;
     if ((rc = launch_tilescan<SWEEP_RESIDUAL>(pf, 0, qn, u0, 1))) return rc;
     return launch_ancestors<R, SWEEP_RESIDUAL>(pf, logw, m, bits, 0, n_over, anc, 0);
   }
   if (kind == GB_RESAMPLE_MULTINOMIAL) {
     if (!pf->cdf) CK(cudaMalloc((void **)&pf->cdf, (size_t)pf->ld * 8));
-    if ((rc = launch_qtotal<R, SWEEP_SYSTEMATIC>(pf, logw, m, bits, 0))) return rc;
+    if (!pf->tiles_valid && (rc = run_wstats(pf, logw, m, false))) return rc;
+    pf->tiles_valid = false;   // tile_q becomes its exclusive prefix
     if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, u0, 1))) return rc;
     if ((rc = launch_ancestors<R, SWEEP_CDF>(pf, logw, m, bits, 0, 0, anc, 0))) return rc;
     int grid = grid_for(pf, multinomial_kernel, pf->n, kBlock);
@@ -826,7 +916,7 @@ extern "C" int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind,
   const double ess = pf->h_stats->ess, lse = pf->h_stats->lse, m = pf->h_stats->m;
   const bool do_resample = ess < ess_threshold;   // :256 (strict; NaN compares false)
   if (!do_resample) return GB_OK;
-  if ((rc = materialize(pf))) return rc;          // two deferred gathers cannot be chained
+  if ((rc = materialize_pending(pf))) return rc;  // two deferred gathers cannot be chained
   // (W_ZERO with nothing pending: the array was really zeroed by the gather / commit that set it)
   // resampling randomness is keyed by the index of the step that produced the weights
   const uint32_t u0 = pf->use_u0 ? pf->u0 : philox_block(pf->seed, 0, (uint32_t)pf->step, PK_RESAMPLE, 0).x;
@@ -839,6 +929,7 @@ extern "C" int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind,
   pf->parents64_valid = false;
   pf->pending_gather = true;
   pf->wstate = W_ZERO;                                  // :266
+  pf->tiles_valid = false;
   pf->use_u0 = false;
   pf->u64_set = false;
   if (!pf->lazy && (rc = run_gather(pf))) return rc;    // :264-272
@@ -847,27 +938,19 @@ extern "C" int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind,
 }
 
 // ---- sharded pieces ----
-extern "C" int gb_pf_quantized_total(gb_pf_t *pf, double m_global, int bits, uint64_t *q_local) {
-  REQ(pf && q_local, "null argument");
-  int rc = materialize(pf);
-  if (rc) return rc;
-  rc = pf->dtype == GB_F64 ? launch_qtotal<double, SWEEP_SYSTEMATIC>(pf, pf->logw, m_global, bits, 0)
-                           : launch_qtotal<float, SWEEP_SYSTEMATIC>(pf, pf->logw, m_global, bits, 0);
-  if (rc) return rc;
-  if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, 0, 0))) return rc;   // totals only
-  if ((rc = fetch_plan(pf))) return rc;
-  *q_local = pf->h_plan->sp.q_total;
-  return GB_OK;
-}
 extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits, uint64_t q_offset, uint64_t q_total,
                                           uint32_t u0, int64_t *slot_lo, int64_t *slot_hi) {
   REQ(pf && slot_lo && slot_hi, "null argument");
   REQ(q_total > 0, "gb_pf_systematic_offspring: zero total weight");
+  REQ(bits == quant_bits(pf->n_global), "gb_pf_systematic_offspring: bits must be gb_quant_bits(n_global)");
+  REQ(pf->tiles_valid && pf->h_stats->m == m_global, "gb_pf_systematic_offspring: call gb_pf_weight_sums(m_global) first");
   int rc;
-  // tile_q still holds the per-tile totals written by gb_pf_quantized_total
-  if ((rc = launch_tilescan<SWEEP_SYSTEMATIC>(pf, q_offset, q_total, u0, 1))) return rc;
-  if ((rc = fetch_plan(pf))) return rc;
-  const long long lo = pf->h_plan->slot_lo, hi = pf->h_plan->slot_hi;
+  // the shard's offspring range is [slots_below(q_offset), slots_below(q_offset + Q_local)): host-side
+  // evaluation of the same exact integer function the kernels use
+  SweepParams sp;
+  sp.q_total = q_total; sp.q_inv = 1.0 / (double)q_total; sp.dscale = (uint64_t)pf->n_global << 32;
+  sp.ratio = (double)pf->n_global / (double)q_total; sp.u0 = u0;
+  const long long lo = slots_below(q_offset, sp), hi = slots_below(q_offset + pf->h_stats->q_total, sp);
   const long long cnt = hi - lo;
   if (cnt > pf->off_cap) {
     cudaFree(pf->off_anc);
@@ -877,10 +960,8 @@ extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits
     pf->off_cap = cap;
   }
   if (cnt > 0) {
-    const long long n_over = (cnt + kChunk - 1) / kChunk;
-    rc = pf->dtype == GB_F64
-             ? launch_ancestors<double, SWEEP_SYSTEMATIC>(pf, pf->logw, m_global, bits, lo, n_over, pf->off_anc, lo)
-             : launch_ancestors<float, SWEEP_SYSTEMATIC>(pf, pf->logw, m_global, bits, lo, n_over, pf->off_anc, lo);
+    rc = pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, m_global, q_offset, q_total, u0, pf->off_anc, lo)
+                             : launch_systematic<float>(pf, pf->logw, m_global, q_offset, q_total, u0, pf->off_anc, lo);
     if (rc) return rc;
   }
   pf->off_lo = lo; pf->off_hi = hi;
@@ -931,6 +1012,7 @@ extern "C" int gb_pf_commit_resample(gb_pf_t *pf, double log_ml_increment) {
   pf->cur ^= 1;
   pf->log_ml_est += log_ml_increment;
   pf->wstate = W_ZERO;
+  pf->tiles_valid = false;
   pf->anc_valid = false;
   pf->parents64_valid = true;
   pf->pending_gather = false;
@@ -957,7 +1039,7 @@ static int blr_generate(gb_pf *pf, const double *obs, int nobs, bool predrawn) {
   a.normals = pf->d_normals;
   a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
   a.seed = pf->seed; a.D = m.D; a.nobs = m.nobs; a.sigma = m.params[2];
-  a.partials = pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
+  a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
 #define GO(R, PD)                                                                   \
   {                                                                                 \
     auto kern = blr_generate_kernel<R, PD>;                                         \
@@ -1028,7 +1110,8 @@ static int raw_workspace(long long n, int dtype, cudaStream_t stream, gb_pf **ou
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&pf->num_sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaError_t e = cudaMalloc((void **)&pf->partials, sizeof(Lse3) * kMaxPartials);
+  cudaError_t e = cudaMalloc((void **)&pf->partials, sizeof(double2) * kMaxPartials);
+  if (e == cudaSuccess) e = alloc_sys_workspace(pf);
   if (e == cudaSuccess) e = cudaMalloc((void **)&pf->ticket, 64);
   if (e == cudaSuccess) e = cudaMemset(pf->ticket, 0, 64);
   if (e == cudaSuccess) e = cudaMalloc((void **)&pf->d_stats, sizeof(WeightStats));
@@ -1043,21 +1126,12 @@ static int raw_workspace(long long n, int dtype, cudaStream_t stream, gb_pf **ou
   return GB_OK;
 }
 
-// max + sums of a raw device array -> ws->h_stats
+// max + sums + quantised tile totals of a raw device array -> ws->h_stats
 static int raw_stats(gb_pf *ws, const void *dev_logw) {
-  if (ws->dtype == GB_F64) {
-    auto kern = lse_kernel<double>;
-    int grid = grid_for(ws, kern, ws->n, kBlock);
-    LAUNCH(ws, GB_K_FINALIZE, kern<<<grid, kBlock, 0, ws->stream>>>((const double *)dev_logw, ws->n, ws->partials, ws->ticket, ws->d_stats));
-  } else {
-    auto kern = lse_kernel<float>;
-    int grid = grid_for(ws, kern, ws->n, kBlock);
-    LAUNCH(ws, GB_K_FINALIZE, kern<<<grid, kBlock, 0, ws->stream>>>((const float *)dev_logw, ws->n, ws->partials, ws->ticket, ws->d_stats));
-  }
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(ws->h_stats, ws->d_stats, sizeof(WeightStats), cudaMemcpyDeviceToHost, ws->stream));
-  CK(cudaStreamSynchronize(ws->stream));
-  return GB_OK;
+  ws->wstate = W_DIRTY;
+  int rc = ensure_max(ws, dev_logw);
+  if (rc) return rc;
+  return run_wstats(ws, dev_logw, 0.0, true);
 }
 
 // NOTE: dev_logw must be padded to a multiple of 2048 elements (the engine's own arrays are); the
@@ -1146,11 +1220,14 @@ extern "C" int gb_logsumexp(const double *a, int64_t n, int dtype, double *lse_o
 template <typename R>
 __global__ void __launch_bounds__(kBlock) noise_kernel(unsigned long long seed, unsigned int step, long long pid0, long long n,
                                                        int ndraw, int uniform, double *__restrict__ out) {
+  __shared__ double s_tab[kMathTabDoubles];
+  const MathTables T = stage_math_tables(s_tab);
+  __syncthreads();
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
     for (int d = 0; d < ndraw; d += 2) {
       R a, b;
       if (uniform) philox_uniform_pair(seed, (unsigned long long)(pid0 + i), step, (unsigned)(d / 2), a, b);
-      else philox_normal_pair(seed, (unsigned long long)(pid0 + i), step, (unsigned)(d / 2), a, b);
+      else philox_normal_pair(seed, (unsigned long long)(pid0 + i), step, (unsigned)(d / 2), T, a, b);
       out[(long long)d * n + i] = (double)a;
       if (d + 1 < ndraw) out[(long long)(d + 1) * n + i] = (double)b;
     }
@@ -1201,6 +1278,20 @@ extern "C" int64_t gb_selftest_slots_below_residual(uint64_t chi, uint64_t clo, 
 }
 extern "C" uint64_t gb_selftest_div128(uint64_t ahi, uint64_t alo, uint64_t d) { return div128_64(ahi, alo, d, 1.0 / (double)d); }
 extern "C" uint64_t gb_selftest_quantize(double x, int bits) { return quantize(x, bits); }
+// fn: 0 log(a), 1 sin(2 pi a), 2 cos(2 pi a), 3 atan2(a, b), 4 exp(a), 5 u52_fast(hi = a, lo = b)
+extern "C" double gb_selftest_math(int fn, double a, double b) {
+  MathTables T = host_math_tables();
+  double s, c;
+  switch (fn) {
+    case 0: return gb_log(a, T);
+    case 1: gb_sincos2pi(a, s, c); return s;
+    case 2: gb_sincos2pi(a, s, c); return c;
+    case 3: return gb_atan2(a, b, T);
+    case 4: return gb_exp(a);
+    case 5: return u52_fast((uint32_t)a, (uint32_t)b);
+  }
+  return NAN;
+}
 extern "C" void gb_selftest_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   U4 r = philox4x32_10(U4{ctr[0], ctr[1], ctr[2], ctr[3]}, key[0], key[1]);
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
@@ -1233,12 +1324,15 @@ template <typename R>
 __global__ void __launch_bounds__(kBlock) dist_random_kernel(int dist, long long n, const double *__restrict__ a, int as,
                                                              const double *__restrict__ b, int bs, int len, unsigned long long seed,
                                                              unsigned int step, double *__restrict__ out) {
+  __shared__ double s_tab[kMathTabDoubles];
+  const MathTables T = stage_math_tables(s_tab);
+  __syncthreads();
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
     const unsigned long long pid = (unsigned long long)i;
     switch (dist) {
       case GB_DIST_NORMAL: {
         R e0, e1;
-        philox_normal_pair(seed, pid, step, 0u, e0, e1);
+        philox_normal_pair(seed, pid, step, 0u, T, e0, e1);
         out[i] = (double)random_normal<R>((R)a[i * as], (R)b[i * bs], e0);
         break;
       }
@@ -1259,7 +1353,7 @@ __global__ void __launch_bounds__(kBlock) dist_random_kernel(int dist, long long
         R eps[kBlrMax];
         for (int k = 0; k < len; k += 2) {
           R e0, e1;
-          philox_normal_pair(seed, pid, step, (unsigned)(k / 2), e0, e1);
+          philox_normal_pair(seed, pid, step, (unsigned)(k / 2), T, e0, e1);
           eps[k] = e0;
           if (k + 1 < len) eps[k + 1] = e1;
         }

@@ -38,29 +38,6 @@ struct ResamplePlan {
   long long n_global;
 };
 
-template <typename R> GB_D void load_items(const R *__restrict__ logw, long long base, long long n, double (&lw)[kItems]);
-template <> GB_D void load_items<double>(const double *__restrict__ logw, long long base, long long n, double (&lw)[kItems]) {
-  const long long i0 = base + (long long)threadIdx.x * kItems;
-#pragma unroll
-  for (int j = 0; j < kItems; j += 2) {
-    // arrays are padded to a multiple of kTile elements, so the vector load is always in bounds
-    double2 v = __ldcs(reinterpret_cast<const double2 *>(logw + i0 + j));
-    lw[j] = (i0 + j < n) ? v.x : -INFINITY;
-    lw[j + 1] = (i0 + j + 1 < n) ? v.y : -INFINITY;
-  }
-}
-template <> GB_D void load_items<float>(const float *__restrict__ logw, long long base, long long n, double (&lw)[kItems]) {
-  const long long i0 = base + (long long)threadIdx.x * kItems;
-#pragma unroll
-  for (int j = 0; j < kItems; j += 4) {
-    float4 v = __ldcs(reinterpret_cast<const float4 *>(logw + i0 + j));
-    lw[j] = (i0 + j < n) ? (double)v.x : -INFINITY;
-    lw[j + 1] = (i0 + j + 1 < n) ? (double)v.y : -INFINITY;
-    lw[j + 2] = (i0 + j + 2 < n) ? (double)v.z : -INFINITY;
-    lw[j + 3] = (i0 + j + 3 < n) ? (double)v.w : -INFINITY;
-  }
-}
-
 // ---- 64-bit / 128-bit block primitives built on warp shuffles ----
 GB_D uint64_t shfl_up_u64(uint64_t v, int d) {
   uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d);
@@ -253,6 +230,7 @@ __global__ void __launch_bounds__(1024) tilescan_kernel(long long ntiles, uint64
     else sp.q_total = q_total_given ? q_total_given : tot.lo;          // single shard: Q_N = local total
     sp.q_inv = 1.0 / (double)sp.q_total;
     sp.dscale = (uint64_t)n_global << 32;
+    sp.ratio = (double)n_global / (double)sp.q_total;
     sp.u0 = u0;
     s_sp = sp;
   }
@@ -517,6 +495,226 @@ __global__ void __launch_bounds__(kBlock) convert_out_kernel(const R *__restrict
 template <typename R>
 __global__ void __launch_bounds__(kBlock) convert_in_kernel(const double *__restrict__ in, R *__restrict__ out, long long n) {
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) out[i] = (R)in[i];
+}
+
+// ==========================================================================================
+// Systematic resampling, production pipeline (v1):
+//   wstats (kernels_step.cuh)  per-tile + per-super-tile integer CDF mass, logsumexp/ESS sums
+//   superscan                  <= 16384 super-tile totals: exclusive prefix + first slot (1 CTA, tiny)
+//   ancestors_sys              one CTA per 2048-particle tile: tile prefix from the super prefix + <= 63
+//                              tile totals, block scan of the quantised weights, offspring range per
+//                              particle from a double-precision estimate with exact 128/64-bit fallback,
+//                              head flags + max-scan in shared memory -> coalesced int32 ancestors
+//   overflow_sys               tiles whose particles own more than kChunk output slots queue themselves;
+//                              this kernel spreads the remaining slots over the whole GPU (exits at once
+//                              when the queue is empty, which is the normal case)
+// ==========================================================================================
+struct OverflowEntry { long long tile, slot0, slot_lo, slot_hi; unsigned long long cbase; };
+
+__global__ void __launch_bounds__(1024) superscan_kernel(long long nsuper, const unsigned long long *__restrict__ super_q,
+                                                         unsigned long long *__restrict__ super_excl,
+                                                         ResamplePlan *plan, uint64_t q_offset, uint64_t q_total_given,
+                                                         long long n_global, uint32_t u0, unsigned int *overflow_count) {
+  __shared__ uint64_t s_w[33];
+  const int T = 1024;
+  const long long per = (nsuper + T - 1) / T;
+  const long long lo = (long long)threadIdx.x * per, hi = lo + per < nsuper ? lo + per : nsuper;
+  uint64_t a = 0;
+  for (long long i = lo; i < hi; i++) a += super_q[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t inc = a;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t o = shfl_up_u64(inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t w = s_w[lane], winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint64_t o = shfl_up_u64(winc, d);
+      if (lane >= d) winc += o;
+    }
+    s_w[lane] = winc - w;
+    if (lane == 31) s_w[32] = winc;
+  }
+  __syncthreads();
+  uint64_t run = s_w[warp] + (inc - a);
+  const uint64_t total = s_w[32];
+  for (long long i = lo; i < hi; i++) {
+    uint64_t v = super_q[i];
+    super_excl[i] = run;
+    run += v;
+  }
+  if (threadIdx.x == 0) {
+    super_excl[nsuper] = total;
+    SweepParams sp;
+    sp.q_total = q_total_given ? q_total_given : total;
+    sp.q_inv = 1.0 / (double)sp.q_total;
+    sp.dscale = (uint64_t)n_global << 32;
+    sp.ratio = (double)n_global / (double)sp.q_total;
+    sp.u0 = u0;
+    plan->sp = sp;
+    plan->q_offset = q_offset;
+    plan->n_global = n_global;
+    plan->slot_lo = slots_below(q_offset, sp);
+    plan->slot_hi = slots_below(q_offset + total, sp);
+    *overflow_count = 0;
+  }
+}
+
+constexpr int kSlotPad = kChunk + kChunk / 32;
+GB_D int pad_idx(int i) { return i + (i >> 5); }
+
+// Scan one tile and fill the ancestors of output slots [lo, hi) (hi - lo <= kChunk) that belong to it.
+// cbase = integer CDF mass before the tile (including q_offset); slot0 = first slot of the tile.
+template <typename R>
+GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits, const SweepParams &sp, long long tile,
+                    uint64_t cbase, long long slot0, long long lo, long long hi, int *__restrict__ anc, long long anc_base,
+                    uint64_t *s_warp64, int *s_slot, long long *s_kend_last) {
+  double lw[kItems];
+  load_items<R>(logw, tile * kTile, n, lw);
+  uint64_t c[kItems];
+  uint64_t t = 0;
+#pragma unroll
+  for (int j = 0; j < kItems; j++) {
+    t += quantize(lw[j] - m, bits);
+    c[j] = t;
+  }
+  uint64_t total;
+  const uint64_t ex = block_exclusive_scan(t, s_warp64, &total);
+  long long kend[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; j++) kend[j] = slots_below_fast(cbase + ex + c[j], sp);
+  s_kend_last[threadIdx.x] = kend[kItems - 1];
+  // clear the slot window
+  const int cnt = (int)(hi - lo);
+  for (int i = threadIdx.x; i < cnt; i += kBlock) s_slot[pad_idx(i)] = -1;
+  __syncthreads();
+  // head flags: particle j owns slots [kstart_j, kend_j); it marks the first of them that is inside [lo, hi)
+  long long kstart = threadIdx.x == 0 ? slot0 : s_kend_last[threadIdx.x - 1];
+#pragma unroll
+  for (int j = 0; j < kItems; j++) {
+    const long long ke = kend[j];
+    if (ke > kstart && ke > lo && kstart < hi) {
+      const long long pos = (kstart > lo ? kstart : lo) - lo;
+      s_slot[pad_idx((int)pos)] = threadIdx.x * kItems + j;
+    }
+    kstart = ke;
+  }
+  __syncthreads();
+  // inclusive max-scan over the window: every slot takes the last head at or before it
+  int L = 1;
+  while (L * kBlock < cnt) L <<= 1;             // entries per thread: power of two <= 32
+  const int base = threadIdx.x * L;
+  int run = -1;
+  for (int i = 0; i < L; i++) {
+    const int k = base + i;
+    if (k < cnt) { const int v = s_slot[pad_idx(k)]; run = v > run ? v : run; }
+  }
+  // block-wide exclusive max-scan of the per-thread maxima
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc = o > inc ? o : inc;
+  }
+  int *s_wmax = reinterpret_cast<int *>(s_warp64);   // 8 ints fit in the 9 x u64 scratch
+  __syncthreads();
+  if (lane == 31) s_wmax[warp] = inc;
+  __syncthreads();
+  int pre = -1;
+  for (int w2 = 0; w2 < warp; w2++) { const int v = s_wmax[w2]; pre = v > pre ? v : pre; }
+  int up = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane > 0) pre = up > pre ? up : pre;
+  run = pre;
+  for (int i = 0; i < L; i++) {
+    const int k = base + i;
+    if (k < cnt) {
+      const int v = s_slot[pad_idx(k)];
+      run = v > run ? v : run;
+      s_slot[pad_idx(k)] = run;
+    }
+  }
+  __syncthreads();
+  // coalesced copy-out
+  const int tile_base = (int)(tile * kTile);
+  int *__restrict__ out = anc + (lo - anc_base);
+  for (int i = threadIdx.x; i < cnt; i += kBlock) __stcs(out + i, tile_base + s_slot[pad_idx(i)]);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const R *__restrict__ logw, long long n, double m, int bits,
+                                                               const uint64_t *__restrict__ tile_q,
+                                                               const unsigned long long *__restrict__ super_excl,
+                                                               const ResamplePlan *__restrict__ plan, int *__restrict__ anc,
+                                                               long long anc_base, OverflowEntry *__restrict__ oflow,
+                                                               unsigned int *__restrict__ oflow_count) {
+  __shared__ uint64_t s_warp64[kBlock / 32 + 1];
+  __shared__ int s_slot[kSlotPad];
+  __shared__ long long s_kend_last[kBlock];
+  __shared__ uint64_t s_cbase;
+  __shared__ long long s_slot0, s_slot_end;
+  const SweepParams sp = plan->sp;
+  const long long tile = blockIdx.x;
+  // CDF mass before this tile: super-tile prefix + the (<= 63) tile totals before it inside the super-tile
+  if (threadIdx.x < 32) {
+    const long long sbase = (tile / kSuper) * kSuper;
+    uint64_t v = 0;
+    for (long long i = sbase + threadIdx.x; i < tile; i += 32) v += tile_q[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += shfl_u64(v, (threadIdx.x ^ o) & 31);
+    if (threadIdx.x == 0) {
+      const uint64_t cb = plan->q_offset + super_excl[tile / kSuper] + v;
+      s_cbase = cb;
+      s_slot0 = slots_below(cb, sp);
+      s_slot_end = slots_below(cb + tile_q[tile], sp);   // == offspring end of the tile's last particle
+    }
+  }
+  __syncthreads();
+  const uint64_t cbase = s_cbase;
+  const long long slot0 = s_slot0, slot_end = s_slot_end;
+  if (slot_end <= slot0) return;     // no particle of this tile has offspring
+  long long hi = slot_end;
+  if (hi > slot0 + kChunk) hi = slot0 + kChunk;
+  tile_fill<R>(logw, n, m, bits, sp, tile, cbase, slot0, slot0, hi, anc, anc_base, s_warp64, s_slot, s_kend_last);
+  if (slot_end > slot0 + kChunk && threadIdx.x == 0) {
+    const unsigned int e = atomicAdd(oflow_count, 1u);
+    oflow[e] = OverflowEntry{tile, slot0, slot0 + kChunk, slot_end, cbase};
+  }
+}
+
+// Remaining slots of heavy tiles: work unit = (queue entry, kChunk-sized piece); units are dealt
+// round-robin to the CTAs of a fixed-size grid.
+template <typename R>
+__global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restrict__ logw, long long n, double m, int bits,
+                                                              const ResamplePlan *__restrict__ plan, int *__restrict__ anc,
+                                                              long long anc_base, const OverflowEntry *__restrict__ oflow,
+                                                              const unsigned int *__restrict__ oflow_count) {
+  __shared__ uint64_t s_warp64[kBlock / 32 + 1];
+  __shared__ int s_slot[kSlotPad];
+  __shared__ long long s_kend_last[kBlock];
+  const unsigned int ne = *oflow_count;
+  if (ne == 0) return;
+  const SweepParams sp = plan->sp;
+  long long unit0 = 0;
+  for (unsigned int e = 0; e < ne; e++) {
+    const OverflowEntry en = oflow[e];
+    const long long pieces = (en.slot_hi - en.slot_lo + kChunk - 1) / kChunk;
+    // first piece of this entry handled by this CTA
+    long long first = ((long long)blockIdx.x - unit0 % gridDim.x + gridDim.x) % gridDim.x;
+    for (long long pc = first; pc < pieces; pc += gridDim.x) {
+      const long long lo = en.slot_lo + pc * kChunk;
+      long long hi = lo + kChunk;
+      if (hi > en.slot_hi) hi = en.slot_hi;
+      __syncthreads();
+      tile_fill<R>(logw, n, m, bits, sp, en.tile, en.cbase, en.slot0, lo, hi, anc, anc_base, s_warp64, s_slot, s_kend_last);
+    }
+    unit0 += pieces;
+  }
 }
 
 }  // namespace gb

@@ -1,20 +1,28 @@
-// kernels_step.cuh -- K1/K2/K3: fused propose + weight + log-weight accumulation + online
-// log-sum-exp / ESS partials, one launch per particle_filter_step! / initialize_particle_filter /
-// importance_sampling call (particle_filter.jl:127-131, :149-151, :196-200, :224-232;
-// importance.jl:28-31, :48-54; inference.jl:3-6; particle_filter.jl:3-12).
+// kernels_step.cuh -- K1/K2/K3 of the particle path.
 //
-// HBM-bound streaming kernel: SoA columns, one 128-bit load/store per thread per column
-// (V = 16/sizeof(R) consecutive particles per thread), grid = resident CTAs * 148 SMs, grid-stride
-// over chunks.  The last CTA to finish folds the per-CTA (max, sum e, sum e^2) partials into the
-// weight statistics, so there is no separate reduction launch.
+//   step_kernel   : fused (deferred resample gather +) propose + weight + log-weight accumulation +
+//                   running max, one launch per particle_filter_step! / initialize_particle_filter /
+//                   importance_sampling call (particle_filter.jl:127-131, :149-151, :196-200, :224-232,
+//                   :264-267; importance.jl:28-31, :48-54).
+//   wstats_kernel : one pass over the log weights that yields everything maybe_resample! /
+//                   log_ml_estimate need: sum exp(lw-m), sum exp(2(lw-m)) (inference.jl:3-6,
+//                   particle_filter.jl:3-12) AND the per-tile totals of the integer-quantised weights the
+//                   resamplers sweep over -- the exp is evaluated once and shared.
+//
+// Both are HBM-streaming kernels: SoA columns, 128-bit loads/stores, grid = resident CTAs x 148 SMs,
+// grid-stride.  The last CTA to finish folds the per-CTA partials (ticket counter), so there is no
+// separate reduction launch.  v0 of the step kernel was issue-bound at 487 instructions per particle
+// (profiles/r1_step_kernel_v0.md); the exp moved into wstats (where the quantiser needs it anyway),
+// the transcendental functions are the table-driven ones of gbmath.cuh.
 #pragma once
 #include "models.cuh"
 
 namespace gb {
 
 struct WeightStats {
-  double m, s1, s2;   // shard-local online LSE triple
+  double m, s1, s2;   // reference max, sum exp(lw-m), sum exp(2(lw-m)) of this shard
   double lse, ess;    // m + log s1 ; s1^2 / s2
+  unsigned long long q_total;   // sum of the quantised weights (wstats)
 };
 
 template <typename R> struct VecOf;
@@ -57,41 +65,35 @@ struct StepArgs {
   long long n, ld, pid_offset;
   unsigned long long seed;
   unsigned int step;
-  Lse3 *partials;         // one per CTA
+  double *partials;       // one running max per CTA
   unsigned int *ticket;
-  WeightStats *stats;
+  WeightStats *stats;     // stats->m receives the max of the new log weights
   ModelParams mp;
 };
 
-GB_D Lse3 lse3_block_reduce(Lse3 v, Lse3 *smem /* kBlock/32 entries */) {
-  v = lse3_warp_reduce(v);
+// maximum() with Julia's NaN propagation (inference.jl:4)
+GB_D double max_nan(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+
+GB_D double block_max(double v, double *smem /* kBlock/32 */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max_nan(v, __shfl_xor_sync(0xffffffffu, v, o));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) smem[warp] = v;
   __syncthreads();
-  Lse3 r = lse3_empty();
+  double r = -INFINITY;
   if (warp == 0) {
-    if (lane < kBlock / 32) r = smem[lane];
-    r = lse3_warp_reduce(r);
+    if (lane < (int)(blockDim.x >> 5)) r = smem[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = max_nan(r, __shfl_xor_sync(0xffffffffu, r, o));
   }
   return r;  // valid in warp 0
 }
 
-GB_D Lse3 load_partial(const Lse3 *p) {   // L2 (coherent) read of another CTA's partial
-  return Lse3{__ldcg(&p->m), __ldcg(&p->s1), __ldcg(&p->s2)};
-}
-GB_D void write_stats(WeightStats *st, const Lse3 &t) {
-  st->m = t.m; st->s1 = t.s1; st->s2 = t.s2;
-  // inference.jl:5: max == -Inf ? -Inf : max + log(sum(exp.(arr .- max)))
-  st->lse = (t.m == -INFINITY) ? -INFINITY : t.m + log(t.s1);
-  // particle_filter.jl:3-6 evaluates exp(-logsumexp(2 lnw)) == s1^2/s2 ; all -Inf => NaN there too
-  st->ess = (t.s1 * t.s1) / t.s2;
-}
-
-// Fold this CTA's partial into global memory; the last CTA reduces all partials into `stats`.
-GB_D void publish_partials(Lse3 acc, Lse3 *partials, unsigned int *ticket, WeightStats *stats) {
-  __shared__ Lse3 s_red[kBlock / 32];
+// Publish this CTA's max; the last CTA reduces all of them into stats->m.
+GB_D void publish_max(double acc, double *partials, unsigned int *ticket, WeightStats *stats) {
+  __shared__ double s_red[32];
   __shared__ bool s_last;
-  Lse3 r = lse3_block_reduce(acc, s_red);
+  double r = block_max(acc, s_red);
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = r;
     __threadfence();
@@ -101,14 +103,12 @@ GB_D void publish_partials(Lse3 acc, Lse3 *partials, unsigned int *ticket, Weigh
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  Lse3 a = lse3_empty();
-  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-    a = lse3_merge(a, load_partial(partials + i));
-  }
+  double a = -INFINITY;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) a = max_nan(a, __ldcg(partials + i));
   __syncthreads();
-  Lse3 t = lse3_block_reduce(a, s_red);
+  a = block_max(a, s_red);
   if (threadIdx.x == 0) {
-    write_stats(stats, t);
+    stats->m = a;
     *ticket = 0;
   }
 }
@@ -117,12 +117,15 @@ template <typename R, int KIND, int PK, bool INIT, bool PREDRAWN, bool GATHER>
 __global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs a) {
   typedef Transition<R, KIND, PK, INIT> Tr;
   constexpr int V = VecOf<R>::V, S = Tr::S, NN = Tr::NN, NU = Tr::NU;
+  __shared__ double s_tab[kMathTabDoubles];
+  const MathTables T = stage_math_tables(s_tab);
+  __syncthreads();
   const R *__restrict__ sin = static_cast<const R *>(a.state_in);
   R *__restrict__ sout = static_cast<R *>(a.state_out);
   R *__restrict__ logw = static_cast<R *>(a.logw);
   R *__restrict__ incr = static_cast<R *>(a.incr);
   const Hoisted<R> hz = Tr::hoist(a.mp);
-  Lse3 acc = lse3_empty();
+  double acc = -INFINITY;
 
   const long long nvec = (a.n + V - 1) / V;
   for (long long iv = (long long)blockIdx.x * kBlock + threadIdx.x; iv < nvec; iv += (long long)gridDim.x * kBlock) {
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs a) {
 #pragma unroll
         for (int d = 0; d < NN; d += 2) {
           R e0, e1;
-          philox_normal_pair(a.seed, pid, a.step, (unsigned)(d / 2), e0, e1);
+          philox_normal_pair(a.seed, pid, a.step, (unsigned)(d / 2), T, e0, e1);
           eps[d] = e0;
           if (d + 1 < NN) eps[d + 1] = e1;
         }
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs a) {
       R pv[S], nx[S];
 #pragma unroll
       for (int s = 0; s < S; s++) pv[s] = INIT ? R(0) : prev[s][v];
-      w[v] = Tr::apply(a.mp, hz, pv, nx, eps, us);
+      w[v] = Tr::apply(a.mp, hz, T, pv, nx, eps, us);
 #pragma unroll
       for (int s = 0; s < S; s++) next[s][v] = nx[s];
     }
@@ -186,24 +189,167 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs a) {
 #pragma unroll
     for (int v = 0; v < V; v++) {
       lw_new[v] = INIT ? w[v] : lw_old[v] + w[v];     // particle_filter.jl:131,151 / :199,231
-      if (i0 + v < a.n) lse3_push(acc, (double)lw_new[v]);
+      if (i0 + v < a.n) acc = max_nan(acc, (double)lw_new[v]);
     }
 #pragma unroll
     for (int s = 0; s < S; s++) vstore<R>(sout + (long long)s * a.ld + i0, next[s]);
     vstore_keep<R>(logw + i0, lw_new);
     if (!INIT) vstore<R>(incr + i0, w);
   }
-  publish_partials(acc, a.partials, a.ticket, a.stats);
+  publish_max(acc, a.partials, a.ticket, a.stats);
 }
 
-// Reduce an existing log-weight array (after gb_pf_set_log_weights, clone, raw-array entries).
+// max of an existing log-weight array (after gb_pf_set_log_weights, clone, raw-array entries)
 template <typename R>
-__global__ void __launch_bounds__(kBlock) lse_kernel(const R *__restrict__ logw, long long n, Lse3 *partials,
+__global__ void __launch_bounds__(kBlock) max_kernel(const R *__restrict__ logw, long long n, double *partials,
                                                      unsigned int *ticket, WeightStats *stats) {
-  Lse3 acc = lse3_empty();
+  double acc = -INFINITY;
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
-    lse3_push(acc, (double)__ldg(logw + i));
-  publish_partials(acc, partials, ticket, stats);
+    acc = max_nan(acc, (double)__ldg(logw + i));
+  publish_max(acc, partials, ticket, stats);
+}
+
+// ------------------------------------------------------------------------------------------
+// wstats: e_i = exp(lw_i - m) once per particle ->
+//   s1 = sum e, s2 = sum e^2            (logsumexp / ESS, fp64)
+//   tile_q[t] = sum over tile t of floor(e_i 2^bits)   (integer CDF mass per 2048-particle tile)
+//   super_q[t / 64] += tile_q[t]                       (per 131072-particle super-tile, integer atomics)
+// m comes from device memory (stats->m, written by the step kernel) or, for sharded filters, from the
+// host (the global max after the all-reduce).
+// ------------------------------------------------------------------------------------------
+constexpr int kSuper = 64;   // tiles per super-tile
+
+template <typename R> GB_D void load_items(const R *__restrict__ logw, long long base, long long n, double (&lw)[kItems]);
+template <> GB_D void load_items<double>(const double *__restrict__ logw, long long base, long long n, double (&lw)[kItems]) {
+  const long long i0 = base + (long long)threadIdx.x * kItems;
+#pragma unroll
+  for (int j = 0; j < kItems; j += 2) {
+    // arrays are padded to a multiple of kTile elements, so the vector load is always in bounds
+    double2 v = *reinterpret_cast<const double2 *>(logw + i0 + j);
+    lw[j] = (i0 + j < n) ? v.x : -INFINITY;
+    lw[j + 1] = (i0 + j + 1 < n) ? v.y : -INFINITY;
+  }
+}
+template <> GB_D void load_items<float>(const float *__restrict__ logw, long long base, long long n, double (&lw)[kItems]) {
+  const long long i0 = base + (long long)threadIdx.x * kItems;
+#pragma unroll
+  for (int j = 0; j < kItems; j += 4) {
+    float4 v = *reinterpret_cast<const float4 *>(logw + i0 + j);
+    lw[j] = (i0 + j < n) ? (double)v.x : -INFINITY;
+    lw[j + 1] = (i0 + j + 1 < n) ? (double)v.y : -INFINITY;
+    lw[j + 2] = (i0 + j + 2 < n) ? (double)v.z : -INFINITY;
+    lw[j + 3] = (i0 + j + 3 < n) ? (double)v.w : -INFINITY;
+  }
+}
+
+// exp(x) and floor(exp(x) 2^bits) for x = lw - m <= 0 from ONE polynomial evaluation; the integer is
+// bit-identical to common.cuh quantize() / oracle go_quantize()
+GB_D void exp_and_quantize(double x, int bits, double &e, uint64_t &q) {
+  if (!(x > -708.0)) { e = 0.0; q = 0; return; }
+  if (x > 0.0) x = 0.0;
+  int k;
+  const double p = gb_exp_parts(x, k);
+  e = p * pow2i(k);
+  const int eb = k + bits;
+  q = eb < 0 ? 0 : (uint64_t)dmul(p, pow2i(eb));
+}
+
+GB_D uint64_t block_sum_u64(uint64_t v, uint64_t *smem /* kBlock/32 */) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, o), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), o);
+    v += ((uint64_t)hi << 32) | lo;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  uint64_t r = 0;
+#pragma unroll
+  for (int k = 0; k < kBlock / 32; k++) r += smem[k];
+  return r;  // valid in every thread
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ logw, long long n, double m_arg, int m_from_device,
+                                                        int bits, uint64_t *__restrict__ tile_q,
+                                                        unsigned long long *__restrict__ super_q, double2 *partials,
+                                                        unsigned int *ticket, WeightStats *stats) {
+  __shared__ uint64_t s_u64[kBlock / 32];
+  __shared__ double2 s_d2[kBlock / 32];
+  __shared__ bool s_last;
+  const double m = m_from_device ? __ldcg(&stats->m) : m_arg;
+  const long long ntiles = (n + kTile - 1) / kTile;
+  double s1 = 0.0, s2 = 0.0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    double lw[kItems];
+    load_items<R>(logw, tile * kTile, n, lw);
+    uint64_t sq = 0;
+#pragma unroll
+    for (int j = 0; j < kItems; j++) {
+      double e;
+      uint64_t q;
+      exp_and_quantize(lw[j] - m, bits, e, q);
+      s1 += e;
+      s2 = fma(e, e, s2);
+      sq += q;
+    }
+    const uint64_t tq = block_sum_u64(sq, s_u64);
+    if (threadIdx.x == 0) {
+      tile_q[tile] = tq;
+      atomicAdd(super_q + tile / kSuper, (unsigned long long)tq);
+    }
+  }
+  // CTA partial sums (fixed order => deterministic for a fixed grid)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_d2[warp] = make_double2(s1, s2);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < kBlock / 32; k++) { a += s_d2[k].x; b += s_d2[k].y; }
+    partials[blockIdx.x] = make_double2(a, b);
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last CTA: fold the partials and the super-tile totals
+  double a = 0.0, b = 0.0;
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += kBlock) {
+    a += __ldcg(&partials[i].x);
+    b += __ldcg(&partials[i].y);
+  }
+  const long long nsuper = (ntiles + kSuper - 1) / kSuper;
+  uint64_t qs = 0;
+  for (long long i = threadIdx.x; i < nsuper; i += kBlock) qs += __ldcg(super_q + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  __syncthreads();
+  if (lane == 0) s_d2[warp] = make_double2(a, b);
+  const uint64_t qtot = block_sum_u64(qs, s_u64);
+  if (threadIdx.x == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int k = 0; k < kBlock / 32; k++) { t1 += s_d2[k].x; t2 += s_d2[k].y; }
+    stats->m = m;
+    stats->s1 = t1;
+    stats->s2 = t2;
+    // inference.jl:5: max == -Inf ? -Inf : max + log(sum(exp.(arr .- max)))
+    stats->lse = (m == -INFINITY) ? -INFINITY : m + log(t1);
+    // particle_filter.jl:3-6: exp(-logsumexp(2 lnw)) == s1^2 / s2 ; all -Inf => NaN there too
+    stats->ess = (t1 * t1) / t2;
+    stats->q_total = qtot;
+    *ticket = 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -224,17 +370,20 @@ struct BlrArgs {
   unsigned long long seed;
   int D, nobs;
   double sigma;
-  Lse3 *partials;
+  double *partials;
   unsigned int *ticket;
   WeightStats *stats;
 };
 
 template <typename R, bool PREDRAWN>
 __global__ void __launch_bounds__(128) blr_generate_kernel(const BlrArgs a) {
+  __shared__ double s_tab[kMathTabDoubles];
+  const MathTables T = stage_math_tables(s_tab);
+  __syncthreads();
   R *__restrict__ sout = static_cast<R *>(a.state_out);
   R *__restrict__ logw = static_cast<R *>(a.logw);
-  const R sigma = (R)a.sigma, log_sigma = Math<R>::log_((R)a.sigma);
-  Lse3 acc = lse3_empty();
+  const R inv_sigma = R(1) / (R)a.sigma, log_sigma = Math<R>::log_((R)a.sigma);
+  double acc = -INFINITY;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
     R w[kBlrMax];
     if (PREDRAWN) {
@@ -245,7 +394,7 @@ __global__ void __launch_bounds__(128) blr_generate_kernel(const BlrArgs a) {
 #pragma unroll
       for (int d = 0; d < kBlrMax; d += 2) {
         R e0 = R(0), e1 = R(0);
-        if (d < a.D) philox_normal_pair(a.seed, pid, 0u, (unsigned)(d / 2), e0, e1);
+        if (d < a.D) philox_normal_pair(a.seed, pid, 0u, (unsigned)(d / 2), T, e0, e1);
         w[d] = e0;
         w[d + 1] = (d + 1 < a.D) ? e1 : R(0);
       }
@@ -265,43 +414,12 @@ __global__ void __launch_bounds__(128) blr_generate_kernel(const BlrArgs a) {
         m2 = fma((R)c_blr_X[j * kBlrMax + d + 2], w[d + 2], m2);
         m3 = fma((R)c_blr_X[j * kBlrMax + d + 3], w[d + 3], m3);
       }
-      lw += logpdf_normal_ls<R>((R)c_blr_y[j], (m0 + m1) + (m2 + m3), sigma, log_sigma);
+      lw += logpdf_normal_fast<R>((R)c_blr_y[j], (m0 + m1) + (m2 + m3), inv_sigma, log_sigma);
     }
     logw[i] = lw;
-    lse3_push(acc, (double)lw);
+    acc = max_nan(acc, (double)lw);
   }
-  // publish_partials assumes kBlock threads per CTA for its shared scratch; 128 <= kBlock is fine
-  __shared__ Lse3 s_red[kBlock / 32];
-  __shared__ bool s_last;
-  {
-    Lse3 v = lse3_warp_reduce(acc);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) s_red[warp] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      Lse3 r = lse3_empty();
-      for (int k = 0; k < (int)(blockDim.x >> 5); k++) r = lse3_merge(r, s_red[k]);
-      a.partials[blockIdx.x] = r;
-      __threadfence();
-      unsigned int t = atomicAdd(a.ticket, 1u);
-      s_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    Lse3 r = lse3_empty();
-    for (unsigned int k = threadIdx.x; k < gridDim.x; k += blockDim.x) r = lse3_merge(r, load_partial(a.partials + k));
-    r = lse3_warp_reduce(r);
-    __syncthreads();
-    if (lane == 0) s_red[warp] = r;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      Lse3 t = lse3_empty();
-      for (int k = 0; k < (int)(blockDim.x >> 5); k++) t = lse3_merge(t, s_red[k]);
-      write_stats(a.stats, t);
-      *a.ticket = 0;
-    }
-  }
+  publish_max(acc, a.partials, a.ticket, a.stats);
 }
 
 // importance.jl:34,57: log_normalized_weights = log_weights .- log_total_weight

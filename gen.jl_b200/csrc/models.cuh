@@ -24,7 +24,7 @@ struct ModelParams {
 };
 
 // Per-thread constants hoisted out of the particle loop (log of fixed standard deviations etc.).
-template <typename R> struct Hoisted { R c0, c1, c2; };
+template <typename R> struct Hoisted { R c0, c1, c2, i0, i1, i2; };
 
 template <typename R, int KIND, int PK, bool INIT> struct Transition;
 
@@ -36,40 +36,43 @@ template <typename R, int PK, bool INIT> struct Transition<R, MODEL_LGSSM, PK, I
     h.c0 = Math<R>::log_((R)mp.p[4]);                  // log r
     h.c1 = Math<R>::log_((R)(INIT ? mp.p[1] : mp.p[3])); // log model std of x
     h.c2 = Math<R>::log_((R)mp.pa[2]);                 // log proposal std
+    h.i0 = R(1) / (R)mp.p[4];
+    h.i1 = R(1) / (R)(INIT ? mp.p[1] : mp.p[3]);
+    h.i2 = R(1) / (R)mp.pa[2];
     return h;
   }
-  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &h, const R *prev, R *next, const R *eps, const R *) {
+  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &h, const MathTables &, const R *prev, R *next, const R *eps, const R *) {
     R mu = INIT ? (R)mp.p[0] : (R)mp.p[2] * prev[0];
     R sd = INIT ? (R)mp.p[1] : (R)mp.p[3];
     if (PK == PROPOSAL_AFFINE_NORMAL) {
       R qmu = INIT ? (R)mp.pa[0] : (R)mp.pa[0] + (R)mp.pa[1] * prev[0];
       R x = random_normal<R>(qmu, (R)mp.pa[2], eps[0]);
-      R lq = logpdf_normal_ls<R>(x, qmu, (R)mp.pa[2], h.c2);
+      R lq = logpdf_normal_fast<R>(x, qmu, h.i2, h.c2);
       R w = R(0);
-      w += logpdf_normal_ls<R>(x, mu, sd, h.c1);
-      w += logpdf_normal_ls<R>((R)mp.obs0, x, (R)mp.p[4], h.c0);
+      w += logpdf_normal_fast<R>(x, mu, h.i1, h.c1);
+      w += logpdf_normal_fast<R>((R)mp.obs0, x, h.i0, h.c0);
       next[0] = x;
       return w - lq;
     }
     R x = random_normal<R>(mu, sd, eps[0]);
     next[0] = x;
-    return logpdf_normal_ls<R>((R)mp.obs0, x, (R)mp.p[4], h.c0);
+    return logpdf_normal_fast<R>((R)mp.obs0, x, h.i0, h.c0);
   }
 };
 
 // ---- cfg 2: stochastic volatility ----
 template <typename R, int PK, bool INIT> struct Transition<R, MODEL_SV, PK, INIT> {
   static constexpr int S = 1, NN = 1, NU = 0;
-  static GB_D Hoisted<R> hoist(const ModelParams &) { return Hoisted<R>{R(0), R(0), R(0)}; }
-  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &, const R *prev, R *next, const R *eps, const R *) {
+  static GB_D Hoisted<R> hoist(const ModelParams &) { return Hoisted<R>{R(0), R(0), R(0), R(0), R(0), R(0)}; }
+  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &, const MathTables &, const R *prev, R *next, const R *eps, const R *) {
     R mean = INIT ? (R)mp.p[0] : (R)mp.p[0] + (R)mp.p[1] * (prev[0] - (R)mp.p[0]);
     R sd = INIT ? (R)mp.p[3] : (R)mp.p[2];
     R hh = random_normal<R>(mean, sd, eps[0]);
     next[0] = hh;
-    // y ~ normal(0, exp(h/2)):  log(std) = h/2 (the reference evaluates log(exp(h/2)); the two agree
-    // to 1 ulp, far inside the 1e-10 weight tolerance, and the hoist saves an fp64 log per particle)
+    // y ~ normal(0, exp(h/2)):  log(std) = h/2 and 1/std = exp(-h/2) (the reference evaluates
+    // log(exp(h/2)) and divides; both agree to ~1 ulp, far inside the 1e-10 weight tolerance)
     R half = hh / R(2);
-    return logpdf_normal_ls<R>((R)mp.obs0, R(0), Math<R>::exp_(half), half);
+    return logpdf_normal_fast<R>((R)mp.obs0, R(0), Math<R>::exp_t(-half), half);
   }
 };
 
@@ -81,9 +84,11 @@ template <typename R, int PK, bool INIT> struct Transition<R, MODEL_BEARINGS, PK
     h.c0 = Math<R>::log_((R)mp.p[9]);      // log measurement_noise
     h.c1 = Math<R>::sqrt_((R)mp.p[8]);     // sqrt(velocity_var)
     h.c2 = R(0);
+    h.i0 = R(1) / (R)mp.p[9];
+    h.i1 = h.i2 = R(0);
     return h;
   }
-  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &h, const R *prev, R *next, const R *eps, const R *) {
+  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &h, const MathTables &T, const R *prev, R *next, const R *eps, const R *) {
     R x, y, vx, vy;
     if (INIT) {
       x = random_normal<R>((R)mp.p[0], (R)mp.p[1], eps[0]);
@@ -97,15 +102,15 @@ template <typename R, int PK, bool INIT> struct Transition<R, MODEL_BEARINGS, PK
       y = prev[1] + vy;
     }
     next[0] = x; next[1] = y; next[2] = vx; next[3] = vy;
-    return logpdf_normal_ls<R>((R)mp.obs0, Math<R>::atan2_(y, x), (R)mp.p[9], h.c0);
+    return logpdf_normal_fast<R>((R)mp.obs0, Math<R>::atan2_t(y, x, T), h.i0, h.c0);
   }
 };
 
 // ---- the reference's own PF test fixture: 3-state HMM (test/inference/particle_filter.jl:52-78) ----
 template <typename R, int PK, bool INIT> struct Transition<R, MODEL_HMM, PK, INIT> {
   static constexpr int S = 1, NN = 0, NU = 1;
-  static GB_D Hoisted<R> hoist(const ModelParams &) { return Hoisted<R>{R(0), R(0), R(0)}; }
-  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &, const R *prev, R *next, const R *, const R *us) {
+  static GB_D Hoisted<R> hoist(const ModelParams &) { return Hoisted<R>{R(0), R(0), R(0), R(0), R(0), R(0)}; }
+  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &, const MathTables &T, const R *prev, R *next, const R *, const R *us) {
     const int K = mp.K, M = mp.M;
     const double *prior = mp.tab, *trans = mp.tab + K, *emis = mp.tab + K + K * K;
     const double *zp = INIT ? prior : trans + ((long long)prev[0] - 1) * K;
@@ -113,16 +118,16 @@ template <typename R, int PK, bool INIT> struct Transition<R, MODEL_HMM, PK, INI
     if (PK == PROPOSAL_CATEGORICAL_TABLE) {
       const double *qp = INIT ? mp.ptab : mp.ptab + ((long long)prev[0] - 1) * K;
       long long z = random_categorical<R>(qp, K, us[0]);
-      R lq = logpdf_categorical<R>(z, qp, K);
+      R lq = logpdf_categorical_t<R>(z, qp, K, T);
       R w = R(0);
-      w += logpdf_categorical<R>(z, zp, K);
-      w += logpdf_categorical<R>(xo, emis + (z - 1) * M, M);
+      w += logpdf_categorical_t<R>(z, zp, K, T);
+      w += logpdf_categorical_t<R>(xo, emis + (z - 1) * M, M, T);
       next[0] = (R)z;
       return w - lq;
     }
     long long z = random_categorical<R>(zp, K, us[0]);
     next[0] = (R)z;
-    return logpdf_categorical<R>(xo, emis + (z - 1) * M, M);
+    return logpdf_categorical_t<R>(xo, emis + (z - 1) * M, M, T);
   }
 };
 

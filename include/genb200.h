@@ -102,10 +102,12 @@ int gb_pf_sync(gb_pf_t *pf);
 
 /* ---- sharded (one process per GPU) pieces of maybe_resample!; the host glue runs the collectives
  *      between them (gen.jl_b200/sharded.py).  All scalars are host values. ---- */
-/* local online log-sum-exp partials of the shard: m = max, s1 = sum exp(lw-m), s2 = sum exp(2(lw-m)) */
-int gb_pf_weight_partials(gb_pf_t *pf, double *m, double *s1, double *s2);
-/* local total of the integer-quantised weights floor(exp(lw - m_global) * 2^bits) */
-int gb_pf_quantized_total(gb_pf_t *pf, double m_global, int bits, uint64_t *q_local);
+/* max of the shard's log weights (NaN propagates like Julia's maximum; all-zero weights: 0.0) */
+int gb_pf_weight_max(gb_pf_t *pf, double *m_local);
+/* One pass over the shard's log weights w.r.t. the GLOBAL max m_ref (after the host's all-reduce):
+ * s1 = sum exp(lw - m_ref), s2 = sum exp(2 (lw - m_ref)) (inference.jl:3-6, particle_filter.jl:3-12) and
+ * q_local = sum floor(exp(lw - m_ref) * 2^bits), the shard's integer CDF mass; bits = gb_quant_bits(n_global). */
+int gb_pf_weight_sums(gb_pf_t *pf, double m_ref, int bits, double *s1, double *s2, uint64_t *q_local);
 /* Offspring of this shard's particles under global-prefix systematic resampling: the shard's
  * particles fill the global slot range [*slot_lo, *slot_hi).  Ancestors (global ids) for that range
  * are kept in the handle for gb_pf_export_offspring. */
@@ -157,7 +159,7 @@ int gb_philox_multinomial_u64(uint64_t seed, uint32_t step, int64_t k0, int64_t 
 int gb_quant_bits(int64_t n_global);                                   /* host-side, no GPU */
 
 /* ---- instrumentation for bench.py: per-kernel CUDA-event timings on the handle's stream ---- */
-enum { GB_K_STEP = 0, GB_K_FINALIZE = 1, GB_K_QTOTAL = 2, GB_K_TILESCAN = 3, GB_K_ANCESTORS = 4, GB_K_GATHER = 5,
+enum { GB_K_STEP = 0, GB_K_FINALIZE = 1 /* weight statistics */, GB_K_QTOTAL = 2, GB_K_TILESCAN = 3, GB_K_ANCESTORS = 4, GB_K_GATHER = 5,
        GB_K_MISC = 6, GB_K_COUNT = 7 };
 int gb_pf_enable_timing(gb_pf_t *pf, int on);
 /* ms[GB_K_COUNT], launches[GB_K_COUNT]; resets the accumulators */
@@ -170,6 +172,9 @@ int64_t gb_selftest_slots_below(uint64_t C, int64_t nslots, uint64_t q_total, ui
 int64_t gb_selftest_slots_below_residual(uint64_t chi, uint64_t clo, uint64_t q_total, uint32_t u0);
 uint64_t gb_selftest_div128(uint64_t ahi, uint64_t alo, uint64_t d);
 uint64_t gb_selftest_quantize(double x, int bits);
+/* fn: 0 log(a), 1 sin(2 pi a), 2 cos(2 pi a), 3 atan2(a, b), 4 exp(a), 5 u52(hi = a, lo = b): the engine's own
+ * fp64 elementary functions (csrc/gbmath.cuh), host instance (bit-identical to the device one) */
+double gb_selftest_math(int fn, double a, double b);
 void gb_selftest_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
 #ifdef __cplusplus

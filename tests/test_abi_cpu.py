@@ -159,3 +159,42 @@ def test_slots_below_matches_bigint_definition(g):
             X = ((C_ << 32) - 1) // Q
             exp = 0 if X < u0 else ((X - u0) >> 32) + 1
         assert lib.gb_selftest_slots_below_residual(C_ >> 64, C_ & (2 ** 64 - 1), Q, u0) == exp
+
+
+def test_gbmath_accuracy_against_mpmath(g):
+    """The engine's own fp64 log / sincos / atan2 / exp (csrc/gbmath.cuh) use only integer ops, fma and
+    IEEE + * / sqrt, so this host instance is bit-identical to the device one: accuracy <= 2 ulp."""
+    import math
+    import mpmath as mp
+    from genb200 import _lib as L
+    f = L.lib().gb_selftest_math
+    mp.mp.prec = 120
+    rnd = random.Random(1)
+
+    def ulps(got, exact):
+        e = float(exact)
+        return abs(mp.mpf(got) - exact) / (math.ulp(e) if e != 0 else mp.mpf(2) ** -1074)
+
+    worst = {"log": 0, "sin": 0, "cos": 0, "atan2": 0, "exp": 0}
+    for _ in range(4000):
+        for x in (rnd.random(), 2.0 ** (-rnd.uniform(0, 53)), 1 - 2.0 ** (-rnd.uniform(1, 52)), rnd.uniform(0.5, 2.0),
+                  10 ** rnd.uniform(-300, 300)):
+            worst["log"] = max(worst["log"], ulps(f(0, x, 0), mp.log(mp.mpf(x))))
+        u = rnd.random()
+        worst["sin"] = max(worst["sin"], abs(mp.mpf(f(1, u, 0)) - mp.sin(2 * mp.pi * mp.mpf(u))) * 2 ** 53)
+        worst["cos"] = max(worst["cos"], abs(mp.mpf(f(2, u, 0)) - mp.cos(2 * mp.pi * mp.mpf(u))) * 2 ** 53)
+        y, x = rnd.gauss(0, 1) * 10 ** rnd.uniform(-3, 3), rnd.gauss(0, 1) * 10 ** rnd.uniform(-3, 3)
+        worst["atan2"] = max(worst["atan2"], ulps(f(3, y, x), mp.atan2(mp.mpf(y), mp.mpf(x))))
+        y, x = rnd.uniform(0.9, 1.0), rnd.uniform(-0.05, 0.05)      # the bearings-only regime
+        worst["atan2"] = max(worst["atan2"], ulps(f(3, y, x), mp.atan2(mp.mpf(y), mp.mpf(x))))
+        a = rnd.uniform(-40, 40)
+        worst["exp"] = max(worst["exp"], ulps(f(4, a, 0), mp.exp(mp.mpf(a))))
+    assert all(v < 2.0 for v in worst.values()), worst
+    # special values / quadrants
+    assert f(1, 0.25, 0) == 1.0 and f(2, 0.5, 0) == -1.0 and f(1, 0.75, 0) == -1.0 and f(2, 0.0, 0) == 1.0
+    assert f(3, 0.0, -1.0) == math.pi and f(3, 1.0, 0.0) == math.pi / 2 and f(3, -1.0, 0.0) == -math.pi / 2
+    assert f(3, 0.0, 0.0) == 0.0 and f(0, 1.0, 0) == 0.0
+    for _ in range(1000):                     # the bit-trick uniform equals the reference definition
+        hi, lo = rnd.getrandbits(32), rnd.getrandbits(32)
+        v = ((hi << 32) | lo) >> 12
+        assert f(5, float(hi), float(lo)) == (v + 0.5) * 2.0 ** -52

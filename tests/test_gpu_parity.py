@@ -112,8 +112,9 @@ def test_logsumexp_and_ess(g, O, n):
     assert abs(ess - O.effective_sample_size(lnw)) <= 1e-9 * ess
     assert g.logsumexp(np.full(n, -np.inf)) == -np.inf                          # inference.jl:5
     if n == 4:
-        # test/inference/importance_sampling.jl:21: logsumexp(log_norm_weights) ~ 0 @ 1e-14
-        assert abs(g.logsumexp(lnw)) < 1e-14
+        # test/inference/importance_sampling.jl:21: logsumexp(log_norm_weights) ~ 0 @ 1e-14 (O(1) weights there)
+        _, lnw1 = O.normalize_weights(rng.standard_normal(4))
+        assert abs(g.logsumexp(lnw1)) < 1e-14
 
 
 # ---------------------------------------------------------------------------------------------
@@ -238,7 +239,9 @@ def test_pf_predrawn_noise_bit_exact(g, O, name, resampler, lazy):
     for t in range(1, len(ys)):
         u0 = int(rng.integers(0, 2 ** 32))
         u64 = rng.integers(0, 2 ** 64, size=n, dtype=np.uint64)
-        thr = n if t % 3 else n / 2            # mix "always" and ESS-triggered resampling
+        # mix "always" (ESS <= N < N + 0.5; exactly N would sit on the strict-< boundary of
+        # particle_filter.jl:256 when all weights are equal) and ESS-triggered resampling
+        thr = n + 0.5 if t % 3 else n / 2
         st.set_resample_noise(u0=u0, u64s=u64 if resampler == "multinomial" else None)
         did = g.maybe_resample_(st, ess_threshold=thr, resampler=resampler)
         did_ref = ref.maybe_resample(ess_threshold=thr, kind=okind(O, resampler), u0=u0, u64s=u64)
@@ -384,7 +387,8 @@ def test_kalman_exact_log_ml(g, O):
     for t in range(1, len(ys)):
         g.maybe_resample_(st, resampler="systematic")
         g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], return_incr=False)
-    assert abs(g.log_ml_estimate(st) - kf) < 0.02
+    # sd of log Z_hat at N = 2^20, T = 100 is ~0.013 (measured with the oracle): 5 sigma
+    assert abs(g.log_ml_estimate(st) - kf) < 0.065
 
 
 # ---------------------------------------------------------------------------------------------
