@@ -39,9 +39,11 @@ GB_DECL_COEFFS(atan, 4, -1.0 / 3.0, 0.2, -1.0 / 7.0, 1.0 / 9.0)
 // exp(r), |r| <= ln2/2: Taylor to r^13 (same values as oracle go_dexp: bit-identical quantisation)
 GB_DECL_COEFFS(exp, 12, 1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
                1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5)
-GB_DECL_COEFFS(misc, 8, GB_LN2_HI, GB_LN2_LO, GB_PI_HI, GB_PI_LO, GB_PIO2_HI, GB_PIO2_LO,
-               1.57079632679489655800e+00 /* pi/2 for the sincos argument */, 1.4426950408889634074 /* log2(e) */)
-enum { MI_LN2_HI = 0, MI_LN2_LO = 1, MI_PI_HI = 2, MI_PI_LO = 3, MI_PIO2_HI = 4, MI_PIO2_LO = 5, MI_PIO2 = 6, MI_LOG2E = 7 };
+GB_DECL_COEFFS(misc, 10, GB_LN2_HI, GB_LN2_LO, GB_PI_HI, GB_PI_LO, GB_PIO2_HI, GB_PIO2_LO,
+               1.57079632679489655800e+00 /* pi/2 for the sincos argument */, 1.4426950408889634074 /* log2(e) */,
+               -6.93147180369123816490e-01 /* -ln2 hi (exp reduction) */, -1.90821492927058770002e-10 /* -ln2 lo */)
+enum { MI_LN2_HI = 0, MI_LN2_LO = 1, MI_PI_HI = 2, MI_PI_LO = 3, MI_PIO2_HI = 4, MI_PIO2_LO = 5, MI_PIO2 = 6, MI_LOG2E = 7,
+       MI_NLN2_HI = 8, MI_NLN2_LO = 9 };
 
 // lookup tables (source of truth in constant memory / host memory; kernels stage them into smem)
 __constant__ double c_log_tab[2 * GB_LOG_TAB_N] = {GB_LOG_TAB_VALUES};
@@ -153,8 +155,8 @@ GB_HD void gb_sincos2pi(double u, double &s, double &c) {
 // exp(x) for |x| < 700 (same reduction and coefficients as the weight quantiser)
 GB_HD double gb_exp_parts(double x, int &kout) {
   const double kd = rint(dmul(x, KC(misc, MI_LOG2E)));
-  double r = fma(kd, -6.93147180369123816490e-01, x);
-  r = fma(kd, -1.90821492927058770002e-10, r);
+  double r = fma(kd, KC(misc, MI_NLN2_HI), x);
+  r = fma(kd, KC(misc, MI_NLN2_LO), r);
   double p = KC(exp, 0);
 #pragma unroll
   for (int i = 1; i < 12; i++) p = fma(p, r, KC(exp, i));
@@ -169,6 +171,32 @@ GB_HD double gb_exp(double x) {
   int k;
   const double p = gb_exp_parts(x, k);
   return p * pow2i(k);
+}
+
+// floor(exp(x) 2^b) for x = lw - max: bit-identical to common.cuh quantize() / oracle go_quantize(), but
+// branch-free and with every coefficient read from the constant bank (the v0 ancestors kernel spent 14%
+// of its issue slots on UMOVs rebuilding these immediates)
+GB_HD uint64_t quantize_k(double x, int b) {
+  const bool dead = !(x > -708.0);            // NaN, -Inf, below the representable floor
+  double xc = dead ? -708.0 : x;
+  xc = xc > 0.0 ? 0.0 : xc;
+  int k;
+  const double p = gb_exp_parts(xc, k);
+  const int e = k + b;
+  const uint64_t q = (uint64_t)dmul(p, pow2i(e < 0 ? 0 : e));
+  return (dead || e < 0) ? 0 : q;
+}
+// exp(x) and floor(exp(x) 2^b) from ONE polynomial evaluation (weight statistics pass)
+GB_HD void exp_and_quantize(double x, int b, double &ex, uint64_t &q) {
+  const bool dead = !(x > -708.0);
+  double xc = dead ? -708.0 : x;
+  xc = xc > 0.0 ? 0.0 : xc;
+  int k;
+  const double p = gb_exp_parts(xc, k);
+  const int e = k + b;
+  const uint64_t qq = (uint64_t)dmul(p, pow2i(e < 0 ? 0 : e));
+  q = (dead || e < 0) ? 0 : qq;
+  ex = dead ? 0.0 : p * pow2i(k);
 }
 
 // atan2(y, x) for finite arguments whose exponents are within +-1000 (anything else: libm)

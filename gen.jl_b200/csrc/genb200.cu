@@ -628,15 +628,16 @@ static int ensure_max(gb_pf *pf, const void *logw) {
 static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_device) {
   const int bits = quant_bits(pf->n_global);
   CK(cudaMemsetAsync(pf->super_q, 0, (size_t)(pf->nsuper + 1) * 8, pf->stream));
+  CK(cudaMemsetAsync(pf->tile_q, 0, (size_t)(pf->ntiles + 1) * 8, pf->stream));
   if (pf->dtype == GB_F64) {
     auto kern = wstats_kernel<double>;
-    int grid = grid_for(pf, kern, pf->ntiles * kBlock, kBlock);
-    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)logw, pf->n, m_arg, from_device ? 1 : 0, bits, pf->tile_q,
+    int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
+    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)logw, pf->n, m_arg, from_device ? 1 : 0, bits, (unsigned long long *)pf->tile_q,
                                                                      pf->super_q, pf->partials, pf->ticket, pf->d_stats));
   } else {
     auto kern = wstats_kernel<float>;
-    int grid = grid_for(pf, kern, pf->ntiles * kBlock, kBlock);
-    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)logw, pf->n, m_arg, from_device ? 1 : 0, bits, pf->tile_q,
+    int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
+    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)logw, pf->n, m_arg, from_device ? 1 : 0, bits, (unsigned long long *)pf->tile_q,
                                                                      pf->super_q, pf->partials, pf->ticket, pf->d_stats));
   }
   CK(cudaGetLastError());
@@ -1277,7 +1278,7 @@ extern "C" int64_t gb_selftest_slots_below_residual(uint64_t chi, uint64_t clo, 
   return slots_below_residual(chi, clo, sp);
 }
 extern "C" uint64_t gb_selftest_div128(uint64_t ahi, uint64_t alo, uint64_t d) { return div128_64(ahi, alo, d, 1.0 / (double)d); }
-extern "C" uint64_t gb_selftest_quantize(double x, int bits) { return quantize(x, bits); }
+extern "C" uint64_t gb_selftest_quantize(double x, int bits) { return quantize_k(x, bits) == quantize(x, bits) ? quantize_k(x, bits) : ~0ull; }
 // fn: 0 log(a), 1 sin(2 pi a), 2 cos(2 pi a), 3 atan2(a, b), 4 exp(a), 5 u52_fast(hi = a, lo = b)
 extern "C" double gb_selftest_math(int fn, double a, double b) {
   MathTables T = host_math_tables();

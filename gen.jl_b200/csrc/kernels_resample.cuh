@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kBlock) qtotal_kernel(const R *__restrict__ lo
     U128 sr = {0, 0};
 #pragma unroll
     for (int j = 0; j < kItems; j++) {
-      uint64_t q = quantize(lw[j] - m, bits);
+      uint64_t q = quantize_k(lw[j] - m, bits);
       if (SWEEP == SWEEP_RESIDUAL) {
         uint64_t c, r;
         residual_split(q, n_global, q_total, c, r);
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kBlock) ancestors_kernel(const R *__restrict__
     U128 tr = {0, 0};
 #pragma unroll
     for (int j = 0; j < kItems; j++) {
-      uint64_t q = quantize(lw[j] - m, bits), rr;
+      uint64_t q = quantize_k(lw[j] - m, bits), rr;
       residual_split(q, n_global, sp.q_total, c[j], rr);
       tc += c[j];
       tr = u128_add(tr, u128_make(rr));
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kBlock) ancestors_kernel(const R *__restrict__
     uint64_t t = 0;
 #pragma unroll
     for (int j = 0; j < kItems; j++) {
-      t += quantize(lw[j] - m, bits);
+      t += quantize_k(lw[j] - m, bits);
       c[j] = t;
     }
     uint64_t dummy64;
@@ -568,40 +568,102 @@ __global__ void __launch_bounds__(1024) superscan_kernel(long long nsuper, const
 constexpr int kSlotPad = kChunk + kChunk / 32;
 GB_D int pad_idx(int i) { return i + (i >> 5); }
 
-// Scan one tile and fill the ancestors of output slots [lo, hi) (hi - lo <= kChunk) that belong to it.
-// cbase = integer CDF mass before the tile (including q_offset); slot0 = first slot of the tile.
-template <typename R>
+// number of slots below CDF value C: double-precision estimate, exact only when the estimate is within
+// 2^-17 slots of a boundary; `slow` is set instead of branching so callers can batch the rare fix-ups
+GB_D int slots_estimate(uint64_t C, double ratio, double u0term, bool &slow) {
+  const double y = fma((double)C, ratio, u0term);
+  const double cc = ceil(y);
+  const bool neg = y < -0x1p-17;
+  slow = !(neg || (cc - y > 0x1p-17 && y - (cc - 1.0) > 0x1p-17));
+  return neg ? 0 : __double2int_rz(cc);
+}
+
+// Shared-memory scratch of one ancestors CTA
+struct TileSmem {
+  uint64_t warp64[kBlock / 32 + 1];
+  int slot[kSlotPad];
+  int kend_last[kBlock];
+  uint64_t cbase;
+  long long slot0;
+};
+
+// Scan one tile and fill the ancestors of the output slots [lo, hi) (hi - lo <= kChunk) that belong to it.
+//   PREFIX = true : regular CTA.  cbase (integer CDF mass before the tile) is produced by warp 0 from the
+//                   super-tile prefix while the other warps already quantise; [lo, hi) = the tile's first
+//                   kChunk slots; returns the tile's slot range through slot0_out / slot_end_out.
+//   PREFIX = false: overflow CTA.  cbase / slot0 / [lo, hi) are given.
+template <typename R, bool PREFIX>
 GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits, const SweepParams &sp, long long tile,
-                    uint64_t cbase, long long slot0, long long lo, long long hi, int *__restrict__ anc, long long anc_base,
-                    uint64_t *s_warp64, int *s_slot, long long *s_kend_last) {
+                    const uint64_t *__restrict__ tile_q, const unsigned long long *__restrict__ super_excl, uint64_t q_offset,
+                    uint64_t cbase_in, long long slot0_in, long long lo_in, long long hi_in, int *__restrict__ anc,
+                    long long anc_base, TileSmem &sm, long long *slot0_out, long long *slot_end_out) {
   double lw[kItems];
   load_items<R>(logw, tile * kTile, n, lw);
+  const double u0term = -(double)sp.u0 * 0x1p-32;
+  // clear the slot window (upper bound on the tile's slot count from its CDF mass) while the loads fly
+  int clear_cnt;
+  if (PREFIX) {
+    const double est = (double)tile_q[tile] * sp.ratio + 2.0;
+    clear_cnt = est > (double)kChunk ? kChunk : (int)est;
+  } else {
+    clear_cnt = (int)(hi_in - lo_in);
+  }
+  for (int i = threadIdx.x; i < clear_cnt; i += kBlock) sm.slot[pad_idx(i)] = -1;
+  if (PREFIX && threadIdx.x < 32) {
+    // CDF mass before this tile: super-tile prefix + the (<= 63) tile totals before it inside the super-tile
+    const long long sbase = (tile / kSuper) * kSuper;
+    uint64_t v = 0;
+    for (long long i = sbase + threadIdx.x; i < tile; i += 32) v += tile_q[i];
+    v = warp_sum_u64(v);
+    if (threadIdx.x == 0) sm.cbase = q_offset + super_excl[tile / kSuper] + v;
+  }
   uint64_t c[kItems];
   uint64_t t = 0;
 #pragma unroll
   for (int j = 0; j < kItems; j++) {
-    t += quantize(lw[j] - m, bits);
+    t += quantize_k(lw[j] - m, bits);
     c[j] = t;
   }
   uint64_t total;
-  const uint64_t ex = block_exclusive_scan(t, s_warp64, &total);
-  long long kend[kItems];
-#pragma unroll
-  for (int j = 0; j < kItems; j++) kend[j] = slots_below_fast(cbase + ex + c[j], sp);
-  s_kend_last[threadIdx.x] = kend[kItems - 1];
-  // clear the slot window
-  const int cnt = (int)(hi - lo);
-  for (int i = threadIdx.x; i < cnt; i += kBlock) s_slot[pad_idx(i)] = -1;
-  __syncthreads();
-  // head flags: particle j owns slots [kstart_j, kend_j); it marks the first of them that is inside [lo, hi)
-  long long kstart = threadIdx.x == 0 ? slot0 : s_kend_last[threadIdx.x - 1];
+  const uint64_t ex = block_exclusive_scan(t, sm.warp64, &total);   // two barriers: sm.cbase is visible after it
+  const uint64_t cbase = PREFIX ? sm.cbase : cbase_in;
+  // offspring end of every particle; rare exact fix-ups batched after the unrolled loop
+  int kend[kItems];
+  unsigned slow = 0;
 #pragma unroll
   for (int j = 0; j < kItems; j++) {
-    const long long ke = kend[j];
-    if (ke > kstart && ke > lo && kstart < hi) {
-      const long long pos = (kstart > lo ? kstart : lo) - lo;
-      s_slot[pad_idx((int)pos)] = threadIdx.x * kItems + j;
-    }
+    bool sl;
+    kend[j] = slots_estimate(cbase + ex + c[j], sp.ratio, u0term, sl);
+    slow |= sl ? (1u << j) : 0u;
+  }
+  if (slow) {
+#pragma unroll
+    for (int j = 0; j < kItems; j++)
+      if (slow & (1u << j)) kend[j] = (int)slots_below(cbase + ex + c[j], sp);
+  }
+  sm.kend_last[threadIdx.x] = kend[kItems - 1];
+  if (PREFIX && threadIdx.x == 0) {
+    bool sl;
+    int s0 = slots_estimate(cbase, sp.ratio, u0term, sl);
+    if (sl) s0 = (int)slots_below(cbase, sp);
+    sm.slot0 = s0;
+  }
+  __syncthreads();
+  const long long slot0 = PREFIX ? sm.slot0 : slot0_in;
+  const long long slot_end = sm.kend_last[kBlock - 1];
+  if (PREFIX) { *slot0_out = slot0; *slot_end_out = slot_end; }
+  const long long lo = PREFIX ? slot0 : lo_in;
+  long long hi = PREFIX ? slot_end : hi_in;
+  if (PREFIX && hi > lo + kChunk) hi = lo + kChunk;
+  const int cnt = (int)(hi - lo);
+  if (cnt <= 0) return;                       // uniform across the CTA
+  // head flags: particle j owns slots [kstart_j, kend_j); it marks the first of them that is inside [lo, hi)
+  int kstart = threadIdx.x == 0 ? (int)slot0 : sm.kend_last[threadIdx.x - 1];
+  const int ilo = (int)lo, ihi = (int)hi;
+#pragma unroll
+  for (int j = 0; j < kItems; j++) {
+    const int ke = kend[j];
+    if (ke > kstart && ke > ilo && kstart < ihi) sm.slot[pad_idx((kstart > ilo ? kstart : ilo) - ilo)] = threadIdx.x * kItems + j;
     kstart = ke;
   }
   __syncthreads();
@@ -612,9 +674,8 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
   int run = -1;
   for (int i = 0; i < L; i++) {
     const int k = base + i;
-    if (k < cnt) { const int v = s_slot[pad_idx(k)]; run = v > run ? v : run; }
+    if (k < cnt) { const int v = sm.slot[pad_idx(k)]; run = v > run ? v : run; }
   }
-  // block-wide exclusive max-scan of the per-thread maxima
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int inc = run;
 #pragma unroll
@@ -622,8 +683,7 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
     int o = __shfl_up_sync(0xffffffffu, inc, d);
     if (lane >= d) inc = o > inc ? o : inc;
   }
-  int *s_wmax = reinterpret_cast<int *>(s_warp64);   // 8 ints fit in the 9 x u64 scratch
-  __syncthreads();
+  int *s_wmax = reinterpret_cast<int *>(sm.warp64);   // 8 ints fit in the 9 x u64 scratch (free since the barrier above)
   if (lane == 31) s_wmax[warp] = inc;
   __syncthreads();
   int pre = -1;
@@ -634,16 +694,16 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
   for (int i = 0; i < L; i++) {
     const int k = base + i;
     if (k < cnt) {
-      const int v = s_slot[pad_idx(k)];
+      const int v = sm.slot[pad_idx(k)];
       run = v > run ? v : run;
-      s_slot[pad_idx(k)] = run;
+      sm.slot[pad_idx(k)] = run;
     }
   }
   __syncthreads();
   // coalesced copy-out
   const int tile_base = (int)(tile * kTile);
   int *__restrict__ out = anc + (lo - anc_base);
-  for (int i = threadIdx.x; i < cnt; i += kBlock) __stcs(out + i, tile_base + s_slot[pad_idx(i)]);
+  for (int i = threadIdx.x; i < cnt; i += kBlock) __stcs(out + i, tile_base + sm.slot[pad_idx(i)]);
 }
 
 template <typename R>
@@ -653,37 +713,14 @@ __global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const R *__restri
                                                                const ResamplePlan *__restrict__ plan, int *__restrict__ anc,
                                                                long long anc_base, OverflowEntry *__restrict__ oflow,
                                                                unsigned int *__restrict__ oflow_count) {
-  __shared__ uint64_t s_warp64[kBlock / 32 + 1];
-  __shared__ int s_slot[kSlotPad];
-  __shared__ long long s_kend_last[kBlock];
-  __shared__ uint64_t s_cbase;
-  __shared__ long long s_slot0, s_slot_end;
+  __shared__ TileSmem sm;
   const SweepParams sp = plan->sp;
   const long long tile = blockIdx.x;
-  // CDF mass before this tile: super-tile prefix + the (<= 63) tile totals before it inside the super-tile
-  if (threadIdx.x < 32) {
-    const long long sbase = (tile / kSuper) * kSuper;
-    uint64_t v = 0;
-    for (long long i = sbase + threadIdx.x; i < tile; i += 32) v += tile_q[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += shfl_u64(v, (threadIdx.x ^ o) & 31);
-    if (threadIdx.x == 0) {
-      const uint64_t cb = plan->q_offset + super_excl[tile / kSuper] + v;
-      s_cbase = cb;
-      s_slot0 = slots_below(cb, sp);
-      s_slot_end = slots_below(cb + tile_q[tile], sp);   // == offspring end of the tile's last particle
-    }
-  }
-  __syncthreads();
-  const uint64_t cbase = s_cbase;
-  const long long slot0 = s_slot0, slot_end = s_slot_end;
-  if (slot_end <= slot0) return;     // no particle of this tile has offspring
-  long long hi = slot_end;
-  if (hi > slot0 + kChunk) hi = slot0 + kChunk;
-  tile_fill<R>(logw, n, m, bits, sp, tile, cbase, slot0, slot0, hi, anc, anc_base, s_warp64, s_slot, s_kend_last);
+  long long slot0, slot_end;
+  tile_fill<R, true>(logw, n, m, bits, sp, tile, tile_q, super_excl, plan->q_offset, 0, 0, 0, 0, anc, anc_base, sm, &slot0, &slot_end);
   if (slot_end > slot0 + kChunk && threadIdx.x == 0) {
     const unsigned int e = atomicAdd(oflow_count, 1u);
-    oflow[e] = OverflowEntry{tile, slot0, slot0 + kChunk, slot_end, cbase};
+    oflow[e] = OverflowEntry{tile, slot0, slot0 + kChunk, slot_end, sm.cbase};
   }
 }
 
@@ -694,9 +731,7 @@ __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restric
                                                               const ResamplePlan *__restrict__ plan, int *__restrict__ anc,
                                                               long long anc_base, const OverflowEntry *__restrict__ oflow,
                                                               const unsigned int *__restrict__ oflow_count) {
-  __shared__ uint64_t s_warp64[kBlock / 32 + 1];
-  __shared__ int s_slot[kSlotPad];
-  __shared__ long long s_kend_last[kBlock];
+  __shared__ TileSmem sm;
   const unsigned int ne = *oflow_count;
   if (ne == 0) return;
   const SweepParams sp = plan->sp;
@@ -704,14 +739,15 @@ __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restric
   for (unsigned int e = 0; e < ne; e++) {
     const OverflowEntry en = oflow[e];
     const long long pieces = (en.slot_hi - en.slot_lo + kChunk - 1) / kChunk;
-    // first piece of this entry handled by this CTA
+    // first piece of this entry handled by this CTA (units are dealt round-robin over the grid)
     long long first = ((long long)blockIdx.x - unit0 % gridDim.x + gridDim.x) % gridDim.x;
     for (long long pc = first; pc < pieces; pc += gridDim.x) {
       const long long lo = en.slot_lo + pc * kChunk;
       long long hi = lo + kChunk;
       if (hi > en.slot_hi) hi = en.slot_hi;
       __syncthreads();
-      tile_fill<R>(logw, n, m, bits, sp, en.tile, en.cbase, en.slot0, lo, hi, anc, anc_base, s_warp64, s_slot, s_kend_last);
+      tile_fill<R, false>(logw, n, m, bits, sp, en.tile, nullptr, nullptr, 0, en.cbase, en.slot0, lo, hi, anc, anc_base, sm, nullptr,
+                          nullptr);
     }
     unit0 += pieces;
   }

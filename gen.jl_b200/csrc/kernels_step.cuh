@@ -45,6 +45,16 @@ template <> GB_D void vstore<double>(double *p, const double (&i)[2]) {
 template <> GB_D void vstore<float>(float *p, const float (&i)[4]) {
   __stcs(reinterpret_cast<float4 *>(p), make_float4(i[0], i[1], i[2], i[3]));
 }
+// plain (L2-allocating) load for data another pass re-reads
+template <typename R> GB_D void vload_keep(const R *p, R (&out)[VecOf<R>::V]);
+template <> GB_D void vload_keep<double>(const double *p, double (&o)[2]) {
+  double2 v = *reinterpret_cast<const double2 *>(p);
+  o[0] = v.x; o[1] = v.y;
+}
+template <> GB_D void vload_keep<float>(const float *p, float (&o)[4]) {
+  float4 v = *reinterpret_cast<const float4 *>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
 // plain (L2-allocating) store for data the very next kernel re-reads
 template <typename R> GB_D void vstore_keep(R *p, const R (&in)[VecOf<R>::V]);
 template <> GB_D void vstore_keep<double>(double *p, const double (&i)[2]) {
@@ -70,6 +80,8 @@ struct StepArgs {
   WeightStats *stats;     // stats->m receives the max of the new log weights
   ModelParams mp;
 };
+
+template <typename T> GB_D void prefetch_l2(const T *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // maximum() with Julia's NaN propagation (inference.jl:4)
 GB_D double max_nan(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
@@ -128,7 +140,21 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs a) {
   double acc = -INFINITY;
 
   const long long nvec = (a.n + V - 1) / V;
-  for (long long iv = (long long)blockIdx.x * kBlock + threadIdx.x; iv < nvec; iv += (long long)gridDim.x * kBlock) {
+  const long long stride = (long long)gridDim.x * kBlock;
+  long long iv = (long long)blockIdx.x * kBlock + threadIdx.x;
+  // Software pipeline for the indirection anc -> state (two dependent DRAM round trips per iteration in
+  // v0, 51% long-scoreboard stalls): the ancestor indices are loaded two iterations ahead into registers
+  // and the ancestor rows of the next iteration are prefetched into L2 while this one computes.
+  int src_cur[V], src_nxt[V];
+  auto load_anc = [&](long long ivx, int (&dst)[V]) {
+    if constexpr (V == 2) { int2 t = __ldcs(reinterpret_cast<const int2 *>(a.anc + ivx * V)); dst[0] = t.x; dst[1] = t.y; }
+    else { int4 t = __ldcs(reinterpret_cast<const int4 *>(a.anc + ivx * V)); dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w; }
+  };
+  if (!INIT && GATHER) {
+    if (iv < nvec) load_anc(iv, src_cur);
+    if (iv + stride < nvec) load_anc(iv + stride, src_nxt);
+  }
+  for (; iv < nvec; iv += stride) {
     const long long i0 = iv * V;
     R prev[S > 0 ? S : 1][V];
     R lw_old[V];
@@ -136,19 +162,30 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs a) {
       if (GATHER) {
         // deferred maybe_resample! gather (particle_filter.jl:264-267): slot k continues the trace of
         // ancestor anc[k]; its log weight was reset to exactly 0.0
-        int src[V];
-        if constexpr (V == 2) { int2 t = __ldcs(reinterpret_cast<const int2 *>(a.anc + i0)); src[0] = t.x; src[1] = t.y; }
-        else { int4 t = __ldcs(reinterpret_cast<const int4 *>(a.anc + i0)); src[0] = t.x; src[1] = t.y; src[2] = t.z; src[3] = t.w; }
 #pragma unroll
         for (int s = 0; s < S; s++)
 #pragma unroll
-          for (int v = 0; v < V; v++) prev[s][v] = __ldg(sin + (long long)s * a.ld + src[v]);
+          for (int v = 0; v < V; v++) prev[s][v] = __ldg(sin + (long long)s * a.ld + src_cur[v]);
 #pragma unroll
         for (int v = 0; v < V; v++) lw_old[v] = R(0);
+        if (iv + stride < nvec) {
+#pragma unroll
+          for (int s = 0; s < S; s++)
+#pragma unroll
+            for (int v = 0; v < V; v++) prefetch_l2(sin + (long long)s * a.ld + src_nxt[v]);
+#pragma unroll
+          for (int v = 0; v < V; v++) src_cur[v] = src_nxt[v];
+          if (iv + 2 * stride < nvec) load_anc(iv + 2 * stride, src_nxt);
+        }
       } else {
 #pragma unroll
         for (int s = 0; s < S; s++) vload<R>(sin + (long long)s * a.ld + i0, prev[s]);
         vload<R>(logw + i0, lw_old);
+        if (iv + stride < nvec) {
+#pragma unroll
+          for (int s = 0; s < S; s++) prefetch_l2(sin + (long long)s * a.ld + i0 + stride * V);
+          prefetch_l2(logw + i0 + stride * V);
+        }
       }
     }
     R next[S][V], w[V];
@@ -222,44 +259,39 @@ constexpr int kSuper = 64;   // tiles per super-tile
 template <typename R> GB_D void load_items(const R *__restrict__ logw, long long base, long long n, double (&lw)[kItems]);
 template <> GB_D void load_items<double>(const double *__restrict__ logw, long long base, long long n, double (&lw)[kItems]) {
   const long long i0 = base + (long long)threadIdx.x * kItems;
+  const bool full = base + kTile <= n;
 #pragma unroll
   for (int j = 0; j < kItems; j += 2) {
     // arrays are padded to a multiple of kTile elements, so the vector load is always in bounds
     double2 v = *reinterpret_cast<const double2 *>(logw + i0 + j);
-    lw[j] = (i0 + j < n) ? v.x : -INFINITY;
-    lw[j + 1] = (i0 + j + 1 < n) ? v.y : -INFINITY;
+    lw[j] = (full || i0 + j < n) ? v.x : -INFINITY;
+    lw[j + 1] = (full || i0 + j + 1 < n) ? v.y : -INFINITY;
   }
 }
 template <> GB_D void load_items<float>(const float *__restrict__ logw, long long base, long long n, double (&lw)[kItems]) {
   const long long i0 = base + (long long)threadIdx.x * kItems;
+  const bool full = base + kTile <= n;
 #pragma unroll
   for (int j = 0; j < kItems; j += 4) {
     float4 v = *reinterpret_cast<const float4 *>(logw + i0 + j);
-    lw[j] = (i0 + j < n) ? (double)v.x : -INFINITY;
-    lw[j + 1] = (i0 + j + 1 < n) ? (double)v.y : -INFINITY;
-    lw[j + 2] = (i0 + j + 2 < n) ? (double)v.z : -INFINITY;
-    lw[j + 3] = (i0 + j + 3 < n) ? (double)v.w : -INFINITY;
+    lw[j] = (full || i0 + j < n) ? (double)v.x : -INFINITY;
+    lw[j + 1] = (full || i0 + j + 1 < n) ? (double)v.y : -INFINITY;
+    lw[j + 2] = (full || i0 + j + 2 < n) ? (double)v.z : -INFINITY;
+    lw[j + 3] = (full || i0 + j + 3 < n) ? (double)v.w : -INFINITY;
   }
 }
 
-// exp(x) and floor(exp(x) 2^bits) for x = lw - m <= 0 from ONE polynomial evaluation; the integer is
-// bit-identical to common.cuh quantize() / oracle go_quantize()
-GB_D void exp_and_quantize(double x, int bits, double &e, uint64_t &q) {
-  if (!(x > -708.0)) { e = 0.0; q = 0; return; }
-  if (x > 0.0) x = 0.0;
-  int k;
-  const double p = gb_exp_parts(x, k);
-  e = p * pow2i(k);
-  const int eb = k + bits;
-  q = eb < 0 ? 0 : (uint64_t)dmul(p, pow2i(eb));
-}
-
-GB_D uint64_t block_sum_u64(uint64_t v, uint64_t *smem /* kBlock/32 */) {
+// 64-bit warp sum
+GB_D uint64_t warp_sum_u64(uint64_t v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, o), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), o);
     v += ((uint64_t)hi << 32) | lo;
   }
+  return v;
+}
+GB_D uint64_t block_sum_u64(uint64_t v, uint64_t *smem /* kBlock/32 */) {
+  v = warp_sum_u64(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();
   if (lane == 0) smem[warp] = v;
@@ -270,34 +302,48 @@ GB_D uint64_t block_sum_u64(uint64_t v, uint64_t *smem /* kBlock/32 */) {
   return r;  // valid in every thread
 }
 
+// Each WARP owns 256-particle segments (no CTA barrier in the streaming loop): striped 128-bit loads,
+// one exp per particle, 64-bit shuffle reduction of the quantised mass, two integer atomics per segment
+// (tile_q / super_q must be zeroed by the caller).
 template <typename R>
 __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ logw, long long n, double m_arg, int m_from_device,
-                                                        int bits, uint64_t *__restrict__ tile_q,
+                                                        int bits, unsigned long long *__restrict__ tile_q,
                                                         unsigned long long *__restrict__ super_q, double2 *partials,
                                                         unsigned int *ticket, WeightStats *stats) {
+  constexpr int V = VecOf<R>::V;
+  constexpr int kSeg = 256, kPerLane = kSeg / 32, kLoads = kPerLane / V;
   __shared__ uint64_t s_u64[kBlock / 32];
   __shared__ double2 s_d2[kBlock / 32];
   __shared__ bool s_last;
   const double m = m_from_device ? __ldcg(&stats->m) : m_arg;
   const long long ntiles = (n + kTile - 1) / kTile;
+  const long long nseg = ntiles * (kTile / kSeg);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double s1 = 0.0, s2 = 0.0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    double lw[kItems];
-    load_items<R>(logw, tile * kTile, n, lw);
+  for (long long seg = (long long)blockIdx.x * (kBlock / 32) + warp; seg < nseg; seg += (long long)gridDim.x * (kBlock / 32)) {
+    const long long base = seg * kSeg;
+    const bool full = base + kSeg <= n;
     uint64_t sq = 0;
 #pragma unroll
-    for (int j = 0; j < kItems; j++) {
-      double e;
-      uint64_t q;
-      exp_and_quantize(lw[j] - m, bits, e, q);
-      s1 += e;
-      s2 = fma(e, e, s2);
-      sq += q;
+    for (int j = 0; j < kLoads; j++) {
+      const long long i0 = base + (long long)(j * 32 + lane) * V;   // padded arrays: always in bounds
+      R v[V];
+      vload_keep<R>(logw + i0, v);
+#pragma unroll
+      for (int k = 0; k < V; k++) {
+        double e;
+        uint64_t q;
+        const double lw = (full || i0 + k < n) ? (double)v[k] : -INFINITY;
+        exp_and_quantize(lw - m, bits, e, q);
+        s1 += e;
+        s2 = fma(e, e, s2);
+        sq += q;
+      }
     }
-    const uint64_t tq = block_sum_u64(sq, s_u64);
-    if (threadIdx.x == 0) {
-      tile_q[tile] = tq;
-      atomicAdd(super_q + tile / kSuper, (unsigned long long)tq);
+    sq = warp_sum_u64(sq);
+    if (lane == 0) {
+      atomicAdd(tile_q + seg / (kTile / kSeg), (unsigned long long)sq);
+      atomicAdd(super_q + seg / (kTile / kSeg) / kSuper, (unsigned long long)sq);
     }
   }
   // CTA partial sums (fixed order => deterministic for a fixed grid)
@@ -306,7 +352,6 @@ __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ lo
     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) s_d2[warp] = make_double2(s1, s2);
   __syncthreads();
   if (threadIdx.x == 0) {
