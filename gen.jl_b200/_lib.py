@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgenb200.so")
+# GENB200_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("GENB200_LIB") or os.path.join(_HERE, "libgenb200.so")
 
 OK, EINVAL, ENOGPU, ECUDA, EUNSUPPORTED, ESTATE = range(6)
 MODEL_LGSSM, MODEL_SV, MODEL_BEARINGS, MODEL_HMM, MODEL_BLR = 1, 2, 3, 4, 5

@@ -565,8 +565,8 @@ __global__ void __launch_bounds__(1024) superscan_kernel(long long nsuper, const
   }
 }
 
-constexpr int kSlotPad = kChunk + kChunk / 32;
-GB_D int pad_idx(int i) { return i + (i >> 5); }
+constexpr int kHeavyCap = 16;                       // offspring a thread writes itself; more => CTA-cooperative fill
+constexpr int kHeavyMax = kChunk / (kHeavyCap + 1) + 2;
 
 // number of slots below CDF value C: double-precision estimate, exact only when the estimate is within
 // 2^-17 slots of a boundary; `slow` is set instead of branching so callers can batch the rare fix-ups
@@ -574,15 +574,18 @@ GB_D int slots_estimate(uint64_t C, double ratio, double u0term, bool &slow) {
   const double y = fma((double)C, ratio, u0term);
   const double cc = ceil(y);
   const bool neg = y < -0x1p-17;
-  slow = !(neg || (cc - y > 0x1p-17 && y - (cc - 1.0) > 0x1p-17));
+  // cc - y in (2^-17, 1 - 2^-17)  <=>  |cc - y - 1/2| < 1/2 - 2^-17
+  slow = !(neg || fabs((cc - y) - 0.5) < 0.5 - 0x1p-17);
   return neg ? 0 : __double2int_rz(cc);
 }
 
 // Shared-memory scratch of one ancestors CTA
 struct TileSmem {
   uint64_t warp64[kBlock / 32 + 1];
-  int slot[kSlotPad];
+  int slot[kChunk];
   int kend_last[kBlock];
+  int3 heavy[kHeavyMax];      // (particle, first slot, end slot) of particles with many offspring
+  int nheavy;
   uint64_t cbase;
   long long slot0;
 };
@@ -592,6 +595,10 @@ struct TileSmem {
 //                   super-tile prefix while the other warps already quantise; [lo, hi) = the tile's first
 //                   kChunk slots; returns the tile's slot range through slot0_out / slot_end_out.
 //   PREFIX = false: overflow CTA.  cbase / slot0 / [lo, hi) are given.
+// Fill: every particle writes its own (usually 0-2) offspring slots into a shared window; particles with
+// more than kHeavyCap offspring are queued and their ranges filled by the whole CTA; the window is then
+// copied out with coalesced stores.  (v1 used head flags + a max-scan: 127 of its 162 instructions per
+// particle were fill bookkeeping, profiles/r1_ancestors.md.)
 template <typename R, bool PREFIX>
 GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits, const SweepParams &sp, long long tile,
                     const uint64_t *__restrict__ tile_q, const unsigned long long *__restrict__ super_excl, uint64_t q_offset,
@@ -600,15 +607,7 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
   double lw[kItems];
   load_items<R>(logw, tile * kTile, n, lw);
   const double u0term = -(double)sp.u0 * 0x1p-32;
-  // clear the slot window (upper bound on the tile's slot count from its CDF mass) while the loads fly
-  int clear_cnt;
-  if (PREFIX) {
-    const double est = (double)tile_q[tile] * sp.ratio + 2.0;
-    clear_cnt = est > (double)kChunk ? kChunk : (int)est;
-  } else {
-    clear_cnt = (int)(hi_in - lo_in);
-  }
-  for (int i = threadIdx.x; i < clear_cnt; i += kBlock) sm.slot[pad_idx(i)] = -1;
+  if (threadIdx.x == 0) sm.nheavy = 0;
   if (PREFIX && threadIdx.x < 32) {
     // CDF mass before this tile: super-tile prefix + the (<= 63) tile totals before it inside the super-tile
     const long long sbase = (tile / kSuper) * kSuper;
@@ -657,53 +656,31 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
   if (PREFIX && hi > lo + kChunk) hi = lo + kChunk;
   const int cnt = (int)(hi - lo);
   if (cnt <= 0) return;                       // uniform across the CTA
-  // head flags: particle j owns slots [kstart_j, kend_j); it marks the first of them that is inside [lo, hi)
+  // particle j owns slots [kstart_j, kend_j)
   int kstart = threadIdx.x == 0 ? (int)slot0 : sm.kend_last[threadIdx.x - 1];
   const int ilo = (int)lo, ihi = (int)hi;
 #pragma unroll
   for (int j = 0; j < kItems; j++) {
-    const int ke = kend[j];
-    if (ke > kstart && ke > ilo && kstart < ihi) sm.slot[pad_idx((kstart > ilo ? kstart : ilo) - ilo)] = threadIdx.x * kItems + j;
-    kstart = ke;
-  }
-  __syncthreads();
-  // inclusive max-scan over the window: every slot takes the last head at or before it
-  int L = 1;
-  while (L * kBlock < cnt) L <<= 1;             // entries per thread: power of two <= 32
-  const int base = threadIdx.x * L;
-  int run = -1;
-  for (int i = 0; i < L; i++) {
-    const int k = base + i;
-    if (k < cnt) { const int v = sm.slot[pad_idx(k)]; run = v > run ? v : run; }
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = run;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int o = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc = o > inc ? o : inc;
-  }
-  int *s_wmax = reinterpret_cast<int *>(sm.warp64);   // 8 ints fit in the 9 x u64 scratch (free since the barrier above)
-  if (lane == 31) s_wmax[warp] = inc;
-  __syncthreads();
-  int pre = -1;
-  for (int w2 = 0; w2 < warp; w2++) { const int v = s_wmax[w2]; pre = v > pre ? v : pre; }
-  int up = __shfl_up_sync(0xffffffffu, inc, 1);
-  if (lane > 0) pre = up > pre ? up : pre;
-  run = pre;
-  for (int i = 0; i < L; i++) {
-    const int k = base + i;
-    if (k < cnt) {
-      const int v = sm.slot[pad_idx(k)];
-      run = v > run ? v : run;
-      sm.slot[pad_idx(k)] = run;
+    const int a0 = (kstart > ilo ? kstart : ilo) - ilo, a1 = (kend[j] < ihi ? kend[j] : ihi) - ilo;
+    const int id = threadIdx.x * kItems + j;
+    if (a1 - a0 > kHeavyCap) {
+      sm.heavy[atomicAdd(&sm.nheavy, 1)] = make_int3(id, a0, a1);
+    } else {
+      for (int k = a0; k < a1; k++) sm.slot[k] = id;
     }
+    kstart = kend[j];
   }
   __syncthreads();
+  const int nh = sm.nheavy;
+  for (int e = 0; e < nh; e++) {
+    const int3 h = sm.heavy[e];
+    for (int k = h.y + threadIdx.x; k < h.z; k += kBlock) sm.slot[k] = h.x;
+  }
+  if (nh) __syncthreads();
   // coalesced copy-out
   const int tile_base = (int)(tile * kTile);
   int *__restrict__ out = anc + (lo - anc_base);
-  for (int i = threadIdx.x; i < cnt; i += kBlock) __stcs(out + i, tile_base + sm.slot[pad_idx(i)]);
+  for (int i = threadIdx.x; i < cnt; i += kBlock) __stcs(out + i, tile_base + sm.slot[i]);
 }
 
 template <typename R>

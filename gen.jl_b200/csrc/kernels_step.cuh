@@ -125,8 +125,11 @@ GB_D void publish_max(double acc, double *partials, unsigned int *ticket, Weight
   }
 }
 
+#ifndef GB_STEP_MINB
+#define GB_STEP_MINB 3
+#endif
 template <typename R, int KIND, int PK, bool INIT, bool PREDRAWN, bool GATHER>
-__global__ void __launch_bounds__(kBlock) step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepArgs a) {
   typedef Transition<R, KIND, PK, INIT> Tr;
   constexpr int V = VecOf<R>::V, S = Tr::S, NN = Tr::NN, NU = Tr::NU;
   __shared__ double s_tab[kMathTabDoubles];
@@ -320,20 +323,31 @@ __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ lo
   const long long nseg = ntiles * (kTile / kSeg);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double s1 = 0.0, s2 = 0.0;
-  for (long long seg = (long long)blockIdx.x * (kBlock / 32) + warp; seg < nseg; seg += (long long)gridDim.x * (kBlock / 32)) {
+  // register double buffering: the next segment's four 128-bit loads are in flight while this one is
+  // evaluated (v1 was 41% long-scoreboard: one segment of loads per warp at a time)
+  const long long sstride = (long long)gridDim.x * (kBlock / 32);
+  long long seg = (long long)blockIdx.x * (kBlock / 32) + warp;
+  R cur[kLoads][V], nxt[kLoads][V];
+  if (seg < nseg) {
+#pragma unroll
+    for (int j = 0; j < kLoads; j++) vload_keep<R>(logw + seg * kSeg + (long long)(j * 32 + lane) * V, cur[j]);
+  }
+  for (; seg < nseg; seg += sstride) {
     const long long base = seg * kSeg;
     const bool full = base + kSeg <= n;
+    if (seg + sstride < nseg) {
+#pragma unroll
+      for (int j = 0; j < kLoads; j++) vload_keep<R>(logw + (seg + sstride) * kSeg + (long long)(j * 32 + lane) * V, nxt[j]);
+    }
     uint64_t sq = 0;
 #pragma unroll
     for (int j = 0; j < kLoads; j++) {
       const long long i0 = base + (long long)(j * 32 + lane) * V;   // padded arrays: always in bounds
-      R v[V];
-      vload_keep<R>(logw + i0, v);
 #pragma unroll
       for (int k = 0; k < V; k++) {
         double e;
         uint64_t q;
-        const double lw = (full || i0 + k < n) ? (double)v[k] : -INFINITY;
+        const double lw = (full || i0 + k < n) ? (double)cur[j][k] : -INFINITY;
         exp_and_quantize(lw - m, bits, e, q);
         s1 += e;
         s2 = fma(e, e, s2);
@@ -345,6 +359,10 @@ __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ lo
       atomicAdd(tile_q + seg / (kTile / kSeg), (unsigned long long)sq);
       atomicAdd(super_q + seg / (kTile / kSeg) / kSuper, (unsigned long long)sq);
     }
+#pragma unroll
+    for (int j = 0; j < kLoads; j++)
+#pragma unroll
+      for (int k = 0; k < V; k++) cur[j][k] = nxt[j][k];
   }
   // CTA partial sums (fixed order => deterministic for a fixed grid)
 #pragma unroll
