@@ -1,0 +1,262 @@
+"""Particle filter sharded over GPUs: one process per GPU (torch.distributed, NCCL over NVLink).
+
+Particles are split into contiguous shards (global id = shard offset + local index).  Propose / weight
+need no communication.  maybe_resample! needs exactly
+
+  * one all-reduce(max) of the shard maxima (8 bytes),
+  * one all-gather of (sum exp(lw-m), sum exp(2(lw-m)), integer CDF mass) per shard (24 bytes) -> global
+    log-sum-exp, ESS and the shard's offset into the global integer CDF (global-prefix systematic
+    resampling: every shard sweeps its own particles against the SAME global slot grid, so the ancestors
+    are bit-identical to the single-GPU / sequential result by construction),
+  * one all-to-all-v of the offspring rows whose destination slot lives on another shard.
+
+All heavy lifting is in libgenb200 (include/genb200.h "sharded pieces"); this file only sequences the
+collectives.  `ShardOps` is the interface to a shard; the CPU test-suite substitutes an oracle-backed
+implementation to exercise the collective logic with the gloo backend (tests/test_sharded_gloo.py).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+from . import api
+
+
+def shard_bounds(n_global, world):
+    """Contiguous shards; the first (n_global % world) shards hold one extra particle."""
+    base, rem = divmod(int(n_global), int(world))
+    counts = [base + (1 if r < rem else 0) for r in range(world)]
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    return counts, offs
+
+
+def slots_below(C_, n_global, q_total, u0):
+    """#{k : floor((k 2^32 + u0) Q / (N 2^32)) < C}: host instance of the kernels' exact integer function."""
+    return int(L.lib().gb_selftest_slots_below(int(C_), int(n_global), int(q_total), int(u0)))
+
+
+def plan_exchange(q_locals, n_global, offs, u0):
+    """From the gathered per-shard integer CDF masses: every shard's offspring slot range and the matrix
+    send[src][dst] = (k_lo, k_hi) of global slots produced by src that are owned by dst."""
+    world = len(q_locals)
+    q_total = int(sum(int(q) for q in q_locals))
+    pref = [0]
+    for q in q_locals:
+        pref.append(pref[-1] + int(q))
+    ranges = [(slots_below(pref[r], n_global, q_total, u0), slots_below(pref[r + 1], n_global, q_total, u0))
+              for r in range(world)]
+    send = [[(0, 0)] * world for _ in range(world)]
+    for s, (lo, hi) in enumerate(ranges):
+        for d in range(world):
+            a, b = max(lo, offs[d]), min(hi, offs[d + 1])
+            send[s][d] = (a, b) if b > a else (a, a)
+    return q_total, pref, ranges, send
+
+
+class ShardOps:
+    """A shard of the particle store behind the C ABI."""
+
+    def __init__(self, state):
+        self.state = state
+        self.h = state._h
+
+    def weight_max(self):
+        v = C.c_double()
+        L.check(L.lib().gb_pf_weight_max(self.h, C.byref(v)))
+        return v.value
+
+    def weight_sums(self, m_ref, bits):
+        s1, s2, q = C.c_double(), C.c_double(), C.c_uint64()
+        L.check(L.lib().gb_pf_weight_sums(self.h, m_ref, bits, C.byref(s1), C.byref(s2), C.byref(q)))
+        return s1.value, s2.value, q.value
+
+    def systematic_offspring(self, m_ref, bits, q_offset, q_total, u0):
+        lo, hi = C.c_int64(), C.c_int64()
+        L.check(L.lib().gb_pf_systematic_offspring(self.h, m_ref, bits, q_offset, q_total, u0, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def export_offspring(self, k_lo, k_hi, rows, parents):
+        L.check(L.lib().gb_pf_export_offspring(self.h, k_lo, k_hi, C.c_void_p(rows.data_ptr()), C.c_void_p(parents.data_ptr())))
+
+    def import_rows(self, dst_lo, count, rows, parents):
+        L.check(L.lib().gb_pf_import_rows(self.h, dst_lo, count, C.c_void_p(rows.data_ptr()), C.c_void_p(parents.data_ptr())))
+
+    def commit(self, log_ml_increment):
+        L.check(L.lib().gb_pf_commit_resample(self.h, log_ml_increment))
+
+    def log_ml_est(self):
+        return self.state.log_ml_est
+
+
+class ShardedParticleFilter:
+    """Gen's particle-filter calls over a filter whose particles are sharded across the process group."""
+
+    def __init__(self, model, n_global, dtype="f64", seed=0, group=None, ops_factory=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_global = int(n_global)
+        self.counts, self.offs = shard_bounds(self.n_global, self.world)
+        self.n_local = self.counts[self.rank]
+        self.seed = int(seed)
+        self.dtype = dtype
+        self.model = model
+        self.step = 0
+        self.bits = int(L.lib().gb_quant_bits(self.n_global))
+        if ops_factory is None:
+            self.local = api.create_particle_filter(model, self.n_local, dtype=dtype, seed=seed, n_global=self.n_global,
+                                                    pid_offset=self.offs[self.rank])
+            self.ops = ShardOps(self.local)
+            self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+            self.tdtype = torch.float64 if api._DTYPES[dtype] == L.F64 else torch.float32
+        else:                                   # CPU test double (oracle-backed shard, gloo backend)
+            self.local = None
+            self.ops = ops_factory(self)
+            self.device = torch.device("cpu")
+            self.tdtype = torch.float64
+        self.state_dim = self.ops.state.state_dim if ops_factory is None else self.ops.state_dim
+        self.last_ess = None
+
+    # ---- collectives (tiny) ----
+    def _allreduce_max(self, x):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
+    def _allgather_triple(self, s1, s2, q):
+        """(s1, s2, q) of every shard; q travels exactly as int64 (q < 2^62)."""
+        loc = np.array([np.float64(s1).view(np.int64), np.float64(s2).view(np.int64), np.int64(q)], dtype=np.int64)
+        if self.world == 1:
+            allv = loc[None, :]
+        else:
+            t = self.torch.from_numpy(loc).to(self.device)
+            out = self.torch.empty(self.world * 3, dtype=self.torch.int64, device=self.device)
+            self.dist.all_gather_into_tensor(out, t, group=self.group)
+            allv = out.cpu().numpy().reshape(self.world, 3)
+        s1s = allv[:, 0].copy().view(np.float64)
+        s2s = allv[:, 1].copy().view(np.float64)
+        return s1s, s2s, [int(v) for v in allv[:, 2]]
+
+    def _all_to_all_v(self, send, send_counts, recv_counts):
+        torch, dist = self.torch, self.dist
+        recv = torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
+        if self.world == 1:
+            recv.copy_(send)
+            return recv
+        if send.device.type == "cuda":
+            dist.all_to_all_single(recv, send, list(map(int, recv_counts)), list(map(int, send_counts)), group=self.group)
+            return recv
+        # gloo / CPU: pairwise exchange
+        so = np.concatenate([[0], np.cumsum(send_counts)]).astype(int)
+        ro = np.concatenate([[0], np.cumsum(recv_counts)]).astype(int)
+        recv[ro[self.rank]:ro[self.rank + 1]] = send[so[self.rank]:so[self.rank + 1]]
+        reqs = []
+        for peer in range(self.world):
+            if peer == self.rank:
+                continue
+            if send_counts[peer]:
+                reqs.append(dist.isend(send[so[peer]:so[peer + 1]].contiguous(), peer, group=self.group))
+            if recv_counts[peer]:
+                reqs.append(dist.irecv(recv[ro[peer]:ro[peer + 1]], peer, group=self.group))
+        for r in reqs:
+            r.wait()
+        return recv
+
+    # ---- Gen API ----
+    def initialize(self, observations, proposal=None, proposal_args=()):
+        api.generate_(self.local, observations, proposal, proposal_args)
+        self.step = 0
+        return self
+
+    def particle_filter_step_(self, new_args, observations, proposal=None, proposal_args=(), return_incr=False):
+        out = api.particle_filter_step_(self.local, new_args, (api.UnknownChange,), observations, proposal, proposal_args,
+                                        return_incr=return_incr)
+        self.step += 1
+        return out
+
+    def _global_stats(self):
+        """Global (m, lse, ess) and the gathered integer masses (particle_filter.jl:3-12 over all shards)."""
+        m = self._allreduce_max(self.ops.weight_max())
+        s1, s2, q = self.ops.weight_sums(m, self.bits)
+        s1s, s2s, qs = self._allgather_triple(s1, s2, q)
+        S1, S2 = float(np.sum(s1s)), float(np.sum(s2s))      # fixed rank order: identical on every rank
+        lse = -math.inf if m == -math.inf else m + math.log(S1)
+        ess = (S1 * S1) / S2 if S2 > 0 else float("nan")
+        return m, lse, ess, qs
+
+    def log_ml_estimate(self):
+        """particle_filter.jl:91-94 with the global log-sum-exp."""
+        _, lse, _, _ = self._global_stats()
+        return self.ops.log_ml_est() + lse - math.log(self.n_global)
+
+    def maybe_resample_(self, ess_threshold=None, verbose=False):
+        """maybe_resample! (particle_filter.jl:249-275) with global-prefix systematic resampling."""
+        thr = self.n_global / 2 if ess_threshold is None else float(ess_threshold)
+        m, lse, ess, qs = self._global_stats()
+        self.last_ess = ess
+        if verbose and self.rank == 0:
+            print("effective sample size: %s, doing resample: %s" % (ess, ess < thr))
+        if not (ess < thr):                                  # :256, strict; NaN compares false
+            return False
+        u0 = api.philox_resample_u0(self.seed, self.step)
+        q_total, pref, ranges, send = plan_exchange(qs, self.n_global, self.offs, u0)
+        lo, hi = self.ops.systematic_offspring(m, self.bits, pref[self.rank], q_total, u0)
+        assert (lo, hi) == ranges[self.rank], "offspring range mismatch between host plan and device sweep"
+        S, torch = self.state_dim, self.torch
+        me = self.rank
+        send_cnt = [send[me][d][1] - send[me][d][0] for d in range(self.world)]
+        recv_cnt = [send[s][me][1] - send[s][me][0] for s in range(self.world)]
+        rows = torch.empty(S * (hi - lo), dtype=self.tdtype, device=self.device)
+        parents = torch.empty(hi - lo, dtype=torch.int64, device=self.device)
+        # export: per destination a contiguous [S][count] block (+ parents), in rank order
+        ro = po = 0
+        for d in range(self.world):
+            a, b = send[me][d]
+            c = b - a
+            if c:
+                self.ops.export_offspring(a, b, rows[ro:ro + S * c], parents[po:po + c])
+            ro += S * c
+            po += c
+        rrows = self._all_to_all_v(rows, [S * c for c in send_cnt], [S * c for c in recv_cnt])
+        rpar = self._all_to_all_v(parents, send_cnt, recv_cnt)
+        ro = po = 0
+        for s in range(self.world):
+            a, b = send[s][me]
+            c = b - a
+            if c:
+                self.ops.import_rows(a - self.offs[me], c, rrows[ro:ro + S * c], rpar[po:po + c])
+            ro += S * c
+            po += c
+        assert po == self.n_local, "resampled shard is not full: %d of %d" % (po, self.n_local)
+        self.ops.commit(lse - math.log(self.n_global))       # :263
+        return True
+
+    # ---- accessors (gather to every rank; for tests / small filters) ----
+    def _gather_array(self, arr, np_dtype):
+        torch, dist = self.torch, self.dist
+        if self.world == 1:
+            return arr
+        cmax = max(self.counts)                      # equal-sized pieces for every backend
+        pad = np.zeros(cmax, dtype=arr.dtype)
+        pad[:len(arr)] = arr
+        t = torch.from_numpy(pad).to(self.device)
+        outs = [torch.empty(cmax, dtype=t.dtype, device=self.device) for _ in self.counts]
+        dist.all_gather(outs, t, group=self.group)
+        return np.concatenate([o.cpu().numpy()[:c] for o, c in zip(outs, self.counts)]).astype(np_dtype)
+
+    def get_log_weights(self):
+        return self._gather_array(api.get_log_weights(self.local), np.float64)
+
+    def get_state(self, field):
+        return self._gather_array(self.local.get_state(field), np.float64)
+
+    def get_parents(self):
+        return self._gather_array(self.local.parents, np.int64)

@@ -1,0 +1,52 @@
+"""Multi-process NCCL check (not a pytest file: needs N GPUs).  Run under torchrun on a multi-GPU box:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/run_sharded_nccl.py
+Every rank drives its shard through ShardedParticleFilter; rank 0 also runs the same filter on one GPU
+through the ordinary API and the results must be bit-identical."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as entry  # noqa: E402
+import fixtures as F  # noqa: E402
+
+
+def main():
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    g = entry.load_package()
+    from genb200 import sharded, _lib as L
+    L.check(L.lib().gb_set_device(lr))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    for n in (100003, 4_000_000):
+        ys = F.bearings_series(8)
+        seed = 17
+        spf = sharded.ShardedParticleFilter(g.bearings_model(), n, seed=seed).initialize(ys[0])
+        nres = 0
+        for t in range(1, len(ys)):
+            nres += spf.maybe_resample_(ess_threshold=(n + 1 if t % 2 else n / 2))
+            spf.particle_filter_step_((t,), ys[t])
+        cols = [spf.get_state(f) for f in range(4)]
+        par = spf.get_parents()
+        lml = spf.log_ml_estimate()
+        if rank == 0:
+            st = g.initialize_particle_filter(g.bearings_model(), (0,), ys[0], n, seed=seed)
+            for t in range(1, len(ys)):
+                g.maybe_resample_(st, ess_threshold=(n + 1 if t % 2 else n / 2), resampler="systematic")
+                g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t])
+            ok = all(np.array_equal(cols[f], st.get_state(f)) for f in range(4)) and np.array_equal(par, st.parents)
+            ok = ok and abs(lml - g.log_ml_estimate(st)) <= 1e-10 * abs(lml)
+            print("NCCL sharded check world=%d n=%d resamples=%d: %s (log ML %.12f)" % (world, n, nres, "OK" if ok else "MISMATCH", lml))
+            if not ok:
+                sys.exit(1)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+"""The sharded pieces of the C ABI on one GPU: K shards of one filter live in the same process and the
+host plays the collectives (sums / prefix / row exchange by device copies).  The resampled filter must be
+bit-identical to the single-shard filter and to the oracle: global-prefix systematic resampling is
+partition independent by construction.  (Real multi-process NCCL runs: tests/run_sharded_nccl.py under
+`gpurun --gpus 2`, and bench.py --gpus N.)"""
+import math
+
+import numpy as np
+import pytest
+
+import fixtures as F
+
+pytestmark = pytest.mark.gpu
+
+
+def run_sharded_in_process(g, model, n, K, ys, seed, dtype="f64"):
+    import torch
+    from genb200 import sharded, _lib as L
+    counts, offs = sharded.shard_bounds(n, K)
+    bits = L.lib().gb_quant_bits(n)
+    shards = [g.create_particle_filter(model, counts[r], dtype=dtype, seed=seed, n_global=n, pid_offset=offs[r]) for r in range(K)]
+    ops = [sharded.ShardOps(s) for s in shards]
+    for s in shards:
+        g.generate_(s, ys[0])
+    S = model.state_dim
+    td = torch.float64 if dtype == "f64" else torch.float32
+    lml_hist = []
+    for t in range(1, len(ys)):
+        m = max(o.weight_max() for o in ops)                                  # all-reduce(max)
+        trip = [o.weight_sums(m, bits) for o in ops]                          # all-gather
+        S1, S2 = sum(x[0] for x in trip), sum(x[1] for x in trip)
+        lse, ess = m + math.log(S1), S1 * S1 / S2
+        if ess < n / 2 or t % 2 == 0:
+            u0 = g.philox_resample_u0(seed, t - 1)
+            qt, pref, ranges, send = sharded.plan_exchange([x[2] for x in trip], n, offs, u0)
+            bufs = {}
+            for r in range(K):
+                lo, hi = ops[r].systematic_offspring(m, bits, pref[r], qt, u0)
+                assert (lo, hi) == ranges[r]
+                for d in range(K):
+                    a, b = send[r][d]
+                    if b > a:
+                        rows = torch.empty(S * (b - a), dtype=td, device="cuda")
+                        par = torch.empty(b - a, dtype=torch.int64, device="cuda")
+                        ops[r].export_offspring(a, b, rows, par)
+                        bufs[(r, d)] = (a, b, rows, par)
+            for (r, d), (a, b, rows, par) in bufs.items():                   # all-to-all-v
+                ops[d].import_rows(a - offs[d], b - a, rows, par)
+            for o in ops:
+                o.commit(lse - math.log(n))
+        for s in shards:
+            g.particle_filter_step_(s, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+        m = max(o.weight_max() for o in ops)
+        trip = [o.weight_sums(m, bits) for o in ops]
+        lml_hist.append(shards[0].log_ml_est + m + math.log(sum(x[0] for x in trip)) - math.log(n))
+    cols = [np.concatenate([s.get_state(f) for s in shards]) for f in range(S)]
+    lw = np.concatenate([g.get_log_weights(s) for s in shards])
+    par = np.concatenate([s.parents for s in shards])
+    return cols, lw, par, lml_hist
+
+
+@pytest.mark.parametrize("K", [2, 3, 8])
+@pytest.mark.parametrize("name", ["bearings", "lgssm"])
+def test_sharded_equals_single_shard_and_oracle(g, O, K, name):
+    if name == "bearings":
+        model, okind, params, ys = g.bearings_model(), O.MODEL_BEARINGS, F.BEARINGS_PARAMS, F.bearings_series(9)
+    else:
+        model, okind, params, ys = g.lgssm_model(**F.LGSSM), O.MODEL_LGSSM, F.lgssm_params(), F.lgssm_series(9)
+    n, seed = 50021, 31
+    cols, lw, par, lml = run_sharded_in_process(g, model, n, K, ys, seed)
+    # single shard through the same pieces (K = 1) and through the ordinary API
+    cols1, lw1, par1, lml1 = run_sharded_in_process(g, model, n, 1, ys, seed)
+    for a, b in zip(cols, cols1):
+        assert np.array_equal(a, b)
+    assert np.array_equal(lw, lw1) and np.array_equal(par, par1)
+    assert np.allclose(lml, lml1, rtol=1e-12, atol=1e-12)
+    # the oracle on the exported Philox noise
+    nn0, nn1 = model.num_normals(True), model.num_normals(False)
+    ref = O.OraclePF.init(okind, params, n, [ys[0]], normals=g.philox_normals(seed, 0, 0, n, nn0))
+    for t in range(1, len(ys)):
+        lse, lnw = O.normalize_weights(ref.log_weights)
+        thr = n + 1 if t % 2 == 0 else n / 2
+        ref.maybe_resample(ess_threshold=thr, kind=O.RESAMPLE_SYSTEMATIC, u0=g.philox_resample_u0(seed, t - 1))
+        ref.step([ys[t]], normals=g.philox_normals(seed, t, 0, n, nn1))
+    for f in range(model.state_dim):
+        assert np.array_equal(cols[f], ref.state(f))
+    assert np.array_equal(par, ref.parents)
+    assert np.allclose(lw, ref.log_weights, rtol=1e-10, atol=1e-10)
+    assert abs(lml[-1] - ref.log_ml_estimate()) <= 1e-10 * abs(ref.log_ml_estimate())
+
+
+def test_sharded_class_world1(g, O):
+    """ShardedParticleFilter without a process group (world = 1) equals the plain API."""
+    import torch
+    from genb200 import sharded
+    ys = F.bearings_series(6)
+    n, seed = 30000, 5
+    spf = sharded.ShardedParticleFilter(g.bearings_model(), n, seed=seed).initialize(ys[0])
+    st = g.initialize_particle_filter(g.bearings_model(), (0,), ys[0], n, seed=seed)
+    for t in range(1, len(ys)):
+        a = spf.maybe_resample_(ess_threshold=n + 1)
+        b = g.maybe_resample_(st, ess_threshold=n + 1, resampler="systematic")
+        assert a == b
+        spf.particle_filter_step_((t,), ys[t])
+        g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t])
+    for f in range(4):
+        assert np.array_equal(spf.get_state(f), st.get_state(f))
+    assert np.array_equal(spf.get_parents(), st.parents)
+    assert abs(spf.log_ml_estimate() - g.log_ml_estimate(st)) < 1e-10
