@@ -63,6 +63,10 @@ SIGNATURES = {
     "gb_pf_weight_max": (i, [vp, dp]),
     "gb_pf_weight_sums": (i, [vp, d, i, dp, dp, u64p]),
     "gb_pf_systematic_offspring": (i, [vp, d, i, u64, u64, u32, i64p, i64p]),
+    "gb_pf_ext_capacity": (i, [vp, i64p]),
+    "gb_pf_offspring_local": (i, [vp, i64, i64]),
+    "gb_pf_import_ext": (i, [vp, i64, i64, i64, vp, vp]),
+    "gb_pf_commit_resample_lazy": (i, [vp, d]),
     "gb_pf_export_offspring": (i, [vp, i64, i64, vp, vp]),
     "gb_pf_import_rows": (i, [vp, i64, i64, vp, vp]),
     "gb_pf_commit_resample": (i, [vp, d]),

@@ -148,6 +148,9 @@ struct gb_pf {
   int dtype = GB_F64;
   size_t esz = 8;
   long long n = 0, n_global = 0, pid_offset = 0, ld = 0;
+  long long n_pad = 0, ext_cap = 0;   // rows [n_pad, n_pad + ext_cap) of every column: offspring received from other shards
+  long long *ext_parents = nullptr;   // global 1-based parents of the received rows
+  bool ext_used = false;
   uint64_t seed = 0;
   int step = 0;
   int S = 0;
@@ -243,7 +246,7 @@ template <typename F> static int grid_for(gb_pf *pf, F kernel, long long work_it
 static void pf_release(gb_pf *pf) {
   if (!pf) return;
   cudaFree(pf->state[0]); cudaFree(pf->state[1]); cudaFree(pf->logw); cudaFree(pf->incr); cudaFree(pf->anc);
-  cudaFree(pf->parents64); cudaFree(pf->partials); cudaFree(pf->ticket); cudaFree(pf->d_stats);
+  cudaFree(pf->parents64); cudaFree(pf->ext_parents); cudaFree(pf->partials); cudaFree(pf->ticket); cudaFree(pf->d_stats);
   cudaFreeHost(pf->h_stats); cudaFree(pf->d_normals); cudaFree(pf->d_uniforms); cudaFree(pf->d_u64);
   cudaFree(pf->super_q); cudaFree(pf->super_excl); cudaFree(pf->oflow); cudaFree(pf->oflow_count);
   cudaFree(pf->tile_q); cudaFree(pf->tile_c); cudaFree(pf->tile_r); cudaFree(pf->tile_slot); cudaFree(pf->d_plan);
@@ -281,10 +284,14 @@ extern "C" int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_glob
   pf->dtype = dtype;
   pf->esz = dtype == GB_F64 ? 8 : 4;
   pf->n = n_local; pf->n_global = n_global; pf->pid_offset = pid_offset;
-  pf->ld = ((n_local + kTile - 1) / kTile) * kTile;
+  pf->n_pad = ((n_local + kTile - 1) / kTile) * kTile;
+  // sharded filters keep head-room for rows migrating in at a resample (25% of the shard + one tile);
+  // a resample that needs more falls back to the staged exchange (gb_pf_import_rows)
+  pf->ext_cap = n_local == n_global ? 0 : ((n_local / 4 + kTile - 1) / kTile + 1) * kTile;
+  pf->ld = pf->n_pad + pf->ext_cap;
   pf->seed = seed;
   pf->S = m->S;
-  pf->ntiles = pf->ld / kTile;
+  pf->ntiles = pf->n_pad / kTile;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&pf->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -300,6 +307,7 @@ extern "C" int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_glob
   if (e == cudaSuccess) e = A(&pf->logw, col, true);
   if (e == cudaSuccess) e = A(&pf->incr, col, true);
   if (e == cudaSuccess) e = A((void **)&pf->anc, (size_t)pf->ld * 4, true);
+  if (e == cudaSuccess && pf->ext_cap) e = A((void **)&pf->ext_parents, (size_t)pf->ext_cap * 8, true);
   if (e == cudaSuccess) e = A((void **)&pf->partials, sizeof(double2) * kMaxPartials, true);
   if (e == cudaSuccess) e = A((void **)&pf->ticket, 64, true);
   if (e == cudaSuccess) e = A((void **)&pf->d_stats, sizeof(WeightStats), true);
@@ -759,19 +767,26 @@ extern "C" int gb_pf_get_state(gb_pf_t *pf, int field, double *out) {
   if (rc) return rc;
   return copy_out(pf, (const char *)pf->state[pf->cur] + (size_t)field * pf->ld * pf->esz, out, pf->n);
 }
+// parents64 = Gen's `parents` (global, 1-based) of the current traces
+static int ensure_parents64(gb_pf *pf) {
+  if (!pf->parents64) CK(cudaMalloc((void **)&pf->parents64, (size_t)pf->ld * 8));
+  if (pf->parents64_valid) return GB_OK;
+  if (pf->anc_valid) {
+    int grid = grid_for(pf, parents_from_anc_kernel, pf->n, kBlock);
+    LAUNCH(pf, GB_K_MISC, parents_from_anc_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->anc, pf->parents64, pf->n, pf->pid_offset,
+                                                                                       pf->ext_used ? pf->n_pad : (long long)1 << 40, pf->ext_parents));
+  } else {
+    int grid = grid_for(pf, iota_parents_kernel, pf->n, kBlock);
+    LAUNCH(pf, GB_K_MISC, iota_parents_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->parents64, pf->n, pf->pid_offset));
+  }
+  CK(cudaGetLastError());
+  pf->parents64_valid = true;
+  return GB_OK;
+}
 extern "C" int gb_pf_get_parents(gb_pf_t *pf, int64_t *out) {
   REQ(pf && out, "null argument");
-  if (!pf->parents64) CK(cudaMalloc((void **)&pf->parents64, (size_t)pf->ld * 8));
-  if (!pf->parents64_valid) {
-    if (pf->anc_valid) {
-      int grid = grid_for(pf, parents_from_anc_kernel, pf->n, kBlock);
-      LAUNCH(pf, GB_K_MISC, parents_from_anc_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->anc, pf->parents64, pf->n, pf->pid_offset));
-    } else {
-      int grid = grid_for(pf, iota_parents_kernel, pf->n, kBlock);
-      LAUNCH(pf, GB_K_MISC, iota_parents_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->parents64, pf->n, pf->pid_offset));
-    }
-    CK(cudaGetLastError());
-  }
+  int rc = ensure_parents64(pf);
+  if (rc) return rc;
   CK(cudaMemcpyAsync(out, pf->parents64, (size_t)pf->n * 8, cudaMemcpyDeviceToHost, pf->stream));
   CK(cudaStreamSynchronize(pf->stream));
   return GB_OK;
@@ -783,6 +798,7 @@ extern "C" int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out) {
   if (rc) return rc;
   rc = ensure_stats(pf);
   if (rc) return rc;
+  if ((rc = ensure_parents64(pf))) return rc;
   gb_pf_t *c = nullptr;
   rc = gb_pf_create(&pf->model, pf->n, pf->n_global, pf->pid_offset, pf->dtype, pf->seed, &c);
   if (rc) return rc;
@@ -791,7 +807,7 @@ extern "C" int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out) {
   c->step = pf->step;
   c->log_ml_est = pf->log_ml_est;
   c->wstate = pf->wstate;
-  c->anc_valid = pf->anc_valid;
+  c->anc_valid = false;            // parents travel as the materialised int64 array
   size_t col = (size_t)pf->ld * pf->esz;
   cudaError_t e = cudaMemcpyAsync(c->state[c->cur], pf->state[pf->cur], col * pf->S, cudaMemcpyDeviceToDevice, pf->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(c->logw, pf->logw, col, cudaMemcpyDeviceToDevice, pf->stream);
@@ -966,8 +982,57 @@ extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits
     if (rc) return rc;
   }
   pf->off_lo = lo; pf->off_hi = hi;
+  pf->ext_used = false;
   *slot_lo = lo; *slot_hi = hi;
   return GB_OK;
+}
+// ---- sharded fast path: slots that stay on this shard keep their ancestors (deferred gather, fused into
+//      the next step); rows arriving from other shards are parked in the extension rows of the current
+//      trace buffer and the slot's ancestor index points there ----
+extern "C" int gb_pf_ext_capacity(const gb_pf_t *pf, int64_t *cap) { REQ(pf && cap, "null argument"); *cap = pf->ext_cap; return GB_OK; }
+extern "C" int gb_pf_offspring_local(gb_pf_t *pf, int64_t k_lo, int64_t k_hi) {
+  REQ(pf, "null handle");
+  REQ(k_lo >= pf->off_lo && k_hi <= pf->off_hi && k_lo <= k_hi, "gb_pf_offspring_local: slots outside the shard's offspring range");
+  REQ(k_lo >= pf->pid_offset && k_hi <= pf->pid_offset + pf->n, "gb_pf_offspring_local: slots not owned by this shard");
+  if (k_hi > k_lo)
+    CK(cudaMemcpyAsync(pf->anc + (k_lo - pf->pid_offset), pf->off_anc + (k_lo - pf->off_lo), (size_t)(k_hi - k_lo) * 4,
+                       cudaMemcpyDeviceToDevice, pf->stream));
+  return GB_OK;
+}
+extern "C" int gb_pf_import_ext(gb_pf_t *pf, int64_t dst_lo, int64_t count, int64_t ext_offset, const void *dev_rows,
+                                const void *dev_parents) {
+  REQ(pf && dev_rows && dev_parents, "null argument");
+  REQ(dst_lo >= 0 && count >= 0 && dst_lo + count <= pf->n, "gb_pf_import_ext: destination outside the shard");
+  if (ext_offset < 0 || ext_offset + count > pf->ext_cap) return fail(GB_ESTATE, "gb_pf_import_ext: extension rows exhausted");
+  if (count == 0) return GB_OK;
+  if (pf->dtype == GB_F64) {
+    auto kern = import_ext_kernel<double>;
+    int grid = grid_for(pf, kern, count, kBlock);
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((double *)pf->state[pf->cur], pf->ld, pf->S, dst_lo, count, pf->n_pad + ext_offset,
+                                                                   (const double *)dev_rows, (const long long *)dev_parents, pf->anc,
+                                                                   pf->ext_parents + ext_offset));
+  } else {
+    auto kern = import_ext_kernel<float>;
+    int grid = grid_for(pf, kern, count, kBlock);
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((float *)pf->state[pf->cur], pf->ld, pf->S, dst_lo, count, pf->n_pad + ext_offset,
+                                                                   (const float *)dev_rows, (const long long *)dev_parents, pf->anc,
+                                                                   pf->ext_parents + ext_offset));
+  }
+  CK(cudaGetLastError());
+  pf->ext_used = true;
+  return GB_OK;
+}
+extern "C" int gb_pf_commit_resample_lazy(gb_pf_t *pf, double log_ml_increment) {
+  REQ(pf, "null handle");
+  pf->log_ml_est += log_ml_increment;       // particle_filter.jl:263
+  pf->wstate = W_ZERO;                      // :266 (the array itself is rewritten by the gather / next step)
+  pf->tiles_valid = false;
+  pf->anc_valid = true;
+  pf->parents64_valid = false;
+  pf->pending_gather = true;
+  int rc = GB_OK;
+  if (!pf->lazy) rc = run_gather(pf);
+  return rc;
 }
 extern "C" int gb_pf_export_offspring(gb_pf_t *pf, int64_t k_lo, int64_t k_hi, void *dev_rows, void *dev_parents) {
   REQ(pf && dev_rows && dev_parents, "null argument");
@@ -1106,7 +1171,7 @@ static int raw_workspace(long long n, int dtype, cudaStream_t stream, gb_pf **ou
   REQ(n >= 1 && n < ((int64_t)1 << 31), "raw resampling: 1 <= n < 2^31");
   gb_pf *pf = new gb_pf;
   pf->dtype = dtype; pf->esz = dtype == GB_F64 ? 8 : 4;
-  pf->n = pf->n_global = n; pf->ld = ((n + kTile - 1) / kTile) * kTile; pf->ntiles = pf->ld / kTile;
+  pf->n = pf->n_global = n; pf->ld = pf->n_pad = ((n + kTile - 1) / kTile) * kTile; pf->ntiles = pf->ld / kTile;
   pf->stream = stream;
   int dev = 0;
   cudaGetDevice(&dev);

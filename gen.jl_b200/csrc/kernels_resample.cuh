@@ -484,9 +484,25 @@ __global__ void __launch_bounds__(kBlock) iota_parents_kernel(long long *__restr
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) p[i] = base + i + 1;
 }
 __global__ void __launch_bounds__(kBlock) parents_from_anc_kernel(const int *__restrict__ anc, long long *__restrict__ p, long long n,
-                                                                  long long base) {
-  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
-    p[i] = base + anc[i] + 1;
+                                                                  long long base, long long ext_begin,
+                                                                  const long long *__restrict__ ext_parents) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+    const long long a = anc[i];
+    p[i] = a >= ext_begin ? ext_parents[a - ext_begin] : base + a + 1;   // rows that migrated in carry their global parent
+  }
+}
+// rows received from another shard -> extension rows [ext_row, ext_row + count) of the current trace
+// buffer; the destination slots' ancestors point at them
+template <typename R>
+__global__ void __launch_bounds__(kBlock) import_ext_kernel(R *__restrict__ scur, long long ld, int S, long long dst_lo, long long count,
+                                                            long long ext_row, const R *__restrict__ rows,
+                                                            const long long *__restrict__ parents_in, int *__restrict__ anc,
+                                                            long long *__restrict__ ext_parents) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < count; i += (long long)gridDim.x * kBlock) {
+    for (int s = 0; s < S; s++) scur[(long long)s * ld + ext_row + i] = rows[(long long)s * count + i];
+    anc[dst_lo + i] = (int)(ext_row + i);
+    ext_parents[i] = parents_in[i];
+  }
 }
 template <typename R>
 __global__ void __launch_bounds__(kBlock) convert_out_kernel(const R *__restrict__ in, double *__restrict__ out, long long n) {

@@ -87,6 +87,22 @@ class ShardOps:
     def commit(self, log_ml_increment):
         L.check(L.lib().gb_pf_commit_resample(self.h, log_ml_increment))
 
+    # fast path: local slots keep their ancestors, incoming rows are parked in the extension rows
+    def ext_capacity(self):
+        v = C.c_int64()
+        L.check(L.lib().gb_pf_ext_capacity(self.h, C.byref(v)))
+        return v.value
+
+    def offspring_local(self, k_lo, k_hi):
+        L.check(L.lib().gb_pf_offspring_local(self.h, k_lo, k_hi))
+
+    def import_ext(self, dst_lo, count, ext_offset, rows, parents):
+        L.check(L.lib().gb_pf_import_ext(self.h, dst_lo, count, ext_offset, C.c_void_p(rows.data_ptr()),
+                                         C.c_void_p(parents.data_ptr())))
+
+    def commit_lazy(self, log_ml_increment):
+        L.check(L.lib().gb_pf_commit_resample_lazy(self.h, log_ml_increment))
+
     def log_ml_est(self):
         return self.state.log_ml_est
 
@@ -122,6 +138,13 @@ class ShardedParticleFilter:
             self.tdtype = torch.float64
         self.state_dim = self.ops.state.state_dim if ops_factory is None else self.ops.state_dim
         self.last_ess = None
+        self._bufs = {}
+        # extension-row capacity of every shard (same formula on every rank: no collective needed)
+        self.ext_caps = None
+        if ops_factory is None and self.world > 1:
+            self.ext_caps = [((c // 4 + 2047) // 2048 + 1) * 2048 for c in self.counts]
+            assert self.ops.ext_capacity() == self.ext_caps[self.rank]
+        self.force_staged = False
 
     # ---- collectives (tiny) ----
     def _allreduce_max(self, x):
@@ -214,6 +237,38 @@ class ShardedParticleFilter:
         me = self.rank
         send_cnt = [send[me][d][1] - send[me][d][0] for d in range(self.world)]
         recv_cnt = [send[s][me][1] - send[s][me][0] for s in range(self.world)]
+        # Fast path when every shard can park its incoming rows in its extension rows (all ranks evaluate
+        # the same predicate from the gathered plan, so no extra collective is needed to agree on it)
+        fast = self.ext_caps is not None and not self.force_staged and all(
+            sum(send[s][d][1] - send[s][d][0] for s in range(self.world) if s != d) <= self.ext_caps[d]
+            for d in range(self.world))
+        if fast:
+            a, b = send[me][me]
+            self.ops.offspring_local(a, b)                   # stays here: ancestors only, gather deferred
+            sc = [0 if d == me else c for d, c in enumerate(send_cnt)]
+            rc = [0 if s == me else c for s, c in enumerate(recv_cnt)]
+            nsend, nrecv = sum(sc), sum(rc)
+            rows, parents = self._buffers(S * nsend, nsend, "send")
+            ro = po = 0
+            for d in range(self.world):
+                if sc[d]:
+                    a, b = send[me][d]
+                    self.ops.export_offspring(a, b, rows[ro:ro + S * sc[d]], parents[po:po + sc[d]])
+                    ro += S * sc[d]
+                    po += sc[d]
+            if self.world > 1:
+                rrows = self._all_to_all_v(rows[:S * nsend], [S * c for c in sc], [S * c for c in rc])
+                rpar = self._all_to_all_v(parents[:nsend], sc, rc)
+                ro = po = 0
+                for s_ in range(self.world):
+                    if rc[s_]:
+                        a, b = send[s_][me]
+                        self.ops.import_ext(a - self.offs[me], rc[s_], po, rrows[ro:ro + S * rc[s_]], rpar[po:po + rc[s_]])
+                        ro += S * rc[s_]
+                        po += rc[s_]
+            self.ops.commit_lazy(lse - math.log(self.n_global))   # :263
+            return True
+        # Staged exchange (arbitrarily skewed weights): every offspring row goes through the all-to-all-v
         rows = torch.empty(S * (hi - lo), dtype=self.tdtype, device=self.device)
         parents = torch.empty(hi - lo, dtype=torch.int64, device=self.device)
         # export: per destination a contiguous [S][count] block (+ parents), in rank order
@@ -238,6 +293,16 @@ class ShardedParticleFilter:
         assert po == self.n_local, "resampled shard is not full: %d of %d" % (po, self.n_local)
         self.ops.commit(lse - math.log(self.n_global))       # :263
         return True
+
+    def _buffers(self, nrows, npar, tag):
+        """Reusable exchange buffers (grown geometrically) instead of one allocation per resample."""
+        torch = self.torch
+        cur = self._bufs.get(tag)
+        if cur is None or cur[0].numel() < nrows or cur[1].numel() < npar:
+            cur = (torch.empty(max(int(nrows * 1.5), 1024), dtype=self.tdtype, device=self.device),
+                   torch.empty(max(int(npar * 1.5), 1024), dtype=torch.int64, device=self.device))
+            self._bufs[tag] = cur
+        return cur
 
     # ---- accessors (gather to every rank; for tests / small filters) ----
     def _gather_array(self, arr, np_dtype):

@@ -113,6 +113,16 @@ int gb_pf_weight_sums(gb_pf_t *pf, double m_ref, int bits, double *s1, double *s
  * are kept in the handle for gb_pf_export_offspring. */
 int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits, uint64_t q_offset, uint64_t q_total,
                                uint32_t u0, int64_t *slot_lo, int64_t *slot_hi);
+/* Fast path of the exchange (used when every shard receives at most gb_pf_ext_capacity rows): slots
+ * [k_lo, k_hi) that stay on this shard just keep their ancestors (the gather is deferred and fused into
+ * the next particle_filter_step!), rows received from other shards are parked in extension rows of the
+ * current trace buffer (ext_offset = running count of received rows) and their slots point there;
+ * gb_pf_commit_resample_lazy then finishes maybe_resample! (particle_filter.jl:263-272). */
+int gb_pf_ext_capacity(const gb_pf_t *pf, int64_t *cap);
+int gb_pf_offspring_local(gb_pf_t *pf, int64_t k_lo, int64_t k_hi);
+int gb_pf_import_ext(gb_pf_t *pf, int64_t dst_lo, int64_t count, int64_t ext_offset, const void *dev_rows,
+                     const void *dev_parents);
+int gb_pf_commit_resample_lazy(gb_pf_t *pf, double log_ml_increment);
 /* Gather rows for global slots [k_lo, k_hi) (inside the shard's offspring range) into DEVICE buffers:
  * dev_rows = S columns of (k_hi-k_lo) elements of the filter dtype, dev_parents = int64 global ids. */
 int gb_pf_export_offspring(gb_pf_t *pf, int64_t k_lo, int64_t k_hi, void *dev_rows, void *dev_parents);

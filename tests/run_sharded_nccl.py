@@ -24,10 +24,11 @@ def main():
     from genb200 import sharded, _lib as L
     L.check(L.lib().gb_set_device(lr))
     rank, world = dist.get_rank(), dist.get_world_size()
-    for n in (100003, 4_000_000):
+    for n, staged in ((100003, False), (100003, True), (4_000_000, False)):
         ys = F.bearings_series(8)
         seed = 17
         spf = sharded.ShardedParticleFilter(g.bearings_model(), n, seed=seed).initialize(ys[0])
+        spf.force_staged = staged
         nres = 0
         for t in range(1, len(ys)):
             nres += spf.maybe_resample_(ess_threshold=(n + 1 if t % 2 else n / 2))
@@ -42,7 +43,7 @@ def main():
                 g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t])
             ok = all(np.array_equal(cols[f], st.get_state(f)) for f in range(4)) and np.array_equal(par, st.parents)
             ok = ok and abs(lml - g.log_ml_estimate(st)) <= 1e-10 * abs(lml)
-            print("NCCL sharded check world=%d n=%d resamples=%d: %s (log ML %.12f)" % (world, n, nres, "OK" if ok else "MISMATCH", lml))
+            print("NCCL sharded check world=%d n=%d staged=%s resamples=%d: %s (log ML %.12f)" % (world, n, staged, nres, "OK" if ok else "MISMATCH", lml))
             if not ok:
                 sys.exit(1)
     dist.destroy_process_group()

@@ -13,7 +13,7 @@ import fixtures as F
 pytestmark = pytest.mark.gpu
 
 
-def run_sharded_in_process(g, model, n, K, ys, seed, dtype="f64"):
+def run_sharded_in_process(g, model, n, K, ys, seed, dtype="f64", fast=False):
     import torch
     from genb200 import sharded, _lib as L
     counts, offs = sharded.shard_bounds(n, K)
@@ -34,20 +34,29 @@ def run_sharded_in_process(g, model, n, K, ys, seed, dtype="f64"):
             u0 = g.philox_resample_u0(seed, t - 1)
             qt, pref, ranges, send = sharded.plan_exchange([x[2] for x in trip], n, offs, u0)
             bufs = {}
+            use_fast = fast and K > 1 and all(
+                sum(send[s_][d][1] - send[s_][d][0] for s_ in range(K) if s_ != d) <= ops[d].ext_capacity() for d in range(K))
             for r in range(K):
                 lo, hi = ops[r].systematic_offspring(m, bits, pref[r], qt, u0)
                 assert (lo, hi) == ranges[r]
                 for d in range(K):
                     a, b = send[r][d]
-                    if b > a:
+                    if use_fast and d == r:
+                        ops[r].offspring_local(a, b)
+                    elif b > a:
                         rows = torch.empty(S * (b - a), dtype=td, device="cuda")
                         par = torch.empty(b - a, dtype=torch.int64, device="cuda")
                         ops[r].export_offspring(a, b, rows, par)
                         bufs[(r, d)] = (a, b, rows, par)
-            for (r, d), (a, b, rows, par) in bufs.items():                   # all-to-all-v
-                ops[d].import_rows(a - offs[d], b - a, rows, par)
+            ext_off = [0] * K
+            for (r, d), (a, b, rows, par) in sorted(bufs.items()):           # all-to-all-v
+                if use_fast:
+                    ops[d].import_ext(a - offs[d], b - a, ext_off[d], rows, par)
+                    ext_off[d] += b - a
+                else:
+                    ops[d].import_rows(a - offs[d], b - a, rows, par)
             for o in ops:
-                o.commit(lse - math.log(n))
+                (o.commit_lazy if use_fast else o.commit)(lse - math.log(n))
         for s in shards:
             g.particle_filter_step_(s, (t,), (g.UnknownChange,), ys[t], return_incr=False)
         m = max(o.weight_max() for o in ops)
@@ -68,6 +77,10 @@ def test_sharded_equals_single_shard_and_oracle(g, O, K, name):
         model, okind, params, ys = g.lgssm_model(**F.LGSSM), O.MODEL_LGSSM, F.lgssm_params(), F.lgssm_series(9)
     n, seed = 50021, 31
     cols, lw, par, lml = run_sharded_in_process(g, model, n, K, ys, seed)
+    # the fast path (local ancestors + extension rows + deferred gather) gives the same filter
+    colsf, lwf, parf, lmlf = run_sharded_in_process(g, model, n, K, ys, seed, fast=True)
+    assert all(np.array_equal(a, b) for a, b in zip(cols, colsf))
+    assert np.array_equal(lw, lwf) and np.array_equal(par, parf) and lml == lmlf
     # single shard through the same pieces (K = 1) and through the ordinary API
     cols1, lw1, par1, lml1 = run_sharded_in_process(g, model, n, 1, ys, seed)
     for a, b in zip(cols, cols1):
