@@ -161,7 +161,7 @@ def run_reference(args):
                                  "restating Gen's particle filter (optimistic stand-in: no trace allocation/dispatch)"},
         "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 def workload_config(args, n_total):
@@ -325,12 +325,30 @@ def run_genb200(args):
         "kernels": kernels,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line goes to the real stdout; everything else the libraries print (NCCL banner, ...)
+    was diverted to stderr."""
+    line = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line.encode())
+    else:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

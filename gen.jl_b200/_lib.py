@@ -62,13 +62,17 @@ SIGNATURES = {
     "gb_pf_sync": (i, [vp]),
     "gb_pf_weight_max": (i, [vp, dp]),
     "gb_pf_weight_sums": (i, [vp, d, i, dp, dp, u64p]),
-    "gb_pf_systematic_offspring": (i, [vp, d, i, u64, u64, u32, i64p, i64p]),
+    "gb_pf_stats_device": (i, [vp, vpp, ip]),
+    "gb_pf_weight_max_device": (i, [vp]),
+    "gb_pf_weight_sums_device": (i, [vp, i]),
+    "gb_pf_systematic_offspring": (i, [vp, d, i, u64, u64, u64, u32, i64p, i64p]),
+    "gb_pf_block_bytes": (i64, [vp, i64]),
     "gb_pf_ext_capacity": (i, [vp, i64p]),
     "gb_pf_offspring_local": (i, [vp, i64, i64]),
-    "gb_pf_import_ext": (i, [vp, i64, i64, i64, vp, vp]),
+    "gb_pf_import_ext": (i, [vp, i64, i64, i64, vp]),
     "gb_pf_commit_resample_lazy": (i, [vp, d]),
-    "gb_pf_export_offspring": (i, [vp, i64, i64, vp, vp]),
-    "gb_pf_import_rows": (i, [vp, i64, i64, vp, vp]),
+    "gb_pf_export_offspring": (i, [vp, i64, i64, vp]),
+    "gb_pf_import_rows": (i, [vp, i64, i64, vp]),
     "gb_pf_commit_resample": (i, [vp, d]),
     "gb_importance_sampling": (i, [vp, i64, i, u64, dp, i, i, dp, i, dp, i, dp, i, dp, dp, vpp]),
     "gb_resample": (i, [dp, i64, i, i, u32, u64p, u64, u32, i64p]),

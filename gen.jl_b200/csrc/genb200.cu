@@ -633,7 +633,7 @@ static int ensure_max(gb_pf *pf, const void *logw) {
 }
 // one pass over the log weights: (s1, s2) w.r.t. the reference max + quantised tile / super-tile totals;
 // the reference max is read from d_stats->m (from_device) or passed by value (sharded: global max)
-static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_device) {
+static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_device, bool sync_host = true) {
   const int bits = quant_bits(pf->n_global);
   CK(cudaMemsetAsync(pf->super_q, 0, (size_t)(pf->nsuper + 1) * 8, pf->stream));
   CK(cudaMemsetAsync(pf->tile_q, 0, (size_t)(pf->ntiles + 1) * 8, pf->stream));
@@ -649,8 +649,12 @@ static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_devic
                                                                      pf->super_q, pf->partials, pf->ticket, pf->d_stats));
   }
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(pf->h_stats, pf->d_stats, sizeof(WeightStats), cudaMemcpyDeviceToHost, pf->stream));
-  CK(cudaStreamSynchronize(pf->stream));
+  if (sync_host) {
+    CK(cudaMemcpyAsync(pf->h_stats, pf->d_stats, sizeof(WeightStats), cudaMemcpyDeviceToHost, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+  } else if (pf->wstate != W_ZERO) {
+    pf->wstate = W_MAX;        // the host copy no longer describes the weights; the device max does
+  }
   pf->tiles_valid = true;
   return GB_OK;
 }
@@ -680,6 +684,33 @@ extern "C" int gb_pf_weight_max(gb_pf_t *pf, double *m_local) {
   CK(cudaStreamSynchronize(pf->stream));
   *m_local = pf->h_stats->m;
   return GB_OK;
+}
+// Device-resident flavour for the sharded flow (no host round trip between the collectives): the host
+// all-reduces stats->m in place, then this launches the statistics pass reading m from device memory.
+extern "C" int gb_pf_stats_device(gb_pf_t *pf, void **dev_stats, int *n_words) {
+  REQ(pf && dev_stats, "null argument");
+  *dev_stats = pf->d_stats;
+  if (n_words) *n_words = (int)(sizeof(WeightStats) / 8);
+  return GB_OK;
+}
+extern "C" int gb_pf_weight_max_device(gb_pf_t *pf) {
+  REQ(pf, "null handle");
+  if (pf->wstate == W_ZERO) {   // all log weights are exactly 0.0: the device copy of the max must say so
+    CK(cudaMemsetAsync(&pf->d_stats->m, 0, sizeof(double), pf->stream));
+    return GB_OK;
+  }
+  if (pf->wstate == W_STATS) {
+    CK(cudaMemcpyAsync(&pf->d_stats->m, &pf->h_stats->m, sizeof(double), cudaMemcpyHostToDevice, pf->stream));
+    return GB_OK;
+  }
+  return ensure_max(pf, pf->logw);
+}
+extern "C" int gb_pf_weight_sums_device(gb_pf_t *pf, int bits) {
+  REQ(pf, "null handle");
+  REQ(bits == quant_bits(pf->n_global), "gb_pf_weight_sums_device: bits must be gb_quant_bits(n_global)");
+  int rc = materialize_pending(pf);
+  if (rc) return rc;
+  return run_wstats(pf, pf->logw, 0.0, true, false);
 }
 extern "C" int gb_pf_weight_sums(gb_pf_t *pf, double m_ref, int bits, double *s1, double *s2, uint64_t *q_local) {
   REQ(pf && s1 && s2 && q_local, "null argument");
@@ -872,18 +903,18 @@ static int fetch_plan(gb_pf *pf) {
 // shard's offspring slots; single shard: q_offset = 0, q_total = 0 (= the local total), anc_base = 0.
 template <typename R>
 static int launch_systematic(gb_pf *pf, const void *logw, double m, uint64_t q_offset, uint64_t q_total, uint32_t u0,
-                             int *anc, long long anc_base) {
+                             const AncOut &ao) {
   const int bits = quant_bits(pf->n_global);
   LAUNCH(pf, GB_K_TILESCAN, superscan_kernel<<<1, 1024, 0, pf->stream>>>(pf->nsuper, pf->super_q, pf->super_excl, pf->d_plan, q_offset,
                                                                           q_total, pf->n_global, u0, pf->oflow_count));
   CK(cudaGetLastError());
   auto kern = ancestors_sys_kernel<R>;
   LAUNCH(pf, GB_K_ANCESTORS, kern<<<(unsigned)pf->ntiles, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->tile_q, pf->super_excl,
-                                                                                    pf->d_plan, anc, anc_base, pf->oflow, pf->oflow_count));
+                                                                                    pf->d_plan, ao, pf->oflow, pf->oflow_count));
   CK(cudaGetLastError());
   auto okern = overflow_sys_kernel<R>;
-  LAUNCH(pf, GB_K_ANCESTORS, okern<<<pf->num_sms * 4, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->d_plan, anc, anc_base,
-                                                                                pf->oflow, pf->oflow_count));
+  LAUNCH(pf, GB_K_ANCESTORS, okern<<<pf->num_sms * 4, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->d_plan, ao, pf->oflow,
+                                                                                pf->oflow_count));
   CK(cudaGetLastError());
   return GB_OK;
 }
@@ -898,7 +929,7 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
   int rc;
   if (kind == GB_RESAMPLE_SYSTEMATIC) {
     if (!pf->tiles_valid && (rc = run_wstats(pf, logw, m, false))) return rc;
-    return launch_systematic<R>(pf, logw, m, 0, 0, u0, anc, 0);
+    return launch_systematic<R>(pf, logw, m, 0, 0, u0, AncOut{anc, 0, pf->n_global, nullptr, 0});
   }
   if (kind == GB_RESAMPLE_RESIDUAL) {
     if ((rc = ensure_residual_ws(pf))) return rc;
@@ -955,19 +986,19 @@ extern "C" int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind,
 }
 
 // ---- sharded pieces ----
-extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits, uint64_t q_offset, uint64_t q_total,
-                                          uint32_t u0, int64_t *slot_lo, int64_t *slot_hi) {
+extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits, uint64_t q_offset, uint64_t q_local,
+                                          uint64_t q_total, uint32_t u0, int64_t *slot_lo, int64_t *slot_hi) {
   REQ(pf && slot_lo && slot_hi, "null argument");
   REQ(q_total > 0, "gb_pf_systematic_offspring: zero total weight");
   REQ(bits == quant_bits(pf->n_global), "gb_pf_systematic_offspring: bits must be gb_quant_bits(n_global)");
-  REQ(pf->tiles_valid && pf->h_stats->m == m_global, "gb_pf_systematic_offspring: call gb_pf_weight_sums(m_global) first");
+  REQ(pf->tiles_valid, "gb_pf_systematic_offspring: call gb_pf_weight_sums(m_global) first");
   int rc;
   // the shard's offspring range is [slots_below(q_offset), slots_below(q_offset + Q_local)): host-side
   // evaluation of the same exact integer function the kernels use
   SweepParams sp;
   sp.q_total = q_total; sp.q_inv = 1.0 / (double)q_total; sp.dscale = (uint64_t)pf->n_global << 32;
   sp.ratio = (double)pf->n_global / (double)q_total; sp.u0 = u0;
-  const long long lo = slots_below(q_offset, sp), hi = slots_below(q_offset + pf->h_stats->q_total, sp);
+  const long long lo = slots_below(q_offset, sp), hi = slots_below(q_offset + q_local, sp);
   const long long cnt = hi - lo;
   if (cnt > pf->off_cap) {
     cudaFree(pf->off_anc);
@@ -977,8 +1008,10 @@ extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits
     pf->off_cap = cap;
   }
   if (cnt > 0) {
-    rc = pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, m_global, q_offset, q_total, u0, pf->off_anc, lo)
-                             : launch_systematic<float>(pf, pf->logw, m_global, q_offset, q_total, u0, pf->off_anc, lo);
+    // offspring slots this shard owns go straight into its `anc` column; the rest into the spill buffer
+    const AncOut ao{pf->anc, pf->pid_offset, pf->pid_offset + pf->n, pf->off_anc, lo};
+    rc = pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, m_global, q_offset, q_total, u0, ao)
+                             : launch_systematic<float>(pf, pf->logw, m_global, q_offset, q_total, u0, ao);
     if (rc) return rc;
   }
   pf->off_lo = lo; pf->off_hi = hi;
@@ -994,14 +1027,10 @@ extern "C" int gb_pf_offspring_local(gb_pf_t *pf, int64_t k_lo, int64_t k_hi) {
   REQ(pf, "null handle");
   REQ(k_lo >= pf->off_lo && k_hi <= pf->off_hi && k_lo <= k_hi, "gb_pf_offspring_local: slots outside the shard's offspring range");
   REQ(k_lo >= pf->pid_offset && k_hi <= pf->pid_offset + pf->n, "gb_pf_offspring_local: slots not owned by this shard");
-  if (k_hi > k_lo)
-    CK(cudaMemcpyAsync(pf->anc + (k_lo - pf->pid_offset), pf->off_anc + (k_lo - pf->off_lo), (size_t)(k_hi - k_lo) * 4,
-                       cudaMemcpyDeviceToDevice, pf->stream));
-  return GB_OK;
+  return GB_OK;   // the sweep already wrote these ancestors into the shard's `anc` column
 }
-extern "C" int gb_pf_import_ext(gb_pf_t *pf, int64_t dst_lo, int64_t count, int64_t ext_offset, const void *dev_rows,
-                                const void *dev_parents) {
-  REQ(pf && dev_rows && dev_parents, "null argument");
+extern "C" int gb_pf_import_ext(gb_pf_t *pf, int64_t dst_lo, int64_t count, int64_t ext_offset, const void *dev_block) {
+  REQ(pf && dev_block, "null argument");
   REQ(dst_lo >= 0 && count >= 0 && dst_lo + count <= pf->n, "gb_pf_import_ext: destination outside the shard");
   if (ext_offset < 0 || ext_offset + count > pf->ext_cap) return fail(GB_ESTATE, "gb_pf_import_ext: extension rows exhausted");
   if (count == 0) return GB_OK;
@@ -1009,14 +1038,12 @@ extern "C" int gb_pf_import_ext(gb_pf_t *pf, int64_t dst_lo, int64_t count, int6
     auto kern = import_ext_kernel<double>;
     int grid = grid_for(pf, kern, count, kBlock);
     LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((double *)pf->state[pf->cur], pf->ld, pf->S, dst_lo, count, pf->n_pad + ext_offset,
-                                                                   (const double *)dev_rows, (const long long *)dev_parents, pf->anc,
-                                                                   pf->ext_parents + ext_offset));
+                                                                   dev_block, pf->anc, pf->ext_parents + ext_offset));
   } else {
     auto kern = import_ext_kernel<float>;
     int grid = grid_for(pf, kern, count, kBlock);
     LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((float *)pf->state[pf->cur], pf->ld, pf->S, dst_lo, count, pf->n_pad + ext_offset,
-                                                                   (const float *)dev_rows, (const long long *)dev_parents, pf->anc,
-                                                                   pf->ext_parents + ext_offset));
+                                                                   dev_block, pf->anc, pf->ext_parents + ext_offset));
   }
   CK(cudaGetLastError());
   pf->ext_used = true;
@@ -1034,41 +1061,46 @@ extern "C" int gb_pf_commit_resample_lazy(gb_pf_t *pf, double log_ml_increment) 
   if (!pf->lazy) rc = run_gather(pf);
   return rc;
 }
-extern "C" int gb_pf_export_offspring(gb_pf_t *pf, int64_t k_lo, int64_t k_hi, void *dev_rows, void *dev_parents) {
-  REQ(pf && dev_rows && dev_parents, "null argument");
+extern "C" int64_t gb_pf_block_bytes(const gb_pf_t *pf, int64_t count) {
+  if (!pf || count < 0) return -1;
+  const int64_t raw = count * (8 + (int64_t)pf->S * (int64_t)pf->esz);
+  return (raw + 15) / 16 * 16;
+}
+extern "C" int gb_pf_export_offspring(gb_pf_t *pf, int64_t k_lo, int64_t k_hi, void *dev_block) {
+  REQ(pf && dev_block, "null argument");
   REQ(k_lo >= pf->off_lo && k_hi <= pf->off_hi && k_lo <= k_hi, "gb_pf_export_offspring: slots outside the shard's offspring range");
   const long long cnt = k_hi - k_lo;
   if (cnt == 0) return GB_OK;
-  const int *anc = pf->off_anc + (k_lo - pf->off_lo);
+  // ancestors of owned slots live in the `anc` column, the others in the spill buffer
+  const long long own_lo = pf->pid_offset, own_hi = pf->pid_offset + pf->n;
+  const bool owned = k_lo >= own_lo && k_hi <= own_hi;
+  REQ(owned || k_hi <= own_lo || k_lo >= own_hi, "gb_pf_export_offspring: range straddles the shard boundary");
+  const int *anc = owned ? pf->anc + (k_lo - own_lo) : pf->off_anc + (k_lo - pf->off_lo);
   if (pf->dtype == GB_F64) {
     auto kern = export_kernel<double>;
     int grid = grid_for(pf, kern, cnt, kBlock);
-    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)pf->state[pf->cur], pf->ld, pf->S, anc, cnt,
-                                                                   (double *)dev_rows, (long long *)dev_parents, pf->pid_offset));
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)pf->state[pf->cur], pf->ld, pf->S, anc, cnt, dev_block, pf->pid_offset));
   } else {
     auto kern = export_kernel<float>;
     int grid = grid_for(pf, kern, cnt, kBlock);
-    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)pf->state[pf->cur], pf->ld, pf->S, anc, cnt,
-                                                                   (float *)dev_rows, (long long *)dev_parents, pf->pid_offset));
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)pf->state[pf->cur], pf->ld, pf->S, anc, cnt, dev_block, pf->pid_offset));
   }
   CK(cudaGetLastError());
   return GB_OK;
 }
-extern "C" int gb_pf_import_rows(gb_pf_t *pf, int64_t dst_lo, int64_t count, const void *dev_rows, const void *dev_parents) {
-  REQ(pf && dev_rows && dev_parents, "null argument");
+extern "C" int gb_pf_import_rows(gb_pf_t *pf, int64_t dst_lo, int64_t count, const void *dev_block) {
+  REQ(pf && dev_block, "null argument");
   REQ(dst_lo >= 0 && count >= 0 && dst_lo + count <= pf->n, "gb_pf_import_rows: destination outside the shard");
   if (count == 0) return GB_OK;
   if (!pf->parents64) CK(cudaMalloc((void **)&pf->parents64, (size_t)pf->ld * 8));
   if (pf->dtype == GB_F64) {
     auto kern = import_kernel<double>;
     int grid = grid_for(pf, kern, count, kBlock);
-    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((double *)pf->state[pf->cur ^ 1], pf->ld, pf->S, dst_lo, count,
-                                                                   (const double *)dev_rows, (const long long *)dev_parents, pf->parents64));
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((double *)pf->state[pf->cur ^ 1], pf->ld, pf->S, dst_lo, count, dev_block, pf->parents64));
   } else {
     auto kern = import_kernel<float>;
     int grid = grid_for(pf, kern, count, kBlock);
-    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((float *)pf->state[pf->cur ^ 1], pf->ld, pf->S, dst_lo, count,
-                                                                   (const float *)dev_rows, (const long long *)dev_parents, pf->parents64));
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((float *)pf->state[pf->cur ^ 1], pf->ld, pf->S, dst_lo, count, dev_block, pf->parents64));
   }
   CK(cudaGetLastError());
   return GB_OK;

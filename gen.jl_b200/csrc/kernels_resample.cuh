@@ -454,12 +454,16 @@ __global__ void __launch_bounds__(kBlock) gather_kernel(const R *__restrict__ si
   }
 }
 
-// gather for the sharded path: rows of slots [0, count) (ancestors anc[0..count)) into a compact
-// [S][count] buffer + int64 global parent ids
+// Exchange block of `count` offspring rows: [parents: count x int64 (global, 1-based)][rows: S x count x R]
+template <typename R> GB_HD long long *block_parents(void *blk) { return reinterpret_cast<long long *>(blk); }
+template <typename R> GB_HD R *block_rows(void *blk, long long count) { return reinterpret_cast<R *>(reinterpret_cast<long long *>(blk) + count); }
+
+// gather for the sharded path: rows of `count` consecutive offspring slots (ancestors anc[0..count)) into a block
 template <typename R>
 __global__ void __launch_bounds__(kBlock) export_kernel(const R *__restrict__ sin, long long ld, int S, const int *__restrict__ anc,
-                                                        long long count, R *__restrict__ rows, long long *__restrict__ parents,
-                                                        long long pid_offset) {
+                                                        long long count, void *blk, long long pid_offset) {
+  long long *parents = block_parents<R>(blk);
+  R *rows = block_rows<R>(blk, count);
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < count; i += (long long)gridDim.x * kBlock) {
     const int src = __ldcs(anc + i);
     for (int s = 0; s < S; s++) rows[(long long)s * count + i] = __ldg(sin + (long long)s * ld + src);
@@ -468,8 +472,9 @@ __global__ void __launch_bounds__(kBlock) export_kernel(const R *__restrict__ si
 }
 template <typename R>
 __global__ void __launch_bounds__(kBlock) import_kernel(R *__restrict__ sout, long long ld, int S, long long dst_lo, long long count,
-                                                        const R *__restrict__ rows, const long long *__restrict__ parents_in,
-                                                        long long *__restrict__ parents) {
+                                                        const void *blk, long long *__restrict__ parents) {
+  const long long *parents_in = block_parents<R>(const_cast<void *>(blk));
+  const R *rows = block_rows<R>(const_cast<void *>(blk), count);
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < count; i += (long long)gridDim.x * kBlock) {
     for (int s = 0; s < S; s++) sout[(long long)s * ld + dst_lo + i] = rows[(long long)s * count + i];
     parents[dst_lo + i] = parents_in[i];
@@ -495,9 +500,10 @@ __global__ void __launch_bounds__(kBlock) parents_from_anc_kernel(const int *__r
 // buffer; the destination slots' ancestors point at them
 template <typename R>
 __global__ void __launch_bounds__(kBlock) import_ext_kernel(R *__restrict__ scur, long long ld, int S, long long dst_lo, long long count,
-                                                            long long ext_row, const R *__restrict__ rows,
-                                                            const long long *__restrict__ parents_in, int *__restrict__ anc,
+                                                            long long ext_row, const void *blk, int *__restrict__ anc,
                                                             long long *__restrict__ ext_parents) {
+  const long long *parents_in = block_parents<R>(const_cast<void *>(blk));
+  const R *rows = block_rows<R>(const_cast<void *>(blk), count);
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < count; i += (long long)gridDim.x * kBlock) {
     for (int s = 0; s < S; s++) scur[(long long)s * ld + ext_row + i] = rows[(long long)s * count + i];
     anc[dst_lo + i] = (int)(ext_row + i);
@@ -581,6 +587,15 @@ __global__ void __launch_bounds__(1024) superscan_kernel(long long nsuper, const
   }
 }
 
+// Where the ancestors of output slot k go: slots this shard owns -> own[k - own_lo] (the shard's `anc`
+// column, consumed by the deferred gather); slots owned by other shards -> spill[k - spill_base]
+struct AncOut {
+  int *own;
+  long long own_lo, own_hi;
+  int *spill;
+  long long spill_base;
+};
+
 constexpr int kHeavyCap = 16;                       // offspring a thread writes itself; more => CTA-cooperative fill
 constexpr int kHeavyMax = kChunk / (kHeavyCap + 1) + 2;
 
@@ -618,8 +633,8 @@ struct TileSmem {
 template <typename R, bool PREFIX>
 GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits, const SweepParams &sp, long long tile,
                     const uint64_t *__restrict__ tile_q, const unsigned long long *__restrict__ super_excl, uint64_t q_offset,
-                    uint64_t cbase_in, long long slot0_in, long long lo_in, long long hi_in, int *__restrict__ anc,
-                    long long anc_base, TileSmem &sm, long long *slot0_out, long long *slot_end_out) {
+                    uint64_t cbase_in, long long slot0_in, long long lo_in, long long hi_in, const AncOut &ao,
+                    TileSmem &sm, long long *slot0_out, long long *slot_end_out) {
   double lw[kItems];
   load_items<R>(logw, tile * kTile, n, lw);
   const double u0term = -(double)sp.u0 * 0x1p-32;
@@ -695,22 +710,25 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
   if (nh) __syncthreads();
   // coalesced copy-out
   const int tile_base = (int)(tile * kTile);
-  int *__restrict__ out = anc + (lo - anc_base);
-  for (int i = threadIdx.x; i < cnt; i += kBlock) __stcs(out + i, tile_base + sm.slot[i]);
+  for (int i = threadIdx.x; i < cnt; i += kBlock) {
+    const long long k = lo + i;
+    int *dst = (k >= ao.own_lo && k < ao.own_hi) ? ao.own + (k - ao.own_lo) : ao.spill + (k - ao.spill_base);
+    __stcs(dst, tile_base + sm.slot[i]);
+  }
 }
 
 template <typename R>
 __global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const R *__restrict__ logw, long long n, double m, int bits,
                                                                const uint64_t *__restrict__ tile_q,
                                                                const unsigned long long *__restrict__ super_excl,
-                                                               const ResamplePlan *__restrict__ plan, int *__restrict__ anc,
-                                                               long long anc_base, OverflowEntry *__restrict__ oflow,
+                                                               const ResamplePlan *__restrict__ plan, const AncOut ao,
+                                                               OverflowEntry *__restrict__ oflow,
                                                                unsigned int *__restrict__ oflow_count) {
   __shared__ TileSmem sm;
   const SweepParams sp = plan->sp;
   const long long tile = blockIdx.x;
   long long slot0, slot_end;
-  tile_fill<R, true>(logw, n, m, bits, sp, tile, tile_q, super_excl, plan->q_offset, 0, 0, 0, 0, anc, anc_base, sm, &slot0, &slot_end);
+  tile_fill<R, true>(logw, n, m, bits, sp, tile, tile_q, super_excl, plan->q_offset, 0, 0, 0, 0, ao, sm, &slot0, &slot_end);
   if (slot_end > slot0 + kChunk && threadIdx.x == 0) {
     const unsigned int e = atomicAdd(oflow_count, 1u);
     oflow[e] = OverflowEntry{tile, slot0, slot0 + kChunk, slot_end, sm.cbase};
@@ -721,8 +739,8 @@ __global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const R *__restri
 // round-robin to the CTAs of a fixed-size grid.
 template <typename R>
 __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restrict__ logw, long long n, double m, int bits,
-                                                              const ResamplePlan *__restrict__ plan, int *__restrict__ anc,
-                                                              long long anc_base, const OverflowEntry *__restrict__ oflow,
+                                                              const ResamplePlan *__restrict__ plan, const AncOut ao,
+                                                              const OverflowEntry *__restrict__ oflow,
                                                               const unsigned int *__restrict__ oflow_count) {
   __shared__ TileSmem sm;
   const unsigned int ne = *oflow_count;
@@ -739,8 +757,7 @@ __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restric
       long long hi = lo + kChunk;
       if (hi > en.slot_hi) hi = en.slot_hi;
       __syncthreads();
-      tile_fill<R, false>(logw, n, m, bits, sp, en.tile, nullptr, nullptr, 0, en.cbase, en.slot0, lo, hi, anc, anc_base, sm, nullptr,
-                          nullptr);
+      tile_fill<R, false>(logw, n, m, bits, sp, en.tile, nullptr, nullptr, 0, en.cbase, en.slot0, lo, hi, ao, sm, nullptr, nullptr);
     }
     unit0 += pieces;
   }

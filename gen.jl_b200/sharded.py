@@ -56,12 +56,21 @@ def plan_exchange(q_locals, n_global, offs, u0):
     return q_total, pref, ranges, send
 
 
+class _DevWords:
+    """Device memory as a torch int64 tensor (through __cuda_array_interface__; no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 3}
+
+
 class ShardOps:
     """A shard of the particle store behind the C ABI."""
 
     def __init__(self, state):
         self.state = state
         self.h = state._h
+        self.state_dim = state.state_dim
+        self.esz = 8 if state.dtype == L.F64 else 4
 
     def weight_max(self):
         v = C.c_double()
@@ -73,16 +82,31 @@ class ShardOps:
         L.check(L.lib().gb_pf_weight_sums(self.h, m_ref, bits, C.byref(s1), C.byref(s2), C.byref(q)))
         return s1.value, s2.value, q.value
 
-    def systematic_offspring(self, m_ref, bits, q_offset, q_total, u0):
+    # device-resident statistics record {m, s1, s2, lse, ess, q_total} for collectives without host round trips
+    def stats_tensor(self, torch):
+        p, n = C.c_void_p(), C.c_int()
+        L.check(L.lib().gb_pf_stats_device(self.h, C.byref(p), C.byref(n)))
+        return torch.as_tensor(_DevWords(p.value, n.value), device="cuda")
+
+    def weight_max_device(self):
+        L.check(L.lib().gb_pf_weight_max_device(self.h))
+
+    def weight_sums_device(self, bits):
+        L.check(L.lib().gb_pf_weight_sums_device(self.h, bits))
+
+    def systematic_offspring(self, m_ref, bits, q_offset, q_local, q_total, u0):
         lo, hi = C.c_int64(), C.c_int64()
-        L.check(L.lib().gb_pf_systematic_offspring(self.h, m_ref, bits, q_offset, q_total, u0, C.byref(lo), C.byref(hi)))
+        L.check(L.lib().gb_pf_systematic_offspring(self.h, m_ref, bits, q_offset, q_local, q_total, u0, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
 
-    def export_offspring(self, k_lo, k_hi, rows, parents):
-        L.check(L.lib().gb_pf_export_offspring(self.h, k_lo, k_hi, C.c_void_p(rows.data_ptr()), C.c_void_p(parents.data_ptr())))
+    def block_bytes(self, count):
+        return int(L.lib().gb_pf_block_bytes(self.h, int(count)))
 
-    def import_rows(self, dst_lo, count, rows, parents):
-        L.check(L.lib().gb_pf_import_rows(self.h, dst_lo, count, C.c_void_p(rows.data_ptr()), C.c_void_p(parents.data_ptr())))
+    def export_offspring(self, k_lo, k_hi, block):
+        L.check(L.lib().gb_pf_export_offspring(self.h, k_lo, k_hi, C.c_void_p(block.data_ptr())))
+
+    def import_rows(self, dst_lo, count, block):
+        L.check(L.lib().gb_pf_import_rows(self.h, dst_lo, count, C.c_void_p(block.data_ptr())))
 
     def commit(self, log_ml_increment):
         L.check(L.lib().gb_pf_commit_resample(self.h, log_ml_increment))
@@ -96,9 +120,8 @@ class ShardOps:
     def offspring_local(self, k_lo, k_hi):
         L.check(L.lib().gb_pf_offspring_local(self.h, k_lo, k_hi))
 
-    def import_ext(self, dst_lo, count, ext_offset, rows, parents):
-        L.check(L.lib().gb_pf_import_ext(self.h, dst_lo, count, ext_offset, C.c_void_p(rows.data_ptr()),
-                                         C.c_void_p(parents.data_ptr())))
+    def import_ext(self, dst_lo, count, ext_offset, block):
+        L.check(L.lib().gb_pf_import_ext(self.h, dst_lo, count, ext_offset, C.c_void_p(block.data_ptr())))
 
     def commit_lazy(self, log_ml_increment):
         L.check(L.lib().gb_pf_commit_resample_lazy(self.h, log_ml_increment))
@@ -136,8 +159,10 @@ class ShardedParticleFilter:
             self.ops = ops_factory(self)
             self.device = torch.device("cpu")
             self.tdtype = torch.float64
-        self.state_dim = self.ops.state.state_dim if ops_factory is None else self.ops.state_dim
+        self.state_dim = self.ops.state_dim
         self.last_ess = None
+        self._stats_t = None        # device-resident statistics record (CUDA shards)
+        self._gather_t = None
         self._bufs = {}
         # extension-row capacity of every shard (same formula on every rank: no collective needed)
         self.ext_caps = None
@@ -170,7 +195,8 @@ class ShardedParticleFilter:
 
     def _all_to_all_v(self, send, send_counts, recv_counts):
         torch, dist = self.torch, self.dist
-        recv = torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
+        recv = self._buffer(int(sum(recv_counts)), "recv")[:int(sum(recv_counts))] if send.dtype == torch.uint8 \
+            else torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
         if self.world == 1:
             recv.copy_(send)
             return recv
@@ -207,9 +233,25 @@ class ShardedParticleFilter:
 
     def _global_stats(self):
         """Global (m, lse, ess) and the gathered integer masses (particle_filter.jl:3-12 over all shards)."""
-        m = self._allreduce_max(self.ops.weight_max())
-        s1, s2, q = self.ops.weight_sums(m, self.bits)
-        s1s, s2s, qs = self._allgather_triple(s1, s2, q)
+        if self.device.type == "cuda" and self.world > 1:
+            # collectives run directly on the shard's device-resident statistics record: all-reduce(max) of
+            # m in place, statistics pass w.r.t. that m, all-gather of the records, ONE device->host read
+            torch, dist = self.torch, self.dist
+            if self._stats_t is None:
+                self._stats_t = self.ops.stats_tensor(torch)
+                self._gather_t = torch.empty(self.world * self._stats_t.numel(), dtype=torch.int64, device=self.device)
+            self.ops.weight_max_device()
+            dist.all_reduce(self._stats_t[0:1].view(torch.float64), op=dist.ReduceOp.MAX, group=self.group)
+            self.ops.weight_sums_device(self.bits)
+            dist.all_gather_into_tensor(self._gather_t, self._stats_t, group=self.group)
+            rec = self._gather_t.cpu().numpy().reshape(self.world, -1)
+            m = float(rec[0, 0:1].copy().view(np.float64)[0])
+            s1s, s2s = rec[:, 1].copy().view(np.float64), rec[:, 2].copy().view(np.float64)
+            qs = [int(v) for v in rec[:, 5]]
+        else:
+            m = self._allreduce_max(self.ops.weight_max())
+            s1, s2, q = self.ops.weight_sums(m, self.bits)
+            s1s, s2s, qs = self._allgather_triple(s1, s2, q)
         S1, S2 = float(np.sum(s1s)), float(np.sum(s2s))      # fixed rank order: identical on every rank
         lse = -math.inf if m == -math.inf else m + math.log(S1)
         ess = (S1 * S1) / S2 if S2 > 0 else float("nan")
@@ -231,76 +273,55 @@ class ShardedParticleFilter:
             return False
         u0 = api.philox_resample_u0(self.seed, self.step)
         q_total, pref, ranges, send = plan_exchange(qs, self.n_global, self.offs, u0)
-        lo, hi = self.ops.systematic_offspring(m, self.bits, pref[self.rank], q_total, u0)
-        assert (lo, hi) == ranges[self.rank], "offspring range mismatch between host plan and device sweep"
-        S, torch = self.state_dim, self.torch
-        me = self.rank
-        send_cnt = [send[me][d][1] - send[me][d][0] for d in range(self.world)]
-        recv_cnt = [send[s][me][1] - send[s][me][0] for s in range(self.world)]
+        me, W = self.rank, self.world
+        lo, hi = self.ops.systematic_offspring(m, self.bits, pref[me], qs[me], q_total, u0)
+        assert (lo, hi) == ranges[me], "offspring range mismatch between host plan and device sweep"
+        send_cnt = [send[me][d][1] - send[me][d][0] for d in range(W)]
+        recv_cnt = [send[s][me][1] - send[s][me][0] for s in range(W)]
         # Fast path when every shard can park its incoming rows in its extension rows (all ranks evaluate
         # the same predicate from the gathered plan, so no extra collective is needed to agree on it)
         fast = self.ext_caps is not None and not self.force_staged and all(
-            sum(send[s][d][1] - send[s][d][0] for s in range(self.world) if s != d) <= self.ext_caps[d]
-            for d in range(self.world))
+            sum(send[s][d][1] - send[s][d][0] for s in range(W) if s != d) <= self.ext_caps[d] for d in range(W))
         if fast:
             a, b = send[me][me]
             self.ops.offspring_local(a, b)                   # stays here: ancestors only, gather deferred
-            sc = [0 if d == me else c for d, c in enumerate(send_cnt)]
-            rc = [0 if s == me else c for s, c in enumerate(recv_cnt)]
-            nsend, nrecv = sum(sc), sum(rc)
-            rows, parents = self._buffers(S * nsend, nsend, "send")
-            ro = po = 0
-            for d in range(self.world):
-                if sc[d]:
+            send_cnt[me] = 0
+            recv_cnt[me] = 0
+        sbytes = [self.ops.block_bytes(c) for c in send_cnt]
+        rbytes = [self.ops.block_bytes(c) for c in recv_cnt]
+        any_traffic = any(send[s][d][1] > send[s][d][0] for s in range(W) for d in range(W) if not (fast and s == d))
+        if any_traffic:
+            sbuf = self._buffer(sum(sbytes), "send")
+            off = 0
+            for d in range(W):                               # per destination one block, in rank order
+                if send_cnt[d]:
                     a, b = send[me][d]
-                    self.ops.export_offspring(a, b, rows[ro:ro + S * sc[d]], parents[po:po + sc[d]])
-                    ro += S * sc[d]
-                    po += sc[d]
-            if self.world > 1:
-                rrows = self._all_to_all_v(rows[:S * nsend], [S * c for c in sc], [S * c for c in rc])
-                rpar = self._all_to_all_v(parents[:nsend], sc, rc)
-                ro = po = 0
-                for s_ in range(self.world):
-                    if rc[s_]:
-                        a, b = send[s_][me]
-                        self.ops.import_ext(a - self.offs[me], rc[s_], po, rrows[ro:ro + S * rc[s_]], rpar[po:po + rc[s_]])
-                        ro += S * rc[s_]
-                        po += rc[s_]
-            self.ops.commit_lazy(lse - math.log(self.n_global))   # :263
-            return True
-        # Staged exchange (arbitrarily skewed weights): every offspring row goes through the all-to-all-v
-        rows = torch.empty(S * (hi - lo), dtype=self.tdtype, device=self.device)
-        parents = torch.empty(hi - lo, dtype=torch.int64, device=self.device)
-        # export: per destination a contiguous [S][count] block (+ parents), in rank order
-        ro = po = 0
-        for d in range(self.world):
-            a, b = send[me][d]
-            c = b - a
-            if c:
-                self.ops.export_offspring(a, b, rows[ro:ro + S * c], parents[po:po + c])
-            ro += S * c
-            po += c
-        rrows = self._all_to_all_v(rows, [S * c for c in send_cnt], [S * c for c in recv_cnt])
-        rpar = self._all_to_all_v(parents, send_cnt, recv_cnt)
-        ro = po = 0
-        for s in range(self.world):
-            a, b = send[s][me]
-            c = b - a
-            if c:
-                self.ops.import_rows(a - self.offs[me], c, rrows[ro:ro + S * c], rpar[po:po + c])
-            ro += S * c
-            po += c
-        assert po == self.n_local, "resampled shard is not full: %d of %d" % (po, self.n_local)
-        self.ops.commit(lse - math.log(self.n_global))       # :263
+                    self.ops.export_offspring(a, b, sbuf[off:off + sbytes[d]])
+                off += sbytes[d]
+            rbuf = self._all_to_all_v(sbuf[:sum(sbytes)], sbytes, rbytes)
+            off = ext = 0
+            for s_ in range(W):
+                if recv_cnt[s_]:
+                    a, b = send[s_][me]
+                    blk = rbuf[off:off + rbytes[s_]]
+                    if fast:
+                        self.ops.import_ext(a - self.offs[me], recv_cnt[s_], ext, blk)
+                        ext += recv_cnt[s_]
+                    else:
+                        self.ops.import_rows(a - self.offs[me], recv_cnt[s_], blk)
+                off += rbytes[s_]
+        if fast:
+            self.ops.commit_lazy(lse - math.log(self.n_global))    # :263
+        else:
+            assert sum(recv_cnt) == self.n_local, "resampled shard is not full"
+            self.ops.commit(lse - math.log(self.n_global))         # :263
         return True
 
-    def _buffers(self, nrows, npar, tag):
-        """Reusable exchange buffers (grown geometrically) instead of one allocation per resample."""
-        torch = self.torch
+    def _buffer(self, nbytes, tag):
+        """Reusable byte buffer for the exchange (grown geometrically) instead of one allocation per resample."""
         cur = self._bufs.get(tag)
-        if cur is None or cur[0].numel() < nrows or cur[1].numel() < npar:
-            cur = (torch.empty(max(int(nrows * 1.5), 1024), dtype=self.tdtype, device=self.device),
-                   torch.empty(max(int(npar * 1.5), 1024), dtype=torch.int64, device=self.device))
+        if cur is None or cur.numel() < nbytes:
+            cur = self.torch.empty(max(int(nbytes * 1.5), 4096), dtype=self.torch.uint8, device=self.device)
             self._bufs[tag] = cur
         return cur
 

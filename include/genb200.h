@@ -108,11 +108,22 @@ int gb_pf_weight_max(gb_pf_t *pf, double *m_local);
  * s1 = sum exp(lw - m_ref), s2 = sum exp(2 (lw - m_ref)) (inference.jl:3-6, particle_filter.jl:3-12) and
  * q_local = sum floor(exp(lw - m_ref) * 2^bits), the shard's integer CDF mass; bits = gb_quant_bits(n_global). */
 int gb_pf_weight_sums(gb_pf_t *pf, double m_ref, int bits, double *s1, double *s2, uint64_t *q_local);
-/* Offspring of this shard's particles under global-prefix systematic resampling: the shard's
- * particles fill the global slot range [*slot_lo, *slot_hi).  Ancestors (global ids) for that range
- * are kept in the handle for gb_pf_export_offspring. */
-int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits, uint64_t q_offset, uint64_t q_total,
-                               uint32_t u0, int64_t *slot_lo, int64_t *slot_hi);
+/* Device-resident flavour of the two calls above, so that the host can run the collectives directly on
+ * device memory (no host round trip): gb_pf_stats_device returns the DEVICE address of the statistics
+ * record {m, s1, s2, lse, ess, q_total} (n_words 8-byte words); gb_pf_weight_max_device makes its m current;
+ * the host all-reduces m in place (max); gb_pf_weight_sums_device fills s1, s2, q_total w.r.t. that m. */
+int gb_pf_stats_device(gb_pf_t *pf, void **dev_stats, int *n_words);
+int gb_pf_weight_max_device(gb_pf_t *pf);
+int gb_pf_weight_sums_device(gb_pf_t *pf, int bits);
+/* Offspring of this shard's particles under global-prefix systematic resampling: the shard's particles
+ * (integer CDF mass q_local, preceded by q_offset of a global q_total) fill the global slot range
+ * [*slot_lo, *slot_hi).  Ancestors of the slots this shard owns itself go straight into its ancestor
+ * column, the others are kept for gb_pf_export_offspring. */
+int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits, uint64_t q_offset, uint64_t q_local,
+                               uint64_t q_total, uint32_t u0, int64_t *slot_lo, int64_t *slot_hi);
+/* Exchange block of `count` offspring rows (DEVICE memory, gb_pf_block_bytes(count) bytes, 16-byte aligned):
+ * [parents: count x int64, global 1-based][rows: S columns x count elements of the filter dtype]. */
+int64_t gb_pf_block_bytes(const gb_pf_t *pf, int64_t count);
 /* Fast path of the exchange (used when every shard receives at most gb_pf_ext_capacity rows): slots
  * [k_lo, k_hi) that stay on this shard just keep their ancestors (the gather is deferred and fused into
  * the next particle_filter_step!), rows received from other shards are parked in extension rows of the
@@ -120,16 +131,15 @@ int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits, uint64_t 
  * gb_pf_commit_resample_lazy then finishes maybe_resample! (particle_filter.jl:263-272). */
 int gb_pf_ext_capacity(const gb_pf_t *pf, int64_t *cap);
 int gb_pf_offspring_local(gb_pf_t *pf, int64_t k_lo, int64_t k_hi);
-int gb_pf_import_ext(gb_pf_t *pf, int64_t dst_lo, int64_t count, int64_t ext_offset, const void *dev_rows,
-                     const void *dev_parents);
+int gb_pf_import_ext(gb_pf_t *pf, int64_t dst_lo, int64_t count, int64_t ext_offset, const void *dev_block);
 int gb_pf_commit_resample_lazy(gb_pf_t *pf, double log_ml_increment);
-/* Gather rows for global slots [k_lo, k_hi) (inside the shard's offspring range) into DEVICE buffers:
- * dev_rows = S columns of (k_hi-k_lo) elements of the filter dtype, dev_parents = int64 global ids. */
-int gb_pf_export_offspring(gb_pf_t *pf, int64_t k_lo, int64_t k_hi, void *dev_rows, void *dev_parents);
-/* Install rows for local slots [dst_lo, dst_lo+count) of the NEW trace buffer from DEVICE buffers of
- * the same layout; gb_pf_commit_resample then swaps buffers, zeroes the log weights and adds
- * log_ml_increment to log_ml_est (particle_filter.jl:263-272). */
-int gb_pf_import_rows(gb_pf_t *pf, int64_t dst_lo, int64_t count, const void *dev_rows, const void *dev_parents);
+/* Staged exchange (arbitrarily skewed weights).  gb_pf_export_offspring gathers the rows of global slots
+ * [k_lo, k_hi) (inside the shard's offspring range, not straddling its own slot range) into a block;
+ * gb_pf_import_rows installs a block at local slots [dst_lo, dst_lo+count) of the NEW trace buffer;
+ * gb_pf_commit_resample then swaps buffers, zeroes the log weights and adds log_ml_increment to
+ * log_ml_est (particle_filter.jl:263-272). */
+int gb_pf_export_offspring(gb_pf_t *pf, int64_t k_lo, int64_t k_hi, void *dev_block);
+int gb_pf_import_rows(gb_pf_t *pf, int64_t dst_lo, int64_t count, const void *dev_block);
 int gb_pf_commit_resample(gb_pf_t *pf, double log_ml_increment);
 
 /* ---- importance_sampling (importance.jl:20-59) ---- */

@@ -37,24 +37,23 @@ def run_sharded_in_process(g, model, n, K, ys, seed, dtype="f64", fast=False):
             use_fast = fast and K > 1 and all(
                 sum(send[s_][d][1] - send[s_][d][0] for s_ in range(K) if s_ != d) <= ops[d].ext_capacity() for d in range(K))
             for r in range(K):
-                lo, hi = ops[r].systematic_offspring(m, bits, pref[r], qt, u0)
+                lo, hi = ops[r].systematic_offspring(m, bits, pref[r], trip[r][2], qt, u0)
                 assert (lo, hi) == ranges[r]
                 for d in range(K):
                     a, b = send[r][d]
                     if use_fast and d == r:
                         ops[r].offspring_local(a, b)
                     elif b > a:
-                        rows = torch.empty(S * (b - a), dtype=td, device="cuda")
-                        par = torch.empty(b - a, dtype=torch.int64, device="cuda")
-                        ops[r].export_offspring(a, b, rows, par)
-                        bufs[(r, d)] = (a, b, rows, par)
+                        blk = torch.empty(ops[r].block_bytes(b - a), dtype=torch.uint8, device="cuda")
+                        ops[r].export_offspring(a, b, blk)
+                        bufs[(r, d)] = (a, b, blk)
             ext_off = [0] * K
-            for (r, d), (a, b, rows, par) in sorted(bufs.items()):           # all-to-all-v
+            for (r, d), (a, b, blk) in sorted(bufs.items()):                 # all-to-all-v
                 if use_fast:
-                    ops[d].import_ext(a - offs[d], b - a, ext_off[d], rows, par)
+                    ops[d].import_ext(a - offs[d], b - a, ext_off[d], blk)
                     ext_off[d] += b - a
                 else:
-                    ops[d].import_rows(a - offs[d], b - a, rows, par)
+                    ops[d].import_rows(a - offs[d], b - a, blk)
             for o in ops:
                 (o.commit_lazy if use_fast else o.commit)(lse - math.log(n))
         for s in shards:

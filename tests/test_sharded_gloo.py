@@ -49,7 +49,11 @@ class OracleShard:
         self.q, self.m, self.bits = [int(v) for v in q], m, bits
         return float(e.sum()), float((e * e).sum()), int(tot)
 
-    def systematic_offspring(self, m, bits, q_offset, q_total, u0):
+    def block_bytes(self, count):
+        return (count * (8 + 8 * self.state_dim) + 15) // 16 * 16
+
+    def systematic_offspring(self, m, bits, q_offset, q_local, q_total, u0):
+        assert q_local == sum(self.q)
         n = self.spf.n_global
 
         def below(Cv):
@@ -67,17 +71,22 @@ class OracleShard:
         self.anc, self.off_lo = np.array(anc, dtype=np.int64), lo
         return lo, lo + len(anc)
 
-    def export_offspring(self, a, b, rows, parents):
+    def export_offspring(self, a, b, block):
+        # block = [parents int64 x c][rows float64 x S x c] (include/genb200.h "Exchange block")
         idx = self.anc[a - self.off_lo:b - self.off_lo]
         c = b - a
+        buf = block.numpy()
+        buf[:8 * c].view(np.int64)[:] = self.spf.offs[self.spf.rank] + idx + 1
+        rows = buf[8 * c:8 * c + 8 * c * self.state_dim].view(np.float64)
         for s in range(self.state_dim):
-            rows[s * c:(s + 1) * c] = torch.from_numpy(self.cols[s][idx])
-        parents[:] = torch.from_numpy(self.spf.offs[self.spf.rank] + idx + 1)
+            rows[s * c:(s + 1) * c] = self.cols[s][idx]
 
-    def import_rows(self, dst_lo, count, rows, parents):
+    def import_rows(self, dst_lo, count, block):
+        buf = block.numpy()
+        self.new_parents[dst_lo:dst_lo + count] = buf[:8 * count].view(np.int64)
+        rows = buf[8 * count:8 * count + 8 * count * self.state_dim].view(np.float64)
         for s in range(self.state_dim):
-            self.new_cols[s][dst_lo:dst_lo + count] = rows[s * count:(s + 1) * count].numpy()
-        self.new_parents[dst_lo:dst_lo + count] = parents.numpy()
+            self.new_cols[s][dst_lo:dst_lo + count] = rows[s * count:(s + 1) * count]
 
     def commit(self, incr):
         self.cols, self.new_cols = self.new_cols, self.cols
