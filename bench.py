@@ -354,9 +354,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="genb200", choices=["genb200", "reference"])
-    ap.add_argument("--particles", type=float, default=1e8, help="particles (total for strong scaling, per GPU for weak)")
+    ap.add_argument("--particles", type=float, default=1e8, help="particles per GPU (weak scaling) / in total (strong scaling)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
+                    help="weak (default): 1e8 particles PER GPU; strong: 1e8 particles in total, sharded")
     ap.add_argument("--cpu-particles", type=int, default=4_000_000)
     ap.add_argument("--ref-particles", type=int, default=4_000_000)
     ap.add_argument("--no-cpu", action="store_true")

@@ -1003,7 +1003,11 @@ extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits
   if (cnt > pf->off_cap) {
     cudaFree(pf->off_anc);
     pf->off_anc = nullptr;
-    long long cap = ((cnt + kTile - 1) / kTile) * kTile;
+    // grow with head-room: the offspring count fluctuates from resample to resample and every
+    // cudaFree/cudaMalloc is a device synchronisation
+    long long want = cnt + cnt / 4 + kTile;
+    if (want < pf->n_pad + pf->n_pad / 4) want = pf->n_pad + pf->n_pad / 4;
+    long long cap = ((want + kTile - 1) / kTile) * kTile;
     CK(cudaMalloc((void **)&pf->off_anc, (size_t)cap * 4));
     pf->off_cap = cap;
   }

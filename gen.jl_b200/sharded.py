@@ -100,7 +100,8 @@ class ShardOps:
         return lo.value, hi.value
 
     def block_bytes(self, count):
-        return int(L.lib().gb_pf_block_bytes(self.h, int(count)))
+        """== gb_pf_block_bytes: [parents int64 x count][rows S x count x esz], rounded up to 16 bytes."""
+        return (int(count) * (8 + self.state_dim * self.esz) + 15) // 16 * 16
 
     def export_offspring(self, k_lo, k_hi, block):
         L.check(L.lib().gb_pf_export_offspring(self.h, k_lo, k_hi, C.c_void_p(block.data_ptr())))

@@ -108,6 +108,9 @@ def test_sharded_class_world1(g, O):
     ys = F.bearings_series(6)
     n, seed = 30000, 5
     spf = sharded.ShardedParticleFilter(g.bearings_model(), n, seed=seed).initialize(ys[0])
+    from genb200 import _lib as L
+    for c in (0, 1, 7, 1000):
+        assert spf.ops.block_bytes(c) == L.lib().gb_pf_block_bytes(spf.local._h, c)
     st = g.initialize_particle_filter(g.bearings_model(), (0,), ys[0], n, seed=seed)
     for t in range(1, len(ys)):
         a = spf.maybe_resample_(ess_threshold=n + 1)
