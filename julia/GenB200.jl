@@ -1,0 +1,200 @@
+# GenB200.jl -- Julia glue: Gen.jl's particle-filter / importance-sampling generics over libgenb200.so.
+#
+# NOT RUN in this repository's CI: the build image has no Julia (SURVEY.md fact 3).  The Python ctypes
+# mirror (gen.jl_b200/api.py) drives exactly the same C ABI (include/genb200.h) and is what the tests
+# exercise; this file is the binding a Gen.jl maintainer would load:
+#
+#     using Gen, GenB200
+#     model = GenB200.bearings_model()                        # a DeviceModel <: GenerativeFunction
+#     state = initialize_particle_filter(model, (0,), choicemap((:z0, zs[1])), 10^8)
+#     for t in 1:T
+#         maybe_resample!(state, ess_threshold = N / 2)
+#         particle_filter_step!(state, (t,), (UnknownChange(),), choicemap((:chain => t => :z, zs[t+1])))
+#     end
+#     log_ml_estimate(state)
+#
+# Julia's multiple dispatch is the plugin mechanism: the methods below are added to Gen's OWN generic
+# functions (src/inference/particle_filter.jl:277-279, importance.jl:124) for the device types.
+module GenB200
+
+using Gen
+import Gen: initialize_particle_filter, particle_filter_step!, maybe_resample!, log_ml_estimate,
+            get_log_weights, get_traces, importance_sampling
+
+const libgenb200 = get(ENV, "GENB200_LIB", "libgenb200.so")
+
+const GB_MODEL_LGSSM, GB_MODEL_SV, GB_MODEL_BEARINGS, GB_MODEL_HMM, GB_MODEL_BLR = 1, 2, 3, 4, 5
+const GB_PROPOSAL_DEFAULT, GB_PROPOSAL_AFFINE_NORMAL, GB_PROPOSAL_CATEGORICAL_TABLE = 0, 1, 2
+const GB_RESAMPLE_MULTINOMIAL, GB_RESAMPLE_SYSTEMATIC, GB_RESAMPLE_RESIDUAL = 0, 1, 2
+const GB_F64, GB_F32 = 0, 1
+
+# every entry returns a status; the message replaces Julia's error(...) (particle_filter.jl:227-229)
+function check(rc::Cint)
+    rc == 0 && return nothing
+    error(unsafe_string(ccall((:gb_last_error, libgenb200), Cstring, ())))
+end
+
+# ---- DeviceModel: a generative function of the supported class ----
+mutable struct DeviceModel <: GenerativeFunction{Any,Trace}
+    handle::Ptr{Cvoid}
+    kind::Int
+    nobs::Int
+    state_dim::Int
+    function DeviceModel(kind::Int, params::Vector{Float64})
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:gb_model_create, libgenb200), Cint, (Cint, Ptr{Cdouble}, Cint, Ref{Ptr{Cvoid}}),
+                    kind, params, length(params), h))
+        m = new(h[], kind,
+                ccall((:gb_model_num_obs, libgenb200), Cint, (Ptr{Cvoid},), h[]),
+                ccall((:gb_model_state_dim, libgenb200), Cint, (Ptr{Cvoid},), h[]))
+        finalizer(x -> ccall((:gb_model_free, libgenb200), Cvoid, (Ptr{Cvoid},), x.handle), m)
+        m
+    end
+end
+
+lgssm_model(; m0=0.0, s0=1.0, a=0.9, q=0.5, r=1.0) = DeviceModel(GB_MODEL_LGSSM, [m0, s0, a, q, r])
+sv_model(; mu=-1.0, phi=0.95, sigma=0.25) = DeviceModel(GB_MODEL_SV, [mu, phi, sigma, sigma / sqrt(1 - phi^2)])
+bearings_model(; x0=(0.01, 0.01), y0=(0.95, 0.01), vx0=(0.002, 0.01), vy0=(-0.013, 0.01),
+               velocity_var=1e-6, measurement_noise=0.005) =
+    DeviceModel(GB_MODEL_BEARINGS, Float64[x0..., y0..., vx0..., vy0..., velocity_var, measurement_noise])
+# layout of test/inference/particle_filter.jl:52-78: transition[z, prev_z], emission[x, z] (column-major = Julia's)
+hmm_model(prior::Vector{Float64}, transition::Matrix{Float64}, emission::Matrix{Float64}) =
+    DeviceModel(GB_MODEL_HMM, vcat(Float64[length(prior), size(emission, 1)], prior, vec(transition), vec(emission)))
+blr_model(X::Matrix{Float64}, sigma::Float64) =
+    DeviceModel(GB_MODEL_BLR, vcat(Float64[size(X, 2), size(X, 1), sigma], vec(permutedims(X))))
+
+struct AffineNormalProposal end            # proposal_args = (c0, c1, std)
+struct CategoricalTableProposal end        # proposal_args = (table,)
+proposal_kind(::Nothing) = GB_PROPOSAL_DEFAULT
+proposal_kind(::AffineNormalProposal) = GB_PROPOSAL_AFFINE_NORMAL
+proposal_kind(::CategoricalTableProposal) = GB_PROPOSAL_CATEGORICAL_TABLE
+flatten_pargs(::Nothing, args) = Float64[]
+flatten_pargs(::AffineNormalProposal, args) = Float64[args...]
+flatten_pargs(::CategoricalTableProposal, args) = Float64[vec(args[1])...]
+
+# observations cross the boundary as a flat Float64 vector in the model's fixed slot order
+# (SURVEY.md section 8b): all leaf values of the choice map in address order
+flatten_obs(obs::ChoiceMap) = Float64[Float64(v) for (_, v) in sort(collect(get_values_deep(obs)), by=first)]
+function get_values_deep(cm::ChoiceMap, prefix=())
+    out = Pair{Any,Any}[]
+    for (k, v) in get_values_shallow(cm); push!(out, (prefix..., k) => v); end
+    for (k, sub) in get_submaps_shallow(cm); append!(out, get_values_deep(sub, (prefix..., k))); end
+    out
+end
+
+# ---- DeviceParticleFilterState: ParticleFilterState (particle_filter.jl:35-41) held as SoA columns in HBM ----
+mutable struct DeviceParticleFilterState
+    handle::Ptr{Cvoid}
+    model::DeviceModel
+    num_particles::Int
+    resampler::Int
+    last_t::Union{Int,Nothing}
+    function DeviceParticleFilterState(h, model, n, last_t)
+        s = new(h, model, n, GB_RESAMPLE_MULTINOMIAL, last_t)   # reference semantics by default (:261-262)
+        finalizer(x -> ccall((:gb_pf_free, libgenb200), Cvoid, (Ptr{Cvoid},), x.handle), s)
+        s
+    end
+end
+
+# lazily materialised fields (tests poke .log_weights / .parents / .log_ml_est: particle_filter.jl:176-197)
+function Base.getproperty(s::DeviceParticleFilterState, f::Symbol)
+    f === :log_weights && return get_log_weights(s)
+    f === :log_ml_est && (r = Ref{Cdouble}(); check(ccall((:gb_pf_get_log_ml_est, libgenb200), Cint, (Ptr{Cvoid}, Ref{Cdouble}), getfield(s, :handle), r)); return r[])
+    if f === :parents
+        out = Vector{Int64}(undef, getfield(s, :num_particles))
+        check(ccall((:gb_pf_get_parents, libgenb200), Cint, (Ptr{Cvoid}, Ptr{Int64}), getfield(s, :handle), out))
+        return out
+    end
+    f === :traces && return get_traces(s)
+    getfield(s, f)
+end
+
+function Base.copy(s::DeviceParticleFilterState)       # particle_filter.jl:43-51
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gb_pf_clone, libgenb200), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), s.handle, h))
+    c = DeviceParticleFilterState(h[], s.model, s.num_particles, s.last_t)
+    c.resampler = s.resampler
+    c
+end
+
+# ---- Gen's generics ----
+function initialize_particle_filter(model::DeviceModel, model_args::Tuple, observations::ChoiceMap,
+                                    proposal, proposal_args::Tuple, num_particles::Int;
+                                    dtype::Int=GB_F64, seed::Integer=rand(UInt64))
+    obs = flatten_obs(observations)
+    pa = flatten_pargs(proposal, proposal_args)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gb_pf_initialize, libgenb200), Cint,
+                (Ptr{Cvoid}, Int64, Cint, UInt64, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Cint, Ref{Ptr{Cvoid}}),
+                model.handle, num_particles, dtype, seed, obs, length(obs), proposal_kind(proposal), pa, length(pa), h))
+    last_t = (length(model_args) >= 1 && model_args[1] isa Integer) ? Int(model_args[1]) : nothing
+    DeviceParticleFilterState(h[], model, num_particles, last_t)
+end
+initialize_particle_filter(model::DeviceModel, model_args::Tuple, observations::ChoiceMap, num_particles::Int; kw...) =
+    initialize_particle_filter(model, model_args, observations, nothing, (), num_particles; kw...)
+
+function particle_filter_step!(state::DeviceParticleFilterState, new_args::Tuple, argdiffs::Tuple,
+                               observations::ChoiceMap, proposal=nothing, proposal_args::Tuple=())
+    # only extension by one time step is supported; anything else would produce a non-empty discard,
+    # which the reference rejects (particle_filter.jl:227-229)
+    if state.last_t !== nothing && length(new_args) >= 1 && new_args[1] != state.last_t + 1
+        error("Choices were updated or deleted inside particle filter step")
+    end
+    obs = flatten_obs(observations)
+    pa = flatten_pargs(proposal, proposal_args)
+    incr = Vector{Float64}(undef, state.num_particles)
+    check(ccall((:gb_pf_step, libgenb200), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}),
+                state.handle, obs, length(obs), proposal_kind(proposal), pa, length(pa), incr))
+    length(new_args) >= 1 && (state.last_t = Int(new_args[1]))
+    (incr,)
+end
+
+function maybe_resample!(state::DeviceParticleFilterState; ess_threshold::Real=state.num_particles / 2, verbose=false)
+    did = Ref{Cint}(0)
+    check(ccall((:gb_pf_maybe_resample, libgenb200), Cint, (Ptr{Cvoid}, Cdouble, Cint, Ref{Cint}),
+                state.handle, Float64(ess_threshold), state.resampler, did))
+    verbose && println("doing resample: $(did[] != 0)")
+    did[] != 0
+end
+
+function log_ml_estimate(state::DeviceParticleFilterState)
+    r = Ref{Cdouble}()
+    check(ccall((:gb_pf_log_ml_estimate, libgenb200), Cint, (Ptr{Cvoid}, Ref{Cdouble}), state.handle, r))
+    r[]
+end
+
+function get_log_weights(state::DeviceParticleFilterState)
+    out = Vector{Float64}(undef, getfield(state, :num_particles))
+    check(ccall((:gb_pf_get_log_weights, libgenb200), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), getfield(state, :handle), out))
+    out
+end
+
+# traces of the supported class are rows of the SoA store: a lazy column view
+struct DeviceTraces; state::DeviceParticleFilterState; end
+get_traces(state::DeviceParticleFilterState) = DeviceTraces(state)
+function column(t::DeviceTraces, field::Int)
+    out = Vector{Float64}(undef, t.state.num_particles)
+    check(ccall((:gb_pf_get_state, libgenb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}), t.state.handle, field, out))
+    out
+end
+
+function importance_sampling(model::DeviceModel, model_args::Tuple, observations::ChoiceMap,
+                             proposal, proposal_args::Tuple, num_samples::Int;
+                             verbose=false, dtype::Int=GB_F64, seed::Integer=rand(UInt64))
+    obs = flatten_obs(observations)
+    pa = flatten_pargs(proposal, proposal_args)
+    lnw = Vector{Float64}(undef, num_samples)
+    lml = Ref{Cdouble}()
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:gb_importance_sampling, libgenb200), Cint,
+                (Ptr{Cvoid}, Int64, Cint, UInt64, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Cint,
+                 Ptr{Cdouble}, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}, Ref{Cdouble}, Ref{Ptr{Cvoid}}),
+                model.handle, num_samples, dtype, seed, obs, length(obs), proposal_kind(proposal), pa, length(pa),
+                C_NULL, 0, C_NULL, 0, lnw, lml, h))
+    (DeviceTraces(DeviceParticleFilterState(h[], model, num_samples, nothing)), lnw, lml[])
+end
+importance_sampling(model::DeviceModel, model_args::Tuple, observations::ChoiceMap, num_samples::Int; kw...) =
+    importance_sampling(model, model_args, observations, nothing, (), num_samples; kw...)
+
+end # module
