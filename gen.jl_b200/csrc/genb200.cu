@@ -166,6 +166,7 @@ struct gb_pf {
   double log_ml_est = 0.0;
   int wstate = W_DIRTY;
   double2 *partials = nullptr;     // per-CTA partials (running max as double, or (s1, s2))
+  bool ws_clean = false;           // tile_q / super_q are all zero (ready to accumulate)
   bool tiles_valid = false;        // tile_q / super_q hold the quantised mass of the current weights w.r.t. h_stats->m
   unsigned int *ticket = nullptr;
   WeightStats *d_stats = nullptr, *h_stats = nullptr;
@@ -635,8 +636,11 @@ static int ensure_max(gb_pf *pf, const void *logw) {
 // the reference max is read from d_stats->m (from_device) or passed by value (sharded: global max)
 static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_device, bool sync_host = true) {
   const int bits = quant_bits(pf->n_global);
-  CK(cudaMemsetAsync(pf->super_q, 0, (size_t)(pf->nsuper + 1) * 8, pf->stream));
-  CK(cudaMemsetAsync(pf->tile_q, 0, (size_t)(pf->ntiles + 1) * 8, pf->stream));
+  if (!pf->ws_clean) {       // the systematic sweep leaves both accumulators zeroed; other paths do not
+    CK(cudaMemsetAsync(pf->super_q, 0, (size_t)(pf->nsuper + 1) * 8, pf->stream));
+    CK(cudaMemsetAsync(pf->tile_q, 0, (size_t)(pf->ntiles + 1) * 8, pf->stream));
+  }
+  pf->ws_clean = false;
   if (pf->dtype == GB_F64) {
     auto kern = wstats_kernel<double>;
     int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
@@ -914,8 +918,10 @@ static int launch_systematic(gb_pf *pf, const void *logw, double m, uint64_t q_o
   CK(cudaGetLastError());
   auto okern = overflow_sys_kernel<R>;
   LAUNCH(pf, GB_K_ANCESTORS, okern<<<pf->num_sms * 4, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->d_plan, ao, pf->oflow,
-                                                                                pf->oflow_count));
+                                                                                pf->oflow_count, (unsigned long long *)pf->tile_q, pf->ntiles));
   CK(cudaGetLastError());
+  pf->tiles_valid = false;   // superscan / overflow zeroed the accumulators for the next statistics pass
+  pf->ws_clean = true;
   return GB_OK;
 }
 

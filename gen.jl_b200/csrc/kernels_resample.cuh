@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(kBlock) convert_in_kernel(const double *__rest
 // ==========================================================================================
 struct OverflowEntry { long long tile, slot0, slot_lo, slot_hi; unsigned long long cbase; };
 
-__global__ void __launch_bounds__(1024) superscan_kernel(long long nsuper, const unsigned long long *__restrict__ super_q,
+__global__ void __launch_bounds__(1024) superscan_kernel(long long nsuper, unsigned long long *__restrict__ super_q,
                                                          unsigned long long *__restrict__ super_excl,
                                                          ResamplePlan *plan, uint64_t q_offset, uint64_t q_total_given,
                                                          long long n_global, uint32_t u0, unsigned int *overflow_count) {
@@ -568,6 +568,7 @@ __global__ void __launch_bounds__(1024) superscan_kernel(long long nsuper, const
   for (long long i = lo; i < hi; i++) {
     uint64_t v = super_q[i];
     super_excl[i] = run;
+    super_q[i] = 0;              // leave the accumulator clean for the next statistics pass (no memset launch)
     run += v;
   }
   if (threadIdx.x == 0) {
@@ -741,8 +742,11 @@ template <typename R>
 __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restrict__ logw, long long n, double m, int bits,
                                                               const ResamplePlan *__restrict__ plan, const AncOut ao,
                                                               const OverflowEntry *__restrict__ oflow,
-                                                              const unsigned int *__restrict__ oflow_count) {
+                                                              const unsigned int *__restrict__ oflow_count,
+                                                              unsigned long long *__restrict__ tile_q, long long ntiles) {
   __shared__ TileSmem sm;
+  // the sweep is done with the per-tile totals: leave the accumulator clean for the next statistics pass
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < ntiles; i += (long long)gridDim.x * kBlock) tile_q[i] = 0;
   const unsigned int ne = *oflow_count;
   if (ne == 0) return;
   const SweepParams sp = plan->sp;

@@ -239,13 +239,28 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
   publish_max(acc, a.partials, a.ticket, a.stats);
 }
 
-// max of an existing log-weight array (after gb_pf_set_log_weights, clone, raw-array entries)
+// max of an existing log-weight array (after gb_pf_set_log_weights, clone, raw-array entries): 128-bit
+// loads, four independent vectors in flight per thread (the array is padded to a multiple of 2048)
 template <typename R>
 __global__ void __launch_bounds__(kBlock) max_kernel(const R *__restrict__ logw, long long n, double *partials,
                                                      unsigned int *ticket, WeightStats *stats) {
+  constexpr int V = VecOf<R>::V, U = 4;
   double acc = -INFINITY;
-  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock)
-    acc = max_nan(acc, (double)__ldg(logw + i));
+  const long long nvec = (n + V - 1) / V;
+  const long long stride = (long long)gridDim.x * kBlock;
+  for (long long iv = (long long)blockIdx.x * kBlock + threadIdx.x; iv < nvec; iv += stride * U) {
+    R v[U][V];
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (iv + u * stride < nvec) vload_keep<R>(logw + (iv + u * stride) * V, v[u]);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (iv + u * stride < nvec) {
+#pragma unroll
+        for (int k = 0; k < V; k++)
+          if ((iv + u * stride) * V + k < n) acc = max_nan(acc, (double)v[u][k]);
+      }
+  }
   publish_max(acc, partials, ticket, stats);
 }
 
