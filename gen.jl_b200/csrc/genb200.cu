@@ -413,7 +413,7 @@ extern "C" int gb_pf_set_resample_noise(gb_pf_t *pf, int use_u0, uint32_t u0, co
 // ------------------------------------------------------------------------------------------
 template <typename R, int KIND, int PK, bool INIT>
 static int launch_step_t(gb_pf *pf, const StepArgs &a, bool predrawn, bool gather) {
-  constexpr int V = VecOf<R>::V;
+  constexpr int V = StepV<R>::V;
   const long long nvec = (pf->n + V - 1) / V;
 #define GO(PD, GA)                                                                         \
   {                                                                                        \

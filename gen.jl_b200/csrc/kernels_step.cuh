@@ -64,6 +64,22 @@ template <> GB_D void vstore_keep<float>(float *p, const float (&i)[4]) {
   *reinterpret_cast<float4 *>(p) = make_float4(i[0], i[1], i[2], i[3]);
 }
 
+// particles per thread of the step kernel (compile-time tuning knob; 128-bit accesses at the default)
+#ifndef GB_STEP_V64
+#define GB_STEP_V64 2
+#endif
+template <typename R> struct StepV { static constexpr int V = VecOf<R>::V; };
+template <> struct StepV<double> { static constexpr int V = GB_STEP_V64; };
+template <typename R, int V> GB_D void svload(const R *p, R (&o)[V]) {
+  if constexpr (V == VecOf<R>::V) vload<R>(p, o); else { for (int k = 0; k < V; k++) o[k] = __ldcs(p + k); }
+}
+template <typename R, int V> GB_D void svstore(R *p, const R (&o)[V]) {
+  if constexpr (V == VecOf<R>::V) vstore<R>(p, o); else { for (int k = 0; k < V; k++) __stcs(p + k, o[k]); }
+}
+template <typename R, int V> GB_D void svstore_keep(R *p, const R (&o)[V]) {
+  if constexpr (V == VecOf<R>::V) vstore_keep<R>(p, o); else { for (int k = 0; k < V; k++) p[k] = o[k]; }
+}
+
 struct StepArgs {
   const void *state_in;   // S columns of stride ld (traces); unused when INIT
   void *state_out;        // S columns of stride ld (new_traces)
@@ -131,7 +147,7 @@ GB_D void publish_max(double acc, double *partials, unsigned int *ticket, Weight
 template <typename R, int KIND, int PK, bool INIT, bool PREDRAWN, bool GATHER>
 __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepArgs a) {
   typedef Transition<R, KIND, PK, INIT> Tr;
-  constexpr int V = VecOf<R>::V, S = Tr::S, NN = Tr::NN, NU = Tr::NU;
+  constexpr int V = StepV<R>::V, S = Tr::S, NN = Tr::NN, NU = Tr::NU;
   __shared__ double s_tab[kMathTabDoubles];
   const MathTables T = stage_math_tables(s_tab);
   __syncthreads();
@@ -150,7 +166,8 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
   // and the ancestor rows of the next iteration are prefetched into L2 while this one computes.
   int src_cur[V], src_nxt[V];
   auto load_anc = [&](long long ivx, int (&dst)[V]) {
-    if constexpr (V == 2) { int2 t = __ldcs(reinterpret_cast<const int2 *>(a.anc + ivx * V)); dst[0] = t.x; dst[1] = t.y; }
+    if constexpr (V == 1) { dst[0] = __ldcs(a.anc + ivx); }
+    else if constexpr (V == 2) { int2 t = __ldcs(reinterpret_cast<const int2 *>(a.anc + ivx * V)); dst[0] = t.x; dst[1] = t.y; }
     else { int4 t = __ldcs(reinterpret_cast<const int4 *>(a.anc + ivx * V)); dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w; }
   };
   if (!INIT && GATHER) {
@@ -182,8 +199,8 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
         }
       } else {
 #pragma unroll
-        for (int s = 0; s < S; s++) vload<R>(sin + (long long)s * a.ld + i0, prev[s]);
-        vload<R>(logw + i0, lw_old);
+        for (int s = 0; s < S; s++) svload<R, V>(sin + (long long)s * a.ld + i0, prev[s]);
+        svload<R, V>(logw + i0, lw_old);
         if (iv + stride < nvec) {
 #pragma unroll
           for (int s = 0; s < S; s++) prefetch_l2(sin + (long long)s * a.ld + i0 + stride * V);
@@ -232,9 +249,9 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
       if (i0 + v < a.n) acc = max_nan(acc, (double)lw_new[v]);
     }
 #pragma unroll
-    for (int s = 0; s < S; s++) vstore<R>(sout + (long long)s * a.ld + i0, next[s]);
-    vstore_keep<R>(logw + i0, lw_new);
-    if (!INIT) vstore<R>(incr + i0, w);
+    for (int s = 0; s < S; s++) svstore<R, V>(sout + (long long)s * a.ld + i0, next[s]);
+    svstore_keep<R, V>(logw + i0, lw_new);
+    if (!INIT) svstore<R, V>(incr + i0, w);
   }
   publish_max(acc, a.partials, a.ticket, a.stats);
 }
