@@ -354,6 +354,19 @@ def maybe_resample_(state, ess_threshold=None, verbose=False, resampler=None):
     return bool(did.value)
 
 
+def particle_filter_run_(state, observations_seq, ess_threshold=None):
+    """T x { maybe_resample!(state, ess_threshold) [systematic]; particle_filter_step!(state, (t,), ..., obs_t) } in one
+    call, without a host round trip per step (include/genb200.h gb_pf_run).  Returns the number of resamples."""
+    obs = np.ascontiguousarray([_flatten_obs(o) for o in observations_seq], dtype=np.float64)
+    T, nobs = obs.shape if obs.ndim == 2 else (len(obs), 1)
+    thr = state.num_particles / 2 if ess_threshold is None else float(ess_threshold)
+    nres = C.c_int()
+    L.check(L.lib().gb_pf_run(state._h, int(T), obs.ctypes.data_as(L.dp), int(nobs), thr, C.byref(nres)))
+    if state._last_t is not None:
+        state._last_t += int(T)
+    return nres.value
+
+
 def log_ml_estimate(state):
     """particle_filter.jl:91-94."""
     v = C.c_double()

@@ -166,6 +166,7 @@ struct gb_pf {
   double log_ml_est = 0.0;
   int wstate = W_DIRTY;
   double2 *partials = nullptr;     // per-CTA partials (running max as double, or (s1, s2))
+  RunCtl *d_ctl = nullptr, *h_ctl = nullptr;   // fused multi-step run (gb_pf_run)
   bool ws_clean = false;           // tile_q / super_q are all zero (ready to accumulate)
   bool tiles_valid = false;        // tile_q / super_q hold the quantised mass of the current weights w.r.t. h_stats->m
   unsigned int *ticket = nullptr;
@@ -249,7 +250,7 @@ static void pf_release(gb_pf *pf) {
   cudaFree(pf->state[0]); cudaFree(pf->state[1]); cudaFree(pf->logw); cudaFree(pf->incr); cudaFree(pf->anc);
   cudaFree(pf->parents64); cudaFree(pf->ext_parents); cudaFree(pf->partials); cudaFree(pf->ticket); cudaFree(pf->d_stats);
   cudaFreeHost(pf->h_stats); cudaFree(pf->d_normals); cudaFree(pf->d_uniforms); cudaFree(pf->d_u64);
-  cudaFree(pf->super_q); cudaFree(pf->super_excl); cudaFree(pf->oflow); cudaFree(pf->oflow_count);
+  cudaFree(pf->d_ctl); cudaFreeHost(pf->h_ctl); cudaFree(pf->super_q); cudaFree(pf->super_excl); cudaFree(pf->oflow); cudaFree(pf->oflow_count);
   cudaFree(pf->tile_q); cudaFree(pf->tile_c); cudaFree(pf->tile_r); cudaFree(pf->tile_slot); cudaFree(pf->d_plan);
   cudaFreeHost(pf->h_plan); cudaFree(pf->cdf); cudaFree(pf->off_anc); cudaFree(pf->d_tab); cudaFree(pf->d_ptab);
   for (auto &t : pf->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -412,7 +413,7 @@ extern "C" int gb_pf_set_resample_noise(gb_pf_t *pf, int use_u0, uint32_t u0, co
 // step / generate dispatch
 // ------------------------------------------------------------------------------------------
 template <typename R, int KIND, int PK, bool INIT>
-static int launch_step_t(gb_pf *pf, const StepArgs &a, bool predrawn, bool gather) {
+static int launch_step_t(gb_pf *pf, const StepArgs &a, bool predrawn, int gather /* 0, 1, 2 = device flag */) {
   constexpr int V = StepV<R>::V;
   const long long nvec = (pf->n + V - 1) / V;
 #define GO(PD, GA)                                                                         \
@@ -422,17 +423,17 @@ static int launch_step_t(gb_pf *pf, const StepArgs &a, bool predrawn, bool gathe
     LAUNCH(pf, GB_K_STEP, kern<<<grid, kBlock, 0, pf->stream>>>(a));                       \
   }
   if (INIT) {
-    if (predrawn) GO(true, false) else GO(false, false)
+    if (predrawn) GO(true, 0) else GO(false, 0)
   } else {
-    if (predrawn) { if (gather) GO(true, true) else GO(true, false) }
-    else { if (gather) GO(false, true) else GO(false, false) }
+    if (predrawn) { if (gather) GO(true, 1) else GO(true, 0) }
+    else { if (gather == 2) GO(false, 2) else if (gather) GO(false, 1) else GO(false, 0) }
   }
 #undef GO
   CK(cudaGetLastError());
   return GB_OK;
 }
 template <typename R, bool INIT>
-static int launch_step_k(gb_pf *pf, const StepArgs &a, int pk, bool predrawn, bool gather) {
+static int launch_step_k(gb_pf *pf, const StepArgs &a, int pk, bool predrawn, int gather) {
   switch (pf->model.kind) {
     case MODEL_LGSSM:
       if (pk == PROPOSAL_AFFINE_NORMAL) return launch_step_t<R, MODEL_LGSSM, PROPOSAL_AFFINE_NORMAL, INIT>(pf, a, predrawn, gather);
@@ -524,8 +525,8 @@ extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, 
     a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
     a.seed = pf->seed; a.step = 0;
     a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
-    rc = pf->dtype == GB_F64 ? launch_step_k<double, true>(pf, a, pk, predrawn, false)
-                             : launch_step_k<float, true>(pf, a, pk, predrawn, false);
+    rc = pf->dtype == GB_F64 ? launch_step_k<double, true>(pf, a, pk, predrawn, 0)
+                             : launch_step_k<float, true>(pf, a, pk, predrawn, 0);
   }
   if (rc) return rc;
   pf->cur ^= 1;
@@ -567,8 +568,8 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
   a.seed = pf->seed; a.step = (unsigned)(pf->step + 1);
   a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
   const bool gather = pf->pending_gather;
-  rc = pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, pk, predrawn, gather)
-                           : launch_step_k<float, false>(pf, a, pk, predrawn, gather);
+  rc = pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, pk, predrawn, gather ? 1 : 0)
+                           : launch_step_k<float, false>(pf, a, pk, predrawn, gather ? 1 : 0);
   if (rc) return rc;
   pf->step += 1;
   pf->cur ^= 1;                       // particle_filter.jl:203-205, :234-237 (swap traces/new_traces)
@@ -634,7 +635,7 @@ static int ensure_max(gb_pf *pf, const void *logw) {
 }
 // one pass over the log weights: (s1, s2) w.r.t. the reference max + quantised tile / super-tile totals;
 // the reference max is read from d_stats->m (from_device) or passed by value (sharded: global max)
-static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_device, bool sync_host = true) {
+static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_device, bool sync_host = true, RunCtl *ctl = nullptr) {
   const int bits = quant_bits(pf->n_global);
   if (!pf->ws_clean) {       // the systematic sweep leaves both accumulators zeroed; other paths do not
     CK(cudaMemsetAsync(pf->super_q, 0, (size_t)(pf->nsuper + 1) * 8, pf->stream));
@@ -645,12 +646,12 @@ static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_devic
     auto kern = wstats_kernel<double>;
     int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
     LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)logw, pf->n, m_arg, from_device ? 1 : 0, bits, (unsigned long long *)pf->tile_q,
-                                                                     pf->super_q, pf->partials, pf->ticket, pf->d_stats));
+                                                                     pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl));
   } else {
     auto kern = wstats_kernel<float>;
     int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
     LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)logw, pf->n, m_arg, from_device ? 1 : 0, bits, (unsigned long long *)pf->tile_q,
-                                                                     pf->super_q, pf->partials, pf->ticket, pf->d_stats));
+                                                                     pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl));
   }
   CK(cudaGetLastError());
   if (sync_host) {
@@ -907,18 +908,19 @@ static int fetch_plan(gb_pf *pf) {
 // shard's offspring slots; single shard: q_offset = 0, q_total = 0 (= the local total), anc_base = 0.
 template <typename R>
 static int launch_systematic(gb_pf *pf, const void *logw, double m, uint64_t q_offset, uint64_t q_total, uint32_t u0,
-                             const AncOut &ao) {
+                             const AncOut &ao, const RunCtl *ctl = nullptr) {
   const int bits = quant_bits(pf->n_global);
   LAUNCH(pf, GB_K_TILESCAN, superscan_kernel<<<1, 1024, 0, pf->stream>>>(pf->nsuper, pf->super_q, pf->super_excl, pf->d_plan, q_offset,
                                                                           q_total, pf->n_global, u0, pf->oflow_count));
   CK(cudaGetLastError());
   auto kern = ancestors_sys_kernel<R>;
   LAUNCH(pf, GB_K_ANCESTORS, kern<<<(unsigned)pf->ntiles, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->tile_q, pf->super_excl,
-                                                                                    pf->d_plan, ao, pf->oflow, pf->oflow_count));
+                                                                                    pf->d_plan, ao, pf->oflow, pf->oflow_count, ctl, pf->d_stats));
   CK(cudaGetLastError());
   auto okern = overflow_sys_kernel<R>;
   LAUNCH(pf, GB_K_ANCESTORS, okern<<<pf->num_sms * 4, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->d_plan, ao, pf->oflow,
-                                                                                pf->oflow_count, (unsigned long long *)pf->tile_q, pf->ntiles));
+                                                                                pf->oflow_count, (unsigned long long *)pf->tile_q, pf->ntiles, ctl,
+                                                                                pf->d_stats));
   CK(cudaGetLastError());
   pf->tiles_valid = false;   // superscan / overflow zeroed the accumulators for the next statistics pass
   pf->ws_clean = true;
@@ -988,6 +990,61 @@ extern "C" int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind,
   pf->u64_set = false;
   if (!pf->lazy && (rc = run_gather(pf))) return rc;    // :264-272
   *did = 1;
+  return GB_OK;
+}
+
+// ---- fused multi-step entry: T x { maybe_resample!(systematic); particle_filter_step! } with the ESS test, the
+//      log-ML update and the gathered/direct choice made on the device (no host round trip per step) ----
+extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double ess_threshold, int *n_resampled) {
+  REQ(pf && obs && T >= 0, "gb_pf_run: bad argument");
+  REQ(pf->n == pf->n_global, "gb_pf_run: single shard only");
+  REQ(pf->model.kind != MODEL_BLR, "the BLR model has no sequential structure (importance sampling only)");
+  REQ(nobs == pf->model.nobs, "gb_pf_run: wrong number of observations per step");
+  REQ(pf->nn_set == 0 && pf->nu_set == 0 && !pf->use_u0, "gb_pf_run: validation noise is not supported by the fused entry");
+  int rc = materialize_pending(pf);
+  if (rc) return rc;
+  if ((rc = gb_pf_weight_max_device(pf))) return rc;     // d_stats->m current for the first statistics pass
+  if (!pf->d_ctl) {
+    CK(cudaMalloc((void **)&pf->d_ctl, sizeof(RunCtl)));
+    CK(cudaMallocHost((void **)&pf->h_ctl, sizeof(RunCtl)));
+  }
+  pf->h_ctl->do_resample = 0; pf->h_ctl->n_resampled = 0;
+  pf->h_ctl->log_ml_est = pf->log_ml_est;
+  pf->h_ctl->ess_threshold = ess_threshold;
+  pf->h_ctl->log_n = log((double)pf->n_global);
+  CK(cudaMemcpyAsync(pf->d_ctl, pf->h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));                // h_ctl is reused for the read-back below
+  const AncOut ao{pf->anc, 0, pf->n_global, nullptr, 0};
+  for (int t = 0; t < T; t++) {
+    // maybe_resample!: statistics + decision on the device, then the (conditional) systematic sweep
+    if ((rc = run_wstats(pf, pf->logw, 0.0, true, false, pf->d_ctl))) return rc;
+    const uint32_t u0 = philox_block(pf->seed, 0, (uint32_t)pf->step, PK_RESAMPLE, 0).x;
+    rc = pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, 0.0, 0, 0, u0, ao, pf->d_ctl)
+                             : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, u0, ao, pf->d_ctl);
+    if (rc) return rc;
+    // particle_filter_step!
+    StepArgs a;
+    memset(&a, 0, sizeof(a));
+    if ((rc = fill_model_params(pf, a.mp, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false))) return rc;
+    a.state_in = pf->state[pf->cur];
+    a.state_out = pf->state[pf->cur ^ 1];
+    a.logw = pf->logw; a.incr = pf->incr;
+    a.anc = pf->anc; a.ctl = pf->d_ctl;
+    a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
+    a.seed = pf->seed; a.step = (unsigned)(pf->step + 1);
+    a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
+    rc = pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, PROPOSAL_DEFAULT, false, 2)
+                             : launch_step_k<float, false>(pf, a, PROPOSAL_DEFAULT, false, 2);
+    if (rc) return rc;
+    pf->step += 1;
+    pf->cur ^= 1;
+  }
+  CK(cudaMemcpyAsync(pf->h_ctl, pf->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));
+  pf->log_ml_est = pf->h_ctl->log_ml_est;
+  if (pf->h_ctl->n_resampled > 0) { pf->anc_valid = true; pf->parents64_valid = false; pf->ext_used = false; }
+  if (T > 0) { pf->wstate = W_MAX; pf->tiles_valid = false; pf->pending_gather = false; }
+  if (n_resampled) *n_resampled = pf->h_ctl->n_resampled;
   return GB_OK;
 }
 

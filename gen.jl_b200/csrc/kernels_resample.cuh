@@ -724,8 +724,13 @@ __global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const R *__restri
                                                                const unsigned long long *__restrict__ super_excl,
                                                                const ResamplePlan *__restrict__ plan, const AncOut ao,
                                                                OverflowEntry *__restrict__ oflow,
-                                                               unsigned int *__restrict__ oflow_count) {
+                                                               unsigned int *__restrict__ oflow_count,
+                                                               const RunCtl *__restrict__ ctl, const WeightStats *__restrict__ dstats) {
   __shared__ TileSmem sm;
+  if (ctl) {                       // fused multi-step run: decision and reference max live on the device
+    if (!ctl->do_resample) return;
+    m = dstats->m;
+  }
   const SweepParams sp = plan->sp;
   const long long tile = blockIdx.x;
   long long slot0, slot_end;
@@ -743,12 +748,14 @@ __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restric
                                                               const ResamplePlan *__restrict__ plan, const AncOut ao,
                                                               const OverflowEntry *__restrict__ oflow,
                                                               const unsigned int *__restrict__ oflow_count,
-                                                              unsigned long long *__restrict__ tile_q, long long ntiles) {
+                                                              unsigned long long *__restrict__ tile_q, long long ntiles,
+                                                              const RunCtl *__restrict__ ctl, const WeightStats *__restrict__ dstats) {
   __shared__ TileSmem sm;
+  if (ctl) m = dstats->m;
   // the sweep is done with the per-tile totals: leave the accumulator clean for the next statistics pass
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < ntiles; i += (long long)gridDim.x * kBlock) tile_q[i] = 0;
   const unsigned int ne = *oflow_count;
-  if (ne == 0) return;
+  if (ne == 0 || (ctl && !ctl->do_resample)) return;
   const SweepParams sp = plan->sp;
   long long unit0 = 0;
   for (unsigned int e = 0; e < ne; e++) {

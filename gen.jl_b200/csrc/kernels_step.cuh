@@ -25,6 +25,17 @@ struct WeightStats {
   unsigned long long q_total;   // sum of the quantised weights (wstats)
 };
 
+// Device-side control block of the fused multi-step entry (gb_pf_run): the ESS test of maybe_resample!
+// (particle_filter.jl:256), the running log-ML (:263) and the gathered/direct choice of the next step live
+// on the device, so T steps run without a host round trip.
+struct RunCtl {
+  int do_resample;        // decision of the current iteration
+  int n_resampled;        // resamples so far in this run
+  double log_ml_est;      // ParticleFilterState.log_ml_est
+  double ess_threshold;
+  double log_n;           // log(num_particles)
+};
+
 template <typename R> struct VecOf;
 template <> struct VecOf<double> { typedef double2 type; static constexpr int V = 2; };
 template <> struct VecOf<float> { typedef float4 type; static constexpr int V = 4; };
@@ -86,6 +97,7 @@ struct StepArgs {
   void *logw;             // ld elements (in/out)
   void *incr;             // ld elements (log incremental weights), unused when INIT
   const int *anc;         // GATHER: local source index of every slot (deferred resample gather)
+  const RunCtl *ctl;      // GATHER == 2: gathered iff ctl->do_resample (decided on the device)
   const double *normals;  // PREDRAWN: [NN][ld] ; else NULL
   const double *uniforms; // PREDRAWN: [NU][ld]
   long long n, ld, pid_offset;
@@ -144,7 +156,7 @@ GB_D void publish_max(double acc, double *partials, unsigned int *ticket, Weight
 #ifndef GB_STEP_MINB
 #define GB_STEP_MINB 3
 #endif
-template <typename R, int KIND, int PK, bool INIT, bool PREDRAWN, bool GATHER>
+template <typename R, int KIND, int PK, bool INIT, bool PREDRAWN, int GATHER /* 0 no, 1 yes, 2 ctl->do_resample */>
 __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepArgs a) {
   typedef Transition<R, KIND, PK, INIT> Tr;
   constexpr int V = StepV<R>::V, S = Tr::S, NN = Tr::NN, NU = Tr::NU;
@@ -170,7 +182,8 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
     else if constexpr (V == 2) { int2 t = __ldcs(reinterpret_cast<const int2 *>(a.anc + ivx * V)); dst[0] = t.x; dst[1] = t.y; }
     else { int4 t = __ldcs(reinterpret_cast<const int4 *>(a.anc + ivx * V)); dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w; }
   };
-  if (!INIT && GATHER) {
+  const bool gather = GATHER == 2 ? (a.ctl->do_resample != 0) : (GATHER == 1);
+  if (!INIT && gather) {
     if (iv < nvec) load_anc(iv, src_cur);
     if (iv + stride < nvec) load_anc(iv + stride, src_nxt);
   }
@@ -179,7 +192,7 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
     R prev[S > 0 ? S : 1][V];
     R lw_old[V];
     if (!INIT) {
-      if (GATHER) {
+      if (gather) {
         // deferred maybe_resample! gather (particle_filter.jl:264-267): slot k continues the trace of
         // ancestor anc[k]; its log weight was reset to exactly 0.0
 #pragma unroll
@@ -344,7 +357,7 @@ template <typename R>
 __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ logw, long long n, double m_arg, int m_from_device,
                                                         int bits, unsigned long long *__restrict__ tile_q,
                                                         unsigned long long *__restrict__ super_q, double2 *partials,
-                                                        unsigned int *ticket, WeightStats *stats) {
+                                                        unsigned int *ticket, WeightStats *stats, RunCtl *ctl) {
   constexpr int V = VecOf<R>::V;
   constexpr int kSeg = 256, kPerLane = kSeg / 32, kLoads = kPerLane / V;
   __shared__ uint64_t s_u64[kBlock / 32];
@@ -443,6 +456,14 @@ __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ lo
     // particle_filter.jl:3-6: exp(-logsumexp(2 lnw)) == s1^2 / s2 ; all -Inf => NaN there too
     stats->ess = (t1 * t1) / t2;
     stats->q_total = qtot;
+    if (ctl) {   // maybe_resample! decision + log-ML update on the device (particle_filter.jl:256, :263)
+      const int flag = stats->ess < ctl->ess_threshold ? 1 : 0;
+      ctl->do_resample = flag;
+      if (flag) {
+        ctl->log_ml_est += stats->lse - ctl->log_n;
+        ctl->n_resampled += 1;
+      }
+    }
     *ticket = 0;
   }
 }

@@ -80,6 +80,11 @@ int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int proposal_kind, cons
 /* maybe_resample! (particle_filter.jl:249-275).  Single shard only (n_local == n_global).
  * Resampling randomness: Philox(seed, step) unless gb_pf_set_resample_noise was called. */
 int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind, int *did_resample);
+/* Throughput entry: T iterations of { maybe_resample!(ess_threshold, systematic); particle_filter_step!(obs[t]) }
+ * (default proposal) with the ESS test (particle_filter.jl:256), the log_ml_est update (:263) and the
+ * gathered/direct choice of the step made ON THE DEVICE, i.e. without the host round trip the Bool return of
+ * maybe_resample! forces per step.  Bit-identical to calling the two entries T times.  obs: T * nobs doubles. */
+int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double ess_threshold, int *n_resampled);
 /* validation mode for the resampler: u0 for systematic/residual, n u64 for multinomial (NULL clears) */
 int gb_pf_set_resample_noise(gb_pf_t *pf, int use_u0, uint32_t u0, const uint64_t *u64s);
 int gb_pf_log_ml_estimate(gb_pf_t *pf, double *out);                 /* particle_filter.jl:91-94 */

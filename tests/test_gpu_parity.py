@@ -478,3 +478,32 @@ def test_determinism(g):
         return st.get_state(0), st.log_weights, st.parents
     a, b = run(), run()
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("name", ["lgssm", "sv", "bearings", "hmm"])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_fused_multi_step_run_equals_api_loop(g, O, name, dtype):
+    """gb_pf_run (device-side ESS test / log-ML / gather choice, no host round trip per step) is bit-identical
+    to calling maybe_resample! + particle_filter_step! T times."""
+    model, _, _, ys, _, _ = model_zoo(g, O)[name]
+    n, seed = 70001, 12
+    for thr in (n / 2, n + 1, 0.0):            # ESS-triggered, always, never
+        a = g.initialize_particle_filter(model, (0,), ys[0], n, dtype=dtype, seed=seed)
+        b = g.initialize_particle_filter(model, (0,), ys[0], n, dtype=dtype, seed=seed)
+        nres = 0
+        for t in range(1, len(ys)):
+            nres += g.maybe_resample_(a, ess_threshold=thr, resampler="systematic")
+            g.particle_filter_step_(a, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+        k = 5
+        got = g.particle_filter_run_(b, ys[1:1 + k], ess_threshold=thr)          # two fused calls back to back
+        got += g.particle_filter_run_(b, ys[1 + k:], ess_threshold=thr)
+        assert got == nres
+        for f in range(model.state_dim):
+            assert np.array_equal(a.get_state(f), b.get_state(f))
+        assert np.array_equal(a.log_weights, b.log_weights)
+        assert np.array_equal(a.parents, b.parents)
+        assert a.log_ml_est == b.log_ml_est
+        assert g.log_ml_estimate(a) == g.log_ml_estimate(b)
+        # and the API keeps working after a fused run
+        assert g.maybe_resample_(a, ess_threshold=n + 1, resampler="systematic") == g.maybe_resample_(b, ess_threshold=n + 1, resampler="systematic")
+        assert np.array_equal(a.get_state(0), b.get_state(0))

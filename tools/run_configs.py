@@ -60,6 +60,16 @@ for dtype, E in (("f64", 8), ("f32", 4)):
     bstep = 5 * 1 * E * 0 + (4 * 1 + 5) * E + 8
     rows.append(("2: SV N=1e6 T=1000 %s, systematic every step" % dtype, "%.3g" % (1e6 * 1000 / dt), "%.1f us/step" % (1e6 * dt / 1000),
                  "log-ML %.6f; %.0f B/particle-step -> %.2f of measured HBM peak (latency regime)" % (lml, bstep, bstep * 1e6 / (dt / 1000) / 1e9 / PEAK)))
+for dtype, E in (("f64", 8), ("f32", 4)):
+    def fused():
+        st = g.initialize_particle_filter(model, (0,), ys[0], 10 ** 6, dtype=dtype, seed=3)
+        g.particle_filter_run_(st, ys[1:], ess_threshold=10 ** 6 + 1)
+        return g.log_ml_estimate(st)
+    fused()
+    dt, lml = timed(fused)
+    bstep = (4 * 1 + 5) * E + 8
+    rows.append(("2: SV N=1e6 T=1000 %s, fused gb_pf_run (no host round trip per step)" % dtype, "%.3g" % (1e6 * 1000 / dt),
+                 "%.1f us/step" % (1e6 * dt / 1000), "log-ML %.6f (== API loop: %s); %.2f of measured HBM peak" % (lml, lml == res[dtype], bstep * 1e6 / (dt / 1000) / 1e9 / PEAK)))
 rows.append(("2: fp32 vs fp64 log-ML", "", "", "relative difference %.2e (different noise streams: statistical)" % abs((res["f32"] - res["f64"]) / res["f64"])))
 
 # ---- cfg 4: BLR importance sampling D=64, 1e7 samples ----
