@@ -386,6 +386,26 @@ def get_traces(state):
     return state.traces
 
 
+def sample_unweighted_traces(state, num_samples, draw=0):
+    """sample_unweighted_traces(state, num_samples) (particle_filter.jl:101-109): traces drawn iid from the weighted
+    collection.  Returns (indices [1-based], rows [num_samples x state_dim])."""
+    n = int(num_samples)
+    idx = np.empty(n, dtype=np.int64)
+    rows = np.empty((state.state_dim, n), dtype=np.float64)
+    L.check(L.lib().gb_pf_sample_unweighted(state._h, n, int(draw), idx.ctypes.data_as(L.i64p), rows.ctypes.data_as(L.dp)))
+    return idx, rows.T.copy()
+
+
+def importance_resampling(model, model_args, observations, *rest, verbose=False, dtype="f64", seed=0):
+    """(trace, lml_est) = importance_resampling(model, model_args, observations, [proposal, proposal_args,] num_samples)
+    (importance.jl:77-122).  The reference streams the N proposals and keeps one by a running Bernoulli swap, which is
+    a single draw from Categorical(normalised weights); here the N samples are generated in one launch and one index is
+    drawn on the device."""
+    traces, lnw, lml = importance_sampling(model, model_args, observations, *rest, dtype=dtype, seed=seed)
+    idx, rows = sample_unweighted_traces(traces._state, 1, draw=0xFFFF)
+    return rows[0], lml
+
+
 def importance_sampling(model, model_args, observations, *rest, verbose=False, dtype="f64", seed=0,
                         normals=None, uniforms=None, return_traces=True):
     """(traces, log_norm_weights, lml_est) = importance_sampling(model, model_args, observations,
@@ -446,7 +466,9 @@ def effective_sample_size_from_logw(arr, dtype="f64"):
 
 
 _DISTS = {"normal": L.DIST_NORMAL, "gamma": L.DIST_GAMMA, "bernoulli": L.DIST_BERNOULLI,
-          "categorical": L.DIST_CATEGORICAL, "mvnormal": L.DIST_MVNORMAL}
+          "categorical": L.DIST_CATEGORICAL, "mvnormal": L.DIST_MVNORMAL, "uniform": 6, "exponential": 7, "laplace": 8,
+          "cauchy": 9, "inv_gamma": 10, "beta": 11, "poisson": 12, "geometric": 13, "binom": 14, "neg_binom": 15,
+          "uniform_discrete": 16}
 
 
 def logpdf(dist, x, a, b=None, dtype="f64"):

@@ -105,6 +105,50 @@ template <typename R> GB_D R random_gamma_philox(R shape, R scale, uint64_t seed
   return (R)(g * (double)scale);
 }
 
+// ---- the remaining scalar built-ins (modeling_library/distributions/*.jl), fp64 ----
+GB_D double logpdf_uniform(double x, double lo, double hi) {            // uniform_continuous.jl:12-14
+  return (x >= lo && x <= hi) ? -log(hi - lo) : -INFINITY;
+}
+GB_D double logpdf_exponential(double x, double rate) {                 // exponential.jl:10-13 (Exponential(1/rate))
+  return x >= 0.0 ? log(rate) - rate * x : -INFINITY;
+}
+GB_D double logpdf_laplace(double x, double loc, double scale) {        // laplace.jl:10-13
+  const double diff = fabs(x - loc);
+  return -diff / scale - log(2.0 * scale);
+}
+GB_D double logpdf_cauchy(double x, double x0, double gamma) {          // cauchy.jl:10-12 (Distributions.Cauchy)
+  const double z = (x - x0) / gamma;
+  return -log(M_PI) - log(gamma) - log1p(z * z);
+}
+GB_D double logpdf_inv_gamma(double x, double shape, double scale) {    // inv_gamma.jl:12-18
+  if (x > 0.0) return shape * log(scale) - (shape + 1.0) * log(x) - lgamma(shape) - (scale / x);
+  return -INFINITY;
+}
+GB_D double logpdf_beta(double x, double a, double b) {                 // beta.jl:13-24 incl. the endpoint special cases
+  const double eps = 2.220446049250313e-16, lbeta = lgamma(a) + lgamma(b) - lgamma(a + b);
+  if (x < 0.0 || x > 1.0) return -INFINITY;
+  if (x == 0.0 && a <= 1.0) return (a - 1.0) * log(eps) - a + 1.0 + (b - 1.0) * log1p(-eps) - lbeta;
+  if (x == 1.0 && b <= 1.0) return (a - 1.0) * log1p(-eps) - b + 1.0 + (b - 1.0) * log(eps) - lbeta;
+  return (a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lbeta;
+}
+GB_D double logpdf_poisson(double xi, double lambda) {                  // poisson.jl:10-12
+  return xi < 0.0 ? -INFINITY : xi * log(lambda) - lambda - lgamma(xi + 1.0);
+}
+GB_D double logpdf_geometric(double xi, double p) {                     // geometric.jl:10-12 (failures before 1st success)
+  return xi < 0.0 ? -INFINITY : log(p) + xi * log1p(-p);
+}
+GB_D double logpdf_binom(double xi, double n, double p) {               // binom.jl:10-12
+  if (xi < 0.0 || xi > n) return -INFINITY;
+  return lgamma(n + 1.0) - lgamma(xi + 1.0) - lgamma(n - xi + 1.0) + xi * log(p) + (n - xi) * log1p(-p);
+}
+GB_D double logpdf_neg_binom(double xi, double r, double p) {           // neg_binom.jl:12-14 (failures before r successes)
+  if (xi < 0.0) return -INFINITY;
+  return lgamma(xi + r) - lgamma(xi + 1.0) - lgamma(r) + r * log(p) + xi * log1p(-p);
+}
+GB_D double logpdf_uniform_discrete(double xi, double lo, double hi) {  // uniform_discrete.jl:10-13
+  return (xi >= lo && xi <= hi) ? -log(hi - lo + 1.0) : -INFINITY;
+}
+
 // mvnormal.jl:12-16: the covariance is shared by all particles, so it is factored ONCE (host, in
 // fp64) instead of once per call as the reference does; the kernel consumes L (row-major lower
 // Cholesky factor, k*k doubles) and logdet:  -(k log 2pi + logdet + |L^-1 (x-mu)|^2) / 2

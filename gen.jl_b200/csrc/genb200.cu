@@ -956,7 +956,7 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
     if ((rc = launch_ancestors<R, SWEEP_CDF>(pf, logw, m, bits, 0, 0, anc, 0))) return rc;
     int grid = grid_for(pf, multinomial_kernel, pf->n, kBlock);
     LAUNCH(pf, GB_K_ANCESTORS, multinomial_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->cdf, pf->tile_q, pf->ntiles, pf->n, pf->d_plan,
-                                                                                   d_u64, seed, step, pf->n, anc));
+                                                                                   d_u64, seed, step, pf->n, anc, (unsigned)PK_MULTI));
     CK(cudaGetLastError());
     return GB_OK;
   }
@@ -990,6 +990,50 @@ extern "C" int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind,
   pf->u64_set = false;
   if (!pf->lazy && (rc = run_gather(pf))) return rc;    // :264-272
   *did = 1;
+  return GB_OK;
+}
+
+// sample_unweighted_traces (particle_filter.jl:101-109): n_samples iid indices from Categorical(normalised weights)
+// (integer CDF + Philox, stream PK_SAMPLE keyed by (seed, draw)), and the corresponding trace rows
+extern "C" int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t draw, int64_t *idx_out, double *rows_out) {
+  REQ(pf && n_samples >= 1 && idx_out, "gb_pf_sample_unweighted: bad argument");
+  REQ(pf->n == pf->n_global, "gb_pf_sample_unweighted: single shard only");
+  int rc = materialize_pending(pf);
+  if (rc) return rc;
+  if ((rc = ensure_stats(pf))) return rc;
+  const double m = pf->h_stats->m;
+  if (!(m > -INFINITY)) return fail(GB_ESTATE, "gb_pf_sample_unweighted: all log weights are -Inf or NaN");
+  if (!pf->tiles_valid && (rc = run_wstats(pf, pf->logw, m, false))) return rc;
+  if (!pf->cdf) CK(cudaMalloc((void **)&pf->cdf, (size_t)pf->ld * 8));
+  const int bits = quant_bits(pf->n_global);
+  pf->tiles_valid = false;   // tile_q becomes its exclusive prefix
+  if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, 0, 1))) return rc;
+  rc = pf->dtype == GB_F64 ? launch_ancestors<double, SWEEP_CDF>(pf, pf->logw, m, bits, 0, 0, nullptr, 0)
+                           : launch_ancestors<float, SWEEP_CDF>(pf, pf->logw, m, bits, 0, 0, nullptr, 0);
+  if (rc) return rc;
+  int *d_idx = nullptr;
+  long long *d_idx1 = nullptr;
+  double *d_rows = nullptr;
+  cudaError_t e = cudaMalloc((void **)&d_idx, (size_t)n_samples * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d_idx1, (size_t)n_samples * 8);
+  if (e == cudaSuccess && rows_out) e = cudaMalloc((void **)&d_rows, (size_t)n_samples * pf->S * 8);
+  if (e == cudaSuccess) {
+    int grid = grid_for(pf, multinomial_kernel, n_samples, kBlock);
+    LAUNCH(pf, GB_K_MISC, multinomial_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->cdf, pf->tile_q, pf->ntiles, pf->n, pf->d_plan, nullptr,
+                                                                              pf->seed, (unsigned)draw, n_samples, d_idx, (unsigned)PK_SAMPLE));
+    if (pf->dtype == GB_F64)
+      LAUNCH(pf, GB_K_MISC, sample_rows_kernel<double><<<grid, kBlock, 0, pf->stream>>>((const double *)pf->state[pf->cur], pf->ld, rows_out ? pf->S : 0,
+                                                                                        d_idx, n_samples, d_rows, d_idx1, pf->pid_offset));
+    else
+      LAUNCH(pf, GB_K_MISC, sample_rows_kernel<float><<<grid, kBlock, 0, pf->stream>>>((const float *)pf->state[pf->cur], pf->ld, rows_out ? pf->S : 0,
+                                                                                       d_idx, n_samples, d_rows, d_idx1, pf->pid_offset));
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(idx_out, d_idx1, (size_t)n_samples * 8, cudaMemcpyDeviceToHost, pf->stream);
+  if (e == cudaSuccess && rows_out) e = cudaMemcpyAsync(rows_out, d_rows, (size_t)n_samples * pf->S * 8, cudaMemcpyDeviceToHost, pf->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
+  cudaFree(d_idx); cudaFree(d_idx1); cudaFree(d_rows);
+  if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_sample_unweighted: ") + cudaGetErrorString(e));
   return GB_OK;
 }
 
@@ -1476,6 +1520,17 @@ __global__ void __launch_bounds__(kBlock) dist_logpdf_kernel(int dist, long long
       case GB_DIST_GAMMA: r = logpdf_gamma<R>((R)x[i], (R)a[i * as], (R)b[i * bs]); break;
       case GB_DIST_BERNOULLI: r = logpdf_bernoulli<R>(x[i] != 0.0, (R)a[i * as]); break;
       case GB_DIST_CATEGORICAL: r = logpdf_categorical<R>((long long)x[i], a, len); break;
+      case GB_DIST_UNIFORM: r = (R)logpdf_uniform(x[i], a[i * as], b[i * bs]); break;
+      case GB_DIST_EXPONENTIAL: r = (R)logpdf_exponential(x[i], a[i * as]); break;
+      case GB_DIST_LAPLACE: r = (R)logpdf_laplace(x[i], a[i * as], b[i * bs]); break;
+      case GB_DIST_CAUCHY: r = (R)logpdf_cauchy(x[i], a[i * as], b[i * bs]); break;
+      case GB_DIST_INV_GAMMA: r = (R)logpdf_inv_gamma(x[i], a[i * as], b[i * bs]); break;
+      case GB_DIST_BETA: r = (R)logpdf_beta(x[i], a[i * as], b[i * bs]); break;
+      case GB_DIST_POISSON: r = (R)logpdf_poisson(x[i], a[i * as]); break;
+      case GB_DIST_GEOMETRIC: r = (R)logpdf_geometric(x[i], a[i * as]); break;
+      case GB_DIST_BINOM: r = (R)logpdf_binom(x[i], a[i * as], b[i * bs]); break;
+      case GB_DIST_NEG_BINOM: r = (R)logpdf_neg_binom(x[i], a[i * as], b[i * bs]); break;
+      case GB_DIST_UNIFORM_DISCRETE: r = (R)logpdf_uniform_discrete(x[i], a[i * as], b[i * bs]); break;
       default: {
         R xv[kBlrMax];
         for (int k = 0; k < len; k++) xv[k] = (R)x[i * len + k];
@@ -1512,6 +1567,28 @@ __global__ void __launch_bounds__(kBlock) dist_random_kernel(int dist, long long
         R u0, u1;
         philox_uniform_pair(seed, pid, step, 0u, u0, u1);
         out[i] = (double)random_categorical<R>(a, len, u0);
+        break;
+      }
+      case GB_DIST_UNIFORM: case GB_DIST_EXPONENTIAL: case GB_DIST_LAPLACE: case GB_DIST_CAUCHY: case GB_DIST_GEOMETRIC:
+      case GB_DIST_UNIFORM_DISCRETE: {   // inverse-CDF samplers on one 52-bit uniform in (0,1)
+        double u0, u1;
+        philox_uniform_pair(seed, pid, step, 0u, u0, u1);
+        const double p0 = a[i * as], p1 = b[i * bs];
+        double v;
+        if (dist == GB_DIST_UNIFORM) v = p0 + (p1 - p0) * u0;
+        else if (dist == GB_DIST_EXPONENTIAL) v = -log1p(-u0) / p0;
+        else if (dist == GB_DIST_LAPLACE) v = u0 < 0.5 ? p0 + p1 * log(2.0 * u0) : p0 - p1 * log(2.0 * (1.0 - u0));
+        else if (dist == GB_DIST_CAUCHY) v = p0 + p1 * (sinpi(u0 - 0.5) / cospi(u0 - 0.5));
+        else if (dist == GB_DIST_GEOMETRIC) v = floor(log1p(-u0) / log1p(-p0));
+        else v = p0 + floor((p1 - p0 + 1.0) * u0);
+        out[i] = v;
+        break;
+      }
+      case GB_DIST_INV_GAMMA: out[i] = b[i * bs] / random_gamma_philox<double>(a[i * as], 1.0, seed, pid, step); break;
+      case GB_DIST_BETA: {
+        const double g1 = random_gamma_philox<double>(a[i * as], 1.0, seed, pid, step);
+        const double g2 = random_gamma_philox<double>(b[i * bs], 1.0, seed ^ 0x9E3779B97F4A7C15ull, pid, step);
+        out[i] = g1 / (g1 + g2);
         break;
       }
       default: {   // mvnormal.jl:30-33: mu + L * randn(k)
@@ -1556,7 +1633,9 @@ static bool host_cholesky(const double *cov, int k, std::vector<double> &L, doub
 static int dist_common(int dist, int dtype, int64_t n, const double *x, const double *a, int as, const double *b, int bs, int len,
                        bool random, uint64_t seed, uint32_t step, double *out) {
   REQ(out && n >= 1, "bad argument");
-  REQ(dist >= GB_DIST_NORMAL && dist <= GB_DIST_MVNORMAL, "unknown distribution");
+  REQ(dist >= GB_DIST_NORMAL && dist <= GB_DIST_UNIFORM_DISCRETE, "unknown distribution");
+  if (random) REQ(dist != GB_DIST_POISSON && dist != GB_DIST_BINOM && dist != GB_DIST_NEG_BINOM,
+                  "random() of poisson / binom / neg_binom is not implemented on the device yet");
   int rc = require_gpu();
   if (rc) return rc;
   const bool vec = dist == GB_DIST_MVNORMAL;

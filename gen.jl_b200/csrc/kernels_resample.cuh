@@ -402,13 +402,14 @@ __global__ void __launch_bounds__(kBlock) ancestors_kernel(const R *__restrict__
 __global__ void __launch_bounds__(kBlock) multinomial_kernel(const uint64_t *__restrict__ cdf, const uint64_t *__restrict__ tile_q,
                                                              long long ntiles, long long n, const ResamplePlan *__restrict__ plan,
                                                              const uint64_t *__restrict__ u64s, unsigned long long seed,
-                                                             unsigned int step, long long nslots, int *__restrict__ anc) {
+                                                             unsigned int step, long long nslots, int *__restrict__ anc,
+                                                             unsigned int stream_kind) {
   const uint64_t qn = plan->sp.q_total;
   for (long long k = (long long)blockIdx.x * kBlock + threadIdx.x; k < nslots; k += (long long)gridDim.x * kBlock) {
     uint64_t u;
     if (u64s) u = u64s[k];
     else {
-      U4 w = philox_block(seed, (uint64_t)k, step, PK_MULTI, 0);
+      U4 w = philox_block(seed, (uint64_t)k, step, stream_kind, 0);
       u = ((uint64_t)w.x << 32) | w.y;
     }
     const uint64_t tau = mulhi64(u, qn);
@@ -478,6 +479,18 @@ __global__ void __launch_bounds__(kBlock) import_kernel(R *__restrict__ sout, lo
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < count; i += (long long)gridDim.x * kBlock) {
     for (int s = 0; s < S; s++) sout[(long long)s * ld + dst_lo + i] = rows[(long long)s * count + i];
     parents[dst_lo + i] = parents_in[i];
+  }
+}
+
+// rows of the sampled particles: out[s][i] = state[s][idx[i]] as fp64; idx1[i] = global 1-based index
+template <typename R>
+__global__ void __launch_bounds__(kBlock) sample_rows_kernel(const R *__restrict__ sin, long long ld, int S, const int *__restrict__ idx,
+                                                             long long count, double *__restrict__ rows, long long *__restrict__ idx1,
+                                                             long long pid_offset) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < count; i += (long long)gridDim.x * kBlock) {
+    const int src = idx[i];
+    for (int s = 0; s < S; s++) rows[(long long)s * count + i] = (double)sin[(long long)s * ld + src];
+    idx1[i] = pid_offset + src + 1;
   }
 }
 

@@ -41,7 +41,12 @@ enum { GB_PROPOSAL_DEFAULT = 0, GB_PROPOSAL_AFFINE_NORMAL = 1, GB_PROPOSAL_CATEG
 enum { GB_RESAMPLE_MULTINOMIAL = 0, GB_RESAMPLE_SYSTEMATIC = 1, GB_RESAMPLE_RESIDUAL = 2 };
 enum { GB_F64 = 0, GB_F32 = 1 };
 /* distributions for the batched logpdf/random entries (modeling_library/distributions/*.jl) */
-enum { GB_DIST_NORMAL = 1, GB_DIST_GAMMA = 2, GB_DIST_BERNOULLI = 3, GB_DIST_CATEGORICAL = 4, GB_DIST_MVNORMAL = 5 };
+enum { GB_DIST_NORMAL = 1, GB_DIST_GAMMA = 2, GB_DIST_BERNOULLI = 3, GB_DIST_CATEGORICAL = 4, GB_DIST_MVNORMAL = 5,
+       /* the other scalar built-ins (batched entries only): (a, b) = */
+       GB_DIST_UNIFORM = 6 /* low, high */, GB_DIST_EXPONENTIAL = 7 /* rate */, GB_DIST_LAPLACE = 8 /* loc, scale */,
+       GB_DIST_CAUCHY = 9 /* x0, gamma */, GB_DIST_INV_GAMMA = 10 /* shape, scale */, GB_DIST_BETA = 11 /* alpha, beta */,
+       GB_DIST_POISSON = 12 /* lambda */, GB_DIST_GEOMETRIC = 13 /* p */, GB_DIST_BINOM = 14 /* n, p */,
+       GB_DIST_NEG_BINOM = 15 /* r, p */, GB_DIST_UNIFORM_DISCRETE = 16 /* low, high */ };
 
 typedef struct gb_model gb_model_t;
 typedef struct gb_pf gb_pf_t;
@@ -80,6 +85,10 @@ int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int proposal_kind, cons
 /* maybe_resample! (particle_filter.jl:249-275).  Single shard only (n_local == n_global).
  * Resampling randomness: Philox(seed, step) unless gb_pf_set_resample_noise was called. */
 int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind, int *did_resample);
+/* sample_unweighted_traces (particle_filter.jl:101-109): n_samples iid draws from Categorical(normalised weights).
+ * idx_out: n_samples 1-based particle indices; rows_out (may be NULL): S columns x n_samples values of the sampled
+ * traces.  `draw` distinguishes successive calls on the same state (Philox stream (seed, draw)). */
+int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t draw, int64_t *idx_out, double *rows_out);
 /* Throughput entry: T iterations of { maybe_resample!(ess_threshold, systematic); particle_filter_step!(obs[t]) }
  * (default proposal) with the ESS test (particle_filter.jl:256), the log_ml_est update (:263) and the
  * gathered/direct choice of the step made ON THE DEVICE, i.e. without the host round trip the Bool return of
