@@ -45,6 +45,9 @@ SIGNATURES = {
     "gb_pf_initialize": (i, [vp, i64, i, u64, dp, i, i, dp, i, vpp]),
     "gb_pf_step": (i, [vp, dp, i, i, dp, i, dp]),
     "gb_pf_maybe_resample": (i, [vp, d, i, ip]),
+    "gb_pf_enable_history": (i, [vp, i]),
+    "gb_pf_history_length": (i, [vp, ip]),
+    "gb_pf_get_trajectory": (i, [vp, i, dp]),
     "gb_pf_sample_unweighted": (i, [vp, i64, u64, i64p, dp]),
     "gb_pf_run": (i, [vp, i, dp, i, d, ip]),
     "gb_pf_set_resample_noise": (i, [vp, i, u32, u64p]),

@@ -230,6 +230,18 @@ class DeviceParticleFilterState:
             up = u64s.ctypes.data_as(L.u64p)
         L.check(L.lib().gb_pf_set_resample_noise(self._h, 0 if u0 is None else 1, 0 if u0 is None else int(u0), up))
 
+    def enable_history(self, on=True):
+        """Keep per-step snapshots + ancestors so that full trajectories can be reconstructed (call before generate)."""
+        L.check(L.lib().gb_pf_enable_history(self._h, int(bool(on))))
+
+    def trajectory(self, field):
+        """[T+1, N] array: value of trace column `field` at every time step along each current particle's lineage."""
+        steps = C.c_int()
+        L.check(L.lib().gb_pf_history_length(self._h, C.byref(steps)))
+        out = np.empty((steps.value, self.num_particles), dtype=np.float64)
+        L.check(L.lib().gb_pf_get_trajectory(self._h, int(field), out.ctypes.data_as(L.dp)))
+        return out
+
     def set_lazy_gather(self, lazy):
         L.check(L.lib().gb_pf_set_lazy_gather(self._h, int(bool(lazy))))
 

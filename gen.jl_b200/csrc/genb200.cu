@@ -166,6 +166,12 @@ struct gb_pf {
   double log_ml_est = 0.0;
   int wstate = W_DIRTY;
   double2 *partials = nullptr;     // per-CTA partials (running max as double, or (s1, s2))
+  // optional history: per step a snapshot of the trace columns and, when a resample preceded the
+  // step, its ancestors -- enough to reconstruct every particle's full trajectory (Gen's traces hold all choices)
+  bool history = false;
+  bool hist_resampled = false;      // a resample happened since the last recorded step
+  std::vector<void *> hist_state;   // [t] -> S columns x n_pad of the filter dtype (t = 0: after generate)
+  std::vector<int *> hist_anc;      // [t] -> ancestors applied BEFORE step t (nullptr: no resample)
   RunCtl *d_ctl = nullptr, *h_ctl = nullptr;   // fused multi-step run (gb_pf_run)
   bool ws_clean = false;           // tile_q / super_q are all zero (ready to accumulate)
   bool tiles_valid = false;        // tile_q / super_q hold the quantised mass of the current weights w.r.t. h_stats->m
@@ -253,6 +259,8 @@ static void pf_release(gb_pf *pf) {
   cudaFree(pf->d_ctl); cudaFreeHost(pf->h_ctl); cudaFree(pf->super_q); cudaFree(pf->super_excl); cudaFree(pf->oflow); cudaFree(pf->oflow_count);
   cudaFree(pf->tile_q); cudaFree(pf->tile_c); cudaFree(pf->tile_r); cudaFree(pf->tile_slot); cudaFree(pf->d_plan);
   cudaFreeHost(pf->h_plan); cudaFree(pf->cdf); cudaFree(pf->off_anc); cudaFree(pf->d_tab); cudaFree(pf->d_ptab);
+  for (auto p : pf->hist_state) cudaFree(p);
+  for (auto p : pf->hist_anc) cudaFree(p);
   for (auto &t : pf->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto e : pf->pool) cudaEventDestroy(e);
   delete pf;
@@ -501,6 +509,62 @@ static int check_noise(gb_pf *pf, bool init, bool *predrawn) {
 
 static int blr_generate(gb_pf *pf, const double *obs, int nobs, bool predrawn);
 
+// snapshot of the current trace columns (+ the ancestors that were applied on the way into this step)
+static int history_record(gb_pf *pf, bool resampled) {
+  void *snap = nullptr;
+  const size_t bytes = (size_t)pf->S * pf->n_pad * pf->esz;
+  CK(cudaMalloc(&snap, bytes));
+  CK(cudaMemcpy2DAsync(snap, (size_t)pf->n_pad * pf->esz, pf->state[pf->cur], (size_t)pf->ld * pf->esz, (size_t)pf->n_pad * pf->esz, pf->S,
+                       cudaMemcpyDeviceToDevice, pf->stream));
+  int *anc = nullptr;
+  if (resampled) {
+    CK(cudaMalloc((void **)&anc, (size_t)pf->n_pad * 4));
+    CK(cudaMemcpyAsync(anc, pf->anc, (size_t)pf->n_pad * 4, cudaMemcpyDeviceToDevice, pf->stream));
+  }
+  pf->hist_state.push_back(snap);
+  pf->hist_anc.push_back(anc);
+  return GB_OK;
+}
+extern "C" int gb_pf_enable_history(gb_pf_t *pf, int on) {
+  REQ(pf, "null handle");
+  REQ(pf->n == pf->n_global, "history is kept for single-shard filters only");
+  pf->history = on != 0;
+  return GB_OK;
+}
+extern "C" int gb_pf_history_length(const gb_pf_t *pf, int *steps) {
+  REQ(pf && steps, "null argument");
+  *steps = (int)pf->hist_state.size();
+  return GB_OK;
+}
+// out[t][i] = value of trace column `field` at time t on the lineage of the CURRENT particle i (t = 0..len-1)
+extern "C" int gb_pf_get_trajectory(gb_pf_t *pf, int field, double *out) {
+  REQ(pf && out, "null argument");
+  REQ(field >= 0 && field < pf->S, "gb_pf_get_trajectory: field out of range");
+  const int len = (int)pf->hist_state.size();
+  REQ(pf->history && len > 0, "gb_pf_get_trajectory: history is off (gb_pf_enable_history before generate)");
+  REQ(len == pf->step + 1, "gb_pf_get_trajectory: history does not cover every step (gb_pf_run does not record history)");
+  int *idx = nullptr;
+  double *d_out = nullptr;
+  CK(cudaMalloc((void **)&idx, (size_t)pf->n_pad * 4));
+  cudaError_t e = cudaMalloc((void **)&d_out, (size_t)pf->n * 8);
+  if (e != cudaSuccess) { cudaFree(idx); return fail(GB_ECUDA, cudaGetErrorString(e)); }
+  int grid = grid_for(pf, iota_int_kernel, pf->n, kBlock);
+  // a pending (deferred) resample has not been applied to the last snapshot: start from its ancestors
+  if (pf->pending_gather) e = cudaMemcpyAsync(idx, pf->anc, (size_t)pf->n * 4, cudaMemcpyDeviceToDevice, pf->stream);
+  else iota_int_kernel<<<grid, kBlock, 0, pf->stream>>>(idx, pf->n);
+  for (int t = len - 1; t >= 0 && e == cudaSuccess; t--) {
+    const char *snap = (const char *)pf->hist_state[t] + (size_t)field * pf->n_pad * pf->esz;
+    if (pf->dtype == GB_F64) backtrace_kernel<double><<<grid, kBlock, 0, pf->stream>>>((const double *)snap, pf->hist_anc[t], idx, pf->n, d_out);
+    else backtrace_kernel<float><<<grid, kBlock, 0, pf->stream>>>((const float *)snap, pf->hist_anc[t], idx, pf->n, d_out);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out + (size_t)t * pf->n, d_out, (size_t)pf->n * 8, cudaMemcpyDeviceToHost, pf->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
+  }
+  cudaFree(idx); cudaFree(d_out);
+  if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_get_trajectory: ") + cudaGetErrorString(e));
+  return GB_OK;
+}
+
 extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, const double *pargs, int npargs) {
   REQ(pf, "null handle");
   REQ(nobs == pf->model.nobs, "gb_pf_generate: wrong number of observations");
@@ -533,6 +597,12 @@ extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, 
   pf->wstate = W_MAX;
   pf->tiles_valid = false;
   pf->nn_set = pf->nu_set = 0;
+  if (pf->history) {
+    for (auto p : pf->hist_state) cudaFree(p);
+    for (auto p : pf->hist_anc) cudaFree(p);
+    pf->hist_state.clear(); pf->hist_anc.clear();
+    if ((rc = history_record(pf, false))) return rc;
+  }
   return GB_OK;
 }
 
@@ -577,6 +647,8 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
   pf->wstate = W_MAX;
   pf->tiles_valid = false;
   pf->nn_set = pf->nu_set = 0;
+  if (pf->history && (rc = history_record(pf, pf->hist_resampled))) return rc;
+  pf->hist_resampled = false;
   if (incr_out) {
     if (pf->dtype == GB_F64) {
       CK(cudaMemcpyAsync(incr_out, pf->incr, (size_t)pf->n * 8, cudaMemcpyDeviceToHost, pf->stream));
@@ -981,6 +1053,7 @@ extern "C" int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind,
                            : compute_ancestors<float>(pf, pf->logw, m, kind, u0, d_u64, pf->seed, (uint32_t)pf->step, pf->anc);
   if (rc) return rc;
   pf->log_ml_est += lse - log((double)pf->n_global);   // :263
+  pf->hist_resampled = true;
   pf->anc_valid = true;
   pf->parents64_valid = false;
   pf->pending_gather = true;

@@ -494,6 +494,21 @@ __global__ void __launch_bounds__(kBlock) sample_rows_kernel(const R *__restrict
   }
 }
 
+// trajectory reconstruction (get_traces with full history): out[i] = snapshot[field][idx[i]]; when a resample
+// preceded this step, the lineage then moves to the ancestor: idx[i] = anc[idx[i]]
+template <typename R>
+__global__ void __launch_bounds__(kBlock) backtrace_kernel(const R *__restrict__ snap, const int *__restrict__ anc, int *__restrict__ idx,
+                                                           long long n, double *__restrict__ out) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+    const int j = idx[i];
+    out[i] = (double)snap[j];
+    if (anc) idx[i] = anc[j];
+  }
+}
+__global__ void __launch_bounds__(kBlock) iota_int_kernel(int *__restrict__ p, long long n) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) p[i] = (int)i;
+}
+
 template <typename R>
 __global__ void __launch_bounds__(kBlock) fill_kernel(R *__restrict__ p, long long n, R v) {
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) p[i] = v;

@@ -85,6 +85,14 @@ int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int proposal_kind, cons
 /* maybe_resample! (particle_filter.jl:249-275).  Single shard only (n_local == n_global).
  * Resampling randomness: Philox(seed, step) unless gb_pf_set_resample_noise was called. */
 int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind, int *did_resample);
+/* Optional trace history (off by default: the throughput configurations keep only the current state).  With history on
+ * (enable BEFORE gb_pf_generate) every generate/step keeps a snapshot of the trace columns and the ancestors of the
+ * resample that preceded it, so that gb_pf_get_trajectory can return, for every CURRENT particle i and every time
+ * t = 0..step, the value the particle's own lineage had: out[t * n + i] -- Gen's traces hold all choices at all times
+ * (get_traces, particle_filter.jl:70-73; `trace[:chain => t => :z]`). */
+int gb_pf_enable_history(gb_pf_t *pf, int on);
+int gb_pf_history_length(const gb_pf_t *pf, int *steps);
+int gb_pf_get_trajectory(gb_pf_t *pf, int field, double *out);
 /* sample_unweighted_traces (particle_filter.jl:101-109): n_samples iid draws from Categorical(normalised weights).
  * idx_out: n_samples 1-based particle indices; rows_out (may be NULL): S columns x n_samples values of the sampled
  * traces.  `draw` distinguishes successive calls on the same state (Philox stream (seed, draw)). */

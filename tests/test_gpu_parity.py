@@ -586,3 +586,41 @@ def test_sample_unweighted_traces_and_importance_resampling(g, O):
 
 def stats_norm_logpdf(x, mu, sd):
     return -0.5 * ((x - mu) / sd) ** 2 - math.log(sd) - 0.5 * math.log(2 * math.pi)
+
+
+@pytest.mark.parametrize("lazy", [True, False])
+def test_full_trajectories_from_history(g, O, lazy):
+    """get_traces with full Gen semantics (every choice at every time, along the particle's own lineage):
+    SURVEY.md 8f row 1.  Reconstructed trajectories equal the oracle's, followed through its parents."""
+    model, okind_m, params, ys, _, _ = model_zoo(g, O)["bearings"]
+    n, seed = 4001, 3
+    st = g.create_particle_filter(model, n, seed=seed)
+    st.set_lazy_gather(lazy)
+    st.enable_history(True)
+    g.generate_(st, ys[0])
+    ref = O.OraclePF.init(okind_m, params, n, [ys[0]], normals=g.philox_normals(seed, 0, 0, n, 4))
+    snaps = [[ref.state(f) for f in range(4)]]
+    lineage = [np.arange(n)]                      # lineage[t][i]: index at time t of current particle i's ancestor
+    for t in range(1, len(ys)):
+        thr = n + 1 if t % 2 else n / 2
+        did = g.maybe_resample_(st, ess_threshold=thr, resampler="systematic")
+        did_ref = ref.maybe_resample(ess_threshold=thr, kind=O.RESAMPLE_SYSTEMATIC, u0=g.philox_resample_u0(seed, t - 1))
+        assert did == did_ref
+        if did_ref:
+            par = ref.parents - 1
+            lineage = [l[par] for l in lineage]
+        g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t])
+        ref.step([ys[t]], normals=g.philox_normals(seed, t, 0, n, 2))
+        snaps.append([ref.state(f) for f in range(4)])
+        lineage.append(np.arange(n))
+    for f in (0, 3):
+        traj = st.trajectory(f)
+        assert traj.shape == (len(ys), n)
+        for t in range(len(ys)):
+            assert np.array_equal(traj[t], snaps[t][f][lineage[t]]), (f, t)
+    # a resample that has not been followed by a step yet is reflected too
+    g.maybe_resample_(st, ess_threshold=n + 1, resampler="systematic")
+    ref.maybe_resample(ess_threshold=n + 1, kind=O.RESAMPLE_SYSTEMATIC, u0=g.philox_resample_u0(seed, len(ys) - 1))
+    par = ref.parents - 1
+    traj = st.trajectory(2)
+    assert np.array_equal(traj[-1], snaps[-1][2][par]) and np.array_equal(traj[0], snaps[0][2][lineage[0][par]])
