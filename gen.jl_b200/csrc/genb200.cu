@@ -549,8 +549,9 @@ extern "C" int gb_pf_get_trajectory(gb_pf_t *pf, int field, double *out) {
   cudaError_t e = cudaMalloc((void **)&d_out, (size_t)pf->n * 8);
   if (e != cudaSuccess) { cudaFree(idx); return fail(GB_ECUDA, cudaGetErrorString(e)); }
   int grid = grid_for(pf, iota_int_kernel, pf->n, kBlock);
-  // a pending (deferred) resample has not been applied to the last snapshot: start from its ancestors
-  if (pf->pending_gather) e = cudaMemcpyAsync(idx, pf->anc, (size_t)pf->n * 4, cudaMemcpyDeviceToDevice, pf->stream);
+  // a resample since the last recorded step (deferred or already gathered) is not in the last snapshot:
+  // start from its ancestors
+  if (pf->hist_resampled) e = cudaMemcpyAsync(idx, pf->anc, (size_t)pf->n * 4, cudaMemcpyDeviceToDevice, pf->stream);
   else iota_int_kernel<<<grid, kBlock, 0, pf->stream>>>(idx, pf->n);
   for (int t = len - 1; t >= 0 && e == cudaSuccess; t--) {
     const char *snap = (const char *)pf->hist_state[t] + (size_t)field * pf->n_pad * pf->esz;
