@@ -172,7 +172,11 @@ struct gb_pf {
   bool hist_resampled = false;      // a resample happened since the last recorded step
   std::vector<void *> hist_state;   // [t] -> S columns x n_pad of the filter dtype (t = 0: after generate)
   std::vector<int *> hist_anc;      // [t] -> ancestors applied BEFORE step t (nullptr: no resample)
-  RunCtl *d_ctl = nullptr, *h_ctl = nullptr;   // fused multi-step run (gb_pf_run)
+  RunCtl *d_ctl = nullptr, *h_ctl = nullptr;   // fused multi-step run (gb_pf_run) / asynchronous sharded run
+  ShardPlanDev *d_shplan = nullptr, *h_shplan = nullptr;
+  long long *d_offs = nullptr;
+  int a_world = 0, a_rank = 0;
+  long long a_cap = 0;
   bool ws_clean = false;           // tile_q / super_q are all zero (ready to accumulate)
   bool tiles_valid = false;        // tile_q / super_q hold the quantised mass of the current weights w.r.t. h_stats->m
   unsigned int *ticket = nullptr;
@@ -256,7 +260,7 @@ static void pf_release(gb_pf *pf) {
   cudaFree(pf->state[0]); cudaFree(pf->state[1]); cudaFree(pf->logw); cudaFree(pf->incr); cudaFree(pf->anc);
   cudaFree(pf->parents64); cudaFree(pf->ext_parents); cudaFree(pf->partials); cudaFree(pf->ticket); cudaFree(pf->d_stats);
   cudaFreeHost(pf->h_stats); cudaFree(pf->d_normals); cudaFree(pf->d_uniforms); cudaFree(pf->d_u64);
-  cudaFree(pf->d_ctl); cudaFreeHost(pf->h_ctl); cudaFree(pf->super_q); cudaFree(pf->super_excl); cudaFree(pf->oflow); cudaFree(pf->oflow_count);
+  cudaFree(pf->d_ctl); cudaFreeHost(pf->h_ctl); cudaFree(pf->d_shplan); cudaFreeHost(pf->h_shplan); cudaFree(pf->d_offs); cudaFree(pf->super_q); cudaFree(pf->super_excl); cudaFree(pf->oflow); cudaFree(pf->oflow_count);
   cudaFree(pf->tile_q); cudaFree(pf->tile_c); cudaFree(pf->tile_r); cudaFree(pf->tile_slot); cudaFree(pf->d_plan);
   cudaFreeHost(pf->h_plan); cudaFree(pf->cdf); cudaFree(pf->off_anc); cudaFree(pf->d_tab); cudaFree(pf->d_ptab);
   for (auto p : pf->hist_state) cudaFree(p);
@@ -981,10 +985,10 @@ static int fetch_plan(gb_pf *pf) {
 // shard's offspring slots; single shard: q_offset = 0, q_total = 0 (= the local total), anc_base = 0.
 template <typename R>
 static int launch_systematic(gb_pf *pf, const void *logw, double m, uint64_t q_offset, uint64_t q_total, uint32_t u0,
-                             const AncOut &ao, const RunCtl *ctl = nullptr) {
+                             const AncOut &ao, const RunCtl *ctl = nullptr, int plan_preset = 0) {
   const int bits = quant_bits(pf->n_global);
   LAUNCH(pf, GB_K_TILESCAN, superscan_kernel<<<1, 1024, 0, pf->stream>>>(pf->nsuper, pf->super_q, pf->super_excl, pf->d_plan, q_offset,
-                                                                          q_total, pf->n_global, u0, pf->oflow_count));
+                                                                          q_total, pf->n_global, u0, pf->oflow_count, plan_preset));
   CK(cudaGetLastError());
   auto kern = ancestors_sys_kernel<R>;
   LAUNCH(pf, GB_K_ANCESTORS, kern<<<(unsigned)pf->ntiles, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->tile_q, pf->super_excl,
@@ -1010,7 +1014,7 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
   int rc;
   if (kind == GB_RESAMPLE_SYSTEMATIC) {
     if (!pf->tiles_valid && (rc = run_wstats(pf, logw, m, false))) return rc;
-    return launch_systematic<R>(pf, logw, m, 0, 0, u0, AncOut{anc, 0, pf->n_global, nullptr, 0});
+    return launch_systematic<R>(pf, logw, m, 0, 0, u0, AncOut{anc, 0, pf->n_global, nullptr, 0, 0});
   }
   if (kind == GB_RESAMPLE_RESIDUAL) {
     if ((rc = ensure_residual_ws(pf))) return rc;
@@ -1132,7 +1136,7 @@ extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double
   pf->h_ctl->log_n = log((double)pf->n_global);
   CK(cudaMemcpyAsync(pf->d_ctl, pf->h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pf->stream));
   CK(cudaStreamSynchronize(pf->stream));                // h_ctl is reused for the read-back below
-  const AncOut ao{pf->anc, 0, pf->n_global, nullptr, 0};
+  const AncOut ao{pf->anc, 0, pf->n_global, nullptr, 0, 0};
   for (int t = 0; t < T; t++) {
     // maybe_resample!: statistics + decision on the device, then the (conditional) systematic sweep
     if ((rc = run_wstats(pf, pf->logw, 0.0, true, false, pf->d_ctl))) return rc;
@@ -1194,7 +1198,7 @@ extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits
   }
   if (cnt > 0) {
     // offspring slots this shard owns go straight into its `anc` column; the rest into the spill buffer
-    const AncOut ao{pf->anc, pf->pid_offset, pf->pid_offset + pf->n, pf->off_anc, lo};
+    const AncOut ao{pf->anc, pf->pid_offset, pf->pid_offset + pf->n, pf->off_anc, lo, pf->off_cap};
     rc = pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, m_global, q_offset, q_total, u0, ao)
                              : launch_systematic<float>(pf, pf->logw, m_global, q_offset, q_total, u0, ao);
     if (rc) return rc;
@@ -1204,6 +1208,126 @@ extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits
   *slot_lo = lo; *slot_hi = hi;
   return GB_OK;
 }
+// ---- asynchronous sharded run: the exchange plan, the resample decision and the log-ML live on the device; the
+//      host only enqueues (collectives in between are issued by gen.jl_b200/sharded.py on the same stream) ----
+extern "C" int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t *offs, int64_t cap_rows, double ess_threshold,
+                                 int64_t *peer_block_bytes_out) {
+  REQ(pf && offs && peer_block_bytes_out, "null argument");
+  REQ(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "gb_pf_async_setup: world size must be <= 64");
+  REQ(offs[rank] == pf->pid_offset && offs[rank + 1] == pf->pid_offset + pf->n && offs[world] == pf->n_global,
+      "gb_pf_async_setup: shard offsets do not match this shard");
+  REQ(cap_rows >= 1, "gb_pf_async_setup: cap_rows must be positive");
+  int rc = materialize_pending(pf);
+  if (rc) return rc;
+  if (!pf->d_ctl) {
+    CK(cudaMalloc((void **)&pf->d_ctl, sizeof(RunCtl)));
+    CK(cudaMallocHost((void **)&pf->h_ctl, sizeof(RunCtl)));
+  }
+  if (!pf->d_shplan) {
+    CK(cudaMalloc((void **)&pf->d_shplan, sizeof(ShardPlanDev)));
+    CK(cudaMallocHost((void **)&pf->h_shplan, sizeof(ShardPlanDev)));
+    CK(cudaMalloc((void **)&pf->d_offs, sizeof(long long) * (kMaxWorld + 1)));
+  }
+  CK(cudaMemsetAsync(pf->d_shplan, 0, sizeof(ShardPlanDev), pf->stream));
+  std::vector<long long> o(offs, offs + world + 1);
+  CK(cudaMemcpyAsync(pf->d_offs, o.data(), sizeof(long long) * (world + 1), cudaMemcpyHostToDevice, pf->stream));
+  pf->h_ctl->do_resample = 0; pf->h_ctl->n_resampled = 0;
+  pf->h_ctl->log_ml_est = pf->log_ml_est;
+  pf->h_ctl->ess_threshold = ess_threshold;
+  pf->h_ctl->log_n = log((double)pf->n_global);
+  CK(cudaMemcpyAsync(pf->d_ctl, pf->h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pf->stream));
+  // spill buffer: offspring of this shard that land outside its own slot range, indexed from the shard's first slot
+  const long long want = pf->n_pad + pf->n_pad / 4 + kTile;
+  if (pf->off_cap < want) {
+    cudaFree(pf->off_anc);
+    pf->off_anc = nullptr;
+    CK(cudaMalloc((void **)&pf->off_anc, (size_t)want * 4));
+    pf->off_cap = want;
+  }
+  CK(cudaStreamSynchronize(pf->stream));
+  pf->a_world = world; pf->a_rank = rank; pf->a_cap = cap_rows;
+  *peer_block_bytes_out = peer_block_bytes(cap_rows, pf->S, (int)pf->esz);
+  return GB_OK;
+}
+extern "C" int gb_pf_async_plan(gb_pf_t *pf, const void *dev_gathered, uint32_t u0) {
+  REQ(pf && dev_gathered && pf->a_world > 0, "gb_pf_async_plan: call gb_pf_async_setup first");
+  LAUNCH(pf, GB_K_TILESCAN, shard_plan_kernel<<<1, kMaxWorld, 0, pf->stream>>>((const long long *)dev_gathered, pf->d_offs, pf->a_world, pf->a_rank,
+                                                                              pf->n_global, u0, pf->a_cap, pf->ext_cap, pf->off_cap, pf->d_ctl,
+                                                                              pf->d_plan, pf->d_shplan));
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+extern "C" int gb_pf_async_sweep(gb_pf_t *pf) {
+  REQ(pf && pf->a_world > 0 && pf->tiles_valid, "gb_pf_async_sweep: statistics pass missing");
+  const AncOut ao{pf->anc, pf->pid_offset, pf->pid_offset + pf->n, pf->off_anc, -1, pf->off_cap};
+  return pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1)
+                             : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1);
+}
+extern "C" int gb_pf_async_export(gb_pf_t *pf, void *dev_sendbuf) {
+  REQ(pf && dev_sendbuf && pf->a_world > 0, "gb_pf_async_export: bad argument");
+  const long long bb = peer_block_bytes(pf->a_cap, pf->S, (int)pf->esz);
+  dim3 grid((unsigned)std::min<long long>((pf->a_cap + kBlock - 1) / kBlock, 64), (unsigned)pf->a_world);
+  if (pf->dtype == GB_F64)
+    LAUNCH(pf, GB_K_GATHER, export_all_kernel<double><<<grid, kBlock, 0, pf->stream>>>((const double *)pf->state[pf->cur], pf->ld, pf->S, pf->off_anc, pf->d_plan,
+                                                                                     pf->d_shplan, pf->d_ctl, (char *)dev_sendbuf, bb, pf->pid_offset, pf->off_cap));
+  else
+    LAUNCH(pf, GB_K_GATHER, export_all_kernel<float><<<grid, kBlock, 0, pf->stream>>>((const float *)pf->state[pf->cur], pf->ld, pf->S, pf->off_anc, pf->d_plan,
+                                                                                    pf->d_shplan, pf->d_ctl, (char *)dev_sendbuf, bb, pf->pid_offset, pf->off_cap));
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+extern "C" int gb_pf_async_import(gb_pf_t *pf, const void *dev_recvbuf) {
+  REQ(pf && dev_recvbuf && pf->a_world > 0, "gb_pf_async_import: bad argument");
+  const long long bb = peer_block_bytes(pf->a_cap, pf->S, (int)pf->esz);
+  dim3 grid((unsigned)std::min<long long>((pf->a_cap + kBlock - 1) / kBlock, 64), (unsigned)pf->a_world);
+  if (pf->dtype == GB_F64)
+    LAUNCH(pf, GB_K_GATHER, import_all_kernel<double><<<grid, kBlock, 0, pf->stream>>>((double *)pf->state[pf->cur], pf->ld, pf->S, pf->n_pad, pf->ext_cap, pf->d_shplan,
+                                                                                     pf->d_ctl, (const char *)dev_recvbuf, bb, pf->pid_offset, pf->anc, pf->ext_parents));
+  else
+    LAUNCH(pf, GB_K_GATHER, import_all_kernel<float><<<grid, kBlock, 0, pf->stream>>>((float *)pf->state[pf->cur], pf->ld, pf->S, pf->n_pad, pf->ext_cap, pf->d_shplan,
+                                                                                    pf->d_ctl, (const char *)dev_recvbuf, bb, pf->pid_offset, pf->anc, pf->ext_parents));
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+extern "C" int gb_pf_async_step(gb_pf_t *pf, const double *obs, int nobs) {
+  REQ(pf && obs && pf->a_world > 0, "gb_pf_async_step: bad argument");
+  REQ(nobs == pf->model.nobs, "gb_pf_async_step: wrong number of observations");
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = fill_model_params(pf, a.mp, obs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false);
+  if (rc) return rc;
+  a.state_in = pf->state[pf->cur];
+  a.state_out = pf->state[pf->cur ^ 1];
+  a.logw = pf->logw; a.incr = pf->incr;
+  a.anc = pf->anc; a.ctl = pf->d_ctl;
+  a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
+  a.seed = pf->seed; a.step = (unsigned)(pf->step + 1);
+  a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
+  rc = pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, PROPOSAL_DEFAULT, false, 2)
+                           : launch_step_k<float, false>(pf, a, PROPOSAL_DEFAULT, false, 2);
+  if (rc) return rc;
+  pf->step += 1;
+  pf->cur ^= 1;
+  pf->wstate = W_MAX;
+  pf->tiles_valid = false;
+  return GB_OK;
+}
+extern "C" int gb_pf_async_finish(gb_pf_t *pf, int *n_resampled, int *overflow) {
+  REQ(pf && pf->a_world > 0, "gb_pf_async_finish: bad argument");
+  CK(cudaMemcpyAsync(pf->h_ctl, pf->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaMemcpyAsync(pf->h_shplan, pf->d_shplan, sizeof(ShardPlanDev), cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));
+  pf->log_ml_est = pf->h_ctl->log_ml_est;
+  if (pf->h_ctl->n_resampled > 0) { pf->anc_valid = true; pf->parents64_valid = false; pf->ext_used = true; }
+  pf->pending_gather = false;
+  if (n_resampled) *n_resampled = pf->h_ctl->n_resampled;
+  if (overflow) *overflow = pf->h_shplan->overflow;
+  if (pf->h_shplan->overflow)
+    return fail(GB_ESTATE, "asynchronous sharded run: an exchange capacity was exceeded (weights too skewed for the fixed-size "
+                           "blocks); the filter state is invalid -- rerun with the synchronous maybe_resample_ path");
+  return GB_OK;
+}
+
 // ---- sharded fast path: slots that stay on this shard keep their ancestors (deferred gather, fused into
 //      the next step); rows arriving from other shards are parked in the extension rows of the current
 //      trace buffer and the slot's ancestor index points there ----

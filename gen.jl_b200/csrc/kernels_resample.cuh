@@ -564,7 +564,8 @@ struct OverflowEntry { long long tile, slot0, slot_lo, slot_hi; unsigned long lo
 __global__ void __launch_bounds__(1024) superscan_kernel(long long nsuper, unsigned long long *__restrict__ super_q,
                                                          unsigned long long *__restrict__ super_excl,
                                                          ResamplePlan *plan, uint64_t q_offset, uint64_t q_total_given,
-                                                         long long n_global, uint32_t u0, unsigned int *overflow_count) {
+                                                         long long n_global, uint32_t u0, unsigned int *overflow_count,
+                                                         int plan_preset) {
   __shared__ uint64_t s_w[33];
   const int T = 1024;
   const long long per = (nsuper + T - 1) / T;
@@ -601,17 +602,19 @@ __global__ void __launch_bounds__(1024) superscan_kernel(long long nsuper, unsig
   }
   if (threadIdx.x == 0) {
     super_excl[nsuper] = total;
-    SweepParams sp;
-    sp.q_total = q_total_given ? q_total_given : total;
-    sp.q_inv = 1.0 / (double)sp.q_total;
-    sp.dscale = (uint64_t)n_global << 32;
-    sp.ratio = (double)n_global / (double)sp.q_total;
-    sp.u0 = u0;
-    plan->sp = sp;
-    plan->q_offset = q_offset;
-    plan->n_global = n_global;
-    plan->slot_lo = slots_below(q_offset, sp);
-    plan->slot_hi = slots_below(q_offset + total, sp);
+    if (!plan_preset) {     // (preset: shard_plan_kernel already wrote the global sweep parameters)
+      SweepParams sp;
+      sp.q_total = q_total_given ? q_total_given : total;
+      sp.q_inv = 1.0 / (double)sp.q_total;
+      sp.dscale = (uint64_t)n_global << 32;
+      sp.ratio = (double)n_global / (double)sp.q_total;
+      sp.u0 = u0;
+      plan->sp = sp;
+      plan->q_offset = q_offset;
+      plan->n_global = n_global;
+      plan->slot_lo = slots_below(q_offset, sp);
+      plan->slot_hi = slots_below(q_offset + total, sp);
+    }
     *overflow_count = 0;
   }
 }
@@ -622,7 +625,8 @@ struct AncOut {
   int *own;
   long long own_lo, own_hi;
   int *spill;
-  long long spill_base;
+  long long spill_base;     // >= 0: host-known first slot of the spill buffer; < 0: plan->slot_lo (device-side plan)
+  long long spill_cap;      // entries in the spill buffer (writes beyond it are dropped: the plan flags the overflow)
 };
 
 constexpr int kHeavyCap = 16;                       // offspring a thread writes itself; more => CTA-cooperative fill
@@ -663,7 +667,7 @@ template <typename R, bool PREFIX>
 GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits, const SweepParams &sp, long long tile,
                     const uint64_t *__restrict__ tile_q, const unsigned long long *__restrict__ super_excl, uint64_t q_offset,
                     uint64_t cbase_in, long long slot0_in, long long lo_in, long long hi_in, const AncOut &ao,
-                    TileSmem &sm, long long *slot0_out, long long *slot_end_out) {
+                    long long spill_base, TileSmem &sm, long long *slot0_out, long long *slot_end_out) {
   double lw[kItems];
   load_items<R>(logw, tile * kTile, n, lw);
   const double u0term = -(double)sp.u0 * 0x1p-32;
@@ -741,8 +745,8 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
   const int tile_base = (int)(tile * kTile);
   for (int i = threadIdx.x; i < cnt; i += kBlock) {
     const long long k = lo + i;
-    int *dst = (k >= ao.own_lo && k < ao.own_hi) ? ao.own + (k - ao.own_lo) : ao.spill + (k - ao.spill_base);
-    __stcs(dst, tile_base + sm.slot[i]);
+    if (k >= ao.own_lo && k < ao.own_hi) __stcs(ao.own + (k - ao.own_lo), tile_base + sm.slot[i]);
+    else if (k - spill_base < ao.spill_cap) __stcs(ao.spill + (k - spill_base), tile_base + sm.slot[i]);
   }
 }
 
@@ -762,7 +766,8 @@ __global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const R *__restri
   const SweepParams sp = plan->sp;
   const long long tile = blockIdx.x;
   long long slot0, slot_end;
-  tile_fill<R, true>(logw, n, m, bits, sp, tile, tile_q, super_excl, plan->q_offset, 0, 0, 0, 0, ao, sm, &slot0, &slot_end);
+  const long long spill_base = ao.spill_base >= 0 ? ao.spill_base : plan->slot_lo;
+  tile_fill<R, true>(logw, n, m, bits, sp, tile, tile_q, super_excl, plan->q_offset, 0, 0, 0, 0, ao, spill_base, sm, &slot0, &slot_end);
   if (slot_end > slot0 + kChunk && threadIdx.x == 0) {
     const unsigned int e = atomicAdd(oflow_count, 1u);
     oflow[e] = OverflowEntry{tile, slot0, slot0 + kChunk, slot_end, sm.cbase};
@@ -796,9 +801,144 @@ __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restric
       long long hi = lo + kChunk;
       if (hi > en.slot_hi) hi = en.slot_hi;
       __syncthreads();
-      tile_fill<R, false>(logw, n, m, bits, sp, en.tile, nullptr, nullptr, 0, en.cbase, en.slot0, lo, hi, ao, sm, nullptr, nullptr);
+      tile_fill<R, false>(logw, n, m, bits, sp, en.tile, nullptr, nullptr, 0, en.cbase, en.slot0, lo, hi, ao,
+                          ao.spill_base >= 0 ? ao.spill_base : plan->slot_lo, sm, nullptr, nullptr);
     }
     unit0 += pieces;
+  }
+}
+
+// ==========================================================================================
+// Asynchronous sharded resample (gen.jl_b200/sharded.py run_): the exchange plan is computed ON THE DEVICE from
+// the all-gathered statistics records, blocks of fixed capacity travel by an equal-split all-to-all, and the
+// resample decision / log-ML live in RunCtl -- no host round trip anywhere in a step.
+// ==========================================================================================
+constexpr int kMaxWorld = 64;
+struct ShardPlanDev {
+  long long send_lo[kMaxWorld], send_hi[kMaxWorld];   // global slots produced here that shard d owns
+  long long recv_lo[kMaxWorld], recv_hi[kMaxWorld];   // global slots produced by shard s that this shard owns
+  long long cap;                                      // rows per peer block
+  int world, rank;
+  int overflow;                                       // sticky: a capacity was exceeded, results are invalid
+};
+
+// one CTA of kMaxWorld threads; rec = world records {m, s1, s2, lse, ess, q} (8-byte words), offs = shard offsets
+__global__ void __launch_bounds__(kMaxWorld) shard_plan_kernel(const long long *__restrict__ rec, const long long *__restrict__ offs,
+                                                              int world, int rank, long long n_global, uint32_t u0,
+                                                              long long cap, long long ext_cap, long long spill_cap,
+                                                              RunCtl *ctl, ResamplePlan *plan, ShardPlanDev *sh) {
+  __shared__ SweepParams s_sp;
+  __shared__ unsigned long long s_pref[kMaxWorld + 1];
+  __shared__ long long s_lo[kMaxWorld], s_hi[kMaxWorld];
+  __shared__ int s_do;
+  const int r = threadIdx.x;
+  if (r == 0) {
+    const double m = __longlong_as_double(rec[0]);
+    double S1 = 0.0, S2 = 0.0;
+    unsigned long long run = 0;
+    for (int k = 0; k < world; k++) {          // fixed rank order: identical on every shard
+      S1 += __longlong_as_double(rec[k * 6 + 1]);
+      S2 += __longlong_as_double(rec[k * 6 + 2]);
+      s_pref[k] = run;
+      run += (unsigned long long)rec[k * 6 + 5];
+    }
+    s_pref[world] = run;
+    const double lse = (m == -INFINITY) ? -INFINITY : m + log(S1);
+    const double ess = (S1 * S1) / S2;
+    const int flag = (ess < ctl->ess_threshold && run > 0) ? 1 : 0;   // particle_filter.jl:256
+    ctl->do_resample = flag;
+    if (flag) { ctl->log_ml_est += lse - ctl->log_n; ctl->n_resampled += 1; }   // :263
+    s_do = flag;
+    SweepParams sp;
+    sp.q_total = run ? run : 1;
+    sp.q_inv = 1.0 / (double)sp.q_total;
+    sp.dscale = (uint64_t)n_global << 32;
+    sp.ratio = (double)n_global / (double)sp.q_total;
+    sp.u0 = u0;
+    s_sp = sp;
+  }
+  __syncthreads();
+  if (r < world) {
+    s_lo[r] = slots_below(s_pref[r], s_sp);
+    s_hi[r] = slots_below(s_pref[r + 1], s_sp);
+  }
+  __syncthreads();
+  if (r == 0) {
+    plan->sp = s_sp;
+    plan->q_offset = s_pref[rank];
+    plan->n_global = n_global;
+    plan->slot_lo = s_lo[rank];
+    plan->slot_hi = s_hi[rank];
+    sh->cap = cap; sh->world = world; sh->rank = rank;
+    if (s_do && s_hi[rank] - s_lo[rank] > spill_cap) sh->overflow = 1;
+    long long recv_total = 0;
+    for (int k = 0; k < world; k++) {
+      if (k == rank) continue;
+      long long a = s_lo[k] > offs[rank] ? s_lo[k] : offs[rank], b = s_hi[k] < offs[rank + 1] ? s_hi[k] : offs[rank + 1];
+      recv_total += b > a ? b - a : 0;
+    }
+    if (s_do && recv_total > ext_cap) sh->overflow = 1;
+  }
+  if (r < world) {
+    long long a = s_lo[rank] > offs[r] ? s_lo[rank] : offs[r], b = s_hi[rank] < offs[r + 1] ? s_hi[rank] : offs[r + 1];
+    if (b < a) b = a;
+    if (r != rank && b - a > cap) { sh->overflow = 1; b = a + cap; }
+    sh->send_lo[r] = a; sh->send_hi[r] = b;
+    long long c = s_lo[r] > offs[rank] ? s_lo[r] : offs[rank], d = s_hi[r] < offs[rank + 1] ? s_hi[r] : offs[rank + 1];
+    if (d < c) d = c;
+    if (r != rank && d - c > cap) d = c + cap;
+    sh->recv_lo[r] = c; sh->recv_hi[r] = d;
+  }
+}
+
+// Fixed-capacity exchange block of one peer: [count int64][pad int64][parents int64 x cap][rows R x S x cap]
+GB_HD long long peer_block_bytes(long long cap, int S, int esz) { return (16 + cap * (8 + (long long)S * esz) + 15) / 16 * 16; }
+
+// blockIdx.y = destination shard; rows of the slots it owns, gathered from this shard's current traces
+template <typename R>
+__global__ void __launch_bounds__(kBlock) export_all_kernel(const R *__restrict__ sin, long long ld, int S, const int *__restrict__ spill,
+                                                            const ResamplePlan *__restrict__ plan, const ShardPlanDev *__restrict__ sh,
+                                                            const RunCtl *__restrict__ ctl, char *__restrict__ sendbuf,
+                                                            long long block_bytes, long long pid_offset, long long spill_cap) {
+  const int d = blockIdx.y;
+  if (d == sh->rank) return;
+  char *blk = sendbuf + (long long)d * block_bytes;
+  const long long cap = sh->cap;
+  long long cnt = ctl->do_resample ? sh->send_hi[d] - sh->send_lo[d] : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<long long *>(blk)[0] = cnt;
+  long long *parents = reinterpret_cast<long long *>(blk) + 2;
+  R *rows = reinterpret_cast<R *>(parents + cap);
+  const long long base = sh->send_lo[d] - plan->slot_lo;       // index into the spill buffer
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < cnt; i += (long long)gridDim.x * kBlock) {
+    const int src = (base + i < spill_cap) ? spill[base + i] : 0;
+    for (int s = 0; s < S; s++) rows[(long long)s * cap + i] = __ldg(sin + (long long)s * ld + src);
+    parents[i] = pid_offset + src + 1;
+  }
+}
+// blockIdx.y = source shard; received rows -> extension rows of the current trace buffer, slots point there
+template <typename R>
+__global__ void __launch_bounds__(kBlock) import_all_kernel(R *__restrict__ scur, long long ld, int S, long long n_pad, long long ext_cap,
+                                                            const ShardPlanDev *__restrict__ sh, const RunCtl *__restrict__ ctl,
+                                                            const char *__restrict__ recvbuf, long long block_bytes,
+                                                            long long my_offset, int *__restrict__ anc, long long *__restrict__ ext_parents) {
+  if (!ctl->do_resample) return;
+  const int sidx = blockIdx.y;
+  if (sidx == sh->rank) return;
+  const long long cap = sh->cap;
+  // extension offset of this source's rows = rows received from lower-ranked sources
+  long long ext = 0;
+  for (int k = 0; k < sidx; k++)
+    if (k != sh->rank) ext += reinterpret_cast<const long long *>(recvbuf + (long long)k * block_bytes)[0];
+  const char *blk = recvbuf + (long long)sidx * block_bytes;
+  const long long cnt = reinterpret_cast<const long long *>(blk)[0];
+  const long long *parents = reinterpret_cast<const long long *>(blk) + 2;
+  const R *rows = reinterpret_cast<const R *>(parents + cap);
+  const long long dst_lo = sh->recv_lo[sidx] - my_offset;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < cnt; i += (long long)gridDim.x * kBlock) {
+    if (ext + i >= ext_cap) break;
+    for (int s = 0; s < S; s++) scur[(long long)s * ld + n_pad + ext + i] = rows[(long long)s * cap + i];
+    anc[dst_lo + i] = (int)(n_pad + ext + i);
+    ext_parents[ext + i] = parents[i];
   }
 }
 

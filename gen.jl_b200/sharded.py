@@ -130,6 +130,34 @@ class ShardOps:
     def log_ml_est(self):
         return self.state.log_ml_est
 
+    # asynchronous run (plan / decision / log-ML on the device)
+    def async_setup(self, world, rank, offs, cap_rows, ess_threshold):
+        o = np.ascontiguousarray(offs, dtype=np.int64)
+        bb = C.c_int64()
+        L.check(L.lib().gb_pf_async_setup(self.h, world, rank, o.ctypes.data_as(L.i64p), int(cap_rows), float(ess_threshold), C.byref(bb)))
+        return bb.value
+
+    def async_plan(self, gathered, u0):
+        L.check(L.lib().gb_pf_async_plan(self.h, C.c_void_p(gathered.data_ptr()), int(u0)))
+
+    def async_sweep(self):
+        L.check(L.lib().gb_pf_async_sweep(self.h))
+
+    def async_export(self, sendbuf):
+        L.check(L.lib().gb_pf_async_export(self.h, C.c_void_p(sendbuf.data_ptr())))
+
+    def async_import(self, recvbuf):
+        L.check(L.lib().gb_pf_async_import(self.h, C.c_void_p(recvbuf.data_ptr())))
+
+    def async_step(self, obs):
+        o = api._flatten_obs(obs)
+        L.check(L.lib().gb_pf_async_step(self.h, o.ctypes.data_as(L.dp), o.size))
+
+    def async_finish(self):
+        nres, ovf = C.c_int(), C.c_int()
+        L.check(L.lib().gb_pf_async_finish(self.h, C.byref(nres), C.byref(ovf)))
+        return nres.value
+
 
 class ShardedParticleFilter:
     """Gen's particle-filter calls over a filter whose particles are sharded across the process group."""
@@ -231,6 +259,49 @@ class ShardedParticleFilter:
                                         return_incr=return_incr)
         self.step += 1
         return out
+
+    def run_(self, observations_seq, ess_threshold=None, cap_rows=None):
+        """T x { maybe_resample!; particle_filter_step! } over the sharded filter WITHOUT any host round trip: the
+        statistics record is all-reduced / all-gathered on the device, the exchange plan, the ESS test and the log-ML
+        update run in a device kernel, the offspring travel in fixed-capacity blocks by an equal-split all-to-all.
+        Same results as the synchronous path (bit for bit) as long as no capacity overflows (else GenB200Error).
+        Returns the number of resamples."""
+        torch, dist, W = self.torch, self.dist, self.world
+        thr = self.n_global / 2 if ess_threshold is None else float(ess_threshold)
+        # rows per fixed-size peer block: the spill between neighbouring shards is O(CV * sqrt(N_local)) rows for
+        # non-degenerate weights; 1/256 of the shard (at least 4096, at most 262144 rows) leaves a wide margin
+        cap = int(cap_rows) if cap_rows else min(max(4096, self.n_local // 256), 262144)
+        bb = self.ops.async_setup(W, self.rank, self.offs, cap, thr)
+        if self._stats_t is None:
+            self._stats_t = self.ops.stats_tensor(torch)
+            self._gather_t = torch.empty(W * self._stats_t.numel(), dtype=torch.int64, device=self.device)
+        key = ("async", bb)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.zeros(W * bb, dtype=torch.uint8, device=self.device),
+                               torch.zeros(W * bb, dtype=torch.uint8, device=self.device))
+        sendbuf, recvbuf = self._bufs[key]
+        m_view = self._stats_t[0:1].view(torch.float64)
+        for obs in observations_seq:
+            self.ops.weight_max_device()
+            if W > 1:
+                dist.all_reduce(m_view, op=dist.ReduceOp.MAX, group=self.group)
+            self.ops.weight_sums_device(self.bits)
+            if W > 1:
+                dist.all_gather_into_tensor(self._gather_t, self._stats_t, group=self.group)
+            else:
+                self._gather_t.copy_(self._stats_t)
+            self.ops.async_plan(self._gather_t, api.philox_resample_u0(self.seed, self.step))
+            self.ops.async_sweep()
+            if W > 1:
+                self.ops.async_export(sendbuf)
+                dist.all_to_all_single(recvbuf, sendbuf, group=self.group)
+                self.ops.async_import(recvbuf)
+            self.ops.async_step(obs)
+            self.step += 1
+        nres = self.ops.async_finish()
+        if self.local is not None and self.local._last_t is not None:
+            self.local._last_t += len(observations_seq)
+        return nres
 
     def _global_stats(self):
         """Global (m, lse, ess) and the gathered integer masses (particle_filter.jl:3-12 over all shards)."""

@@ -137,6 +137,23 @@ int gb_pf_weight_sums(gb_pf_t *pf, double m_ref, int bits, double *s1, double *s
 int gb_pf_stats_device(gb_pf_t *pf, void **dev_stats, int *n_words);
 int gb_pf_weight_max_device(gb_pf_t *pf);
 int gb_pf_weight_sums_device(gb_pf_t *pf, int bits);
+/* Asynchronous flavour of the whole sharded step (no host round trip; used by ShardedParticleFilter.run_):
+ *   setup  : shard offsets (world+1), rows per fixed-size peer block, ESS threshold; returns the peer block size
+ *   per step (all asynchronous on the handle's stream; the host issues the collectives in between):
+ *     gb_pf_weight_max_device -> all-reduce(max) of the statistics record's m -> gb_pf_weight_sums_device ->
+ *     all-gather of the records -> gb_pf_async_plan (decision, log-ML, exchange plan ON THE DEVICE) ->
+ *     gb_pf_async_sweep (ancestors) -> gb_pf_async_export -> equal-split all-to-all of world blocks ->
+ *     gb_pf_async_import -> gb_pf_async_step
+ *   finish : one device->host read (log_ml_est, #resamples, overflow flag).  Overflow (a peer block, the extension
+ *            rows or the spill buffer too small for the weight skew) invalidates the run: GB_ESTATE. */
+int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t *offs, int64_t cap_rows, double ess_threshold,
+                      int64_t *peer_block_bytes_out);
+int gb_pf_async_plan(gb_pf_t *pf, const void *dev_gathered, uint32_t u0);
+int gb_pf_async_sweep(gb_pf_t *pf);
+int gb_pf_async_export(gb_pf_t *pf, void *dev_sendbuf);
+int gb_pf_async_import(gb_pf_t *pf, const void *dev_recvbuf);
+int gb_pf_async_step(gb_pf_t *pf, const double *obs, int nobs);
+int gb_pf_async_finish(gb_pf_t *pf, int *n_resampled, int *overflow);
 /* Offspring of this shard's particles under global-prefix systematic resampling: the shard's particles
  * (integer CDF mass q_local, preceded by q_offset of a global q_total) fill the global slot range
  * [*slot_lo, *slot_hi).  Ancestors of the slots this shard owns itself go straight into its ancestor

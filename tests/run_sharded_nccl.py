@@ -46,6 +46,22 @@ def main():
             print("NCCL sharded check world=%d n=%d staged=%s resamples=%d: %s (log ML %.12f)" % (world, n, staged, nres, "OK" if ok else "MISMATCH", lml))
             if not ok:
                 sys.exit(1)
+    # asynchronous run (device-side plan, fixed-capacity equal-split all-to-all) vs the fused single-GPU run
+    for n in (100003, 4_000_000):
+        ys = F.bearings_series(10)
+        spf = sharded.ShardedParticleFilter(g.bearings_model(), n, seed=9).initialize(ys[0])
+        nres = spf.run_(ys[1:], ess_threshold=n / 2)
+        cols = [spf.get_state(f) for f in range(4)]
+        par = spf.get_parents()
+        lml = spf.log_ml_estimate()
+        if rank == 0:
+            st = g.initialize_particle_filter(g.bearings_model(), (0,), ys[0], n, seed=9)
+            nres1 = g.particle_filter_run_(st, ys[1:], ess_threshold=n / 2)
+            ok = nres == nres1 and all(np.array_equal(cols[f], st.get_state(f)) for f in range(4)) and np.array_equal(par, st.parents)
+            ok = ok and abs(lml - g.log_ml_estimate(st)) <= 1e-10 * abs(lml)
+            print("NCCL async sharded run world=%d n=%d resamples=%d: %s (log ML %.12f)" % (world, n, nres, "OK" if ok else "MISMATCH", lml))
+            if not ok:
+                sys.exit(1)
     dist.destroy_process_group()
 
 

@@ -122,3 +122,70 @@ def test_sharded_class_world1(g, O):
         assert np.array_equal(spf.get_state(f), st.get_state(f))
     assert np.array_equal(spf.get_parents(), st.parents)
     assert abs(spf.log_ml_estimate() - g.log_ml_estimate(st)) < 1e-10
+
+
+def run_async_in_process(g, model, n, K, ys, seed, thr, cap_rows):
+    """K shards in one process driven through the ASYNCHRONOUS sharded entries; the host plays the three collectives
+    with device copies (no host round trip otherwise)."""
+    import torch
+    from genb200 import sharded, _lib as L
+    counts, offs = sharded.shard_bounds(n, K)
+    bits = L.lib().gb_quant_bits(n)
+    shards = [g.create_particle_filter(model, counts[r], seed=seed, n_global=n, pid_offset=offs[r]) for r in range(K)]
+    ops = [sharded.ShardOps(s) for s in shards]
+    for s in shards:
+        g.generate_(s, ys[0])
+    bb = [o.async_setup(K, r, offs, cap_rows, thr) for r, o in enumerate(ops)][0]
+    stats = [o.stats_tensor(torch) for o in ops]
+    gathered = torch.empty(K * stats[0].numel(), dtype=torch.int64, device="cuda")
+    send = [torch.zeros(K * bb, dtype=torch.uint8, device="cuda") for _ in range(K)]
+    recv = [torch.zeros(K * bb, dtype=torch.uint8, device="cuda") for _ in range(K)]
+    for t in range(1, len(ys)):
+        for o in ops:
+            o.weight_max_device()
+        m = torch.stack([st[0:1].view(torch.float64) for st in stats]).max()          # all-reduce(max)
+        for st in stats:
+            st[0:1].view(torch.float64).fill_(m)
+        for o in ops:
+            o.weight_sums_device(bits)
+        gathered.copy_(torch.cat(stats))                                                # all-gather
+        u0 = g.philox_resample_u0(seed, t - 1)
+        for o in ops:
+            o.async_plan(gathered, u0)
+            o.async_sweep()
+        for r, o in enumerate(ops):
+            o.async_export(send[r])
+        for r in range(K):                                                              # equal-split all-to-all
+            for d in range(K):
+                recv[d][r * bb:(r + 1) * bb] = send[r][d * bb:(d + 1) * bb]
+        for r, o in enumerate(ops):
+            o.async_import(recv[r])
+            o.async_step(ys[t])
+    nres = [o.async_finish() for o in ops]
+    assert len(set(nres)) == 1
+    cols = [np.concatenate([s.get_state(f) for s in shards]) for f in range(model.state_dim)]
+    lw = np.concatenate([g.get_log_weights(s) for s in shards])
+    par = np.concatenate([s.parents for s in shards])
+    return cols, lw, par, shards[0].log_ml_est, nres[0]
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 8])
+def test_async_sharded_run_equals_single_gpu(g, K):
+    model, ys = g.bearings_model(), F.bearings_series(9)
+    n, seed = 60013, 23
+    for thr in (n / 2, n + 1):
+        ref = g.initialize_particle_filter(model, (0,), ys[0], n, seed=seed)
+        nres_ref = g.particle_filter_run_(ref, ys[1:], ess_threshold=thr)
+        cols, lw, par, lml, nres = run_async_in_process(g, model, n, K, ys, seed, thr, cap_rows=8192)
+        assert nres == nres_ref
+        for f in range(4):
+            assert np.array_equal(cols[f], ref.get_state(f))
+        assert np.array_equal(lw, ref.log_weights) and np.array_equal(par, ref.parents)
+        assert abs(lml - ref.log_ml_est) <= 1e-12 * max(1.0, abs(lml))
+
+
+def test_async_sharded_overflow_is_reported(g):
+    """Fixed-capacity blocks too small for the weight skew: the run must fail loudly, never silently."""
+    model, ys = g.bearings_model(), F.bearings_series(4)
+    with pytest.raises(g.GenB200Error):
+        run_async_in_process(g, model, 60013, 2, ys, 5, 60014, cap_rows=1)
