@@ -70,11 +70,15 @@ SIGNATURES = {
     "gb_pf_stats_device": (i, [vp, vpp, ip]),
     "gb_pf_weight_max_device": (i, [vp]),
     "gb_pf_weight_sums_device": (i, [vp, i]),
-    "gb_pf_async_setup": (i, [vp, i, i, i64p, i64, d, i64p]),
+    "gb_pf_ipc_bundle_bytes": (i, []),
+    "gb_pf_ipc_export": (i, [vp, vp, ip]),
+    "gb_pf_async_attach_ipc": (i, [vp, i, vp]),
+    "gb_pf_async_attach_local": (i, [vp, i, vp]),
+    "gb_pf_async_setup": (i, [vp, i, i, i64p, d]),
+    "gb_pf_async_cur": (i, [vp, ip]),
     "gb_pf_async_plan": (i, [vp, vp, u32]),
     "gb_pf_async_sweep": (i, [vp]),
-    "gb_pf_async_export": (i, [vp, vp]),
-    "gb_pf_async_import": (i, [vp, vp]),
+    "gb_pf_async_export": (i, [vp]),
     "gb_pf_async_step": (i, [vp, dp, i]),
     "gb_pf_async_finish": (i, [vp, ip, ip]),
     "gb_pf_systematic_offspring": (i, [vp, d, i, u64, u64, u64, u32, i64p, i64p]),

@@ -1208,17 +1208,26 @@ extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits
   *slot_lo = lo; *slot_hi = hi;
   return GB_OK;
 }
-// ---- asynchronous sharded run: the exchange plan, the resample decision and the log-ML live on the device; the
-//      host only enqueues (collectives in between are issued by gen.jl_b200/sharded.py on the same stream) ----
-extern "C" int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t *offs, int64_t cap_rows, double ess_threshold,
-                                 int64_t *peer_block_bytes_out) {
-  REQ(pf && offs && peer_block_bytes_out, "null argument");
-  REQ(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "gb_pf_async_setup: world size must be <= 64");
-  REQ(offs[rank] == pf->pid_offset && offs[rank + 1] == pf->pid_offset + pf->n && offs[world] == pf->n_global,
-      "gb_pf_async_setup: shard offsets do not match this shard");
-  REQ(cap_rows >= 1, "gb_pf_async_setup: cap_rows must be positive");
-  int rc = materialize_pending(pf);
-  if (rc) return rc;
+// ---- asynchronous sharded run: the exchange plan, the resample decision and the log-ML live on the device; offspring
+//      owned by other shards are written straight into their memory (CUDA IPC peer pointers over NVLink); the host only
+//      enqueues (the collectives in between are issued by gen.jl_b200/sharded.py on the same stream) ----
+struct IpcBundle { cudaIpcMemHandle_t h[4]; long long ld, n_pad, ext_cap; };
+extern "C" int gb_pf_ipc_export(gb_pf_t *pf, void *bundle_out, int *nbytes) {
+  REQ(pf && bundle_out && nbytes, "null argument");
+  REQ(pf->ext_parents, "gb_pf_ipc_export: not a sharded filter (n_local == n_global)");
+  IpcBundle b;
+  memset(&b, 0, sizeof(b));
+  CK(cudaIpcGetMemHandle(&b.h[0], pf->state[0]));
+  CK(cudaIpcGetMemHandle(&b.h[1], pf->state[1]));
+  CK(cudaIpcGetMemHandle(&b.h[2], pf->anc));
+  CK(cudaIpcGetMemHandle(&b.h[3], pf->ext_parents));
+  b.ld = pf->ld; b.n_pad = pf->n_pad; b.ext_cap = pf->ext_cap;
+  memcpy(bundle_out, &b, sizeof(b));
+  *nbytes = (int)sizeof(b);
+  return GB_OK;
+}
+extern "C" int gb_pf_ipc_bundle_bytes(void) { return (int)sizeof(IpcBundle); }
+static int ensure_async_alloc(gb_pf *pf) {
   if (!pf->d_ctl) {
     CK(cudaMalloc((void **)&pf->d_ctl, sizeof(RunCtl)));
     CK(cudaMallocHost((void **)&pf->h_ctl, sizeof(RunCtl)));
@@ -1226,9 +1235,48 @@ extern "C" int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t
   if (!pf->d_shplan) {
     CK(cudaMalloc((void **)&pf->d_shplan, sizeof(ShardPlanDev)));
     CK(cudaMallocHost((void **)&pf->h_shplan, sizeof(ShardPlanDev)));
+    memset(pf->h_shplan, 0, sizeof(ShardPlanDev));
     CK(cudaMalloc((void **)&pf->d_offs, sizeof(long long) * (kMaxWorld + 1)));
   }
-  CK(cudaMemsetAsync(pf->d_shplan, 0, sizeof(ShardPlanDev), pf->stream));
+  return GB_OK;
+}
+// peer in ANOTHER process: open its IPC bundle
+extern "C" int gb_pf_async_attach_ipc(gb_pf_t *pf, int peer_rank, const void *bundle) {
+  REQ(pf && bundle && peer_rank >= 0 && peer_rank < kMaxWorld, "gb_pf_async_attach_ipc: bad argument");
+  int rc = ensure_async_alloc(pf);
+  if (rc) return rc;
+  IpcBundle b;
+  memcpy(&b, bundle, sizeof(b));
+  PeerMem &pm = pf->h_shplan->peer[peer_rank];
+  void *p[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int k = 0; k < 4; k++) CK(cudaIpcOpenMemHandle(&p[k], b.h[k], cudaIpcMemLazyEnablePeerAccess));
+  pm.state[0] = p[0]; pm.state[1] = p[1]; pm.anc = (int *)p[2]; pm.ext_parents = (long long *)p[3];
+  pm.ld = b.ld; pm.n_pad = b.n_pad; pm.ext_cap = b.ext_cap;
+  return GB_OK;
+}
+// peer in THIS process (several shards on one GPU: tests)
+extern "C" int gb_pf_async_attach_local(gb_pf_t *pf, int peer_rank, gb_pf_t *peer) {
+  REQ(pf && peer && peer_rank >= 0 && peer_rank < kMaxWorld, "gb_pf_async_attach_local: bad argument");
+  int rc = ensure_async_alloc(pf);
+  if (rc) return rc;
+  PeerMem &pm = pf->h_shplan->peer[peer_rank];
+  pm.state[0] = peer->state[0]; pm.state[1] = peer->state[1]; pm.anc = peer->anc; pm.ext_parents = peer->ext_parents;
+  pm.ld = peer->ld; pm.n_pad = peer->n_pad; pm.ext_cap = peer->ext_cap;
+  return GB_OK;
+}
+extern "C" int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t *offs, double ess_threshold) {
+  REQ(pf && offs, "null argument");
+  REQ(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "gb_pf_async_setup: world size must be <= 64");
+  REQ(offs[rank] == pf->pid_offset && offs[rank + 1] == pf->pid_offset + pf->n && offs[world] == pf->n_global,
+      "gb_pf_async_setup: shard offsets do not match this shard");
+  int rc = materialize_pending(pf);
+  if (rc) return rc;
+  if ((rc = ensure_async_alloc(pf))) return rc;
+  for (int d = 0; d < world; d++)
+    if (d != rank) REQ(pf->h_shplan->peer[d].anc != nullptr, "gb_pf_async_setup: attach every peer first (gb_pf_async_attach_*)");
+  // both trace buffers must be in lock step with the peers': cur parity is part of the protocol
+  pf->h_shplan->world = world; pf->h_shplan->rank = rank; pf->h_shplan->overflow = 0;
+  CK(cudaMemcpyAsync(pf->d_shplan, pf->h_shplan, sizeof(ShardPlanDev), cudaMemcpyHostToDevice, pf->stream));
   std::vector<long long> o(offs, offs + world + 1);
   CK(cudaMemcpyAsync(pf->d_offs, o.data(), sizeof(long long) * (world + 1), cudaMemcpyHostToDevice, pf->stream));
   pf->h_ctl->do_resample = 0; pf->h_ctl->n_resampled = 0;
@@ -1236,7 +1284,7 @@ extern "C" int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t
   pf->h_ctl->ess_threshold = ess_threshold;
   pf->h_ctl->log_n = log((double)pf->n_global);
   CK(cudaMemcpyAsync(pf->d_ctl, pf->h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pf->stream));
-  // spill buffer: offspring of this shard that land outside its own slot range, indexed from the shard's first slot
+  // spill buffer: ancestors of the offspring that land outside this shard's own slot range
   const long long want = pf->n_pad + pf->n_pad / 4 + kTile;
   if (pf->off_cap < want) {
     cudaFree(pf->off_anc);
@@ -1245,15 +1293,14 @@ extern "C" int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t
     pf->off_cap = want;
   }
   CK(cudaStreamSynchronize(pf->stream));
-  pf->a_world = world; pf->a_rank = rank; pf->a_cap = cap_rows;
-  *peer_block_bytes_out = peer_block_bytes(cap_rows, pf->S, (int)pf->esz);
+  pf->a_world = world; pf->a_rank = rank;
   return GB_OK;
 }
+extern "C" int gb_pf_async_cur(const gb_pf_t *pf, int *cur) { REQ(pf && cur, "null argument"); *cur = pf->cur; return GB_OK; }
 extern "C" int gb_pf_async_plan(gb_pf_t *pf, const void *dev_gathered, uint32_t u0) {
   REQ(pf && dev_gathered && pf->a_world > 0, "gb_pf_async_plan: call gb_pf_async_setup first");
   LAUNCH(pf, GB_K_TILESCAN, shard_plan_kernel<<<1, kMaxWorld, 0, pf->stream>>>((const long long *)dev_gathered, pf->d_offs, pf->a_world, pf->a_rank,
-                                                                              pf->n_global, u0, pf->a_cap, pf->ext_cap, pf->off_cap, pf->d_ctl,
-                                                                              pf->d_plan, pf->d_shplan));
+                                                                              pf->n_global, u0, pf->off_cap, pf->d_ctl, pf->d_plan, pf->d_shplan));
   CK(cudaGetLastError());
   return GB_OK;
 }
@@ -1263,29 +1310,17 @@ extern "C" int gb_pf_async_sweep(gb_pf_t *pf) {
   return pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1)
                              : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1);
 }
-extern "C" int gb_pf_async_export(gb_pf_t *pf, void *dev_sendbuf) {
-  REQ(pf && dev_sendbuf && pf->a_world > 0, "gb_pf_async_export: bad argument");
-  const long long bb = peer_block_bytes(pf->a_cap, pf->S, (int)pf->esz);
-  dim3 grid((unsigned)std::min<long long>((pf->a_cap + kBlock - 1) / kBlock, 64), (unsigned)pf->a_world);
+// offspring owned by other shards -> their memory (peer stores); the caller runs a barrier collective afterwards
+extern "C" int gb_pf_async_export(gb_pf_t *pf) {
+  REQ(pf && pf->a_world > 0, "gb_pf_async_export: bad argument");
+  if (pf->a_world == 1) return GB_OK;
+  dim3 grid((unsigned)std::min<long long>(std::max<long long>(pf->n / (64 * kBlock), 1), 64), (unsigned)pf->a_world);
   if (pf->dtype == GB_F64)
-    LAUNCH(pf, GB_K_GATHER, export_all_kernel<double><<<grid, kBlock, 0, pf->stream>>>((const double *)pf->state[pf->cur], pf->ld, pf->S, pf->off_anc, pf->d_plan,
-                                                                                     pf->d_shplan, pf->d_ctl, (char *)dev_sendbuf, bb, pf->pid_offset, pf->off_cap));
+    LAUNCH(pf, GB_K_GATHER, export_p2p_kernel<double><<<grid, kBlock, 0, pf->stream>>>((const double *)pf->state[pf->cur], pf->ld, pf->S, pf->off_anc, pf->d_plan,
+                                                                                     pf->d_shplan, pf->d_ctl, pf->d_offs, pf->cur, pf->pid_offset, pf->off_cap));
   else
-    LAUNCH(pf, GB_K_GATHER, export_all_kernel<float><<<grid, kBlock, 0, pf->stream>>>((const float *)pf->state[pf->cur], pf->ld, pf->S, pf->off_anc, pf->d_plan,
-                                                                                    pf->d_shplan, pf->d_ctl, (char *)dev_sendbuf, bb, pf->pid_offset, pf->off_cap));
-  CK(cudaGetLastError());
-  return GB_OK;
-}
-extern "C" int gb_pf_async_import(gb_pf_t *pf, const void *dev_recvbuf) {
-  REQ(pf && dev_recvbuf && pf->a_world > 0, "gb_pf_async_import: bad argument");
-  const long long bb = peer_block_bytes(pf->a_cap, pf->S, (int)pf->esz);
-  dim3 grid((unsigned)std::min<long long>((pf->a_cap + kBlock - 1) / kBlock, 64), (unsigned)pf->a_world);
-  if (pf->dtype == GB_F64)
-    LAUNCH(pf, GB_K_GATHER, import_all_kernel<double><<<grid, kBlock, 0, pf->stream>>>((double *)pf->state[pf->cur], pf->ld, pf->S, pf->n_pad, pf->ext_cap, pf->d_shplan,
-                                                                                     pf->d_ctl, (const char *)dev_recvbuf, bb, pf->pid_offset, pf->anc, pf->ext_parents));
-  else
-    LAUNCH(pf, GB_K_GATHER, import_all_kernel<float><<<grid, kBlock, 0, pf->stream>>>((float *)pf->state[pf->cur], pf->ld, pf->S, pf->n_pad, pf->ext_cap, pf->d_shplan,
-                                                                                    pf->d_ctl, (const char *)dev_recvbuf, bb, pf->pid_offset, pf->anc, pf->ext_parents));
+    LAUNCH(pf, GB_K_GATHER, export_p2p_kernel<float><<<grid, kBlock, 0, pf->stream>>>((const float *)pf->state[pf->cur], pf->ld, pf->S, pf->off_anc, pf->d_plan,
+                                                                                    pf->d_shplan, pf->d_ctl, pf->d_offs, pf->cur, pf->pid_offset, pf->off_cap));
   CK(cudaGetLastError());
   return GB_OK;
 }

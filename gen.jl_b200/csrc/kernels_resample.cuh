@@ -809,15 +809,25 @@ __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restric
 }
 
 // ==========================================================================================
-// Asynchronous sharded resample (gen.jl_b200/sharded.py run_): the exchange plan is computed ON THE DEVICE from
-// the all-gathered statistics records, blocks of fixed capacity travel by an equal-split all-to-all, and the
-// resample decision / log-ML live in RunCtl -- no host round trip anywhere in a step.
+// Asynchronous sharded resample (gen.jl_b200/sharded.py run_): no host round trip anywhere in a step.
+//   * the statistics records are all-reduced / all-gathered on the device (NCCL on device memory);
+//   * shard_plan_kernel turns them into the ESS test, the log-ML update and the exchange plan ON THE DEVICE;
+//   * offspring owned by another shard are written by export_p2p_kernel STRAIGHT INTO THAT SHARD'S MEMORY over
+//     NVLink (peer pointers from CUDA IPC): rows into the extension rows of its current trace buffer, the slot's
+//     ancestor index and the global parent id next to them -- no staging buffer, no all-to-all, traffic = spill;
+//   * one tiny all-reduce afterwards is the barrier that orders the remote writes before the next step kernel.
 // ==========================================================================================
 constexpr int kMaxWorld = 64;
+struct PeerMem {           // a peer shard's arrays (device pointers valid in THIS process)
+  void *state[2];          // its two trace buffers
+  int *anc;
+  long long *ext_parents;
+  long long ld, n_pad, ext_cap;
+};
 struct ShardPlanDev {
+  PeerMem peer[kMaxWorld];
   long long send_lo[kMaxWorld], send_hi[kMaxWorld];   // global slots produced here that shard d owns
-  long long recv_lo[kMaxWorld], recv_hi[kMaxWorld];   // global slots produced by shard s that this shard owns
-  long long cap;                                      // rows per peer block
+  long long ext_off[kMaxWorld];                       // first extension row at shard d for the rows sent from here
   int world, rank;
   int overflow;                                       // sticky: a capacity was exceeded, results are invalid
 };
@@ -825,8 +835,7 @@ struct ShardPlanDev {
 // one CTA of kMaxWorld threads; rec = world records {m, s1, s2, lse, ess, q} (8-byte words), offs = shard offsets
 __global__ void __launch_bounds__(kMaxWorld) shard_plan_kernel(const long long *__restrict__ rec, const long long *__restrict__ offs,
                                                               int world, int rank, long long n_global, uint32_t u0,
-                                                              long long cap, long long ext_cap, long long spill_cap,
-                                                              RunCtl *ctl, ResamplePlan *plan, ShardPlanDev *sh) {
+                                                              long long spill_cap, RunCtl *ctl, ResamplePlan *plan, ShardPlanDev *sh) {
   __shared__ SweepParams s_sp;
   __shared__ unsigned long long s_pref[kMaxWorld + 1];
   __shared__ long long s_lo[kMaxWorld], s_hi[kMaxWorld];
@@ -869,76 +878,47 @@ __global__ void __launch_bounds__(kMaxWorld) shard_plan_kernel(const long long *
     plan->n_global = n_global;
     plan->slot_lo = s_lo[rank];
     plan->slot_hi = s_hi[rank];
-    sh->cap = cap; sh->world = world; sh->rank = rank;
     if (s_do && s_hi[rank] - s_lo[rank] > spill_cap) sh->overflow = 1;
-    long long recv_total = 0;
-    for (int k = 0; k < world; k++) {
-      if (k == rank) continue;
-      long long a = s_lo[k] > offs[rank] ? s_lo[k] : offs[rank], b = s_hi[k] < offs[rank + 1] ? s_hi[k] : offs[rank + 1];
-      recv_total += b > a ? b - a : 0;
-    }
-    if (s_do && recv_total > ext_cap) sh->overflow = 1;
   }
   if (r < world) {
+    // rows going from this shard to shard r, and where they start in r's extension rows: after the rows r receives
+    // from lower-ranked sources (every shard evaluates the same arithmetic, so all agree)
     long long a = s_lo[rank] > offs[r] ? s_lo[rank] : offs[r], b = s_hi[rank] < offs[r + 1] ? s_hi[rank] : offs[r + 1];
     if (b < a) b = a;
-    if (r != rank && b - a > cap) { sh->overflow = 1; b = a + cap; }
+    long long before = 0, total = 0;
+    for (int k = 0; k < world; k++) {
+      if (k == r) continue;
+      long long c = s_lo[k] > offs[r] ? s_lo[k] : offs[r], d = s_hi[k] < offs[r + 1] ? s_hi[k] : offs[r + 1];
+      const long long cnt = d > c ? d - c : 0;
+      if (k < rank) before += cnt;
+      total += cnt;
+    }
+    if (r != rank && s_do && total > sh->peer[r].ext_cap) { sh->overflow = 1; b = a; }   // r cannot park its incoming rows
     sh->send_lo[r] = a; sh->send_hi[r] = b;
-    long long c = s_lo[r] > offs[rank] ? s_lo[r] : offs[rank], d = s_hi[r] < offs[rank + 1] ? s_hi[r] : offs[rank + 1];
-    if (d < c) d = c;
-    if (r != rank && d - c > cap) d = c + cap;
-    sh->recv_lo[r] = c; sh->recv_hi[r] = d;
+    sh->ext_off[r] = before;
   }
 }
 
-// Fixed-capacity exchange block of one peer: [count int64][pad int64][parents int64 x cap][rows R x S x cap]
-GB_HD long long peer_block_bytes(long long cap, int S, int esz) { return (16 + cap * (8 + (long long)S * esz) + 15) / 16 * 16; }
-
-// blockIdx.y = destination shard; rows of the slots it owns, gathered from this shard's current traces
+// blockIdx.y = destination shard d: the rows of the slots d owns go straight into d's memory (NVLink peer stores)
 template <typename R>
-__global__ void __launch_bounds__(kBlock) export_all_kernel(const R *__restrict__ sin, long long ld, int S, const int *__restrict__ spill,
+__global__ void __launch_bounds__(kBlock) export_p2p_kernel(const R *__restrict__ sin, long long ld, int S, const int *__restrict__ spill,
                                                             const ResamplePlan *__restrict__ plan, const ShardPlanDev *__restrict__ sh,
-                                                            const RunCtl *__restrict__ ctl, char *__restrict__ sendbuf,
-                                                            long long block_bytes, long long pid_offset, long long spill_cap) {
+                                                            const RunCtl *__restrict__ ctl, const long long *__restrict__ offs,
+                                                            int cur, long long pid_offset, long long spill_cap) {
   const int d = blockIdx.y;
-  if (d == sh->rank) return;
-  char *blk = sendbuf + (long long)d * block_bytes;
-  const long long cap = sh->cap;
-  long long cnt = ctl->do_resample ? sh->send_hi[d] - sh->send_lo[d] : 0;
-  if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<long long *>(blk)[0] = cnt;
-  long long *parents = reinterpret_cast<long long *>(blk) + 2;
-  R *rows = reinterpret_cast<R *>(parents + cap);
-  const long long base = sh->send_lo[d] - plan->slot_lo;       // index into the spill buffer
+  if (d == sh->rank || !ctl->do_resample) return;
+  const long long cnt = sh->send_hi[d] - sh->send_lo[d];
+  if (cnt <= 0) return;
+  const PeerMem pm = sh->peer[d];
+  R *__restrict__ dst = static_cast<R *>(pm.state[cur]);
+  const long long base = sh->send_lo[d] - plan->slot_lo;       // index into this shard's spill buffer
+  const long long dst_slot0 = sh->send_lo[d] - offs[d];        // local slot at the destination
+  const long long ext0 = pm.n_pad + sh->ext_off[d];
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < cnt; i += (long long)gridDim.x * kBlock) {
     const int src = (base + i < spill_cap) ? spill[base + i] : 0;
-    for (int s = 0; s < S; s++) rows[(long long)s * cap + i] = __ldg(sin + (long long)s * ld + src);
-    parents[i] = pid_offset + src + 1;
-  }
-}
-// blockIdx.y = source shard; received rows -> extension rows of the current trace buffer, slots point there
-template <typename R>
-__global__ void __launch_bounds__(kBlock) import_all_kernel(R *__restrict__ scur, long long ld, int S, long long n_pad, long long ext_cap,
-                                                            const ShardPlanDev *__restrict__ sh, const RunCtl *__restrict__ ctl,
-                                                            const char *__restrict__ recvbuf, long long block_bytes,
-                                                            long long my_offset, int *__restrict__ anc, long long *__restrict__ ext_parents) {
-  if (!ctl->do_resample) return;
-  const int sidx = blockIdx.y;
-  if (sidx == sh->rank) return;
-  const long long cap = sh->cap;
-  // extension offset of this source's rows = rows received from lower-ranked sources
-  long long ext = 0;
-  for (int k = 0; k < sidx; k++)
-    if (k != sh->rank) ext += reinterpret_cast<const long long *>(recvbuf + (long long)k * block_bytes)[0];
-  const char *blk = recvbuf + (long long)sidx * block_bytes;
-  const long long cnt = reinterpret_cast<const long long *>(blk)[0];
-  const long long *parents = reinterpret_cast<const long long *>(blk) + 2;
-  const R *rows = reinterpret_cast<const R *>(parents + cap);
-  const long long dst_lo = sh->recv_lo[sidx] - my_offset;
-  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < cnt; i += (long long)gridDim.x * kBlock) {
-    if (ext + i >= ext_cap) break;
-    for (int s = 0; s < S; s++) scur[(long long)s * ld + n_pad + ext + i] = rows[(long long)s * cap + i];
-    anc[dst_lo + i] = (int)(n_pad + ext + i);
-    ext_parents[ext + i] = parents[i];
+    for (int s = 0; s < S; s++) dst[(long long)s * pm.ld + ext0 + i] = __ldg(sin + (long long)s * ld + src);
+    pm.anc[dst_slot0 + i] = (int)(ext0 + i);
+    pm.ext_parents[sh->ext_off[d] + i] = pid_offset + src + 1;   // Gen's parents are 1-based, global
   }
 }
 

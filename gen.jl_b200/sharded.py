@@ -130,12 +130,28 @@ class ShardOps:
     def log_ml_est(self):
         return self.state.log_ml_est
 
-    # asynchronous run (plan / decision / log-ML on the device)
-    def async_setup(self, world, rank, offs, cap_rows, ess_threshold):
+    # asynchronous run (plan / decision / log-ML on the device, offspring by peer stores)
+    def ipc_bundle(self):
+        n = L.lib().gb_pf_ipc_bundle_bytes()
+        buf = (C.c_char * n)()
+        nb = C.c_int()
+        L.check(L.lib().gb_pf_ipc_export(self.h, buf, C.byref(nb)))
+        return bytes(buf[:nb.value])
+
+    def attach_ipc(self, peer_rank, bundle):
+        L.check(L.lib().gb_pf_async_attach_ipc(self.h, int(peer_rank), C.c_char_p(bundle)))
+
+    def attach_local(self, peer_rank, peer_ops):
+        L.check(L.lib().gb_pf_async_attach_local(self.h, int(peer_rank), peer_ops.h))
+
+    def async_cur(self):
+        v = C.c_int()
+        L.check(L.lib().gb_pf_async_cur(self.h, C.byref(v)))
+        return v.value
+
+    def async_setup(self, world, rank, offs, ess_threshold):
         o = np.ascontiguousarray(offs, dtype=np.int64)
-        bb = C.c_int64()
-        L.check(L.lib().gb_pf_async_setup(self.h, world, rank, o.ctypes.data_as(L.i64p), int(cap_rows), float(ess_threshold), C.byref(bb)))
-        return bb.value
+        L.check(L.lib().gb_pf_async_setup(self.h, world, rank, o.ctypes.data_as(L.i64p), float(ess_threshold)))
 
     def async_plan(self, gathered, u0):
         L.check(L.lib().gb_pf_async_plan(self.h, C.c_void_p(gathered.data_ptr()), int(u0)))
@@ -143,11 +159,8 @@ class ShardOps:
     def async_sweep(self):
         L.check(L.lib().gb_pf_async_sweep(self.h))
 
-    def async_export(self, sendbuf):
-        L.check(L.lib().gb_pf_async_export(self.h, C.c_void_p(sendbuf.data_ptr())))
-
-    def async_import(self, recvbuf):
-        L.check(L.lib().gb_pf_async_import(self.h, C.c_void_p(recvbuf.data_ptr())))
+    def async_export(self):
+        L.check(L.lib().gb_pf_async_export(self.h))
 
     def async_step(self, obs):
         o = api._flatten_obs(obs)
@@ -192,6 +205,8 @@ class ShardedParticleFilter:
         self.last_ess = None
         self._stats_t = None        # device-resident statistics record (CUDA shards)
         self._gather_t = None
+        self._barrier_t = None
+        self._peers_attached = False
         self._bufs = {}
         # extension-row capacity of every shard (same formula on every rank: no collective needed)
         self.ext_caps = None
@@ -260,26 +275,29 @@ class ShardedParticleFilter:
         self.step += 1
         return out
 
-    def run_(self, observations_seq, ess_threshold=None, cap_rows=None):
+    def run_(self, observations_seq, ess_threshold=None):
         """T x { maybe_resample!; particle_filter_step! } over the sharded filter WITHOUT any host round trip: the
         statistics record is all-reduced / all-gathered on the device, the exchange plan, the ESS test and the log-ML
-        update run in a device kernel, the offspring travel in fixed-capacity blocks by an equal-split all-to-all.
-        Same results as the synchronous path (bit for bit) as long as no capacity overflows (else GenB200Error).
-        Returns the number of resamples."""
+        update run in a device kernel, and offspring owned by another shard are written straight into that shard's memory
+        over NVLink (CUDA IPC peer pointers), followed by a one-word all-reduce as the barrier.  Same results as the
+        synchronous path bit for bit, as long as no shard receives more rows than its extension rows hold (25 % of the
+        shard; otherwise GenB200Error and the synchronous staged path must be used).  Returns the number of resamples."""
         torch, dist, W = self.torch, self.dist, self.world
         thr = self.n_global / 2 if ess_threshold is None else float(ess_threshold)
-        # rows per fixed-size peer block: the spill between neighbouring shards is O(CV * sqrt(N_local)) rows for
-        # non-degenerate weights; 1/256 of the shard (at least 4096, at most 262144 rows) leaves a wide margin
-        cap = int(cap_rows) if cap_rows else min(max(4096, self.n_local // 256), 262144)
-        bb = self.ops.async_setup(W, self.rank, self.offs, cap, thr)
+        if not self._peers_attached and W > 1:
+            bundles = [None] * W
+            dist.all_gather_object(bundles, (self.ops.ipc_bundle(), self.ops.async_cur()), group=self.group)
+            assert len({b[1] for b in bundles}) == 1, "trace buffers of the shards are out of lock step"
+            for r, (bundle, _) in enumerate(bundles):
+                if r != self.rank:
+                    self.ops.attach_ipc(r, bundle)
+            self._peers_attached = True
+        self.ops.async_setup(W, self.rank, self.offs, thr)
         if self._stats_t is None:
             self._stats_t = self.ops.stats_tensor(torch)
             self._gather_t = torch.empty(W * self._stats_t.numel(), dtype=torch.int64, device=self.device)
-        key = ("async", bb)
-        if key not in self._bufs:
-            self._bufs[key] = (torch.zeros(W * bb, dtype=torch.uint8, device=self.device),
-                               torch.zeros(W * bb, dtype=torch.uint8, device=self.device))
-        sendbuf, recvbuf = self._bufs[key]
+        if self._barrier_t is None:
+            self._barrier_t = torch.zeros(1, dtype=torch.int32, device=self.device)
         m_view = self._stats_t[0:1].view(torch.float64)
         for obs in observations_seq:
             self.ops.weight_max_device()
@@ -293,9 +311,8 @@ class ShardedParticleFilter:
             self.ops.async_plan(self._gather_t, api.philox_resample_u0(self.seed, self.step))
             self.ops.async_sweep()
             if W > 1:
-                self.ops.async_export(sendbuf)
-                dist.all_to_all_single(recvbuf, sendbuf, group=self.group)
-                self.ops.async_import(recvbuf)
+                self.ops.async_export()                                   # peer stores over NVLink
+                dist.all_reduce(self._barrier_t, group=self.group)      # barrier: remote rows landed before the step reads them
             self.ops.async_step(obs)
             self.step += 1
         nres = self.ops.async_finish()

@@ -137,21 +137,27 @@ int gb_pf_weight_sums(gb_pf_t *pf, double m_ref, int bits, double *s1, double *s
 int gb_pf_stats_device(gb_pf_t *pf, void **dev_stats, int *n_words);
 int gb_pf_weight_max_device(gb_pf_t *pf);
 int gb_pf_weight_sums_device(gb_pf_t *pf, int bits);
-/* Asynchronous flavour of the whole sharded step (no host round trip; used by ShardedParticleFilter.run_):
- *   setup  : shard offsets (world+1), rows per fixed-size peer block, ESS threshold; returns the peer block size
+/* Asynchronous flavour of the whole sharded step (no host round trip; used by ShardedParticleFilter.run_).
+ * Offspring owned by another shard are written by a kernel STRAIGHT INTO THAT SHARD'S MEMORY (peer stores over NVLink):
+ * rows into the extension rows of its current trace buffer, plus the slot's ancestor index and global parent id.
+ *   once   : gb_pf_ipc_export -> all-gather of the bundles -> gb_pf_async_attach_ipc for every peer
+ *            (gb_pf_async_attach_local when the peer shard lives in the same process) -> gb_pf_async_setup
  *   per step (all asynchronous on the handle's stream; the host issues the collectives in between):
  *     gb_pf_weight_max_device -> all-reduce(max) of the statistics record's m -> gb_pf_weight_sums_device ->
- *     all-gather of the records -> gb_pf_async_plan (decision, log-ML, exchange plan ON THE DEVICE) ->
- *     gb_pf_async_sweep (ancestors) -> gb_pf_async_export -> equal-split all-to-all of world blocks ->
- *     gb_pf_async_import -> gb_pf_async_step
- *   finish : one device->host read (log_ml_est, #resamples, overflow flag).  Overflow (a peer block, the extension
- *            rows or the spill buffer too small for the weight skew) invalidates the run: GB_ESTATE. */
-int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t *offs, int64_t cap_rows, double ess_threshold,
-                      int64_t *peer_block_bytes_out);
+ *     all-gather of the records -> gb_pf_async_plan (ESS test, log-ML, exchange plan ON THE DEVICE) ->
+ *     gb_pf_async_sweep (ancestors) -> gb_pf_async_export (peer stores) -> any tiny collective as a barrier ->
+ *     gb_pf_async_step
+ *   finish : one device->host read (log_ml_est, #resamples, overflow flag).  Overflow (a shard's extension rows or the
+ *            spill buffer too small for the weight skew) invalidates the run: GB_ESTATE. */
+int gb_pf_ipc_bundle_bytes(void);
+int gb_pf_ipc_export(gb_pf_t *pf, void *bundle_out, int *nbytes);
+int gb_pf_async_attach_ipc(gb_pf_t *pf, int peer_rank, const void *bundle);
+int gb_pf_async_attach_local(gb_pf_t *pf, int peer_rank, gb_pf_t *peer);
+int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t *offs, double ess_threshold);
+int gb_pf_async_cur(const gb_pf_t *pf, int *cur);
 int gb_pf_async_plan(gb_pf_t *pf, const void *dev_gathered, uint32_t u0);
 int gb_pf_async_sweep(gb_pf_t *pf);
-int gb_pf_async_export(gb_pf_t *pf, void *dev_sendbuf);
-int gb_pf_async_import(gb_pf_t *pf, const void *dev_recvbuf);
+int gb_pf_async_export(gb_pf_t *pf);
 int gb_pf_async_step(gb_pf_t *pf, const double *obs, int nobs);
 int gb_pf_async_finish(gb_pf_t *pf, int *n_resampled, int *overflow);
 /* Offspring of this shard's particles under global-prefix systematic resampling: the shard's particles

@@ -124,9 +124,10 @@ def test_sharded_class_world1(g, O):
     assert abs(spf.log_ml_estimate() - g.log_ml_estimate(st)) < 1e-10
 
 
-def run_async_in_process(g, model, n, K, ys, seed, thr, cap_rows):
-    """K shards in one process driven through the ASYNCHRONOUS sharded entries; the host plays the three collectives
-    with device copies (no host round trip otherwise)."""
+def run_async_in_process(g, model, n, K, ys, seed, thr):
+    """K shards in one process driven through the ASYNCHRONOUS sharded entries: the host plays the two small
+    collectives with device copies; offspring go shard-to-shard by the export kernel's peer stores (here: pointers of
+    the other handles in the same process)."""
     import torch
     from genb200 import sharded, _lib as L
     counts, offs = sharded.shard_bounds(n, K)
@@ -135,11 +136,13 @@ def run_async_in_process(g, model, n, K, ys, seed, thr, cap_rows):
     ops = [sharded.ShardOps(s) for s in shards]
     for s in shards:
         g.generate_(s, ys[0])
-    bb = [o.async_setup(K, r, offs, cap_rows, thr) for r, o in enumerate(ops)][0]
+    for r, o in enumerate(ops):
+        for d, p in enumerate(ops):
+            if d != r:
+                o.attach_local(d, p)
+        o.async_setup(K, r, offs, thr)
     stats = [o.stats_tensor(torch) for o in ops]
     gathered = torch.empty(K * stats[0].numel(), dtype=torch.int64, device="cuda")
-    send = [torch.zeros(K * bb, dtype=torch.uint8, device="cuda") for _ in range(K)]
-    recv = [torch.zeros(K * bb, dtype=torch.uint8, device="cuda") for _ in range(K)]
     for t in range(1, len(ys)):
         for o in ops:
             o.weight_max_device()
@@ -153,13 +156,9 @@ def run_async_in_process(g, model, n, K, ys, seed, thr, cap_rows):
         for o in ops:
             o.async_plan(gathered, u0)
             o.async_sweep()
-        for r, o in enumerate(ops):
-            o.async_export(send[r])
-        for r in range(K):                                                              # equal-split all-to-all
-            for d in range(K):
-                recv[d][r * bb:(r + 1) * bb] = send[r][d * bb:(d + 1) * bb]
-        for r, o in enumerate(ops):
-            o.async_import(recv[r])
+        for o in ops:
+            o.async_export()                                                            # peer stores
+        for o in ops:                                                                   # (barrier: same stream here)
             o.async_step(ys[t])
     nres = [o.async_finish() for o in ops]
     assert len(set(nres)) == 1
@@ -176,7 +175,7 @@ def test_async_sharded_run_equals_single_gpu(g, K):
     for thr in (n / 2, n + 1):
         ref = g.initialize_particle_filter(model, (0,), ys[0], n, seed=seed)
         nres_ref = g.particle_filter_run_(ref, ys[1:], ess_threshold=thr)
-        cols, lw, par, lml, nres = run_async_in_process(g, model, n, K, ys, seed, thr, cap_rows=8192)
+        cols, lw, par, lml, nres = run_async_in_process(g, model, n, K, ys, seed, thr)
         assert nres == nres_ref
         for f in range(4):
             assert np.array_equal(cols[f], ref.get_state(f))
@@ -185,7 +184,36 @@ def test_async_sharded_run_equals_single_gpu(g, K):
 
 
 def test_async_sharded_overflow_is_reported(g):
-    """Fixed-capacity blocks too small for the weight skew: the run must fail loudly, never silently."""
-    model, ys = g.bearings_model(), F.bearings_series(4)
+    """A shard that would receive more rows than its extension rows hold (here: all the weight sits in shard 0) must make
+    the asynchronous run fail loudly, never silently."""
+    import torch
+    from genb200 import sharded, _lib as L
+    model, ys = g.lgssm_model(**F.LGSSM), F.lgssm_series(3)
+    n, K = 40000, 2
+    counts, offs = sharded.shard_bounds(n, K)
+    shards = [g.create_particle_filter(model, counts[r], seed=1, n_global=n, pid_offset=offs[r]) for r in range(K)]
+    ops = [sharded.ShardOps(s) for s in shards]
+    for s in shards:
+        g.generate_(s, ys[0])
+    shards[1].log_weights = np.full(counts[1], -800.0)            # shard 1 has no weight: all its slots come from shard 0
+    for r, o in enumerate(ops):
+        o.attach_local(1 - r, ops[1 - r])
+        o.async_setup(K, r, offs, n + 1)
+    stats = [o.stats_tensor(torch) for o in ops]
+    for o in ops:
+        o.weight_max_device()
+    m = torch.stack([st[0:1].view(torch.float64) for st in stats]).max()
+    for st in stats:
+        st[0:1].view(torch.float64).fill_(m)
+    for o in ops:
+        o.weight_sums_device(L.lib().gb_quant_bits(n))
+    gathered = torch.cat(stats).clone()
+    for o in ops:
+        o.async_plan(gathered, 7)
+        o.async_sweep()
+    for o in ops:
+        o.async_export()
+    for o in ops:
+        o.async_step(ys[1])
     with pytest.raises(g.GenB200Error):
-        run_async_in_process(g, model, 60013, 2, ys, 5, 60014, cap_rows=1)
+        ops[0].async_finish()

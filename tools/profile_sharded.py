@@ -21,6 +21,10 @@ L.check(L.lib().gb_set_device(lr))
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
 zs = F.bearings_series(40)
 spf = sharded.ShardedParticleFilter(g.bearings_model(), n, seed=1).initialize(zs[0])
+if len(sys.argv) > 2 and sys.argv[2] == "async_first":
+    spf.run_([zs[t] for t in range(1, 4)], ess_threshold=n + 1)
+    for t in range(4, 7):
+        spf.particle_filter_step_((t,), zs[t])
 marks = {}
 
 
@@ -38,7 +42,7 @@ def wrap(obj, name):
 
 
 for nm in ("weight_max_device", "weight_sums_device", "systematic_offspring", "export_offspring", "import_ext", "commit_lazy",
-           "offspring_local", "block_bytes"):
+           "offspring_local"):
     wrap(spf.ops, nm)
 wrap(spf, "_all_to_all_v")
 wrap(spf, "_global_stats")
