@@ -174,6 +174,7 @@ struct gb_pf {
   std::vector<int *> hist_anc;      // [t] -> ancestors applied BEFORE step t (nullptr: no resample)
   RunCtl *d_ctl = nullptr, *h_ctl = nullptr;   // fused multi-step run (gb_pf_run) / asynchronous sharded run
   ShardPlanDev *d_shplan = nullptr, *h_shplan = nullptr;
+  std::vector<void *> ipc_opened;   // peer allocations mapped through CUDA IPC (closed with the handle)
   long long *d_offs = nullptr;
   int a_world = 0, a_rank = 0;
   long long a_cap = 0;
@@ -263,6 +264,7 @@ static void pf_release(gb_pf *pf) {
   cudaFree(pf->d_ctl); cudaFreeHost(pf->h_ctl); cudaFree(pf->d_shplan); cudaFreeHost(pf->h_shplan); cudaFree(pf->d_offs); cudaFree(pf->super_q); cudaFree(pf->super_excl); cudaFree(pf->oflow); cudaFree(pf->oflow_count);
   cudaFree(pf->tile_q); cudaFree(pf->tile_c); cudaFree(pf->tile_r); cudaFree(pf->tile_slot); cudaFree(pf->d_plan);
   cudaFreeHost(pf->h_plan); cudaFree(pf->cdf); cudaFree(pf->off_anc); cudaFree(pf->d_tab); cudaFree(pf->d_ptab);
+  for (auto p : pf->ipc_opened) cudaIpcCloseMemHandle(p);
   for (auto p : pf->hist_state) cudaFree(p);
   for (auto p : pf->hist_anc) cudaFree(p);
   for (auto &t : pf->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -603,7 +605,8 @@ extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, 
   pf->tiles_valid = false;
   pf->nn_set = pf->nu_set = 0;
   if (pf->history) {
-    for (auto p : pf->hist_state) cudaFree(p);
+    for (auto p : pf->ipc_opened) cudaIpcCloseMemHandle(p);
+  for (auto p : pf->hist_state) cudaFree(p);
     for (auto p : pf->hist_anc) cudaFree(p);
     pf->hist_state.clear(); pf->hist_anc.clear();
     if ((rc = history_record(pf, false))) return rc;
@@ -1249,7 +1252,10 @@ extern "C" int gb_pf_async_attach_ipc(gb_pf_t *pf, int peer_rank, const void *bu
   memcpy(&b, bundle, sizeof(b));
   PeerMem &pm = pf->h_shplan->peer[peer_rank];
   void *p[4] = {nullptr, nullptr, nullptr, nullptr};
-  for (int k = 0; k < 4; k++) CK(cudaIpcOpenMemHandle(&p[k], b.h[k], cudaIpcMemLazyEnablePeerAccess));
+  for (int k = 0; k < 4; k++) {
+    CK(cudaIpcOpenMemHandle(&p[k], b.h[k], cudaIpcMemLazyEnablePeerAccess));
+    pf->ipc_opened.push_back(p[k]);
+  }
   pm.state[0] = p[0]; pm.state[1] = p[1]; pm.anc = (int *)p[2]; pm.ext_parents = (long long *)p[3];
   pm.ld = b.ld; pm.n_pad = b.n_pad; pm.ext_cap = b.ext_cap;
   return GB_OK;

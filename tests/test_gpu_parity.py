@@ -321,10 +321,12 @@ def test_pf_fp32_mode(g, O, name):
         st.set_noise(eps)
         incr, = g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t])
         incr_ref = ref.step([ys[t]], normals=eps)
-        # per-particle weights: fp32 state error is amplified by the likelihood's curvature
+        # per-particle weights: fp32 state / atan2f error is amplified by the likelihood's curvature (1/sigma = 200
+        # for the bearings model: measured 1.1e-4 there, 7e-7 for SV); the 1e-5 bar applies to the log-ML above
         assert np.max(np.abs(incr - incr_ref) / np.maximum(1.0, np.abs(incr_ref))) < 2e-3
         lml, lml_ref = g.log_ml_estimate(st), ref.log_ml_estimate()
-        assert abs(lml - lml_ref) <= RTOL32 * max(1.0, abs(lml_ref)) * 10
+        # north_star: log-ML within 1e-5 relative in fp32 (measured worst case: 1.9e-6, bearings; tools/fp32_check.py)
+        assert abs(lml - lml_ref) <= RTOL32 * max(1.0, abs(lml_ref))
         # resync the oracle's state so errors do not compound through the nonlinear dynamics
         for f in range(model.state_dim):
             s = st.get_state(f)
