@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GENB200_LIB") or os.path.join(_HERE, "libgenb200.so")
 
 OK, EINVAL, ENOGPU, ECUDA, EUNSUPPORTED, ESTATE = range(6)
-MODEL_LGSSM, MODEL_SV, MODEL_BEARINGS, MODEL_HMM, MODEL_BLR = 1, 2, 3, 4, 5
+MODEL_LGSSM, MODEL_SV, MODEL_BEARINGS, MODEL_HMM, MODEL_BLR, MODEL_SPEC = 1, 2, 3, 4, 5, 6
 PROPOSAL_DEFAULT, PROPOSAL_AFFINE_NORMAL, PROPOSAL_CATEGORICAL_TABLE = 0, 1, 2
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL = 0, 1, 2
 F64, F32 = 0, 1

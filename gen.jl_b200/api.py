@@ -114,6 +114,89 @@ def blr_model(X, sigma):
     return DeviceModel(L.MODEL_BLR, np.concatenate([[D, n, sigma], X.ravel()]), "blr")
 
 
+class SpecProgram:
+    """Builder of one SSA program of a GB_MODEL_SPEC model (include/genb200.h).  Methods return register numbers."""
+    _CODES = dict(add=10, sub=11, mul=12, div=13, atan2=18)
+    _UNARY = dict(neg=14, sqrt=15, exp=16, log=17, abs=19)
+
+    def __init__(self):
+        self.ops = []
+        self.nreg = 0
+
+    def _new(self):
+        r = self.nreg
+        self.nreg += 1
+        if r >= 32:
+            raise ValueError("a spec program may use at most 32 registers")
+        return r
+
+    def _emit(self, code, dst, a=0, b=0, imm=0.0):
+        self.ops.append((code, dst, a, b, float(imm)))
+        return dst
+
+    def const(self, v):
+        return self._emit(0, self._new(), imm=v)
+
+    def prev(self, field):
+        return self._emit(1, self._new(), field)
+
+    def param(self, idx):
+        return self._emit(2, self._new(), idx)
+
+    def obs(self, idx=0):
+        return self._emit(3, self._new(), idx)
+
+    def time(self):
+        return self._emit(4, self._new())
+
+    def __getattr__(self, name):
+        if name in SpecProgram._CODES:
+            return lambda a, b: self._emit(SpecProgram._CODES[name], self._new(), a, b)
+        if name in SpecProgram._UNARY:
+            return lambda a: self._emit(SpecProgram._UNARY[name], self._new(), a)
+        raise AttributeError(name)
+
+    def sample_normal(self, mu, std):
+        return self._emit(20, self._new(), mu, std)
+
+    def observe_normal(self, x, mu, std):
+        self._emit(21, x, mu, std)
+
+    def sample_bernoulli(self, p):
+        return self._emit(22, self._new(), p)
+
+    def observe_bernoulli(self, x, p):
+        self._emit(23, x, p)
+
+    def sample_gamma(self, shape, scale):
+        return self._emit(24, self._new(), shape, scale)
+
+    def observe_gamma(self, x, shape, scale):
+        self._emit(25, x, shape, scale)
+
+    def sample_categorical(self, offset_reg, length):
+        return self._emit(26, self._new(), offset_reg, int(length))
+
+    def observe_categorical(self, x, offset_reg, length):
+        self._emit(27, x, offset_reg, int(length))
+
+    def store(self, field, reg):
+        self._emit(30, field, reg)
+
+
+def spec_model(state_dim, params, num_obs, generate_program, step_program=None, name="spec"):
+    """A model of the supported class from its declarative specification: `generate_program` is the static-IR
+    function at t = 0, `step_program` the Unfold kernel (extend-by-one update)."""
+    params = np.asarray(params, dtype=np.float64).reshape(-1)
+    gops = list(generate_program.ops)
+    sops = list(step_program.ops) if step_program is not None else []
+    flat = [float(state_dim), float(params.size), float(num_obs), float(len(gops)), float(len(sops))]
+    flat += list(params)
+    for op in gops + sops:
+        flat += [float(v) for v in op]
+    return DeviceModel(L.MODEL_SPEC, flat, name)
+
+
 class AffineNormalProposal:
     """x ~ normal(c0 + c1 * x_prev, std): proposal_args = (c0, c1, std)."""
     kind = L.PROPOSAL_AFFINE_NORMAL

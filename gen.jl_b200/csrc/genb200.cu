@@ -7,6 +7,7 @@
 #include "../../include/genb200.h"
 #include "gbmath.cuh"
 #include "kernels_resample.cuh"
+#include "kernels_spec.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -69,13 +70,21 @@ struct gb_model {
   int kind = 0;
   std::vector<double> params;
   int S = 0, nobs = 1, K = 0, M = 0, D = 0;
+  // GB_MODEL_SPEC: parsed program
+  std::vector<SpecOp> ops;
+  std::vector<double> spec_params;
+  int n_init_ops = 0, n_step_ops = 0;
+  int nn[2] = {0, 0}, nu[2] = {0, 0};   // normal / uniform draws of the step [0] and generate [1] programs
+  long long spec_id = 0;
 };
+static long long g_spec_next_id = 1, g_spec_loaded = 0;
 
 static int model_state_dim(int kind, const double *p) {
   switch (kind) {
     case MODEL_LGSSM: case MODEL_SV: case MODEL_HMM: return 1;
     case MODEL_BEARINGS: return 4;
     case MODEL_BLR: return (int)p[0];
+    case MODEL_SPEC: return (int)p[0];
   }
   return -1;
 }
@@ -112,6 +121,15 @@ extern "C" int gb_model_create(int kind, const double *params, int nparams, gb_m
       need = 3 + n * D;
       break;
     }
+    case MODEL_SPEC: {
+      REQ(nparams >= 5, "SPEC params: [S, n_params, n_obs, n_init_ops, n_step_ops, params..., ops (code, dst, a, b, imm)...]");
+      const int S = (int)params[0], np_ = (int)params[1], no = (int)params[2], ni = (int)params[3], ns = (int)params[4];
+      if (!(S >= 1 && S <= kSpecMaxState && np_ >= 0 && np_ <= kSpecMaxParams && no >= 1 && no <= 64 && ni >= 1 && ns >= 0 &&
+            ni + ns <= kSpecMaxOps))
+        return fail(GB_EUNSUPPORTED, "SPEC: limits are 16 state fields, 2048 parameters, 64 observations, 256 ops");
+      need = 5 + np_ + 5 * (ni + ns);
+      break;
+    }
     default:
       return fail(GB_EUNSUPPORTED, "gb_model_create: model kind outside the supported class");
   }
@@ -119,6 +137,46 @@ extern "C" int gb_model_create(int kind, const double *params, int nparams, gb_m
   gb_model *m = new gb_model;
   m->kind = kind;
   m->params.assign(params, params + nparams);
+  if (kind == MODEL_SPEC) {
+    const int np_ = (int)params[1], ni = (int)params[3], ns = (int)params[4];
+    m->nobs = (int)params[2];
+    m->n_init_ops = ni; m->n_step_ops = ns;
+    m->spec_params.assign(params + 5, params + 5 + np_);
+    const double *q = params + 5 + np_;
+    int stored[2][kSpecMaxState] = {{0}};
+    const int S = (int)params[0];
+    for (int k = 0; k < ni + ns; k++, q += 5) {
+      SpecOp op{(int)q[0], (int)q[1], (int)q[2], (int)q[3], q[4]};
+      const int prog = k < ni ? 1 : 0;   // 1 = generate, 0 = step
+      bool ok = op.dst >= 0 && op.dst < kSpecRegs;
+      auto reg = [](int r) { return r >= 0 && r < kSpecRegs; };
+      switch (op.code) {
+        case OP_CONST: case OP_TIME: break;
+        case OP_PREV: ok = ok && op.a >= 0 && op.a < S && prog == 0; break;
+        case OP_PARAM: ok = ok && op.a >= 0 && op.a < np_; break;
+        case OP_OBS: ok = ok && op.a >= 0 && op.a < m->nobs; break;
+        case OP_ADD: case OP_SUB: case OP_MUL: case OP_DIV: case OP_ATAN2: ok = ok && reg(op.a) && reg(op.b); break;
+        case OP_NEG: case OP_SQRT: case OP_EXP: case OP_LOG: case OP_ABS: ok = ok && reg(op.a); break;
+        case OP_SAMPLE_NORMAL: ok = ok && reg(op.a) && reg(op.b); m->nn[prog]++; break;
+        case OP_OBSERVE_NORMAL: case OP_OBSERVE_GAMMA: ok = ok && reg(op.a) && reg(op.b); break;
+        case OP_SAMPLE_GAMMA: ok = ok && reg(op.a) && reg(op.b); break;
+        case OP_SAMPLE_BERNOULLI: ok = ok && reg(op.a); m->nu[prog]++; break;
+        case OP_OBSERVE_BERNOULLI: ok = ok && reg(op.a); break;
+        case OP_SAMPLE_CATEGORICAL: ok = ok && reg(op.a) && op.b >= 1 && op.b <= np_; m->nu[prog]++; break;
+        case OP_OBSERVE_CATEGORICAL: ok = ok && reg(op.a) && op.b >= 1 && op.b <= np_; break;
+        case OP_STORE: ok = op.dst >= 0 && op.dst < S && reg(op.a); if (ok) stored[prog][op.dst]++; break;
+        default: ok = false;
+      }
+      if (!ok) { delete m; return fail(GB_EINVAL, "SPEC: malformed op #" + std::to_string(k)); }
+      m->ops.push_back(op);
+    }
+    for (int f = 0; f < S; f++)
+      if (stored[1][f] != 1 || (ns > 0 && stored[0][f] != 1)) {
+        delete m;
+        return fail(GB_EINVAL, "SPEC: every state field must be stored exactly once by the generate program and by the step program");
+      }
+    m->spec_id = g_spec_next_id++;
+  }
   m->S = model_state_dim(kind, params);
   if (kind == MODEL_HMM) { m->K = (int)params[0]; m->M = (int)params[1]; }
   if (kind == MODEL_BLR) { m->D = (int)params[0]; m->nobs = (int)params[1]; }
@@ -129,9 +187,13 @@ extern "C" void gb_model_free(gb_model_t *m) { delete m; }
 extern "C" int gb_model_state_dim(const gb_model_t *m) { return m ? m->S : -1; }
 extern "C" int gb_model_num_obs(const gb_model_t *m) { return m ? m->nobs : -1; }
 extern "C" int gb_model_num_normals(const gb_model_t *m, int, int is_init) {
+  if (m && m->kind == MODEL_SPEC) return m->nn[is_init ? 1 : 0];
   return m ? model_num_normals(m->kind, m->params.data(), is_init) : -1;
 }
-extern "C" int gb_model_num_uniforms(const gb_model_t *m, int, int) { return m ? model_num_uniforms(m->kind) : -1; }
+extern "C" int gb_model_num_uniforms(const gb_model_t *m, int, int is_init) {
+  if (m && m->kind == MODEL_SPEC) return m->nu[is_init ? 1 : 0];
+  return m ? model_num_uniforms(m->kind) : -1;
+}
 
 // ------------------------------------------------------------------------------------------
 // particle store
@@ -506,6 +568,7 @@ static int fill_model_params(gb_pf *pf, ModelParams &mp, const double *obs, int 
 static int check_noise(gb_pf *pf, bool init, bool *predrawn) {
   const gb_model &m = pf->model;
   int nn = model_num_normals(m.kind, m.params.data(), init), nu = model_num_uniforms(m.kind);
+  if (m.kind == MODEL_SPEC) { nn = m.nn[init ? 1 : 0]; nu = m.nu[init ? 1 : 0]; }
   *predrawn = (pf->nn_set > 0 || pf->nu_set > 0);
   if (*predrawn) {
     REQ(pf->nn_set >= nn && pf->nu_set >= nu, "gb_pf_set_noise: fewer pre-drawn rows than this call consumes");
@@ -514,6 +577,73 @@ static int check_noise(gb_pf *pf, bool init, bool *predrawn) {
 }
 
 static int blr_generate(gb_pf *pf, const double *obs, int nobs, bool predrawn);
+
+// GB_MODEL_SPEC: program + parameters into constant memory (once per model), observations per call
+template <typename R, bool INIT>
+static int launch_spec(gb_pf *pf, const double *obs, int nobs, bool predrawn, int gather) {
+  const gb_model &m = pf->model;
+  if (g_spec_loaded != m.spec_id) {
+    CK(cudaMemcpyToSymbolAsync(c_spec_ops, m.ops.data(), m.ops.size() * sizeof(SpecOp), 0, cudaMemcpyHostToDevice, pf->stream));
+    if (!m.spec_params.empty())
+      CK(cudaMemcpyToSymbolAsync(c_spec_params, m.spec_params.data(), m.spec_params.size() * 8, 0, cudaMemcpyHostToDevice, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    g_spec_loaded = m.spec_id;
+  }
+  double ob[64];
+  for (int k = 0; k < nobs; k++) ob[k] = obs[k];
+  CK(cudaMemcpyToSymbolAsync(c_spec_obs, ob, (size_t)nobs * 8, 0, cudaMemcpyHostToDevice, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));   // `ob` lives on this stack frame
+  SpecArgs a;
+  memset(&a, 0, sizeof(a));
+  a.state_in = INIT ? nullptr : pf->state[pf->cur];
+  a.state_out = pf->state[pf->cur ^ 1];
+  a.logw = pf->logw; a.incr = pf->incr;
+  a.anc = pf->anc; a.ctl = pf->d_ctl;
+  a.normals = pf->d_normals; a.uniforms = pf->d_uniforms;
+  a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
+  a.seed = pf->seed; a.step = INIT ? 0u : (unsigned)(pf->step + 1);
+  a.op_begin = INIT ? 0 : m.n_init_ops;
+  a.op_end = INIT ? m.n_init_ops : m.n_init_ops + m.n_step_ops;
+  a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
+#define GO(PD, GA)                                                                         \
+  {                                                                                        \
+    auto kern = spec_kernel<R, INIT, PD, GA>;                                              \
+    int grid = grid_for(pf, kern, pf->n, kBlock);                                          \
+    LAUNCH(pf, GB_K_STEP, kern<<<grid, kBlock, 0, pf->stream>>>(a));                       \
+  }
+  if (INIT) { if (predrawn) GO(true, 0) else GO(false, 0) }
+  else if (predrawn) { if (gather) GO(true, 1) else GO(true, 0) }
+  else { if (gather == 2) GO(false, 2) else if (gather) GO(false, 1) else GO(false, 0) }
+#undef GO
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+
+// One `generate` (init) or extend-by-one `update` sweep over the shard for whatever model kind the handle holds.
+// gather: 0 direct input, 1 through the pending ancestors, 2 decided by the device (RunCtl).
+static int launch_model(gb_pf *pf, const double *obs, int nobs, int pk, const double *pargs, int npargs, bool init,
+                        bool predrawn, int gather) {
+  if (pf->model.kind == MODEL_SPEC) {
+    REQ(pk == PROPOSAL_DEFAULT, "SPEC models carry their proposal inside the program (default proposal only)");
+    REQ(init || pf->model.n_step_ops > 0, "this SPEC model has no step program");
+    if (pf->dtype == GB_F64) return init ? launch_spec<double, true>(pf, obs, nobs, predrawn, 0) : launch_spec<double, false>(pf, obs, nobs, predrawn, gather);
+    return init ? launch_spec<float, true>(pf, obs, nobs, predrawn, 0) : launch_spec<float, false>(pf, obs, nobs, predrawn, gather);
+  }
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = fill_model_params(pf, a.mp, obs, nobs, pk, pargs, npargs, init);
+  if (rc) return rc;
+  a.state_in = init ? nullptr : pf->state[pf->cur];
+  a.state_out = pf->state[pf->cur ^ 1];
+  a.logw = pf->logw; a.incr = pf->incr;
+  a.anc = pf->anc; a.ctl = pf->d_ctl;
+  a.normals = pf->d_normals; a.uniforms = pf->d_uniforms;
+  a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
+  a.seed = pf->seed; a.step = init ? 0u : (unsigned)(pf->step + 1);
+  a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
+  if (init) return pf->dtype == GB_F64 ? launch_step_k<double, true>(pf, a, pk, predrawn, 0) : launch_step_k<float, true>(pf, a, pk, predrawn, 0);
+  return pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, pk, predrawn, gather) : launch_step_k<float, false>(pf, a, pk, predrawn, gather);
+}
 
 // snapshot of the current trace columns (+ the ancestors that were applied on the way into this step)
 static int history_record(gb_pf *pf, bool resampled) {
@@ -585,19 +715,7 @@ extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, 
     REQ(pk == PROPOSAL_DEFAULT, "BLR supports the default proposal only");
     rc = blr_generate(pf, obs, nobs, predrawn);
   } else {
-    StepArgs a;
-    memset(&a, 0, sizeof(a));
-    rc = fill_model_params(pf, a.mp, obs, nobs, pk, pargs, npargs, true);
-    if (rc) return rc;
-    a.state_in = nullptr;
-    a.state_out = pf->state[pf->cur ^ 1];
-    a.logw = pf->logw; a.incr = pf->incr;
-    a.normals = pf->d_normals; a.uniforms = pf->d_uniforms;
-    a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
-    a.seed = pf->seed; a.step = 0;
-    a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
-    rc = pf->dtype == GB_F64 ? launch_step_k<double, true>(pf, a, pk, predrawn, 0)
-                             : launch_step_k<float, true>(pf, a, pk, predrawn, 0);
+    rc = launch_model(pf, obs, nobs, pk, pargs, npargs, true, predrawn, 0);
   }
   if (rc) return rc;
   pf->cur ^= 1;
@@ -633,21 +751,8 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
   bool predrawn;
   int rc = check_noise(pf, false, &predrawn);
   if (rc) return rc;
-  StepArgs a;
-  memset(&a, 0, sizeof(a));
-  rc = fill_model_params(pf, a.mp, obs, nobs, pk, pargs, npargs, false);
-  if (rc) return rc;
-  a.state_in = pf->state[pf->cur];
-  a.state_out = pf->state[pf->cur ^ 1];
-  a.logw = pf->logw; a.incr = pf->incr;
-  a.anc = pf->anc;
-  a.normals = pf->d_normals; a.uniforms = pf->d_uniforms;
-  a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
-  a.seed = pf->seed; a.step = (unsigned)(pf->step + 1);
-  a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
   const bool gather = pf->pending_gather;
-  rc = pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, pk, predrawn, gather ? 1 : 0)
-                           : launch_step_k<float, false>(pf, a, pk, predrawn, gather ? 1 : 0);
+  rc = launch_model(pf, obs, nobs, pk, pargs, npargs, false, predrawn, gather ? 1 : 0);
   if (rc) return rc;
   pf->step += 1;
   pf->cur ^= 1;                       // particle_filter.jl:203-205, :234-237 (swap traces/new_traces)
@@ -1148,19 +1253,7 @@ extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double
                              : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, u0, ao, pf->d_ctl);
     if (rc) return rc;
     // particle_filter_step!
-    StepArgs a;
-    memset(&a, 0, sizeof(a));
-    if ((rc = fill_model_params(pf, a.mp, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false))) return rc;
-    a.state_in = pf->state[pf->cur];
-    a.state_out = pf->state[pf->cur ^ 1];
-    a.logw = pf->logw; a.incr = pf->incr;
-    a.anc = pf->anc; a.ctl = pf->d_ctl;
-    a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
-    a.seed = pf->seed; a.step = (unsigned)(pf->step + 1);
-    a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
-    rc = pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, PROPOSAL_DEFAULT, false, 2)
-                             : launch_step_k<float, false>(pf, a, PROPOSAL_DEFAULT, false, 2);
-    if (rc) return rc;
+    if ((rc = launch_model(pf, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false, false, 2))) return rc;
     pf->step += 1;
     pf->cur ^= 1;
   }
@@ -1333,19 +1426,7 @@ extern "C" int gb_pf_async_export(gb_pf_t *pf) {
 extern "C" int gb_pf_async_step(gb_pf_t *pf, const double *obs, int nobs) {
   REQ(pf && obs && pf->a_world > 0, "gb_pf_async_step: bad argument");
   REQ(nobs == pf->model.nobs, "gb_pf_async_step: wrong number of observations");
-  StepArgs a;
-  memset(&a, 0, sizeof(a));
-  int rc = fill_model_params(pf, a.mp, obs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false);
-  if (rc) return rc;
-  a.state_in = pf->state[pf->cur];
-  a.state_out = pf->state[pf->cur ^ 1];
-  a.logw = pf->logw; a.incr = pf->incr;
-  a.anc = pf->anc; a.ctl = pf->d_ctl;
-  a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
-  a.seed = pf->seed; a.step = (unsigned)(pf->step + 1);
-  a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
-  rc = pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, PROPOSAL_DEFAULT, false, 2)
-                           : launch_step_k<float, false>(pf, a, PROPOSAL_DEFAULT, false, 2);
+  int rc = launch_model(pf, obs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false, false, 2);
   if (rc) return rc;
   pf->step += 1;
   pf->cur ^= 1;

@@ -11,7 +11,7 @@
 
 namespace gb {
 
-enum { MODEL_LGSSM = 1, MODEL_SV = 2, MODEL_BEARINGS = 3, MODEL_HMM = 4, MODEL_BLR = 5 };
+enum { MODEL_LGSSM = 1, MODEL_SV = 2, MODEL_BEARINGS = 3, MODEL_HMM = 4, MODEL_BLR = 5, MODEL_SPEC = 6 };
 enum { PROPOSAL_DEFAULT = 0, PROPOSAL_AFFINE_NORMAL = 1, PROPOSAL_CATEGORICAL_TABLE = 2 };
 
 struct ModelParams {

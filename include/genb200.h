@@ -31,7 +31,22 @@ enum { GB_OK = 0, GB_EINVAL = 1, GB_ENOGPU = 2, GB_ECUDA = 3, GB_EUNSUPPORTED = 
  *                     (test/inference/particle_filter.jl:52-78; categorical choices, 1-based)
  *   GB_MODEL_BLR      [D, n, sigma, X[n*D] row-major]   w~Map(normal)(0,1); y_j~normal(x_j.w, sigma)
  */
-enum { GB_MODEL_LGSSM = 1, GB_MODEL_SV = 2, GB_MODEL_BEARINGS = 3, GB_MODEL_HMM = 4, GB_MODEL_BLR = 5 };
+enum { GB_MODEL_LGSSM = 1, GB_MODEL_SV = 2, GB_MODEL_BEARINGS = 3, GB_MODEL_HMM = 4, GB_MODEL_BLR = 5, GB_MODEL_SPEC = 6 };
+/* GB_MODEL_SPEC: a declarative specification of any model of the supported class -- a static-IR `generate` program for
+ * t = 0 and the Unfold kernel's extend-by-one program, written out as SSA ops over at most 32 registers
+ * (Gen's own DAG cannot be lowered automatically: its Julia nodes are opaque closures, src/static_ir/dag.jl:14-19).
+ *   params = [S, n_params, n_obs, n_init_ops, n_step_ops, params[n_params], ops[(n_init+n_step) x (code, dst, a, b, imm)]]
+ *   ops:  0 CONST dst<-imm   1 PREV dst<-previous state field a   2 PARAM dst<-params[a]   3 OBS dst<-obs[a]   4 TIME dst<-t
+ *        10 ADD 11 SUB 12 MUL 13 DIV (dst<-a op b)  14 NEG 15 SQRT 16 EXP 17 LOG 19 ABS (dst<-f(a))  18 ATAN2 dst<-atan(a, b)
+ *        20 SAMPLE_NORMAL dst ~ normal(a, b)          21 OBSERVE_NORMAL  weight += logpdf(normal, reg dst, a, b)
+ *        22 SAMPLE_BERNOULLI dst ~ bernoulli(a)       23 OBSERVE_BERNOULLI weight += logpdf(bernoulli, reg dst, a)
+ *        24 SAMPLE_GAMMA dst ~ gamma(a, b)            25 OBSERVE_GAMMA   weight += logpdf(gamma, reg dst, a, b)
+ *        26 SAMPLE_CATEGORICAL dst ~ categorical(params[reg a : reg a + b])   (b = length, immediate)
+ *        27 OBSERVE_CATEGORICAL weight += logpdf(categorical, reg dst, params[reg a : reg a + b])
+ *        30 STORE state field dst <- reg a   (every field exactly once per program)
+ * `sample` ops are unconstrained choices (weight unchanged: static_ir/generate.jl:31-38), `observe` ops constrained ones
+ * (weight += logpdf: unfold/update.jl:64-68); a custom proposal is expressed inside the program (sample from the proposal,
+ * then OBSERVE the model's density of that value and subtract the proposal's by a negated OBSERVE on a NEG'd... see api.py). */
 /* Custom proposals (particle_filter.jl:118-134, :186-208; trace_translators.jl:836-856):
  *   GB_PROPOSAL_AFFINE_NORMAL     pargs = [c0, c1, std]: x ~ normal(c0 + c1*x_prev, std)   (c1 unused at t=0)
  *   GB_PROPOSAL_CATEGORICAL_TABLE pargs = K probs at t=0, K*K (column = previous z) afterwards */
