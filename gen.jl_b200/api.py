@@ -183,6 +183,12 @@ class SpecProgram:
     def store(self, field, reg):
         self._emit(30, field, reg)
 
+    def add_weight(self, reg):
+        self._emit(31, 0, reg)
+
+    def logpdf_normal(self, x, mu, std):
+        return self._emit(32, self._new(), mu, std, imm=x)
+
 
 def spec_model(state_dim, params, num_obs, generate_program, step_program=None, name="spec"):
     """A model of the supported class from its declarative specification: `generate_program` is the static-IR

@@ -165,6 +165,8 @@ extern "C" int gb_model_create(int kind, const double *params, int nparams, gb_m
         case OP_SAMPLE_CATEGORICAL: ok = ok && reg(op.a) && op.b >= 1 && op.b <= np_; m->nu[prog]++; break;
         case OP_OBSERVE_CATEGORICAL: ok = ok && reg(op.a) && op.b >= 1 && op.b <= np_; break;
         case OP_STORE: ok = op.dst >= 0 && op.dst < S && reg(op.a); if (ok) stored[prog][op.dst]++; break;
+        case OP_WEIGHT: ok = reg(op.a); break;
+        case OP_LOGPDF_NORMAL: ok = ok && reg(op.a) && reg(op.b) && reg((int)op.imm); break;
         default: ok = false;
       }
       if (!ok) { delete m; return fail(GB_EINVAL, "SPEC: malformed op #" + std::to_string(k)); }

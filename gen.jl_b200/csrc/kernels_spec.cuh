@@ -20,7 +20,7 @@ enum {
   OP_ABS = 19,
   OP_SAMPLE_NORMAL = 20, OP_OBSERVE_NORMAL = 21, OP_SAMPLE_BERNOULLI = 22, OP_OBSERVE_BERNOULLI = 23,
   OP_SAMPLE_GAMMA = 24, OP_OBSERVE_GAMMA = 25, OP_SAMPLE_CATEGORICAL = 26, OP_OBSERVE_CATEGORICAL = 27,
-  OP_STORE = 30
+  OP_STORE = 30, OP_WEIGHT = 31, OP_LOGPDF_NORMAL = 32
 };
 constexpr int kSpecMaxOps = 256, kSpecMaxParams = 2048, kSpecRegs = 32, kSpecMaxState = 16;
 
@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
           break;
         case OP_OBSERVE_GAMMA: w += logpdf_gamma<R>(regs[op.dst], regs[op.a], regs[op.b]); break;                 // gamma.jl:10-16
         case OP_STORE: st_stream(sout + (long long)op.dst * a.ld + i, regs[op.a]); break;
+        case OP_WEIGHT: w += regs[op.a]; break;                                     // e.g. minus a proposal score
+        case OP_LOGPDF_NORMAL: regs[op.dst] = logpdf_normal<R>(regs[(int)op.imm], regs[op.a], regs[op.b]); break;
         default: break;
       }
     }

@@ -44,9 +44,11 @@ enum { GB_MODEL_LGSSM = 1, GB_MODEL_SV = 2, GB_MODEL_BEARINGS = 3, GB_MODEL_HMM 
  *        26 SAMPLE_CATEGORICAL dst ~ categorical(params[reg a : reg a + b])   (b = length, immediate)
  *        27 OBSERVE_CATEGORICAL weight += logpdf(categorical, reg dst, params[reg a : reg a + b])
  *        30 STORE state field dst <- reg a   (every field exactly once per program)
+ *        31 WEIGHT weight += reg a              32 LOGPDF_NORMAL dst <- logpdf(normal, reg (int)imm, a, b)
  * `sample` ops are unconstrained choices (weight unchanged: static_ir/generate.jl:31-38), `observe` ops constrained ones
- * (weight += logpdf: unfold/update.jl:64-68); a custom proposal is expressed inside the program (sample from the proposal,
- * then OBSERVE the model's density of that value and subtract the proposal's by a negated OBSERVE on a NEG'd... see api.py). */
+ * (weight += logpdf: unfold/update.jl:64-68).  A custom proposal (particle_filter.jl:186-208, trace_translators.jl:854) is
+ * written inside the program: sample from the proposal, OBSERVE the model's density of the proposed value, and subtract
+ * the proposal's score (LOGPDF_NORMAL, NEG, WEIGHT). */
 /* Custom proposals (particle_filter.jl:118-134, :186-208; trace_translators.jl:836-856):
  *   GB_PROPOSAL_AFFINE_NORMAL     pargs = [c0, c1, std]: x ~ normal(c0 + c1*x_prev, std)   (c1 unused at t=0)
  *   GB_PROPOSAL_CATEGORICAL_TABLE pargs = K probs at t=0, K*K (column = previous z) afterwards */

@@ -749,3 +749,43 @@ def test_spec_model_outside_the_presets(g, O):
         bad.store(0, bad.const(1.0))
         bad.store(0, bad.const(2.0))
         g.spec_model(2, [], 1, bad)
+
+
+def test_spec_model_custom_proposal(g, O):
+    """A custom proposal written inside the spec (sample from q, observe the model density, subtract q's score) equals
+    the built-in LGSSM + AffineNormalProposal and the oracle's weight algebra (trace_translators.jl:854)."""
+    L_ = F.LGSSM
+    ys = F.lgssm_series(8)
+    n = 20001
+
+    def prog(t0):
+        p = g.SpecProgram()
+        c0, c1, qsd = p.param(5), p.param(6), p.param(7)
+        if t0:
+            mu, sd, qmu = p.param(0), p.param(1), c0
+        else:
+            px = p.prev(0)
+            mu, sd, qmu = p.mul(p.param(2), px), p.param(3), p.add(c0, p.mul(c1, px))
+        x = p.sample_normal(qmu, qsd)
+        lq = p.logpdf_normal(x, qmu, qsd)
+        p.observe_normal(x, mu, sd)
+        p.observe_normal(p.obs(0), x, p.param(4))
+        p.add_weight(p.neg(lq))
+        p.store(0, x)
+        return p
+    pa = (0.05, 0.7, 0.6)
+    spec = g.spec_model(1, [L_["m0"], L_["s0"], L_["a"], L_["q"], L_["r"], *pa], 1, prog(True), prog(False))
+    builtin = g.lgssm_model(**L_)
+    rng = np.random.default_rng(4)
+    a, b = g.create_particle_filter(builtin, n), g.create_particle_filter(spec, n)
+    eps = rng.standard_normal((1, n))
+    a.set_noise(eps); b.set_noise(eps)
+    g.generate_(a, ys[0], g.AffineNormalProposal(), pa)
+    g.generate_(b, ys[0])
+    assert np.array_equal(a.get_state(0), b.get_state(0)) and close(b.log_weights, a.log_weights, RTOL64)
+    for t in range(1, len(ys)):
+        eps = rng.standard_normal((1, n))
+        a.set_noise(eps); b.set_noise(eps)
+        ia, = g.particle_filter_step_(a, (t,), (g.UnknownChange,), ys[t], g.AffineNormalProposal(), pa)
+        ib, = g.particle_filter_step_(b, (t,), (g.UnknownChange,), ys[t])
+        assert np.array_equal(a.get_state(0), b.get_state(0)) and close(ib, ia, 1e-9)
