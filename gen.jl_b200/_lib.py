@@ -14,6 +14,7 @@ OK, EINVAL, ENOGPU, ECUDA, EUNSUPPORTED, ESTATE = range(6)
 MODEL_LGSSM, MODEL_SV, MODEL_BEARINGS, MODEL_HMM, MODEL_BLR, MODEL_SPEC = 1, 2, 3, 4, 5, 6
 PROPOSAL_DEFAULT, PROPOSAL_AFFINE_NORMAL, PROPOSAL_CATEGORICAL_TABLE = 0, 1, 2
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL = 0, 1, 2
+MH_RESIMULATE, MH_DRIFT = 0, 1
 F64, F32 = 0, 1
 DIST_NORMAL, DIST_GAMMA, DIST_BERNOULLI, DIST_CATEGORICAL, DIST_MVNORMAL = 1, 2, 3, 4, 5
 K_STEP, K_FINALIZE, K_QTOTAL, K_TILESCAN, K_ANCESTORS, K_GATHER, K_MISC, K_COUNT = range(8)
@@ -49,6 +50,7 @@ SIGNATURES = {
     "gb_pf_history_length": (i, [vp, ip]),
     "gb_pf_get_trajectory": (i, [vp, i, dp]),
     "gb_pf_sample_unweighted": (i, [vp, i64, u64, i64p, dp]),
+    "gb_pf_rejuvenate": (i, [vp, i, dp, i, d, i64p, dp]),
     "gb_pf_run": (i, [vp, i, dp, i, d, ip]),
     "gb_pf_set_resample_noise": (i, [vp, i, u32, u64p]),
     "gb_pf_log_ml_estimate": (i, [vp, dp]),

@@ -455,6 +455,22 @@ def maybe_resample_(state, ess_threshold=None, verbose=False, resampler=None):
     return bool(did.value)
 
 
+def rejuvenate_(state, observations, move="resimulate", drift_std=0.0, return_alpha=False):
+    """The tutorial's rejuvenation loop `for i in 1:N  state.traces[i], _ = mh(state.traces[i], ...)`
+    (docs/src/tutorials/smc.md:459-463, :518-520) for the moves the Markov store supports: on the latent choices of
+    the latest time step.  move = "resimulate": mh(trace, select(latest latents)) (mh.jl:16-27);
+    move = "drift": mh(trace, gaussian_drift_proposal, (drift_std,)) (mh.jl:37-58).  Call between
+    particle_filter_step_ and maybe_resample_; `observations` are the latest step's.
+    Returns the number of accepted moves (and the log acceptance ratios with return_alpha=True)."""
+    obs = _flatten_obs(observations)
+    mv = {"resimulate": L.MH_RESIMULATE, "drift": L.MH_DRIFT}[move]
+    acc = C.c_int64()
+    alpha = np.empty(state.num_particles, dtype=np.float64) if return_alpha else None
+    L.check(L.lib().gb_pf_rejuvenate(state._h, mv, obs.ctypes.data_as(L.dp), obs.size, float(drift_std), C.byref(acc),
+                                     None if alpha is None else alpha.ctypes.data_as(L.dp)))
+    return (acc.value, alpha) if return_alpha else acc.value
+
+
 def particle_filter_run_(state, observations_seq, ess_threshold=None):
     """T x { maybe_resample!(state, ess_threshold) [systematic]; particle_filter_step!(state, (t,), ..., obs_t) } in one
     call, without a host round trip per step (include/genb200.h gb_pf_run).  Returns the number of resamples."""

@@ -8,6 +8,7 @@
 #include "gbmath.cuh"
 #include "kernels_resample.cuh"
 #include "kernels_spec.cuh"
+#include "kernels_mh.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -225,6 +226,9 @@ struct gb_pf {
   bool anc_valid = false;
   bool pending_gather = false;    // resample decided, rows not moved yet (lazy gather)
   bool lazy = true;
+  bool mh_ok = false;             // state[cur ^ 1] still holds the parents of the current traces (MH rejuvenation)
+  bool mh_parent_anc = false;     // ... reached through `anc` (the last step gathered through it)
+  unsigned int mh_moves = 0;      // rejuvenation sweeps applied since the last step (Philox draw-index block)
   long long *parents64 = nullptr; // global 1-based parents (sharded path)
   bool parents64_valid = false;
   double log_ml_est = 0.0;
@@ -724,9 +728,9 @@ extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, 
   pf->wstate = W_MAX;
   pf->tiles_valid = false;
   pf->nn_set = pf->nu_set = 0;
+  pf->mh_ok = pf->model.kind != MODEL_BLR; pf->mh_parent_anc = false; pf->mh_moves = 0;
   if (pf->history) {
-    for (auto p : pf->ipc_opened) cudaIpcCloseMemHandle(p);
-  for (auto p : pf->hist_state) cudaFree(p);
+    for (auto p : pf->hist_state) cudaFree(p);
     for (auto p : pf->hist_anc) cudaFree(p);
     pf->hist_state.clear(); pf->hist_anc.clear();
     if ((rc = history_record(pf, false))) return rc;
@@ -762,6 +766,7 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
   pf->wstate = W_MAX;
   pf->tiles_valid = false;
   pf->nn_set = pf->nu_set = 0;
+  pf->mh_ok = true; pf->mh_parent_anc = gather; pf->mh_moves = 0;
   if (pf->history && (rc = history_record(pf, pf->hist_resampled))) return rc;
   pf->hist_resampled = false;
   if (incr_out) {
@@ -775,6 +780,97 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
       for (long long i = 0; i < pf->n; i++) incr_out[i] = tmp[i];
     }
   }
+  return GB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// MH rejuvenation of every particle's latest latent choices (kernels_mh.cuh; mh.jl:16-27, :37-58)
+// ------------------------------------------------------------------------------------------
+template <typename R, int KIND, bool INIT>
+static int launch_mh_t(gb_pf *pf, const MhArgs &a, int move, bool predrawn) {
+#define GO(MV, PD)                                                                  \
+  {                                                                                 \
+    auto kern = mh_kernel<R, KIND, INIT, MV, PD>;                                   \
+    int grid = grid_for(pf, kern, pf->n, kBlock);                                   \
+    LAUNCH(pf, GB_K_MISC, kern<<<grid, kBlock, 0, pf->stream>>>(a));                \
+  }
+  if (move == MH_RESIMULATE) { if (predrawn) GO(MH_RESIMULATE, true) else GO(MH_RESIMULATE, false) }
+  else { if (predrawn) GO(MH_DRIFT, true) else GO(MH_DRIFT, false) }
+#undef GO
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+template <typename R, bool INIT>
+static int launch_mh_k(gb_pf *pf, const MhArgs &a, int move, bool predrawn) {
+  switch (pf->model.kind) {
+    case MODEL_LGSSM: return launch_mh_t<R, MODEL_LGSSM, INIT>(pf, a, move, predrawn);
+    case MODEL_SV: return launch_mh_t<R, MODEL_SV, INIT>(pf, a, move, predrawn);
+    case MODEL_BEARINGS: return launch_mh_t<R, MODEL_BEARINGS, INIT>(pf, a, move, predrawn);
+    case MODEL_HMM: return launch_mh_t<R, MODEL_HMM, INIT>(pf, a, move, predrawn);
+  }
+  return fail(GB_EUNSUPPORTED, "gb_pf_rejuvenate: this model kind has no MH rejuvenation moves");
+}
+extern "C" int gb_pf_rejuvenate(gb_pf_t *pf, int move, const double *obs, int nobs, double drift_std, int64_t *n_accepted,
+                                double *alpha_out) {
+  REQ(pf, "null handle");
+  REQ(move == MH_RESIMULATE || move == MH_DRIFT, "gb_pf_rejuvenate: unknown move");
+  const int kind = pf->model.kind;
+  REQ(kind == MODEL_LGSSM || kind == MODEL_SV || kind == MODEL_BEARINGS || kind == MODEL_HMM,
+      "gb_pf_rejuvenate: this model kind has no MH rejuvenation moves");
+  if (move == MH_DRIFT) {
+    if (kind == MODEL_HMM) return fail(GB_EUNSUPPORTED, "gb_pf_rejuvenate: a Gaussian drift move needs continuous latent choices");
+    REQ(drift_std > 0.0, "gb_pf_rejuvenate: drift_std must be positive");
+  }
+  REQ(nobs == pf->model.nobs, "gb_pf_rejuvenate: wrong number of observations (pass the latest step's observations)");
+  if (!pf->mh_ok || pf->pending_gather)
+    return fail(GB_ESTATE, "gb_pf_rejuvenate: the parents of the current traces are no longer resident -- call it after "
+                           "initialize / particle_filter_step and before maybe_resample (docs/src/tutorials/smc.md:459-466)");
+  const bool init = pf->step == 0;
+  const int nn = move == MH_DRIFT ? (kind == MODEL_BEARINGS ? (init ? 4 : 2) : 1) : model_num_normals(kind, pf->model.params.data(), init);
+  const int nu = (move == MH_DRIFT ? 0 : model_num_uniforms(kind)) + 1;
+  const bool predrawn = pf->nn_set > 0 || pf->nu_set > 0;
+  if (predrawn) REQ(pf->nn_set >= nn && pf->nu_set >= nu, "gb_pf_set_noise: a move consumes the transition's normal rows (drift: one per "
+                                                          "latent choice) and its uniform rows plus ONE accept row");
+  MhArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = fill_model_params(pf, a.mp, obs, nobs, PROPOSAL_DEFAULT, nullptr, 0, init);
+  if (rc) return rc;
+  unsigned long long *d_acc = nullptr;
+  double *d_alpha = nullptr;
+  CK(cudaMalloc((void **)&d_acc, 8));
+  CK(cudaMemsetAsync(d_acc, 0, 8, pf->stream));
+  if (alpha_out) {
+    cudaError_t e = cudaMalloc((void **)&d_alpha, (size_t)pf->n * 8);
+    if (e != cudaSuccess) { cudaFree(d_acc); return fail(GB_ECUDA, cudaGetErrorString(e)); }
+  }
+  a.parent = pf->state[pf->cur ^ 1];
+  a.cur = pf->state[pf->cur];
+  a.anc = (!init && pf->mh_parent_anc) ? pf->anc : nullptr;
+  a.normals = pf->d_normals; a.uniforms = pf->d_uniforms;
+  a.alpha_out = d_alpha;
+  a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
+  a.seed = pf->seed; a.step = (unsigned)pf->step; a.move = pf->mh_moves;
+  a.drift_sd = drift_std;
+  a.accepted = d_acc;
+  if (init) rc = pf->dtype == GB_F64 ? launch_mh_k<double, true>(pf, a, move, predrawn) : launch_mh_k<float, true>(pf, a, move, predrawn);
+  else rc = pf->dtype == GB_F64 ? launch_mh_k<double, false>(pf, a, move, predrawn) : launch_mh_k<float, false>(pf, a, move, predrawn);
+  unsigned long long acc = 0;
+  cudaError_t e = cudaSuccess;
+  if (!rc) {
+    e = cudaMemcpyAsync(&acc, d_acc, 8, cudaMemcpyDeviceToHost, pf->stream);
+    if (e == cudaSuccess && alpha_out) e = cudaMemcpyAsync(alpha_out, d_alpha, (size_t)pf->n * 8, cudaMemcpyDeviceToHost, pf->stream);
+    // the latest history snapshot follows the rejuvenated traces
+    if (e == cudaSuccess && pf->history && !pf->hist_state.empty())
+      e = cudaMemcpy2DAsync(pf->hist_state.back(), (size_t)pf->n_pad * pf->esz, pf->state[pf->cur], (size_t)pf->ld * pf->esz,
+                            (size_t)pf->n_pad * pf->esz, pf->S, cudaMemcpyDeviceToDevice, pf->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
+  }
+  cudaFree(d_acc); cudaFree(d_alpha);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_rejuvenate: ") + cudaGetErrorString(e));
+  pf->mh_moves += 1;
+  pf->nn_set = pf->nu_set = 0;
+  if (n_accepted) *n_accepted = (int64_t)acc;
   return GB_OK;
 }
 
@@ -799,6 +895,7 @@ static int run_gather(gb_pf *pf) {   // materialise a deferred resample gather
   }
   CK(cudaGetLastError());
   pf->cur ^= 1;                       // particle_filter.jl:270-272
+  pf->mh_ok = false;
   pf->pending_gather = false;
   pf->tiles_valid = false;
   return GB_OK;
@@ -1169,6 +1266,7 @@ extern "C" int gb_pf_maybe_resample(gb_pf_t *pf, double ess_threshold, int kind,
   if (rc) return rc;
   pf->log_ml_est += lse - log((double)pf->n_global);   // :263
   pf->hist_resampled = true;
+  pf->mh_ok = false;              // `anc` now describes the NEXT generation
   pf->anc_valid = true;
   pf->parents64_valid = false;
   pf->pending_gather = true;
@@ -1228,6 +1326,7 @@ extern "C" int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t 
 // ---- fused multi-step entry: T x { maybe_resample!(systematic); particle_filter_step! } with the ESS test, the
 //      log-ML update and the gathered/direct choice made on the device (no host round trip per step) ----
 extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double ess_threshold, int *n_resampled) {
+  if (pf) pf->mh_ok = false;
   REQ(pf && obs && T >= 0, "gb_pf_run: bad argument");
   REQ(pf->n == pf->n_global, "gb_pf_run: single shard only");
   REQ(pf->model.kind != MODEL_BLR, "the BLR model has no sequential structure (importance sampling only)");
@@ -1271,6 +1370,7 @@ extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double
 // ---- sharded pieces ----
 extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits, uint64_t q_offset, uint64_t q_local,
                                           uint64_t q_total, uint32_t u0, int64_t *slot_lo, int64_t *slot_hi) {
+  if (pf) pf->mh_ok = false;
   REQ(pf && slot_lo && slot_hi, "null argument");
   REQ(q_total > 0, "gb_pf_systematic_offspring: zero total weight");
   REQ(bits == quant_bits(pf->n_global), "gb_pf_systematic_offspring: bits must be gb_quant_bits(n_global)");
@@ -1399,6 +1499,7 @@ extern "C" int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t
 }
 extern "C" int gb_pf_async_cur(const gb_pf_t *pf, int *cur) { REQ(pf && cur, "null argument"); *cur = pf->cur; return GB_OK; }
 extern "C" int gb_pf_async_plan(gb_pf_t *pf, const void *dev_gathered, uint32_t u0) {
+  if (pf) pf->mh_ok = false;
   REQ(pf && dev_gathered && pf->a_world > 0, "gb_pf_async_plan: call gb_pf_async_setup first");
   LAUNCH(pf, GB_K_TILESCAN, shard_plan_kernel<<<1, kMaxWorld, 0, pf->stream>>>((const long long *)dev_gathered, pf->d_offs, pf->a_world, pf->a_rank,
                                                                               pf->n_global, u0, pf->off_cap, pf->d_ctl, pf->d_plan, pf->d_shplan));
@@ -1406,6 +1507,7 @@ extern "C" int gb_pf_async_plan(gb_pf_t *pf, const void *dev_gathered, uint32_t 
   return GB_OK;
 }
 extern "C" int gb_pf_async_sweep(gb_pf_t *pf) {
+  if (pf) pf->mh_ok = false;
   REQ(pf && pf->a_world > 0 && pf->tiles_valid, "gb_pf_async_sweep: statistics pass missing");
   const AncOut ao{pf->anc, pf->pid_offset, pf->pid_offset + pf->n, pf->off_anc, -1, pf->off_cap};
   return pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1)
@@ -1426,6 +1528,7 @@ extern "C" int gb_pf_async_export(gb_pf_t *pf) {
   return GB_OK;
 }
 extern "C" int gb_pf_async_step(gb_pf_t *pf, const double *obs, int nobs) {
+  if (pf) pf->mh_ok = false;
   REQ(pf && obs && pf->a_world > 0, "gb_pf_async_step: bad argument");
   REQ(nobs == pf->model.nobs, "gb_pf_async_step: wrong number of observations");
   int rc = launch_model(pf, obs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false, false, 2);
@@ -1463,6 +1566,7 @@ extern "C" int gb_pf_offspring_local(gb_pf_t *pf, int64_t k_lo, int64_t k_hi) {
   return GB_OK;   // the sweep already wrote these ancestors into the shard's `anc` column
 }
 extern "C" int gb_pf_import_ext(gb_pf_t *pf, int64_t dst_lo, int64_t count, int64_t ext_offset, const void *dev_block) {
+  if (pf) pf->mh_ok = false;
   REQ(pf && dev_block, "null argument");
   REQ(dst_lo >= 0 && count >= 0 && dst_lo + count <= pf->n, "gb_pf_import_ext: destination outside the shard");
   if (ext_offset < 0 || ext_offset + count > pf->ext_cap) return fail(GB_ESTATE, "gb_pf_import_ext: extension rows exhausted");
@@ -1483,6 +1587,7 @@ extern "C" int gb_pf_import_ext(gb_pf_t *pf, int64_t dst_lo, int64_t count, int6
   return GB_OK;
 }
 extern "C" int gb_pf_commit_resample_lazy(gb_pf_t *pf, double log_ml_increment) {
+  if (pf) pf->mh_ok = false;
   REQ(pf, "null handle");
   pf->log_ml_est += log_ml_increment;       // particle_filter.jl:263
   pf->wstate = W_ZERO;                      // :266 (the array itself is rewritten by the gather / next step)
@@ -1522,6 +1627,7 @@ extern "C" int gb_pf_export_offspring(gb_pf_t *pf, int64_t k_lo, int64_t k_hi, v
   return GB_OK;
 }
 extern "C" int gb_pf_import_rows(gb_pf_t *pf, int64_t dst_lo, int64_t count, const void *dev_block) {
+  if (pf) pf->mh_ok = false;
   REQ(pf && dev_block, "null argument");
   REQ(dst_lo >= 0 && count >= 0 && dst_lo + count <= pf->n, "gb_pf_import_rows: destination outside the shard");
   if (count == 0) return GB_OK;
@@ -1539,6 +1645,7 @@ extern "C" int gb_pf_import_rows(gb_pf_t *pf, int64_t dst_lo, int64_t count, con
   return GB_OK;
 }
 extern "C" int gb_pf_commit_resample(gb_pf_t *pf, double log_ml_increment) {
+  if (pf) pf->mh_ok = false;
   REQ(pf, "null handle");
   pf->cur ^= 1;
   pf->log_ml_est += log_ml_increment;

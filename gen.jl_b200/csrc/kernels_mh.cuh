@@ -1,0 +1,104 @@
+// kernels_mh.cuh -- Metropolis-Hastings rejuvenation moves on every particle of the filter.
+//
+// The reference's users write   for i in 1:N  state.traces[i], _ = mh(state.traces[i], ...)   between
+// particle_filter_step! and maybe_resample! (docs/src/tutorials/smc.md:459-463, :518-520).  The engine's store is
+// Markov (current state + the buffer the last step read from), so the moves offered are the ones that touch the
+// latent choices of the LATEST kernel application, whose parent state is still resident:
+//   MH_RESIMULATE  mh(trace, select(<latest latents>))  (src/inference/mh.jl:16-27): the selected choices are
+//                  re-drawn from the model's transition; regenerate's weight is the score change of the retained
+//                  choices whose arguments changed (src/dynamic/regenerate.jl:36-50) = log p(y|x') - log p(y|x).
+//   MH_DRIFT       mh(trace, proposal, args) with a Gaussian-drift proposal c' ~ normal(c, std) on every latest latent
+//                  choice (mh.jl:37-58, tutorial perturbation_proposal smc.md:492-502): alpha = update weight
+//                  (dynamic/update.jl:46-62: score' - score of the constrained latents and of the observation)
+//                  - fwd_weight + bwd_weight.
+// accept iff log(rand()) < alpha (mh.jl:20, :52).  Particle weights are untouched, as in the reference.
+#pragma once
+#include "kernels_step.cuh"
+
+namespace gb {
+
+enum { MH_RESIMULATE = 0, MH_DRIFT = 1 };
+constexpr uint32_t kMhPairBase = 0x800000u;   // Philox draw-index block reserved for the moves: base + 16 * move + k
+
+struct MhArgs {
+  ModelParams mp;
+  const void *parent;   // the buffer the last step read its inputs from
+  void *cur;            // current traces (updated in place)
+  const int *anc;       // parent row of particle i (the last step's fused gather); nullptr: row i
+  const double *normals, *uniforms;   // PREDRAWN: [rows][ld]; the LAST uniform row is the accept draw
+  double *alpha_out;    // optional: log acceptance ratios
+  long long n, ld, pid_offset;
+  unsigned long long seed;
+  unsigned int step, move;
+  double drift_sd;
+  unsigned long long *accepted;
+};
+
+template <typename R, int KIND, bool INIT, int MOVE, bool PREDRAWN>
+__global__ void __launch_bounds__(kBlock) mh_kernel(const MhArgs a) {
+  using Tr = Transition<R, KIND, PROPOSAL_DEFAULT, INIT>;
+  constexpr int S = Tr::S, NN = MOVE == MH_DRIFT ? Tr::ND : Tr::NN, NU = MOVE == MH_DRIFT ? 0 : Tr::NU;
+  __shared__ double s_tab[kMathTabDoubles];
+  const MathTables T = stage_math_tables(s_tab);
+  __syncthreads();
+  const Hoisted<R> h = Tr::hoist(a.mp);
+  const R *__restrict__ par = static_cast<const R *>(a.parent);
+  R *__restrict__ cur = static_cast<R *>(a.cur);
+  const R dsd = (R)a.drift_sd, ldsd = Math<R>::log_((R)a.drift_sd);
+  const uint32_t base = kMhPairBase + 16u * a.move;
+  unsigned int nacc = 0;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < a.n; i += (long long)gridDim.x * kBlock) {
+    const unsigned long long pid = (unsigned long long)(a.pid_offset + i);
+    R prev[S], st[S], next[S], eps[NN > 0 ? NN : 1], us[NU > 0 ? NU : 1];
+    if (!INIT) {
+      const long long src = a.anc ? (long long)a.anc[i] : i;
+#pragma unroll
+      for (int s = 0; s < S; s++) prev[s] = __ldg(par + (long long)s * a.ld + src);
+    } else {
+#pragma unroll
+      for (int s = 0; s < S; s++) prev[s] = R(0);
+    }
+#pragma unroll
+    for (int s = 0; s < S; s++) st[s] = cur[(long long)s * a.ld + i];
+    R ua;
+    if (PREDRAWN) {
+#pragma unroll
+      for (int d = 0; d < NN; d++) eps[d] = (R)a.normals[(long long)d * a.ld + i];
+#pragma unroll
+      for (int d = 0; d < NU; d++) us[d] = (R)a.uniforms[(long long)d * a.ld + i];
+      ua = (R)a.uniforms[(long long)NU * a.ld + i];
+    } else {
+#pragma unroll
+      for (int d = 0; d < NN; d += 2) {
+        R e0, e1;
+        philox_normal_pair(a.seed, pid, a.step, base + (uint32_t)(d >> 1), T, e0, e1);
+        eps[d] = e0;
+        if (d + 1 < NN) eps[d + 1] = e1;
+      }
+      R u0, u1;
+      philox_uniform_pair(a.seed, pid, a.step, base + 15u, u0, u1);
+      ua = u0;
+      if (NU > 0) us[0] = u1;
+    }
+    R alpha;
+    if (MOVE == MH_RESIMULATE) {
+      const R w_new = Tr::apply(a.mp, h, T, prev, next, eps, us);
+      alpha = w_new - Tr::obs_logpdf(a.mp, h, T, st);                       // regenerate.jl:47-50
+    } else {
+      const R fwd_minus_bwd = Tr::drift(a.mp, h, prev, st, next, eps, dsd, ldsd);
+      R w = Tr::latent_logpdf(a.mp, h, T, prev, next) - Tr::latent_logpdf(a.mp, h, T, prev, st);   // update.jl:46-50
+      w += Tr::obs_logpdf(a.mp, h, T, next) - Tr::obs_logpdf(a.mp, h, T, st);
+      alpha = w - fwd_minus_bwd;                                            // mh.jl:49
+    }
+    if (a.alpha_out) a.alpha_out[i] = (double)alpha;
+    if (Math<R>::log_(ua) < alpha) {                                        // mh.jl:20, :52 (NaN => reject)
+#pragma unroll
+      for (int s = 0; s < S; s++) cur[(long long)s * a.ld + i] = next[s];
+      nacc++;
+    }
+  }
+  nacc = __reduce_add_sync(0xffffffffu, nacc);
+  if ((threadIdx.x & 31) == 0 && nacc) atomicAdd(a.accepted, (unsigned long long)nacc);
+}
+
+}  // namespace gb

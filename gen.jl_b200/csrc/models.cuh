@@ -41,7 +41,7 @@ template <typename R, int PK, bool INIT> struct Transition<R, MODEL_LGSSM, PK, I
     h.i2 = R(1) / (R)mp.pa[2];
     return h;
   }
-  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &h, const MathTables &, const R *prev, R *next, const R *eps, const R *) {
+  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &h, const MathTables &T, const R *prev, R *next, const R *eps, const R *) {
     R mu = INIT ? (R)mp.p[0] : (R)mp.p[2] * prev[0];
     R sd = INIT ? (R)mp.p[1] : (R)mp.p[3];
     if (PK == PROPOSAL_AFFINE_NORMAL) {
@@ -56,7 +56,21 @@ template <typename R, int PK, bool INIT> struct Transition<R, MODEL_LGSSM, PK, I
     }
     R x = random_normal<R>(mu, sd, eps[0]);
     next[0] = x;
-    return logpdf_normal_fast<R>((R)mp.obs0, x, h.i0, h.c0);
+    return obs_logpdf(mp, h, T, next);
+  }
+  // scores used by the MH rejuvenation moves (kernels_mh.cuh): the observed choice given the state, and the
+  // latent choices of the latest kernel application given the parent state; `drift` perturbs those choices
+  static constexpr int ND = 1;
+  static GB_D R obs_logpdf(const ModelParams &mp, const Hoisted<R> &h, const MathTables &, const R *st) {
+    return logpdf_normal_fast<R>((R)mp.obs0, st[0], h.i0, h.c0);
+  }
+  static GB_D R latent_logpdf(const ModelParams &mp, const Hoisted<R> &h, const MathTables &, const R *prev, const R *st) {
+    R mu = INIT ? (R)mp.p[0] : (R)mp.p[2] * prev[0];
+    return logpdf_normal_fast<R>(st[0], mu, h.i1, h.c1);
+  }
+  static GB_D R drift(const ModelParams &, const Hoisted<R> &, const R *, const R *st, R *next, const R *eps, R sd, R lsd) {
+    next[0] = random_normal<R>(st[0], sd, eps[0]);
+    return logpdf_normal_ls<R>(next[0], st[0], sd, lsd) - logpdf_normal_ls<R>(st[0], next[0], sd, lsd);   // fwd - bwd
   }
 };
 
@@ -64,15 +78,27 @@ template <typename R, int PK, bool INIT> struct Transition<R, MODEL_LGSSM, PK, I
 template <typename R, int PK, bool INIT> struct Transition<R, MODEL_SV, PK, INIT> {
   static constexpr int S = 1, NN = 1, NU = 0;
   static GB_D Hoisted<R> hoist(const ModelParams &) { return Hoisted<R>{R(0), R(0), R(0), R(0), R(0), R(0)}; }
-  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &, const MathTables &, const R *prev, R *next, const R *eps, const R *) {
+  static GB_D R apply(const ModelParams &mp, const Hoisted<R> &h, const MathTables &T, const R *prev, R *next, const R *eps, const R *) {
     R mean = INIT ? (R)mp.p[0] : (R)mp.p[0] + (R)mp.p[1] * (prev[0] - (R)mp.p[0]);
     R sd = INIT ? (R)mp.p[3] : (R)mp.p[2];
     R hh = random_normal<R>(mean, sd, eps[0]);
     next[0] = hh;
+    return obs_logpdf(mp, h, T, next);
+  }
+  static constexpr int ND = 1;
+  static GB_D R obs_logpdf(const ModelParams &mp, const Hoisted<R> &, const MathTables &, const R *st) {
     // y ~ normal(0, exp(h/2)):  log(std) = h/2 and 1/std = exp(-h/2) (the reference evaluates
     // log(exp(h/2)) and divides; both agree to ~1 ulp, far inside the 1e-10 weight tolerance)
-    R half = hh / R(2);
+    R half = st[0] / R(2);
     return logpdf_normal_fast<R>((R)mp.obs0, R(0), Math<R>::exp_t(-half), half);
+  }
+  static GB_D R latent_logpdf(const ModelParams &mp, const Hoisted<R> &, const MathTables &, const R *prev, const R *st) {
+    R mean = INIT ? (R)mp.p[0] : (R)mp.p[0] + (R)mp.p[1] * (prev[0] - (R)mp.p[0]);
+    return logpdf_normal<R>(st[0], mean, INIT ? (R)mp.p[3] : (R)mp.p[2]);
+  }
+  static GB_D R drift(const ModelParams &, const Hoisted<R> &, const R *, const R *st, R *next, const R *eps, R sd, R lsd) {
+    next[0] = random_normal<R>(st[0], sd, eps[0]);
+    return logpdf_normal_ls<R>(next[0], st[0], sd, lsd) - logpdf_normal_ls<R>(st[0], next[0], sd, lsd);
   }
 };
 
@@ -102,7 +128,38 @@ template <typename R, int PK, bool INIT> struct Transition<R, MODEL_BEARINGS, PK
       y = prev[1] + vy;
     }
     next[0] = x; next[1] = y; next[2] = vx; next[3] = vy;
-    return logpdf_normal_fast<R>((R)mp.obs0, Math<R>::atan2_t(y, x, T), h.i0, h.c0);
+    return obs_logpdf(mp, h, T, next);
+  }
+  static constexpr int ND = INIT ? 4 : 2;
+  static GB_D R obs_logpdf(const ModelParams &mp, const Hoisted<R> &h, const MathTables &T, const R *st) {
+    return logpdf_normal_fast<R>((R)mp.obs0, Math<R>::atan2_t(st[1], st[0], T), h.i0, h.c0);
+  }
+  static GB_D R latent_logpdf(const ModelParams &mp, const Hoisted<R> &h, const MathTables &, const R *prev, const R *st) {
+    R w = R(0);
+    if (INIT) {
+      for (int k = 0; k < 4; k++) w += logpdf_normal<R>(st[k], (R)mp.p[2 * k], (R)mp.p[2 * k + 1]);
+    } else {
+      w += logpdf_normal<R>(st[2], prev[2], h.c1);
+      w += logpdf_normal<R>(st[3], prev[3], h.c1);
+    }
+    return w;
+  }
+  // the choices are (x0, y0, vx0, vy0) at t = 0 and (vx, vy) afterwards; positions follow deterministically
+  static GB_D R drift(const ModelParams &, const Hoisted<R> &, const R *prev, const R *st, R *next, const R *eps, R sd, R lsd) {
+    R d = R(0);
+    if (INIT) {
+      for (int k = 0; k < 4; k++) {
+        next[k] = random_normal<R>(st[k], sd, eps[k]);
+        d += logpdf_normal_ls<R>(next[k], st[k], sd, lsd) - logpdf_normal_ls<R>(st[k], next[k], sd, lsd);
+      }
+    } else {
+      next[2] = random_normal<R>(st[2], sd, eps[0]);
+      next[3] = random_normal<R>(st[3], sd, eps[1]);
+      next[0] = prev[0] + next[2];
+      next[1] = prev[1] + next[3];
+      for (int k = 2; k < 4; k++) d += logpdf_normal_ls<R>(next[k], st[k], sd, lsd) - logpdf_normal_ls<R>(st[k], next[k], sd, lsd);
+    }
+    return d;
   }
 };
 
@@ -128,6 +185,19 @@ template <typename R, int PK, bool INIT> struct Transition<R, MODEL_HMM, PK, INI
     long long z = random_categorical<R>(zp, K, us[0]);
     next[0] = (R)z;
     return logpdf_categorical_t<R>(xo, emis + (z - 1) * M, M, T);
+  }
+  static constexpr int ND = 0;   // discrete latent: resimulation move only
+  static GB_D R obs_logpdf(const ModelParams &mp, const Hoisted<R> &, const MathTables &T, const R *st) {
+    const int K = mp.K, M = mp.M;
+    return logpdf_categorical_t<R>((long long)mp.obs0, mp.tab + K + K * K + ((long long)st[0] - 1) * M, M, T);
+  }
+  static GB_D R latent_logpdf(const ModelParams &mp, const Hoisted<R> &, const MathTables &T, const R *prev, const R *st) {
+    const int K = mp.K;
+    return logpdf_categorical_t<R>((long long)st[0], INIT ? mp.tab : mp.tab + K + ((long long)prev[0] - 1) * K, K, T);
+  }
+  static GB_D R drift(const ModelParams &, const Hoisted<R> &, const R *, const R *st, R *next, const R *, R, R) {
+    next[0] = st[0];
+    return R(0);
   }
 };
 

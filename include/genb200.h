@@ -114,6 +114,20 @@ int gb_pf_get_trajectory(gb_pf_t *pf, int field, double *out);
  * idx_out: n_samples 1-based particle indices; rows_out (may be NULL): S columns x n_samples values of the sampled
  * traces.  `draw` distinguishes successive calls on the same state (Philox stream (seed, draw)). */
 int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t draw, int64_t *idx_out, double *rows_out);
+/* MH rejuvenation of EVERY particle: the tutorial loop
+ *   for i in 1:N  state.traces[i], _ = mh(state.traces[i], ...)  end      (docs/src/tutorials/smc.md:459-463, :518-520)
+ * for moves on the latent choices of the LATEST kernel application (the only ones whose parent state the Markov store
+ * still holds).  GB_MH_RESIMULATE = mh(trace, select(<latest latents>)) (src/inference/mh.jl:16-27; weight =
+ * regenerate's, src/dynamic/regenerate.jl:36-50); GB_MH_DRIFT = mh(trace, proposal, args) with c' ~ normal(c, drift_std)
+ * on every latest latent choice (mh.jl:37-58).  Accept iff log(rand()) < alpha.  Weights are untouched.  Valid after
+ * gb_pf_generate / gb_pf_step and before gb_pf_maybe_resample (GB_ESTATE otherwise); obs = the latest observations.
+ * n_accepted, alpha_out (n log acceptance ratios) may be NULL.  Validation mode (gb_pf_set_noise): normals = the
+ * transition's rows (drift: one per latent choice), uniforms = the transition's rows followed by ONE accept row.
+ * Models: LGSSM, SV, BEARINGS, HMM (resimulate only). */
+#define GB_MH_RESIMULATE 0
+#define GB_MH_DRIFT 1
+int gb_pf_rejuvenate(gb_pf_t *pf, int move, const double *obs, int nobs, double drift_std, int64_t *n_accepted,
+                     double *alpha_out);
 /* Throughput entry: T iterations of { maybe_resample!(ess_threshold, systematic); particle_filter_step!(obs[t]) }
  * (default proposal) with the ESS test (particle_filter.jl:256), the log_ml_est update (:263) and the
  * gathered/direct choice of the step made ON THE DEVICE, i.e. without the host round trip the Bool return of

@@ -487,6 +487,7 @@ struct go_pf {
   double *logw;      /* particle_filter.jl:38 */
   double log_ml_est; /* :39 */
   int64_t *parents;  /* :40, 1-based */
+  int mh_ok;         /* new_state still holds the parents of `state` (rows aligned) */
 };
 
 int go_model_state_dim(int kind, const double *p) {
@@ -660,6 +661,7 @@ go_pf_t *go_pf_init(int kind, const double *params, int nparams, int64_t n, uint
   swap_traces(pf);
   pf->log_ml_est = 0.0;                                            /* :133, :153 */
   for (int64_t i = 0; i < n; i++) pf->parents[i] = i + 1;         /* collect(1:num_particles) */
+  pf->mh_ok = kind != GO_MODEL_BLR;
   return pf;
 }
 /* particle_filter.jl:186-240 */
@@ -671,6 +673,7 @@ int go_pf_step(go_pf_t *pf, const double *obs, int pk, const double *pa, const d
 #pragma omp parallel for schedule(static) if (g_threads > 1)
   for (int64_t i = 0; i < pf->n; i++) pf->logw[i] += incr[i];     /* :199, :231 */
   swap_traces(pf);                                                 /* :203-205, :234-237 */
+  pf->mh_ok = 1;
   if (!incr_out) free(incr);
   return 0;
 }
@@ -709,8 +712,126 @@ int go_pf_maybe_resample(go_pf_t *pf, double ess_threshold, int kind, int use_gi
     pf->logw[i] = 0.0;
   }
   swap_traces(pf);                                                 /* :270-272 */
+  pf->mh_ok = 0;
   free(anc);
   return 1;
+}
+/* ---- MH rejuvenation of the latest latent choices (src/inference/mh.jl) ----------------------------------------
+ * Scores of the choices of the latest kernel application: the observation given the state and the latent choices
+ * given the parent state.  Same distributions and arguments as particle_transition above. */
+static double model_obs_logpdf(int kind, const double *p, const double *st, const double *obs) {
+  switch (kind) {
+    case GO_MODEL_LGSSM: return go_logpdf_normal(obs[0], st[0], p[4]);
+    case GO_MODEL_SV: return go_logpdf_normal(obs[0], 0.0, exp(st[0] / 2.0));
+    case GO_MODEL_BEARINGS: return go_logpdf_normal(obs[0], atan2(st[1], st[0]), p[9]);
+    case GO_MODEL_HMM: {
+      int K = (int)p[0], M = (int)p[1];
+      return go_logpdf_categorical((int64_t)obs[0], p + 2 + K + K * K + ((int64_t)st[0] - 1) * M, M);
+    }
+  }
+  return NAN;
+}
+/* number of latent choices of the latest kernel application and their values c[] inside the state */
+static int model_latent_choices(int kind, int t, const int **idx) {
+  static const int one[1] = {0}, all4[4] = {0, 1, 2, 3}, vel[2] = {2, 3};
+  if (kind == GO_MODEL_BEARINGS) { *idx = t == 0 ? all4 : vel; return t == 0 ? 4 : 2; }
+  *idx = one;
+  return 1;
+}
+/* score of latent choice k (value v) given the parent state */
+static double model_latent_score(int kind, const double *p, int t, const double *prev, int k, double v) {
+  switch (kind) {
+    case GO_MODEL_LGSSM: return go_logpdf_normal(v, t == 0 ? p[0] : p[2] * prev[0], t == 0 ? p[1] : p[3]);
+    case GO_MODEL_SV: return go_logpdf_normal(v, t == 0 ? p[0] : p[0] + p[1] * (prev[0] - p[0]), t == 0 ? p[3] : p[2]);
+    case GO_MODEL_BEARINGS:
+      if (t == 0) return go_logpdf_normal(v, p[2 * k], p[2 * k + 1]);
+      return go_logpdf_normal(v, prev[2 + k], sqrt(p[8]));
+    case GO_MODEL_HMM: {
+      int K = (int)p[0];
+      return go_logpdf_categorical((int64_t)v, t == 0 ? p + 2 : p + 2 + K + ((int64_t)prev[0] - 1) * K, K);
+    }
+  }
+  return NAN;
+}
+/* the state as a function of the latent choices (bearings: positions follow from the velocities) */
+static void model_state_from_choices(int kind, int t, const double *prev, const double *c, double *st) {
+  if (kind == GO_MODEL_BEARINGS && t > 0) {
+    st[2] = c[0]; st[3] = c[1];
+    st[0] = prev[0] + c[0];
+    st[1] = prev[1] + c[1];
+    return;
+  }
+  int S = kind == GO_MODEL_BEARINGS ? 4 : 1;
+  for (int s = 0; s < S; s++) st[s] = c[s];
+}
+
+/* One MH move on every particle.  move 0: mh(trace, selection of the latest latents) -- mh.jl:16-27, the weight is
+ * regenerate's: sum of (score - prev_score) over retained choices (dynamic/regenerate.jl:47-50) = the observation's.
+ * move 1: mh(trace, proposal, args) with c' ~ normal(c, drift_std) per latent choice -- mh.jl:37-58; the update
+ * weight is sum of (score - prev_score) over constrained latents and the observation (dynamic/update.jl:46-50).
+ * Noise: pre-drawn rows (normals: the transition's / one per drifted choice; uniforms: the transition's rows then one
+ * accept row) or Philox draw-index block 0x800000 + 16 * move_index.  Requires the parents to be resident: call
+ * after init/step and before a resample.  alpha_out/accepted_out may be NULL.  Returns #accepted or -1. */
+int64_t go_pf_rejuvenate(go_pf_t *pf, int move, const double *obs, double drift_std, uint32_t move_index,
+                         const double *normals, const double *uniforms, double *alpha_out, uint8_t *accepted_out) {
+  const int kind = pf->kind, S = pf->S, t = pf->step;
+  const int64_t n = pf->n;
+  if (!pf->mh_ok || kind == GO_MODEL_BLR || (move == 1 && kind == GO_MODEL_HMM)) return -1;
+  const int *cidx;
+  const int nc = model_latent_choices(kind, t, &cidx);
+  const int nn = move == 1 ? nc : go_model_num_normals(kind, pf->params, 0, t == 0);
+  const int nu = move == 1 ? 0 : go_model_num_uniforms(kind, pf->params, 0, t == 0);
+  const uint32_t base = 0x800000u + 16u * move_index;
+  int64_t total = 0;
+#pragma omp parallel for schedule(static) reduction(+ : total) if (g_threads > 1)
+  for (int64_t i = 0; i < n; i++) {
+    double prev[8] = {0}, st[8], next[8], eps[8], us[4], ua;
+    for (int s = 0; s < S; s++) { st[s] = pf->state[(int64_t)s * n + i]; if (t > 0) prev[s] = pf->new_state[(int64_t)s * n + i]; }
+    if (normals || uniforms) {
+      for (int d = 0; d < nn; d++) eps[d] = normals[(int64_t)d * n + i];
+      for (int d = 0; d < nu; d++) us[d] = uniforms[(int64_t)d * n + i];
+      ua = uniforms[(int64_t)nu * n + i];
+    } else {
+      for (int d = 0; d < nn; d += 2) {
+        double a, b;
+        philox_normal_pair(pf->seed, (uint64_t)i, (uint32_t)t, base + (uint32_t)(d / 2), &a, &b);
+        eps[d] = a;
+        if (d + 1 < nn) eps[d + 1] = b;
+      }
+      double a, b;
+      philox_uniform_pair(pf->seed, (uint64_t)i, (uint32_t)t, base + 15u, &a, &b);
+      ua = a;
+      us[0] = b;
+    }
+    double alpha;
+    if (move == 0) {
+      double w_new = particle_transition(kind, pf->params, t, prev, next, obs, 0, NULL, eps, us);
+      alpha = 0.0;
+      alpha += w_new - model_obs_logpdf(kind, pf->params, st, obs);          /* regenerate.jl:47-50 */
+    } else {
+      double c_new[4], fwd = 0.0, bwd = 0.0, weight = 0.0;
+      for (int k = 0; k < nc; k++) {
+        double c = st[cidx[k]];
+        c_new[k] = go_random_normal(c, drift_std, eps[k]);                   /* proposal: {addr} ~ normal(choices[addr], std) */
+        fwd += go_logpdf_normal(c_new[k], c, drift_std);                     /* propose: mh.jl:44 */
+      }
+      model_state_from_choices(kind, t, prev, c_new, next);
+      for (int k = 0; k < nc; k++)                                           /* update.jl:46-50 */
+        weight += model_latent_score(kind, pf->params, t, prev, k, c_new[k]) -
+                  model_latent_score(kind, pf->params, t, prev, k, st[cidx[k]]);
+      weight += model_obs_logpdf(kind, pf->params, next, obs) - model_obs_logpdf(kind, pf->params, st, obs);
+      for (int k = 0; k < nc; k++) bwd += go_logpdf_normal(st[cidx[k]], c_new[k], drift_std);   /* assess: mh.jl:48 */
+      alpha = weight - fwd + bwd;                                            /* mh.jl:49 */
+    }
+    int acc = log(ua) < alpha;                                               /* mh.jl:20, :52 */
+    if (alpha_out) alpha_out[i] = alpha;
+    if (accepted_out) accepted_out[i] = (uint8_t)acc;
+    if (acc) {
+      for (int s = 0; s < S; s++) pf->state[(int64_t)s * n + i] = next[s];
+      total++;
+    }
+  }
+  return total;
 }
 /* particle_filter.jl:91-94 */
 double go_pf_log_ml_estimate(const go_pf_t *pf) {

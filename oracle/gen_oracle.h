@@ -94,6 +94,10 @@ int go_pf_step(go_pf_t *pf, const double *obs, int proposal_kind, const double *
 /* particle_filter.jl:249-275 with the integer-CDF resamplers; u64s only for multinomial validation */
 int go_pf_maybe_resample(go_pf_t *pf, double ess_threshold, int kind, int use_given_u0, uint32_t u0,
                          const uint64_t *u64s, double *ess_out);
+/* MH rejuvenation of every particle's latest latent choices: move 0 = mh(trace, selection) (mh.jl:16-27),
+ * move 1 = mh(trace, gaussian-drift proposal, (drift_std,)) (mh.jl:37-58).  Returns #accepted, -1 if unsupported. */
+int64_t go_pf_rejuvenate(go_pf_t *pf, int move, const double *obs, double drift_std, uint32_t move_index,
+                         const double *normals, const double *uniforms, double *alpha_out, uint8_t *accepted_out);
 double go_pf_log_ml_estimate(const go_pf_t *pf);        /* particle_filter.jl:91-94 */
 const double *go_pf_log_weights(const go_pf_t *pf);     /* :82-84 */
 const int64_t *go_pf_parents(const go_pf_t *pf);        /* 1-based */

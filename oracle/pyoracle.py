@@ -68,6 +68,7 @@ def lib():
             "go_pf_init": (vp, [i, _dp, i, i64, u64, _dp, i, _dp, _dp, _dp]),
             "go_pf_step": (i, [vp, _dp, i, _dp, _dp, _dp, _dp]),
             "go_pf_maybe_resample": (i, [vp, d, i, i, u32, _u64p, _dp]),
+            "go_pf_rejuvenate": (i64, [vp, i, _dp, d, u32, _dp, _dp, _dp, C.POINTER(C.c_uint8)]),
             "go_pf_log_ml_estimate": (d, [vp]),
             "go_pf_log_weights": (_dp, [vp]),
             "go_pf_parents": (_i64p, [vp]),
@@ -247,6 +248,20 @@ class OraclePF:
             raise ValueError("oracle resample failed rc=%d" % rc)
         self.last_ess = ess.value
         return bool(rc)
+
+    def rejuvenate(self, obs, move=0, drift_std=0.0, move_index=0, normals=None, uniforms=None):
+        """mh() on every particle's latest latent choices (src/inference/mh.jl:16-27 / :37-58).
+        Returns (#accepted, log acceptance ratios, accepted flags)."""
+        oa, op = _d(obs)
+        na, np_ = _d(normals)
+        ua, up = _d(uniforms)
+        alpha = np.empty(self.n, dtype=np.float64)
+        acc = np.empty(self.n, dtype=np.uint8)
+        r = lib().go_pf_rejuvenate(self._p, move, op, float(drift_std), move_index, np_, up, alpha.ctypes.data_as(_dp),
+                                   acc.ctypes.data_as(C.POINTER(C.c_uint8)))
+        if r < 0:
+            raise ValueError("oracle: MH move unsupported in this state / for this model")
+        return r, alpha, acc.astype(bool)
 
     @property
     def n(self):

@@ -1,0 +1,221 @@
+"""MH rejuvenation moves on every particle's latest latent choices.
+
+Reference semantics: src/inference/mh.jl:16-27 (selection / regenerate), :37-58 (custom proposal), used on particle
+filter states as in docs/src/tutorials/smc.md:459-463, :518-520.  CPU tests pin the oracle's acceptance ratios on
+independently computed target densities and on the exact posterior of the reference's HMM fixture; GPU tests compare
+the CUDA kernel with the oracle (accept decisions and states bit-exact, ratios 1e-10)."""
+import math
+
+import numpy as np
+import pytest
+
+import fixtures as F
+
+RTOL64 = 1e-10
+
+
+def npdf(x, mu, sd):
+    z = (x - mu) / sd
+    return -(z * z + math.log(2 * math.pi)) / 2 - np.log(sd)
+
+
+# ---------------------------------------------------------------- CPU: the oracle's moves
+def test_oracle_drift_ratio_is_target_density_ratio(O):
+    """Gaussian drift is symmetric, so alpha = log pi(x') - log pi(x), pi = p(x | parent) p(y | x)."""
+    n = 500
+    rng = np.random.default_rng(3)
+    ys = F.lgssm_series(3)
+    p = F.lgssm_params()
+    pf = O.OraclePF.init(O.MODEL_LGSSM, p, n, [ys[0]], normals=rng.standard_normal((1, n)))
+    pf.step([ys[1]], normals=rng.standard_normal((1, n)))
+    x_old = pf.state(0)
+    eps, ua = rng.standard_normal((1, n)), rng.random((1, n))
+    # the parents x0: the same generate sweep replayed from the same seed
+    rng2 = np.random.default_rng(3)
+    parent = O.OraclePF.init(O.MODEL_LGSSM, p, n, [ys[0]], normals=rng2.standard_normal((1, n))).state(0)
+    nacc, alpha, acc = pf.rejuvenate([ys[1]], move=1, drift_std=0.3, normals=eps, uniforms=ua)
+    x_prop = x_old + 0.3 * eps[0]
+    logpi = lambda x: npdf(x, p[2] * parent, p[3]) + npdf(ys[1], x, p[4])
+    assert np.allclose(alpha, logpi(x_prop) - logpi(x_old), rtol=1e-9, atol=1e-9)
+    assert np.array_equal(acc, np.log(ua[0]) < alpha) and nacc == acc.sum()
+    assert np.array_equal(pf.state(0), np.where(acc, x_prop, x_old))
+    # weights are untouched by mh (the reference never writes state.log_weights there)
+    assert 0 < nacc < n
+
+
+def test_oracle_resimulation_ratio_is_likelihood_ratio(O):
+    n = 400
+    rng = np.random.default_rng(4)
+    zs = F.bearings_series(3)
+    p = F.BEARINGS_PARAMS
+    pf = O.OraclePF.init(O.MODEL_BEARINGS, p, n, [zs[0]], normals=rng.standard_normal((4, n)))
+    lw0 = pf.log_weights
+    old = np.stack([pf.state(f) for f in range(4)])
+    eps, ua = rng.standard_normal((4, n)), rng.random((1, n))
+    nacc, alpha, acc = pf.rejuvenate([zs[0]], move=0, normals=eps, uniforms=ua)
+    new = np.stack([p[2 * k] + p[2 * k + 1] * eps[k] for k in range(4)])
+    lik = lambda s: npdf(zs[0], np.arctan2(s[1], s[0]), p[9])
+    assert np.allclose(alpha, lik(new) - lik(old), rtol=1e-9, atol=1e-9)
+    assert np.array_equal(np.stack([pf.state(f) for f in range(4)]), np.where(acc, new, old))
+    assert np.array_equal(pf.log_weights, lw0)
+    pf.maybe_resample(ess_threshold=n + 1, u0=5)
+    with pytest.raises(ValueError):                      # parents are gone after a resample
+        pf.rejuvenate([zs[0]], move=0, normals=eps, uniforms=ua)
+
+
+def test_oracle_hmm_resimulation_converges_to_exact_posterior(O):
+    """The reference's HMM fixture (test/inference/particle_filter.jl:52-78): repeated mh(trace, select(:z)) at t = 0
+    leaves every particle distributed as p(z0 | x0) = prior .* emission[x0, :] normalised."""
+    n = 40000
+    pf = O.OraclePF.init(O.MODEL_HMM, F.hmm_params(), n, [F.HMM_OBS[0]], seed=11)
+    for k in range(12):
+        pf.rejuvenate([F.HMM_OBS[0]], move=0, move_index=k)
+    post = F.hmm_init_proposal(F.HMM_OBS[0])
+    freq = np.bincount(pf.state(0).astype(int), minlength=4)[1:] / n
+    assert np.abs(freq - post).max() < 5 * math.sqrt(0.25 / n)
+
+
+# ---------------------------------------------------------------- GPU: CUDA kernel vs oracle
+def zoo(g, O):
+    return {
+        "lgssm": (g.lgssm_model(**F.LGSSM), O.MODEL_LGSSM, F.lgssm_params(), F.lgssm_series(8)),
+        "sv": (g.sv_model(**F.SV), O.MODEL_SV, F.sv_params(), F.sv_series(8)),
+        "bearings": (g.bearings_model(), O.MODEL_BEARINGS, F.BEARINGS_PARAMS, F.bearings_series(8)),
+        "hmm": (g.hmm_model(F.HMM_PRIOR, F.HMM_TRANSITION, F.HMM_EMISSION), O.MODEL_HMM, F.hmm_params(),
+                np.array([1, 1, 2, 3, 3, 1, 2, 2], dtype=float)),
+    }
+
+
+def mh_rows(model, move, init, name):
+    if move == "drift":
+        return ({"bearings": 4 if init else 2}.get(name, 1), 1)
+    return (model.num_normals(init), model.num_uniforms(init) + 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lgssm", "sv", "bearings", "hmm"])
+@pytest.mark.parametrize("move", ["resimulate", "drift"])
+@pytest.mark.parametrize("lazy", [True, False])
+def test_rejuvenation_predrawn_matches_oracle(g, O, name, move, lazy):
+    if name == "hmm" and move == "drift":
+        pytest.skip("drift needs continuous latents")
+    model, okind, params, ys = zoo(g, O)[name]
+    n = 2777
+    rng = np.random.default_rng(hash((name, move)) % 2 ** 32)
+    drift = {"lgssm": 0.3, "sv": 0.2, "bearings": 1e-3}.get(name, 0.0)
+    omove = 0 if move == "resimulate" else 1
+    st = g.create_particle_filter(model, n)
+    st.set_lazy_gather(lazy)
+
+    def noise(init):
+        nn, nu = model.num_normals(init), model.num_uniforms(init)
+        return (rng.standard_normal((max(nn, 1), n)) if nn else None), (rng.random((max(nu, 1), n)) if nu else None)
+
+    def sweep(t):
+        nn, nu = mh_rows(model, move, t == 0, name)
+        e, u = rng.standard_normal((max(nn, 1), n)), rng.random((nu, n))
+        st.set_noise(e if nn else None, u)
+        nacc, alpha = g.rejuvenate_(st, ys[t], move=move, drift_std=drift, return_alpha=True)
+        nacc_ref, alpha_ref, acc_ref = ref.rejuvenate([ys[t]], move=omove, drift_std=drift, normals=e if nn else None, uniforms=u)
+        fin = np.isfinite(alpha_ref)
+        assert np.array_equal(np.isfinite(alpha), fin)
+        assert np.allclose(alpha[fin], alpha_ref[fin], rtol=RTOL64, atol=RTOL64 * 10)
+        assert nacc == nacc_ref
+        for f in range(model.state_dim):
+            assert np.array_equal(st.get_state(f), ref.state(f)), (t, f)
+        return nacc
+
+    e, u = noise(True)
+    st.set_noise(e, u)
+    g.generate_(st, ys[0])
+    ref = O.OraclePF.init(okind, params, n, [ys[0]], normals=e, uniforms=u)
+    total = sweep(0) + sweep(0)
+    for t in range(1, len(ys)):
+        u0 = int(rng.integers(0, 2 ** 32))
+        thr = n + 0.5 if t % 2 else n / 8
+        st.set_resample_noise(u0=u0)
+        assert g.maybe_resample_(st, ess_threshold=thr, resampler="systematic") == ref.maybe_resample(ess_threshold=thr, u0=u0)
+        e, u = noise(False)
+        st.set_noise(e, u)
+        g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t])
+        ref.step([ys[t]], normals=e, uniforms=u)
+        lw = st.log_weights
+        total += sweep(t)
+        if t % 3 == 0:
+            total += sweep(t)
+        assert np.array_equal(st.log_weights, lw)                    # mh never touches the weights
+    assert 0 < total
+    assert np.array_equal(st.parents, ref.parents)
+    assert abs(g.log_ml_estimate(st) - ref.log_ml_estimate()) <= RTOL64 * abs(ref.log_ml_estimate())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lgssm", "bearings", "hmm"])
+def test_rejuvenation_philox_mode_matches_oracle(g, O, name):
+    """Production mode: both sides draw the move's noise from Philox block 0x800000 + 16 * move."""
+    model, okind, params, ys = zoo(g, O)[name]
+    n = 5000
+    st = g.initialize_particle_filter(model, (0,), ys[0], n, seed=77)
+    ref = O.OraclePF.init(okind, params, n, [ys[0]], seed=77)
+    moves = ["resimulate"] if name == "hmm" else ["resimulate", "drift"]
+    drift = 0.3 if name == "lgssm" else 1e-3
+    for t in range(0, 4):
+        if t > 0:
+            assert g.maybe_resample_(st, ess_threshold=n + 0.5, resampler="systematic") == ref.maybe_resample(ess_threshold=n + 0.5)
+            g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t])
+            ref.step([ys[t]])
+        for k, mv in enumerate(moves * 2):
+            nacc = g.rejuvenate_(st, ys[t], move=mv, drift_std=drift)
+            nacc_ref, _, _ = ref.rejuvenate([ys[t]], move=0 if mv == "resimulate" else 1, drift_std=drift, move_index=k)
+            # engine normals come from the table-driven log/sincos (<= 2 ulp from libm): states agree to rounding and
+            # an accept decision can differ only for a draw within ~1e-13 of the ratio
+            assert abs(nacc - nacc_ref) <= 1
+            for f in range(model.state_dim):
+                a, b = st.get_state(f), ref.state(f)
+                assert np.mean(np.abs(a - b) <= 1e-12 * np.maximum(1.0, np.abs(b))) > 0.999
+    assert abs(g.log_ml_estimate(st) - ref.log_ml_estimate()) < 1e-6
+
+
+@pytest.mark.gpu
+def test_rejuvenation_hmm_converges_to_exact_posterior_and_state_errors(g):
+    n = 40000
+    model = g.hmm_model(F.HMM_PRIOR, F.HMM_TRANSITION, F.HMM_EMISSION)
+    st = g.initialize_particle_filter(model, (0,), F.HMM_OBS[0], n, seed=5)
+    for _ in range(12):
+        g.rejuvenate_(st, F.HMM_OBS[0])
+    freq = np.bincount(st.get_state(0).astype(int), minlength=4)[1:] / n
+    assert np.abs(freq - F.hmm_init_proposal(F.HMM_OBS[0])).max() < 5 * math.sqrt(0.25 / n)
+    with pytest.raises(g.GenB200Error):                              # drift needs continuous latent choices
+        g.rejuvenate_(st, F.HMM_OBS[0], move="drift", drift_std=0.1)
+    assert g.maybe_resample_(st, ess_threshold=n + 0.5)
+    with pytest.raises(g.GenB200Error, match="maybe_resample"):       # parents gone once a resample was decided
+        g.rejuvenate_(st, F.HMM_OBS[0])
+    g.particle_filter_step_(st, (1,), (g.UnknownChange,), F.HMM_OBS[1])
+    assert g.rejuvenate_(st, F.HMM_OBS[1]) > 0
+
+
+@pytest.mark.gpu
+def test_rejuvenation_fp32_and_history(g, O):
+    """fp32 filter: ratios to 1e-4 of the fp64 oracle; with history on, the latest snapshot follows the moved traces."""
+    n = 4096
+    rng = np.random.default_rng(9)
+    ys = F.lgssm_series(4)
+    model = g.lgssm_model(**F.LGSSM)
+    st = g.create_particle_filter(model, n, dtype="f32")
+    st.enable_history()
+    e0 = rng.standard_normal((1, n)).astype(np.float32).astype(np.float64)
+    st.set_noise(e0)
+    g.generate_(st, ys[0])
+    ref = O.OraclePF.init(O.MODEL_LGSSM, F.lgssm_params(), n, [ys[0]], normals=e0)
+    e1 = rng.standard_normal((1, n)).astype(np.float32).astype(np.float64)
+    st.set_noise(e1)
+    g.particle_filter_step_(st, (1,), (g.UnknownChange,), ys[1])
+    ref.step([ys[1]], normals=e1)
+    em, um = rng.standard_normal((1, n)).astype(np.float32).astype(np.float64), rng.random((1, n))
+    st.set_noise(em, um)
+    nacc, alpha = g.rejuvenate_(st, ys[1], move="drift", drift_std=0.25, return_alpha=True)
+    nacc_ref, alpha_ref, _ = ref.rejuvenate([ys[1]], move=1, drift_std=0.25, normals=em, uniforms=um)
+    assert np.allclose(alpha, alpha_ref, rtol=1e-4, atol=2e-4)
+    assert abs(nacc - nacc_ref) <= 0.002 * n + 2
+    traj = st.trajectory(0)
+    assert np.array_equal(traj[-1], st.get_state(0))
