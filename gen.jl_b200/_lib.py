@@ -52,6 +52,9 @@ SIGNATURES = {
     "gb_pf_sample_unweighted": (i, [vp, i64, u64, i64p, dp]),
     "gb_pf_rejuvenate": (i, [vp, i, dp, i, d, i64p, dp]),
     "gb_pf_run": (i, [vp, i, dp, i, d, ip]),
+    "gb_spec_jit_source": (i, [vp, C.c_char_p, i64, i64p]),
+    "gb_spec_jit_compile": (i, [vp, i, i64p]),
+    "gb_pf_spec_backend": (i, [vp, ip]),
     "gb_pf_set_resample_noise": (i, [vp, i, u32, u64p]),
     "gb_pf_log_ml_estimate": (i, [vp, dp]),
     "gb_pf_get_log_weights": (i, [vp, dp]),

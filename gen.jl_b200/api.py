@@ -203,6 +203,22 @@ def spec_model(state_dim, params, num_obs, generate_program, step_program=None, 
     return DeviceModel(L.MODEL_SPEC, flat, name)
 
 
+def spec_jit_source(model):
+    """The CUDA C++ translation unit the library generates from a spec model's programs (NVRTC input)."""
+    need = C.c_int64()
+    L.check(L.lib().gb_spec_jit_source(model._h, None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    L.check(L.lib().gb_spec_jit_source(model._h, buf, need.value, None))
+    return buf.value.decode()
+
+
+def spec_jit_compile(model, dtype="f64"):
+    """Compile (not load) the specialised kernels for sm_100a; returns the cubin size.  Needs libnvrtc, no GPU."""
+    nb = C.c_int64()
+    L.check(L.lib().gb_spec_jit_compile(model._h, _DTYPES[dtype], C.byref(nb)))
+    return nb.value
+
+
 class AffineNormalProposal:
     """x ~ normal(c0 + c1 * x_prev, std): proposal_args = (c0, c1, std)."""
     kind = L.PROPOSAL_AFFINE_NORMAL
@@ -330,6 +346,13 @@ class DeviceParticleFilterState:
         out = np.empty((steps.value, self.num_particles), dtype=np.float64)
         L.check(L.lib().gb_pf_get_trajectory(self._h, int(field), out.ctypes.data_as(L.dp)))
         return out
+
+    @property
+    def spec_backend(self):
+        """GB_MODEL_SPEC filters: "nvrtc" / "interpreter" for the kernel the last generate/step ran, else None."""
+        b = C.c_int()
+        L.check(L.lib().gb_pf_spec_backend(self._h, C.byref(b)))
+        return {1: "nvrtc", 0: "interpreter"}.get(b.value)
 
     def set_lazy_gather(self, lazy):
         L.check(L.lib().gb_pf_set_lazy_gather(self._h, int(bool(lazy))))

@@ -4,10 +4,23 @@
 // a*b+c written in this tree stays two roundings; where a fused multiply-add is wanted it is written
 // as fma() explicitly.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
+#else
+// NVRTC (run-time specialisation of GB_MODEL_SPEC programs, csrc/spec_jit.inc): no host headers
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+typedef unsigned char uint8_t;
+typedef unsigned long size_t;
+#define INFINITY __int_as_float(0x7f800000)
+#define NAN __int_as_float(0x7fffffff)
+#define M_PI 3.14159265358979323846
+#endif
 
 typedef unsigned __int128 u128;
 
@@ -136,12 +149,14 @@ GB_HD uint64_t quantize(double x, int b) {
   if (e < 0) return 0;
   return (uint64_t)dmul(p, pow2i(e));
 }
+#ifndef __CUDACC_RTC__
 inline __host__ int quant_bits(int64_t n) {
   int lg = 0;
   while (((int64_t)1 << lg) < n) lg++;
   int b = 62 - lg;
   return b > 52 ? 52 : b;
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // 128 / 64 -> 64 bit floor division via a double reciprocal and exact integer correction.

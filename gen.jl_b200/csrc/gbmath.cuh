@@ -63,7 +63,9 @@ GB_D MathTables stage_math_tables(double *smem /* kMathTabDoubles */) {
   for (int i = threadIdx.x; i < GB_ATAN_TAB_N; i += blockDim.x) smem[2 * GB_LOG_TAB_N + i] = c_atan_tab[i];
   return MathTables{smem, smem + 2 * GB_LOG_TAB_N};
 }
+#ifndef __CUDACC_RTC__
 inline __host__ MathTables host_math_tables() { return MathTables{h_log_tab, h_atan_tab}; }
+#endif
 
 GB_HD uint64_t dbits(double x) {
 #ifdef __CUDA_ARCH__

@@ -228,7 +228,8 @@ struct gb_pf {
   bool lazy = true;
   bool mh_ok = false;             // state[cur ^ 1] still holds the parents of the current traces (MH rejuvenation)
   bool mh_parent_anc = false;     // ... reached through `anc` (the last step gathered through it)
-  unsigned int mh_moves = 0;      // rejuvenation sweeps applied since the last step (Philox draw-index block)
+  unsigned int mh_moves = 0;
+  int spec_backend = -1;          // GB_MODEL_SPEC: 1 = NVRTC-specialised kernel, 0 = interpreter (last launch)      // rejuvenation sweeps applied since the last step (Philox draw-index block)
   long long *parents64 = nullptr; // global 1-based parents (sharded path)
   bool parents64_valid = false;
   double log_ml_est = 0.0;
@@ -585,20 +586,11 @@ static int check_noise(gb_pf *pf, bool init, bool *predrawn) {
 static int blr_generate(gb_pf *pf, const double *obs, int nobs, bool predrawn);
 
 // GB_MODEL_SPEC: program + parameters into constant memory (once per model), observations per call
+#include "spec_jit.inc"
+
 template <typename R, bool INIT>
 static int launch_spec(gb_pf *pf, const double *obs, int nobs, bool predrawn, int gather) {
   const gb_model &m = pf->model;
-  if (g_spec_loaded != m.spec_id) {
-    CK(cudaMemcpyToSymbolAsync(c_spec_ops, m.ops.data(), m.ops.size() * sizeof(SpecOp), 0, cudaMemcpyHostToDevice, pf->stream));
-    if (!m.spec_params.empty())
-      CK(cudaMemcpyToSymbolAsync(c_spec_params, m.spec_params.data(), m.spec_params.size() * 8, 0, cudaMemcpyHostToDevice, pf->stream));
-    CK(cudaStreamSynchronize(pf->stream));
-    g_spec_loaded = m.spec_id;
-  }
-  double ob[64];
-  for (int k = 0; k < nobs; k++) ob[k] = obs[k];
-  CK(cudaMemcpyToSymbolAsync(c_spec_obs, ob, (size_t)nobs * 8, 0, cudaMemcpyHostToDevice, pf->stream));
-  CK(cudaStreamSynchronize(pf->stream));   // `ob` lives on this stack frame
   SpecArgs a;
   memset(&a, 0, sizeof(a));
   a.state_in = INIT ? nullptr : pf->state[pf->cur];
@@ -611,6 +603,41 @@ static int launch_spec(gb_pf *pf, const double *obs, int nobs, bool predrawn, in
   a.op_begin = INIT ? 0 : m.n_init_ops;
   a.op_end = INIT ? m.n_init_ops : m.n_init_ops + m.n_step_ops;
   a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
+  for (int k = 0; k < nobs && k < kSpecMaxObs; k++) a.obs[k] = obs[k];
+  // the NVRTC-specialised kernel when it can be built, else the interpreter
+  if (JitModule *jm = spec_jit_get(m, pf->dtype)) {
+    const int v = jit_variant(INIT, predrawn, gather);
+    long long blocks = (pf->n + kBlock - 1) / kBlock;
+    const int grid = (int)std::max(1ll, std::min(blocks, (long long)pf->num_sms * jm->occ[v]));
+    StepArgs sa;   // fast form: the program is a Transition<> of the step kernel itself
+    if (jm->fast) {
+      memset(&sa, 0, sizeof(sa));
+      sa.state_in = a.state_in; sa.state_out = a.state_out; sa.logw = a.logw; sa.incr = a.incr; sa.anc = a.anc; sa.ctl = a.ctl;
+      sa.normals = a.normals; sa.uniforms = a.uniforms; sa.n = a.n; sa.ld = a.ld; sa.pid_offset = a.pid_offset;
+      sa.seed = a.seed; sa.step = a.step; sa.partials = a.partials; sa.ticket = a.ticket; sa.stats = a.stats;
+      sa.mp.obs0 = obs[0];
+      for (int k = 1; k < nobs && k < 16; k++) sa.mp.obsx[k - 1] = obs[k];
+      sa.mp.step = a.step;
+    }
+    void *params[] = {jm->fast ? (void *)&sa : (void *)&a};
+    CUresult cr = CUDA_SUCCESS;
+    LAUNCH(pf, GB_K_STEP, cr = g_jit.LaunchKernel(jm->fn[v], grid, 1, 1, kBlock, 1, 1, 0, (CUstream)pf->stream, params, nullptr));
+    if (cr != CUDA_SUCCESS) {
+      const char *es = nullptr;
+      g_jit.GetErrorString(cr, &es);
+      return fail(GB_ECUDA, std::string("cuLaunchKernel(spec_jit_kernel): ") + (es ? es : "?"));
+    }
+    pf->spec_backend = 1;
+    return GB_OK;
+  }
+  pf->spec_backend = 0;
+  if (g_spec_loaded != m.spec_id) {
+    CK(cudaMemcpyToSymbolAsync(c_spec_ops, m.ops.data(), m.ops.size() * sizeof(SpecOp), 0, cudaMemcpyHostToDevice, pf->stream));
+    if (!m.spec_params.empty())
+      CK(cudaMemcpyToSymbolAsync(c_spec_params, m.spec_params.data(), m.spec_params.size() * 8, 0, cudaMemcpyHostToDevice, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    g_spec_loaded = m.spec_id;
+  }
 #define GO(PD, GA)                                                                         \
   {                                                                                        \
     auto kern = spec_kernel<R, INIT, PD, GA>;                                              \
@@ -622,6 +649,37 @@ static int launch_spec(gb_pf *pf, const double *obs, int nobs, bool predrawn, in
   else { if (gather == 2) GO(false, 2) else if (gather) GO(false, 1) else GO(false, 0) }
 #undef GO
   CK(cudaGetLastError());
+  return GB_OK;
+}
+
+// introspection of the run-time specialisation (tests, docs): generated source, compile check, backend in use
+extern "C" int gb_spec_jit_source(const gb_model_t *m, char *buf, int64_t cap, int64_t *needed) {
+  REQ(m && m->kind == MODEL_SPEC, "gb_spec_jit_source: not a GB_MODEL_SPEC model");
+  const std::string src = spec_codegen(*m);
+  if (needed) *needed = (int64_t)src.size() + 1;
+  if (buf && cap > 0) {
+    const size_t k = std::min((size_t)cap - 1, src.size());
+    memcpy(buf, src.data(), k);
+    buf[k] = 0;
+  }
+  return GB_OK;
+}
+// compile (not load) the model's kernels for sm_100a: needs libnvrtc only, no GPU.  cubin_bytes may be NULL.
+extern "C" int gb_spec_jit_compile(const gb_model_t *m, int dtype, int64_t *cubin_bytes) {
+  REQ(m && m->kind == MODEL_SPEC, "gb_spec_jit_compile: not a GB_MODEL_SPEC model");
+  REQ(dtype == GB_F64 || dtype == GB_F32, "gb_spec_jit_compile: dtype");
+  std::vector<char> cubin;
+  std::vector<std::string> lowered;
+  std::string log;
+  const int rc = spec_jit_compile(*m, dtype, cubin, lowered, log);
+  if (rc) return fail(rc, "gb_spec_jit_compile: " + log);
+  if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+  return GB_OK;
+}
+// 1: the last generate/step of this filter ran the NVRTC-specialised kernel; 0: the interpreter; -1: not a SPEC model / not run yet
+extern "C" int gb_pf_spec_backend(const gb_pf_t *pf, int *backend) {
+  REQ(pf && backend, "null argument");
+  *backend = pf->model.kind == MODEL_SPEC ? pf->spec_backend : -1;
   return GB_OK;
 }
 

@@ -10,7 +10,7 @@
 // op (uniform control flow, program and parameters in constant memory), registers live in local memory;
 // the transcendental work dominates exactly as in the specialised kernels.
 #pragma once
-#include "kernels_step.cuh"
+#include "spec_args.cuh"
 
 namespace gb {
 
@@ -22,28 +22,12 @@ enum {
   OP_SAMPLE_GAMMA = 24, OP_OBSERVE_GAMMA = 25, OP_SAMPLE_CATEGORICAL = 26, OP_OBSERVE_CATEGORICAL = 27,
   OP_STORE = 30, OP_WEIGHT = 31, OP_LOGPDF_NORMAL = 32
 };
-constexpr int kSpecMaxOps = 256, kSpecMaxParams = 2048, kSpecRegs = 32, kSpecMaxState = 16;
+constexpr int kSpecMaxOps = 256, kSpecMaxParams = 2048, kSpecMaxState = 16;
 
 struct SpecOp { int code, dst, a, b; double imm; };
 __constant__ SpecOp c_spec_ops[kSpecMaxOps];
 __constant__ double c_spec_params[kSpecMaxParams];
-__constant__ double c_spec_obs[64];
 
-struct SpecArgs {
-  const void *state_in;
-  void *state_out;
-  void *logw, *incr;
-  const int *anc;
-  const RunCtl *ctl;
-  const double *normals, *uniforms;   // PREDRAWN [nd][ld]
-  long long n, ld, pid_offset;
-  unsigned long long seed;
-  unsigned int step;
-  int op_begin, op_end;               // slice of c_spec_ops to run (generate / step program)
-  double *partials;
-  unsigned int *ticket;
-  WeightStats *stats;
-};
 
 template <typename R, bool INIT, bool PREDRAWN, int GATHER>
 __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
@@ -69,7 +53,7 @@ __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
         case OP_CONST: regs[op.dst] = (R)op.imm; break;
         case OP_PREV: regs[op.dst] = INIT ? R(0) : __ldg(sin + (long long)op.a * a.ld + src); break;
         case OP_PARAM: regs[op.dst] = (R)c_spec_params[op.a]; break;
-        case OP_OBS: regs[op.dst] = (R)c_spec_obs[op.a]; break;
+        case OP_OBS: regs[op.dst] = (R)a.obs[op.a]; break;
         case OP_TIME: regs[op.dst] = (R)a.step; break;
         case OP_ADD: regs[op.dst] = regs[op.a] + regs[op.b]; break;
         case OP_SUB: regs[op.dst] = regs[op.a] - regs[op.b]; break;

@@ -21,6 +21,9 @@ struct ModelParams {
   const double *tab;   // DEVICE: HMM prior | transition | emission
   const double *ptab;  // DEVICE: HMM proposal table for this step
   int K, M;
+  // GB_MODEL_SPEC programs lowered onto the step kernel at run time (spec_jit.inc): observations 1..15, step index
+  double obsx[15];
+  unsigned int step;
 };
 
 // Per-thread constants hoisted out of the particle loop (log of fixed standard deviations etc.).

@@ -128,6 +128,18 @@ int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t draw, int64
 #define GB_MH_DRIFT 1
 int gb_pf_rejuvenate(gb_pf_t *pf, int move, const double *obs, int nobs, double drift_std, int64_t *n_accepted,
                      double *alpha_out);
+/* Run-time specialisation of GB_MODEL_SPEC models.  Gen turns a static-IR function into straight-line code per trace
+ * type (`@generated` functions, src/static_ir/generate.jl:68-109, update.jl:467-513); here the program that crossed
+ * this boundary is lowered to CUDA C++ (one statement per node, parameters as literals) and compiled for sm_100a
+ * with NVRTC on first use, per (model, dtype, device).  If libnvrtc / libcuda cannot be opened, or with
+ * GENB200_SPEC_JIT=0 in the environment, the generic interpreter kernel runs the same program instead (same device
+ * functions: identical states, weights equal to rounding of constant-folded logs).
+ *   gb_spec_jit_source   the generated translation unit (buf may be NULL to query *needed)
+ *   gb_spec_jit_compile  compile only (no GPU needed); GB_EUNSUPPORTED + the NVRTC log in gb_last_error() on failure
+ *   gb_pf_spec_backend   which kernel the filter's last generate/step ran: 1 specialised, 0 interpreter, -1 n/a */
+int gb_spec_jit_source(const gb_model_t *m, char *buf, int64_t cap, int64_t *needed);
+int gb_spec_jit_compile(const gb_model_t *m, int dtype, int64_t *cubin_bytes);
+int gb_pf_spec_backend(const gb_pf_t *pf, int *backend);
 /* Throughput entry: T iterations of { maybe_resample!(ess_threshold, systematic); particle_filter_step!(obs[t]) }
  * (default proposal) with the ESS test (particle_filter.jl:256), the log_ml_est update (:263) and the
  * gathered/direct choice of the step made ON THE DEVICE, i.e. without the host round trip the Bool return of

@@ -197,4 +197,36 @@ end
 importance_sampling(model::DeviceModel, model_args::Tuple, observations::ChoiceMap, num_samples::Int; kw...) =
     importance_sampling(model, model_args, observations, nothing, (), num_samples; kw...)
 
+# sample_unweighted_traces (particle_filter.jl:101-109): 1-based indices of num_samples iid draws + their rows
+function sample_unweighted_traces(state::DeviceParticleFilterState, num_samples::Int; draw::Integer=0)
+    idx = Vector{Int64}(undef, num_samples)
+    rows = Matrix{Float64}(undef, num_samples, state.model.state_dim)
+    check(ccall((:gb_pf_sample_unweighted, libgenb200), Cint, (Ptr{Cvoid}, Int64, UInt64, Ptr{Int64}, Ptr{Cdouble}),
+                state.handle, num_samples, UInt64(draw), idx, rows))
+    (idx, rows)
+end
+
+# The tutorial's rejuvenation loop (docs/src/tutorials/smc.md:459-463, :518-520)
+#     for i in 1:N  state.traces[i], _ = mh(state.traces[i], ...)  end
+# for moves on the latest latent choices: move = :resimulate is mh(trace, selection) (mh.jl:16-27),
+# move = :drift is mh(trace, gaussian_drift_proposal, (drift_std,)) (mh.jl:37-58).  Returns the number accepted.
+function rejuvenate!(state::DeviceParticleFilterState, observations::ChoiceMap; move::Symbol=:resimulate, drift_std::Real=0.0)
+    obs = flatten_obs(observations)
+    acc = Ref{Int64}(0)
+    check(ccall((:gb_pf_rejuvenate, libgenb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cdouble, Ref{Int64}, Ptr{Cdouble}),
+                state.handle, move == :drift ? 1 : 0, obs, length(obs), Float64(drift_std), acc, C_NULL))
+    acc[]
+end
+
+# T x { maybe_resample!; particle_filter_step! } without a host round trip per step (gb_pf_run)
+function particle_filter_run!(state::DeviceParticleFilterState, observations::Vector{<:ChoiceMap};
+                              ess_threshold::Real=state.num_particles / 2)
+    obs = reduce(vcat, [flatten_obs(o) for o in observations])
+    nres = Ref{Cint}(0)
+    T = length(observations)
+    check(ccall((:gb_pf_run, libgenb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cdouble, Ref{Cint}),
+                state.handle, T, obs, div(length(obs), T), Float64(ess_threshold), nres))
+    nres[]
+end
+
 end # module

@@ -198,3 +198,25 @@ def test_gbmath_accuracy_against_mpmath(g):
         hi, lo = rnd.getrandbits(32), rnd.getrandbits(32)
         v = ((hi << 32) | lo) >> 12
         assert f(5, float(hi), float(lo)) == (v + 0.5) * 2.0 ** -52
+
+
+def test_spec_programs_lower_to_cuda_and_compile_for_sm100a_without_a_gpu(g):
+    """GB_MODEL_SPEC run-time specialisation: the generated translation unit has one statement per node and NVRTC
+    compiles it for sm_100a here (no GPU needed to compile; loading and launching are covered by the gpu tests)."""
+    gen, step = g.SpecProgram(), g.SpecProgram()
+    x = gen.sample_normal(gen.param(0), gen.param(1))
+    gen.observe_normal(gen.obs(0), x, gen.const(0.7))
+    gen.store(0, x)
+    x = step.sample_normal(step.mul(step.const(0.9), step.prev(0)), step.param(1))
+    b = step.sample_bernoulli(step.const(0.25))
+    step.observe_gamma(step.obs(0), step.const(2.0), step.exp(x))
+    step.store(0, step.add(x, b))
+    model = g.spec_model(1, [0.0, 1.5], 1, gen, step)
+    src = g.spec_jit_source(model)
+    assert "spec_jit_kernel" in src and "philox_normal_pair" in src and "logpdf_gamma<R>" in src
+    assert "(R)(0x1.8p+0)" in src                       # parameters are baked in as exact literals
+    assert src.count("st_stream(sout") == 2
+    for dtype in ("f64", "f32"):
+        assert g.spec_jit_compile(model, dtype) > 10000   # a cubin came back
+    with pytest.raises(g.GenB200Error):
+        g.spec_jit_compile(g.lgssm_model(), "f64")        # presets are compiled ahead of time

@@ -670,8 +670,15 @@ def hmm_spec(g):
     return g.spec_model(1, params, 1, gen, step, "hmm-spec")
 
 
+@pytest.fixture(params=["nvrtc", "interpreter"])
+def spec_backend(request, monkeypatch):
+    """Run a spec-model test once through the NVRTC-specialised kernel and once through the interpreter kernel."""
+    monkeypatch.setenv("GENB200_SPEC_JIT", "1" if request.param == "nvrtc" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("name", ["bearings", "hmm"])
-def test_spec_model_equals_builtin_kind_and_oracle(g, O, name):
+def test_spec_model_equals_builtin_kind_and_oracle(g, O, name, spec_backend):
     """The same model written as a declarative spec gives bit-identical states / ancestors and 1e-10 weights."""
     builtin, okind_m, params, ys, _, _ = model_zoo(g, O)[name]
     spec = bearings_spec(g) if name == "bearings" else hmm_spec(g)
@@ -698,9 +705,56 @@ def test_spec_model_equals_builtin_kind_and_oracle(g, O, name):
         g.particle_filter_step_(c, (t,), (g.UnknownChange,), ys[t], return_incr=False)
     g.particle_filter_run_(d, ys[1:], ess_threshold=n / 2)
     assert np.array_equal(c.get_state(0), d.get_state(0)) and c.log_ml_est == d.log_ml_est
+    assert b.spec_backend == spec_backend and d.spec_backend == spec_backend and a.spec_backend is None
 
 
-def test_spec_model_outside_the_presets(g, O):
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_spec_nvrtc_kernel_equals_interpreter(g, monkeypatch, dtype):
+    """Same program, same device functions: the run-time specialised kernel and the interpreter give identical states
+    and ancestors; weights agree to the rounding of constant-folded log(std)."""
+    ys = F.bearings_series(10)
+    n = 100003
+    out = {}
+    for backend in ("1", "0"):
+        monkeypatch.setenv("GENB200_SPEC_JIT", backend)
+        st = g.initialize_particle_filter(bearings_spec(g), (0,), ys[0], n, dtype=dtype, seed=21)
+        for t in range(1, len(ys)):
+            g.maybe_resample_(st, ess_threshold=n / 2 if t % 2 else n + 1, resampler="systematic")
+            g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+        out[backend] = (np.stack([st.get_state(f) for f in range(4)]), st.parents, st.log_weights, g.log_ml_estimate(st), st.spec_backend)
+    assert out["1"][4] == "nvrtc" and out["0"][4] == "interpreter"
+    assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
+    tol = 1e-12 if dtype == "f64" else 1e-5
+    assert np.allclose(out["1"][2], out["0"][2], rtol=tol, atol=tol * 10) and abs(out["1"][3] - out["0"][3]) <= tol * abs(out["0"][3])
+
+
+def test_spec_nvrtc_general_loop_with_gamma_draws(g, monkeypatch):
+    """Programs with gamma draws (rejection sampler on its own Philox stream) are specialised into the plain particle
+    loop instead of the step kernel; still identical to the interpreter, and the gamma moments come out right."""
+    gen, step = g.SpecProgram(), g.SpecProgram()
+    x = gen.sample_gamma(gen.const(2.0), gen.const(1.5))
+    gen.observe_normal(gen.obs(0), gen.log(x), gen.const(0.5))
+    gen.store(0, x)
+    x = step.mul(step.prev(0), step.sample_gamma(step.const(3.0), step.const(0.3)))
+    step.observe_normal(step.obs(0), step.log(x), step.const(0.5))
+    step.store(0, x)
+    n = 200001
+    out = {}
+    for backend in ("1", "0"):
+        monkeypatch.setenv("GENB200_SPEC_JIT", backend)
+        st = g.initialize_particle_filter(g.spec_model(1, [], 1, gen, step), (0,), 0.9, n, seed=2)
+        x0 = st.get_state(0)
+        g.maybe_resample_(st, ess_threshold=n + 1, resampler="systematic")
+        g.particle_filter_step_(st, (1,), (g.UnknownChange,), 0.4, return_incr=False)
+        out[backend] = (x0, st.get_state(0), st.log_weights, st.spec_backend)
+    assert out["1"][3] == "nvrtc" and out["0"][3] == "interpreter"
+    assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
+    assert np.allclose(out["1"][2], out["0"][2], rtol=1e-12, atol=1e-11)
+    x0 = out["1"][0]
+    assert abs(x0.mean() - 3.0) < 5 * math.sqrt(4.5 / n) and abs(x0.var() - 4.5) < 0.1     # gamma(2, 1.5): mean 3, var 4.5
+
+
+def test_spec_model_outside_the_presets(g, O, spec_backend):
     """A model no preset covers -- gamma-distributed state with multiplicative noise, Bernoulli and gamma
     observations -- checked against a numpy restatement of the same program on pre-drawn noise."""
     from scipy import special
@@ -751,7 +805,7 @@ def test_spec_model_outside_the_presets(g, O):
         g.spec_model(2, [], 1, bad)
 
 
-def test_spec_model_custom_proposal(g, O):
+def test_spec_model_custom_proposal(g, O, spec_backend):
     """A custom proposal written inside the spec (sample from q, observe the model density, subtract q's score) equals
     the built-in LGSSM + AffineNormalProposal and the oracle's weight algebra (trace_translators.jl:854)."""
     L_ = F.LGSSM

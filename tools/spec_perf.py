@@ -6,7 +6,9 @@ g = entry.load_package()
 import test_gpu_parity as T
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
 zs = F.bearings_series(12)
-for label, model in (("specialised", g.bearings_model()), ("spec program", T.bearings_spec(g))):
+for label, model, jit in (("specialised kind (ahead of time)", g.bearings_model(), "1"), ("spec program, NVRTC-specialised", T.bearings_spec(g), "1"),
+                          ("spec program, interpreter", T.bearings_spec(g), "0")):
+    os.environ["GENB200_SPEC_JIT"] = jit
     st = g.initialize_particle_filter(model, (0,), zs[0], n, seed=1)
     for t in range(1, 4):
         g.maybe_resample_(st, ess_threshold=n + 1, resampler="systematic")
@@ -16,5 +18,5 @@ for label, model in (("specialised", g.bearings_model()), ("spec program", T.bea
         g.maybe_resample_(st, ess_threshold=n + 1, resampler="systematic")
         g.particle_filter_step_(st, (t,), (g.UnknownChange,), zs[t], return_incr=False)
     tm = st.get_timing()
-    print(label, {k: round(v[0] / max(1, v[1]), 4) for k, v in tm.items() if v[1]}, "log ML", g.log_ml_estimate(st))
+    print(label, {k: round(v[0] / max(1, v[1]), 4) for k, v in tm.items() if v[1]}, "log ML", g.log_ml_estimate(st), "backend", st.spec_backend)
     del st
