@@ -317,10 +317,10 @@ def run_genb200(args):
     if world == 1 and not args.no_cpu:
         O = entry.load_oracle()
         threads = O.lib().go_get_max_threads()
-        rate, secs = cpu_pf_rate(args.cpu_particles, 6, threads, zs)
+        rate, secs = cpu_pf_rate(args.cpu_particles, 10, threads, zs)
         rate1, secs1 = cpu_pf_rate(args.cpu_particles // 4, 4, 1, zs)
         cpu = {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-               "sample": "%d particles x 6 steps of the same bearings PF (%.1f s); C oracle restating Gen's PF"
+               "sample": "%d particles x 10 steps of the same bearings PF (%.1f s); C oracle restating Gen's PF"
                          % (args.cpu_particles, secs),
                "single_thread_value": rate1,
                "note": "Gen.jl (pure Julia) cannot run in this image; tutorial-derived Gen.jl figure is "
@@ -335,7 +335,9 @@ def run_genb200(args):
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 80,
                 "ms_per_step": ms_e2e / args.steps, "log_ml_estimate": lml,
                 "note": "maybe_resample_ + particle_filter_step_ + log_ml_estimate through the host API each step: "
-                        "observation passed from host memory, weight statistics read back twice (40 B each)"},
+                        "observation passed from host memory, weight statistics read back twice (40 B each); the N log "
+                        "incremental weights particle_filter_step! returns stay on the device as a lazy vector "
+                        "(gb_pf_get_log_increments) and are not read"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": step_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -383,8 +385,8 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
                     help="weak (default): 1e8 particles PER GPU; strong: 1e8 particles in total, sharded")
-    ap.add_argument("--cpu-particles", type=int, default=4_000_000)
-    ap.add_argument("--ref-particles", type=int, default=4_000_000)
+    ap.add_argument("--cpu-particles", type=int, default=20_000_000)
+    ap.add_argument("--ref-particles", type=int, default=20_000_000)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -58,6 +58,7 @@ SIGNATURES = {
     "gb_pf_set_resample_noise": (i, [vp, i, u32, u64p]),
     "gb_pf_log_ml_estimate": (i, [vp, dp]),
     "gb_pf_get_log_weights": (i, [vp, dp]),
+    "gb_pf_get_log_increments": (i, [vp, dp]),
     "gb_pf_set_log_weights": (i, [vp, dp]),
     "gb_pf_get_parents": (i, [vp, i64p]),
     "gb_pf_get_state": (i, [vp, i, dp]),

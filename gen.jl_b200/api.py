@@ -348,6 +348,13 @@ class DeviceParticleFilterState:
         return out
 
     @property
+    def log_incremental_weights(self):
+        """The return value of the last particle_filter_step_ (read on demand from the device)."""
+        out = np.empty(self.num_particles, dtype=np.float64)
+        L.check(L.lib().gb_pf_get_log_increments(self._h, out.ctypes.data_as(L.dp)))
+        return out
+
+    @property
     def spec_backend(self):
         """GB_MODEL_SPEC filters: "nvrtc" / "interpreter" for the kernel the last generate/step ran, else None."""
         b = C.c_int()

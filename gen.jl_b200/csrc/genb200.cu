@@ -229,6 +229,7 @@ struct gb_pf {
   bool mh_ok = false;             // state[cur ^ 1] still holds the parents of the current traces (MH rejuvenation)
   bool mh_parent_anc = false;     // ... reached through `anc` (the last step gathered through it)
   unsigned int mh_moves = 0;
+  int incr_step = -1;             // step index whose log incremental weights `incr` holds
   int spec_backend = -1;          // GB_MODEL_SPEC: 1 = NVRTC-specialised kernel, 0 = interpreter (last launch)      // rejuvenation sweeps applied since the last step (Philox draw-index block)
   long long *parents64 = nullptr; // global 1-based parents (sharded path)
   bool parents64_valid = false;
@@ -825,6 +826,7 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
   pf->tiles_valid = false;
   pf->nn_set = pf->nu_set = 0;
   pf->mh_ok = true; pf->mh_parent_anc = gather; pf->mh_moves = 0;
+  pf->incr_step = pf->step;
   if (pf->history && (rc = history_record(pf, pf->hist_resampled))) return rc;
   pf->hist_resampled = false;
   if (incr_out) {
@@ -1121,6 +1123,14 @@ extern "C" int gb_pf_get_log_weights(gb_pf_t *pf, double *out) {
   int rc = materialize(pf);
   if (rc) return rc;
   return copy_out(pf, pf->logw, out, pf->n);
+}
+// the log incremental weights of the LAST particle_filter_step! (its return value, particle_filter.jl:199-207, :231-239),
+// kept on the device until the next step so that a caller who never looks at them does not pay the N-element copy
+extern "C" int gb_pf_get_log_increments(gb_pf_t *pf, double *out) {
+  REQ(pf && out, "null argument");
+  if (pf->step < 1 || pf->incr_step != pf->step)
+    return fail(GB_ESTATE, "gb_pf_get_log_increments: no particle_filter_step has produced increments for the current step");
+  return copy_out(pf, pf->incr, out, pf->n);
 }
 extern "C" int gb_pf_set_log_weights(gb_pf_t *pf, const double *in) {
   REQ(pf && in, "null argument");

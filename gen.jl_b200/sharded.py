@@ -275,6 +275,16 @@ class ShardedParticleFilter:
         self.step += 1
         return out
 
+    def rejuvenate_(self, observations, move="resimulate", drift_std=0.0):
+        """MH rejuvenation of every particle's latest latent choices (api.rejuvenate_): shard-local work, keyed by the
+        global particle id, so the result does not depend on the GPU count.  Returns the global number of accepted moves."""
+        acc = api.rejuvenate_(self.local, observations, move=move, drift_std=drift_std)
+        if self.world == 1:
+            return acc
+        t = self.torch.tensor([acc], dtype=self.torch.int64, device=self.device)
+        self.dist.all_reduce(t, group=self.group)
+        return int(t.item())
+
     def run_(self, observations_seq, ess_threshold=None):
         """T x { maybe_resample!; particle_filter_step! } over the sharded filter WITHOUT any host round trip: the
         statistics record is all-reduced / all-gathered on the device, the exchange plan, the ESS test and the log-ML

@@ -149,6 +149,10 @@ int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double ess_thresh
 int gb_pf_set_resample_noise(gb_pf_t *pf, int use_u0, uint32_t u0, const uint64_t *u64s);
 int gb_pf_log_ml_estimate(gb_pf_t *pf, double *out);                 /* particle_filter.jl:91-94 */
 int gb_pf_get_log_weights(gb_pf_t *pf, double *out_n);               /* :82-84 (unnormalised) */
+/* The return value of the last particle_filter_step! (:199-207, :231-239), read on demand: gb_pf_step(..., NULL) leaves
+ * the N increments on the device and the glue returns a lazy vector that calls this on first access. GB_ESTATE when
+ * the filter has moved on (or has not stepped yet). */
+int gb_pf_get_log_increments(gb_pf_t *pf, double *out_n);
 int gb_pf_set_log_weights(gb_pf_t *pf, const double *in_n);          /* tests poke .log_weights (:176-197) */
 int gb_pf_get_parents(gb_pf_t *pf, int64_t *out_n);                  /* :40, 1-based, global ids */
 int gb_pf_get_state(gb_pf_t *pf, int field, double *out_n);          /* column `field` of the traces */

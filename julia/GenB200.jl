@@ -142,12 +142,27 @@ function particle_filter_step!(state::DeviceParticleFilterState, new_args::Tuple
     end
     obs = flatten_obs(observations)
     pa = flatten_pargs(proposal, proposal_args)
-    incr = Vector{Float64}(undef, state.num_particles)
     check(ccall((:gb_pf_step, libgenb200), Cint,
                 (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Cint, Ptr{Cdouble}),
-                state.handle, obs, length(obs), proposal_kind(proposal), pa, length(pa), incr))
+                state.handle, obs, length(obs), proposal_kind(proposal), pa, length(pa), C_NULL))
     length(new_args) >= 1 && (state.last_t = Int(new_args[1]))
-    (incr,)
+    (LazyIncrements(state, nothing),)
+end
+
+# The (log_incremental_weights,) return value of particle_filter_step! as a vector that stays on the device until
+# it is indexed: at N = 1e8 an eager copy would move 800 MB per step that most callers never read.
+mutable struct LazyIncrements <: AbstractVector{Float64}
+    state::DeviceParticleFilterState
+    data::Union{Nothing,Vector{Float64}}
+end
+Base.size(v::LazyIncrements) = (getfield(v.state, :num_particles),)
+function Base.getindex(v::LazyIncrements, i::Int)
+    if v.data === nothing
+        out = Vector{Float64}(undef, getfield(v.state, :num_particles))
+        check(ccall((:gb_pf_get_log_increments, libgenb200), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), getfield(v.state, :handle), out))
+        v.data = out
+    end
+    v.data[i]
 end
 
 function maybe_resample!(state::DeviceParticleFilterState; ess_threshold::Real=state.num_particles / 2, verbose=false)

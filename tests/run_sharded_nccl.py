@@ -29,10 +29,11 @@ def main():
         seed = 17
         spf = sharded.ShardedParticleFilter(g.bearings_model(), n, seed=seed).initialize(ys[0])
         spf.force_staged = staged
-        nres = 0
+        nres = nacc = nacc1 = 0
         for t in range(1, len(ys)):
             nres += spf.maybe_resample_(ess_threshold=(n + 1 if t % 2 else n / 2))
             spf.particle_filter_step_((t,), ys[t])
+            nacc += spf.rejuvenate_(ys[t], move="drift" if t % 2 else "resimulate", drift_std=1e-3)   # shard-local MH moves
         cols = [spf.get_state(f) for f in range(4)]
         par = spf.get_parents()
         lml = spf.log_ml_estimate()
@@ -41,9 +42,10 @@ def main():
             for t in range(1, len(ys)):
                 g.maybe_resample_(st, ess_threshold=(n + 1 if t % 2 else n / 2), resampler="systematic")
                 g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t])
-            ok = all(np.array_equal(cols[f], st.get_state(f)) for f in range(4)) and np.array_equal(par, st.parents)
+                nacc1 += g.rejuvenate_(st, ys[t], move="drift" if t % 2 else "resimulate", drift_std=1e-3)
+            ok = nacc == nacc1 and nacc > 0 and all(np.array_equal(cols[f], st.get_state(f)) for f in range(4)) and np.array_equal(par, st.parents)
             ok = ok and abs(lml - g.log_ml_estimate(st)) <= 1e-10 * abs(lml)
-            print("NCCL sharded check world=%d n=%d staged=%s resamples=%d: %s (log ML %.12f)" % (world, n, staged, nres, "OK" if ok else "MISMATCH", lml))
+            print("NCCL sharded check world=%d n=%d staged=%s resamples=%d mh-accepts=%d: %s (log ML %.12f)" % (world, n, staged, nres, nacc, "OK" if ok else "MISMATCH", lml))
             if not ok:
                 sys.exit(1)
     # asynchronous run (device-side plan, fixed-capacity equal-split all-to-all) vs the fused single-GPU run

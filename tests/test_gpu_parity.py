@@ -258,6 +258,7 @@ def test_pf_predrawn_noise_bit_exact(g, O, name, resampler, lazy):
         incr_ref = ref.step([ys[t]], proposal_kind=opk or 0, pargs=opa, normals=eps if nn1 else None,
                             uniforms=us if nu1 else None)
         assert len(incr) == n                                                    # particle_filter.jl test :137
+        assert np.array_equal(st.log_incremental_weights, incr)                  # the same vector, read on demand
         assert close(incr, incr_ref, RTOL64)
         for f in range(model.state_dim):
             assert np.array_equal(st.get_state(f), ref.state(f)), (t, f)         # resampled states bit-exact

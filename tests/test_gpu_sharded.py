@@ -13,7 +13,7 @@ import fixtures as F
 pytestmark = pytest.mark.gpu
 
 
-def run_sharded_in_process(g, model, n, K, ys, seed, dtype="f64", fast=False):
+def run_sharded_in_process(g, model, n, K, ys, seed, dtype="f64", fast=False, mh=None):
     import torch
     from genb200 import sharded, _lib as L
     counts, offs = sharded.shard_bounds(n, K)
@@ -58,6 +58,8 @@ def run_sharded_in_process(g, model, n, K, ys, seed, dtype="f64", fast=False):
                 (o.commit_lazy if use_fast else o.commit)(lse - math.log(n))
         for s in shards:
             g.particle_filter_step_(s, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+            if mh is not None:                                                # rejuvenation is shard-local
+                mh.append(g.rejuvenate_(s, ys[t], move="drift" if t % 2 else "resimulate", drift_std=1e-3))
         m = max(o.weight_max() for o in ops)
         trip = [o.weight_sums(m, bits) for o in ops]
         lml_hist.append(shards[0].log_ml_est + m + math.log(sum(x[0] for x in trip)) - math.log(n))
@@ -65,6 +67,22 @@ def run_sharded_in_process(g, model, n, K, ys, seed, dtype="f64", fast=False):
     lw = np.concatenate([g.get_log_weights(s) for s in shards])
     par = np.concatenate([s.parents for s in shards])
     return cols, lw, par, lml_hist
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_sharded_rejuvenation_equals_single_shard(g, fast):
+    """MH rejuvenation after each step is shard-local (parents are resident on the shard, through the extension rows
+    when offspring migrated in) and keyed by the global particle id: K shards == 1 shard, bit for bit."""
+    model, ys, n, seed = g.bearings_model(), F.bearings_series(7), 40009, 5
+    acc3, acc1 = [], []
+    cols, lw, par, lml = run_sharded_in_process(g, model, n, 3, ys, seed, fast=fast, mh=acc3)
+    cols1, lw1, par1, lml1 = run_sharded_in_process(g, model, n, 1, ys, seed, mh=acc1)
+    assert all(np.array_equal(a, b) for a, b in zip(cols, cols1))
+    assert np.array_equal(lw, lw1) and np.array_equal(par, par1)
+    assert [sum(acc3[3 * k:3 * k + 3]) for k in range(len(acc1))] == acc1 and sum(acc1) > 0
+    # and it changed the filter
+    cols0, _, _, _ = run_sharded_in_process(g, model, n, 1, ys, seed)
+    assert not np.array_equal(cols0[2], cols1[2])
 
 
 @pytest.mark.parametrize("K", [2, 3, 8])
