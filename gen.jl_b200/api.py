@@ -189,6 +189,18 @@ class SpecProgram:
     def logpdf_normal(self, x, mu, std):
         return self._emit(32, self._new(), mu, std, imm=x)
 
+    # the other scalar built-ins (distributions/*.jl): dist is a name of _DISTS; one-parameter ones ignore b
+    def sample(self, dist, a, b=None):
+        """dst ~ dist(a, b) by inverse CDF (uniform, exponential, laplace, cauchy, geometric, uniform_discrete)."""
+        return self._emit(40, self._new(), a, a if b is None else b, imm=_DISTS[dist])
+
+    def observe(self, dist, x, a, b=None):
+        """weight += logpdf(dist, reg x, a, b)."""
+        self._emit(41, x, a, a if b is None else b, imm=_DISTS[dist])
+
+    def logpdf(self, dist, x, a, b=None):
+        return self._emit(42, self._new(), a, a if b is None else b, imm=_DISTS[dist] + 100 * x)
+
 
 def spec_model(state_dim, params, num_obs, generate_program, step_program=None, name="spec"):
     """A model of the supported class from its declarative specification: `generate_program` is the static-IR

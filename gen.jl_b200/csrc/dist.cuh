@@ -149,6 +149,42 @@ GB_D double logpdf_uniform_discrete(double xi, double lo, double hi) {  // unifo
   return (xi >= lo && xi <= hi) ? -log(hi - lo + 1.0) : -INFINITY;
 }
 
+// distribution ids of the scalar built-ins above (== GB_DIST_* of include/genb200.h, static_assert in genb200.cu)
+enum { DIST_UNIFORM = 6, DIST_EXPONENTIAL = 7, DIST_LAPLACE = 8, DIST_CAUCHY = 9, DIST_INV_GAMMA = 10, DIST_BETA = 11,
+       DIST_POISSON = 12, DIST_GEOMETRIC = 13, DIST_BINOM = 14, DIST_NEG_BINOM = 15, DIST_UNIFORM_DISCRETE = 16 };
+GB_D double logpdf_scalar(int dist, double x, double a, double b) {
+  switch (dist) {
+    case DIST_UNIFORM: return logpdf_uniform(x, a, b);
+    case DIST_EXPONENTIAL: return logpdf_exponential(x, a);
+    case DIST_LAPLACE: return logpdf_laplace(x, a, b);
+    case DIST_CAUCHY: return logpdf_cauchy(x, a, b);
+    case DIST_INV_GAMMA: return logpdf_inv_gamma(x, a, b);
+    case DIST_BETA: return logpdf_beta(x, a, b);
+    case DIST_POISSON: return logpdf_poisson(x, a);
+    case DIST_GEOMETRIC: return logpdf_geometric(x, a);
+    case DIST_BINOM: return logpdf_binom(x, a, b);
+    case DIST_NEG_BINOM: return logpdf_neg_binom(x, a, b);
+    case DIST_UNIFORM_DISCRETE: return logpdf_uniform_discrete(x, a, b);
+  }
+  return NAN;
+}
+// inverse-CDF draws on one uniform in (0,1) for the built-ins that have a closed-form quantile function
+GB_D bool has_invcdf(int dist) {
+  return dist == DIST_UNIFORM || dist == DIST_EXPONENTIAL || dist == DIST_LAPLACE || dist == DIST_CAUCHY || dist == DIST_GEOMETRIC ||
+         dist == DIST_UNIFORM_DISCRETE;
+}
+GB_D double random_invcdf(int dist, double p0, double p1, double u) {
+  switch (dist) {
+    case DIST_UNIFORM: return p0 + (p1 - p0) * u;
+    case DIST_EXPONENTIAL: return -log1p(-u) / p0;
+    case DIST_LAPLACE: return u < 0.5 ? p0 + p1 * log(2.0 * u) : p0 - p1 * log(2.0 * (1.0 - u));
+    case DIST_CAUCHY: return p0 + p1 * (sinpi(u - 0.5) / cospi(u - 0.5));
+    case DIST_GEOMETRIC: return floor(log1p(-u) / log1p(-p0));
+    case DIST_UNIFORM_DISCRETE: return p0 + floor((p1 - p0 + 1.0) * u);
+  }
+  return NAN;
+}
+
 // mvnormal.jl:12-16: the covariance is shared by all particles, so it is factored ONCE (host, in
 // fp64) instead of once per call as the reference does; the kernel consumes L (row-major lower
 // Cholesky factor, k*k doubles) and logdet:  -(k log 2pi + logdet + |L^-1 (x-mu)|^2) / 2

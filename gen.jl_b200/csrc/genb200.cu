@@ -79,6 +79,10 @@ struct gb_model {
   long long spec_id = 0;
 };
 static long long g_spec_next_id = 1, g_spec_loaded = 0;
+static_assert(DIST_UNIFORM == GB_DIST_UNIFORM && DIST_EXPONENTIAL == GB_DIST_EXPONENTIAL && DIST_LAPLACE == GB_DIST_LAPLACE &&
+              DIST_CAUCHY == GB_DIST_CAUCHY && DIST_INV_GAMMA == GB_DIST_INV_GAMMA && DIST_BETA == GB_DIST_BETA &&
+              DIST_POISSON == GB_DIST_POISSON && DIST_GEOMETRIC == GB_DIST_GEOMETRIC && DIST_BINOM == GB_DIST_BINOM &&
+              DIST_NEG_BINOM == GB_DIST_NEG_BINOM && DIST_UNIFORM_DISCRETE == GB_DIST_UNIFORM_DISCRETE, "distribution ids");
 
 static int model_state_dim(int kind, const double *p) {
   switch (kind) {
@@ -168,6 +172,19 @@ extern "C" int gb_model_create(int kind, const double *params, int nparams, gb_m
         case OP_STORE: ok = op.dst >= 0 && op.dst < S && reg(op.a); if (ok) stored[prog][op.dst]++; break;
         case OP_WEIGHT: ok = reg(op.a); break;
         case OP_LOGPDF_NORMAL: ok = ok && reg(op.a) && reg(op.b) && reg((int)op.imm); break;
+        case OP_SAMPLE_DIST: {      // inverse-CDF draw of built-in (int)imm from the uniform stream
+          const int di = (int)op.imm;
+          ok = ok && reg(op.a) && reg(op.b) && (di == DIST_UNIFORM || di == DIST_EXPONENTIAL || di == DIST_LAPLACE || di == DIST_CAUCHY ||
+                                               di == DIST_GEOMETRIC || di == DIST_UNIFORM_DISCRETE);
+          m->nu[prog]++;
+          break;
+        }
+        case OP_OBSERVE_DIST: ok = ok && reg(op.a) && reg(op.b) && (int)op.imm >= DIST_UNIFORM && (int)op.imm <= DIST_UNIFORM_DISCRETE; break;
+        case OP_LOGPDF_DIST: {
+          const int di = (int)op.imm % 100, xr = (int)op.imm / 100;
+          ok = ok && reg(op.a) && reg(op.b) && reg(xr) && di >= DIST_UNIFORM && di <= DIST_UNIFORM_DISCRETE;
+          break;
+        }
         default: ok = false;
       }
       if (!ok) { delete m; return fail(GB_EINVAL, "SPEC: malformed op #" + std::to_string(k)); }
@@ -2017,17 +2034,11 @@ __global__ void __launch_bounds__(kBlock) dist_logpdf_kernel(int dist, long long
       case GB_DIST_GAMMA: r = logpdf_gamma<R>((R)x[i], (R)a[i * as], (R)b[i * bs]); break;
       case GB_DIST_BERNOULLI: r = logpdf_bernoulli<R>(x[i] != 0.0, (R)a[i * as]); break;
       case GB_DIST_CATEGORICAL: r = logpdf_categorical<R>((long long)x[i], a, len); break;
-      case GB_DIST_UNIFORM: r = (R)logpdf_uniform(x[i], a[i * as], b[i * bs]); break;
-      case GB_DIST_EXPONENTIAL: r = (R)logpdf_exponential(x[i], a[i * as]); break;
-      case GB_DIST_LAPLACE: r = (R)logpdf_laplace(x[i], a[i * as], b[i * bs]); break;
-      case GB_DIST_CAUCHY: r = (R)logpdf_cauchy(x[i], a[i * as], b[i * bs]); break;
-      case GB_DIST_INV_GAMMA: r = (R)logpdf_inv_gamma(x[i], a[i * as], b[i * bs]); break;
-      case GB_DIST_BETA: r = (R)logpdf_beta(x[i], a[i * as], b[i * bs]); break;
-      case GB_DIST_POISSON: r = (R)logpdf_poisson(x[i], a[i * as]); break;
-      case GB_DIST_GEOMETRIC: r = (R)logpdf_geometric(x[i], a[i * as]); break;
-      case GB_DIST_BINOM: r = (R)logpdf_binom(x[i], a[i * as], b[i * bs]); break;
-      case GB_DIST_NEG_BINOM: r = (R)logpdf_neg_binom(x[i], a[i * as], b[i * bs]); break;
-      case GB_DIST_UNIFORM_DISCRETE: r = (R)logpdf_uniform_discrete(x[i], a[i * as], b[i * bs]); break;
+      case GB_DIST_UNIFORM: case GB_DIST_EXPONENTIAL: case GB_DIST_LAPLACE: case GB_DIST_CAUCHY: case GB_DIST_INV_GAMMA:
+      case GB_DIST_BETA: case GB_DIST_POISSON: case GB_DIST_GEOMETRIC: case GB_DIST_BINOM: case GB_DIST_NEG_BINOM:
+      case GB_DIST_UNIFORM_DISCRETE:
+        r = (R)logpdf_scalar(dist, x[i], a[i * as], b ? b[i * bs] : 0.0);
+        break;
       default: {
         R xv[kBlrMax];
         for (int k = 0; k < len; k++) xv[k] = (R)x[i * len + k];
@@ -2070,14 +2081,7 @@ __global__ void __launch_bounds__(kBlock) dist_random_kernel(int dist, long long
       case GB_DIST_UNIFORM_DISCRETE: {   // inverse-CDF samplers on one 52-bit uniform in (0,1)
         double u0, u1;
         philox_uniform_pair(seed, pid, step, 0u, u0, u1);
-        const double p0 = a[i * as], p1 = b[i * bs];
-        double v;
-        if (dist == GB_DIST_UNIFORM) v = p0 + (p1 - p0) * u0;
-        else if (dist == GB_DIST_EXPONENTIAL) v = -log1p(-u0) / p0;
-        else if (dist == GB_DIST_LAPLACE) v = u0 < 0.5 ? p0 + p1 * log(2.0 * u0) : p0 - p1 * log(2.0 * (1.0 - u0));
-        else if (dist == GB_DIST_CAUCHY) v = p0 + p1 * (sinpi(u0 - 0.5) / cospi(u0 - 0.5));
-        else if (dist == GB_DIST_GEOMETRIC) v = floor(log1p(-u0) / log1p(-p0));
-        else v = p0 + floor((p1 - p0 + 1.0) * u0);
+        const double v = random_invcdf(dist, a[i * as], b ? b[i * bs] : 0.0, u0);
         out[i] = v;
         break;
       }

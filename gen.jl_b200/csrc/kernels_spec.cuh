@@ -20,7 +20,8 @@ enum {
   OP_ABS = 19,
   OP_SAMPLE_NORMAL = 20, OP_OBSERVE_NORMAL = 21, OP_SAMPLE_BERNOULLI = 22, OP_OBSERVE_BERNOULLI = 23,
   OP_SAMPLE_GAMMA = 24, OP_OBSERVE_GAMMA = 25, OP_SAMPLE_CATEGORICAL = 26, OP_OBSERVE_CATEGORICAL = 27,
-  OP_STORE = 30, OP_WEIGHT = 31, OP_LOGPDF_NORMAL = 32
+  OP_STORE = 30, OP_WEIGHT = 31, OP_LOGPDF_NORMAL = 32,
+  OP_SAMPLE_DIST = 40, OP_OBSERVE_DIST = 41, OP_LOGPDF_DIST = 42   // the other scalar built-ins: imm = distribution id (+ 100 * x register)
 };
 constexpr int kSpecMaxOps = 256, kSpecMaxParams = 2048, kSpecMaxState = 16;
 
@@ -75,13 +76,14 @@ __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
           break;
         }
         case OP_OBSERVE_NORMAL: w += logpdf_normal<R>(regs[op.dst], regs[op.a], regs[op.b]); break;   // normal.jl:56-59
-        case OP_SAMPLE_BERNOULLI: case OP_SAMPLE_CATEGORICAL: {
+        case OP_SAMPLE_BERNOULLI: case OP_SAMPLE_CATEGORICAL: case OP_SAMPLE_DIST: {
           R u;
           if (PREDRAWN) u = (R)__ldcs(a.uniforms + (long long)n_unif * a.ld + i);
           else if (n_unif & 1) u = spare_u;
           else philox_uniform_pair(a.seed, pid, a.step, (unsigned)(n_unif >> 1), u, spare_u);
           n_unif++;
-          if (op.code == OP_SAMPLE_BERNOULLI) regs[op.dst] = random_bernoulli<R>(regs[op.a], u) ? R(1) : R(0);   // bernoulli.jl:19
+          if (op.code == OP_SAMPLE_DIST) regs[op.dst] = (R)random_invcdf((int)op.imm, (double)regs[op.a], (double)regs[op.b], (double)u);
+          else if (op.code == OP_SAMPLE_BERNOULLI) regs[op.dst] = random_bernoulli<R>(regs[op.a], u) ? R(1) : R(0);   // bernoulli.jl:19
           else regs[op.dst] = (R)random_categorical<R>(c_spec_params + (int)regs[op.a], op.b, u);                  // categorical.jl:20-22
           break;
         }
@@ -100,6 +102,10 @@ __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
         case OP_STORE: st_stream(sout + (long long)op.dst * a.ld + i, regs[op.a]); break;
         case OP_WEIGHT: w += regs[op.a]; break;                                     // e.g. minus a proposal score
         case OP_LOGPDF_NORMAL: regs[op.dst] = logpdf_normal<R>(regs[(int)op.imm], regs[op.a], regs[op.b]); break;
+        case OP_OBSERVE_DIST: w += (R)logpdf_scalar((int)op.imm, (double)regs[op.dst], (double)regs[op.a], (double)regs[op.b]); break;
+        case OP_LOGPDF_DIST:
+          regs[op.dst] = (R)logpdf_scalar((int)op.imm % 100, (double)regs[(int)op.imm / 100], (double)regs[op.a], (double)regs[op.b]);
+          break;
         default: break;
       }
     }

@@ -45,6 +45,10 @@ enum { GB_MODEL_LGSSM = 1, GB_MODEL_SV = 2, GB_MODEL_BEARINGS = 3, GB_MODEL_HMM 
  *        27 OBSERVE_CATEGORICAL weight += logpdf(categorical, reg dst, params[reg a : reg a + b])
  *        30 STORE state field dst <- reg a   (every field exactly once per program)
  *        31 WEIGHT weight += reg a              32 LOGPDF_NORMAL dst <- logpdf(normal, reg (int)imm, a, b)
+ *        40 SAMPLE_DIST dst ~ D(a, b), D = GB_DIST_* (int)imm, for the built-ins with a closed-form quantile function
+ *           (uniform, exponential, laplace, cauchy, geometric, uniform_discrete; one draw of the uniform stream)
+ *        41 OBSERVE_DIST weight += logpdf(D, reg dst, a, b), D = GB_DIST_UNIFORM .. GB_DIST_UNIFORM_DISCRETE
+ *        42 LOGPDF_DIST dst <- logpdf(D, reg x, a, b) with imm = D + 100 * x
  * `sample` ops are unconstrained choices (weight unchanged: static_ir/generate.jl:31-38), `observe` ops constrained ones
  * (weight += logpdf: unfold/update.jl:64-68).  A custom proposal (particle_filter.jl:186-208, trace_translators.jl:854) is
  * written inside the program: sample from the proposal, OBSERVE the model's density of the proposed value, and subtract
@@ -57,7 +61,7 @@ enum { GB_PROPOSAL_DEFAULT = 0, GB_PROPOSAL_AFFINE_NORMAL = 1, GB_PROPOSAL_CATEG
  * (exact integer-CDF definitions shared with the oracle). */
 enum { GB_RESAMPLE_MULTINOMIAL = 0, GB_RESAMPLE_SYSTEMATIC = 1, GB_RESAMPLE_RESIDUAL = 2 };
 enum { GB_F64 = 0, GB_F32 = 1 };
-/* distributions for the batched logpdf/random entries (modeling_library/distributions/*.jl) */
+/* distributions for the batched logpdf/random entries (modeling_library/distributions/<name>.jl) */
 enum { GB_DIST_NORMAL = 1, GB_DIST_GAMMA = 2, GB_DIST_BERNOULLI = 3, GB_DIST_CATEGORICAL = 4, GB_DIST_MVNORMAL = 5,
        /* the other scalar built-ins (batched entries only): (a, b) = */
        GB_DIST_UNIFORM = 6 /* low, high */, GB_DIST_EXPONENTIAL = 7 /* rate */, GB_DIST_LAPLACE = 8 /* loc, scale */,

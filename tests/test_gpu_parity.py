@@ -806,6 +806,55 @@ def test_spec_model_outside_the_presets(g, O, spec_backend):
         g.spec_model(2, [], 1, bad)
 
 
+def test_spec_model_other_builtin_distributions(g, spec_backend):
+    """SAMPLE_DIST / OBSERVE_DIST / LOGPDF_DIST ops: choices of the other scalar built-ins (uniform_continuous.jl,
+    laplace.jl, exponential.jl, cauchy.jl, poisson.jl, beta.jl) inside a spec program, against scipy on pre-drawn
+    uniforms."""
+    from scipy import stats
+    n = 4099
+    gen, step = g.SpecProgram(), g.SpecProgram()
+    x = gen.sample("uniform", gen.const(0.5), gen.const(2.0))
+    gen.observe("poisson", gen.obs(0), gen.exp(x))
+    gen.store(0, x)
+    gen.store(1, gen.const(0.0))
+    px = step.prev(0)
+    x = step.add(px, step.sample("laplace", step.const(0.0), step.const(0.1)))
+    wait = step.sample("exponential", step.const(3.0))
+    step.observe("poisson", step.obs(0), step.exp(x))
+    step.observe("cauchy", step.obs(1), x, step.const(0.5))
+    frac = step.div(wait, step.add(wait, step.const(1.0)))
+    step.add_weight(step.logpdf("beta", frac, step.const(2.0), step.const(3.0)))
+    step.store(0, x)
+    step.store(1, step.add(step.prev(1), wait))
+    model = g.spec_model(2, [], 2, gen, step)
+    assert model.num_uniforms(True) == 1 and model.num_uniforms(False) == 2 and model.num_normals(False) == 0
+    rng = np.random.default_rng(12)
+    st = g.create_particle_filter(model, n)
+    u = rng.random((1, n))
+    st.set_noise(None, u)
+    g.generate_(st, [3.0, 0.0])
+    x_ref = 0.5 + (2.0 - 0.5) * u[0]
+    assert np.allclose(st.get_state(0), x_ref, rtol=1e-15)
+    assert close(st.log_weights, stats.poisson.logpmf(3, np.exp(x_ref)), 1e-9)
+    tot = np.zeros(n)
+    for t, (y, z) in enumerate([(2.0, 1.4), (5.0, 0.9)], start=1):
+        u = rng.random((2, n))
+        st.set_noise(None, u)
+        incr, = g.particle_filter_step_(st, (t,), (g.UnknownChange,), [y, z])
+        lap = np.where(u[0] < 0.5, 0.1 * np.log(2 * u[0]), -0.1 * np.log(2 * (1 - u[0])))
+        x_ref = x_ref + lap
+        wait = -np.log1p(-u[1]) / 3.0
+        tot = tot + wait
+        w_ref = stats.poisson.logpmf(int(y), np.exp(x_ref)) + stats.cauchy.logpdf(z, x_ref, 0.5) + stats.beta.logpdf(wait / (wait + 1), 2, 3)
+        assert np.allclose(st.get_state(0), x_ref, rtol=1e-14, atol=1e-15) and np.allclose(st.get_state(1), tot, rtol=1e-14)
+        assert close(incr, w_ref, 1e-9)
+    assert st.spec_backend == spec_backend
+    with pytest.raises(g.GenB200Error):        # no closed-form quantile: sampling poisson is not offered
+        bad = g.SpecProgram()
+        bad.store(0, bad.sample("poisson", bad.const(1.0)))
+        g.spec_model(1, [], 1, bad)
+
+
 def test_spec_model_custom_proposal(g, O, spec_backend):
     """A custom proposal written inside the spec (sample from q, observe the model density, subtract q's score) equals
     the built-in LGSSM + AffineNormalProposal and the oracle's weight algebra (trace_translators.jl:854)."""
