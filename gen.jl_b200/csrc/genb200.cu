@@ -1748,11 +1748,12 @@ extern "C" int gb_pf_commit_resample(gb_pf_t *pf, double log_ml_increment) {
 // ------------------------------------------------------------------------------------------
 static int blr_generate(gb_pf *pf, const double *obs, int nobs, bool predrawn) {
   const gb_model &m = pf->model;
-  std::vector<double> X((size_t)kBlrMax * kBlrMax, 0.0), y(kBlrMax, 0.0);
+  std::vector<double> Xt((size_t)kBlrMax * kBlrMax, 0.0), y(kBlrMax, 0.0);   // [pair k][row j][2]
   for (int j = 0; j < m.nobs; j++)
-    for (int d = 0; d < m.D; d++) X[(size_t)j * kBlrMax + d] = m.params[3 + (size_t)j * m.D + d];
+    for (int d = 0; d < m.D; d++) Xt[((size_t)(d / 2) * kBlrMax + j) * 2 + (d & 1)] = m.params[3 + (size_t)j * m.D + d];
   for (int j = 0; j < nobs; j++) y[j] = obs[j];
-  CK(cudaMemcpyToSymbolAsync(c_blr_X, X.data(), X.size() * 8, 0, cudaMemcpyHostToDevice, pf->stream));
+  if (!pf->d_tab) CK(cudaMalloc((void **)&pf->d_tab, Xt.size() * 8));
+  CK(cudaMemcpyAsync(pf->d_tab, Xt.data(), Xt.size() * 8, cudaMemcpyHostToDevice, pf->stream));
   CK(cudaMemcpyToSymbolAsync(c_blr_y, y.data(), y.size() * 8, 0, cudaMemcpyHostToDevice, pf->stream));
   CK(cudaStreamSynchronize(pf->stream));
   BlrArgs a;
@@ -1760,6 +1761,7 @@ static int blr_generate(gb_pf *pf, const double *obs, int nobs, bool predrawn) {
   a.state_out = pf->state[pf->cur ^ 1];
   a.logw = pf->logw;
   a.normals = pf->d_normals;
+  a.Xt = pf->d_tab;
   a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
   a.seed = pf->seed; a.D = m.D; a.nobs = m.nobs; a.sigma = m.params[2];
   a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;

@@ -470,18 +470,23 @@ __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ lo
 
 // ------------------------------------------------------------------------------------------
 // cfg 4: Bayesian linear regression importance sampler (importance.jl:20-36 over
-// w ~ Map(normal)(0,1), y_j ~ normal(x_j . w, sigma); map/generate.jl:10-37).  One thread per
-// sample keeps w[64] in registers; X sits in constant memory so every multiply-add takes its matrix
-// operand from the constant bank (no load instruction, no tensor cores: north_star).
+// w ~ Map(normal)(0,1), y_j ~ normal(x_j . w, sigma); map/generate.jl:10-37).  One thread per sample.
+// The thread never holds w: it keeps the 64 running means m_j = sum_d X[j][d] w[d] in registers and, in a
+// ROLLED loop over pairs of latents, draws (w_2k, w_2k+1) (one Philox block -> one Box-Muller pair), streams
+// them to the trace columns and folds them into all 64 means (128 independent FMAs per pair: no dependency
+// stalls; the loop body is ~600 instructions, so it lives in the instruction cache -- the fully unrolled
+// first version was 117 KB of straight-line code at 2 warps per scheduler and ran at half this speed).
+// X sits in shared memory in the filter's precision, pair-major, and is read by warp-uniform (broadcast)
+// 128-bit loads.  No tensor cores (north_star): CUDA-core FMA at the fp64 rate is the bound.
 // ------------------------------------------------------------------------------------------
 constexpr int kBlrMax = 64;
-__constant__ double c_blr_X[kBlrMax * kBlrMax];   // [n][64] zero padded
 __constant__ double c_blr_y[kBlrMax];
 
 struct BlrArgs {
   void *state_out;   // D columns of stride ld
   void *logw;
   const double *normals;  // PREDRAWN [D][ld]
+  const double *Xt;       // DEVICE [32 pairs][64 rows][2]: X[j][2k], X[j][2k+1], zero padded
   long long n, ld, pid_offset;
   unsigned long long seed;
   int D, nobs;
@@ -491,47 +496,57 @@ struct BlrArgs {
   WeightStats *stats;
 };
 
+template <typename R> struct Pair2;
+template <> struct Pair2<double> { typedef double2 type; };
+template <> struct Pair2<float> { typedef float2 type; };
+
+#ifndef GB_BLR_MINB
+#define GB_BLR_MINB 3
+#endif
 template <typename R, bool PREDRAWN>
-__global__ void __launch_bounds__(128) blr_generate_kernel(const BlrArgs a) {
+__global__ void __launch_bounds__(128, GB_BLR_MINB) blr_generate_kernel(const BlrArgs a) {
+  typedef typename Pair2<R>::type R2;
   __shared__ double s_tab[kMathTabDoubles];
+  __shared__ __align__(16) R s_X[kBlrMax * kBlrMax];
   const MathTables T = stage_math_tables(s_tab);
+  for (int t = threadIdx.x; t < kBlrMax * kBlrMax; t += blockDim.x) s_X[t] = (R)a.Xt[t];
   __syncthreads();
   R *__restrict__ sout = static_cast<R *>(a.state_out);
   R *__restrict__ logw = static_cast<R *>(a.logw);
   const R inv_sigma = R(1) / (R)a.sigma, log_sigma = Math<R>::log_((R)a.sigma);
+  const int npairs = (a.D + 1) / 2;
   double acc = -INFINITY;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
-    R w[kBlrMax];
-    if (PREDRAWN) {
+    const unsigned long long pid = (unsigned long long)(a.pid_offset + i);
+    R m[kBlrMax];
 #pragma unroll
-      for (int d = 0; d < kBlrMax; d++) w[d] = d < a.D ? (R)__ldcs(a.normals + (long long)d * a.ld + i) : R(0);
-    } else {
-      const unsigned long long pid = (unsigned long long)(a.pid_offset + i);
-#pragma unroll
-      for (int d = 0; d < kBlrMax; d += 2) {
-        R e0 = R(0), e1 = R(0);
-        if (d < a.D) philox_normal_pair(a.seed, pid, 0u, (unsigned)(d / 2), T, e0, e1);
-        w[d] = e0;
-        w[d + 1] = (d + 1 < a.D) ? e1 : R(0);
-      }
-    }
-    // normal(0, 1): mu + std * eps = 0 + 1 * eps (normal.jl:128) is exactly eps
-#pragma unroll
-    for (int d = 0; d < kBlrMax; d++)
-      if (d < a.D) st_stream(sout + (long long)d * a.ld + i, w[d]);
-    R lw = R(0);
+    for (int j = 0; j < kBlrMax; j++) m[j] = R(0);
 #pragma unroll 1
-    for (int j = 0; j < a.nobs; j++) {
-      R m0 = R(0), m1 = R(0), m2 = R(0), m3 = R(0);
-#pragma unroll
-      for (int d = 0; d < kBlrMax; d += 4) {
-        m0 = fma((R)c_blr_X[j * kBlrMax + d + 0], w[d + 0], m0);
-        m1 = fma((R)c_blr_X[j * kBlrMax + d + 1], w[d + 1], m1);
-        m2 = fma((R)c_blr_X[j * kBlrMax + d + 2], w[d + 2], m2);
-        m3 = fma((R)c_blr_X[j * kBlrMax + d + 3], w[d + 3], m3);
+    for (int k = 0; k < npairs; k++) {
+      const bool two = 2 * k + 1 < a.D;
+      R e0, e1;
+      if (PREDRAWN) {
+        e0 = (R)__ldcs(a.normals + (long long)(2 * k) * a.ld + i);
+        e1 = two ? (R)__ldcs(a.normals + (long long)(2 * k + 1) * a.ld + i) : R(0);
+      } else {
+        philox_normal_pair(a.seed, pid, 0u, (unsigned)k, T, e0, e1);
+        if (!two) e1 = R(0);
       }
-      lw += logpdf_normal_fast<R>((R)c_blr_y[j], (m0 + m1) + (m2 + m3), inv_sigma, log_sigma);
+      // normal(0, 1): mu + std * eps = 0 + 1 * eps (normal.jl:128) is exactly eps
+      st_stream(sout + (long long)(2 * k) * a.ld + i, e0);
+      if (two) st_stream(sout + (long long)(2 * k + 1) * a.ld + i, e1);
+      const R2 *__restrict__ xr = reinterpret_cast<const R2 *>(s_X + k * (2 * kBlrMax));
+#pragma unroll
+      for (int j = 0; j < kBlrMax; j++) {
+        const R2 x = xr[j];
+        m[j] = fma(x.x, e0, m[j]);
+        m[j] = fma(x.y, e1, m[j]);
+      }
     }
+    R lw = R(0);
+#pragma unroll
+    for (int j = 0; j < kBlrMax; j++)
+      if (j < a.nobs) lw += logpdf_normal_fast<R>((R)c_blr_y[j], m[j], inv_sigma, log_sigma);   // map/generate.jl:16-17, in order
     logw[i] = lw;
     acc = max_nan(acc, (double)lw);
   }
