@@ -172,6 +172,37 @@ def workload_config(args, n_total):
             "parallelism": "particles sharded over %d GPU(s)" % args.gpus}
 
 
+def log_ml_error_check(g):
+    """BASELINE.json's metric ends with "log-ML error": configs[0] (1-D linear-Gaussian SSM, N = 1000, T = 100,
+    systematic resampling at ESS < N/2) has an exact answer, the Kalman-filter log marginal likelihood computed here."""
+    import math
+    ys = F.lgssm_series(101)
+    m0, s0, a, q, r = F.LGSSM["m0"], F.LGSSM["s0"], F.LGSSM["a"], F.LGSSM["q"], F.LGSSM["r"]
+    m, P, exact = m0, s0 * s0, 0.0
+    for t, y in enumerate(ys):
+        if t > 0:
+            m, P = a * m, a * a * P + q * q
+        S = P + r * r
+        exact += -0.5 * (math.log(2 * math.pi * S) + (y - m) ** 2 / S)
+        m, P = m + P / S * (y - m), P * (1 - P / S)
+    model = g.lgssm_model(**F.LGSSM)
+    out = {}
+    for dtype in ("f64", "f32"):
+        ests = []
+        for seed in range(32):
+            st = g.initialize_particle_filter(model, (0,), ys[0], 1000, dtype=dtype, seed=seed)
+            for t in range(1, len(ys)):
+                g.maybe_resample_(st, ess_threshold=500, resampler="systematic")
+                g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+            ests.append(g.log_ml_estimate(st))
+        mean = sum(ests) / len(ests)
+        sd = (sum((e - mean) ** 2 for e in ests) / (len(ests) - 1)) ** 0.5
+        out[dtype] = {"mean_error": mean - exact, "sd_over_seeds": sd, "standard_error": sd / len(ests) ** 0.5}
+    return {"config": "BASELINE.json configs[0]: 1-D linear-Gaussian SSM, N=1000, T=100, 32 seeds, systematic @ ESS<N/2",
+            "exact": "Kalman filter log marginal likelihood", "exact_value": exact, **out,
+            "note": "E[log Z_hat] <= log Z (Jensen): the expected bias is about -var/2"}
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -351,6 +382,7 @@ def run_genb200(args):
                                     "frac": whole_step_gbs / peak, "frac_of_8TBs_spec": whole_step_gbs / 8000.0}},
         "kernels": kernels,
         "cpu_baseline": cpu,
+        "log_ml_error": log_ml_error_check(g) if world == 1 else None,
     }
     emit(out)
     if dist is not None:

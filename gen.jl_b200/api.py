@@ -412,7 +412,16 @@ class DeviceParticleFilterState:
             return False
         return all(np.array_equal(self.get_state(f), other.get_state(f)) for f in range(self.state_dim))
 
-    __hash__ = None
+    # Base.hash (particle_filter.jl:59-63): over the same fields == compares, so equal states hash equal
+    def __hash__(self):
+        import hashlib
+        h = hashlib.blake2b(digest_size=8)
+        for f in range(self.state_dim):
+            h.update(self.get_state(f).tobytes())
+        h.update(self.log_weights.tobytes())
+        h.update(np.float64(self.log_ml_est).tobytes())
+        h.update(self.parents.tobytes())
+        return int.from_bytes(h.digest(), "little", signed=True)
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -448,9 +448,9 @@ def test_pf_state_copy_and_fields(g):
     st = g.initialize_particle_filter(m, (0,), 0.1, 1000, seed=3)
     assert np.array_equal(st.parents, np.arange(1, 1001)) and st.log_ml_est == 0.0
     c = st.copy()
-    assert c == st and c is not st
+    assert c == st and c is not st and hash(c) == hash(st)     # Base.copy / == / hash (particle_filter.jl:43-63)
     g.particle_filter_step_(st, (1,), (g.UnknownChange,), 0.2)
-    assert not (c == st)
+    assert not (c == st) and hash(c) != hash(st)
     lw = np.linspace(-3, 0, 1000)
     c.log_weights = lw
     assert np.array_equal(c.log_weights, lw)
