@@ -29,6 +29,12 @@ typedef unsigned __int128 u128;
 
 namespace gb {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream drains; it must pdl_wait() before touching anything the predecessor wrote.
+// pdl_trigger() lets the successor's CTAs be scheduled as this grid's CTAs retire.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 constexpr int kBlock = 256;          // threads per CTA for every streaming kernel
 constexpr int kTile = 2048;          // particles per scan tile (kBlock * kItems)
 constexpr int kItems = kTile / kBlock;

@@ -327,6 +327,28 @@ struct LaunchScope {
     __VA_ARGS__;                  \
   } while (0)
 
+// Kernels of the per-step chain (weight statistics -> super-tile scan -> ancestors -> overflow -> step) are launched
+// with programmatic dependent launch: each starts while its predecessor drains and waits (pdl_wait) before reading.
+// GENB200_PDL=0 launches them plainly.
+static bool pdl_enabled() {
+  static const bool on = [] { const char *e = getenv("GENB200_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... P, typename... A>
+static cudaError_t klaunch(void (*kern)(P...), unsigned grid, unsigned block, cudaStream_t st, A &&...args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
+
 static std::unordered_map<const void *, int> g_occ;
 template <typename F> static int grid_for(gb_pf *pf, F kernel, long long work_items, int block) {
   const void *key = (const void *)kernel;
@@ -521,7 +543,7 @@ static int launch_step_t(gb_pf *pf, const StepArgs &a, bool predrawn, int gather
   {                                                                                        \
     auto kern = step_kernel<R, KIND, PK, INIT, PD, GA>;                                    \
     int grid = grid_for(pf, kern, nvec, kBlock);                                           \
-    LAUNCH(pf, GB_K_STEP, kern<<<grid, kBlock, 0, pf->stream>>>(a));                       \
+    LAUNCH(pf, GB_K_STEP, klaunch(kern, grid, kBlock, pf->stream, a));                     \
   }
   if (INIT) {
     if (predrawn) GO(true, 0) else GO(false, 0)
@@ -639,7 +661,17 @@ static int launch_spec(gb_pf *pf, const double *obs, int nobs, bool predrawn, in
     }
     void *params[] = {jm->fast ? (void *)&sa : (void *)&a};
     CUresult cr = CUDA_SUCCESS;
-    LAUNCH(pf, GB_K_STEP, cr = g_jit.LaunchKernel(jm->fn[v], grid, 1, 1, kBlock, 1, 1, 0, (CUstream)pf->stream, params, nullptr));
+    CUlaunchConfig lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDimX = grid; lc.gridDimY = lc.gridDimZ = 1;
+    lc.blockDimX = kBlock; lc.blockDimY = lc.blockDimZ = 1;
+    lc.hStream = (CUstream)pf->stream;
+    CUlaunchAttribute lat[1];
+    lat[0].id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+    lat[0].value.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = lat;
+    lc.numAttrs = pdl_enabled() ? 1 : 0;
+    LAUNCH(pf, GB_K_STEP, cr = g_jit.LaunchKernelEx(&lc, jm->fn[v], params, nullptr));
     if (cr != CUDA_SUCCESS) {
       const char *es = nullptr;
       g_jit.GetErrorString(cr, &es);
@@ -660,7 +692,7 @@ static int launch_spec(gb_pf *pf, const double *obs, int nobs, bool predrawn, in
   {                                                                                        \
     auto kern = spec_kernel<R, INIT, PD, GA>;                                              \
     int grid = grid_for(pf, kern, pf->n, kBlock);                                          \
-    LAUNCH(pf, GB_K_STEP, kern<<<grid, kBlock, 0, pf->stream>>>(a));                       \
+    LAUNCH(pf, GB_K_STEP, klaunch(kern, grid, kBlock, pf->stream, a));                     \
   }
   if (INIT) { if (predrawn) GO(true, 0) else GO(false, 0) }
   else if (predrawn) { if (gather) GO(true, 1) else GO(true, 0) }
@@ -984,11 +1016,11 @@ static int ensure_max(gb_pf *pf, const void *logw) {
   if (pf->dtype == GB_F64) {
     auto kern = max_kernel<double>;
     int grid = grid_for(pf, kern, pf->n, kBlock);
-    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)logw, pf->n, (double *)pf->partials, pf->ticket, pf->d_stats));
+    LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const double *)logw, pf->n, (double *)pf->partials, pf->ticket, pf->d_stats));
   } else {
     auto kern = max_kernel<float>;
     int grid = grid_for(pf, kern, pf->n, kBlock);
-    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)logw, pf->n, (double *)pf->partials, pf->ticket, pf->d_stats));
+    LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const float *)logw, pf->n, (double *)pf->partials, pf->ticket, pf->d_stats));
   }
   CK(cudaGetLastError());
   pf->wstate = W_MAX;
@@ -1006,13 +1038,13 @@ static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_devic
   if (pf->dtype == GB_F64) {
     auto kern = wstats_kernel<double>;
     int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
-    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)logw, pf->n, m_arg, from_device ? 1 : 0, bits, (unsigned long long *)pf->tile_q,
-                                                                     pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl));
+    LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const double *)logw, pf->n, m_arg, from_device ? 1 : 0, bits,
+                                      (unsigned long long *)pf->tile_q, pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl));
   } else {
     auto kern = wstats_kernel<float>;
     int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
-    LAUNCH(pf, GB_K_FINALIZE, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)logw, pf->n, m_arg, from_device ? 1 : 0, bits, (unsigned long long *)pf->tile_q,
-                                                                     pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl));
+    LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const float *)logw, pf->n, m_arg, from_device ? 1 : 0, bits,
+                                      (unsigned long long *)pf->tile_q, pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl));
   }
   CK(cudaGetLastError());
   if (sync_host) {
@@ -1279,17 +1311,18 @@ template <typename R>
 static int launch_systematic(gb_pf *pf, const void *logw, double m, uint64_t q_offset, uint64_t q_total, uint32_t u0,
                              const AncOut &ao, const RunCtl *ctl = nullptr, int plan_preset = 0) {
   const int bits = quant_bits(pf->n_global);
-  LAUNCH(pf, GB_K_TILESCAN, superscan_kernel<<<1, 1024, 0, pf->stream>>>(pf->nsuper, pf->super_q, pf->super_excl, pf->d_plan, q_offset,
-                                                                          q_total, pf->n_global, u0, pf->oflow_count, plan_preset));
+  LAUNCH(pf, GB_K_TILESCAN, klaunch(superscan_kernel, 1, 1024, pf->stream, pf->nsuper, pf->super_q, pf->super_excl, pf->d_plan, q_offset, q_total,
+                                    pf->n_global, u0, pf->oflow_count, plan_preset));
   CK(cudaGetLastError());
   auto kern = ancestors_sys_kernel<R>;
-  LAUNCH(pf, GB_K_ANCESTORS, kern<<<(unsigned)pf->ntiles, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->tile_q, pf->super_excl,
-                                                                                    pf->d_plan, ao, pf->oflow, pf->oflow_count, ctl, pf->d_stats));
+  LAUNCH(pf, GB_K_ANCESTORS, klaunch(kern, (unsigned)pf->ntiles, kBlock, pf->stream, (const R *)logw, pf->n, m, bits, (const uint64_t *)pf->tile_q,
+                                     (const unsigned long long *)pf->super_excl, (const ResamplePlan *)pf->d_plan, ao, pf->oflow, pf->oflow_count, ctl,
+                                     (const WeightStats *)pf->d_stats));
   CK(cudaGetLastError());
   auto okern = overflow_sys_kernel<R>;
-  LAUNCH(pf, GB_K_ANCESTORS, okern<<<pf->num_sms * 4, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->d_plan, ao, pf->oflow,
-                                                                                pf->oflow_count, (unsigned long long *)pf->tile_q, pf->ntiles, ctl,
-                                                                                pf->d_stats));
+  LAUNCH(pf, GB_K_ANCESTORS, klaunch(okern, (unsigned)pf->num_sms * 4, kBlock, pf->stream, (const R *)logw, pf->n, m, bits, (const ResamplePlan *)pf->d_plan, ao,
+                                     (const OverflowEntry *)pf->oflow, (const unsigned int *)pf->oflow_count, (unsigned long long *)pf->tile_q, pf->ntiles, ctl,
+                                     (const WeightStats *)pf->d_stats));
   CK(cudaGetLastError());
   pf->tiles_valid = false;   // superscan / overflow zeroed the accumulators for the next statistics pass
   pf->ws_clean = true;

@@ -567,6 +567,8 @@ __global__ void __launch_bounds__(1024) superscan_kernel(long long nsuper, unsig
                                                          long long n_global, uint32_t u0, unsigned int *overflow_count,
                                                          int plan_preset) {
   __shared__ uint64_t s_w[33];
+  pdl_trigger();
+  pdl_wait();
   const int T = 1024;
   const long long per = (nsuper + T - 1) / T;
   const long long lo = (long long)threadIdx.x * per, hi = lo + per < nsuper ? lo + per : nsuper;
@@ -759,6 +761,8 @@ __global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const R *__restri
                                                                unsigned int *__restrict__ oflow_count,
                                                                const RunCtl *__restrict__ ctl, const WeightStats *__restrict__ dstats) {
   __shared__ TileSmem sm;
+  pdl_trigger();
+  pdl_wait();
   if (ctl) {                       // fused multi-step run: decision and reference max live on the device
     if (!ctl->do_resample) return;
     m = dstats->m;
@@ -784,6 +788,8 @@ __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restric
                                                               unsigned long long *__restrict__ tile_q, long long ntiles,
                                                               const RunCtl *__restrict__ ctl, const WeightStats *__restrict__ dstats) {
   __shared__ TileSmem sm;
+  pdl_trigger();
+  pdl_wait();
   if (ctl) m = dstats->m;
   // the sweep is done with the per-tile totals: leave the accumulator clean for the next statistics pass
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < ntiles; i += (long long)gridDim.x * kBlock) tile_q[i] = 0;

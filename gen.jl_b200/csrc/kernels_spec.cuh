@@ -33,8 +33,10 @@ __constant__ double c_spec_params[kSpecMaxParams];
 template <typename R, bool INIT, bool PREDRAWN, int GATHER>
 __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
   __shared__ double s_tab[kMathTabDoubles];
+  pdl_trigger();
   const MathTables T = stage_math_tables(s_tab);
   __syncthreads();
+  pdl_wait();
   const R *__restrict__ sin = static_cast<const R *>(a.state_in);
   R *__restrict__ sout = static_cast<R *>(a.state_out);
   R *__restrict__ logw = static_cast<R *>(a.logw);

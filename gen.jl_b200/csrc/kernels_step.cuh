@@ -161,8 +161,10 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
   typedef Transition<R, KIND, PK, INIT> Tr;
   constexpr int V = StepV<R>::V, S = Tr::S, NN = Tr::NN, NU = Tr::NU;
   __shared__ double s_tab[kMathTabDoubles];
-  const MathTables T = stage_math_tables(s_tab);
+  pdl_trigger();
+  const MathTables T = stage_math_tables(s_tab);   // constants only: overlaps the predecessor's tail
   __syncthreads();
+  pdl_wait();
   const R *__restrict__ sin = static_cast<const R *>(a.state_in);
   R *__restrict__ sout = static_cast<R *>(a.state_out);
   R *__restrict__ logw = static_cast<R *>(a.logw);
@@ -275,6 +277,8 @@ template <typename R>
 __global__ void __launch_bounds__(kBlock) max_kernel(const R *__restrict__ logw, long long n, double *partials,
                                                      unsigned int *ticket, WeightStats *stats) {
   constexpr int V = VecOf<R>::V, U = 4;
+  pdl_trigger();
+  pdl_wait();
   double acc = -INFINITY;
   const long long nvec = (n + V - 1) / V;
   const long long stride = (long long)gridDim.x * kBlock;
@@ -363,6 +367,8 @@ __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ lo
   __shared__ uint64_t s_u64[kBlock / 32];
   __shared__ double2 s_d2[kBlock / 32];
   __shared__ bool s_last;
+  pdl_trigger();
+  pdl_wait();
   const double m = m_from_device ? __ldcg(&stats->m) : m_arg;
   const long long ntiles = (n + kTile - 1) / kTile;
   const long long nseg = ntiles * (kTile / kSeg);
