@@ -1028,7 +1028,11 @@ static int ensure_max(gb_pf *pf, const void *logw) {
 }
 // one pass over the log weights: (s1, s2) w.r.t. the reference max + quantised tile / super-tile totals;
 // the reference max is read from d_stats->m (from_device) or passed by value (sharded: global max)
-static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_device, bool sync_host = true, RunCtl *ctl = nullptr) {
+static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_device, bool sync_host = true, RunCtl *ctl = nullptr,
+                      const FusedPlan *fused = nullptr) {
+  FusedPlan fp;
+  memset(&fp, 0, sizeof(fp));
+  if (fused) fp = *fused;
   const int bits = quant_bits(pf->n_global);
   if (!pf->ws_clean) {       // the systematic sweep leaves both accumulators zeroed; other paths do not
     CK(cudaMemsetAsync(pf->super_q, 0, (size_t)(pf->nsuper + 1) * 8, pf->stream));
@@ -1039,12 +1043,12 @@ static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_devic
     auto kern = wstats_kernel<double>;
     int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
     LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const double *)logw, pf->n, m_arg, from_device ? 1 : 0, bits,
-                                      (unsigned long long *)pf->tile_q, pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl));
+                                      (unsigned long long *)pf->tile_q, pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl, fp));
   } else {
     auto kern = wstats_kernel<float>;
     int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
     LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const float *)logw, pf->n, m_arg, from_device ? 1 : 0, bits,
-                                      (unsigned long long *)pf->tile_q, pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl));
+                                      (unsigned long long *)pf->tile_q, pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl, fp));
   }
   CK(cudaGetLastError());
   if (sync_host) {
@@ -1309,10 +1313,12 @@ static int fetch_plan(gb_pf *pf) {
 // shard's offspring slots; single shard: q_offset = 0, q_total = 0 (= the local total), anc_base = 0.
 template <typename R>
 static int launch_systematic(gb_pf *pf, const void *logw, double m, uint64_t q_offset, uint64_t q_total, uint32_t u0,
-                             const AncOut &ao, const RunCtl *ctl = nullptr, int plan_preset = 0) {
+                             const AncOut &ao, const RunCtl *ctl = nullptr, int plan_preset = 0, bool plan_done = false) {
   const int bits = quant_bits(pf->n_global);
-  LAUNCH(pf, GB_K_TILESCAN, klaunch(superscan_kernel, 1, 1024, pf->stream, pf->nsuper, pf->super_q, pf->super_excl, pf->d_plan, q_offset, q_total,
-                                    pf->n_global, u0, pf->oflow_count, plan_preset));
+  if (!plan_done) {   // (fused run: the statistics kernel's last CTA already scanned the super-tiles and wrote the plan)
+    LAUNCH(pf, GB_K_TILESCAN, klaunch(superscan_kernel, 1, 1024, pf->stream, pf->nsuper, pf->super_q, pf->super_excl, pf->d_plan, q_offset, q_total,
+                                      pf->n_global, u0, pf->oflow_count, plan_preset));
+  }
   CK(cudaGetLastError());
   auto kern = ancestors_sys_kernel<R>;
   LAUNCH(pf, GB_K_ANCESTORS, klaunch(kern, (unsigned)pf->ntiles, kBlock, pf->stream, (const R *)logw, pf->n, m, bits, (const uint64_t *)pf->tile_q,
@@ -1466,10 +1472,11 @@ extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double
   const AncOut ao{pf->anc, 0, pf->n_global, nullptr, 0, 0};
   for (int t = 0; t < T; t++) {
     // maybe_resample!: statistics + decision on the device, then the (conditional) systematic sweep
-    if ((rc = run_wstats(pf, pf->logw, 0.0, true, false, pf->d_ctl))) return rc;
     const uint32_t u0 = philox_block(pf->seed, 0, (uint32_t)pf->step, PK_RESAMPLE, 0).x;
-    rc = pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, 0.0, 0, 0, u0, ao, pf->d_ctl)
-                             : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, u0, ao, pf->d_ctl);
+    const FusedPlan fp{pf->d_plan, pf->super_excl, pf->oflow_count, pf->n_global, u0};
+    if ((rc = run_wstats(pf, pf->logw, 0.0, true, false, pf->d_ctl, &fp))) return rc;
+    rc = pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, 0.0, 0, 0, u0, ao, pf->d_ctl, 0, true)
+                             : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, u0, ao, pf->d_ctl, 0, true);
     if (rc) return rc;
     // particle_filter_step!
     if ((rc = launch_model(pf, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false, false, 2))) return rc;

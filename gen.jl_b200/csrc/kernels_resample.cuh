@@ -29,21 +29,7 @@ GB_HD U128 u128_make(uint64_t lo) { return U128{lo, 0}; }
 
 enum { SWEEP_SYSTEMATIC = 0, SWEEP_RESIDUAL = 1, SWEEP_CDF = 2 };
 
-// Everything the ancestors pass needs to know about the global sweep; written by tilescan.
-struct ResamplePlan {
-  SweepParams sp;
-  uint64_t q_offset;     // integer CDF mass of the shards before this one
-  long long slot_lo;     // first / one-past-last global output slot filled by this shard's particles
-  long long slot_hi;
-  long long n_global;
-};
-
 // ---- 64-bit / 128-bit block primitives built on warp shuffles ----
-GB_D uint64_t shfl_up_u64(uint64_t v, int d) {
-  uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d);
-  uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), d);
-  return ((uint64_t)hi << 32) | lo;
-}
 GB_D uint64_t shfl_u64(uint64_t v, int src) {
   uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
   uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
@@ -569,56 +555,7 @@ __global__ void __launch_bounds__(1024) superscan_kernel(long long nsuper, unsig
   __shared__ uint64_t s_w[33];
   pdl_trigger();
   pdl_wait();
-  const int T = 1024;
-  const long long per = (nsuper + T - 1) / T;
-  const long long lo = (long long)threadIdx.x * per, hi = lo + per < nsuper ? lo + per : nsuper;
-  uint64_t a = 0;
-  for (long long i = lo; i < hi; i++) a += super_q[i];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint64_t inc = a;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint64_t o = shfl_up_u64(inc, d);
-    if (lane >= d) inc += o;
-  }
-  if (lane == 31) s_w[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint64_t w = s_w[lane], winc = w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint64_t o = shfl_up_u64(winc, d);
-      if (lane >= d) winc += o;
-    }
-    s_w[lane] = winc - w;
-    if (lane == 31) s_w[32] = winc;
-  }
-  __syncthreads();
-  uint64_t run = s_w[warp] + (inc - a);
-  const uint64_t total = s_w[32];
-  for (long long i = lo; i < hi; i++) {
-    uint64_t v = super_q[i];
-    super_excl[i] = run;
-    super_q[i] = 0;              // leave the accumulator clean for the next statistics pass (no memset launch)
-    run += v;
-  }
-  if (threadIdx.x == 0) {
-    super_excl[nsuper] = total;
-    if (!plan_preset) {     // (preset: shard_plan_kernel already wrote the global sweep parameters)
-      SweepParams sp;
-      sp.q_total = q_total_given ? q_total_given : total;
-      sp.q_inv = 1.0 / (double)sp.q_total;
-      sp.dscale = (uint64_t)n_global << 32;
-      sp.ratio = (double)n_global / (double)sp.q_total;
-      sp.u0 = u0;
-      plan->sp = sp;
-      plan->q_offset = q_offset;
-      plan->n_global = n_global;
-      plan->slot_lo = slots_below(q_offset, sp);
-      plan->slot_hi = slots_below(q_offset + total, sp);
-    }
-    *overflow_count = 0;
-  }
+  superscan_block(nsuper, super_q, super_excl, plan, q_offset, q_total_given, n_global, u0, overflow_count, plan_preset, s_w);
 }
 
 // Where the ancestors of output slot k go: slots this shard owns -> own[k - own_lo] (the shard's `anc`

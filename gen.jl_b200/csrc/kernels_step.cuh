@@ -298,6 +298,88 @@ __global__ void __launch_bounds__(kBlock) max_kernel(const R *__restrict__ logw,
   publish_max(acc, partials, ticket, stats);
 }
 
+// Everything the ancestors pass needs to know about the global sweep; written by the super-tile scan.
+struct ResamplePlan {
+  SweepParams sp;
+  uint64_t q_offset;     // integer CDF mass of the shards before this one
+  long long slot_lo;     // first / one-past-last global output slot filled by this shard's particles
+  long long slot_hi;
+  long long n_global;
+};
+
+GB_D uint64_t shfl_up_u64(uint64_t v, int d) {
+  uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d);
+  uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), d);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// Exclusive scan of the super-tile totals by ONE CTA (any multiple of 32 threads up to 1024) + the sweep plan.
+// Runs as its own tiny kernel (superscan_kernel) or, in the fused multi-step run, in the tail of the statistics
+// kernel's last CTA, which saves a launch per step.  Leaves super_q zeroed for the next statistics pass.
+GB_D void superscan_block(long long nsuper, unsigned long long *__restrict__ super_q, unsigned long long *__restrict__ super_excl,
+                          ResamplePlan *plan, uint64_t q_offset, uint64_t q_total_given, long long n_global, uint32_t u0,
+                          unsigned int *overflow_count, int plan_preset, uint64_t *s_w /* 33 */) {
+  const int T = blockDim.x;
+  const long long per = (nsuper + T - 1) / T;
+  const long long lo = (long long)threadIdx.x * per, hi = lo + per < nsuper ? lo + per : nsuper;
+  uint64_t a = 0;
+  for (long long i = lo; i < hi; i++) a += __ldcg(super_q + i);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = T >> 5;
+  uint64_t inc = a;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t o = shfl_up_u64(inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t w = lane < nwarp ? s_w[lane] : 0, winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint64_t o = shfl_up_u64(winc, d);
+      if (lane >= d) winc += o;
+    }
+    s_w[lane] = winc - w;
+    if (lane == 31) s_w[32] = winc;
+  }
+  __syncthreads();
+  uint64_t run = s_w[warp] + (inc - a);
+  const uint64_t total = s_w[32];
+  for (long long i = lo; i < hi; i++) {
+    uint64_t v = __ldcg(super_q + i);
+    super_excl[i] = run;
+    super_q[i] = 0;              // leave the accumulator clean for the next statistics pass (no memset launch)
+    run += v;
+  }
+  if (threadIdx.x == 0) {
+    super_excl[nsuper] = total;
+    if (!plan_preset) {     // (preset: shard_plan_kernel already wrote the global sweep parameters)
+      SweepParams sp;
+      sp.q_total = q_total_given ? q_total_given : total;
+      sp.q_inv = 1.0 / (double)sp.q_total;
+      sp.dscale = (uint64_t)n_global << 32;
+      sp.ratio = (double)n_global / (double)sp.q_total;
+      sp.u0 = u0;
+      plan->sp = sp;
+      plan->q_offset = q_offset;
+      plan->n_global = n_global;
+      plan->slot_lo = slots_below(q_offset, sp);
+      plan->slot_hi = slots_below(q_offset + total, sp);
+    }
+    *overflow_count = 0;
+  }
+}
+
+// the sweep plan computed in the tail of the statistics kernel (plan == nullptr: not fused)
+struct FusedPlan {
+  ResamplePlan *plan;
+  unsigned long long *super_excl;
+  unsigned int *overflow_count;
+  long long n_global;
+  uint32_t u0;
+};
+
 // ------------------------------------------------------------------------------------------
 // wstats: e_i = exp(lw_i - m) once per particle ->
 //   s1 = sum e, s2 = sum e^2            (logsumexp / ESS, fp64)
@@ -361,10 +443,11 @@ template <typename R>
 __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ logw, long long n, double m_arg, int m_from_device,
                                                         int bits, unsigned long long *__restrict__ tile_q,
                                                         unsigned long long *__restrict__ super_q, double2 *partials,
-                                                        unsigned int *ticket, WeightStats *stats, RunCtl *ctl) {
+                                                        unsigned int *ticket, WeightStats *stats, RunCtl *ctl, const FusedPlan fp) {
   constexpr int V = VecOf<R>::V;
   constexpr int kSeg = 256, kPerLane = kSeg / 32, kLoads = kPerLane / V;
   __shared__ uint64_t s_u64[kBlock / 32];
+  __shared__ uint64_t s_u64_33[33];
   __shared__ double2 s_d2[kBlock / 32];
   __shared__ bool s_last;
   pdl_trigger();
@@ -471,6 +554,10 @@ __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ lo
       }
     }
     *ticket = 0;
+  }
+  if (fp.plan) {   // fused multi-step run: the super-tile scan + sweep plan ride on this CTA (one launch less per step)
+    __syncthreads();
+    superscan_block(nsuper, super_q, fp.super_excl, fp.plan, 0, 0, fp.n_global, fp.u0, fp.overflow_count, 0, s_u64_33);
   }
 }
 
