@@ -308,7 +308,11 @@ def run_genb200(args):
     e0.record()
     lml = None
     for _ in range(args.steps):
-        lml = step(t, sync_scalar=True)
+        if world > 1 and args.e2e_api == "run":
+            spf.run_([zs[t]], ess_threshold=thr)       # one observation per call, passed from host memory
+            lml = spf.log_ml_estimate()                # device -> host read of the step's result
+        else:
+            lml = step(t, sync_scalar=True)
         t += 1
     e1.record()
     barrier()
@@ -420,6 +424,9 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=20_000_000)
     ap.add_argument("--ref-particles", type=int, default=20_000_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-api", default="sync", choices=["sync", "run"],
+                    help="multi-GPU end-to-end loop: maybe_resample_/particle_filter_step_ per step (sync) or run_ with one "
+                         "observation per call (run)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

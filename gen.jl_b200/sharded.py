@@ -214,6 +214,11 @@ class ShardedParticleFilter:
             self.ext_caps = [((c // 4 + 2047) // 2048 + 1) * 2048 for c in self.counts]
             assert self.ops.ext_capacity() == self.ext_caps[self.rank]
         self.force_staged = False
+        # global weight statistics are cached until the weights change (log_ml_estimate followed by maybe_resample!
+        # costs one statistics pass and one pair of collectives, as on a single GPU); every rank makes the same
+        # sequence of calls, so all ranks hit or miss together
+        self._wver = 0
+        self._stats_cache = (-1, None)
 
     # ---- collectives (tiny) ----
     def _allreduce_max(self, x):
@@ -267,12 +272,14 @@ class ShardedParticleFilter:
     def initialize(self, observations, proposal=None, proposal_args=()):
         api.generate_(self.local, observations, proposal, proposal_args)
         self.step = 0
+        self._wver += 1
         return self
 
     def particle_filter_step_(self, new_args, observations, proposal=None, proposal_args=(), return_incr=False):
         out = api.particle_filter_step_(self.local, new_args, (api.UnknownChange,), observations, proposal, proposal_args,
                                         return_incr=return_incr)
         self.step += 1
+        self._wver += 1
         return out
 
     def rejuvenate_(self, observations, move="resimulate", drift_std=0.0):
@@ -326,12 +333,20 @@ class ShardedParticleFilter:
             self.ops.async_step(obs)
             self.step += 1
         nres = self.ops.async_finish()
+        self._wver += 1
         if self.local is not None and self.local._last_t is not None:
             self.local._last_t += len(observations_seq)
         return nres
 
     def _global_stats(self):
         """Global (m, lse, ess) and the gathered integer masses (particle_filter.jl:3-12 over all shards)."""
+        if self._stats_cache[0] == self._wver:
+            return self._stats_cache[1]
+        out = self._global_stats_uncached()
+        self._stats_cache = (self._wver, out)
+        return out
+
+    def _global_stats_uncached(self):
         if self.device.type == "cuda" and self.world > 1:
             # collectives run directly on the shard's device-resident statistics record: all-reduce(max) of
             # m in place, statistics pass w.r.t. that m, all-gather of the records, ONE device->host read
@@ -370,6 +385,7 @@ class ShardedParticleFilter:
             print("effective sample size: %s, doing resample: %s" % (ess, ess < thr))
         if not (ess < thr):                                  # :256, strict; NaN compares false
             return False
+        self._wver += 1                                      # the weights are about to become 0 (:266)
         u0 = api.philox_resample_u0(self.seed, self.step)
         q_total, pref, ranges, send = plan_exchange(qs, self.n_global, self.offs, u0)
         me, W = self.rank, self.world
