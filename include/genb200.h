@@ -138,6 +138,7 @@ int gb_pf_rejuvenate(gb_pf_t *pf, int move, const double *obs, int nobs, double 
  * with NVRTC on first use, per (model, dtype, device).  If libnvrtc / libcuda cannot be opened, or with
  * GENB200_SPEC_JIT=0 in the environment, the generic interpreter kernel runs the same program instead (same device
  * functions: identical states, weights equal to rounding of constant-folded logs).
+ * GENB200_JIT_CACHE=<dir> keeps the compiled programs on disk (file name = hash of source + headers + dtype).
  *   gb_spec_jit_source   the generated translation unit (buf may be NULL to query *needed)
  *   gb_spec_jit_compile  compile only (no GPU needed); GB_EUNSUPPORTED + the NVRTC log in gb_last_error() on failure
  *   gb_pf_spec_backend   which kernel the filter's last generate/step ran: 1 specialised, 0 interpreter, -1 n/a */

@@ -220,3 +220,27 @@ def test_spec_programs_lower_to_cuda_and_compile_for_sm100a_without_a_gpu(g):
         assert g.spec_jit_compile(model, dtype) > 10000   # a cubin came back
     with pytest.raises(g.GenB200Error):
         g.spec_jit_compile(g.lgssm_model(), "f64")        # presets are compiled ahead of time
+
+
+def test_spec_jit_disk_cache(g, tmp_path, monkeypatch):
+    """GENB200_JIT_CACHE=<dir>: the compiled program is stored under a hash of (source, headers, dtype) and reused."""
+    import time
+    monkeypatch.setenv("GENB200_JIT_CACHE", str(tmp_path))
+
+    def model(c):
+        gen = g.SpecProgram()
+        x = gen.sample_normal(gen.const(c), gen.const(1.0))
+        gen.observe_normal(gen.obs(0), x, gen.const(0.5))
+        gen.store(0, x)
+        return g.spec_model(1, [], 1, gen)
+    t0 = time.perf_counter()
+    nb = g.spec_jit_compile(model(0.25), "f64")
+    t_cold = time.perf_counter() - t0
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert len(files) == 1 and files[0].startswith("genb200_") and files[0].endswith(".jit")
+    t0 = time.perf_counter()
+    assert g.spec_jit_compile(model(0.25), "f64") == nb            # a new model handle with the same program: cache hit
+    assert time.perf_counter() - t0 < t_cold / 5
+    g.spec_jit_compile(model(0.5), "f64")                           # different literal -> different program
+    g.spec_jit_compile(model(0.25), "f32")                          # different dtype -> different program
+    assert len(list(tmp_path.iterdir())) == 3
