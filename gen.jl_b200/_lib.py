@@ -93,6 +93,7 @@ SIGNATURES = {
     "gb_pf_offspring_local": (i, [vp, i64, i64]),
     "gb_pf_import_ext": (i, [vp, i64, i64, i64, vp]),
     "gb_pf_commit_resample_lazy": (i, [vp, d]),
+    "gb_pf_async_commit": (i, [vp, d]),
     "gb_pf_export_offspring": (i, [vp, i64, i64, vp]),
     "gb_pf_import_rows": (i, [vp, i64, i64, vp]),
     "gb_pf_commit_resample": (i, [vp, d]),

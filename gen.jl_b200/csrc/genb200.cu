@@ -1724,6 +1724,14 @@ extern "C" int gb_pf_commit_resample_lazy(gb_pf_t *pf, double log_ml_increment) 
   if (!pf->lazy) rc = run_gather(pf);
   return rc;
 }
+// host-side bookkeeping of a resample the CALLER decided (synchronous maybe_resample!) whose offspring were exchanged by
+// the device-planned peer stores (gb_pf_async_plan / _sweep / _export + the caller's barrier)
+extern "C" int gb_pf_async_commit(gb_pf_t *pf, double log_ml_increment) {
+  REQ(pf && pf->a_world > 0, "gb_pf_async_commit: call gb_pf_async_setup first");
+  int rc = gb_pf_commit_resample_lazy(pf, log_ml_increment);
+  if (pf->a_world > 1) pf->ext_used = true;
+  return rc;
+}
 extern "C" int64_t gb_pf_block_bytes(const gb_pf_t *pf, int64_t count) {
   if (!pf || count < 0) return -1;
   const int64_t raw = count * (8 + (int64_t)pf->S * (int64_t)pf->esz);

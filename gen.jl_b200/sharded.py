@@ -127,6 +127,9 @@ class ShardOps:
     def commit_lazy(self, log_ml_increment):
         L.check(L.lib().gb_pf_commit_resample_lazy(self.h, log_ml_increment))
 
+    def async_commit(self, log_ml_increment):
+        L.check(L.lib().gb_pf_async_commit(self.h, log_ml_increment))
+
     def log_ml_est(self):
         return self.state.log_ml_est
 
@@ -214,6 +217,7 @@ class ShardedParticleFilter:
             self.ext_caps = [((c // 4 + 2047) // 2048 + 1) * 2048 for c in self.counts]
             assert self.ops.ext_capacity() == self.ext_caps[self.rank]
         self.force_staged = False
+        self.use_p2p = True           # synchronous maybe_resample_: exchange by peer stores (False: all-to-all-v of blocks)
         # global weight statistics are cached until the weights change (log_ml_estimate followed by maybe_resample!
         # costs one statistics pass and one pair of collectives, as on a single GPU); every rank makes the same
         # sequence of calls, so all ranks hit or miss together
@@ -292,6 +296,19 @@ class ShardedParticleFilter:
         self.dist.all_reduce(t, group=self.group)
         return int(t.item())
 
+    def _attach_peers(self):
+        """Exchange CUDA IPC handles of the shards' buffers once (collective), so that offspring can be written straight
+        into the owning shard's memory over NVLink."""
+        if self._peers_attached or self.world == 1:
+            return
+        bundles = [None] * self.world
+        self.dist.all_gather_object(bundles, (self.ops.ipc_bundle(), self.ops.async_cur()), group=self.group)
+        assert len({b[1] for b in bundles}) == 1, "trace buffers of the shards are out of lock step"
+        for r, (bundle, _) in enumerate(bundles):
+            if r != self.rank:
+                self.ops.attach_ipc(r, bundle)
+        self._peers_attached = True
+
     def run_(self, observations_seq, ess_threshold=None):
         """T x { maybe_resample!; particle_filter_step! } over the sharded filter WITHOUT any host round trip: the
         statistics record is all-reduced / all-gathered on the device, the exchange plan, the ESS test and the log-ML
@@ -301,14 +318,7 @@ class ShardedParticleFilter:
         shard; otherwise GenB200Error and the synchronous staged path must be used).  Returns the number of resamples."""
         torch, dist, W = self.torch, self.dist, self.world
         thr = self.n_global / 2 if ess_threshold is None else float(ess_threshold)
-        if not self._peers_attached and W > 1:
-            bundles = [None] * W
-            dist.all_gather_object(bundles, (self.ops.ipc_bundle(), self.ops.async_cur()), group=self.group)
-            assert len({b[1] for b in bundles}) == 1, "trace buffers of the shards are out of lock step"
-            for r, (bundle, _) in enumerate(bundles):
-                if r != self.rank:
-                    self.ops.attach_ipc(r, bundle)
-            self._peers_attached = True
+        self._attach_peers()
         self.ops.async_setup(W, self.rank, self.offs, thr)
         if self._stats_t is None:
             self._stats_t = self.ops.stats_tensor(torch)
@@ -389,14 +399,28 @@ class ShardedParticleFilter:
         u0 = api.philox_resample_u0(self.seed, self.step)
         q_total, pref, ranges, send = plan_exchange(qs, self.n_global, self.offs, u0)
         me, W = self.rank, self.world
-        lo, hi = self.ops.systematic_offspring(m, self.bits, pref[me], qs[me], q_total, u0)
-        assert (lo, hi) == ranges[me], "offspring range mismatch between host plan and device sweep"
-        send_cnt = [send[me][d][1] - send[me][d][0] for d in range(W)]
-        recv_cnt = [send[s][me][1] - send[s][me][0] for s in range(W)]
         # Fast path when every shard can park its incoming rows in its extension rows (all ranks evaluate
         # the same predicate from the gathered plan, so no extra collective is needed to agree on it)
         fast = self.ext_caps is not None and not self.force_staged and all(
             sum(send[s][d][1] - send[s][d][0] for s in range(W) if s != d) <= self.ext_caps[d] for d in range(W))
+        if fast and self.use_p2p and self.device.type == "cuda" and W > 1:
+            # the decision was taken here (the Bool is returned), the exchange itself is the asynchronous run's: plan
+            # on the device from the gathered records, ancestors, offspring written into the owning shards' memory
+            # by peer stores over NVLink, a one-word all-reduce as the barrier -- no staging blocks, no all-to-all
+            self._attach_peers()
+            self.ops.async_setup(W, me, self.offs, math.inf)
+            self.ops.async_plan(self._gather_t, u0)
+            self.ops.async_sweep()
+            self.ops.async_export()
+            if self._barrier_t is None:
+                self._barrier_t = self.torch.zeros(1, dtype=self.torch.int32, device=self.device)
+            self.dist.all_reduce(self._barrier_t, group=self.group)
+            self.ops.async_commit(lse - math.log(self.n_global))   # :263
+            return True
+        lo, hi = self.ops.systematic_offspring(m, self.bits, pref[me], qs[me], q_total, u0)
+        assert (lo, hi) == ranges[me], "offspring range mismatch between host plan and device sweep"
+        send_cnt = [send[me][d][1] - send[me][d][0] for d in range(W)]
+        recv_cnt = [send[s][me][1] - send[s][me][0] for s in range(W)]
         if fast:
             a, b = send[me][me]
             self.ops.offspring_local(a, b)                   # stays here: ancestors only, gather deferred

@@ -230,6 +230,9 @@ int gb_pf_ext_capacity(const gb_pf_t *pf, int64_t *cap);
 int gb_pf_offspring_local(gb_pf_t *pf, int64_t k_lo, int64_t k_hi);
 int gb_pf_import_ext(gb_pf_t *pf, int64_t dst_lo, int64_t count, int64_t ext_offset, const void *dev_block);
 int gb_pf_commit_resample_lazy(gb_pf_t *pf, double log_ml_increment);
+/* The same bookkeeping after an exchange done by the device-planned peer stores (gb_pf_async_plan / _sweep / _export and
+ * the caller's barrier) when the CALLER took the resampling decision: the synchronous maybe_resample! over NVLink peers. */
+int gb_pf_async_commit(gb_pf_t *pf, double log_ml_increment);
 /* Staged exchange (arbitrarily skewed weights).  gb_pf_export_offspring gathers the rows of global slots
  * [k_lo, k_hi) (inside the shard's offspring range, not straddling its own slot range) into a block;
  * gb_pf_import_rows installs a block at local slots [dst_lo, dst_lo+count) of the NEW trace buffer;

@@ -24,11 +24,13 @@ def main():
     from genb200 import sharded, _lib as L
     L.check(L.lib().gb_set_device(lr))
     rank, world = dist.get_rank(), dist.get_world_size()
-    for n, staged in ((100003, False), (100003, True), (4_000_000, False)):
+    # synchronous path: exchange by peer stores (default), by all-to-all-v of blocks, by the staged fallback
+    for n, staged, p2p in ((100003, False, True), (100003, False, False), (100003, True, False), (4_000_000, False, True)):
         ys = F.bearings_series(8)
         seed = 17
         spf = sharded.ShardedParticleFilter(g.bearings_model(), n, seed=seed).initialize(ys[0])
         spf.force_staged = staged
+        spf.use_p2p = p2p
         nres = nacc = nacc1 = 0
         for t in range(1, len(ys)):
             nres += spf.maybe_resample_(ess_threshold=(n + 1 if t % 2 else n / 2))
@@ -45,7 +47,7 @@ def main():
                 nacc1 += g.rejuvenate_(st, ys[t], move="drift" if t % 2 else "resimulate", drift_std=1e-3)
             ok = nacc == nacc1 and nacc > 0 and all(np.array_equal(cols[f], st.get_state(f)) for f in range(4)) and np.array_equal(par, st.parents)
             ok = ok and abs(lml - g.log_ml_estimate(st)) <= 1e-10 * abs(lml)
-            print("NCCL sharded check world=%d n=%d staged=%s resamples=%d mh-accepts=%d: %s (log ML %.12f)" % (world, n, staged, nres, nacc, "OK" if ok else "MISMATCH", lml))
+            print("NCCL sharded check world=%d n=%d staged=%s p2p=%s resamples=%d mh-accepts=%d: %s (log ML %.12f)" % (world, n, staged, p2p, nres, nacc, "OK" if ok else "MISMATCH", lml))
             if not ok:
                 sys.exit(1)
     # asynchronous run (device-side plan, fixed-capacity equal-split all-to-all) vs the fused single-GPU run
