@@ -9,6 +9,7 @@
 #include "kernels_resample.cuh"
 #include "kernels_spec.cuh"
 #include "kernels_mh.cuh"
+#include "kernels_small.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -1449,6 +1450,55 @@ extern "C" int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t 
 
 // ---- fused multi-step entry: T x { maybe_resample!(systematic); particle_filter_step! } with the ESS test, the
 //      log-ML update and the gathered/direct choice made on the device (no host round trip per step) ----
+// ---- small particle counts: the whole T-step loop in one single-CTA kernel (kernels_small.cuh) ----
+static bool small_run_eligible(const gb_pf *pf, int T) {
+  static const bool on = [] { const char *e = getenv("GENB200_SMALL_RUN"); return !(e && e[0] == '0'); }();
+  const int k = pf->model.kind;
+  return on && T > 0 && pf->n <= kSmallMax && pf->n == pf->n_global && pf->pid_offset == 0 && !pf->history &&
+         (k == MODEL_LGSSM || k == MODEL_SV || k == MODEL_BEARINGS || k == MODEL_HMM);
+}
+static int small_run(gb_pf *pf, int T, const double *obs, int nobs, int *n_resampled) {
+  SmallRunArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = GB_OK;
+  for (int t = 0; t < T && !rc; t++)   // per-step argument checks (HMM: observation in 1..M), parameters from the last one
+    rc = fill_model_params(pf, a.mp, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false);
+  if (rc) return rc;
+  double *d_obs = nullptr;
+  CK(cudaMalloc((void **)&d_obs, (size_t)T * nobs * 8));
+  cudaError_t e = cudaMemcpyAsync(d_obs, obs, (size_t)T * nobs * 8, cudaMemcpyHostToDevice, pf->stream);
+  a.obs = d_obs; a.T = T; a.nobs = nobs;
+  a.state[0] = pf->state[0]; a.state[1] = pf->state[1]; a.cur = pf->cur;
+  a.logw = pf->logw; a.incr = pf->incr; a.anc = pf->anc;
+  a.n = pf->n; a.ld = pf->ld; a.seed = pf->seed; a.step = (unsigned)pf->step;
+  a.bits = quant_bits(pf->n_global);
+  a.ctl = pf->d_ctl; a.stats = pf->d_stats;
+  if (e == cudaSuccess) {
+#define GO(R, K) LAUNCH(pf, GB_K_STEP, small_run_kernel<R, K><<<1, kSmallThreads, 0, pf->stream>>>(a))
+    const bool f64 = pf->dtype == GB_F64;
+    switch (pf->model.kind) {
+      case MODEL_LGSSM: if (f64) GO(double, MODEL_LGSSM); else GO(float, MODEL_LGSSM); break;
+      case MODEL_SV: if (f64) GO(double, MODEL_SV); else GO(float, MODEL_SV); break;
+      case MODEL_BEARINGS: if (f64) GO(double, MODEL_BEARINGS); else GO(float, MODEL_BEARINGS); break;
+      default: if (f64) GO(double, MODEL_HMM); else GO(float, MODEL_HMM); break;
+    }
+#undef GO
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pf->h_ctl, pf->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, pf->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
+  cudaFree(d_obs);
+  if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_run (single-CTA path): ") + cudaGetErrorString(e));
+  pf->log_ml_est = pf->h_ctl->log_ml_est;
+  pf->step += T;
+  pf->cur ^= (T & 1);
+  pf->incr_step = pf->step;
+  if (pf->h_ctl->n_resampled > 0) { pf->anc_valid = true; pf->parents64_valid = false; pf->ext_used = false; }
+  pf->wstate = W_MAX; pf->tiles_valid = false; pf->pending_gather = false;
+  if (n_resampled) *n_resampled = pf->h_ctl->n_resampled;
+  return GB_OK;
+}
+
 extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double ess_threshold, int *n_resampled) {
   if (pf) pf->mh_ok = false;
   REQ(pf && obs && T >= 0, "gb_pf_run: bad argument");
@@ -1469,6 +1519,7 @@ extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double
   pf->h_ctl->log_n = log((double)pf->n_global);
   CK(cudaMemcpyAsync(pf->d_ctl, pf->h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pf->stream));
   CK(cudaStreamSynchronize(pf->stream));                // h_ctl is reused for the read-back below
+  if (small_run_eligible(pf, T)) return small_run(pf, T, obs, nobs, n_resampled);
   const AncOut ao{pf->anc, 0, pf->n_global, nullptr, 0, 0};
   for (int t = 0; t < T; t++) {
     // maybe_resample!: statistics + decision on the device, then the (conditional) systematic sweep

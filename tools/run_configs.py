@@ -49,6 +49,20 @@ dt = (time.perf_counter() - t0) / 32
 rows.append(("1: LGSSM N=1e3 T=100 fp64, systematic @ ESS<N/2", "%.3g" % (1000 * 100 / dt), "%.1f us/step" % (1e6 * dt / 100),
              "mean log-ML error vs Kalman %.4f (sd %.3f over 32 seeds)" % (np.mean(ests) - kf, np.std(ests))))
 
+def pf_run_fused(model, ys, n, dtype, thr, seed):
+    st = g.initialize_particle_filter(model, (0,), ys[0], n, dtype=dtype, seed=seed)
+    g.particle_filter_run_(st, ys[1:], ess_threshold=thr)
+    return g.log_ml_estimate(st)
+
+
+pf_run_fused(model, ys, 1000, "f64", 500, 0)
+t0 = time.perf_counter()
+ests = [pf_run_fused(model, ys, 1000, "f64", 500, s) for s in range(32)]
+dt = (time.perf_counter() - t0) / 32
+rows.append(("1: same, fused gb_pf_run (N <= 4096: the whole loop in one single-CTA kernel)", "%.3g" % (1000 * 100 / dt),
+             "%.1f us/step" % (1e6 * dt / 100), "mean log-ML error vs Kalman %.4f (sd %.3f over 32 seeds); includes filter "
+             "creation and the log-ML read per seed" % (np.mean(ests) - kf, np.std(ests))))
+
 # ---- cfg 2: SV N=1e6, T=1000 ----
 ys = F.sv_series(1001)
 model = g.sv_model(**F.SV)
