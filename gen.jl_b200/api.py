@@ -704,6 +704,18 @@ def philox_multinomial_u64(seed, step, k0, n):
     return out
 
 
+def cache_trim():
+    """Return the allocator's cached device / pinned blocks to the driver."""
+    L.check(L.lib().gb_cache_trim())
+
+
+def cache_stats():
+    """(cached bytes, cached blocks, live blocks) of the library's caching allocator."""
+    a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+    L.check(L.lib().gb_cache_stats(C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
 def device_count():
     c = C.c_int()
     L.check(L.lib().gb_device_count(C.byref(c)))

@@ -40,6 +40,8 @@ static int fail(int code, const std::string &msg) {
     if (!(cond)) return fail(GB_EINVAL, msg);   \
   } while (0)
 
+#include "alloc.inc"
+
 extern "C" const char *gb_last_error(void) { return g_err.c_str(); }
 extern "C" const char *gb_version(void) { return "genb200 0.1 (sm_100a)"; }
 
@@ -368,15 +370,16 @@ template <typename F> static int grid_for(gb_pf *pf, F kernel, long long work_it
 
 static void pf_release(gb_pf *pf) {
   if (!pf) return;
-  cudaFree(pf->state[0]); cudaFree(pf->state[1]); cudaFree(pf->logw); cudaFree(pf->incr); cudaFree(pf->anc);
-  cudaFree(pf->parents64); cudaFree(pf->ext_parents); cudaFree(pf->partials); cudaFree(pf->ticket); cudaFree(pf->d_stats);
-  cudaFreeHost(pf->h_stats); cudaFree(pf->d_normals); cudaFree(pf->d_uniforms); cudaFree(pf->d_u64);
-  cudaFree(pf->d_ctl); cudaFreeHost(pf->h_ctl); cudaFree(pf->d_shplan); cudaFreeHost(pf->h_shplan); cudaFree(pf->d_offs); cudaFree(pf->super_q); cudaFree(pf->super_excl); cudaFree(pf->oflow); cudaFree(pf->oflow_count);
-  cudaFree(pf->tile_q); cudaFree(pf->tile_c); cudaFree(pf->tile_r); cudaFree(pf->tile_slot); cudaFree(pf->d_plan);
-  cudaFreeHost(pf->h_plan); cudaFree(pf->cdf); cudaFree(pf->off_anc); cudaFree(pf->d_tab); cudaFree(pf->d_ptab);
+  FreeBatch fb__;
+  gb_dev_free(pf->state[0]); gb_dev_free(pf->state[1]); gb_dev_free(pf->logw); gb_dev_free(pf->incr); gb_dev_free(pf->anc);
+  gb_dev_free(pf->parents64); gb_dev_free(pf->ext_parents); gb_dev_free(pf->partials); gb_dev_free(pf->ticket); gb_dev_free(pf->d_stats);
+  gb_host_free(pf->h_stats); gb_dev_free(pf->d_normals); gb_dev_free(pf->d_uniforms); gb_dev_free(pf->d_u64);
+  gb_dev_free(pf->d_ctl); gb_host_free(pf->h_ctl); gb_dev_free(pf->d_shplan); gb_host_free(pf->h_shplan); gb_dev_free(pf->d_offs); gb_dev_free(pf->super_q); gb_dev_free(pf->super_excl); gb_dev_free(pf->oflow); gb_dev_free(pf->oflow_count);
+  gb_dev_free(pf->tile_q); gb_dev_free(pf->tile_c); gb_dev_free(pf->tile_r); gb_dev_free(pf->tile_slot); gb_dev_free(pf->d_plan);
+  gb_host_free(pf->h_plan); gb_dev_free(pf->cdf); gb_dev_free(pf->off_anc); gb_dev_free(pf->d_tab); gb_dev_free(pf->d_ptab);
   for (auto p : pf->ipc_opened) cudaIpcCloseMemHandle(p);
-  for (auto p : pf->hist_state) cudaFree(p);
-  for (auto p : pf->hist_anc) cudaFree(p);
+  for (auto p : pf->hist_state) gb_dev_free(p);
+  for (auto p : pf->hist_anc) gb_dev_free(p);
   for (auto &t : pf->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto e : pf->pool) cudaEventDestroy(e);
   delete pf;
@@ -388,10 +391,10 @@ static const int kMaxPartials = 148 * 16 + 64;
 // workspace of the systematic pipeline: super-tile totals / prefixes and the overflow queue
 static cudaError_t alloc_sys_workspace(gb_pf *pf) {
   pf->nsuper = (pf->ntiles + kSuper - 1) / kSuper;
-  cudaError_t e = cudaMalloc((void **)&pf->super_q, (size_t)(pf->nsuper + 1) * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->super_excl, (size_t)(pf->nsuper + 1) * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->oflow, (size_t)(pf->n_global / kChunk + 2) * sizeof(OverflowEntry));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->oflow_count, 64);
+  cudaError_t e = gb_dev_alloc((void **)&pf->super_q, (size_t)(pf->nsuper + 1) * 8);
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->super_excl, (size_t)(pf->nsuper + 1) * 8);
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->oflow, (size_t)(pf->n_global / kChunk + 2) * sizeof(OverflowEntry));
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->oflow_count, 64);
   if (e == cudaSuccess) e = cudaMemset(pf->oflow_count, 0, 64);
   return e;
 }
@@ -422,7 +425,7 @@ extern "C" int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_glob
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&pf->num_sms, cudaDevAttrMultiProcessorCount, dev);
   auto A = [&](void **p, size_t bytes, bool zero) -> cudaError_t {
-    cudaError_t e = cudaMalloc(p, bytes);
+    cudaError_t e = gb_dev_alloc(p, bytes);
     if (e == cudaSuccess && zero) e = cudaMemset(*p, 0, bytes);
     return e;
   };
@@ -437,11 +440,11 @@ extern "C" int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_glob
   if (e == cudaSuccess) e = A((void **)&pf->partials, sizeof(double2) * kMaxPartials, true);
   if (e == cudaSuccess) e = A((void **)&pf->ticket, 64, true);
   if (e == cudaSuccess) e = A((void **)&pf->d_stats, sizeof(WeightStats), true);
-  if (e == cudaSuccess) e = cudaMallocHost((void **)&pf->h_stats, sizeof(WeightStats));
+  if (e == cudaSuccess) e = gb_host_alloc((void **)&pf->h_stats, sizeof(WeightStats));
   if (e == cudaSuccess) e = A((void **)&pf->tile_q, (size_t)(pf->ntiles + 1) * 8, true);
   if (e == cudaSuccess) e = A((void **)&pf->tile_slot, (size_t)(pf->ntiles + 1) * 8, true);
   if (e == cudaSuccess) e = A((void **)&pf->d_plan, sizeof(ResamplePlan), true);
-  if (e == cudaSuccess) e = cudaMallocHost((void **)&pf->h_plan, sizeof(ResamplePlan));
+  if (e == cudaSuccess) e = gb_host_alloc((void **)&pf->h_plan, sizeof(ResamplePlan));
   if (e == cudaSuccess) e = alloc_sys_workspace(pf);
   if (e == cudaSuccess && m->kind == MODEL_HMM) {
     size_t nt = m->params.size() - 2;
@@ -493,9 +496,9 @@ extern "C" int gb_pf_get_timing(gb_pf_t *pf, double *ms, int64_t *launches) {
 // upload [nd][n] host doubles into a [nd][ld] device buffer
 static int upload_rows(gb_pf *pf, double **dbuf, int *cap, const double *src, int nd) {
   if (nd > *cap) {
-    cudaFree(*dbuf);
+    gb_dev_free(*dbuf);
     *dbuf = nullptr;
-    CK(cudaMalloc((void **)dbuf, (size_t)nd * pf->ld * 8));
+    CK(gb_dev_alloc((void **)dbuf, (size_t)nd * pf->ld * 8));
     CK(cudaMemsetAsync(*dbuf, 0, (size_t)nd * pf->ld * 8, pf->stream));
     *cap = nd;
   }
@@ -525,7 +528,7 @@ extern "C" int gb_pf_set_resample_noise(gb_pf_t *pf, int use_u0, uint32_t u0, co
   pf->u0 = u0;
   pf->u64_set = false;
   if (u64s) {
-    if (!pf->d_u64) CK(cudaMalloc((void **)&pf->d_u64, (size_t)pf->ld * 8));
+    if (!pf->d_u64) CK(gb_dev_alloc((void **)&pf->d_u64, (size_t)pf->ld * 8));
     CK(cudaMemcpyAsync(pf->d_u64, u64s, (size_t)pf->n * 8, cudaMemcpyHostToDevice, pf->stream));
     CK(cudaStreamSynchronize(pf->stream));
     pf->u64_set = true;
@@ -599,9 +602,9 @@ static int fill_model_params(gb_pf *pf, ModelParams &mp, const double *obs, int 
     int need = init ? m.K : m.K * m.K;
     REQ(pargs && npargs == need, "categorical-table proposal: K probabilities at t=0, K*K afterwards");
     if (pf->ptab_cap < need) {
-      cudaFree(pf->d_ptab);
+      gb_dev_free(pf->d_ptab);
       pf->d_ptab = nullptr;
-      CK(cudaMalloc((void **)&pf->d_ptab, (size_t)m.K * m.K * 8));
+      CK(gb_dev_alloc((void **)&pf->d_ptab, (size_t)m.K * m.K * 8));
       pf->ptab_cap = m.K * m.K;
     }
     CK(cudaMemcpyAsync(pf->d_ptab, pargs, (size_t)need * 8, cudaMemcpyHostToDevice, pf->stream));
@@ -764,12 +767,12 @@ static int launch_model(gb_pf *pf, const double *obs, int nobs, int pk, const do
 static int history_record(gb_pf *pf, bool resampled) {
   void *snap = nullptr;
   const size_t bytes = (size_t)pf->S * pf->n_pad * pf->esz;
-  CK(cudaMalloc(&snap, bytes));
+  CK(gb_dev_alloc(&snap, bytes));
   CK(cudaMemcpy2DAsync(snap, (size_t)pf->n_pad * pf->esz, pf->state[pf->cur], (size_t)pf->ld * pf->esz, (size_t)pf->n_pad * pf->esz, pf->S,
                        cudaMemcpyDeviceToDevice, pf->stream));
   int *anc = nullptr;
   if (resampled) {
-    CK(cudaMalloc((void **)&anc, (size_t)pf->n_pad * 4));
+    CK(gb_dev_alloc((void **)&anc, (size_t)pf->n_pad * 4));
     CK(cudaMemcpyAsync(anc, pf->anc, (size_t)pf->n_pad * 4, cudaMemcpyDeviceToDevice, pf->stream));
   }
   pf->hist_state.push_back(snap);
@@ -796,9 +799,9 @@ extern "C" int gb_pf_get_trajectory(gb_pf_t *pf, int field, double *out) {
   REQ(len == pf->step + 1, "gb_pf_get_trajectory: history does not cover every step (gb_pf_run does not record history)");
   int *idx = nullptr;
   double *d_out = nullptr;
-  CK(cudaMalloc((void **)&idx, (size_t)pf->n_pad * 4));
-  cudaError_t e = cudaMalloc((void **)&d_out, (size_t)pf->n * 8);
-  if (e != cudaSuccess) { cudaFree(idx); return fail(GB_ECUDA, cudaGetErrorString(e)); }
+  CK(gb_dev_alloc((void **)&idx, (size_t)pf->n_pad * 4));
+  cudaError_t e = gb_dev_alloc((void **)&d_out, (size_t)pf->n * 8);
+  if (e != cudaSuccess) { gb_dev_free(idx); return fail(GB_ECUDA, cudaGetErrorString(e)); }
   int grid = grid_for(pf, iota_int_kernel, pf->n, kBlock);
   // a resample since the last recorded step (deferred or already gathered) is not in the last snapshot:
   // start from its ancestors
@@ -812,7 +815,7 @@ extern "C" int gb_pf_get_trajectory(gb_pf_t *pf, int field, double *out) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(out + (size_t)t * pf->n, d_out, (size_t)pf->n * 8, cudaMemcpyDeviceToHost, pf->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
   }
-  cudaFree(idx); cudaFree(d_out);
+  gb_dev_free(idx); gb_dev_free(d_out);
   if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_get_trajectory: ") + cudaGetErrorString(e));
   return GB_OK;
 }
@@ -839,8 +842,8 @@ extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, 
   pf->nn_set = pf->nu_set = 0;
   pf->mh_ok = pf->model.kind != MODEL_BLR; pf->mh_parent_anc = false; pf->mh_moves = 0;
   if (pf->history) {
-    for (auto p : pf->hist_state) cudaFree(p);
-    for (auto p : pf->hist_anc) cudaFree(p);
+    for (auto p : pf->hist_state) gb_dev_free(p);
+    for (auto p : pf->hist_anc) gb_dev_free(p);
     pf->hist_state.clear(); pf->hist_anc.clear();
     if ((rc = history_record(pf, false))) return rc;
   }
@@ -947,11 +950,11 @@ extern "C" int gb_pf_rejuvenate(gb_pf_t *pf, int move, const double *obs, int no
   if (rc) return rc;
   unsigned long long *d_acc = nullptr;
   double *d_alpha = nullptr;
-  CK(cudaMalloc((void **)&d_acc, 8));
+  CK(gb_dev_alloc((void **)&d_acc, 8));
   CK(cudaMemsetAsync(d_acc, 0, 8, pf->stream));
   if (alpha_out) {
-    cudaError_t e = cudaMalloc((void **)&d_alpha, (size_t)pf->n * 8);
-    if (e != cudaSuccess) { cudaFree(d_acc); return fail(GB_ECUDA, cudaGetErrorString(e)); }
+    cudaError_t e = gb_dev_alloc((void **)&d_alpha, (size_t)pf->n * 8);
+    if (e != cudaSuccess) { gb_dev_free(d_acc); return fail(GB_ECUDA, cudaGetErrorString(e)); }
   }
   a.parent = pf->state[pf->cur ^ 1];
   a.cur = pf->state[pf->cur];
@@ -975,7 +978,7 @@ extern "C" int gb_pf_rejuvenate(gb_pf_t *pf, int move, const double *obs, int no
                             (size_t)pf->n_pad * pf->esz, pf->S, cudaMemcpyDeviceToDevice, pf->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
   }
-  cudaFree(d_acc); cudaFree(d_alpha);
+  gb_dev_free(d_acc); gb_dev_free(d_alpha);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_rejuvenate: ") + cudaGetErrorString(e));
   pf->mh_moves += 1;
@@ -1211,7 +1214,7 @@ extern "C" int gb_pf_get_state(gb_pf_t *pf, int field, double *out) {
 }
 // parents64 = Gen's `parents` (global, 1-based) of the current traces
 static int ensure_parents64(gb_pf *pf) {
-  if (!pf->parents64) CK(cudaMalloc((void **)&pf->parents64, (size_t)pf->ld * 8));
+  if (!pf->parents64) CK(gb_dev_alloc((void **)&pf->parents64, (size_t)pf->ld * 8));
   if (pf->parents64_valid) return GB_OK;
   if (pf->anc_valid) {
     int grid = grid_for(pf, parents_from_anc_kernel, pf->n, kBlock);
@@ -1257,7 +1260,7 @@ extern "C" int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out) {
   if (e == cudaSuccess) e = cudaMemcpyAsync(c->anc, pf->anc, (size_t)pf->ld * 4, cudaMemcpyDeviceToDevice, pf->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_stats, pf->d_stats, sizeof(WeightStats), cudaMemcpyDeviceToDevice, pf->stream);
   if (e == cudaSuccess && pf->parents64_valid) {
-    e = cudaMalloc((void **)&c->parents64, (size_t)pf->ld * 8);
+    e = gb_dev_alloc((void **)&c->parents64, (size_t)pf->ld * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->parents64, pf->parents64, (size_t)pf->ld * 8, cudaMemcpyDeviceToDevice, pf->stream);
     c->parents64_valid = true;
   }
@@ -1271,8 +1274,8 @@ extern "C" int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out) {
 // resampling
 // ------------------------------------------------------------------------------------------
 static int ensure_residual_ws(gb_pf *pf) {
-  if (!pf->tile_c) CK(cudaMalloc((void **)&pf->tile_c, (size_t)(pf->ntiles + 1) * 8));
-  if (!pf->tile_r) CK(cudaMalloc((void **)&pf->tile_r, (size_t)(pf->ntiles + 1) * sizeof(U128)));
+  if (!pf->tile_c) CK(gb_dev_alloc((void **)&pf->tile_c, (size_t)(pf->ntiles + 1) * 8));
+  if (!pf->tile_r) CK(gb_dev_alloc((void **)&pf->tile_r, (size_t)(pf->ntiles + 1) * sizeof(U128)));
   return GB_OK;
 }
 
@@ -1358,7 +1361,7 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
     return launch_ancestors<R, SWEEP_RESIDUAL>(pf, logw, m, bits, 0, n_over, anc, 0);
   }
   if (kind == GB_RESAMPLE_MULTINOMIAL) {
-    if (!pf->cdf) CK(cudaMalloc((void **)&pf->cdf, (size_t)pf->ld * 8));
+    if (!pf->cdf) CK(gb_dev_alloc((void **)&pf->cdf, (size_t)pf->ld * 8));
     if (!pf->tiles_valid && (rc = run_wstats(pf, logw, m, false))) return rc;
     pf->tiles_valid = false;   // tile_q becomes its exclusive prefix
     if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, u0, 1))) return rc;
@@ -1415,7 +1418,7 @@ extern "C" int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t 
   const double m = pf->h_stats->m;
   if (!(m > -INFINITY)) return fail(GB_ESTATE, "gb_pf_sample_unweighted: all log weights are -Inf or NaN");
   if (!pf->tiles_valid && (rc = run_wstats(pf, pf->logw, m, false))) return rc;
-  if (!pf->cdf) CK(cudaMalloc((void **)&pf->cdf, (size_t)pf->ld * 8));
+  if (!pf->cdf) CK(gb_dev_alloc((void **)&pf->cdf, (size_t)pf->ld * 8));
   const int bits = quant_bits(pf->n_global);
   pf->tiles_valid = false;   // tile_q becomes its exclusive prefix
   if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, 0, 1))) return rc;
@@ -1425,9 +1428,9 @@ extern "C" int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t 
   int *d_idx = nullptr;
   long long *d_idx1 = nullptr;
   double *d_rows = nullptr;
-  cudaError_t e = cudaMalloc((void **)&d_idx, (size_t)n_samples * 4);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_idx1, (size_t)n_samples * 8);
-  if (e == cudaSuccess && rows_out) e = cudaMalloc((void **)&d_rows, (size_t)n_samples * pf->S * 8);
+  cudaError_t e = gb_dev_alloc((void **)&d_idx, (size_t)n_samples * 4);
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&d_idx1, (size_t)n_samples * 8);
+  if (e == cudaSuccess && rows_out) e = gb_dev_alloc((void **)&d_rows, (size_t)n_samples * pf->S * 8);
   if (e == cudaSuccess) {
     int grid = grid_for(pf, multinomial_kernel, n_samples, kBlock);
     LAUNCH(pf, GB_K_MISC, multinomial_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->cdf, pf->tile_q, pf->ntiles, pf->n, pf->d_plan, nullptr,
@@ -1443,7 +1446,7 @@ extern "C" int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t 
   if (e == cudaSuccess) e = cudaMemcpyAsync(idx_out, d_idx1, (size_t)n_samples * 8, cudaMemcpyDeviceToHost, pf->stream);
   if (e == cudaSuccess && rows_out) e = cudaMemcpyAsync(rows_out, d_rows, (size_t)n_samples * pf->S * 8, cudaMemcpyDeviceToHost, pf->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
-  cudaFree(d_idx); cudaFree(d_idx1); cudaFree(d_rows);
+  gb_dev_free(d_idx); gb_dev_free(d_idx1); gb_dev_free(d_rows);
   if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_sample_unweighted: ") + cudaGetErrorString(e));
   return GB_OK;
 }
@@ -1465,7 +1468,7 @@ static int small_run(gb_pf *pf, int T, const double *obs, int nobs, int *n_resam
     rc = fill_model_params(pf, a.mp, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false);
   if (rc) return rc;
   double *d_obs = nullptr;
-  CK(cudaMalloc((void **)&d_obs, (size_t)T * nobs * 8));
+  CK(gb_dev_alloc((void **)&d_obs, (size_t)T * nobs * 8));
   cudaError_t e = cudaMemcpyAsync(d_obs, obs, (size_t)T * nobs * 8, cudaMemcpyHostToDevice, pf->stream);
   a.obs = d_obs; a.T = T; a.nobs = nobs;
   a.state[0] = pf->state[0]; a.state[1] = pf->state[1]; a.cur = pf->cur;
@@ -1487,7 +1490,7 @@ static int small_run(gb_pf *pf, int T, const double *obs, int nobs, int *n_resam
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(pf->h_ctl, pf->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, pf->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
-  cudaFree(d_obs);
+  gb_dev_free(d_obs);
   if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_run (single-CTA path): ") + cudaGetErrorString(e));
   pf->log_ml_est = pf->h_ctl->log_ml_est;
   pf->step += T;
@@ -1510,8 +1513,8 @@ extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double
   if (rc) return rc;
   if ((rc = gb_pf_weight_max_device(pf))) return rc;     // d_stats->m current for the first statistics pass
   if (!pf->d_ctl) {
-    CK(cudaMalloc((void **)&pf->d_ctl, sizeof(RunCtl)));
-    CK(cudaMallocHost((void **)&pf->h_ctl, sizeof(RunCtl)));
+    CK(gb_dev_alloc((void **)&pf->d_ctl, sizeof(RunCtl)));
+    CK(gb_host_alloc((void **)&pf->h_ctl, sizeof(RunCtl)));
   }
   pf->h_ctl->do_resample = 0; pf->h_ctl->n_resampled = 0;
   pf->h_ctl->log_ml_est = pf->log_ml_est;
@@ -1560,14 +1563,14 @@ extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits
   const long long lo = slots_below(q_offset, sp), hi = slots_below(q_offset + q_local, sp);
   const long long cnt = hi - lo;
   if (cnt > pf->off_cap) {
-    cudaFree(pf->off_anc);
+    gb_dev_free(pf->off_anc);
     pf->off_anc = nullptr;
     // grow with head-room: the offspring count fluctuates from resample to resample and every
     // cudaFree/cudaMalloc is a device synchronisation
     long long want = cnt + cnt / 4 + kTile;
     if (want < pf->n_pad + pf->n_pad / 4) want = pf->n_pad + pf->n_pad / 4;
     long long cap = ((want + kTile - 1) / kTile) * kTile;
-    CK(cudaMalloc((void **)&pf->off_anc, (size_t)cap * 4));
+    CK(gb_dev_alloc((void **)&pf->off_anc, (size_t)cap * 4));
     pf->off_cap = cap;
   }
   if (cnt > 0) {
@@ -1603,14 +1606,14 @@ extern "C" int gb_pf_ipc_export(gb_pf_t *pf, void *bundle_out, int *nbytes) {
 extern "C" int gb_pf_ipc_bundle_bytes(void) { return (int)sizeof(IpcBundle); }
 static int ensure_async_alloc(gb_pf *pf) {
   if (!pf->d_ctl) {
-    CK(cudaMalloc((void **)&pf->d_ctl, sizeof(RunCtl)));
-    CK(cudaMallocHost((void **)&pf->h_ctl, sizeof(RunCtl)));
+    CK(gb_dev_alloc((void **)&pf->d_ctl, sizeof(RunCtl)));
+    CK(gb_host_alloc((void **)&pf->h_ctl, sizeof(RunCtl)));
   }
   if (!pf->d_shplan) {
-    CK(cudaMalloc((void **)&pf->d_shplan, sizeof(ShardPlanDev)));
-    CK(cudaMallocHost((void **)&pf->h_shplan, sizeof(ShardPlanDev)));
+    CK(gb_dev_alloc((void **)&pf->d_shplan, sizeof(ShardPlanDev)));
+    CK(gb_host_alloc((void **)&pf->h_shplan, sizeof(ShardPlanDev)));
     memset(pf->h_shplan, 0, sizeof(ShardPlanDev));
-    CK(cudaMalloc((void **)&pf->d_offs, sizeof(long long) * (kMaxWorld + 1)));
+    CK(gb_dev_alloc((void **)&pf->d_offs, sizeof(long long) * (kMaxWorld + 1)));
   }
   return GB_OK;
 }
@@ -1664,9 +1667,9 @@ extern "C" int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t
   // spill buffer: ancestors of the offspring that land outside this shard's own slot range
   const long long want = pf->n_pad + pf->n_pad / 4 + kTile;
   if (pf->off_cap < want) {
-    cudaFree(pf->off_anc);
+    gb_dev_free(pf->off_anc);
     pf->off_anc = nullptr;
-    CK(cudaMalloc((void **)&pf->off_anc, (size_t)want * 4));
+    CK(gb_dev_alloc((void **)&pf->off_anc, (size_t)want * 4));
     pf->off_cap = want;
   }
   CK(cudaStreamSynchronize(pf->stream));
@@ -1815,7 +1818,7 @@ extern "C" int gb_pf_import_rows(gb_pf_t *pf, int64_t dst_lo, int64_t count, con
   REQ(pf && dev_block, "null argument");
   REQ(dst_lo >= 0 && count >= 0 && dst_lo + count <= pf->n, "gb_pf_import_rows: destination outside the shard");
   if (count == 0) return GB_OK;
-  if (!pf->parents64) CK(cudaMalloc((void **)&pf->parents64, (size_t)pf->ld * 8));
+  if (!pf->parents64) CK(gb_dev_alloc((void **)&pf->parents64, (size_t)pf->ld * 8));
   if (pf->dtype == GB_F64) {
     auto kern = import_kernel<double>;
     int grid = grid_for(pf, kern, count, kBlock);
@@ -1851,7 +1854,7 @@ static int blr_generate(gb_pf *pf, const double *obs, int nobs, bool predrawn) {
   for (int j = 0; j < m.nobs; j++)
     for (int d = 0; d < m.D; d++) Xt[((size_t)(d / 2) * kBlrMax + j) * 2 + (d & 1)] = m.params[3 + (size_t)j * m.D + d];
   for (int j = 0; j < nobs; j++) y[j] = obs[j];
-  if (!pf->d_tab) CK(cudaMalloc((void **)&pf->d_tab, Xt.size() * 8));
+  if (!pf->d_tab) CK(gb_dev_alloc((void **)&pf->d_tab, Xt.size() * 8));
   CK(cudaMemcpyAsync(pf->d_tab, Xt.data(), Xt.size() * 8, cudaMemcpyHostToDevice, pf->stream));
   CK(cudaMemcpyToSymbolAsync(c_blr_y, y.data(), y.size() * 8, 0, cudaMemcpyHostToDevice, pf->stream));
   CK(cudaStreamSynchronize(pf->stream));
@@ -1891,7 +1894,7 @@ extern "C" int gb_importance_sampling(const gb_model_t *m, int64_t n, int dtype,
   *lml_out = pf->h_stats->lse - log((double)n);                      // :33, :56
   if (lognormw_out) {                                                // :34, :57
     double *d_out = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_out, (size_t)n * 8);
+    cudaError_t e = gb_dev_alloc((void **)&d_out, (size_t)n * 8);
     if (e != cudaSuccess) { pf_release(pf); return fail(GB_ECUDA, cudaGetErrorString(e)); }
     if (dtype == GB_F64) {
       auto kern = normalize_kernel<double>;
@@ -1904,7 +1907,7 @@ extern "C" int gb_importance_sampling(const gb_model_t *m, int64_t n, int dtype,
     }
     e = cudaMemcpyAsync(lognormw_out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, pf->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
-    cudaFree(d_out);
+    gb_dev_free(d_out);
     if (e != cudaSuccess) { pf_release(pf); return fail(GB_ECUDA, cudaGetErrorString(e)); }
   }
   if (pf_out) *pf_out = pf; else pf_release(pf);
@@ -1934,16 +1937,16 @@ static int raw_workspace(long long n, int dtype, cudaStream_t stream, gb_pf **ou
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&pf->num_sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaError_t e = cudaMalloc((void **)&pf->partials, sizeof(double2) * kMaxPartials);
+  cudaError_t e = gb_dev_alloc((void **)&pf->partials, sizeof(double2) * kMaxPartials);
   if (e == cudaSuccess) e = alloc_sys_workspace(pf);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->ticket, 64);
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->ticket, 64);
   if (e == cudaSuccess) e = cudaMemset(pf->ticket, 0, 64);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->d_stats, sizeof(WeightStats));
-  if (e == cudaSuccess) e = cudaMallocHost((void **)&pf->h_stats, sizeof(WeightStats));
-  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->tile_q, (size_t)(pf->ntiles + 1) * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->tile_slot, (size_t)(pf->ntiles + 1) * 8);
-  if (e == cudaSuccess) e = cudaMalloc((void **)&pf->d_plan, sizeof(ResamplePlan));
-  if (e == cudaSuccess) e = cudaMallocHost((void **)&pf->h_plan, sizeof(ResamplePlan));
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->d_stats, sizeof(WeightStats));
+  if (e == cudaSuccess) e = gb_host_alloc((void **)&pf->h_stats, sizeof(WeightStats));
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->tile_q, (size_t)(pf->ntiles + 1) * 8);
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->tile_slot, (size_t)(pf->ntiles + 1) * 8);
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->d_plan, sizeof(ResamplePlan));
+  if (e == cudaSuccess) e = gb_host_alloc((void **)&pf->h_plan, sizeof(ResamplePlan));
   if (e != cudaSuccess) { pf_release(pf); return fail(GB_ECUDA, std::string("raw workspace: ") + cudaGetErrorString(e)); }
   g_raw.pf = pf; g_raw.n = n; g_raw.dtype = dtype;
   *out = pf;
@@ -1986,11 +1989,11 @@ extern "C" int gb_resample(const double *logw, int64_t n, int dtype, int kind, u
   uint64_t *d_u = nullptr;
   std::vector<float> tmpf;
   std::vector<int> anc32(n);
-  cudaError_t e = cudaMalloc(&d_lw, (size_t)ld * esz);
+  cudaError_t e = gb_dev_alloc(&d_lw, (size_t)ld * esz);
   if (e == cudaSuccess) e = cudaMemset(d_lw, 0xFF, (size_t)ld * esz);   // padding = NaN, masked by index anyway
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d_anc, (size_t)ld * 4);
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&d_anc, (size_t)ld * 4);
   if (e == cudaSuccess && u64s) {
-    e = cudaMalloc((void **)&d_u, (size_t)ld * 8);
+    e = gb_dev_alloc((void **)&d_u, (size_t)ld * 8);
     if (e == cudaSuccess) e = cudaMemcpy(d_u, u64s, (size_t)n * 8, cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) {
@@ -2008,7 +2011,7 @@ extern "C" int gb_resample(const double *logw, int64_t n, int dtype, int kind, u
     e = cudaMemcpy(anc32.data(), d_anc, (size_t)n * 4, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = fail(GB_ECUDA, std::string("gb_resample: ") + cudaGetErrorString(e));
   }
-  cudaFree(d_lw); cudaFree(d_anc); cudaFree(d_u);
+  gb_dev_free(d_lw); gb_dev_free(d_anc); gb_dev_free(d_u);
   if (rc) return rc;
   for (long long i = 0; i < n; i++) anc_out[i] = anc32[i];
   return GB_OK;
@@ -2021,7 +2024,7 @@ extern "C" int gb_logsumexp(const double *a, int64_t n, int dtype, double *lse_o
   if (rc) return rc;
   void *d = nullptr;
   const size_t esz = dtype == GB_F64 ? 8 : 4;
-  CK(cudaMalloc(&d, (size_t)n * esz));
+  CK(gb_dev_alloc(&d, (size_t)n * esz));
   cudaError_t e;
   if (dtype == GB_F64) e = cudaMemcpy(d, a, (size_t)n * 8, cudaMemcpyHostToDevice);
   else {
@@ -2029,9 +2032,9 @@ extern "C" int gb_logsumexp(const double *a, int64_t n, int dtype, double *lse_o
     for (long long i = 0; i < n; i++) t[i] = (float)a[i];
     e = cudaMemcpy(d, t.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
   }
-  if (e != cudaSuccess) { cudaFree(d); return fail(GB_ECUDA, cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { gb_dev_free(d); return fail(GB_ECUDA, cudaGetErrorString(e)); }
   rc = raw_stats(ws, d);
-  cudaFree(d);
+  gb_dev_free(d);
   if (rc) return rc;
   if (lse_out) *lse_out = ws->h_stats->lse;
   if (ess_out) *ess_out = ws->h_stats->ess;
@@ -2061,13 +2064,13 @@ static int export_noise(uint64_t seed, uint32_t step, int64_t pid0, int64_t n, i
   int rc = require_gpu();
   if (rc) return rc;
   double *d = nullptr;
-  CK(cudaMalloc((void **)&d, (size_t)n * ndraw * 8));
+  CK(gb_dev_alloc((void **)&d, (size_t)n * ndraw * 8));
   int grid = (int)std::min<long long>((n + kBlock - 1) / kBlock, 148 * 8);
   if (dtype == GB_F64) noise_kernel<double><<<grid, kBlock>>>(seed, step, pid0, n, ndraw, uniform, d);
   else noise_kernel<float><<<grid, kBlock>>>(seed, step, pid0, n, ndraw, uniform, d);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpy(out, d, (size_t)n * ndraw * 8, cudaMemcpyDeviceToHost);
-  cudaFree(d);
+  gb_dev_free(d);
   if (e != cudaSuccess) return fail(GB_ECUDA, std::string("noise export: ") + cudaGetErrorString(e));
   return GB_OK;
 }
@@ -2256,11 +2259,11 @@ static int dist_common(int dist, int dtype, int64_t n, const double *x, const do
   double *dx = nullptr, *da = nullptr, *db = nullptr, *dout = nullptr;
   cudaError_t e = cudaSuccess;
   size_t nout = random ? nx : (size_t)n;
-  if (!random) { e = cudaMalloc((void **)&dx, nx * 8); if (e == cudaSuccess) e = cudaMemcpy(dx, x, nx * 8, cudaMemcpyHostToDevice); }
-  if (e == cudaSuccess) e = cudaMalloc((void **)&da, na * 8);
+  if (!random) { e = gb_dev_alloc((void **)&dx, nx * 8); if (e == cudaSuccess) e = cudaMemcpy(dx, x, nx * 8, cudaMemcpyHostToDevice); }
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&da, na * 8);
   if (e == cudaSuccess) e = cudaMemcpy(da, a, na * 8, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess && nb) { e = cudaMalloc((void **)&db, nb * 8); if (e == cudaSuccess) e = cudaMemcpy(db, bsrc, nb * 8, cudaMemcpyHostToDevice); }
-  if (e == cudaSuccess) e = cudaMalloc((void **)&dout, nout * 8);
+  if (e == cudaSuccess && nb) { e = gb_dev_alloc((void **)&db, nb * 8); if (e == cudaSuccess) e = cudaMemcpy(db, bsrc, nb * 8, cudaMemcpyHostToDevice); }
+  if (e == cudaSuccess) e = gb_dev_alloc((void **)&dout, nout * 8);
   if (e == cudaSuccess) {
     int grid = (int)std::min<long long>((n + kBlock - 1) / kBlock, 148 * 8);
     const int as_ = (dist == GB_DIST_CATEGORICAL || vec) ? 0 : (as ? 1 : 0), bs_ = vec ? 0 : (bs ? 1 : 0);
@@ -2275,7 +2278,7 @@ static int dist_common(int dist, int dtype, int64_t n, const double *x, const do
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(out, dout, nout * 8, cudaMemcpyDeviceToHost);
-  cudaFree(dx); cudaFree(da); cudaFree(db); cudaFree(dout);
+  gb_dev_free(dx); gb_dev_free(da); gb_dev_free(db); gb_dev_free(dout);
   if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_dist: ") + cudaGetErrorString(e));
   return GB_OK;
 }

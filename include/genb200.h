@@ -75,6 +75,11 @@ typedef struct gb_pf gb_pf_t;
 const char *gb_last_error(void);
 const char *gb_version(void);
 int gb_device_count(int *count);              /* 0 devices => *count = 0, returns GB_OK */
+/* Device and pinned-host buffers released by gb_pf_free / gb_model_free are kept on a per-device free list and reused by
+ * the next filter (a raw cudaMalloc/cudaFree cycle costs more than running a small filter).  GENB200_CACHE_MB caps the
+ * cached bytes (default 8192; 0 = no caching).  gb_cache_trim returns the cached blocks to the driver. */
+int gb_cache_trim(void);
+int gb_cache_stats(int64_t *cached_bytes, int64_t *cached_blocks, int64_t *live_blocks);
 int gb_set_device(int device);
 
 /* ---- model handles (replace GenerativeFunction objects of the supported class) ---- */

@@ -462,6 +462,38 @@ def test_pf_state_copy_and_fields(g):
     assert st.log_ml_est != 0.0 and c2.log_ml_est == st.log_ml_est
 
 
+def test_caching_allocator_reuses_blocks(g):
+    """Buffers of a freed filter go to the allocator's free list and serve the next filter of the same shape."""
+    import gc
+    m = g.lgssm_model()
+    gc.collect()
+    g.cache_trim()
+    assert g.cache_stats()[:2] == (0, 0)
+    live_before = g.cache_stats()[2]                                    # blocks of filters other tests still hold
+    st = g.initialize_particle_filter(m, (0,), 0.1, 50000, seed=1)
+    ref = st.get_state(0)
+    owned = g.cache_stats()[2] - live_before
+    assert owned > 10
+    del st
+    gc.collect()
+    cached, blocks, live = g.cache_stats()
+    assert cached > 50000 * 8 * 4 and blocks == owned and live == live_before
+    st2 = g.initialize_particle_filter(m, (0,), 0.1, 50000, seed=1)     # same shapes: served from the cache
+    assert g.cache_stats()[1] <= 3 and np.array_equal(st2.get_state(0), ref)
+    for t in range(1, 4):                                               # recycled (non-zeroed) blocks behave like fresh ones
+        g.maybe_resample_(st2, ess_threshold=50001, resampler="systematic")
+        g.particle_filter_step_(st2, (t,), (g.UnknownChange,), 0.2, return_incr=False)
+    st3 = g.initialize_particle_filter(m, (0,), 0.1, 50000, seed=1)
+    for t in range(1, 4):
+        g.maybe_resample_(st3, ess_threshold=50001, resampler="systematic")
+        g.particle_filter_step_(st3, (t,), (g.UnknownChange,), 0.2, return_incr=False)
+    assert st2 == st3
+    del st2, st3
+    gc.collect()
+    g.cache_trim()
+    assert g.cache_stats()[:2] == (0, 0)
+
+
 def test_all_minus_inf_weights(g):
     # SURVEY.md section 8a edge semantics: lse = -Inf, ESS = NaN, no resample, log_ml_estimate = -Inf
     st = g.initialize_particle_filter(g.lgssm_model(), (0,), 0.1, 64)
