@@ -244,4 +244,51 @@ function particle_filter_run!(state::DeviceParticleFilterState, observations::Ve
     nres[]
 end
 
+# ---- GB_MODEL_SPEC: a static-IR function of the supported class written out as SSA ops (include/genb200.h) ----
+# Gen's own IR cannot be lowered automatically (JuliaNode.fn is an opaque closure, src/static_ir/dag.jl:14-19), so the
+# program is built with this small builder; every method returns the register holding the node's value.
+mutable struct SpecProgram
+    ops::Vector{NTuple{5,Float64}}
+    nreg::Int
+    SpecProgram() = new(NTuple{5,Float64}[], 0)
+end
+function _emit!(p::SpecProgram, code, dst, a=0, b=0, imm=0.0)
+    push!(p.ops, (Float64(code), Float64(dst), Float64(a), Float64(b), Float64(imm))); dst
+end
+_new!(p::SpecProgram) = (p.nreg >= 32 && error("a spec program may use at most 32 registers"); p.nreg += 1; p.nreg - 1)
+spec_const(p, v) = _emit!(p, 0, _new!(p), 0, 0, v)
+spec_prev(p, field) = _emit!(p, 1, _new!(p), field)
+spec_param(p, idx) = _emit!(p, 2, _new!(p), idx)
+spec_obs(p, idx=0) = _emit!(p, 3, _new!(p), idx)
+spec_time(p) = _emit!(p, 4, _new!(p))
+for (name, code) in ((:add, 10), (:sub, 11), (:mul, 12), (:div, 13), (:atan2, 18))
+    @eval $(Symbol("spec_", name))(p, a, b) = _emit!(p, $code, _new!(p), a, b)
+end
+for (name, code) in ((:neg, 14), (:sqrt, 15), (:exp, 16), (:log, 17), (:abs, 19))
+    @eval $(Symbol("spec_", name))(p, a) = _emit!(p, $code, _new!(p), a)
+end
+sample_normal!(p, mu, std) = _emit!(p, 20, _new!(p), mu, std)          # {addr} ~ normal(mu, std), unconstrained
+observe_normal!(p, x, mu, std) = (_emit!(p, 21, x, mu, std); nothing)  # constrained: weight += logpdf
+sample_bernoulli!(p, q) = _emit!(p, 22, _new!(p), q)
+observe_bernoulli!(p, x, q) = (_emit!(p, 23, x, q); nothing)
+sample_gamma!(p, shape, scale) = _emit!(p, 24, _new!(p), shape, scale)
+observe_gamma!(p, x, shape, scale) = (_emit!(p, 25, x, shape, scale); nothing)
+sample_categorical!(p, offset_reg, len) = _emit!(p, 26, _new!(p), offset_reg, len)
+observe_categorical!(p, x, offset_reg, len) = (_emit!(p, 27, x, offset_reg, len); nothing)
+store!(p, field, reg) = (_emit!(p, 30, field, reg); nothing)
+add_weight!(p, reg) = (_emit!(p, 31, 0, reg); nothing)
+logpdf_normal!(p, x, mu, std) = _emit!(p, 32, _new!(p), mu, std, x)
+sample_dist!(p, dist::Int, a, b=a) = _emit!(p, 40, _new!(p), a, b, dist)          # dist = GB_DIST_* with a quantile function
+observe_dist!(p, dist::Int, x, a, b=a) = (_emit!(p, 41, x, a, b, dist); nothing)
+
+const GB_MODEL_SPEC = 6
+"A DeviceModel from its `generate` program (t = 0) and its Unfold kernel program (extend-by-one `update`)."
+function spec_model(state_dim::Int, params::Vector{Float64}, num_obs::Int, generate::SpecProgram, step::Union{SpecProgram,Nothing}=nothing)
+    sops = step === nothing ? NTuple{5,Float64}[] : step.ops
+    flat = Float64[state_dim, length(params), num_obs, length(generate.ops), length(sops)]
+    append!(flat, params)
+    for op in vcat(generate.ops, sops); append!(flat, op); end
+    DeviceModel(GB_MODEL_SPEC, flat)
+end
+
 end # module

@@ -5,6 +5,7 @@ noise; log weights / log-ML within 1e-10 relative in fp64 and 1e-5 in fp32; log-
 exact Kalman / HMM-forward values.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -974,3 +975,41 @@ def test_spec_model_custom_proposal(g, O, spec_backend):
         ia, = g.particle_filter_step_(a, (t,), (g.UnknownChange,), ys[t], g.AffineNormalProposal(), pa)
         ib, = g.particle_filter_step_(b, (t,), (g.UnknownChange,), ys[t])
         assert np.array_equal(a.get_state(0), b.get_state(0)) and close(ib, ia, 1e-9)
+
+
+def test_runtime_knobs_do_not_change_results(g, tmp_path):
+    """GENB200_PDL=0 (plain launches), GENB200_SMALL_RUN=0 (multi-kernel fused run at small N), GENB200_CACHE_MB=0 (no
+    block cache), GENB200_SPEC_JIT=0: same filter, same numbers (the knobs are read once per process -> subprocess)."""
+    import json
+    import subprocess
+    import sys
+    script = tmp_path / "knobs.py"
+    script.write_text('''
+import json, os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import __graft_entry__ as entry, fixtures as F
+import numpy as np
+g = entry.load_package()
+out = {}
+for n in (3000, 200000):
+    ys = F.bearings_series(9)
+    st = g.initialize_particle_filter(g.bearings_model(), (0,), ys[0], n, seed=4)
+    nres = g.particle_filter_run_(st, ys[1:5], ess_threshold=n / 2)
+    for t in range(5, 9):
+        nres += g.maybe_resample_(st, ess_threshold=n / 2, resampler="systematic")
+        g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+    out[str(n)] = [nres, g.log_ml_estimate(st), float(st.get_state(0).sum()), int(st.parents.sum())]
+print("RESULT " + json.dumps(out))
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),) * 2)
+
+    def run(env):
+        e = dict(os.environ)
+        e.update(env)
+        p = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=e, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        return json.loads([l for l in p.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    base = run({})
+    knobs = run({"GENB200_PDL": "0", "GENB200_SMALL_RUN": "0", "GENB200_CACHE_MB": "0", "GENB200_SPEC_JIT": "0"})
+    for n in base:
+        assert base[n][0] == knobs[n][0] and base[n][2:] == knobs[n][2:]            # resamples, states, parents: identical
+        assert abs(base[n][1] - knobs[n][1]) <= 1e-12 * abs(base[n][1])             # log ML: reduction order only
