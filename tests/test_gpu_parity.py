@@ -184,6 +184,42 @@ def test_resampler_properties_large(g):
     assert np.array_equal(g.resample(np.zeros(n), "systematic", u0=999), np.arange(n))
 
 
+def test_full_size_bearings_filter_properties(g):
+    """BASELINE.json configs[2] at its full size (N = 10^8, fp64), where the sequential oracle is out of reach: the
+    size-independent properties of one maybe_resample! + particle_filter_step! and the fused run."""
+    n = 10 ** 8
+    zs = F.bearings_series(4)
+    st = g.initialize_particle_filter(g.bearings_model(), (0,), zs[0], n, seed=20242)
+    g.particle_filter_step_(st, (1,), (g.UnknownChange,), zs[1], return_incr=False)
+    lw = st.log_weights
+    x_before = st.get_state(0)
+    lml_before = g.log_ml_estimate(st)
+    w = np.exp(lw - lw.max())
+    lse = lw.max() + math.log(w.sum())
+    assert abs(lml_before - (lse - math.log(n))) <= 1e-10 * abs(lml_before)                 # particle_filter.jl:91-94
+    ess = w.sum() ** 2 / (w * w).sum()
+    assert abs(st.ess() - ess) <= 1e-9 * ess                                               # :3-6
+    w /= w.sum()
+    assert g.maybe_resample_(st, ess_threshold=n + 0.5, resampler="systematic")
+    par = st.parents - 1
+    assert par[0] >= 0 and par[-1] < n and np.all(par[1:] >= par[:-1])                      # sorted ancestors
+    cnt = np.bincount(par, minlength=n)
+    assert cnt.sum() == n and np.max(np.abs(cnt - n * w)) < 1.0 + 1e-3                      # |offspring - N w| < 1
+    del cnt, w
+    assert np.array_equal(st.get_state(0), x_before[par])                                   # the gather (:264-267)
+    assert np.all(st.log_weights == 0.0)                                                    # :266
+    assert abs(st.log_ml_est - (lse - math.log(n))) <= 1e-10 * abs(lse)                     # :263
+    del x_before, par, lw
+    # two more steps through the API loop == the fused device-controlled run, bit for bit
+    other = st.copy()
+    for t in (2, 3):
+        g.maybe_resample_(st, ess_threshold=n / 2, resampler="systematic")
+        g.particle_filter_step_(st, (t,), (g.UnknownChange,), zs[t], return_incr=False)
+    g.particle_filter_run_(other, zs[2:4], ess_threshold=n / 2)
+    assert g.log_ml_estimate(st) == g.log_ml_estimate(other) and st.log_ml_est == other.log_ml_est
+    assert np.array_equal(st.get_state(3), other.get_state(3))
+
+
 # ---------------------------------------------------------------------------------------------
 # particle filter: validation mode (pre-drawn noise), all models
 # ---------------------------------------------------------------------------------------------
@@ -1000,7 +1036,7 @@ for n in (3000, 200000):
         g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], return_incr=False)
     out[str(n)] = [nres, g.log_ml_estimate(st), float(st.get_state(0).sum()), int(st.parents.sum())]
 print("RESULT " + json.dumps(out))
-''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),) * 2)
+''' % ((os.path.dirname(os.path.dirname(os.path.abspath(__file__))),) * 2))
 
     def run(env):
         e = dict(os.environ)
