@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -1163,17 +1165,74 @@ static int materialize(gb_pf *pf) {
   return GB_OK;
 }
 
-static int copy_out(gb_pf *pf, const void *dsrc, double *out, long long n) {
-  if (pf->dtype == GB_F64) {
-    CK(cudaMemcpyAsync(out, dsrc, (size_t)n * 8, cudaMemcpyDeviceToHost, pf->stream));
-    CK(cudaStreamSynchronize(pf->stream));
-  } else {
-    std::vector<float> tmp(n);
-    CK(cudaMemcpyAsync(tmp.data(), dsrc, (size_t)n * 4, cudaMemcpyDeviceToHost, pf->stream));
-    CK(cudaStreamSynchronize(pf->stream));
-    for (long long i = 0; i < n; i++) out[i] = tmp[i];
+// Device -> caller memory for the N-element results (log weights, trace columns, parents, normalised IS weights).
+// The caller's buffer is pageable and usually untouched (a fresh Julia / numpy array): a plain cudaMemcpy then runs at
+// 3-4 GB/s (80 MB of log weights: 21 ms, three times the kernel that produced them).  Large copies are therefore staged:
+// DMA into two cached pinned chunks at link speed while a few host threads move the previous chunk into the caller's
+// pages (and widen float -> double for fp32 filters on the way).
+template <typename Src, typename Dst>
+static void host_fan_out(Dst *dst, const Src *src, size_t n) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int T = (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+  auto work = [=](int t) {
+    const size_t lo = n * t / T, hi = n * (t + 1) / T;
+    if (std::is_same<Src, Dst>::value) memcpy((void *)(dst + lo), (const void *)(src + lo), (hi - lo) * sizeof(Dst));
+    else for (size_t i = lo; i < hi; i++) dst[i] = (Dst)src[i];
+  };
+  if (T == 1 || n < (1u << 18)) { for (int t = 0; t < T; t++) work(t); return; }
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; t++) th.emplace_back(work, t);
+  work(0);
+  for (auto &x : th) x.join();
+}
+template <typename Src, typename Dst>
+static int staged_d2h(cudaStream_t stream, const Src *dsrc, Dst *out, size_t n) {
+  constexpr size_t kChunkBytes = 16u << 20;
+  const size_t per = kChunkBytes / sizeof(Src);
+  if (n * sizeof(Src) < (4u << 20)) {       // small: one plain copy (+ widening)
+    if (std::is_same<Src, Dst>::value) {
+      CK(cudaMemcpyAsync(out, dsrc, n * sizeof(Src), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+    } else {
+      std::vector<Src> tmp(n);
+      CK(cudaMemcpyAsync(tmp.data(), dsrc, n * sizeof(Src), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      for (size_t i = 0; i < n; i++) out[i] = (Dst)tmp[i];
+    }
+    return GB_OK;
   }
+  Src *pin[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaError_t e = gb_host_alloc(&pin[0], kChunkBytes);
+  if (e == cudaSuccess) e = gb_host_alloc(&pin[1], kChunkBytes);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+  const size_t nchunks = (n + per - 1) / per;
+  for (size_t k = 0; k <= nchunks && e == cudaSuccess; k++) {
+    if (k < nchunks) {
+      const size_t off = k * per, cnt = std::min(per, n - off);
+      e = cudaMemcpyAsync(pin[k & 1], dsrc + off, cnt * sizeof(Src), cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaEventRecord(ev[k & 1], stream);
+    }
+    if (k > 0 && e == cudaSuccess) {        // chunk k is in flight while chunk k-1 lands in the caller's pages
+      const size_t off = (k - 1) * per, cnt = std::min(per, n - off);
+      e = cudaEventSynchronize(ev[(k - 1) & 1]);
+      if (e == cudaSuccess) host_fan_out(out + off, pin[(k - 1) & 1], cnt);
+    }
+  }
+  if (e != cudaSuccess) cudaStreamSynchronize(stream);
+  {
+    FreeBatch fb__;
+    gb_host_free(pin[0]); gb_host_free(pin[1]);
+  }
+  if (ev[0]) cudaEventDestroy(ev[0]);
+  if (ev[1]) cudaEventDestroy(ev[1]);
+  if (e != cudaSuccess) return fail(GB_ECUDA, std::string("device -> host copy: ") + cudaGetErrorString(e));
   return GB_OK;
+}
+static int copy_out(gb_pf *pf, const void *dsrc, double *out, long long n) {
+  if (pf->dtype == GB_F64) return staged_d2h(pf->stream, (const double *)dsrc, out, (size_t)n);
+  return staged_d2h(pf->stream, (const float *)dsrc, out, (size_t)n);
 }
 extern "C" int gb_pf_get_log_weights(gb_pf_t *pf, double *out) {
   REQ(pf && out, "null argument");
@@ -1232,9 +1291,7 @@ extern "C" int gb_pf_get_parents(gb_pf_t *pf, int64_t *out) {
   REQ(pf && out, "null argument");
   int rc = ensure_parents64(pf);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(out, pf->parents64, (size_t)pf->n * 8, cudaMemcpyDeviceToHost, pf->stream));
-  CK(cudaStreamSynchronize(pf->stream));
-  return GB_OK;
+  return staged_d2h(pf->stream, (const long long *)pf->parents64, (long long *)out, (size_t)pf->n);
 }
 
 extern "C" int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out) {
@@ -1905,10 +1962,11 @@ extern "C" int gb_importance_sampling(const gb_model_t *m, int64_t n, int dtype,
       int grid = grid_for(pf, kern, n, kBlock);
       LAUNCH(pf, GB_K_MISC, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)pf->logw, n, pf->d_stats, d_out));
     }
-    e = cudaMemcpyAsync(lognormw_out, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost, pf->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
+    e = cudaGetLastError();
+    const int crc = e == cudaSuccess ? staged_d2h(pf->stream, (const double *)d_out, lognormw_out, (size_t)n) : GB_OK;
     gb_dev_free(d_out);
     if (e != cudaSuccess) { pf_release(pf); return fail(GB_ECUDA, cudaGetErrorString(e)); }
+    if (crc) { pf_release(pf); return crc; }
   }
   if (pf_out) *pf_out = pf; else pf_release(pf);
   return GB_OK;
