@@ -52,6 +52,7 @@ SIGNATURES = {
     "gb_pf_sample_unweighted": (i, [vp, i64, u64, i64p, dp]),
     "gb_pf_rejuvenate": (i, [vp, i, dp, i, d, i64p, dp]),
     "gb_pf_run": (i, [vp, i, dp, i, d, ip]),
+    "gb_pf_run_mh": (i, [vp, i, dp, i, d, i, d, i, ip, i64p]),
     "gb_cache_trim": (i, []),
     "gb_cache_stats": (i, [i64p, i64p, i64p]),
     "gb_spec_jit_source": (i, [vp, C.c_char_p, i64, i64p]),

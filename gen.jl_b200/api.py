@@ -522,17 +522,28 @@ def rejuvenate_(state, observations, move="resimulate", drift_std=0.0, return_al
     return (acc.value, alpha) if return_alpha else acc.value
 
 
-def particle_filter_run_(state, observations_seq, ess_threshold=None):
+def particle_filter_run_(state, observations_seq, ess_threshold=None, rejuvenation=None):
     """T x { maybe_resample!(state, ess_threshold) [systematic]; particle_filter_step!(state, (t,), ..., obs_t) } in one
-    call, without a host round trip per step (include/genb200.h gb_pf_run).  Returns the number of resamples."""
+    call, without a host round trip per step (include/genb200.h gb_pf_run).  Returns the number of resamples.
+    rejuvenation = (move, drift_std, sweeps) adds `sweeps` MH moves (rejuvenate_) after every step -- the tutorial's
+    particle_filter_rejuv loop (docs/src/tutorials/smc.md:513-531); then (resamples, accepted moves) is returned."""
     obs = np.ascontiguousarray([_flatten_obs(o) for o in observations_seq], dtype=np.float64)
     T, nobs = obs.shape if obs.ndim == 2 else (len(obs), 1)
     thr = state.num_particles / 2 if ess_threshold is None else float(ess_threshold)
     nres = C.c_int()
-    L.check(L.lib().gb_pf_run(state._h, int(T), obs.ctypes.data_as(L.dp), int(nobs), thr, C.byref(nres)))
+    if rejuvenation is None:
+        L.check(L.lib().gb_pf_run(state._h, int(T), obs.ctypes.data_as(L.dp), int(nobs), thr, C.byref(nres)))
+        out = nres.value
+    else:
+        move, drift_std, sweeps = rejuvenation
+        acc = C.c_int64()
+        L.check(L.lib().gb_pf_run_mh(state._h, int(T), obs.ctypes.data_as(L.dp), int(nobs), thr,
+                                     {"resimulate": L.MH_RESIMULATE, "drift": L.MH_DRIFT}[move], float(drift_std), int(sweeps),
+                                     C.byref(nres), C.byref(acc)))
+        out = (nres.value, acc.value)
     if state._last_t is not None:
         state._last_t += int(T)
-    return nres.value
+    return out
 
 
 def log_ml_estimate(state):

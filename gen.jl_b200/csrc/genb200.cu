@@ -1559,7 +1559,9 @@ static int small_run(gb_pf *pf, int T, const double *obs, int nobs, int *n_resam
   return GB_OK;
 }
 
-extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double ess_threshold, int *n_resampled) {
+// T x { maybe_resample!; particle_filter_step!; [sweeps x mh on the latest latents] } without a host round trip
+static int pf_run_impl(gb_pf *pf, int T, const double *obs, int nobs, double ess_threshold, int move, double drift_std, int sweeps,
+                       int *n_resampled, int64_t *n_accepted) {
   if (pf) pf->mh_ok = false;
   REQ(pf && obs && T >= 0, "gb_pf_run: bad argument");
   REQ(pf->n == pf->n_global, "gb_pf_run: single shard only");
@@ -1579,7 +1581,17 @@ extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double
   pf->h_ctl->log_n = log((double)pf->n_global);
   CK(cudaMemcpyAsync(pf->d_ctl, pf->h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pf->stream));
   CK(cudaStreamSynchronize(pf->stream));                // h_ctl is reused for the read-back below
-  if (small_run_eligible(pf, T)) return small_run(pf, T, obs, nobs, n_resampled);
+  if (sweeps == 0 && small_run_eligible(pf, T)) return small_run(pf, T, obs, nobs, n_resampled);
+  unsigned long long *d_acc = nullptr;
+  if (sweeps > 0) {
+    const int kind = pf->model.kind;
+    REQ(move == MH_RESIMULATE || move == MH_DRIFT, "gb_pf_run_mh: unknown move");
+    if (!(kind == MODEL_LGSSM || kind == MODEL_SV || kind == MODEL_BEARINGS || kind == MODEL_HMM) || (move == MH_DRIFT && kind == MODEL_HMM))
+      return fail(GB_EUNSUPPORTED, "gb_pf_run_mh: this model kind does not have this MH rejuvenation move");
+    REQ(move != MH_DRIFT || drift_std > 0.0, "gb_pf_run_mh: drift_std must be positive");
+    CK(gb_dev_alloc((void **)&d_acc, 8));
+    CK(cudaMemsetAsync(d_acc, 0, 8, pf->stream));
+  }
   const AncOut ao{pf->anc, 0, pf->n_global, nullptr, 0, 0};
   for (int t = 0; t < T; t++) {
     // maybe_resample!: statistics + decision on the device, then the (conditional) systematic sweep
@@ -1590,17 +1602,47 @@ extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double
                              : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, u0, ao, pf->d_ctl, 0, true);
     if (rc) return rc;
     // particle_filter_step!
-    if ((rc = launch_model(pf, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false, false, 2))) return rc;
+    if ((rc = launch_model(pf, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false, false, 2))) break;
     pf->step += 1;
     pf->cur ^= 1;
+    // rejuvenation of the traces just extended (docs/src/tutorials/smc.md:459-463, :518-520): their parents are the
+    // buffer the step read from, through `anc` iff the device decided to resample in this iteration
+    for (int sw = 0; sw < sweeps && !rc; sw++) {
+      MhArgs a;
+      memset(&a, 0, sizeof(a));
+      if ((rc = fill_model_params(pf, a.mp, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false))) break;
+      a.parent = pf->state[pf->cur ^ 1];
+      a.cur = pf->state[pf->cur];
+      a.anc = pf->anc; a.ctl = pf->d_ctl;
+      a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
+      a.seed = pf->seed; a.step = (unsigned)pf->step; a.move = (unsigned)sw;
+      a.drift_sd = drift_std;
+      a.accepted = d_acc;
+      rc = pf->dtype == GB_F64 ? launch_mh_k<double, false>(pf, a, move, false) : launch_mh_k<float, false>(pf, a, move, false);
+    }
+    if (rc) break;
   }
-  CK(cudaMemcpyAsync(pf->h_ctl, pf->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, pf->stream));
-  CK(cudaStreamSynchronize(pf->stream));
+  unsigned long long acc = 0;
+  cudaError_t ce = cudaMemcpyAsync(pf->h_ctl, pf->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, pf->stream);
+  if (ce == cudaSuccess && d_acc) ce = cudaMemcpyAsync(&acc, d_acc, 8, cudaMemcpyDeviceToHost, pf->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(pf->stream);
+  gb_dev_free(d_acc);
+  if (rc) return rc;
+  if (ce != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_run: ") + cudaGetErrorString(ce));
+  if (n_accepted) *n_accepted = (int64_t)acc;
   pf->log_ml_est = pf->h_ctl->log_ml_est;
   if (pf->h_ctl->n_resampled > 0) { pf->anc_valid = true; pf->parents64_valid = false; pf->ext_used = false; }
   if (T > 0) { pf->wstate = W_MAX; pf->tiles_valid = false; pf->pending_gather = false; }
   if (n_resampled) *n_resampled = pf->h_ctl->n_resampled;
   return GB_OK;
+}
+extern "C" int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double ess_threshold, int *n_resampled) {
+  return pf_run_impl(pf, T, obs, nobs, ess_threshold, 0, 0.0, 0, n_resampled, nullptr);
+}
+extern "C" int gb_pf_run_mh(gb_pf_t *pf, int T, const double *obs, int nobs, double ess_threshold, int move, double drift_std, int sweeps,
+                            int *n_resampled, int64_t *n_accepted) {
+  REQ(sweeps >= 0 && sweeps <= 1024, "gb_pf_run_mh: sweeps must be in 0..1024");
+  return pf_run_impl(pf, T, obs, nobs, ess_threshold, move, drift_std, sweeps, n_resampled, n_accepted);
 }
 
 // ---- sharded pieces ----

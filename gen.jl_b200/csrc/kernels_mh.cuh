@@ -25,6 +25,7 @@ struct MhArgs {
   const void *parent;   // the buffer the last step read its inputs from
   void *cur;            // current traces (updated in place)
   const int *anc;       // parent row of particle i (the last step's fused gather); nullptr: row i
+  const RunCtl *ctl;    // fused run: the gather decision was taken on the device (ctl->do_resample); nullptr: host-known
   const double *normals, *uniforms;   // PREDRAWN: [rows][ld]; the LAST uniform row is the accept draw
   double *alpha_out;    // optional: log acceptance ratios
   long long n, ld, pid_offset;
@@ -46,12 +47,13 @@ __global__ void __launch_bounds__(kBlock) mh_kernel(const MhArgs a) {
   R *__restrict__ cur = static_cast<R *>(a.cur);
   const R dsd = (R)a.drift_sd, ldsd = Math<R>::log_((R)a.drift_sd);
   const uint32_t base = kMhPairBase + 16u * a.move;
+  const bool via_anc = a.ctl ? (a.ctl->do_resample != 0) : (a.anc != nullptr);
   unsigned int nacc = 0;
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < a.n; i += (long long)gridDim.x * kBlock) {
     const unsigned long long pid = (unsigned long long)(a.pid_offset + i);
     R prev[S], st[S], next[S], eps[NN > 0 ? NN : 1], us[NU > 0 ? NU : 1];
     if (!INIT) {
-      const long long src = a.anc ? (long long)a.anc[i] : i;
+      const long long src = via_anc ? (long long)a.anc[i] : i;
 #pragma unroll
       for (int s = 0; s < S; s++) prev[s] = __ldg(par + (long long)s * a.ld + src);
     } else {

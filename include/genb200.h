@@ -155,6 +155,11 @@ int gb_pf_spec_backend(const gb_pf_t *pf, int *backend);
  * gathered/direct choice of the step made ON THE DEVICE, i.e. without the host round trip the Bool return of
  * maybe_resample! forces per step.  Bit-identical to calling the two entries T times.  obs: T * nobs doubles. */
 int gb_pf_run(gb_pf_t *pf, int T, const double *obs, int nobs, double ess_threshold, int *n_resampled);
+/* The same loop with `sweeps` MH rejuvenation moves (gb_pf_rejuvenate's, GB_MH_*) on the traces each step just extended
+ * -- the tutorial's particle_filter_rejuv loop (docs/src/tutorials/smc.md:513-531) in one call; identical to calling
+ * gb_pf_maybe_resample / gb_pf_step / gb_pf_rejuvenate x sweeps per step.  n_accepted: total accepted moves. */
+int gb_pf_run_mh(gb_pf_t *pf, int T, const double *obs, int nobs, double ess_threshold, int move, double drift_std, int sweeps,
+                 int *n_resampled, int64_t *n_accepted);
 /* validation mode for the resampler: u0 for systematic/residual, n u64 for multinomial (NULL clears) */
 int gb_pf_set_resample_noise(gb_pf_t *pf, int use_u0, uint32_t u0, const uint64_t *u64s);
 int gb_pf_log_ml_estimate(gb_pf_t *pf, double *out);                 /* particle_filter.jl:91-94 */

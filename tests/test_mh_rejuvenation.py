@@ -219,3 +219,26 @@ def test_rejuvenation_fp32_and_history(g, O):
     assert abs(nacc - nacc_ref) <= 0.002 * n + 2
     traj = st.trajectory(0)
     assert np.array_equal(traj[-1], st.get_state(0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,move,n", [("bearings", "drift", 30011), ("lgssm", "resimulate", 30011), ("hmm", "resimulate", 2500),
+                                         ("sv", "drift", 1000)])
+def test_fused_run_with_rejuvenation_equals_api_loop(g, O, name, move, n):
+    """gb_pf_run_mh: the tutorial's particle_filter_rejuv loop in one call == maybe_resample_ / step_ / rejuvenate_ x 2."""
+    model, _, _, ys = zoo(g, O)[name]
+    drift = {"bearings": 1e-3, "sv": 0.2}.get(name, 0.0)
+    a = g.initialize_particle_filter(model, (0,), ys[0], n, seed=6)
+    b = g.initialize_particle_filter(model, (0,), ys[0], n, seed=6)
+    nres = nacc = 0
+    for t in range(1, len(ys)):
+        nres += g.maybe_resample_(a, ess_threshold=0.9 * n, resampler="systematic")
+        g.particle_filter_step_(a, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+        for _ in range(2):
+            nacc += g.rejuvenate_(a, ys[t], move=move, drift_std=drift)
+    nres_b, nacc_b = g.particle_filter_run_(b, ys[1:], ess_threshold=0.9 * n, rejuvenation=(move, drift, 2))
+    assert (nres, nacc) == (nres_b, nacc_b) and nacc > 0 and nres > 0
+    for f in range(model.state_dim):
+        assert np.array_equal(a.get_state(f), b.get_state(f))
+    assert np.array_equal(a.parents, b.parents) and np.array_equal(a.log_weights, b.log_weights)
+    assert a.log_ml_est == b.log_ml_est
