@@ -84,10 +84,12 @@ struct gb_model {
   long long spec_id = 0;
 };
 static long long g_spec_next_id = 1, g_spec_loaded = 0;
-static_assert(DIST_UNIFORM == GB_DIST_UNIFORM && DIST_EXPONENTIAL == GB_DIST_EXPONENTIAL && DIST_LAPLACE == GB_DIST_LAPLACE &&
-              DIST_CAUCHY == GB_DIST_CAUCHY && DIST_INV_GAMMA == GB_DIST_INV_GAMMA && DIST_BETA == GB_DIST_BETA &&
-              DIST_POISSON == GB_DIST_POISSON && DIST_GEOMETRIC == GB_DIST_GEOMETRIC && DIST_BINOM == GB_DIST_BINOM &&
-              DIST_NEG_BINOM == GB_DIST_NEG_BINOM && DIST_UNIFORM_DISCRETE == GB_DIST_UNIFORM_DISCRETE, "distribution ids");
+static_assert((int)DIST_UNIFORM == (int)GB_DIST_UNIFORM && (int)DIST_EXPONENTIAL == (int)GB_DIST_EXPONENTIAL &&
+              (int)DIST_LAPLACE == (int)GB_DIST_LAPLACE && (int)DIST_CAUCHY == (int)GB_DIST_CAUCHY &&
+              (int)DIST_INV_GAMMA == (int)GB_DIST_INV_GAMMA && (int)DIST_BETA == (int)GB_DIST_BETA &&
+              (int)DIST_POISSON == (int)GB_DIST_POISSON && (int)DIST_GEOMETRIC == (int)GB_DIST_GEOMETRIC &&
+              (int)DIST_BINOM == (int)GB_DIST_BINOM && (int)DIST_NEG_BINOM == (int)GB_DIST_NEG_BINOM &&
+              (int)DIST_UNIFORM_DISCRETE == (int)GB_DIST_UNIFORM_DISCRETE, "distribution ids");
 
 static int model_state_dim(int kind, const double *p) {
   switch (kind) {
@@ -1157,13 +1159,7 @@ template <typename R> static int fill_dev(gb_pf *pf, R *p, long long n, R v) {
   return GB_OK;
 }
 // deferred state -> the arrays really hold what the API says they hold
-static int materialize(gb_pf *pf) {
-  bool was_pending = pf->pending_gather;
-  int rc = run_gather(pf);   // also zeroes logw
-  if (rc) return rc;
-  (void)was_pending;
-  return GB_OK;
-}
+static int materialize(gb_pf *pf) { return run_gather(pf); /* also zeroes logw */ }
 
 // Device -> caller memory for the N-element results (log weights, trace columns, parents, normalised IS weights).
 // The caller's buffer is pageable and usually untouched (a fresh Julia / numpy array): a plain cudaMemcpy then runs at
@@ -1362,11 +1358,6 @@ static int launch_ancestors(gb_pf *pf, const void *logw, double m, int bits, lon
                                                                               pf->tile_r, pf->tile_slot, pf->d_plan, pf->ntiles,
                                                                               over_base, anc, anc_base, pf->cdf));
   CK(cudaGetLastError());
-  return GB_OK;
-}
-static int fetch_plan(gb_pf *pf) {
-  CK(cudaMemcpyAsync(pf->h_plan, pf->d_plan, sizeof(ResamplePlan), cudaMemcpyDeviceToHost, pf->stream));
-  CK(cudaStreamSynchronize(pf->stream));
   return GB_OK;
 }
 
