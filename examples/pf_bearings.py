@@ -28,6 +28,7 @@ def main():
     g = entry.load_package()
     zs = F.bearings_series(51)
     model = g.bearings_model()
+    g.log_ml_estimate(g.initialize_particle_filter(model, (0,), {"z0": zs[0]}, 1000))   # CUDA context + module load
     t0 = time.perf_counter()
     state = g.initialize_particle_filter(model, (0,), {"z0": zs[0]}, n, seed=1)
     resamples = 0
