@@ -85,6 +85,17 @@ def test_sharded_rejuvenation_equals_single_shard(g, fast):
     assert not np.array_equal(cols0[2], cols1[2])
 
 
+def test_sharded_spec_model_equals_builtin_kind(g):
+    """A GB_MODEL_SPEC program (NVRTC-specialised) on a sharded filter: Philox is keyed by the global particle id and the
+    extension rows work the same way, so 3 shards of the spec model == 1 shard of the hand-written kind."""
+    from test_gpu_parity import bearings_spec
+    ys, n, seed = F.bearings_series(7), 40009, 12
+    cols, lw, par, lml = run_sharded_in_process(g, bearings_spec(g), n, 3, ys, seed, fast=True)
+    cols1, lw1, par1, lml1 = run_sharded_in_process(g, g.bearings_model(), n, 1, ys, seed)
+    assert all(np.array_equal(a, b) for a, b in zip(cols, cols1)) and np.array_equal(par, par1)
+    assert np.allclose(lw, lw1, rtol=1e-10, atol=1e-10) and np.allclose(lml, lml1, rtol=1e-10)
+
+
 @pytest.mark.parametrize("K", [2, 3, 8])
 @pytest.mark.parametrize("name", ["bearings", "lgssm"])
 def test_sharded_equals_single_shard_and_oracle(g, O, K, name):
