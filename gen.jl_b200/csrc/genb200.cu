@@ -253,6 +253,8 @@ struct gb_pf {
   bool mh_ok = false;             // state[cur ^ 1] still holds the parents of the current traces (MH rejuvenation)
   bool mh_parent_anc = false;     // ... reached through `anc` (the last step gathered through it)
   unsigned int mh_moves = 0;
+  void *lik = nullptr;            // GB_MODEL_SPEC rejuvenation: score of every particle's constrained choices (kernels_mh.cuh)
+  int lik_step = -1;              // step index `lik` belongs to
   int incr_step = -1;             // step index whose log incremental weights `incr` holds
   int spec_backend = -1;          // GB_MODEL_SPEC: 1 = NVRTC-specialised kernel, 0 = interpreter (last launch)      // rejuvenation sweeps applied since the last step (Philox draw-index block)
   long long *parents64 = nullptr; // global 1-based parents (sharded path)
@@ -380,6 +382,7 @@ static void pf_release(gb_pf *pf) {
   gb_host_free(pf->h_stats); gb_dev_free(pf->d_normals); gb_dev_free(pf->d_uniforms); gb_dev_free(pf->d_u64);
   gb_dev_free(pf->d_ctl); gb_host_free(pf->h_ctl); gb_dev_free(pf->d_shplan); gb_host_free(pf->h_shplan); gb_dev_free(pf->d_offs); gb_dev_free(pf->super_q); gb_dev_free(pf->super_excl); gb_dev_free(pf->oflow); gb_dev_free(pf->oflow_count);
   gb_dev_free(pf->tile_q); gb_dev_free(pf->tile_c); gb_dev_free(pf->tile_r); gb_dev_free(pf->tile_slot); gb_dev_free(pf->d_plan);
+  gb_dev_free(pf->lik);
   gb_host_free(pf->h_plan); gb_dev_free(pf->cdf); gb_dev_free(pf->off_anc); gb_dev_free(pf->d_tab); gb_dev_free(pf->d_ptab);
   for (auto p : pf->ipc_opened) cudaIpcCloseMemHandle(p);
   for (auto p : pf->hist_state) gb_dev_free(p);
@@ -844,7 +847,7 @@ extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, 
   pf->wstate = W_MAX;
   pf->tiles_valid = false;
   pf->nn_set = pf->nu_set = 0;
-  pf->mh_ok = pf->model.kind != MODEL_BLR; pf->mh_parent_anc = false; pf->mh_moves = 0;
+  pf->mh_ok = pf->model.kind != MODEL_BLR; pf->mh_parent_anc = false; pf->mh_moves = 0; pf->lik_step = -1;
   if (pf->history) {
     for (auto p : pf->hist_state) gb_dev_free(p);
     for (auto p : pf->hist_anc) gb_dev_free(p);
@@ -927,11 +930,90 @@ static int launch_mh_k(gb_pf *pf, const MhArgs &a, int move, bool predrawn) {
   }
   return fail(GB_EUNSUPPORTED, "gb_pf_rejuvenate: this model kind has no MH rejuvenation moves");
 }
+// GB_MODEL_SPEC: resimulation move through the NVRTC-specialised Transition (mh_resim_lik_kernel)
+static int spec_rejuvenate(gb_pf *pf, int move, const double *obs, int nobs, int64_t *n_accepted, double *alpha_out) {
+  const gb_model &m = pf->model;
+  if (move != MH_RESIMULATE)
+    return fail(GB_EUNSUPPORTED, "gb_pf_rejuvenate: GB_MODEL_SPEC models offer the resimulation move only");
+  REQ(nobs == m.nobs && obs, "gb_pf_rejuvenate: wrong number of observations (pass the latest step's observations)");
+  if (!pf->mh_ok || pf->pending_gather)
+    return fail(GB_ESTATE, "gb_pf_rejuvenate: the parents of the current traces are no longer resident -- call it after "
+                           "initialize / particle_filter_step and before maybe_resample (docs/src/tutorials/smc.md:459-466)");
+  const bool init = pf->step == 0;
+  const int b = init ? 0 : m.n_init_ops, e = init ? m.n_init_ops : m.n_init_ops + m.n_step_ops;
+  for (int k = b; k < e; k++)
+    if (m.ops[k].code == OP_WEIGHT || m.ops[k].code == OP_LOGPDF_NORMAL || m.ops[k].code == OP_LOGPDF_DIST)
+      return fail(GB_EUNSUPPORTED, "gb_pf_rejuvenate: the program carries a custom proposal (WEIGHT / LOGPDF ops); its weight is not "
+                                   "the score of the observed choices, which the resimulation move needs");
+  JitModule *jm = spec_jit_get(m, pf->dtype);
+  const bool predrawn = pf->nn_set > 0 || pf->nu_set > 0;
+  const int v = (init ? 2 : 0) + (predrawn ? 1 : 0);
+  if (!jm || !jm->fast || !jm->mh[v])
+    return fail(GB_EUNSUPPORTED, "gb_pf_rejuvenate: needs the NVRTC-specialised kernels of this program (libnvrtc unavailable, "
+                                 "GENB200_SPEC_JIT=0, or a program with gamma draws / more than 16 observations)");
+  if (predrawn) REQ(pf->nn_set >= m.nn[init ? 1 : 0] && pf->nu_set >= m.nu[init ? 1 : 0] + 1,
+                    "gb_pf_set_noise: a move consumes the program's normal rows and its uniform rows plus ONE accept row");
+  if (!pf->lik) CK(gb_dev_alloc(&pf->lik, (size_t)pf->ld * pf->esz));
+  if (pf->lik_step != pf->step) {   // scores of the current traces = what the last generate / step added to the weights
+    if (!init && pf->incr_step != pf->step) return fail(GB_ESTATE, "gb_pf_rejuvenate: the step's log incremental weights are gone");
+    CK(cudaMemcpyAsync(pf->lik, init ? pf->logw : pf->incr, (size_t)pf->n * pf->esz, cudaMemcpyDeviceToDevice, pf->stream));
+    pf->lik_step = pf->step;
+  }
+  MhArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mp.obs0 = obs[0];
+  for (int k = 1; k < nobs && k < 16; k++) a.mp.obsx[k - 1] = obs[k];
+  a.mp.step = (unsigned)pf->step;
+  unsigned long long *d_acc = nullptr;
+  double *d_alpha = nullptr;
+  CK(gb_dev_alloc((void **)&d_acc, 8));
+  CK(cudaMemsetAsync(d_acc, 0, 8, pf->stream));
+  if (alpha_out) {
+    cudaError_t e2 = gb_dev_alloc((void **)&d_alpha, (size_t)pf->n * 8);
+    if (e2 != cudaSuccess) { gb_dev_free(d_acc); return fail(GB_ECUDA, cudaGetErrorString(e2)); }
+  }
+  a.parent = pf->state[pf->cur ^ 1];
+  a.cur = pf->state[pf->cur];
+  a.anc = (!init && pf->mh_parent_anc) ? pf->anc : nullptr;
+  a.normals = pf->d_normals; a.uniforms = pf->d_uniforms;
+  a.alpha_out = d_alpha;
+  a.lik = pf->lik;
+  a.n = pf->n; a.ld = pf->ld; a.pid_offset = pf->pid_offset;
+  a.seed = pf->seed; a.step = (unsigned)pf->step; a.move = pf->mh_moves;
+  a.accepted = d_acc;
+  long long blocks = (pf->n + kBlock - 1) / kBlock;
+  const int grid = (int)std::max(1ll, std::min(blocks, (long long)pf->num_sms * jm->mh_occ[v]));
+  void *params[] = {&a};
+  CUresult cr = CUDA_SUCCESS;
+  LAUNCH(pf, GB_K_MISC, cr = g_jit.LaunchKernel(jm->mh[v], grid, 1, 1, kBlock, 1, 1, 0, (CUstream)pf->stream, params, nullptr));
+  unsigned long long acc = 0;
+  cudaError_t ce = cudaSuccess;
+  if (cr == CUDA_SUCCESS) {
+    ce = cudaMemcpyAsync(&acc, d_acc, 8, cudaMemcpyDeviceToHost, pf->stream);
+    if (ce == cudaSuccess && alpha_out) ce = cudaMemcpyAsync(alpha_out, d_alpha, (size_t)pf->n * 8, cudaMemcpyDeviceToHost, pf->stream);
+    if (ce == cudaSuccess && pf->history && !pf->hist_state.empty())
+      ce = cudaMemcpy2DAsync(pf->hist_state.back(), (size_t)pf->n_pad * pf->esz, pf->state[pf->cur], (size_t)pf->ld * pf->esz,
+                             (size_t)pf->n_pad * pf->esz, pf->S, cudaMemcpyDeviceToDevice, pf->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(pf->stream);
+  }
+  gb_dev_free(d_acc); gb_dev_free(d_alpha);
+  if (cr != CUDA_SUCCESS) {
+    const char *es = nullptr;
+    g_jit.GetErrorString(cr, &es);
+    return fail(GB_ECUDA, std::string("cuLaunchKernel(mh_resim_lik_kernel): ") + (es ? es : "?"));
+  }
+  if (ce != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_rejuvenate: ") + cudaGetErrorString(ce));
+  pf->mh_moves += 1;
+  pf->nn_set = pf->nu_set = 0;
+  if (n_accepted) *n_accepted = (int64_t)acc;
+  return GB_OK;
+}
 extern "C" int gb_pf_rejuvenate(gb_pf_t *pf, int move, const double *obs, int nobs, double drift_std, int64_t *n_accepted,
                                 double *alpha_out) {
   REQ(pf, "null handle");
   REQ(move == MH_RESIMULATE || move == MH_DRIFT, "gb_pf_rejuvenate: unknown move");
   const int kind = pf->model.kind;
+  if (kind == MODEL_SPEC) return spec_rejuvenate(pf, move, obs, nobs, n_accepted, alpha_out);
   REQ(kind == MODEL_LGSSM || kind == MODEL_SV || kind == MODEL_BEARINGS || kind == MODEL_HMM,
       "gb_pf_rejuvenate: this model kind has no MH rejuvenation moves");
   if (move == MH_DRIFT) {

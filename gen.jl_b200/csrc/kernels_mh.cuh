@@ -28,6 +28,7 @@ struct MhArgs {
   const RunCtl *ctl;    // fused run: the gather decision was taken on the device (ctl->do_resample); nullptr: host-known
   const double *normals, *uniforms;   // PREDRAWN: [rows][ld]; the LAST uniform row is the accept draw
   double *alpha_out;    // optional: log acceptance ratios
+  void *lik;            // mh_resim_lik_kernel: score of the constrained choices of every particle's latest step (in/out)
   long long n, ld, pid_offset;
   unsigned long long seed;
   unsigned int step, move;
@@ -96,6 +97,73 @@ __global__ void __launch_bounds__(kBlock) mh_kernel(const MhArgs a) {
     if (Math<R>::log_(ua) < alpha) {                                        // mh.jl:20, :52 (NaN => reject)
 #pragma unroll
       for (int s = 0; s < S; s++) cur[(long long)s * a.ld + i] = next[s];
+      nacc++;
+    }
+  }
+  nacc = __reduce_add_sync(0xffffffffu, nacc);
+  if ((threadIdx.x & 31) == 0 && nacc) atomicAdd(a.accepted, (unsigned long long)nacc);
+}
+
+// Resimulation move for models that only offer Transition<>::apply (GB_MODEL_SPEC programs lowered at run time): the
+// score of the retained constrained choices under the CURRENT latents is not recomputed but carried per particle in
+// `lik` (initialised from the step's log incremental weights, updated on acceptance), so
+//   alpha = (sum of observe scores at the re-drawn latents) - lik[i]            (mh.jl:16-27, regenerate.jl:47-50).
+// Valid for programs whose weight is exactly that sum (no proposal-correction terms).
+template <typename R, int KIND, bool INIT, bool PREDRAWN>
+__global__ void __launch_bounds__(kBlock) mh_resim_lik_kernel(const MhArgs a) {
+  using Tr = Transition<R, KIND, PROPOSAL_DEFAULT, INIT>;
+  constexpr int S = Tr::S, NN = Tr::NN, NU = Tr::NU;
+  __shared__ double s_tab[kMathTabDoubles];
+  const MathTables T = stage_math_tables(s_tab);
+  __syncthreads();
+  const Hoisted<R> h = Tr::hoist(a.mp);
+  const R *__restrict__ par = static_cast<const R *>(a.parent);
+  R *__restrict__ cur = static_cast<R *>(a.cur);
+  R *__restrict__ lik = static_cast<R *>(a.lik);
+  const uint32_t base = kMhPairBase + 16u * a.move;
+  const bool via_anc = a.ctl ? (a.ctl->do_resample != 0) : (a.anc != nullptr);
+  unsigned int nacc = 0;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < a.n; i += (long long)gridDim.x * kBlock) {
+    const unsigned long long pid = (unsigned long long)(a.pid_offset + i);
+    R prev[S], next[S], eps[NN > 0 ? NN : 1], us[NU > 0 ? NU : 1];
+    const long long src = (!INIT && via_anc) ? (long long)a.anc[i] : i;
+#pragma unroll
+    for (int s = 0; s < S; s++) prev[s] = INIT ? R(0) : __ldg(par + (long long)s * a.ld + src);
+    R ua;
+    if (PREDRAWN) {
+#pragma unroll
+      for (int d = 0; d < NN; d++) eps[d] = (R)a.normals[(long long)d * a.ld + i];
+#pragma unroll
+      for (int d = 0; d < NU; d++) us[d] = (R)a.uniforms[(long long)d * a.ld + i];
+      ua = (R)a.uniforms[(long long)NU * a.ld + i];
+    } else {
+#pragma unroll
+      for (int d = 0; d < NN; d += 2) {
+        R e0, e1;
+        philox_normal_pair(a.seed, pid, a.step, base + (uint32_t)(d >> 1), T, e0, e1);
+        eps[d] = e0;
+        if (d + 1 < NN) eps[d + 1] = e1;
+      }
+      // accept draw: first uniform of pair base + 15; the transition's own uniforms: pairs base + 8 ...
+      R u0, u1;
+      philox_uniform_pair(a.seed, pid, a.step, base + 15u, u0, u1);
+      ua = u0;
+      if (NU > 0) us[0] = u1;
+#pragma unroll
+      for (int d = 1; d < NU; d += 2) {
+        R v0, v1;
+        philox_uniform_pair(a.seed, pid, a.step, base + 8u + (uint32_t)(d >> 1), v0, v1);
+        us[d] = v0;
+        if (d + 1 < NU) us[d + 1] = v1;
+      }
+    }
+    const R w_new = Tr::apply(a.mp, h, T, prev, next, eps, us);
+    const R alpha = w_new - lik[i];
+    if (a.alpha_out) a.alpha_out[i] = (double)alpha;
+    if (Math<R>::log_(ua) < alpha) {
+#pragma unroll
+      for (int s = 0; s < S; s++) cur[(long long)s * a.ld + i] = next[s];
+      lik[i] = w_new;
       nacc++;
     }
   }

@@ -132,7 +132,8 @@ int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t draw, int64
  * gb_pf_generate / gb_pf_step and before gb_pf_maybe_resample (GB_ESTATE otherwise); obs = the latest observations.
  * n_accepted, alpha_out (n log acceptance ratios) may be NULL.  Validation mode (gb_pf_set_noise): normals = the
  * transition's rows (drift: one per latent choice), uniforms = the transition's rows followed by ONE accept row.
- * Models: LGSSM, SV, BEARINGS, HMM (resimulate only). */
+ * Models: LGSSM, SV, BEARINGS, HMM (resimulate only), SPEC (resimulate only; needs the NVRTC-specialised kernels and a program
+ * without inline proposal terms -- WEIGHT / LOGPDF ops). */
 #define GB_MH_RESIMULATE 0
 #define GB_MH_DRIFT 1
 int gb_pf_rejuvenate(gb_pf_t *pf, int move, const double *obs, int nobs, double drift_std, int64_t *n_accepted,

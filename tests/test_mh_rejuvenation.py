@@ -242,3 +242,54 @@ def test_fused_run_with_rejuvenation_equals_api_loop(g, O, name, move, n):
         assert np.array_equal(a.get_state(f), b.get_state(f))
     assert np.array_equal(a.parents, b.parents) and np.array_equal(a.log_weights, b.log_weights)
     assert a.log_ml_est == b.log_ml_est
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["bearings", "hmm"])
+def test_spec_model_resimulation_equals_builtin_kind(g, O, name, monkeypatch):
+    """GB_MODEL_SPEC programs get the resimulation move through their NVRTC-specialised Transition; the score of the current
+    latents is carried per particle instead of recomputed.  Same Philox streams => same moves as the hand-written kind
+    (the ratio differs by the rounding of a constant-folded log, so an accept can flip only on a measure-zero tie)."""
+    from test_gpu_parity import bearings_spec, hmm_spec
+    monkeypatch.setenv("GENB200_SPEC_JIT", "1")
+    builtin, _, _, ys = zoo(g, O)[name]
+    spec = bearings_spec(g) if name == "bearings" else hmm_spec(g)
+    n = 20011
+    a = g.initialize_particle_filter(builtin, (0,), ys[0], n, seed=3)
+    b = g.initialize_particle_filter(spec, (0,), ys[0], n, seed=3)
+    total = 0
+    for t in range(0, 5):
+        if t > 0:
+            thr = n + 0.5 if t % 2 else n / 3
+            assert g.maybe_resample_(a, ess_threshold=thr, resampler="systematic") == g.maybe_resample_(b, ess_threshold=thr, resampler="systematic")
+            g.particle_filter_step_(a, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+            g.particle_filter_step_(b, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+        for _ in range(3):
+            na, alpha_a = g.rejuvenate_(a, ys[t], return_alpha=True)
+            nb, alpha_b = g.rejuvenate_(b, ys[t], return_alpha=True)
+            fin = np.isfinite(alpha_a)
+            assert np.array_equal(fin, np.isfinite(alpha_b)) and np.allclose(alpha_a[fin], alpha_b[fin], rtol=1e-10, atol=1e-9)
+            assert abs(na - nb) <= 1
+            total += nb
+            for f in range(builtin.state_dim):
+                assert np.mean(a.get_state(f) == b.get_state(f)) > 0.9999
+    assert total > 0 and b.spec_backend == "nvrtc"
+    assert np.array_equal(a.parents, b.parents)
+    with pytest.raises(g.GenB200Error, match="resimulation move only"):
+        g.rejuvenate_(b, ys[4], move="drift", drift_std=0.1)
+    monkeypatch.setenv("GENB200_SPEC_JIT", "0")                       # interpreter backend: no specialised Transition
+    c = g.initialize_particle_filter(spec, (0,), ys[0], 1000, seed=3)
+    with pytest.raises(g.GenB200Error, match="NVRTC"):
+        g.rejuvenate_(c, ys[0])
+
+
+@pytest.mark.gpu
+def test_spec_model_with_inline_proposal_has_no_resimulation_move(g):
+    p = g.SpecProgram()
+    x = p.sample_normal(p.const(0.0), p.const(1.0))
+    p.observe_normal(p.obs(0), x, p.const(0.5))
+    p.add_weight(p.neg(p.logpdf_normal(x, p.const(0.0), p.const(1.0))))
+    p.store(0, x)
+    st = g.initialize_particle_filter(g.spec_model(1, [], 1, p), (0,), 0.3, 1000)
+    with pytest.raises(g.GenB200Error, match="custom proposal"):
+        g.rejuvenate_(st, 0.3)
