@@ -223,6 +223,7 @@ class ShardedParticleFilter:
         # sequence of calls, so all ranks hit or miss together
         self._wver = 0
         self._stats_cache = (-1, None)
+        self._setup_thr = None
 
     # ---- collectives (tiny) ----
     def _allreduce_max(self, x):
@@ -320,6 +321,7 @@ class ShardedParticleFilter:
         thr = self.n_global / 2 if ess_threshold is None else float(ess_threshold)
         self._attach_peers()
         self.ops.async_setup(W, self.rank, self.offs, thr)
+        self._setup_thr = None                               # the run's RunCtl (threshold, log-ML) is live on the device
         if self._stats_t is None:
             self._stats_t = self.ops.stats_tensor(torch)
             self._gather_t = torch.empty(W * self._stats_t.numel(), dtype=torch.int64, device=self.device)
@@ -408,7 +410,9 @@ class ShardedParticleFilter:
             # on the device from the gathered records, ancestors, offspring written into the owning shards' memory
             # by peer stores over NVLink, a one-word all-reduce as the barrier -- no staging blocks, no all-to-all
             self._attach_peers()
-            self.ops.async_setup(W, me, self.offs, math.inf)
+            if self._setup_thr != math.inf:                  # device-side plan state: once, unless run_ re-armed it
+                self.ops.async_setup(W, me, self.offs, math.inf)
+                self._setup_thr = math.inf
             self.ops.async_plan(self._gather_t, u0)
             self.ops.async_sweep()
             self.ops.async_export()
