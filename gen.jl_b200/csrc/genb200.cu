@@ -83,7 +83,8 @@ struct gb_model {
   int nn[2] = {0, 0}, nu[2] = {0, 0};   // normal / uniform draws of the step [0] and generate [1] programs
   long long spec_id = 0;
 };
-static long long g_spec_next_id = 1, g_spec_loaded = 0;
+static long long g_spec_next_id = 1;
+static long long g_spec_loaded[64] = {0};   // per device: id of the program currently in the interpreter's constant memory
 static_assert((int)DIST_UNIFORM == (int)GB_DIST_UNIFORM && (int)DIST_EXPONENTIAL == (int)GB_DIST_EXPONENTIAL &&
               (int)DIST_LAPLACE == (int)GB_DIST_LAPLACE && (int)DIST_CAUCHY == (int)GB_DIST_CAUCHY &&
               (int)DIST_INV_GAMMA == (int)GB_DIST_INV_GAMMA && (int)DIST_BETA == (int)GB_DIST_BETA &&
@@ -359,15 +360,19 @@ static cudaError_t klaunch(void (*kern)(P...), unsigned grid, unsigned block, cu
 }
 
 static std::unordered_map<const void *, int> g_occ;
+static std::mutex g_occ_mu;
 template <typename F> static int grid_for(gb_pf *pf, F kernel, long long work_items, int block) {
   const void *key = (const void *)kernel;
-  auto it = g_occ.find(key);
   int occ;
-  if (it == g_occ.end()) {
-    occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) occ = 1;
-    g_occ[key] = occ;
-  } else occ = it->second;
+  {
+    std::lock_guard<std::mutex> lk(g_occ_mu);
+    auto it = g_occ.find(key);
+    if (it == g_occ.end()) {
+      occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) occ = 1;
+      g_occ[key] = occ;
+    } else occ = it->second;
+  }
   long long blocks = (work_items + block - 1) / block;
   long long cap = (long long)pf->num_sms * occ;
   if (blocks < 1) blocks = 1;
@@ -692,12 +697,15 @@ static int launch_spec(gb_pf *pf, const double *obs, int nobs, bool predrawn, in
     return GB_OK;
   }
   pf->spec_backend = 0;
-  if (g_spec_loaded != m.spec_id) {
+  int spec_dev = 0;
+  cudaGetDevice(&spec_dev);
+  spec_dev = spec_dev >= 0 && spec_dev < 64 ? spec_dev : 0;
+  if (g_spec_loaded[spec_dev] != m.spec_id) {
     CK(cudaMemcpyToSymbolAsync(c_spec_ops, m.ops.data(), m.ops.size() * sizeof(SpecOp), 0, cudaMemcpyHostToDevice, pf->stream));
     if (!m.spec_params.empty())
       CK(cudaMemcpyToSymbolAsync(c_spec_params, m.spec_params.data(), m.spec_params.size() * 8, 0, cudaMemcpyHostToDevice, pf->stream));
     CK(cudaStreamSynchronize(pf->stream));
-    g_spec_loaded = m.spec_id;
+    g_spec_loaded[spec_dev] = m.spec_id;
   }
 #define GO(PD, GA)                                                                         \
   {                                                                                        \
