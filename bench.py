@@ -56,12 +56,13 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.rows = []
+        self.windows = []
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -70,12 +71,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        """A timed region (host clock): only samples taken inside a region count."""
+        self.windows.append((t0, t1))
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -83,7 +87,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if self.windows and not any(a <= ts <= b for a, b in self.windows):
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -96,7 +102,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "nvidia-smi every 20 ms; samples inside the device-timed and the end-to-end timed regions"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -214,6 +221,8 @@ def run_genb200(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi needs a few 100 ms to come up: start it before the filter is built
     g = entry.load_package()
     from genb200 import _lib as L
     L.check(L.lib().gb_set_device(local_rank))
@@ -272,9 +281,8 @@ def run_genb200(args):
     #      8-byte observation argument and the 40-byte weight-statistics read maybe_resample! needs) ----
     state.enable_timing(True)
     state.get_timing()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    w0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     if world == 1:
@@ -286,7 +294,7 @@ def run_genb200(args):
         t += args.steps
     ev1.record()
     barrier()
-    clocks = sampler.stop()
+    sampler.window(w0, time.perf_counter())
     ms = ev0.elapsed_time(ev1)
     timing = state.get_timing()
     state.enable_timing(False)
@@ -304,6 +312,7 @@ def run_genb200(args):
             step(t, sync_scalar=True)
             t += 1
     barrier()
+    w0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     lml = None
@@ -316,6 +325,8 @@ def run_genb200(args):
         t += 1
     e1.record()
     barrier()
+    sampler.window(w0, time.perf_counter())
+    clocks = sampler.stop()
     ms_e2e = e0.elapsed_time(e1)
     if dist is not None:
         tt = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
