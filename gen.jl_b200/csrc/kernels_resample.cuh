@@ -666,10 +666,14 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
   for (int j = 0; j < kItems; j++) {
     const int a0 = (kstart > ilo ? kstart : ilo) - ilo, a1 = (kend[j] < ihi ? kend[j] : ihi) - ilo;
     const int id = threadIdx.x * kItems + j;
-    if (a1 - a0 > kHeavyCap) {
+    const int cnt_j = a1 - a0;
+    if (cnt_j > kHeavyCap) {
       sm.heavy[atomicAdd(&sm.nheavy, 1)] = make_int3(id, a0, a1);
     } else {
-      for (int k = a0; k < a1; k++) sm.slot[k] = id;
+      // 0, 1 or 2 offspring is the common case after regular resampling: two predicated stores, no loop
+      if (cnt_j > 0) sm.slot[a0] = id;
+      if (cnt_j > 1) sm.slot[a0 + 1] = id;
+      for (int k = a0 + 2; k < a1; k++) sm.slot[k] = id;
     }
     kstart = kend[j];
   }
