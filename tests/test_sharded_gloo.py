@@ -168,3 +168,42 @@ def test_plan_exchange_covers_every_slot_once():
         for d in range(world):                                  # every destination slot is received exactly once
             got = sum(send[s][d][1] - send[s][d][0] for s in range(world))
             assert got == counts[d]
+
+
+def test_plan_exchange_matches_oracle_ancestors_property(O):
+    """Property (hypothesis): for arbitrary weights, shard counts and u0, the slot ranges the host plan assigns to the
+    shards are exactly the runs of the oracle's global systematic ancestors that fall into each shard."""
+    from hypothesis import given, settings, strategies as st
+    import __graft_entry__ as entry
+    entry.load_package()
+    from genb200 import sharded
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 400), st.integers(1, 6), st.integers(0, 2 ** 32 - 1), st.integers(0, 2 ** 31),
+           st.sampled_from(["normal", "skewed", "equal", "onehot"]))
+    def check(n, world, u0, seed, shape):
+        world = min(world, n)
+        rng = np.random.default_rng(seed)
+        if shape == "normal":
+            lw = 3.0 * rng.standard_normal(n)
+        elif shape == "skewed":
+            lw = -rng.exponential(30.0, n)
+        elif shape == "equal":
+            lw = np.zeros(n)
+        else:
+            lw = np.full(n, -60.0)
+            lw[rng.integers(0, n)] = 0.0
+        counts, offs = sharded.shard_bounds(n, world)
+        q, total = O.quantized_weights(lw)
+        q_locals = [int(sum(int(v) for v in q[offs[r]:offs[r + 1]])) for r in range(world)]
+        assert sum(q_locals) == total
+        anc = O.resample(O.RESAMPLE_SYSTEMATIC, lw, u0=u0)
+        qt, pref, ranges, send = sharded.plan_exchange(q_locals, n, offs, u0)
+        owner = np.searchsorted(np.array(offs[1:]), anc, side="right")      # shard holding each slot's ancestor
+        for r in range(world):
+            lo, hi = ranges[r]
+            assert np.all(owner[lo:hi] == r) and np.count_nonzero(owner == r) == hi - lo
+            for d in range(world):                                            # and what r sends to d is d's part of it
+                a, b = send[r][d]
+                assert b - a == np.count_nonzero((owner == r) & (np.arange(n) >= offs[d]) & (np.arange(n) < offs[d + 1]))
+    check()
