@@ -1395,6 +1395,8 @@ extern "C" int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out) {
   c->step = pf->step;
   c->log_ml_est = pf->log_ml_est;
   c->wstate = pf->wstate;
+  *c->h_stats = *pf->h_stats;      // W_STATS: the host record describes the (copied) weights
+  c->incr_step = pf->incr_step;
   c->anc_valid = false;            // parents travel as the materialised int64 array
   size_t col = (size_t)pf->ld * pf->esz;
   cudaError_t e = cudaMemcpyAsync(c->state[c->cur], pf->state[pf->cur], col * pf->S, cudaMemcpyDeviceToDevice, pf->stream);

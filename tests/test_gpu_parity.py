@@ -486,6 +486,7 @@ def test_pf_state_copy_and_fields(g):
     assert np.array_equal(st.parents, np.arange(1, 1001)) and st.log_ml_est == 0.0
     c = st.copy()
     assert c == st and c is not st and hash(c) == hash(st)     # Base.copy / == / hash (particle_filter.jl:43-63)
+    assert g.log_ml_estimate(c) == g.log_ml_estimate(st) and c.ess() == st.ess()   # cached statistics travel with the copy
     g.particle_filter_step_(st, (1,), (g.UnknownChange,), 0.2)
     assert not (c == st) and hash(c) != hash(st)
     lw = np.linspace(-3, 0, 1000)
