@@ -233,15 +233,26 @@ function rejuvenate!(state::DeviceParticleFilterState, observations::ChoiceMap; 
     acc[]
 end
 
-# T x { maybe_resample!; particle_filter_step! } without a host round trip per step (gb_pf_run)
+# T x { maybe_resample!; particle_filter_step! [; sweeps x mh on the newest latents] } without a host round trip per step
+# (gb_pf_run / gb_pf_run_mh): the loops of docs/src/tutorials/smc.md:674-689 and :513-531 as one call.
+# Returns the number of resamples (and, with rejuvenation, the number of accepted moves).
 function particle_filter_run!(state::DeviceParticleFilterState, observations::Vector{<:ChoiceMap};
-                              ess_threshold::Real=state.num_particles / 2)
+                              ess_threshold::Real=state.num_particles / 2,
+                              move::Union{Symbol,Nothing}=nothing, drift_std::Real=0.0, sweeps::Int=1)
     obs = reduce(vcat, [flatten_obs(o) for o in observations])
     nres = Ref{Cint}(0)
     T = length(observations)
-    check(ccall((:gb_pf_run, libgenb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cdouble, Ref{Cint}),
-                state.handle, T, obs, div(length(obs), T), Float64(ess_threshold), nres))
-    nres[]
+    if move === nothing
+        check(ccall((:gb_pf_run, libgenb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cdouble, Ref{Cint}),
+                    state.handle, T, obs, div(length(obs), T), Float64(ess_threshold), nres))
+        return nres[]
+    end
+    nacc = Ref{Int64}(0)
+    check(ccall((:gb_pf_run_mh, libgenb200), Cint,
+                (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cdouble, Cint, Cdouble, Cint, Ref{Cint}, Ref{Int64}),
+                state.handle, T, obs, div(length(obs), T), Float64(ess_threshold), move == :drift ? 1 : 0, Float64(drift_std), sweeps,
+                nres, nacc))
+    (nres[], nacc[])
 end
 
 # ---- GB_MODEL_SPEC: a static-IR function of the supported class written out as SSA ops (include/genb200.h) ----
