@@ -686,6 +686,11 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
   if (nh) __syncthreads();
   // coalesced copy-out
   const int tile_base = (int)(tile * kTile);
+  if (lo >= ao.own_lo && hi <= ao.own_hi) {     // the usual case (always, on a single shard): every slot is this shard's own
+    int *__restrict__ dst = ao.own + (lo - ao.own_lo);
+    for (int i = threadIdx.x; i < cnt; i += kBlock) __stcs(dst + i, tile_base + sm.slot[i]);
+    return;
+  }
   for (int i = threadIdx.x; i < cnt; i += kBlock) {
     const long long k = lo + i;
     if (k >= ao.own_lo && k < ao.own_hi) __stcs(ao.own + (k - ao.own_lo), tile_base + sm.slot[i]);
