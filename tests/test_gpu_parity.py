@@ -974,6 +974,28 @@ def test_spec_model_other_builtin_distributions(g, spec_backend):
         g.spec_model(1, [], 1, bad)
 
 
+def test_importance_sampling_of_a_spec_model(g, spec_backend):
+    """importance_sampling (importance.jl:20-36) over a static-IR function given as a spec program: a conjugate
+    normal-normal model, so the log marginal likelihood is known in closed form; the same program as the built-in LGSSM
+    at t = 0 gives the same weights."""
+    m0, s0, r, y = 0.3, 1.2, 0.7, 0.9
+    gen = g.SpecProgram()
+    x = gen.sample_normal(gen.param(0), gen.param(1))
+    gen.observe_normal(gen.obs(0), x, gen.param(2))
+    gen.store(0, x)
+    spec = g.spec_model(1, [m0, s0, r], 1, gen)
+    n = 400000
+    tr, lnw, lml = g.importance_sampling(spec, (), y, n, seed=5)
+    tr2, lnw2, lml2 = g.importance_sampling(g.lgssm_model(m0=m0, s0=s0, a=0.9, q=0.5, r=r), (0,), y, n, seed=5)
+    assert abs(g.logsumexp(lnw)) < 1e-12                                          # test/inference/importance_sampling.jl:18-34
+    assert np.array_equal(tr.column(0), tr2.column(0)) and np.allclose(lnw, lnw2, rtol=1e-11, atol=1e-11)
+    exact = -0.5 * (math.log(2 * math.pi * (s0 * s0 + r * r)) + (y - m0) ** 2 / (s0 * s0 + r * r))
+    assert abs(lml - exact) < 0.01 and abs(lml - lml2) < 1e-11
+    w = np.exp(lnw)
+    post_mean = m0 + s0 * s0 / (s0 * s0 + r * r) * (y - m0)
+    assert abs((w * tr.column(0)).sum() - post_mean) < 0.01                      # self-normalised posterior mean
+
+
 def test_spec_model_custom_proposal(g, O, spec_backend):
     """A custom proposal written inside the spec (sample from q, observe the model density, subtract q's score) equals
     the built-in LGSSM + AffineNormalProposal and the oracle's weight algebra (trace_translators.jl:854)."""
