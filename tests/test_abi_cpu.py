@@ -67,6 +67,16 @@ def test_model_validation(g):
     assert m.state_dim == 4 and m.num_obs == 1 and m.num_normals(True) == 4 and m.num_normals(False) == 2
     h = g.hmm_model([0.5, 0.5], np.eye(2), np.eye(2))
     assert h.state_dim == 1 and h.num_uniforms(False) == 1
+    # argument checks come before any device work: maximum sizes and shard geometry are rejected with GB_EINVAL
+    for n_local, n_global, off in ((2 ** 31, 2 ** 31, 0), (0, 10, 0), (10, 5, 0), (6, 10, 5)):
+        with pytest.raises(g.GenB200Error) as ei:
+            g.create_particle_filter(m, n_local, n_global=n_global, pid_offset=off)
+        assert ei.value.code == L.EINVAL
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(g.GenB200Error) as ei:
+            g.create_particle_filter(m, 10, dtype="f64")
+        assert ei.value.code == L.ENOGPU                                 # ... and everything else needs the GPU
 
 
 def test_philox_matches_oracle_and_known_answer(g, O):
