@@ -299,6 +299,8 @@ struct gb_pf {
   uint64_t *cdf = nullptr;
   int *off_anc = nullptr;         // sharded: ancestors of the shard's offspring range
   long long off_cap = 0, off_lo = 0, off_hi = 0;
+  int *guide = nullptr;              // multinomial: guide table (systematic ancestors for u0 = 0)
+  uint64_t *tile_save = nullptr;     // multinomial: the tile totals while the guide sweep consumes them
   double *d_tab = nullptr, *d_ptab = nullptr;
   int ptab_cap = 0;
   cudaStream_t stream = 0;
@@ -387,7 +389,7 @@ static void pf_release(gb_pf *pf) {
   gb_host_free(pf->h_stats); gb_dev_free(pf->d_normals); gb_dev_free(pf->d_uniforms); gb_dev_free(pf->d_u64);
   gb_dev_free(pf->d_ctl); gb_host_free(pf->h_ctl); gb_dev_free(pf->d_shplan); gb_host_free(pf->h_shplan); gb_dev_free(pf->d_offs); gb_dev_free(pf->super_q); gb_dev_free(pf->super_excl); gb_dev_free(pf->oflow); gb_dev_free(pf->oflow_count);
   gb_dev_free(pf->tile_q); gb_dev_free(pf->tile_c); gb_dev_free(pf->tile_r); gb_dev_free(pf->tile_slot); gb_dev_free(pf->d_plan);
-  gb_dev_free(pf->lik);
+  gb_dev_free(pf->lik); gb_dev_free(pf->guide); gb_dev_free(pf->tile_save);
   gb_host_free(pf->h_plan); gb_dev_free(pf->cdf); gb_dev_free(pf->off_anc); gb_dev_free(pf->d_tab); gb_dev_free(pf->d_ptab);
   for (auto p : pf->ipc_opened) cudaIpcCloseMemHandle(p);
   for (auto p : pf->hist_state) gb_dev_free(p);
@@ -1504,11 +1506,19 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
     if (!pf->cdf) CK(gb_dev_alloc((void **)&pf->cdf, (size_t)pf->ld * 8));
     if (!pf->tiles_valid && (rc = run_wstats(pf, logw, m, false))) return rc;
     pf->tiles_valid = false;   // tile_q becomes its exclusive prefix
+    // guide table first: the systematic sweep for u0 = 0 consumes (and zeroes) the tile totals, so they are parked meanwhile
+    if (!pf->guide) CK(gb_dev_alloc((void **)&pf->guide, (size_t)pf->ld * 4));
+    if (!pf->tile_save) CK(gb_dev_alloc((void **)&pf->tile_save, (size_t)(pf->ntiles + 1) * 8));
+    CK(cudaMemcpyAsync(pf->tile_save, pf->tile_q, (size_t)(pf->ntiles + 1) * 8, cudaMemcpyDeviceToDevice, pf->stream));
+    if ((rc = launch_systematic<R>(pf, logw, m, 0, 0, 0u, AncOut{pf->guide, 0, pf->n_global, nullptr, 0, 0}))) return rc;
+    CK(cudaMemcpyAsync(pf->tile_q, pf->tile_save, (size_t)(pf->ntiles + 1) * 8, cudaMemcpyDeviceToDevice, pf->stream));
+    pf->ws_clean = false;
+    pf->tiles_valid = false;
     if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, u0, 1))) return rc;
     if ((rc = launch_ancestors<R, SWEEP_CDF>(pf, logw, m, bits, 0, 0, anc, 0))) return rc;
-    int grid = grid_for(pf, multinomial_kernel, pf->n, kBlock);
-    LAUNCH(pf, GB_K_ANCESTORS, multinomial_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->cdf, pf->tile_q, pf->ntiles, pf->n, pf->d_plan,
-                                                                                   d_u64, seed, step, pf->n, anc, (unsigned)PK_MULTI));
+    int grid = grid_for(pf, multinomial_guided_kernel, pf->n, kBlock);
+    LAUNCH(pf, GB_K_ANCESTORS, multinomial_guided_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->cdf, pf->guide, pf->n, pf->d_plan, d_u64, seed,
+                                                                                          step, pf->n, anc, (unsigned)PK_MULTI));
     CK(cudaGetLastError());
     return GB_OK;
   }
