@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -103,7 +103,7 @@ class ClockSampler:
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "window": "nvidia-smi every 20 ms; samples inside the device-timed and the end-to-end timed regions"}
+                "window": "nvidia-smi every 10 ms; samples inside the device-timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -295,6 +295,7 @@ def run_genb200(args):
     ev1.record()
     barrier()
     sampler.window(w0, time.perf_counter())
+    clocks = sampler.stop()              # (before the end-to-end loop: polling nvidia-smi perturbs its host round trips)
     ms = ev0.elapsed_time(ev1)
     timing = state.get_timing()
     state.enable_timing(False)
@@ -312,7 +313,6 @@ def run_genb200(args):
             step(t, sync_scalar=True)
             t += 1
     barrier()
-    w0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     lml = None
@@ -325,8 +325,6 @@ def run_genb200(args):
         t += 1
     e1.record()
     barrier()
-    sampler.window(w0, time.perf_counter())
-    clocks = sampler.stop()
     ms_e2e = e0.elapsed_time(e1)
     if dist is not None:
         tt = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
