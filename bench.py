@@ -73,6 +73,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
+    def wait_ready(self, timeout=3.0):
+        """nvidia-smi takes 0.1-0.5 s to print its first row: the timed region starts only once it is sampling."""
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.005)
+
     def window(self, t0, t1):
         """A timed region (host clock): only samples taken inside a region count."""
         self.windows.append((t0, t1))
@@ -281,6 +287,7 @@ def run_genb200(args):
     #      8-byte observation argument and the 40-byte weight-statistics read maybe_resample! needs) ----
     state.enable_timing(True)
     state.get_timing()
+    sampler.wait_ready()
     barrier()
     w0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
