@@ -239,3 +239,56 @@ def test_resampler_statistics(O):
     cnt = np.bincount(anc, minlength=n)
     assert np.all(np.abs(cnt - n * w) < 1.0 + 1e-6)
     assert np.all(np.diff(anc) >= 0)
+
+
+def test_guide_table_bracket_contains_every_multinomial_draw():
+    """The argument behind the guided multinomial kernel (csrc/kernels_resample.cuh), checked on the CPU with exact integers:
+    with guide[j] = smallest i with cdf[i] > floor(j Q / N), a draw tau in [0, Q) whose cell estimate j is anywhere in
+    {J-2, J-1, J} (J = floor(tau N / Q); the device gets j from a double product minus one) has its ancestor -- the
+    smallest i with cdf[i] > tau -- inside [guide[j], guide[min(j + 3, N - 1)] or N - 1]."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 300), st.integers(0, 2 ** 31), st.sampled_from(["uniform", "sparse", "tiny", "onehot"]))
+    def check(n, seed, shape):
+        rng = np.random.default_rng(seed)
+        if shape == "uniform":
+            q = rng.integers(0, 2 ** 40, size=n)
+        elif shape == "sparse":
+            q = rng.integers(0, 2 ** 40, size=n) * (rng.random(n) < 0.1)
+        elif shape == "tiny":
+            q = rng.integers(0, 4, size=n)
+            q[rng.integers(0, n)] += 2 ** 45
+        else:
+            q = np.zeros(n, dtype=np.int64)
+            q[rng.integers(0, n)] = 2 ** 50
+        q = [int(v) for v in q]
+        Q = sum(q)
+        if Q == 0:
+            return
+        cdf, c = [], 0
+        for v in q:
+            c += v
+            cdf.append(c)
+        cdf_np = np.array(cdf, dtype=object)
+
+        def first_above(t):                       # smallest i with cdf[i] > t
+            lo, hi = 0, n - 1
+            while lo < hi:
+                mid = (lo + hi) // 2
+                if cdf[mid] > t:
+                    hi = mid
+                else:
+                    lo = mid + 1
+            return lo
+        guide = [first_above((j * Q) // n) for j in range(n)]
+        taus = [int(t) for t in rng.integers(0, min(Q, 2 ** 62), size=40)] + [0, Q - 1]
+        for tau in taus:
+            ans = first_above(tau)
+            J = (tau * n) // Q
+            for j in (J - 2, J - 1, J):
+                j = min(max(j, 0), n - 1)
+                a = guide[j]
+                b = guide[j + 3] if j + 3 < n else n - 1
+                assert a <= ans <= b, (n, tau, j, a, ans, b)
+    check()
