@@ -84,12 +84,42 @@ SIGNATURES = {
     "gb_pf_async_attach_ipc": (i, [vp, i, vp]),
     "gb_pf_async_attach_local": (i, [vp, i, vp]),
     "gb_pf_async_setup": (i, [vp, i, i, i64p, d]),
+    "gb_pf_async_arm": (i, [vp, d]),
     "gb_pf_async_cur": (i, [vp, ip]),
-    "gb_pf_async_plan": (i, [vp, vp, u32]),
+    "gb_pf_xchg_post": (i, [vp]),
+    "gb_pf_xchg_stats": (i, [vp]),
+    "gb_pf_async_plan": (i, [vp, u32, d, i]),
     "gb_pf_async_sweep": (i, [vp]),
     "gb_pf_async_export": (i, [vp]),
+    "gb_pf_async_wait": (i, [vp]),
     "gb_pf_async_step": (i, [vp, dp, i]),
+    "gb_pf_async_iterate": (i, [vp, dp, i]),
     "gb_pf_async_finish": (i, [vp, ip, ip]),
+    "gb_pf_xchg_read": (i, [vp, dp, dp, u64p, ip]),
+    "gb_pf_xchg_records": (i, [vp, dp, u64p]),
+    "gb_pf_xchg_commit": (i, [vp, ip, dp]),
+    "gb_spf_create": (i, [vp, i64, i, u64, i, ip, vpp]),
+    "gb_spf_generate": (i, [vp, dp, i, i, dp, i]),
+    "gb_spf_initialize": (i, [vp, i64, i, u64, i, ip, dp, i, i, dp, i, vpp]),
+    "gb_spf_step": (i, [vp, dp, i, i, dp, i]),
+    "gb_spf_maybe_resample": (i, [vp, d, ip]),
+    "gb_spf_set_resample_noise": (i, [vp, i, u32]),
+    "gb_spf_run": (i, [vp, i, dp, i, d, ip]),
+    "gb_spf_log_ml_estimate": (i, [vp, dp]),
+    "gb_spf_get_log_ml_est": (i, [vp, dp]),
+    "gb_spf_get_ess": (i, [vp, dp, dp]),
+    "gb_spf_get_log_weights": (i, [vp, dp]),
+    "gb_spf_get_log_increments": (i, [vp, dp]),
+    "gb_spf_get_state": (i, [vp, i, dp]),
+    "gb_spf_get_parents": (i, [vp, i64p]),
+    "gb_spf_num_shards": (i, [vp, ip]),
+    "gb_spf_shard": (i, [vp, i, vpp, i64p]),
+    "gb_spf_num_particles": (i, [vp, i64p]),
+    "gb_spf_step_index": (i, [vp, ip]),
+    "gb_spf_sync": (i, [vp]),
+    "gb_spf_free": (None, [vp]),
+    "gb_spf_importance_sampling": (i, [vp, i64, i, u64, i, ip, dp, i, i, dp, i, dp, dp, vpp]),
+    "gb_spf_resample": (i, [dp, i64, i, i, ip, u32, i64p]),
     "gb_pf_systematic_offspring": (i, [vp, d, i, u64, u64, u64, u32, i64p, i64p]),
     "gb_pf_block_bytes": (i64, [vp, i64]),
     "gb_pf_ext_capacity": (i, [vp, i64p]),

@@ -271,6 +271,11 @@ struct gb_pf {
   std::vector<int *> hist_anc;      // [t] -> ancestors applied BEFORE step t (nullptr: no resample)
   RunCtl *d_ctl = nullptr, *h_ctl = nullptr;   // fused multi-step run (gb_pf_run) / asynchronous sharded run
   ShardPlanDev *d_shplan = nullptr, *h_shplan = nullptr;
+  XchgMail *mail = nullptr;         // this shard's mailbox of the peer-memory exchange (kernels_step.cuh), written by peers
+  XchgCtl *d_xc = nullptr, *h_xc = nullptr;
+  bool xc_on = false;               // d_stats->xc is attached: every publish_max posts this shard's max to its peers
+  bool max_posted = false;          // ... and the max of the CURRENT weights has been posted
+  int device = 0;                   // the CUDA device that owns every buffer of this handle
   std::vector<void *> ipc_opened;   // peer allocations mapped through CUDA IPC (closed with the handle)
   long long *d_offs = nullptr;
   int a_world = 0, a_rank = 0;
@@ -381,9 +386,19 @@ template <typename F> static int grid_for(gb_pf *pf, F kernel, long long work_it
   return (int)std::min(blocks, cap);
 }
 
+struct DeviceScope {      // make `dev` current for the scope (handles of a multi-GPU filter live on different devices)
+  int prev = -1;
+  explicit DeviceScope(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
 static void pf_release(gb_pf *pf) {
   if (!pf) return;
+  DeviceScope ds__(pf->device);
   FreeBatch fb__;
+  gb_dev_free(pf->mail); gb_dev_free(pf->d_xc); gb_host_free(pf->h_xc);
   gb_dev_free(pf->state[0]); gb_dev_free(pf->state[1]); gb_dev_free(pf->logw); gb_dev_free(pf->incr); gb_dev_free(pf->anc);
   gb_dev_free(pf->parents64); gb_dev_free(pf->ext_parents); gb_dev_free(pf->partials); gb_dev_free(pf->ticket); gb_dev_free(pf->d_stats);
   gb_host_free(pf->h_stats); gb_dev_free(pf->d_normals); gb_dev_free(pf->d_uniforms); gb_dev_free(pf->d_u64);
@@ -437,6 +452,7 @@ extern "C" int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_glob
   pf->ntiles = pf->n_pad / kTile;
   int dev = 0;
   cudaGetDevice(&dev);
+  pf->device = dev;
   cudaDeviceGetAttribute(&pf->num_sms, cudaDevAttrMultiProcessorCount, dev);
   auto A = [&](void **p, size_t bytes, bool zero) -> cudaError_t {
     cudaError_t e = gb_dev_alloc(p, bytes);
@@ -855,6 +871,7 @@ extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, 
   if (rc) return rc;
   pf->cur ^= 1;
   pf->wstate = W_MAX;
+  pf->max_posted = pf->xc_on;
   pf->tiles_valid = false;
   pf->nn_set = pf->nu_set = 0;
   pf->mh_ok = pf->model.kind != MODEL_BLR; pf->mh_parent_anc = false; pf->mh_moves = 0; pf->lik_step = -1;
@@ -893,6 +910,7 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
   pf->cur ^= 1;                       // particle_filter.jl:203-205, :234-237 (swap traces/new_traces)
   pf->pending_gather = false;
   pf->wstate = W_MAX;
+  pf->max_posted = pf->xc_on;
   pf->tiles_valid = false;
   pf->nn_set = pf->nu_set = 0;
   pf->mh_ok = true; pf->mh_parent_anc = gather; pf->mh_moves = 0;
@@ -1124,12 +1142,13 @@ static int ensure_max(gb_pf *pf, const void *logw) {
   }
   CK(cudaGetLastError());
   pf->wstate = W_MAX;
+  pf->max_posted = pf->xc_on;
   return GB_OK;
 }
 // one pass over the log weights: (s1, s2) w.r.t. the reference max + quantised tile / super-tile totals;
 // the reference max is read from d_stats->m (from_device) or passed by value (sharded: global max)
 static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_device, bool sync_host = true, RunCtl *ctl = nullptr,
-                      const FusedPlan *fused = nullptr) {
+                      const FusedPlan *fused = nullptr, bool exchange = false) {
   FusedPlan fp;
   memset(&fp, 0, sizeof(fp));
   if (fused) fp = *fused;
@@ -1142,17 +1161,17 @@ static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_devic
   if (pf->dtype == GB_F64) {
     auto kern = wstats_kernel<double>;
     int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
-    LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const double *)logw, pf->n, m_arg, from_device ? 1 : 0, bits,
+    LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const double *)logw, pf->n, m_arg, exchange ? 2 : (from_device ? 1 : 0), bits,
                                       (unsigned long long *)pf->tile_q, pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl, fp));
   } else {
     auto kern = wstats_kernel<float>;
     int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
-    LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const float *)logw, pf->n, m_arg, from_device ? 1 : 0, bits,
+    LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const float *)logw, pf->n, m_arg, exchange ? 2 : (from_device ? 1 : 0), bits,
                                       (unsigned long long *)pf->tile_q, pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl, fp));
   }
   CK(cudaGetLastError());
   if (sync_host) {
-    CK(cudaMemcpyAsync(pf->h_stats, pf->d_stats, sizeof(WeightStats), cudaMemcpyDeviceToHost, pf->stream));
+    CK(cudaMemcpyAsync(pf->h_stats, pf->d_stats, kStatsRecordBytes, cudaMemcpyDeviceToHost, pf->stream));
     CK(cudaStreamSynchronize(pf->stream));
   } else if (pf->wstate != W_ZERO) {
     pf->wstate = W_MAX;        // the host copy no longer describes the weights; the device max does
@@ -1192,7 +1211,7 @@ extern "C" int gb_pf_weight_max(gb_pf_t *pf, double *m_local) {
 extern "C" int gb_pf_stats_device(gb_pf_t *pf, void **dev_stats, int *n_words) {
   REQ(pf && dev_stats, "null argument");
   *dev_stats = pf->d_stats;
-  if (n_words) *n_words = (int)(sizeof(WeightStats) / 8);
+  if (n_words) *n_words = kStatsRecordBytes / 8;
   return GB_OK;
 }
 extern "C" int gb_pf_weight_max_device(gb_pf_t *pf) {
@@ -1349,6 +1368,7 @@ extern "C" int gb_pf_set_log_weights(gb_pf_t *pf, const double *in) {
   }
   CK(cudaStreamSynchronize(pf->stream));
   pf->wstate = W_DIRTY;
+  pf->max_posted = false;
   pf->tiles_valid = false;
   return GB_OK;
 }
@@ -1405,7 +1425,7 @@ extern "C" int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out) {
   if (e == cudaSuccess) e = cudaMemcpyAsync(c->logw, pf->logw, col, cudaMemcpyDeviceToDevice, pf->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(c->incr, pf->incr, col, cudaMemcpyDeviceToDevice, pf->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(c->anc, pf->anc, (size_t)pf->ld * 4, cudaMemcpyDeviceToDevice, pf->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_stats, pf->d_stats, sizeof(WeightStats), cudaMemcpyDeviceToDevice, pf->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_stats, pf->d_stats, kStatsRecordBytes, cudaMemcpyDeviceToDevice, pf->stream);
   if (e == cudaSuccess && pf->parents64_valid) {
     e = gb_dev_alloc((void **)&c->parents64, (size_t)pf->ld * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->parents64, pf->parents64, (size_t)pf->ld * 8, cudaMemcpyDeviceToDevice, pf->stream);
@@ -1675,29 +1695,43 @@ static int pf_run_impl(gb_pf *pf, int T, const double *obs, int nobs, double ess
   CK(cudaMemcpyAsync(pf->d_ctl, pf->h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pf->stream));
   CK(cudaStreamSynchronize(pf->stream));                // h_ctl is reused for the read-back below
   if (sweeps == 0 && small_run_eligible(pf, T)) return small_run(pf, T, obs, nobs, n_resampled);
-  unsigned long long *d_acc = nullptr;
   if (sweeps > 0) {
     const int kind = pf->model.kind;
     REQ(move == MH_RESIMULATE || move == MH_DRIFT, "gb_pf_run_mh: unknown move");
     if (!(kind == MODEL_LGSSM || kind == MODEL_SV || kind == MODEL_BEARINGS || kind == MODEL_HMM) || (move == MH_DRIFT && kind == MODEL_HMM))
       return fail(GB_EUNSUPPORTED, "gb_pf_run_mh: this model kind does not have this MH rejuvenation move");
     REQ(move != MH_DRIFT || drift_std > 0.0, "gb_pf_run_mh: drift_std must be positive");
+  }
+  // every step's arguments are checked BEFORE the first launch (as the single-CTA path does): a bad observation at step t > 0
+  // must not leave the handle half way through the run
+  if (pf->model.kind == MODEL_SPEC) {
+    REQ(pf->model.n_step_ops > 0, "this SPEC model has no step program");
+  } else {
+    ModelParams mp_check;
+    for (int t = 0; t < T; t++)
+      if ((rc = fill_model_params(pf, mp_check, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false))) return rc;
+  }
+  unsigned long long *d_acc = nullptr;
+  if (sweeps > 0) {
     CK(gb_dev_alloc((void **)&d_acc, 8));
-    CK(cudaMemsetAsync(d_acc, 0, 8, pf->stream));
+    cudaError_t me = cudaMemsetAsync(d_acc, 0, 8, pf->stream);
+    if (me != cudaSuccess) { gb_dev_free(d_acc); return fail(GB_ECUDA, std::string("gb_pf_run_mh: ") + cudaGetErrorString(me)); }
   }
   const AncOut ao{pf->anc, 0, pf->n_global, nullptr, 0, 0};
-  for (int t = 0; t < T; t++) {
+  int done = 0;          // steps fully enqueued
+  for (int t = 0; t < T && !rc; t++) {
     // maybe_resample!: statistics + decision on the device, then the (conditional) systematic sweep
     const uint32_t u0 = philox_block(pf->seed, 0, (uint32_t)pf->step, PK_RESAMPLE, 0).x;
     const FusedPlan fp{pf->d_plan, pf->super_excl, pf->oflow_count, pf->n_global, u0};
-    if ((rc = run_wstats(pf, pf->logw, 0.0, true, false, pf->d_ctl, &fp))) return rc;
+    if ((rc = run_wstats(pf, pf->logw, 0.0, true, false, pf->d_ctl, &fp))) break;
     rc = pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, 0.0, 0, 0, u0, ao, pf->d_ctl, 0, true)
                              : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, u0, ao, pf->d_ctl, 0, true);
-    if (rc) return rc;
+    if (rc) break;
     // particle_filter_step!
     if ((rc = launch_model(pf, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false, false, 2))) break;
     pf->step += 1;
     pf->cur ^= 1;
+    done = t + 1;
     // rejuvenation of the traces just extended (docs/src/tutorials/smc.md:459-463, :518-520): their parents are the
     // buffer the step read from, through `anc` iff the device decided to resample in this iteration
     for (int sw = 0; sw < sweeps && !rc; sw++) {
@@ -1713,19 +1747,25 @@ static int pf_run_impl(gb_pf *pf, int T, const double *obs, int nobs, double ess
       a.accepted = d_acc;
       rc = pf->dtype == GB_F64 ? launch_mh_k<double, false>(pf, a, move, false) : launch_mh_k<float, false>(pf, a, move, false);
     }
-    if (rc) break;
   }
+  // Read the control block back and bring the host-side bookkeeping in line with whatever WAS enqueued -- also when a
+  // launch failed part of the way (the device has run `done` complete steps and possibly the resampling half of one more)
   unsigned long long acc = 0;
   cudaError_t ce = cudaMemcpyAsync(pf->h_ctl, pf->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, pf->stream);
   if (ce == cudaSuccess && d_acc) ce = cudaMemcpyAsync(&acc, d_acc, 8, cudaMemcpyDeviceToHost, pf->stream);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(pf->stream);
   gb_dev_free(d_acc);
+  if (ce == cudaSuccess && (done > 0 || rc)) {
+    // (a launch that failed after validation is a CUDA error, i.e. fatal for the context; the cached statistics are dropped)
+    pf->wstate = rc ? W_DIRTY : W_MAX;
+    pf->tiles_valid = false; pf->ws_clean = false; pf->pending_gather = false;
+    if (done > 0) pf->incr_step = pf->step;
+    if (pf->h_ctl->n_resampled > 0) { pf->anc_valid = true; pf->parents64_valid = false; pf->ext_used = false; }
+    pf->log_ml_est = pf->h_ctl->log_ml_est;
+  }
   if (rc) return rc;
   if (ce != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_run: ") + cudaGetErrorString(ce));
   if (n_accepted) *n_accepted = (int64_t)acc;
-  pf->log_ml_est = pf->h_ctl->log_ml_est;
-  if (pf->h_ctl->n_resampled > 0) { pf->anc_valid = true; pf->parents64_valid = false; pf->ext_used = false; }
-  if (T > 0) { pf->wstate = W_MAX; pf->tiles_valid = false; pf->pending_gather = false; }
   if (n_resampled) *n_resampled = pf->h_ctl->n_resampled;
   return GB_OK;
 }
@@ -1780,22 +1820,7 @@ extern "C" int gb_pf_systematic_offspring(gb_pf_t *pf, double m_global, int bits
 // ---- asynchronous sharded run: the exchange plan, the resample decision and the log-ML live on the device; offspring
 //      owned by other shards are written straight into their memory (CUDA IPC peer pointers over NVLink); the host only
 //      enqueues (the collectives in between are issued by gen.jl_b200/sharded.py on the same stream) ----
-struct IpcBundle { cudaIpcMemHandle_t h[4]; long long ld, n_pad, ext_cap; };
-extern "C" int gb_pf_ipc_export(gb_pf_t *pf, void *bundle_out, int *nbytes) {
-  REQ(pf && bundle_out && nbytes, "null argument");
-  REQ(pf->ext_parents, "gb_pf_ipc_export: not a sharded filter (n_local == n_global)");
-  IpcBundle b;
-  memset(&b, 0, sizeof(b));
-  CK(cudaIpcGetMemHandle(&b.h[0], pf->state[0]));
-  CK(cudaIpcGetMemHandle(&b.h[1], pf->state[1]));
-  CK(cudaIpcGetMemHandle(&b.h[2], pf->anc));
-  CK(cudaIpcGetMemHandle(&b.h[3], pf->ext_parents));
-  b.ld = pf->ld; b.n_pad = pf->n_pad; b.ext_cap = pf->ext_cap;
-  memcpy(bundle_out, &b, sizeof(b));
-  *nbytes = (int)sizeof(b);
-  return GB_OK;
-}
-extern "C" int gb_pf_ipc_bundle_bytes(void) { return (int)sizeof(IpcBundle); }
+struct IpcBundle { cudaIpcMemHandle_t h[5]; long long ld, n_pad, ext_cap; };
 static int ensure_async_alloc(gb_pf *pf) {
   if (!pf->d_ctl) {
     CK(gb_dev_alloc((void **)&pf->d_ctl, sizeof(RunCtl)));
@@ -1807,55 +1832,110 @@ static int ensure_async_alloc(gb_pf *pf) {
     memset(pf->h_shplan, 0, sizeof(ShardPlanDev));
     CK(gb_dev_alloc((void **)&pf->d_offs, sizeof(long long) * (kMaxWorld + 1)));
   }
+  if (!pf->mail) {
+    CK(gb_dev_alloc((void **)&pf->mail, sizeof(XchgMail)));
+    CK(cudaMemset(pf->mail, 0, sizeof(XchgMail)));
+    CK(gb_dev_alloc((void **)&pf->d_xc, sizeof(XchgCtl)));
+    CK(gb_host_alloc((void **)&pf->h_xc, sizeof(XchgCtl)));
+    memset(pf->h_xc, 0, sizeof(XchgCtl));
+  }
   return GB_OK;
 }
+extern "C" int gb_pf_ipc_export(gb_pf_t *pf, void *bundle_out, int *nbytes) {
+  REQ(pf && bundle_out && nbytes, "null argument");
+  REQ(pf->ext_parents, "gb_pf_ipc_export: not a sharded filter (n_local == n_global)");
+  DeviceScope ds__(pf->device);
+  int rc = ensure_async_alloc(pf);
+  if (rc) return rc;
+  IpcBundle b;
+  memset(&b, 0, sizeof(b));
+  CK(cudaIpcGetMemHandle(&b.h[0], pf->state[0]));
+  CK(cudaIpcGetMemHandle(&b.h[1], pf->state[1]));
+  CK(cudaIpcGetMemHandle(&b.h[2], pf->anc));
+  CK(cudaIpcGetMemHandle(&b.h[3], pf->ext_parents));
+  CK(cudaIpcGetMemHandle(&b.h[4], pf->mail));
+  b.ld = pf->ld; b.n_pad = pf->n_pad; b.ext_cap = pf->ext_cap;
+  memcpy(bundle_out, &b, sizeof(b));
+  *nbytes = (int)sizeof(b);
+  return GB_OK;
+}
+extern "C" int gb_pf_ipc_bundle_bytes(void) { return (int)sizeof(IpcBundle); }
 // peer in ANOTHER process: open its IPC bundle
 extern "C" int gb_pf_async_attach_ipc(gb_pf_t *pf, int peer_rank, const void *bundle) {
   REQ(pf && bundle && peer_rank >= 0 && peer_rank < kMaxWorld, "gb_pf_async_attach_ipc: bad argument");
+  DeviceScope ds__(pf->device);
   int rc = ensure_async_alloc(pf);
   if (rc) return rc;
   IpcBundle b;
   memcpy(&b, bundle, sizeof(b));
   PeerMem &pm = pf->h_shplan->peer[peer_rank];
-  void *p[4] = {nullptr, nullptr, nullptr, nullptr};
-  for (int k = 0; k < 4; k++) {
+  void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int k = 0; k < 5; k++) {
     CK(cudaIpcOpenMemHandle(&p[k], b.h[k], cudaIpcMemLazyEnablePeerAccess));
     pf->ipc_opened.push_back(p[k]);
   }
   pm.state[0] = p[0]; pm.state[1] = p[1]; pm.anc = (int *)p[2]; pm.ext_parents = (long long *)p[3];
   pm.ld = b.ld; pm.n_pad = b.n_pad; pm.ext_cap = b.ext_cap;
+  pf->h_xc->peer[peer_rank] = (XchgMail *)p[4];
   return GB_OK;
 }
-// peer in THIS process (several shards on one GPU: tests)
+// peer in THIS process (another device with peer access enabled, or the same device)
 extern "C" int gb_pf_async_attach_local(gb_pf_t *pf, int peer_rank, gb_pf_t *peer) {
   REQ(pf && peer && peer_rank >= 0 && peer_rank < kMaxWorld, "gb_pf_async_attach_local: bad argument");
-  int rc = ensure_async_alloc(pf);
-  if (rc) return rc;
+  int rc;
+  { DeviceScope ds__(pf->device); if ((rc = ensure_async_alloc(pf))) return rc; }
+  { DeviceScope ds__(peer->device); if ((rc = ensure_async_alloc(peer))) return rc; }
+  if (peer->device != pf->device) {
+    DeviceScope ds__(pf->device);
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, pf->device, peer->device));
+    if (!can) return fail(GB_EUNSUPPORTED, "gb_pf_async_attach_local: no peer access between the two devices");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e);
+    cudaGetLastError();
+  }
   PeerMem &pm = pf->h_shplan->peer[peer_rank];
   pm.state[0] = peer->state[0]; pm.state[1] = peer->state[1]; pm.anc = peer->anc; pm.ext_parents = peer->ext_parents;
   pm.ld = peer->ld; pm.n_pad = peer->n_pad; pm.ext_cap = peer->ext_cap;
+  pf->h_xc->peer[peer_rank] = peer->mail;
   return GB_OK;
 }
+static long long xchg_timeout_cycles() {
+  const char *e = getenv("GENB200_XCHG_TIMEOUT_MS");
+  const double ms = e ? atof(e) : 20000.0;
+  return (long long)(ms * 1.9e6);       // ~1.9 GHz SM clock
+}
+// ONCE per filter, after every peer has been attached: shard geometry, the exchange control block and the mailbox.
+// Resets this shard's mailbox and post counters, so the caller must put a barrier ACROSS ALL SHARDS (device idle on every
+// shard) between this call and the first gb_pf_xchg_stats / gb_pf_async_iterate.
 extern "C" int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t *offs, double ess_threshold) {
   REQ(pf && offs, "null argument");
   REQ(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "gb_pf_async_setup: world size must be <= 64");
   REQ(offs[rank] == pf->pid_offset && offs[rank + 1] == pf->pid_offset + pf->n && offs[world] == pf->n_global,
       "gb_pf_async_setup: shard offsets do not match this shard");
+  DeviceScope ds__(pf->device);
   int rc = materialize_pending(pf);
   if (rc) return rc;
   if ((rc = ensure_async_alloc(pf))) return rc;
   for (int d = 0; d < world; d++)
-    if (d != rank) REQ(pf->h_shplan->peer[d].anc != nullptr, "gb_pf_async_setup: attach every peer first (gb_pf_async_attach_*)");
+    if (d != rank) REQ(pf->h_shplan->peer[d].anc != nullptr && pf->h_xc->peer[d] != nullptr,
+                       "gb_pf_async_setup: attach every peer first (gb_pf_async_attach_*)");
   // both trace buffers must be in lock step with the peers': cur parity is part of the protocol
   pf->h_shplan->world = world; pf->h_shplan->rank = rank; pf->h_shplan->overflow = 0;
   CK(cudaMemcpyAsync(pf->d_shplan, pf->h_shplan, sizeof(ShardPlanDev), cudaMemcpyHostToDevice, pf->stream));
   std::vector<long long> o(offs, offs + world + 1);
   CK(cudaMemcpyAsync(pf->d_offs, o.data(), sizeof(long long) * (world + 1), cudaMemcpyHostToDevice, pf->stream));
-  pf->h_ctl->do_resample = 0; pf->h_ctl->n_resampled = 0;
-  pf->h_ctl->log_ml_est = pf->log_ml_est;
-  pf->h_ctl->ess_threshold = ess_threshold;
-  pf->h_ctl->log_n = log((double)pf->n_global);
-  CK(cudaMemcpyAsync(pf->d_ctl, pf->h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pf->stream));
+  XchgCtl *xc = pf->h_xc;
+  xc->mine = pf->mail; xc->peer[rank] = pf->mail;
+  xc->world = world; xc->rank = rank;
+  xc->seq_a = xc->seq_b = xc->seq_c = 0;
+  xc->timeout_cycles = xchg_timeout_cycles();
+  xc->error = 0; xc->export_ticket = 0;
+  CK(cudaMemsetAsync(pf->mail, 0, sizeof(XchgMail), pf->stream));
+  CK(cudaMemcpyAsync(pf->d_xc, xc, sizeof(XchgCtl), cudaMemcpyHostToDevice, pf->stream));
+  CK(cudaMemcpyAsync(&pf->d_stats->xc, &pf->d_xc, sizeof(XchgCtl *), cudaMemcpyHostToDevice, pf->stream));
+  pf->xc_on = true;
+  pf->max_posted = false;
   // spill buffer: ancestors of the offspring that land outside this shard's own slot range
   const long long want = pf->n_pad + pf->n_pad / 4 + kTile;
   if (pf->off_cap < want) {
@@ -1866,35 +1946,104 @@ extern "C" int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t
   }
   CK(cudaStreamSynchronize(pf->stream));
   pf->a_world = world; pf->a_rank = rank;
+  return gb_pf_async_arm(pf, ess_threshold);
+}
+// per run / per synchronous maybe_resample!: the device-side control block takes over the host's log_ml_est and threshold
+extern "C" int gb_pf_async_arm(gb_pf_t *pf, double ess_threshold) {
+  REQ(pf && pf->a_world > 0, "gb_pf_async_arm: call gb_pf_async_setup first");
+  DeviceScope ds__(pf->device);
+  pf->h_ctl->do_resample = 0; pf->h_ctl->n_resampled = 0;
+  pf->h_ctl->log_ml_est = pf->log_ml_est;
+  pf->h_ctl->ess_threshold = ess_threshold;
+  pf->h_ctl->log_n = log((double)pf->n_global);
+  CK(cudaMemcpyAsync(pf->d_ctl, pf->h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));       // h_ctl is reused for the read-back
   return GB_OK;
 }
 extern "C" int gb_pf_async_cur(const gb_pf_t *pf, int *cur) { REQ(pf && cur, "null argument"); *cur = pf->cur; return GB_OK; }
-extern "C" int gb_pf_async_plan(gb_pf_t *pf, const void *dev_gathered, uint32_t u0) {
+// Phases A + B of the exchange for the current weights: (post this shard's max if the kernel that produced the weights did
+// not: gb_pf_xchg_post) -> statistics pass w.r.t. the GLOBAL max, whose last CTA posts (sum e, sum e^2, integer CDF mass) to
+// every shard.  A driver with several shards on ONE stream calls gb_pf_xchg_post for all of them first.
+extern "C" int gb_pf_xchg_post(gb_pf_t *pf) {
+  REQ(pf && pf->a_world > 0 && pf->xc_on, "gb_pf_xchg_post: call gb_pf_async_setup first");
+  DeviceScope ds__(pf->device);
+  int rc = materialize_pending(pf);
+  if (rc) return rc;
+  if (!pf->max_posted) {
+    if (pf->wstate == W_ZERO) {     // all log weights are exactly 0.0
+      CK(cudaMemsetAsync(&pf->d_stats->m, 0, sizeof(double), pf->stream));
+      LAUNCH(pf, GB_K_MISC, xchg_post_max_kernel<<<1, 32, 0, pf->stream>>>(pf->d_stats));
+      CK(cudaGetLastError());
+      pf->max_posted = true;
+    } else {                        // (d_stats->m may hold a previous GLOBAL max: recompute the shard's own)
+      pf->wstate = W_DIRTY;
+      if ((rc = ensure_max(pf, pf->logw))) return rc;
+    }
+  }
+  return GB_OK;
+}
+extern "C" int gb_pf_xchg_stats(gb_pf_t *pf) {
+  int rc = gb_pf_xchg_post(pf);
+  if (rc) return rc;
+  DeviceScope ds__(pf->device);
+  const int keep = pf->wstate;
+  rc = run_wstats(pf, pf->logw, 0.0, true, false, nullptr, nullptr, true);
+  pf->wstate = keep == W_ZERO ? W_ZERO : W_MAX;   // d_stats->m is now the global max: still a valid reference for this shard
+  return rc;
+}
+// ESS test + log-ML update + exchange plan on the device from the G records in this shard's mailbox.  ess_threshold NaN:
+// the armed threshold.  do_scan != 0 prepares the sweep that follows (consumes the super-tile totals).
+extern "C" int gb_pf_async_plan(gb_pf_t *pf, uint32_t u0, double ess_threshold, int do_scan) {
   if (pf) pf->mh_ok = false;
-  REQ(pf && dev_gathered && pf->a_world > 0, "gb_pf_async_plan: call gb_pf_async_setup first");
-  LAUNCH(pf, GB_K_TILESCAN, shard_plan_kernel<<<1, kMaxWorld, 0, pf->stream>>>((const long long *)dev_gathered, pf->d_offs, pf->a_world, pf->a_rank,
-                                                                              pf->n_global, u0, pf->off_cap, pf->d_ctl, pf->d_plan, pf->d_shplan));
+  REQ(pf && pf->a_world > 0 && pf->xc_on, "gb_pf_async_plan: call gb_pf_async_setup first");
+  REQ(!do_scan || pf->tiles_valid, "gb_pf_async_plan: statistics pass missing (gb_pf_xchg_stats)");
+  DeviceScope ds__(pf->device);
+  LAUNCH(pf, GB_K_TILESCAN, klaunch(shard_plan_kernel, 1, 1024, pf->stream, pf->d_stats, (const long long *)pf->d_offs, pf->n_global, u0, ess_threshold,
+                                    do_scan, pf->off_cap, pf->d_ctl, pf->d_plan, pf->d_shplan, pf->nsuper, pf->super_q, pf->super_excl,
+                                    pf->oflow_count));
   CK(cudaGetLastError());
   return GB_OK;
 }
 extern "C" int gb_pf_async_sweep(gb_pf_t *pf) {
   if (pf) pf->mh_ok = false;
   REQ(pf && pf->a_world > 0 && pf->tiles_valid, "gb_pf_async_sweep: statistics pass missing");
+  DeviceScope ds__(pf->device);
   const AncOut ao{pf->anc, pf->pid_offset, pf->pid_offset + pf->n, pf->off_anc, -1, pf->off_cap};
-  return pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1)
-                             : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1);
+  return pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1, true)
+                             : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1, true);
 }
-// offspring owned by other shards -> their memory (peer stores); the caller runs a barrier collective afterwards
+// offspring owned by other shards -> their memory (peer stores) + phase C post; gb_pf_async_wait orders them before the step
 extern "C" int gb_pf_async_export(gb_pf_t *pf) {
   REQ(pf && pf->a_world > 0, "gb_pf_async_export: bad argument");
   if (pf->a_world == 1) return GB_OK;
-  dim3 grid((unsigned)std::min<long long>(std::max<long long>(pf->n / (64 * kBlock), 1), 64), (unsigned)pf->a_world);
+  DeviceScope ds__(pf->device);
+  const unsigned gx = (unsigned)std::min<long long>(std::max<long long>(pf->n / (64 * kBlock), 1), 64);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(gx, (unsigned)pf->a_world, 1);
+  cfg.blockDim = dim3(kBlock, 1, 1);
+  cfg.stream = pf->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   if (pf->dtype == GB_F64)
-    LAUNCH(pf, GB_K_GATHER, export_p2p_kernel<double><<<grid, kBlock, 0, pf->stream>>>((const double *)pf->state[pf->cur], pf->ld, pf->S, pf->off_anc, pf->d_plan,
-                                                                                     pf->d_shplan, pf->d_ctl, pf->d_offs, pf->cur, pf->pid_offset, pf->off_cap));
+    LAUNCH(pf, GB_K_GATHER, cudaLaunchKernelEx(&cfg, export_p2p_kernel<double>, (const double *)pf->state[pf->cur], pf->ld, pf->S, (const int *)pf->off_anc,
+                                               (const ResamplePlan *)pf->d_plan, (const ShardPlanDev *)pf->d_shplan, (const RunCtl *)pf->d_ctl,
+                                               (const long long *)pf->d_offs, pf->cur, pf->pid_offset, pf->off_cap, pf->d_stats));
   else
-    LAUNCH(pf, GB_K_GATHER, export_p2p_kernel<float><<<grid, kBlock, 0, pf->stream>>>((const float *)pf->state[pf->cur], pf->ld, pf->S, pf->off_anc, pf->d_plan,
-                                                                                    pf->d_shplan, pf->d_ctl, pf->d_offs, pf->cur, pf->pid_offset, pf->off_cap));
+    LAUNCH(pf, GB_K_GATHER, cudaLaunchKernelEx(&cfg, export_p2p_kernel<float>, (const float *)pf->state[pf->cur], pf->ld, pf->S, (const int *)pf->off_anc,
+                                               (const ResamplePlan *)pf->d_plan, (const ShardPlanDev *)pf->d_shplan, (const RunCtl *)pf->d_ctl,
+                                               (const long long *)pf->d_offs, pf->cur, pf->pid_offset, pf->off_cap, pf->d_stats));
+  CK(cudaGetLastError());
+  return GB_OK;
+}
+extern "C" int gb_pf_async_wait(gb_pf_t *pf) {
+  REQ(pf && pf->a_world > 0, "gb_pf_async_wait: bad argument");
+  if (pf->a_world == 1) return GB_OK;
+  DeviceScope ds__(pf->device);
+  LAUNCH(pf, GB_K_MISC, klaunch(xchg_wait_kernel, 1, kMaxWorld, pf->stream, pf->d_stats, (const RunCtl *)pf->d_ctl));
   CK(cudaGetLastError());
   return GB_OK;
 }
@@ -1902,27 +2051,89 @@ extern "C" int gb_pf_async_step(gb_pf_t *pf, const double *obs, int nobs) {
   if (pf) pf->mh_ok = false;
   REQ(pf && obs && pf->a_world > 0, "gb_pf_async_step: bad argument");
   REQ(nobs == pf->model.nobs, "gb_pf_async_step: wrong number of observations");
+  DeviceScope ds__(pf->device);
   int rc = launch_model(pf, obs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false, false, 2);
   if (rc) return rc;
   pf->step += 1;
   pf->cur ^= 1;
   pf->wstate = W_MAX;
+  pf->max_posted = pf->xc_on;
   pf->tiles_valid = false;
+  pf->incr_step = pf->step;
+  return GB_OK;
+}
+// one whole iteration { maybe_resample!(armed threshold); particle_filter_step!(obs) } of ONE shard, nothing but enqueues
+extern "C" int gb_pf_async_iterate(gb_pf_t *pf, const double *obs, int nobs) {
+  REQ(pf && pf->a_world > 0, "gb_pf_async_iterate: call gb_pf_async_setup first");
+  const uint32_t u0 = philox_block(pf->seed, 0, (uint32_t)pf->step, PK_RESAMPLE, 0).x;
+  int rc = gb_pf_xchg_stats(pf);
+  if (!rc) rc = gb_pf_async_plan(pf, u0, NAN, 1);
+  if (!rc) rc = gb_pf_async_sweep(pf);
+  if (!rc) rc = gb_pf_async_export(pf);
+  if (!rc) rc = gb_pf_async_wait(pf);
+  if (!rc) rc = gb_pf_async_step(pf, obs, nobs);
+  return rc;
+}
+static int xchg_check(gb_pf *pf) {      // after a host sync: capacity overflow / exchange timeout flags
+  if (pf->h_shplan->overflow)
+    return fail(GB_ESTATE, "sharded resample: an exchange capacity was exceeded (weights too skewed for the extension rows); "
+                           "the filter state is invalid -- use the staged synchronous path");
+  if (pf->h_xc->error)
+    return fail(GB_ESTATE, "sharded resample: a peer did not answer within GENB200_XCHG_TIMEOUT_MS (shards out of lock step?)");
   return GB_OK;
 }
 extern "C" int gb_pf_async_finish(gb_pf_t *pf, int *n_resampled, int *overflow) {
   REQ(pf && pf->a_world > 0, "gb_pf_async_finish: bad argument");
+  DeviceScope ds__(pf->device);
   CK(cudaMemcpyAsync(pf->h_ctl, pf->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, pf->stream));
   CK(cudaMemcpyAsync(pf->h_shplan, pf->d_shplan, sizeof(ShardPlanDev), cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaMemcpyAsync(&pf->h_xc->error, &pf->d_xc->error, sizeof(int), cudaMemcpyDeviceToHost, pf->stream));
   CK(cudaStreamSynchronize(pf->stream));
   pf->log_ml_est = pf->h_ctl->log_ml_est;
-  if (pf->h_ctl->n_resampled > 0) { pf->anc_valid = true; pf->parents64_valid = false; pf->ext_used = true; }
+  if (pf->h_ctl->n_resampled > 0) { pf->anc_valid = true; pf->parents64_valid = false; pf->ext_used = pf->a_world > 1; }
   pf->pending_gather = false;
   if (n_resampled) *n_resampled = pf->h_ctl->n_resampled;
-  if (overflow) *overflow = pf->h_shplan->overflow;
-  if (pf->h_shplan->overflow)
-    return fail(GB_ESTATE, "asynchronous sharded run: an exchange capacity was exceeded (weights too skewed for the fixed-size "
-                           "blocks); the filter state is invalid -- rerun with the synchronous maybe_resample_ path");
+  if (overflow) *overflow = pf->h_shplan->overflow | (pf->h_xc->error << 1);
+  return xchg_check(pf);
+}
+// Global weight statistics {m, sum e, sum e^2, lse, ess, Q} over ALL shards as the last gb_pf_async_plan saw them, and its
+// decision; one device -> host read.
+extern "C" int gb_pf_xchg_read(gb_pf_t *pf, double *lse, double *ess, uint64_t *q_total, int *do_resample) {
+  REQ(pf && pf->a_world > 0, "gb_pf_xchg_read: bad argument");
+  DeviceScope ds__(pf->device);
+  CK(cudaMemcpyAsync(pf->h_ctl, pf->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaMemcpyAsync(pf->h_shplan, pf->d_shplan, sizeof(ShardPlanDev), cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaMemcpyAsync(&pf->h_xc->error, &pf->d_xc->error, sizeof(int), cudaMemcpyDeviceToHost, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));
+  if (lse) *lse = pf->h_shplan->global.lse;
+  if (ess) *ess = pf->h_shplan->global.ess;
+  if (q_total) *q_total = pf->h_shplan->global.q_total;
+  if (do_resample) *do_resample = pf->h_ctl->do_resample;
+  return xchg_check(pf);
+}
+// (no device access) the global max and every shard's integer CDF mass as of the last gb_pf_xchg_read
+extern "C" int gb_pf_xchg_records(gb_pf_t *pf, double *m_global, uint64_t *q_shard) {
+  REQ(pf && pf->a_world > 0 && pf->h_shplan, "gb_pf_xchg_records: bad argument");
+  if (m_global) *m_global = pf->h_shplan->global.m;
+  if (q_shard) for (int r = 0; r < pf->a_world; r++) q_shard[r] = pf->h_shplan->q_shard[r];
+  return GB_OK;
+}
+// Synchronous maybe_resample! over the exchange: after plan(threshold) -> sweep -> export -> wait, read the device's
+// decision and do the host-side bookkeeping of particle_filter.jl:263-272 (the gather stays deferred).
+extern "C" int gb_pf_xchg_commit(gb_pf_t *pf, int *did_resample, double *ess) {
+  REQ(pf && did_resample, "null argument");
+  int did = 0;
+  int rc = gb_pf_xchg_read(pf, nullptr, ess, nullptr, &did);
+  if (rc) return rc;
+  *did_resample = did;
+  if (!did) return GB_OK;
+  pf->log_ml_est = pf->h_ctl->log_ml_est;
+  pf->wstate = W_ZERO; pf->max_posted = false;
+  pf->tiles_valid = false;
+  pf->anc_valid = true; pf->parents64_valid = false;
+  pf->pending_gather = true;
+  pf->ext_used = pf->a_world > 1;
+  pf->mh_ok = false;
   return GB_OK;
 }
 
@@ -2113,15 +2324,17 @@ extern "C" int gb_importance_sampling(const gb_model_t *m, int64_t n, int dtype,
 struct RawWs {       // per-thread cached workspace: a gb_pf shell without particle columns
   gb_pf *pf = nullptr;
   long long n = 0;
-  int dtype = -1;
+  int dtype = -1, device = -1;
 };
 static thread_local RawWs g_raw;
 
 static int raw_workspace(long long n, int dtype, cudaStream_t stream, gb_pf **out) {
-  if (g_raw.pf && g_raw.n == n && g_raw.dtype == dtype) { g_raw.pf->stream = stream; *out = g_raw.pf; return GB_OK; }
-  if (g_raw.pf) { pf_release(g_raw.pf); g_raw.pf = nullptr; }
   int rc = require_gpu();
   if (rc) return rc;
+  int cur_dev = 0;
+  cudaGetDevice(&cur_dev);
+  if (g_raw.pf && g_raw.n == n && g_raw.dtype == dtype && g_raw.device == cur_dev) { g_raw.pf->stream = stream; *out = g_raw.pf; return GB_OK; }
+  if (g_raw.pf) { pf_release(g_raw.pf); g_raw.pf = nullptr; }
   REQ(n >= 1 && n < ((int64_t)1 << 31), "raw resampling: 1 <= n < 2^31");
   gb_pf *pf = new gb_pf;
   pf->dtype = dtype; pf->esz = dtype == GB_F64 ? 8 : 4;
@@ -2129,19 +2342,21 @@ static int raw_workspace(long long n, int dtype, cudaStream_t stream, gb_pf **ou
   pf->stream = stream;
   int dev = 0;
   cudaGetDevice(&dev);
+  pf->device = dev;
   cudaDeviceGetAttribute(&pf->num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaError_t e = gb_dev_alloc((void **)&pf->partials, sizeof(double2) * kMaxPartials);
   if (e == cudaSuccess) e = alloc_sys_workspace(pf);
   if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->ticket, 64);
   if (e == cudaSuccess) e = cudaMemset(pf->ticket, 0, 64);
   if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->d_stats, sizeof(WeightStats));
+  if (e == cudaSuccess) e = cudaMemset(pf->d_stats, 0, sizeof(WeightStats));     // (xc = nullptr: not a sharded filter)
   if (e == cudaSuccess) e = gb_host_alloc((void **)&pf->h_stats, sizeof(WeightStats));
   if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->tile_q, (size_t)(pf->ntiles + 1) * 8);
   if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->tile_slot, (size_t)(pf->ntiles + 1) * 8);
   if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->d_plan, sizeof(ResamplePlan));
   if (e == cudaSuccess) e = gb_host_alloc((void **)&pf->h_plan, sizeof(ResamplePlan));
   if (e != cudaSuccess) { pf_release(pf); return fail(GB_ECUDA, std::string("raw workspace: ") + cudaGetErrorString(e)); }
-  g_raw.pf = pf; g_raw.n = n; g_raw.dtype = dtype;
+  g_raw.pf = pf; g_raw.n = n; g_raw.dtype = dtype; g_raw.device = dev;
   *out = pf;
   return GB_OK;
 }
@@ -2485,3 +2700,16 @@ extern "C" int gb_dist_random(int dist, int dtype, int64_t n, const double *a, i
   REQ(a, "null argument");
   return dist_common(dist, dtype, n, nullptr, a, as, b, bs, len, true, seed, step, out);
 }
+
+// out[i] -= shift over a large host array (importance.jl:34,57 on the gathered log weights)
+static void host_shift(double *a, size_t n, double shift) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int T = (n < (1u << 18)) ? 1 : (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+  auto work = [=](int t) { for (size_t i = n * t / T, hi = n * (t + 1) / T; i < hi; i++) a[i] -= shift; };
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; t++) th.emplace_back(work, t);
+  work(0);
+  for (auto &x : th) x.join();
+}
+
+#include "spf.inc"

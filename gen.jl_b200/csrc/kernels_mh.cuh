@@ -38,65 +38,67 @@ struct MhArgs {
 
 template <typename R, int KIND, bool INIT, int MOVE, bool PREDRAWN>
 __global__ void __launch_bounds__(kBlock) mh_kernel(const MhArgs a) {
-  using Tr = Transition<R, KIND, PROPOSAL_DEFAULT, INIT>;
+  typedef typename Arith<R>::type A;     // storage R, arithmetic fp64 (models.cuh)
+  using Tr = Transition<A, KIND, PROPOSAL_DEFAULT, INIT>;
   constexpr int S = Tr::S, NN = MOVE == MH_DRIFT ? Tr::ND : Tr::NN, NU = MOVE == MH_DRIFT ? 0 : Tr::NU;
+  static_assert(NU <= 1, "mh_kernel draws at most one transition uniform (second word of the accept pair)");
   __shared__ double s_tab[kMathTabDoubles];
   const MathTables T = stage_math_tables(s_tab);
   __syncthreads();
-  const Hoisted<R> h = Tr::hoist(a.mp);
+  const Hoisted<A> h = Tr::hoist(a.mp);
   const R *__restrict__ par = static_cast<const R *>(a.parent);
   R *__restrict__ cur = static_cast<R *>(a.cur);
-  const R dsd = (R)a.drift_sd, ldsd = Math<R>::log_((R)a.drift_sd);
+  const A dsd = (A)a.drift_sd, ldsd = Math<A>::log_((A)a.drift_sd);
   const uint32_t base = kMhPairBase + 16u * a.move;
   const bool via_anc = a.ctl ? (a.ctl->do_resample != 0) : (a.anc != nullptr);
   unsigned int nacc = 0;
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < a.n; i += (long long)gridDim.x * kBlock) {
     const unsigned long long pid = (unsigned long long)(a.pid_offset + i);
-    R prev[S], st[S], next[S], eps[NN > 0 ? NN : 1], us[NU > 0 ? NU : 1];
+    A prev[S], st[S], next[S], eps[NN > 0 ? NN : 1], us[NU > 0 ? NU : 1];
     if (!INIT) {
       const long long src = via_anc ? (long long)a.anc[i] : i;
 #pragma unroll
-      for (int s = 0; s < S; s++) prev[s] = __ldg(par + (long long)s * a.ld + src);
+      for (int s = 0; s < S; s++) prev[s] = (A)__ldg(par + (long long)s * a.ld + src);
     } else {
 #pragma unroll
-      for (int s = 0; s < S; s++) prev[s] = R(0);
+      for (int s = 0; s < S; s++) prev[s] = A(0);
     }
 #pragma unroll
-    for (int s = 0; s < S; s++) st[s] = cur[(long long)s * a.ld + i];
-    R ua;
+    for (int s = 0; s < S; s++) st[s] = (A)cur[(long long)s * a.ld + i];
+    A ua;
     if (PREDRAWN) {
 #pragma unroll
-      for (int d = 0; d < NN; d++) eps[d] = (R)a.normals[(long long)d * a.ld + i];
+      for (int d = 0; d < NN; d++) eps[d] = (A)(R)a.normals[(long long)d * a.ld + i];
 #pragma unroll
-      for (int d = 0; d < NU; d++) us[d] = (R)a.uniforms[(long long)d * a.ld + i];
-      ua = (R)a.uniforms[(long long)NU * a.ld + i];
+      for (int d = 0; d < NU; d++) us[d] = (A)(R)a.uniforms[(long long)d * a.ld + i];
+      ua = (A)(R)a.uniforms[(long long)NU * a.ld + i];
     } else {
 #pragma unroll
       for (int d = 0; d < NN; d += 2) {
         R e0, e1;
         philox_normal_pair(a.seed, pid, a.step, base + (uint32_t)(d >> 1), T, e0, e1);
-        eps[d] = e0;
-        if (d + 1 < NN) eps[d + 1] = e1;
+        eps[d] = (A)e0;
+        if (d + 1 < NN) eps[d + 1] = (A)e1;
       }
       R u0, u1;
       philox_uniform_pair(a.seed, pid, a.step, base + 15u, u0, u1);
-      ua = u0;
-      if (NU > 0) us[0] = u1;
+      ua = (A)u0;
+      if (NU > 0) us[0] = (A)u1;
     }
-    R alpha;
+    A alpha;
     if (MOVE == MH_RESIMULATE) {
-      const R w_new = Tr::apply(a.mp, h, T, prev, next, eps, us);
+      const A w_new = Tr::apply(a.mp, h, T, prev, next, eps, us);
       alpha = w_new - Tr::obs_logpdf(a.mp, h, T, st);                       // regenerate.jl:47-50
     } else {
-      const R fwd_minus_bwd = Tr::drift(a.mp, h, prev, st, next, eps, dsd, ldsd);
-      R w = Tr::latent_logpdf(a.mp, h, T, prev, next) - Tr::latent_logpdf(a.mp, h, T, prev, st);   // update.jl:46-50
+      const A fwd_minus_bwd = Tr::drift(a.mp, h, prev, st, next, eps, dsd, ldsd);
+      A w = Tr::latent_logpdf(a.mp, h, T, prev, next) - Tr::latent_logpdf(a.mp, h, T, prev, st);   // update.jl:46-50
       w += Tr::obs_logpdf(a.mp, h, T, next) - Tr::obs_logpdf(a.mp, h, T, st);
       alpha = w - fwd_minus_bwd;                                            // mh.jl:49
     }
     if (a.alpha_out) a.alpha_out[i] = (double)alpha;
-    if (Math<R>::log_(ua) < alpha) {                                        // mh.jl:20, :52 (NaN => reject)
+    if (Math<A>::log_(ua) < alpha) {                                        // mh.jl:20, :52 (NaN => reject)
 #pragma unroll
-      for (int s = 0; s < S; s++) cur[(long long)s * a.ld + i] = next[s];
+      for (int s = 0; s < S; s++) cur[(long long)s * a.ld + i] = (R)next[s];
       nacc++;
     }
   }
@@ -111,12 +113,13 @@ __global__ void __launch_bounds__(kBlock) mh_kernel(const MhArgs a) {
 // Valid for programs whose weight is exactly that sum (no proposal-correction terms).
 template <typename R, int KIND, bool INIT, bool PREDRAWN>
 __global__ void __launch_bounds__(kBlock) mh_resim_lik_kernel(const MhArgs a) {
-  using Tr = Transition<R, KIND, PROPOSAL_DEFAULT, INIT>;
+  typedef typename Arith<R>::type A;     // storage R, arithmetic fp64 (models.cuh)
+  using Tr = Transition<A, KIND, PROPOSAL_DEFAULT, INIT>;
   constexpr int S = Tr::S, NN = Tr::NN, NU = Tr::NU;
   __shared__ double s_tab[kMathTabDoubles];
   const MathTables T = stage_math_tables(s_tab);
   __syncthreads();
-  const Hoisted<R> h = Tr::hoist(a.mp);
+  const Hoisted<A> h = Tr::hoist(a.mp);
   const R *__restrict__ par = static_cast<const R *>(a.parent);
   R *__restrict__ cur = static_cast<R *>(a.cur);
   R *__restrict__ lik = static_cast<R *>(a.lik);
@@ -125,45 +128,45 @@ __global__ void __launch_bounds__(kBlock) mh_resim_lik_kernel(const MhArgs a) {
   unsigned int nacc = 0;
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < a.n; i += (long long)gridDim.x * kBlock) {
     const unsigned long long pid = (unsigned long long)(a.pid_offset + i);
-    R prev[S], next[S], eps[NN > 0 ? NN : 1], us[NU > 0 ? NU : 1];
+    A prev[S], next[S], eps[NN > 0 ? NN : 1], us[NU > 0 ? NU : 1];
     const long long src = (!INIT && via_anc) ? (long long)a.anc[i] : i;
 #pragma unroll
-    for (int s = 0; s < S; s++) prev[s] = INIT ? R(0) : __ldg(par + (long long)s * a.ld + src);
-    R ua;
+    for (int s = 0; s < S; s++) prev[s] = INIT ? A(0) : (A)__ldg(par + (long long)s * a.ld + src);
+    A ua;
     if (PREDRAWN) {
 #pragma unroll
-      for (int d = 0; d < NN; d++) eps[d] = (R)a.normals[(long long)d * a.ld + i];
+      for (int d = 0; d < NN; d++) eps[d] = (A)(R)a.normals[(long long)d * a.ld + i];
 #pragma unroll
-      for (int d = 0; d < NU; d++) us[d] = (R)a.uniforms[(long long)d * a.ld + i];
-      ua = (R)a.uniforms[(long long)NU * a.ld + i];
+      for (int d = 0; d < NU; d++) us[d] = (A)(R)a.uniforms[(long long)d * a.ld + i];
+      ua = (A)(R)a.uniforms[(long long)NU * a.ld + i];
     } else {
 #pragma unroll
       for (int d = 0; d < NN; d += 2) {
         R e0, e1;
         philox_normal_pair(a.seed, pid, a.step, base + (uint32_t)(d >> 1), T, e0, e1);
-        eps[d] = e0;
-        if (d + 1 < NN) eps[d + 1] = e1;
+        eps[d] = (A)e0;
+        if (d + 1 < NN) eps[d + 1] = (A)e1;
       }
       // accept draw: first uniform of pair base + 15; the transition's own uniforms: pairs base + 8 ...
       R u0, u1;
       philox_uniform_pair(a.seed, pid, a.step, base + 15u, u0, u1);
-      ua = u0;
-      if (NU > 0) us[0] = u1;
+      ua = (A)u0;
+      if (NU > 0) us[0] = (A)u1;
 #pragma unroll
       for (int d = 1; d < NU; d += 2) {
         R v0, v1;
         philox_uniform_pair(a.seed, pid, a.step, base + 8u + (uint32_t)(d >> 1), v0, v1);
-        us[d] = v0;
-        if (d + 1 < NU) us[d + 1] = v1;
+        us[d] = (A)v0;
+        if (d + 1 < NU) us[d + 1] = (A)v1;
       }
     }
-    const R w_new = Tr::apply(a.mp, h, T, prev, next, eps, us);
-    const R alpha = w_new - lik[i];
+    const A w_new = Tr::apply(a.mp, h, T, prev, next, eps, us);
+    const A alpha = w_new - (A)lik[i];
     if (a.alpha_out) a.alpha_out[i] = (double)alpha;
-    if (Math<R>::log_(ua) < alpha) {
+    if (Math<A>::log_(ua) < alpha) {
 #pragma unroll
-      for (int s = 0; s < S; s++) cur[(long long)s * a.ld + i] = next[s];
-      lik[i] = w_new;
+      for (int s = 0; s < S; s++) cur[(long long)s * a.ld + i] = (R)next[s];
+      lik[i] = (R)w_new;
       nacc++;
     }
   }

@@ -794,15 +794,15 @@ __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restric
 }
 
 // ==========================================================================================
-// Asynchronous sharded resample (gen.jl_b200/sharded.py run_): no host round trip anywhere in a step.
-//   * the statistics records are all-reduced / all-gathered on the device (NCCL on device memory);
-//   * shard_plan_kernel turns them into the ESS test, the log-ML update and the exchange plan ON THE DEVICE;
-//   * offspring owned by another shard are written by export_p2p_kernel STRAIGHT INTO THAT SHARD'S MEMORY over
-//     NVLink (peer pointers from CUDA IPC): rows into the extension rows of its current trace buffer, the slot's
-//     ancestor index and the global parent id next to them -- no staging buffer, no all-to-all, traffic = spill;
-//   * one tiny all-reduce afterwards is the barrier that orders the remote writes before the next step kernel.
+// Sharded resample without a host round trip and without collectives (one shard per GPU):
+//   * the global max / the per-shard sums travel through the peer-memory mailboxes of kernels_step.cuh (phases A, B);
+//   * shard_plan_kernel turns them into the ESS test, the log-ML update and the exchange plan ON THE DEVICE (every shard
+//     evaluates the same arithmetic on the same G records, so all agree without talking), then scans the super-tiles;
+//   * offspring owned by another shard are written by export_p2p_kernel STRAIGHT INTO THAT SHARD'S MEMORY over NVLink
+//     (peer pointers: same process or CUDA IPC): rows into the extension rows of its current trace buffer, the slot's
+//     ancestor index and the global parent id next to them -- no staging buffer, no all-to-all, traffic = the spill;
+//   * its last CTA posts a "done" flag to every peer (phase C); xchg_wait_kernel holds the next step until all arrived.
 // ==========================================================================================
-constexpr int kMaxWorld = 64;
 struct PeerMem {           // a peer shard's arrays (device pointers valid in THIS process)
   void *state[2];          // its two trace buffers
   int *anc;
@@ -815,34 +815,53 @@ struct ShardPlanDev {
   long long ext_off[kMaxWorld];                       // first extension row at shard d for the rows sent from here
   int world, rank;
   int overflow;                                       // sticky: a capacity was exceeded, results are invalid
+  WeightStats global;                                 // {m, S1, S2, lse, ess, Q} over ALL shards (what the host reads)
+  unsigned long long q_shard[kMaxWorld];              // every shard's integer CDF mass (host-side capacity check)
 };
 
-// one CTA of kMaxWorld threads; rec = world records {m, s1, s2, lse, ess, q} (8-byte words), offs = shard offsets
-__global__ void __launch_bounds__(kMaxWorld) shard_plan_kernel(const long long *__restrict__ rec, const long long *__restrict__ offs,
-                                                              int world, int rank, long long n_global, uint32_t u0,
-                                                              long long spill_cap, RunCtl *ctl, ResamplePlan *plan, ShardPlanDev *sh) {
+// One CTA (1024 threads).  Waits for every shard's record (phase B), takes the maybe_resample! decision
+// (particle_filter.jl:256; ess_threshold NaN: the run's own threshold in ctl), updates the log-ML estimate (:263), writes
+// the sweep + exchange plan and, when a sweep follows (do_scan), the exclusive scan of this shard's super-tile totals.
+__global__ void __launch_bounds__(1024) shard_plan_kernel(WeightStats *stats, const long long *__restrict__ offs, long long n_global, uint32_t u0,
+                                                          double ess_threshold, int do_scan, long long spill_cap, RunCtl *ctl,
+                                                          ResamplePlan *plan, ShardPlanDev *sh, long long nsuper,
+                                                          unsigned long long *__restrict__ super_q,
+                                                          unsigned long long *__restrict__ super_excl, unsigned int *overflow_count) {
   __shared__ SweepParams s_sp;
   __shared__ unsigned long long s_pref[kMaxWorld + 1];
   __shared__ long long s_lo[kMaxWorld], s_hi[kMaxWorld];
   __shared__ int s_do;
+  __shared__ uint64_t s_w[33];
+  pdl_trigger();
+  pdl_wait();
+  XchgCtl *xc = stats->xc;
+  const int world = xc->world, rank = xc->rank;
   const int r = threadIdx.x;
+  const unsigned long long seq = __ldcg(&xc->seq_b);
+  if (r < world) xchg_spin(&xc->mine->rec_seq[r], seq, xc);
+  __syncthreads();
+  const int slot = (int)(seq & 1);
   if (r == 0) {
-    const double m = __longlong_as_double(rec[0]);
+    const double m = __ldcg(&stats->m);        // the GLOBAL max: wstats folded phase A and left it here
     double S1 = 0.0, S2 = 0.0;
     unsigned long long run = 0;
     for (int k = 0; k < world; k++) {          // fixed rank order: identical on every shard
-      S1 += __longlong_as_double(rec[k * 6 + 1]);
-      S2 += __longlong_as_double(rec[k * 6 + 2]);
+      S1 += __ldcg(&xc->mine->s1[slot][k]);
+      S2 += __ldcg(&xc->mine->s2[slot][k]);
       s_pref[k] = run;
-      run += (unsigned long long)rec[k * 6 + 5];
+      const unsigned long long qk = __ldcg(&xc->mine->q[slot][k]);
+      sh->q_shard[k] = qk;
+      run += qk;
     }
     s_pref[world] = run;
-    const double lse = (m == -INFINITY) ? -INFINITY : m + log(S1);
-    const double ess = (S1 * S1) / S2;
-    const int flag = (ess < ctl->ess_threshold && run > 0) ? 1 : 0;   // particle_filter.jl:256
+    const double lse = (m == -INFINITY) ? -INFINITY : m + log(S1);   // inference.jl:5
+    const double ess = (S1 * S1) / S2;                                // particle_filter.jl:3-6
+    const double thr = ess_threshold == ess_threshold ? ess_threshold : ctl->ess_threshold;
+    const int flag = (ess < thr && run > 0) ? 1 : 0;                  // :256
     ctl->do_resample = flag;
     if (flag) { ctl->log_ml_est += lse - ctl->log_n; ctl->n_resampled += 1; }   // :263
     s_do = flag;
+    sh->global.m = m; sh->global.s1 = S1; sh->global.s2 = S2; sh->global.lse = lse; sh->global.ess = ess; sh->global.q_total = run;
     SweepParams sp;
     sp.q_total = run ? run : 1;
     sp.q_inv = 1.0 / (double)sp.q_total;
@@ -882,29 +901,60 @@ __global__ void __launch_bounds__(kMaxWorld) shard_plan_kernel(const long long *
     sh->send_lo[r] = a; sh->send_hi[r] = b;
     sh->ext_off[r] = before;
   }
+  if (do_scan) {
+    __syncthreads();
+    superscan_block(nsuper, super_q, super_excl, plan, 0, 0, n_global, u0, overflow_count, 1, s_w);
+  }
 }
 
-// blockIdx.y = destination shard d: the rows of the slots d owns go straight into d's memory (NVLink peer stores)
+// blockIdx.y = destination shard d: the rows of the slots d owns go straight into d's memory (NVLink peer stores).
+// The last CTA of the grid to finish posts this shard's "done" flag (phase C) to every peer.
 template <typename R>
 __global__ void __launch_bounds__(kBlock) export_p2p_kernel(const R *__restrict__ sin, long long ld, int S, const int *__restrict__ spill,
                                                             const ResamplePlan *__restrict__ plan, const ShardPlanDev *__restrict__ sh,
                                                             const RunCtl *__restrict__ ctl, const long long *__restrict__ offs,
-                                                            int cur, long long pid_offset, long long spill_cap) {
+                                                            int cur, long long pid_offset, long long spill_cap, WeightStats *stats) {
+  __shared__ bool s_last;
+  pdl_trigger();
+  pdl_wait();
+  if (!ctl->do_resample) return;               // uniform over the grid and over the shards: nobody posts, nobody waits
   const int d = blockIdx.y;
-  if (d == sh->rank || !ctl->do_resample) return;
-  const long long cnt = sh->send_hi[d] - sh->send_lo[d];
-  if (cnt <= 0) return;
-  const PeerMem pm = sh->peer[d];
-  R *__restrict__ dst = static_cast<R *>(pm.state[cur]);
-  const long long base = sh->send_lo[d] - plan->slot_lo;       // index into this shard's spill buffer
-  const long long dst_slot0 = sh->send_lo[d] - offs[d];        // local slot at the destination
-  const long long ext0 = pm.n_pad + sh->ext_off[d];
-  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < cnt; i += (long long)gridDim.x * kBlock) {
-    const int src = (base + i < spill_cap) ? spill[base + i] : 0;
-    for (int s = 0; s < S; s++) dst[(long long)s * pm.ld + ext0 + i] = __ldg(sin + (long long)s * ld + src);
-    pm.anc[dst_slot0 + i] = (int)(ext0 + i);
-    pm.ext_parents[sh->ext_off[d] + i] = pid_offset + src + 1;   // Gen's parents are 1-based, global
+  const long long cnt = d == sh->rank ? 0 : sh->send_hi[d] - sh->send_lo[d];
+  if (cnt > 0) {
+    const PeerMem pm = sh->peer[d];
+    R *__restrict__ dst = static_cast<R *>(pm.state[cur]);
+    const long long base = sh->send_lo[d] - plan->slot_lo;       // index into this shard's spill buffer
+    const long long dst_slot0 = sh->send_lo[d] - offs[d];        // local slot at the destination
+    const long long ext0 = pm.n_pad + sh->ext_off[d];
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < cnt; i += (long long)gridDim.x * kBlock) {
+      const int src = (base + i < spill_cap) ? spill[base + i] : 0;
+      for (int s = 0; s < S; s++) dst[(long long)s * pm.ld + ext0 + i] = __ldg(sin + (long long)s * ld + src);
+      pm.anc[dst_slot0 + i] = (int)(ext0 + i);
+      pm.ext_parents[sh->ext_off[d] + i] = pid_offset + src + 1;   // Gen's parents are 1-based, global
+    }
+    __threadfence_system();                      // this thread's peer stores are ordered before the flag below
   }
+  XchgCtl *xc = stats->xc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&xc->export_ticket, 1u);
+    s_last = (t == gridDim.x * gridDim.y - 1);
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0) return;
+  __threadfence_system();
+  xc->export_ticket = 0;
+  const unsigned long long seq = xc->seq_c + 1;
+  xc->seq_c = seq;
+  for (int r = 0; r < xc->world; r++) st_release_sys(&xc->peer[r]->done_seq[xc->rank], seq);
+}
+// phase C wait: every peer's offspring rows have landed in this shard's extension rows
+__global__ void __launch_bounds__(kMaxWorld) xchg_wait_kernel(WeightStats *stats, const RunCtl *__restrict__ ctl) {
+  pdl_trigger();
+  pdl_wait();
+  if (!ctl->do_resample) return;
+  XchgCtl *xc = stats->xc;
+  if ((int)threadIdx.x < xc->world) xchg_spin(&xc->mine->done_seq[threadIdx.x], __ldcg(&xc->seq_c), xc);
 }
 
 }  // namespace gb

@@ -74,7 +74,8 @@ GB_D uint64_t small_block_scan(uint64_t v, uint64_t *s /* 17 */, uint64_t *total
 
 template <typename R, int KIND>
 __global__ void __launch_bounds__(kSmallThreads, 1) small_run_kernel(const SmallRunArgs a) {
-  typedef Transition<R, KIND, PROPOSAL_DEFAULT, false> Tr;
+  typedef typename Arith<R>::type A;     // storage R, arithmetic fp64 (models.cuh)
+  typedef Transition<A, KIND, PROPOSAL_DEFAULT, false> Tr;
   constexpr int S = Tr::S, NN = Tr::NN, NU = Tr::NU, P = kSmallItems;
   __shared__ double s_tab[kMathTabDoubles];
   __shared__ int s_anc[kSmallMax];
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) small_run_kernel(const Small
   R *__restrict__ logw = static_cast<R *>(a.logw);
   R *__restrict__ incr = static_cast<R *>(a.incr);
   ModelParams mp = a.mp;
-  const Hoisted<R> hz = Tr::hoist(mp);
+  const Hoisted<A> hz = Tr::hoist(mp);
   R lw[P];
 #pragma unroll
   for (int j = 0; j < P; j++) lw[j] = (j < per && i0 + j < n) ? logw[i0 + j] : R(0);
@@ -167,28 +168,28 @@ __global__ void __launch_bounds__(kSmallThreads, 1) small_run_kernel(const Small
       const int i = i0 + j;
       if (j < per && i < n) {
         const int src = resample ? s_anc[i] : i;
-        R pv[S], nx[S], eps[NN > 0 ? NN : 1], us[NU > 0 ? NU : 1];
+        A pv[S], nx[S], eps[NN > 0 ? NN : 1], us[NU > 0 ? NU : 1];
 #pragma unroll
-        for (int s = 0; s < S; s++) pv[s] = sin[(long long)s * a.ld + src];
+        for (int s = 0; s < S; s++) pv[s] = (A)sin[(long long)s * a.ld + src];
 #pragma unroll
         for (int d = 0; d < NN; d += 2) {
           R e0, e1;
           philox_normal_pair(a.seed, (unsigned long long)i, nstep, (unsigned)(d / 2), T, e0, e1);
-          eps[d] = e0;
-          if (d + 1 < NN) eps[d + 1] = e1;
+          eps[d] = (A)e0;
+          if (d + 1 < NN) eps[d + 1] = (A)e1;
         }
 #pragma unroll
         for (int d = 0; d < NU; d += 2) {
           R u0, u1;
           philox_uniform_pair(a.seed, (unsigned long long)i, nstep, (unsigned)(d / 2), u0, u1);
-          us[d] = u0;
-          if (d + 1 < NU) us[d + 1] = u1;
+          us[d] = (A)u0;
+          if (d + 1 < NU) us[d + 1] = (A)u1;
         }
-        const R w = Tr::apply(mp, hz, T, pv, nx, eps, us);
+        const A w = Tr::apply(mp, hz, T, pv, nx, eps, us);
 #pragma unroll
-        for (int s = 0; s < S; s++) sout[(long long)s * a.ld + i] = nx[s];
-        lw[j] = (resample ? R(0) : lw[j]) + w;                      // :231 (after :266 when resampled)
-        if (t == a.T - 1) incr[i] = w;
+        for (int s = 0; s < S; s++) sout[(long long)s * a.ld + i] = (R)nx[s];
+        lw[j] = (R)((resample ? A(0) : (A)lw[j]) + w);              // :231 (after :266 when resampled)
+        if (t == a.T - 1) incr[i] = (R)w;
       }
     }
     cur ^= 1;

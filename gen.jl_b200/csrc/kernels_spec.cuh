@@ -30,17 +30,18 @@ __constant__ SpecOp c_spec_ops[kSpecMaxOps];
 __constant__ double c_spec_params[kSpecMaxParams];
 
 
-template <typename R, bool INIT, bool PREDRAWN, int GATHER>
+template <typename ST, bool INIT, bool PREDRAWN, int GATHER>
 __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
+  typedef typename Arith<ST>::type R;     // ST = storage type of the filter; the program is evaluated in fp64 (models.cuh)
   __shared__ double s_tab[kMathTabDoubles];
   pdl_trigger();
   const MathTables T = stage_math_tables(s_tab);
   __syncthreads();
   pdl_wait();
-  const R *__restrict__ sin = static_cast<const R *>(a.state_in);
-  R *__restrict__ sout = static_cast<R *>(a.state_out);
-  R *__restrict__ logw = static_cast<R *>(a.logw);
-  R *__restrict__ incr = static_cast<R *>(a.incr);
+  const ST *__restrict__ sin = static_cast<const ST *>(a.state_in);
+  ST *__restrict__ sout = static_cast<ST *>(a.state_out);
+  ST *__restrict__ logw = static_cast<ST *>(a.logw);
+  ST *__restrict__ incr = static_cast<ST *>(a.incr);
   const bool gather = GATHER == 2 ? (a.ctl->do_resample != 0) : (GATHER == 1);
   double acc = -INFINITY;
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < a.n; i += (long long)gridDim.x * kBlock) {
@@ -49,12 +50,12 @@ __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
     R regs[kSpecRegs];
     R w = R(0);
     int n_norm = 0, n_unif = 0, n_gamma = 0;
-    R spare_n = R(0), spare_u = R(0);
+    ST spare_n = ST(0), spare_u = ST(0);
     for (int k = a.op_begin; k < a.op_end; k++) {
       const SpecOp op = c_spec_ops[k];
       switch (op.code) {
         case OP_CONST: regs[op.dst] = (R)op.imm; break;
-        case OP_PREV: regs[op.dst] = INIT ? R(0) : __ldg(sin + (long long)op.a * a.ld + src); break;
+        case OP_PREV: regs[op.dst] = INIT ? R(0) : (R)__ldg(sin + (long long)op.a * a.ld + src); break;
         case OP_PARAM: regs[op.dst] = (R)c_spec_params[op.a]; break;
         case OP_OBS: regs[op.dst] = (R)a.obs[op.a]; break;
         case OP_TIME: regs[op.dst] = (R)a.step; break;
@@ -69,24 +70,24 @@ __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
         case OP_LOG: regs[op.dst] = Math<R>::log_(regs[op.a]); break;
         case OP_ATAN2: regs[op.dst] = Math<R>::atan2_t(regs[op.a], regs[op.b], T); break;
         case OP_SAMPLE_NORMAL: {      // normal.jl:128: mu + std * randn()
-          R e;
-          if (PREDRAWN) e = (R)__ldcs(a.normals + (long long)n_norm * a.ld + i);
+          ST e;                        // noise in the storage precision
+          if (PREDRAWN) e = (ST)__ldcs(a.normals + (long long)n_norm * a.ld + i);
           else if (n_norm & 1) e = spare_n;
           else philox_normal_pair(a.seed, pid, a.step, (unsigned)(n_norm >> 1), T, e, spare_n);
           n_norm++;
-          regs[op.dst] = random_normal<R>(regs[op.a], regs[op.b], e);
+          regs[op.dst] = random_normal<R>(regs[op.a], regs[op.b], (R)e);
           break;
         }
         case OP_OBSERVE_NORMAL: w += logpdf_normal<R>(regs[op.dst], regs[op.a], regs[op.b]); break;   // normal.jl:56-59
         case OP_SAMPLE_BERNOULLI: case OP_SAMPLE_CATEGORICAL: case OP_SAMPLE_DIST: {
-          R u;
-          if (PREDRAWN) u = (R)__ldcs(a.uniforms + (long long)n_unif * a.ld + i);
+          ST u;
+          if (PREDRAWN) u = (ST)__ldcs(a.uniforms + (long long)n_unif * a.ld + i);
           else if (n_unif & 1) u = spare_u;
           else philox_uniform_pair(a.seed, pid, a.step, (unsigned)(n_unif >> 1), u, spare_u);
           n_unif++;
           if (op.code == OP_SAMPLE_DIST) regs[op.dst] = (R)random_invcdf((int)op.imm, (double)regs[op.a], (double)regs[op.b], (double)u);
-          else if (op.code == OP_SAMPLE_BERNOULLI) regs[op.dst] = random_bernoulli<R>(regs[op.a], u) ? R(1) : R(0);   // bernoulli.jl:19
-          else regs[op.dst] = (R)random_categorical<R>(c_spec_params + (int)regs[op.a], op.b, u);                  // categorical.jl:20-22
+          else if (op.code == OP_SAMPLE_BERNOULLI) regs[op.dst] = random_bernoulli<R>(regs[op.a], (R)u) ? R(1) : R(0);   // bernoulli.jl:19
+          else regs[op.dst] = (R)random_categorical<R>(c_spec_params + (int)regs[op.a], op.b, (R)u);                  // categorical.jl:20-22
           break;
         }
         case OP_OBSERVE_BERNOULLI: w += logpdf_bernoulli<R>(regs[op.dst] != R(0), regs[op.a]); break;             // bernoulli.jl:10-12
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
           n_gamma++;
           break;
         case OP_OBSERVE_GAMMA: w += logpdf_gamma<R>(regs[op.dst], regs[op.a], regs[op.b]); break;                 // gamma.jl:10-16
-        case OP_STORE: st_stream(sout + (long long)op.dst * a.ld + i, regs[op.a]); break;
+        case OP_STORE: st_stream(sout + (long long)op.dst * a.ld + i, (ST)regs[op.a]); break;
         case OP_WEIGHT: w += regs[op.a]; break;                                     // e.g. minus a proposal score
         case OP_LOGPDF_NORMAL: regs[op.dst] = logpdf_normal<R>(regs[(int)op.imm], regs[op.a], regs[op.b]); break;
         case OP_OBSERVE_DIST: w += (R)logpdf_scalar((int)op.imm, (double)regs[op.dst], (double)regs[op.a], (double)regs[op.b]); break;
@@ -111,10 +112,10 @@ __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
         default: break;
       }
     }
-    const R lw_old = (INIT || gather) ? R(0) : logw[i];
-    const R lw_new = INIT ? w : lw_old + w;                    // particle_filter.jl:131,151 / :199,231
+    const R lw_old = (INIT || gather) ? R(0) : (R)logw[i];
+    const ST lw_new = (ST)(INIT ? w : lw_old + w);             // particle_filter.jl:131,151 / :199,231
     logw[i] = lw_new;
-    if (!INIT) st_stream(incr + i, w);
+    if (!INIT) st_stream(incr + i, (ST)w);
     acc = max_nan(acc, (double)lw_new);
   }
   publish_max(acc, a.partials, a.ticket, a.stats);

@@ -19,11 +19,71 @@
 
 namespace gb {
 
+struct XchgCtl;
 struct WeightStats {
   double m, s1, s2;   // reference max, sum exp(lw-m), sum exp(2(lw-m)) of this shard
   double lse, ess;    // m + log s1 ; s1^2 / s2
   unsigned long long q_total;   // sum of the quantised weights (wstats)
+  XchgCtl *xc;        // sharded filters: the peer-memory exchange below (nullptr: single shard).  NOT part of the record.
 };
+constexpr int kStatsRecordBytes = 48;   // {m, s1, s2, lse, ess, q_total}: what is copied to the host / to a clone
+
+// ------------------------------------------------------------------------------------------
+// Device-side exchange between the shards of one filter (one shard per GPU; NVLink / NVSwitch peer memory).
+// maybe_resample! over G shards needs the global max of the log weights, the per-shard (sum e, sum e^2, integer CDF mass)
+// and a barrier after the offspring rows have been written into their owners' memory.  Instead of three NCCL collectives
+// per step (launch + protocol latency of ~35 us each: a third of the 8-GPU strong-scaling step), the producing kernel's
+// last CTA peer-stores its 8..24 byte contribution into EVERY shard's mailbox, followed by a sequence flag, and the
+// consuming kernel spins on the G flags of its own (local) mailbox:
+//   phase A  publish_max (tail of the step / max kernel)  -> mx[src]            consumed at the start of wstats
+//   phase B  wstats' last CTA                             -> (s1, s2, q)[src]   consumed by shard_plan_kernel
+//   phase C  export_p2p_kernel's last CTA                 -> done flag          consumed by xchg_wait_kernel before the step
+// Payload slots alternate with the parity of the sequence number; a shard can never be more than one phase ahead of a
+// peer (each phase consumes what every peer produced in the previous one), so two slots are enough.  Every shard
+// executes the same sequence of kernels (SPMD), so the expected sequence number is the shard's own post counter.
+// Spins are bounded (timeout_cycles): a lost peer sets `error` instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxWorld = 64;
+struct XchgMail {
+  double mx[2][kMaxWorld];
+  double s1[2][kMaxWorld], s2[2][kMaxWorld];
+  unsigned long long q[2][kMaxWorld];
+  unsigned long long mx_seq[kMaxWorld], rec_seq[kMaxWorld], done_seq[kMaxWorld];
+};
+struct XchgCtl {
+  XchgMail *peer[kMaxWorld];      // every shard's mailbox as seen from THIS device (own included)
+  XchgMail *mine;
+  int world, rank;
+  unsigned long long seq_a, seq_b, seq_c;   // sequence number of this shard's last post per phase
+  long long timeout_cycles;
+  int error;                      // sticky: a wait timed out
+  unsigned int export_ticket;
+};
+GB_D unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+GB_D void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// wait until *flag >= seq (flag lives in this shard's own memory; a peer writes it)
+GB_D void xchg_spin(const unsigned long long *flag, unsigned long long seq, XchgCtl *xc) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < seq) {
+    if (clock64() - t0 > xc->timeout_cycles) { xc->error = 1; break; }
+    __nanosleep(40);
+  }
+}
+// phase A post (one thread): this shard's max of the log weights into every mailbox
+GB_D void xchg_post_max(XchgCtl *xc, double m) {
+  const unsigned long long seq = xc->seq_a + 1;
+  xc->seq_a = seq;
+  const int slot = (int)(seq & 1), me = xc->rank;
+  for (int r = 0; r < xc->world; r++) xc->peer[r]->mx[slot][me] = m;
+  __threadfence_system();
+  for (int r = 0; r < xc->world; r++) st_release_sys(&xc->peer[r]->mx_seq[me], seq);
+}
 
 // Device-side control block of the fused multi-step entry (gb_pf_run): the ESS test of maybe_resample!
 // (particle_filter.jl:256), the running log-ML (:263) and the gathered/direct choice of the next step live
@@ -75,20 +135,30 @@ template <> GB_D void vstore_keep<float>(float *p, const float (&i)[4]) {
   *reinterpret_cast<float4 *>(p) = make_float4(i[0], i[1], i[2], i[3]);
 }
 
-// particles per thread of the step kernel (compile-time tuning knob; 128-bit accesses at the default)
+// particles per thread of the step kernel (compile-time tuning knobs; 128-bit accesses for fp64 at the default; fp32
+// filters run the same fp64 transition, so two particles per thread (64-bit accesses) keep them free of register spills)
 #ifndef GB_STEP_V64
 #define GB_STEP_V64 2
 #endif
-template <typename R> struct StepV { static constexpr int V = VecOf<R>::V; };
+#ifndef GB_STEP_V32
+#define GB_STEP_V32 2
+#endif
+template <typename R> struct StepV { static constexpr int V = GB_STEP_V32; };
 template <> struct StepV<double> { static constexpr int V = GB_STEP_V64; };
 template <typename R, int V> GB_D void svload(const R *p, R (&o)[V]) {
-  if constexpr (V == VecOf<R>::V) vload<R>(p, o); else { for (int k = 0; k < V; k++) o[k] = __ldcs(p + k); }
+  if constexpr (V == VecOf<R>::V) vload<R>(p, o);
+  else if constexpr (sizeof(R) == 4 && V == 2) { float2 t = __ldcs(reinterpret_cast<const float2 *>(p)); o[0] = t.x; o[1] = t.y; }
+  else { for (int k = 0; k < V; k++) o[k] = __ldcs(p + k); }
 }
 template <typename R, int V> GB_D void svstore(R *p, const R (&o)[V]) {
-  if constexpr (V == VecOf<R>::V) vstore<R>(p, o); else { for (int k = 0; k < V; k++) __stcs(p + k, o[k]); }
+  if constexpr (V == VecOf<R>::V) vstore<R>(p, o);
+  else if constexpr (sizeof(R) == 4 && V == 2) __stcs(reinterpret_cast<float2 *>(p), make_float2(o[0], o[1]));
+  else { for (int k = 0; k < V; k++) __stcs(p + k, o[k]); }
 }
 template <typename R, int V> GB_D void svstore_keep(R *p, const R (&o)[V]) {
-  if constexpr (V == VecOf<R>::V) vstore_keep<R>(p, o); else { for (int k = 0; k < V; k++) p[k] = o[k]; }
+  if constexpr (V == VecOf<R>::V) vstore_keep<R>(p, o);
+  else if constexpr (sizeof(R) == 4 && V == 2) *reinterpret_cast<float2 *>(p) = make_float2(o[0], o[1]);
+  else { for (int k = 0; k < V; k++) p[k] = o[k]; }
 }
 
 struct StepArgs {
@@ -150,7 +220,13 @@ GB_D void publish_max(double acc, double *partials, unsigned int *ticket, Weight
   if (threadIdx.x == 0) {
     stats->m = a;
     *ticket = 0;
+    XchgCtl *xc = stats->xc;
+    if (xc) xchg_post_max(xc, a);     // sharded filter: phase A of the peer-memory exchange
   }
+}
+// the same post for a max that is known without a pass over the weights (all zero after a resample, host-cached)
+__global__ void xchg_post_max_kernel(WeightStats *stats) {
+  if (threadIdx.x == 0 && stats->xc) xchg_post_max(stats->xc, stats->m);
 }
 
 #ifndef GB_STEP_MINB
@@ -158,7 +234,11 @@ GB_D void publish_max(double acc, double *partials, unsigned int *ticket, Weight
 #endif
 template <typename R, int KIND, int PK, bool INIT, bool PREDRAWN, int GATHER /* 0 no, 1 yes, 2 ctl->do_resample */>
 __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepArgs a) {
-  typedef Transition<R, KIND, PK, INIT> Tr;
+  // R is the STORAGE type (traces, log weights, noise); the transition itself (propose + logpdf) is always evaluated in
+  // fp64 on the widened values (models.cuh "Arith"), so a GB_F32 filter differs from the fp64 one only by the rounding of
+  // what it stores.
+  typedef typename Arith<R>::type A;
+  typedef Transition<A, KIND, PK, INIT> Tr;
   constexpr int V = StepV<R>::V, S = Tr::S, NN = Tr::NN, NU = Tr::NU;
   __shared__ double s_tab[kMathTabDoubles];
   pdl_trigger();
@@ -169,7 +249,7 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
   R *__restrict__ sout = static_cast<R *>(a.state_out);
   R *__restrict__ logw = static_cast<R *>(a.logw);
   R *__restrict__ incr = static_cast<R *>(a.incr);
-  const Hoisted<R> hz = Tr::hoist(a.mp);
+  const Hoisted<A> hz = Tr::hoist(a.mp);
   double acc = -INFINITY;
 
   const long long nvec = (a.n + V - 1) / V;
@@ -223,45 +303,42 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
         }
       }
     }
-    R next[S][V], w[V];
+    R next[S][V], w[V], lw_new[V];
 #pragma unroll
     for (int v = 0; v < V; v++) {
       const long long i = i0 + v;
-      R eps[NN > 0 ? NN : 1], us[NU > 0 ? NU : 1];
+      A eps[NN > 0 ? NN : 1], us[NU > 0 ? NU : 1];
       if (PREDRAWN) {
 #pragma unroll
-        for (int d = 0; d < NN; d++) eps[d] = (R)__ldcs(a.normals + (long long)d * a.ld + i);
+        for (int d = 0; d < NN; d++) eps[d] = (A)(R)__ldcs(a.normals + (long long)d * a.ld + i);
 #pragma unroll
-        for (int d = 0; d < NU; d++) us[d] = (R)__ldcs(a.uniforms + (long long)d * a.ld + i);
+        for (int d = 0; d < NU; d++) us[d] = (A)(R)__ldcs(a.uniforms + (long long)d * a.ld + i);
       } else {
         const unsigned long long pid = (unsigned long long)(a.pid_offset + i);
 #pragma unroll
         for (int d = 0; d < NN; d += 2) {
-          R e0, e1;
+          R e0, e1;                  // the noise itself is drawn in the storage precision
           philox_normal_pair(a.seed, pid, a.step, (unsigned)(d / 2), T, e0, e1);
-          eps[d] = e0;
-          if (d + 1 < NN) eps[d + 1] = e1;
+          eps[d] = (A)e0;
+          if (d + 1 < NN) eps[d + 1] = (A)e1;
         }
 #pragma unroll
         for (int d = 0; d < NU; d += 2) {
           R u0, u1;
           philox_uniform_pair(a.seed, pid, a.step, (unsigned)(d / 2), u0, u1);
-          us[d] = u0;
-          if (d + 1 < NU) us[d + 1] = u1;
+          us[d] = (A)u0;
+          if (d + 1 < NU) us[d + 1] = (A)u1;
         }
       }
-      R pv[S], nx[S];
+      A pv[S], nx[S];
 #pragma unroll
-      for (int s = 0; s < S; s++) pv[s] = INIT ? R(0) : prev[s][v];
-      w[v] = Tr::apply(a.mp, hz, T, pv, nx, eps, us);
+      for (int s = 0; s < S; s++) pv[s] = INIT ? A(0) : (A)prev[s][v];
+      const A wa = Tr::apply(a.mp, hz, T, pv, nx, eps, us);
 #pragma unroll
-      for (int s = 0; s < S; s++) next[s][v] = nx[s];
-    }
-    R lw_new[V];
-#pragma unroll
-    for (int v = 0; v < V; v++) {
-      lw_new[v] = INIT ? w[v] : lw_old[v] + w[v];     // particle_filter.jl:131,151 / :199,231
-      if (i0 + v < a.n) acc = max_nan(acc, (double)lw_new[v]);
+      for (int s = 0; s < S; s++) next[s][v] = (R)nx[s];
+      w[v] = (R)wa;
+      lw_new[v] = (R)(INIT ? wa : (A)lw_old[v] + wa);     // particle_filter.jl:131,151 / :199,231
+      if (i < a.n) acc = max_nan(acc, (double)lw_new[v]);
     }
 #pragma unroll
     for (int s = 0; s < S; s++) svstore<R, V>(sout + (long long)s * a.ld + i0, next[s]);
@@ -450,9 +527,26 @@ __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ lo
   __shared__ uint64_t s_u64_33[33];
   __shared__ double2 s_d2[kBlock / 32];
   __shared__ bool s_last;
+  __shared__ double s_m;
   pdl_trigger();
   pdl_wait();
-  const double m = m_from_device ? __ldcg(&stats->m) : m_arg;
+  double m = m_from_device ? __ldcg(&stats->m) : m_arg;
+  XchgCtl *xc = m_from_device == 2 ? stats->xc : nullptr;
+  if (xc) {
+    // phase A of the exchange: every shard's max arrives in this shard's mailbox; the global max is their maximum,
+    // taken in rank order by every CTA (identical bits everywhere)
+    const unsigned long long seq = __ldcg(&xc->seq_a);
+    const int world = xc->world;
+    if ((int)threadIdx.x < world) xchg_spin(&xc->mine->mx_seq[threadIdx.x], seq, xc);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double g = -INFINITY;
+      for (int r = 0; r < world; r++) g = max_nan(g, __ldcg(&xc->mine->mx[seq & 1][r]));
+      s_m = g;
+    }
+    __syncthreads();
+    m = s_m;
+  }
   const long long ntiles = (n + kTile - 1) / kTile;
   const long long nseg = ntiles * (kTile / kSeg);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -545,6 +639,17 @@ __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ lo
     // particle_filter.jl:3-6: exp(-logsumexp(2 lnw)) == s1^2 / s2 ; all -Inf => NaN there too
     stats->ess = (t1 * t1) / t2;
     stats->q_total = qtot;
+    if (xc) {    // phase B of the exchange: this shard's (sum e, sum e^2, integer CDF mass) into every mailbox
+      const unsigned long long seq = xc->seq_b + 1;
+      xc->seq_b = seq;
+      const int slot = (int)(seq & 1), me = xc->rank;
+      for (int r = 0; r < xc->world; r++) {
+        XchgMail *pm = xc->peer[r];
+        pm->s1[slot][me] = t1; pm->s2[slot][me] = t2; pm->q[slot][me] = qtot;
+      }
+      __threadfence_system();
+      for (int r = 0; r < xc->world; r++) st_release_sys(&xc->peer[r]->rec_seq[me], seq);
+    }
     if (ctl) {   // maybe_resample! decision + log-ML update on the device (particle_filter.jl:256, :263)
       const int flag = stats->ess < ctl->ess_threshold ? 1 : 0;
       ctl->do_resample = flag;

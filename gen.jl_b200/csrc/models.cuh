@@ -26,6 +26,13 @@ struct ModelParams {
   unsigned int step;
 };
 
+// Arithmetic type of the per-particle transition for a filter whose STORAGE type is R: always fp64.  A GB_F32 filter
+// keeps traces, log weights and noise in fp32 (half the HBM traffic) but widens them for propose + logpdf, so its log
+// weights differ from the fp64 filter's only through the rounding of what is stored: a single-precision atan2 or
+// (obs - mean) / sigma residual is amplified by the likelihood's curvature (1/sigma = 200 for the bearings model) to
+// 1e-4 relative per particle, ten times the 1e-5 bar.  The kernels are HBM / issue bound, not fp64-pipe bound.
+template <typename R> struct Arith { typedef double type; };
+
 // Per-thread constants hoisted out of the particle loop (log of fixed standard deviations etc.).
 template <typename R> struct Hoisted { R c0, c1, c2, i0, i1, i2; };
 

@@ -156,8 +156,32 @@ class ShardOps:
         o = np.ascontiguousarray(offs, dtype=np.int64)
         L.check(L.lib().gb_pf_async_setup(self.h, world, rank, o.ctypes.data_as(L.i64p), float(ess_threshold)))
 
-    def async_plan(self, gathered, u0):
-        L.check(L.lib().gb_pf_async_plan(self.h, C.c_void_p(gathered.data_ptr()), int(u0)))
+    def async_arm(self, ess_threshold):
+        L.check(L.lib().gb_pf_async_arm(self.h, float(ess_threshold)))
+
+    def xchg_post(self):
+        L.check(L.lib().gb_pf_xchg_post(self.h))
+
+    def xchg_stats(self):
+        L.check(L.lib().gb_pf_xchg_stats(self.h))
+
+    def async_plan(self, u0, ess_threshold, do_scan):
+        L.check(L.lib().gb_pf_async_plan(self.h, int(u0), float(ess_threshold), int(do_scan)))
+
+    def xchg_read(self, world):
+        """Global (m, lse, ess) and every shard's integer CDF mass after gb_pf_xchg_stats + gb_pf_async_plan: one D2H read."""
+        lse, ess, m = C.c_double(), C.c_double(), C.c_double()
+        qs = (C.c_uint64 * world)()
+        L.check(L.lib().gb_pf_xchg_read(self.h, C.byref(lse), C.byref(ess), None, None))
+        L.check(L.lib().gb_pf_xchg_records(self.h, C.byref(m), qs))
+        return m.value, lse.value, ess.value, [int(q) for q in qs]
+
+    def async_wait(self):
+        L.check(L.lib().gb_pf_async_wait(self.h))
+
+    def async_iterate(self, obs):
+        o = api._flatten_obs(obs)
+        L.check(L.lib().gb_pf_async_iterate(self.h, o.ctypes.data_as(L.dp), o.size))
 
     def async_sweep(self):
         L.check(L.lib().gb_pf_async_sweep(self.h))
@@ -206,9 +230,6 @@ class ShardedParticleFilter:
             self.tdtype = torch.float64
         self.state_dim = self.ops.state_dim
         self.last_ess = None
-        self._stats_t = None        # device-resident statistics record (CUDA shards)
-        self._gather_t = None
-        self._barrier_t = None
         self._peers_attached = False
         self._bufs = {}
         # extension-row capacity of every shard (same formula on every rank: no collective needed)
@@ -223,7 +244,6 @@ class ShardedParticleFilter:
         # sequence of calls, so all ranks hit or miss together
         self._wver = 0
         self._stats_cache = (-1, None)
-        self._setup_thr = None
 
     # ---- collectives (tiny) ----
     def _allreduce_max(self, x):
@@ -300,7 +320,11 @@ class ShardedParticleFilter:
     def _attach_peers(self):
         """Exchange CUDA IPC handles of the shards' buffers once (collective), so that offspring can be written straight
         into the owning shard's memory over NVLink."""
-        if self._peers_attached or self.world == 1:
+        if self._peers_attached:
+            return
+        if self.world == 1:
+            self.ops.async_setup(1, 0, self.offs, math.inf)
+            self._peers_attached = True
             return
         bundles = [None] * self.world
         self.dist.all_gather_object(bundles, (self.ops.ipc_bundle(), self.ops.async_cur()), group=self.group)
@@ -308,41 +332,26 @@ class ShardedParticleFilter:
         for r, (bundle, _) in enumerate(bundles):
             if r != self.rank:
                 self.ops.attach_ipc(r, bundle)
+        # exchange control block + mailbox reset, ONCE; nobody may post before every shard has reset its mailbox
+        self.ops.async_setup(self.world, self.rank, self.offs, math.inf)
+        self.torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)
         self._peers_attached = True
 
     def run_(self, observations_seq, ess_threshold=None):
-        """T x { maybe_resample!; particle_filter_step! } over the sharded filter WITHOUT any host round trip: the
-        statistics record is all-reduced / all-gathered on the device, the exchange plan, the ESS test and the log-ML
-        update run in a device kernel, and offspring owned by another shard are written straight into that shard's memory
-        over NVLink (CUDA IPC peer pointers), followed by a one-word all-reduce as the barrier.  Same results as the
-        synchronous path bit for bit, as long as no shard receives more rows than its extension rows hold (25 % of the
-        shard; otherwise GenB200Error and the synchronous staged path must be used).  Returns the number of resamples."""
-        torch, dist, W = self.torch, self.dist, self.world
+        """T x { maybe_resample!; particle_filter_step! } over the sharded filter WITHOUT any host round trip and without
+        collectives: the shards' maxima, sums and "rows delivered" flags travel through peer-memory mailboxes written and
+        awaited by the kernels themselves, the exchange plan, the ESS test and the log-ML update run in a device kernel,
+        and offspring owned by another shard are written straight into that shard's memory over NVLink (CUDA IPC peer
+        pointers) -- include/genb200.h "Sharded maybe_resample! WITHOUT collectives".  The host only enqueues (one C call
+        per step).  Same results as the synchronous path bit for bit, as long as no shard receives more rows than its
+        extension rows hold (25 % of the shard; otherwise GenB200Error and the synchronous staged path must be used).
+        Returns the number of resamples."""
         thr = self.n_global / 2 if ess_threshold is None else float(ess_threshold)
         self._attach_peers()
-        self.ops.async_setup(W, self.rank, self.offs, thr)
-        self._setup_thr = None                               # the run's RunCtl (threshold, log-ML) is live on the device
-        if self._stats_t is None:
-            self._stats_t = self.ops.stats_tensor(torch)
-            self._gather_t = torch.empty(W * self._stats_t.numel(), dtype=torch.int64, device=self.device)
-        if self._barrier_t is None:
-            self._barrier_t = torch.zeros(1, dtype=torch.int32, device=self.device)
-        m_view = self._stats_t[0:1].view(torch.float64)
+        self.ops.async_arm(thr)
         for obs in observations_seq:
-            self.ops.weight_max_device()
-            if W > 1:
-                dist.all_reduce(m_view, op=dist.ReduceOp.MAX, group=self.group)
-            self.ops.weight_sums_device(self.bits)
-            if W > 1:
-                dist.all_gather_into_tensor(self._gather_t, self._stats_t, group=self.group)
-            else:
-                self._gather_t.copy_(self._stats_t)
-            self.ops.async_plan(self._gather_t, api.philox_resample_u0(self.seed, self.step))
-            self.ops.async_sweep()
-            if W > 1:
-                self.ops.async_export()                                   # peer stores over NVLink
-                dist.all_reduce(self._barrier_t, group=self.group)      # barrier: remote rows landed before the step reads them
-            self.ops.async_step(obs)
+            self.ops.async_iterate(obs)
             self.step += 1
         nres = self.ops.async_finish()
         self._wver += 1
@@ -359,21 +368,13 @@ class ShardedParticleFilter:
         return out
 
     def _global_stats_uncached(self):
-        if self.device.type == "cuda" and self.world > 1:
-            # collectives run directly on the shard's device-resident statistics record: all-reduce(max) of
-            # m in place, statistics pass w.r.t. that m, all-gather of the records, ONE device->host read
-            torch, dist = self.torch, self.dist
-            if self._stats_t is None:
-                self._stats_t = self.ops.stats_tensor(torch)
-                self._gather_t = torch.empty(self.world * self._stats_t.numel(), dtype=torch.int64, device=self.device)
-            self.ops.weight_max_device()
-            dist.all_reduce(self._stats_t[0:1].view(torch.float64), op=dist.ReduceOp.MAX, group=self.group)
-            self.ops.weight_sums_device(self.bits)
-            dist.all_gather_into_tensor(self._gather_t, self._stats_t, group=self.group)
-            rec = self._gather_t.cpu().numpy().reshape(self.world, -1)
-            m = float(rec[0, 0:1].copy().view(np.float64)[0])
-            s1s, s2s = rec[:, 1].copy().view(np.float64), rec[:, 2].copy().view(np.float64)
-            qs = [int(v) for v in rec[:, 5]]
+        if self.device.type == "cuda" and self.use_p2p:
+            # peer-memory exchange (no collective): statistics pass w.r.t. the global max, every shard's record in every
+            # mailbox, the global record assembled by a device kernel, ONE device->host read
+            self._attach_peers()
+            self.ops.xchg_stats()
+            self.ops.async_plan(0, -math.inf, 0)
+            return self.ops.xchg_read(self.world)
         else:
             m = self._allreduce_max(self.ops.weight_max())
             s1, s2, q = self.ops.weight_sums(m, self.bits)
@@ -397,28 +398,24 @@ class ShardedParticleFilter:
             print("effective sample size: %s, doing resample: %s" % (ess, ess < thr))
         if not (ess < thr):                                  # :256, strict; NaN compares false
             return False
-        self._wver += 1                                      # the weights are about to become 0 (:266)
         u0 = api.philox_resample_u0(self.seed, self.step)
-        q_total, pref, ranges, send = plan_exchange(qs, self.n_global, self.offs, u0)
         me, W = self.rank, self.world
+        if sum(int(q) for q in qs) == 0:                     # no representable weight mass: nothing to resample from
+            return False
+        self._wver += 1                                      # the weights are about to become 0 (:266)
+        q_total, pref, ranges, send = plan_exchange(qs, self.n_global, self.offs, u0)
         # Fast path when every shard can park its incoming rows in its extension rows (all ranks evaluate
         # the same predicate from the gathered plan, so no extra collective is needed to agree on it)
         fast = self.ext_caps is not None and not self.force_staged and all(
             sum(send[s][d][1] - send[s][d][0] for s in range(W) if s != d) <= self.ext_caps[d] for d in range(W))
-        if fast and self.use_p2p and self.device.type == "cuda" and W > 1:
-            # the decision was taken here (the Bool is returned), the exchange itself is the asynchronous run's: plan
-            # on the device from the gathered records, ancestors, offspring written into the owning shards' memory
-            # by peer stores over NVLink, a one-word all-reduce as the barrier -- no staging blocks, no all-to-all
-            self._attach_peers()
-            if self._setup_thr != math.inf:                  # device-side plan state: once, unless run_ re-armed it
-                self.ops.async_setup(W, me, self.offs, math.inf)
-                self._setup_thr = math.inf
-            self.ops.async_plan(self._gather_t, u0)
+        if self.device.type == "cuda" and self.use_p2p and (fast or W == 1):
+            # The decision was taken here (the Bool is returned); the exchange itself is only enqueued: plan on the device
+            # from the records in the mailbox, ancestors, offspring written into the owning shards' memory by peer stores
+            # over NVLink, flags as the barrier -- no staging blocks, no all-to-all, no collective
+            self.ops.async_plan(u0, math.inf, 1)
             self.ops.async_sweep()
             self.ops.async_export()
-            if self._barrier_t is None:
-                self._barrier_t = self.torch.zeros(1, dtype=self.torch.int32, device=self.device)
-            self.dist.all_reduce(self._barrier_t, group=self.group)
+            self.ops.async_wait()
             self.ops.async_commit(lse - math.log(self.n_global))   # :263
             return True
         lo, hi = self.ops.systematic_offspring(m, self.bits, pref[me], qs[me], q_total, u0)

@@ -200,29 +200,50 @@ int gb_pf_weight_sums(gb_pf_t *pf, double m_ref, int bits, double *s1, double *s
 int gb_pf_stats_device(gb_pf_t *pf, void **dev_stats, int *n_words);
 int gb_pf_weight_max_device(gb_pf_t *pf);
 int gb_pf_weight_sums_device(gb_pf_t *pf, int bits);
-/* Asynchronous flavour of the whole sharded step (no host round trip; used by ShardedParticleFilter.run_).
- * Offspring owned by another shard are written by a kernel STRAIGHT INTO THAT SHARD'S MEMORY (peer stores over NVLink):
- * rows into the extension rows of its current trace buffer, plus the slot's ancestor index and global parent id.
- *   once   : gb_pf_ipc_export -> all-gather of the bundles -> gb_pf_async_attach_ipc for every peer
- *            (gb_pf_async_attach_local when the peer shard lives in the same process) -> gb_pf_async_setup
- *   per step (all asynchronous on the handle's stream; the host issues the collectives in between):
- *     gb_pf_weight_max_device -> all-reduce(max) of the statistics record's m -> gb_pf_weight_sums_device ->
- *     all-gather of the records -> gb_pf_async_plan (ESS test, log-ML, exchange plan ON THE DEVICE) ->
- *     gb_pf_async_sweep (ancestors) -> gb_pf_async_export (peer stores) -> any tiny collective as a barrier ->
- *     gb_pf_async_step
- *   finish : one device->host read (log_ml_est, #resamples, overflow flag).  Overflow (a shard's extension rows or the
- *            spill buffer too small for the weight skew) invalidates the run: GB_ESTATE. */
+/* Sharded maybe_resample! WITHOUT collectives and without a host round trip: everything the shards tell each
+ * other travels through peer memory over NVLink / NVSwitch, written and awaited by the kernels themselves.
+ *   - every shard owns a small mailbox; the last CTA of the kernel that produced the weights peer-stores the shard's max
+ *     into EVERY mailbox (phase A), the statistics kernel waits for the G maxima, reduces w.r.t. the global max and
+ *     peer-stores (sum e, sum e^2, integer CDF mass) (phase B); a one-CTA kernel waits for the G records and computes the
+ *     ESS test (particle_filter.jl:256), the log-ML update (:263) and the exchange plan -- the same arithmetic on the
+ *     same records on every shard, so all agree without talking;
+ *   - offspring owned by another shard are written by a kernel STRAIGHT INTO THAT SHARD'S MEMORY: rows into the
+ *     extension rows of its current trace buffer, plus the slot's ancestor index and global parent id; its last CTA
+ *     posts a "done" flag (phase C) that the peers wait for before their next particle_filter_step! reads the rows.
+ *   once   : gb_pf_ipc_export -> exchange of the bundles (any transport) -> gb_pf_async_attach_ipc for every peer in
+ *            another process / gb_pf_async_attach_local for peers in this process -> gb_pf_async_setup -> a barrier
+ *            across all shards (the set-up resets the mailbox)
+ *   per run: gb_pf_async_arm(threshold), then per step gb_pf_async_iterate(obs) = gb_pf_xchg_stats -> gb_pf_async_plan ->
+ *            gb_pf_async_sweep -> gb_pf_async_export -> gb_pf_async_wait -> gb_pf_async_step (enqueues only)
+ *   finish : gb_pf_async_finish, one device->host read (log_ml_est, #resamples, overflow / time-out flags).  Overflow (a
+ *            shard's extension rows or spill buffer too small for the weight skew) or a peer that did not answer within
+ *            GENB200_XCHG_TIMEOUT_MS (default 20000) invalidates the run: GB_ESTATE.
+ * Synchronous maybe_resample! (the Bool return needs one host read): gb_pf_xchg_stats -> gb_pf_async_plan(u0, -inf, 0) ->
+ * gb_pf_xchg_read gives the global lse / ESS; the caller decides; gb_pf_async_plan(u0, +inf, 1) -> sweep -> export -> wait ->
+ * gb_pf_async_commit.  Several shards on ONE device (tests): give them one stream and enqueue phase by phase over the shards. */
 int gb_pf_ipc_bundle_bytes(void);
 int gb_pf_ipc_export(gb_pf_t *pf, void *bundle_out, int *nbytes);
 int gb_pf_async_attach_ipc(gb_pf_t *pf, int peer_rank, const void *bundle);
 int gb_pf_async_attach_local(gb_pf_t *pf, int peer_rank, gb_pf_t *peer);
 int gb_pf_async_setup(gb_pf_t *pf, int world, int rank, const int64_t *offs, double ess_threshold);
+int gb_pf_async_arm(gb_pf_t *pf, double ess_threshold);
 int gb_pf_async_cur(const gb_pf_t *pf, int *cur);
-int gb_pf_async_plan(gb_pf_t *pf, const void *dev_gathered, uint32_t u0);
+int gb_pf_xchg_post(gb_pf_t *pf);    /* phase A only (no-op when the producing kernel already posted); implied by gb_pf_xchg_stats */
+int gb_pf_xchg_stats(gb_pf_t *pf);
+/* ess_threshold NaN: the armed one; do_scan != 0 when a sweep follows */
+int gb_pf_async_plan(gb_pf_t *pf, uint32_t u0, double ess_threshold, int do_scan);
 int gb_pf_async_sweep(gb_pf_t *pf);
 int gb_pf_async_export(gb_pf_t *pf);
+int gb_pf_async_wait(gb_pf_t *pf);
 int gb_pf_async_step(gb_pf_t *pf, const double *obs, int nobs);
+int gb_pf_async_iterate(gb_pf_t *pf, const double *obs, int nobs);
 int gb_pf_async_finish(gb_pf_t *pf, int *n_resampled, int *overflow);
+/* global statistics over ALL shards and the decision of the last gb_pf_async_plan (one device->host read) */
+int gb_pf_xchg_read(gb_pf_t *pf, double *lse, double *ess, uint64_t *q_total, int *do_resample);
+/* (no device access) the global max and every shard's integer CDF mass (world entries) as of the last gb_pf_xchg_read */
+int gb_pf_xchg_records(gb_pf_t *pf, double *m_global, uint64_t *q_shard);
+/* the same read + the host-side bookkeeping of a resample the DEVICE decided (gb_pf_async_plan with a finite threshold) */
+int gb_pf_xchg_commit(gb_pf_t *pf, int *did_resample, double *ess);
 /* Offspring of this shard's particles under global-prefix systematic resampling: the shard's particles
  * (integer CDF mass q_local, preceded by q_offset of a global q_total) fill the global slot range
  * [*slot_lo, *slot_hi).  Ancestors of the slots this shard owns itself go straight into its ancestor
@@ -252,6 +273,42 @@ int gb_pf_async_commit(gb_pf_t *pf, double log_ml_increment);
 int gb_pf_export_offspring(gb_pf_t *pf, int64_t k_lo, int64_t k_hi, void *dev_block);
 int gb_pf_import_rows(gb_pf_t *pf, int64_t dst_lo, int64_t count, const void *dev_block);
 int gb_pf_commit_resample(gb_pf_t *pf, double log_ml_increment);
+
+/* ---- ONE filter sharded over several GPUs, driven from the one calling thread ----
+ * gb_spf_* mirror the gb_pf_* entries above over G shards with contiguous global particle ids (the first n % G shards hold
+ * one extra particle).  devices: G device indices (NULL: shard r on device r; indices may repeat -- several shards on one
+ * GPU).  Results are bit-identical to the single-GPU filter for every G: Philox noise is keyed by the global particle id
+ * and maybe_resample! is global-prefix systematic resampling over the exact integer CDF.  No NCCL, no MPI: the shards
+ * exchange through peer memory (see "Sharded maybe_resample! WITHOUT collectives" above); needs peer access between the
+ * devices (NVLink / NVSwitch or PCIe P2P).  Resampler: systematic. */
+typedef struct gb_spf gb_spf_t;
+int gb_spf_create(const gb_model_t *m, int64_t n_global, int dtype, uint64_t seed, int nshards, const int *devices, gb_spf_t **out);
+int gb_spf_generate(gb_spf_t *spf, const double *obs, int nobs, int proposal_kind, const double *pargs, int npargs);
+int gb_spf_initialize(const gb_model_t *m, int64_t n, int dtype, uint64_t seed, int nshards, const int *devices, const double *obs,
+                      int nobs, int proposal_kind, const double *pargs, int npargs, gb_spf_t **out);
+int gb_spf_step(gb_spf_t *spf, const double *obs, int nobs, int proposal_kind, const double *pargs, int npargs);
+int gb_spf_maybe_resample(gb_spf_t *spf, double ess_threshold, int *did_resample);
+int gb_spf_set_resample_noise(gb_spf_t *spf, int use_u0, uint32_t u0);
+int gb_spf_run(gb_spf_t *spf, int T, const double *obs, int nobs, double ess_threshold, int *n_resampled);
+int gb_spf_log_ml_estimate(gb_spf_t *spf, double *out);
+int gb_spf_get_log_ml_est(gb_spf_t *spf, double *out);
+int gb_spf_get_ess(gb_spf_t *spf, double *ess_out, double *lse_out);
+int gb_spf_get_log_weights(gb_spf_t *spf, double *out_n);
+int gb_spf_get_log_increments(gb_spf_t *spf, double *out_n);
+int gb_spf_get_state(gb_spf_t *spf, int field, double *out_n);
+int gb_spf_get_parents(gb_spf_t *spf, int64_t *out_n);
+int gb_spf_num_shards(const gb_spf_t *spf, int *nshards);
+int gb_spf_shard(gb_spf_t *spf, int r, gb_pf_t **shard /* borrowed */, int64_t *pid_offset);
+int gb_spf_num_particles(const gb_spf_t *spf, int64_t *n);
+int gb_spf_step_index(const gb_spf_t *spf, int *step);
+int gb_spf_sync(gb_spf_t *spf);
+void gb_spf_free(gb_spf_t *spf);
+/* importance_sampling (importance.jl:20-59) with the samples sharded: only the log-sum-exp crosses devices (cfg 4) */
+int gb_spf_importance_sampling(const gb_model_t *m, int64_t n, int dtype, uint64_t seed, int nshards, const int *devices,
+                               const double *obs, int nobs, int proposal_kind, const double *pargs, int npargs,
+                               double *lognormw_out, double *lml_out, gb_spf_t **spf_out);
+/* global-prefix systematic resampling of a raw log-weight array sharded over the devices (cfg 5); ancestors 0-based */
+int gb_spf_resample(const double *logw, int64_t n, int dtype, int nshards, const int *devices, uint32_t u0, int64_t *anc_out);
 
 /* ---- importance_sampling (importance.jl:20-59) ---- */
 /* lognormw_out: n doubles (may be NULL); lml_out: log ML estimate; pf_out (may be NULL) receives the

@@ -488,7 +488,15 @@ struct go_pf {
   double log_ml_est; /* :39 */
   int64_t *parents;  /* :40, 1-based */
   int mh_ok;         /* new_state still holds the parents of `state` (rows aligned) */
+  int storage_f32;   /* GB_F32 storage model: traces, log weights and increments are rounded to float when stored */
 };
+
+/* Storage model of the engine's GB_F32 filters (this repo's extension; Gen itself is Float64 only): the per-particle
+ * arithmetic below stays fp64, but every value written to the particle store -- trace fields, log weights, log
+ * incremental weights -- is rounded to single precision first.  Applies to filters created AFTER the call. */
+static int g_storage_f32 = 0;
+void go_set_storage_f32(int on) { g_storage_f32 = on != 0; }
+static inline double st_round(const go_pf_t *pf, double v) { return pf->storage_f32 ? (double)(float)v : v; }
 
 int go_model_state_dim(int kind, const double *p) {
   switch (kind) {
@@ -638,7 +646,7 @@ static void run_particles(go_pf_t *pf, int t, const double *obs, int pk, const d
       }
     }
     w_out[i] = particle_transition(kind, pf->params, t, prev, next, obs, pk, pa, eps, us);
-    for (int s = 0; s < S; s++) pf->new_state[(int64_t)s * n + i] = next[s];
+    for (int s = 0; s < S; s++) pf->new_state[(int64_t)s * n + i] = st_round(pf, next[s]);
   }
 }
 static void swap_traces(go_pf_t *pf) { double *t = pf->state; pf->state = pf->new_state; pf->new_state = t; }
@@ -651,6 +659,7 @@ go_pf_t *go_pf_init(int kind, const double *params, int nparams, int64_t n, uint
   if (S < 1 || S > 64 || n < 1) return NULL;
   go_pf_t *pf = (go_pf_t *)calloc(1, sizeof(*pf));
   pf->kind = kind; pf->nparams = nparams; pf->S = S; pf->n = n; pf->seed = seed; pf->step = 0;
+  pf->storage_f32 = g_storage_f32;
   pf->params = (double *)malloc((size_t)nparams * 8);
   memcpy(pf->params, params, (size_t)nparams * 8);
   pf->state = (double *)calloc((size_t)S * n, 8);
@@ -658,6 +667,8 @@ go_pf_t *go_pf_init(int kind, const double *params, int nparams, int64_t n, uint
   pf->logw = (double *)malloc((size_t)n * 8);
   pf->parents = (int64_t *)malloc((size_t)n * 8);
   run_particles(pf, 0, obs, pk, pa, normals, uniforms, pf->logw); /* :127-131, :149-151 */
+  if (pf->storage_f32)
+    for (int64_t i = 0; i < n; i++) pf->logw[i] = (double)(float)pf->logw[i];
   swap_traces(pf);
   pf->log_ml_est = 0.0;                                            /* :133, :153 */
   for (int64_t i = 0; i < n; i++) pf->parents[i] = i + 1;         /* collect(1:num_particles) */
@@ -671,7 +682,10 @@ int go_pf_step(go_pf_t *pf, const double *obs, int pk, const double *pa, const d
   pf->step += 1;
   run_particles(pf, pf->step, obs, pk, pa, normals, uniforms, incr);
 #pragma omp parallel for schedule(static) if (g_threads > 1)
-  for (int64_t i = 0; i < pf->n; i++) pf->logw[i] += incr[i];     /* :199, :231 */
+  for (int64_t i = 0; i < pf->n; i++) {
+    pf->logw[i] = st_round(pf, pf->logw[i] + incr[i]);            /* :199, :231 */
+    incr[i] = st_round(pf, incr[i]);
+  }
   swap_traces(pf);                                                 /* :203-205, :234-237 */
   pf->mh_ok = 1;
   if (!incr_out) free(incr);
@@ -714,6 +728,25 @@ int go_pf_maybe_resample(go_pf_t *pf, double ess_threshold, int kind, int use_gi
   swap_traces(pf);                                                 /* :270-272 */
   pf->mh_ok = 0;
   free(anc);
+  return 1;
+}
+/* The resampling branch of maybe_resample! (particle_filter.jl:261-272) with the ancestors GIVEN (1-based `parents`)
+ * instead of drawn: log_ml_est is updated from this filter's own weights, traces are gathered, weights reset.  Used to
+ * keep two filters on the same genealogy while each keeps its own arithmetic (fp32-storage engine vs fp64 oracle). */
+int go_pf_resample_given(go_pf_t *pf, const int64_t *parents) {
+  const int64_t n = pf->n;
+  for (int64_t i = 0; i < n; i++)
+    if (parents[i] < 1 || parents[i] > n) return -1;
+  double lse = go_logsumexp(pf->logw, n);
+  pf->log_ml_est += lse - log((double)n);                          /* :263 */
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+  for (int64_t i = 0; i < n; i++) {                                /* :264-267 */
+    pf->parents[i] = parents[i];
+    for (int s = 0; s < pf->S; s++) pf->new_state[(int64_t)s * n + i] = pf->state[(int64_t)s * n + (parents[i] - 1)];
+    pf->logw[i] = 0.0;
+  }
+  swap_traces(pf);                                                 /* :270-272 */
+  pf->mh_ok = 0;
   return 1;
 }
 /* ---- MH rejuvenation of the latest latent choices (src/inference/mh.jl) ----------------------------------------
@@ -827,7 +860,7 @@ int64_t go_pf_rejuvenate(go_pf_t *pf, int move, const double *obs, double drift_
     if (alpha_out) alpha_out[i] = alpha;
     if (accepted_out) accepted_out[i] = (uint8_t)acc;
     if (acc) {
-      for (int s = 0; s < S; s++) pf->state[(int64_t)s * n + i] = next[s];
+      for (int s = 0; s < S; s++) pf->state[(int64_t)s * n + i] = st_round(pf, next[s]);
       total++;
     }
   }

@@ -82,6 +82,9 @@ int go_model_num_uniforms(int kind, const double *params, int proposal_kind, int
 int go_model_num_obs(int kind, const double *params);
 
 void go_set_threads(int nthreads);
+/* GB_F32 storage model (this repo's extension): filters created after go_set_storage_f32(1) round every stored trace
+ * field, log weight and log incremental weight to single precision; the arithmetic stays fp64. */
+void go_set_storage_f32(int on);
 int go_get_max_threads(void);
 
 /* particle_filter.jl:118-154.  normals/uniforms: pre-drawn [ndraw][n] (NULL => Philox(seed)). */
@@ -94,6 +97,8 @@ int go_pf_step(go_pf_t *pf, const double *obs, int proposal_kind, const double *
 /* particle_filter.jl:249-275 with the integer-CDF resamplers; u64s only for multinomial validation */
 int go_pf_maybe_resample(go_pf_t *pf, double ess_threshold, int kind, int use_given_u0, uint32_t u0,
                          const uint64_t *u64s, double *ess_out);
+/* the resampling branch of maybe_resample! (:261-272) with GIVEN 1-based parents (validation: shared genealogy) */
+int go_pf_resample_given(go_pf_t *pf, const int64_t *parents);
 /* MH rejuvenation of every particle's latest latent choices: move 0 = mh(trace, selection) (mh.jl:16-27),
  * move 1 = mh(trace, gaussian-drift proposal, (drift_std,)) (mh.jl:37-58).  Returns #accepted, -1 if unsupported. */
 int64_t go_pf_rejuvenate(go_pf_t *pf, int move, const double *obs, double drift_std, uint32_t move_index,

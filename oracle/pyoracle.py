@@ -64,10 +64,12 @@ def lib():
             "go_model_num_uniforms": (i, [i, _dp, i, i]),
             "go_model_num_obs": (i, [i, _dp]),
             "go_set_threads": (None, [i]),
+            "go_set_storage_f32": (None, [i]),
             "go_get_max_threads": (i, []),
             "go_pf_init": (vp, [i, _dp, i, i64, u64, _dp, i, _dp, _dp, _dp]),
             "go_pf_step": (i, [vp, _dp, i, _dp, _dp, _dp, _dp]),
             "go_pf_maybe_resample": (i, [vp, d, i, i, u32, _u64p, _dp]),
+            "go_pf_resample_given": (i, [vp, _i64p]),
             "go_pf_rejuvenate": (i64, [vp, i, _dp, d, u32, _dp, _dp, _dp, C.POINTER(C.c_uint8)]),
             "go_pf_log_ml_estimate": (d, [vp]),
             "go_pf_log_weights": (_dp, [vp]),
@@ -233,6 +235,12 @@ class OraclePF:
         rc = lib().go_pf_step(self._p, op, proposal_kind, gp, np_, up, incr.ctypes.data_as(_dp))
         assert rc == 0
         return incr
+
+    def resample_given(self, parents):
+        """The resampling branch of maybe_resample! with the given 1-based parents (shared genealogy, own weights)."""
+        p = np.ascontiguousarray(parents, dtype=np.int64)
+        rc = lib().go_pf_resample_given(self._p, p.ctypes.data_as(_i64p))
+        assert rc == 1, rc
 
     def maybe_resample(self, ess_threshold=None, kind=RESAMPLE_SYSTEMATIC, u0=None, u64s=None):
         if ess_threshold is None:

@@ -1,7 +1,9 @@
-"""Multi-process NCCL check (not a pytest file: needs N GPUs).  Run under torchrun on a multi-GPU box:
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/run_sharded_nccl.py
-Every rank drives its shard through ShardedParticleFilter; rank 0 also runs the same filter on one GPU
-through the ordinary API and the results must be bit-identical."""
+"""One process per GPU (needs N >= 2 GPUs; spawned by tests/test_gpu_multigpu.py::test_multiprocess_ipc_sharded_filter):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/run_sharded_multiproc.py
+Every rank drives its shard through ShardedParticleFilter -- peer-memory exchange over CUDA IPC pointers (no collective
+in the step), the all-to-all-v fallback and the staged fallback; rank 0 also runs the same filter on one GPU through the
+ordinary API and the results must be bit-identical.  torch.distributed only carries the IPC handles, the result gathers
+and (fallback paths) the block exchange."""
 import os
 import sys
 
@@ -47,10 +49,10 @@ def main():
                 nacc1 += g.rejuvenate_(st, ys[t], move="drift" if t % 2 else "resimulate", drift_std=1e-3)
             ok = nacc == nacc1 and nacc > 0 and all(np.array_equal(cols[f], st.get_state(f)) for f in range(4)) and np.array_equal(par, st.parents)
             ok = ok and abs(lml - g.log_ml_estimate(st)) <= 1e-10 * abs(lml)
-            print("NCCL sharded check world=%d n=%d staged=%s p2p=%s resamples=%d mh-accepts=%d: %s (log ML %.12f)" % (world, n, staged, p2p, nres, nacc, "OK" if ok else "MISMATCH", lml))
+            print("multi-process sharded check world=%d n=%d staged=%s p2p=%s resamples=%d mh-accepts=%d: %s (log ML %.12f)" % (world, n, staged, p2p, nres, nacc, "OK" if ok else "MISMATCH", lml))
             if not ok:
                 sys.exit(1)
-    # asynchronous run (device-side plan, fixed-capacity equal-split all-to-all) vs the fused single-GPU run
+    # asynchronous run (device-side plan and exchange, nothing but enqueues on the host) vs the fused single-GPU run
     for n in (100003, 4_000_000):
         ys = F.bearings_series(10)
         spf = sharded.ShardedParticleFilter(g.bearings_model(), n, seed=9).initialize(ys[0])
@@ -63,7 +65,7 @@ def main():
             nres1 = g.particle_filter_run_(st, ys[1:], ess_threshold=n / 2)
             ok = nres == nres1 and all(np.array_equal(cols[f], st.get_state(f)) for f in range(4)) and np.array_equal(par, st.parents)
             ok = ok and abs(lml - g.log_ml_estimate(st)) <= 1e-10 * abs(lml)
-            print("NCCL async sharded run world=%d n=%d resamples=%d: %s (log ML %.12f)" % (world, n, nres, "OK" if ok else "MISMATCH", lml))
+            print("multi-process async sharded run world=%d n=%d resamples=%d: %s (log ML %.12f)" % (world, n, nres, "OK" if ok else "MISMATCH", lml))
             if not ok:
                 sys.exit(1)
     dist.destroy_process_group()

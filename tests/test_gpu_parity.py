@@ -184,6 +184,44 @@ def test_resampler_properties_large(g):
     assert np.array_equal(g.resample(np.zeros(n), "systematic", u0=999), np.arange(n))
 
 
+def test_cfg5_resamplers_full_size(g, O):
+    """BASELINE.json configs[4] at N = 10^8 log weights: systematic and residual ancestors bit-exact against the sequential
+    oracle (O(N) sweeps: a few seconds each on the host); multinomial -- whose oracle is a 27-step binary search per draw
+    over an 800 MB CDF -- exact on 2*10^5 sampled slots against an independent numpy searchsorted over the oracle's integer
+    CDF, plus the size-independent properties (range, unbiased counts)."""
+    n = 10 ** 8
+    lw = F.resample_logw(n, "normal")
+    u0 = 2718281828
+    for kind in ("systematic", "residual"):
+        got = g.resample(lw, kind, u0=u0)
+        exp = O.resample(okind(O, kind), lw, u0=u0)
+        assert np.array_equal(got, exp), (kind, np.flatnonzero(got != exp)[:5])
+        del got, exp
+    # multinomial: Philox-keyed uniforms (integer exact on both sides)
+    seed, step = 31, 4
+    anc = g.resample(lw, "multinomial", seed=seed, step=step)
+    assert anc.min() >= 0 and anc.max() < n
+    m = float(lw.max())
+    q, qn = O.quantized_weights(lw)
+    cdf = np.cumsum(q, dtype=np.uint64)
+    assert int(cdf[-1]) == int(qn)
+    rng = np.random.default_rng(5)
+    ks = np.unique(np.concatenate([rng.integers(0, n, size=200000), [0, 1, n - 2, n - 1]]))
+    us = np.concatenate([O.philox_multinomial_u64(seed, step, int(k), 1) for k in ks[:2000]])          # spot slots, exact stream
+    taus = np.array([(int(u) * int(qn)) >> 64 for u in us], dtype=np.uint64)
+    assert np.array_equal(anc[ks[:2000]], np.searchsorted(cdf, taus, side="right"))
+    # contiguous block of slots (vectorised stream export) for the bulk of the sampled check
+    k0 = int(rng.integers(0, n - 200000))
+    us = O.philox_multinomial_u64(seed, step, k0, 200000)
+    taus = np.array([(int(u) * int(qn)) >> 64 for u in us], dtype=np.uint64)
+    assert np.array_equal(anc[k0:k0 + 200000], np.searchsorted(cdf, taus, side="right"))
+    w = np.exp(lw - m)
+    w /= w.sum()
+    cnt = np.bincount(anc, minlength=n)
+    top = np.argsort(w)[-1000:]
+    assert abs(cnt[top].sum() - n * w[top].sum()) < 6 * math.sqrt(n * w[top].sum())                    # unbiased counts
+
+
 def test_full_size_bearings_filter_properties(g):
     """BASELINE.json configs[2] at its full size (N = 10^8, fp64), where the sequential oracle is out of reach: the
     size-independent properties of one maybe_resample! + particle_filter_step! and the fused run."""
@@ -333,42 +371,118 @@ def test_pf_philox_mode_matches_oracle_on_exported_noise(g, O, name):
     assert abs(g.log_ml_estimate(st) - ref.log_ml_estimate()) <= RTOL64 * abs(ref.log_ml_estimate())
 
 
+def _series(name, T):
+    return {"lgssm": F.lgssm_series, "sv": F.sv_series, "bearings": F.bearings_series}[name](T)
+
+
 @pytest.mark.parametrize("name", ["lgssm", "sv", "bearings"])
 def test_pf_fp32_mode(g, O, name):
-    """fp32 store and arithmetic: log weights / log-ML within 1e-5 relative of the fp64 oracle on the
-    same (fp32-representable) noise, resampling forced to follow the oracle's ancestors."""
-    model, okind_m, params, ys, _, _ = model_zoo(g, O)[name]
-    n = 20000
+    """GB_F32 filters store traces / log weights / noise in fp32 and evaluate the transition in fp64 on the widened
+    values (csrc/models.cuh Arith).  60 steps WITHOUT any resynchronisation against
+      (a) the oracle under the same storage model (oracle go_set_storage_f32: fp64 arithmetic, stored values rounded to
+          float): traces and ancestors bit-exact, log incremental weights / log weights / log-ML within 1e-5 (they agree
+          to ~1e-7: one float rounding of the stored value);
+      (b) the plain fp64 oracle (Gen's arithmetic and storage) on the same noise and the same genealogy (it resamples
+          with the engine's ancestors but keeps its own fp64 traces and weights -- two free-running filters whose weights
+          differ by 1e-7 pick different ancestors at a few slot boundaries per resample, which moves log-ML by O(1/N) per
+          flip: Monte-Carlo noise, not arithmetic): log-ML within 1e-5 at every step; per-particle log weights within
+          1e-5 for the contracting models (lgssm, sv).
+    For the bearings model per-particle agreement with (b) is limited by the storage format, not by the arithmetic: one
+    float rounding of a position (2^-25) moves the bearing by 3e-8 rad, the likelihood's curvature (1/sigma = 200)
+    turns that into ~2e-5 of log weight, and since positions integrate the velocities the roundings accumulate along
+    the trajectory: after 60 steps the positions of 20000 particles are off by up to ~1e-6 (5 sigma of
+    the accumulated roundings), i.e. up to ~6e-3 of log weight for a particle 3 sigma from the observation.  Bound asserted
+    here 2e-2, measured value printed."""
+    model, okind_m, params, _, _, _ = model_zoo(g, O)[name]
+    T, n = 60, 20000
+    ys = _series(name, T + 1)
     rng = np.random.default_rng(3)
     nn0, nn1 = model.num_normals(True), model.num_normals(False)
     st = g.create_particle_filter(model, n, dtype="f32")
     eps = rng.standard_normal((nn0, n)).astype(np.float32).astype(np.float64)
     st.set_noise(eps)
     g.generate_(st, ys[0])
-    ref = O.OraclePF.init(okind_m, params, n, [ys[0]], normals=eps)
-    assert close(st.log_weights, ref.log_weights, RTOL32 * 20)
-    for t in range(1, 6):
-        # keep both sides on the same ancestors: feed the engine's fp32 log weights to the oracle
-        ref.log_weights = st.log_weights
+    O.lib().go_set_storage_f32(1)
+    try:
+        ref = O.OraclePF.init(okind_m, params, n, [ys[0]], normals=eps)
+    finally:
+        O.lib().go_set_storage_f32(0)
+    ref64 = O.OraclePF.init(okind_m, params, n, [ys[0]], normals=eps)
+    assert close(st.log_weights, ref.log_weights, RTOL32)
+    nres, gap64 = 0, 0.0
+    for t in range(1, T + 1):
+        thr = n if t % 3 else n / 2                                            # forced and ESS-triggered resamples
         st.set_resample_noise(u0=1234 + t)
-        did = g.maybe_resample_(st, ess_threshold=n, resampler="systematic")
-        did_ref = ref.maybe_resample(ess_threshold=n, kind=O.RESAMPLE_SYSTEMATIC, u0=1234 + t)
-        assert did and did_ref
-        assert np.array_equal(st.parents, ref.parents)                          # integer CDF: exact in fp32 too
+        did = g.maybe_resample_(st, ess_threshold=thr, resampler="systematic")
+        assert did == ref.maybe_resample(ess_threshold=thr, kind=O.RESAMPLE_SYSTEMATIC, u0=1234 + t)
+        nres += did
+        if did:
+            assert np.array_equal(st.parents, ref.parents), t                   # integer CDF of the same stored weights
+            ref64.resample_given(ref.parents)
         eps = rng.standard_normal((nn1, n)).astype(np.float32).astype(np.float64)
         st.set_noise(eps)
         incr, = g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t])
         incr_ref = ref.step([ys[t]], normals=eps)
-        # per-particle weights: fp32 state / atan2f error is amplified by the likelihood's curvature (1/sigma = 200
-        # for the bearings model: measured 1.1e-4 there, 7e-7 for SV); the 1e-5 bar applies to the log-ML above
-        assert np.max(np.abs(incr - incr_ref) / np.maximum(1.0, np.abs(incr_ref))) < 2e-3
-        lml, lml_ref = g.log_ml_estimate(st), ref.log_ml_estimate()
-        # north_star: log-ML within 1e-5 relative in fp32 (measured worst case: 1.9e-6, bearings; tools/fp32_check.py)
-        assert abs(lml - lml_ref) <= RTOL32 * max(1.0, abs(lml_ref))
-        # resync the oracle's state so errors do not compound through the nonlinear dynamics
-        for f in range(model.state_dim):
-            s = st.get_state(f)
-            np.ctypeslib.as_array(O.lib().go_pf_state(ref._p, f), shape=(n,))[:] = s
+        incr64 = ref64.step([ys[t]], normals=eps)
+        assert close(incr, incr_ref, RTOL32), (t, np.max(np.abs(incr - incr_ref) / np.maximum(1.0, np.abs(incr_ref))))
+        gap64 = max(gap64, float(np.max(np.abs(incr - incr64) / np.maximum(1.0, np.abs(incr64)))))
+        assert close(st.log_weights, ref.log_weights, RTOL32), t
+        lml, lml_ref, lml64 = g.log_ml_estimate(st), ref.log_ml_estimate(), ref64.log_ml_estimate()
+        assert abs(lml - lml_ref) <= RTOL32 * max(1.0, abs(lml_ref)), (t, lml, lml_ref)
+        # north_star: log-ML within 1e-5 relative of the fp64 filter
+        assert abs(lml - lml64) <= RTOL32 * max(1.0, abs(lml64)), (t, lml, lml64)
+    assert nres >= T // 3
+    for f in range(model.state_dim):
+        assert np.array_equal(st.get_state(f), ref.state(f)), f               # stored traces bit-exact after 60 steps
+    print("fp32 %s: worst per-particle |incr - incr_fp64| / max(1, |incr_fp64|) over %d steps = %.2e" % (name, T, gap64))
+    assert gap64 <= (2e-2 if name == "bearings" else RTOL32), gap64
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_cfg2_stochastic_volatility_full_size(g, O, dtype):
+    """BASELINE.json configs[1]: stochastic volatility, N = 10^6, here T = 200 of the 1000 steps (the oracle replays every
+    step on the host), production (Philox) noise exported from the device and shared with the oracle, systematic
+    resampling at ESS < N/2, no resynchronisation.  fp64: traces and ancestors bit-exact, log weights / log-ML within
+    1e-10.  fp32: the same against the oracle under the fp32 storage model, and log-ML within 1e-5 of the plain fp64
+    oracle run on the same noise and genealogy (test_pf_fp32_mode explains why the ancestors are shared)."""
+    n, T, seed = 10 ** 6, 200, 20241
+    model, ys = g.sv_model(**F.SV), F.sv_series(T + 1)
+    f32 = dtype == "f32"
+    O.lib().go_set_threads(O.lib().go_get_max_threads())
+    try:
+        st = g.initialize_particle_filter(model, (0,), ys[0], n, dtype=dtype, seed=seed)
+        e0 = g.philox_normals(seed, 0, 0, n, 1, dtype=dtype)
+        O.lib().go_set_storage_f32(1 if f32 else 0)
+        ref = O.OraclePF.init(O.MODEL_SV, F.sv_params(), n, [ys[0]], normals=e0)
+        O.lib().go_set_storage_f32(0)
+        ref64 = O.OraclePF.init(O.MODEL_SV, F.sv_params(), n, [ys[0]], normals=e0) if f32 else None
+        tol = RTOL32 if f32 else RTOL64
+        nres = 0
+        for t in range(1, T + 1):
+            u0 = g.philox_resample_u0(seed, t - 1)
+            did = g.maybe_resample_(st, resampler="systematic")
+            assert did == ref.maybe_resample(kind=O.RESAMPLE_SYSTEMATIC, u0=u0), t
+            if ref64 is not None and did:
+                ref64.resample_given(ref.parents)            # same genealogy, own fp64 traces and weights
+            nres += did
+            g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+            e = g.philox_normals(seed, t, 0, n, 1, dtype=dtype)
+            ref.step([ys[t]], normals=e)
+            if ref64 is not None:
+                ref64.step([ys[t]], normals=e)
+            if t % 20 == 0 or t == T:
+                lml, lml_ref = g.log_ml_estimate(st), ref.log_ml_estimate()
+                assert abs(lml - lml_ref) <= tol * max(1.0, abs(lml_ref)), (t, lml, lml_ref)
+                if ref64 is not None:
+                    lml64 = ref64.log_ml_estimate()
+                    assert abs(lml - lml64) <= RTOL32 * max(1.0, abs(lml64)), (t, lml, lml64)
+        assert nres >= 10
+        assert np.array_equal(st.get_state(0), ref.state(0))                   # traces bit-exact after 200 steps
+        assert np.array_equal(st.parents, ref.parents)
+        assert close(st.log_weights, ref.log_weights, tol)
+    finally:
+        O.lib().go_set_storage_f32(0)
+        O.lib().go_set_threads(1)
 
 
 # ---------------------------------------------------------------------------------------------

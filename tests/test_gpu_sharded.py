@@ -1,7 +1,7 @@
 """The sharded pieces of the C ABI on one GPU: K shards of one filter live in the same process and the
 host plays the collectives (sums / prefix / row exchange by device copies).  The resampled filter must be
 bit-identical to the single-shard filter and to the oracle: global-prefix systematic resampling is
-partition independent by construction.  (Real multi-process NCCL runs: tests/run_sharded_nccl.py under
+partition independent by construction.  (Real multi-process NCCL runs: tests/run_sharded_multiproc.py under
 `gpurun --gpus 2`, and bench.py --gpus N.)"""
 import math
 
@@ -154,13 +154,12 @@ def test_sharded_class_world1(g, O):
 
 
 def run_async_in_process(g, model, n, K, ys, seed, thr):
-    """K shards in one process driven through the ASYNCHRONOUS sharded entries: the host plays the two small
-    collectives with device copies; offspring go shard-to-shard by the export kernel's peer stores (here: pointers of
-    the other handles in the same process)."""
-    import torch
-    from genb200 import sharded, _lib as L
+    """K shards in one process (one GPU, one stream) driven through the ASYNCHRONOUS sharded entries.  Nothing is played
+    by the host: the shards' maxima, sums and "rows delivered" flags go through the peer-memory mailboxes, offspring
+    through the export kernel's peer stores (here: pointers of the other handles in the same process).  With one
+    stream the host enqueues phase by phase over the shards, so every post precedes the wait that needs it."""
+    from genb200 import sharded
     counts, offs = sharded.shard_bounds(n, K)
-    bits = L.lib().gb_quant_bits(n)
     shards = [g.create_particle_filter(model, counts[r], seed=seed, n_global=n, pid_offset=offs[r]) for r in range(K)]
     ops = [sharded.ShardOps(s) for s in shards]
     for s in shards:
@@ -169,26 +168,17 @@ def run_async_in_process(g, model, n, K, ys, seed, thr):
         for d, p in enumerate(ops):
             if d != r:
                 o.attach_local(d, p)
+    for r, o in enumerate(ops):
         o.async_setup(K, r, offs, thr)
-    stats = [o.stats_tensor(torch) for o in ops]
-    gathered = torch.empty(K * stats[0].numel(), dtype=torch.int64, device="cuda")
     for t in range(1, len(ys)):
-        for o in ops:
-            o.weight_max_device()
-        m = torch.stack([st[0:1].view(torch.float64) for st in stats]).max()          # all-reduce(max)
-        for st in stats:
-            st[0:1].view(torch.float64).fill_(m)
-        for o in ops:
-            o.weight_sums_device(bits)
-        gathered.copy_(torch.cat(stats))                                                # all-gather
         u0 = g.philox_resample_u0(seed, t - 1)
-        for o in ops:
-            o.async_plan(gathered, u0)
-            o.async_sweep()
-        for o in ops:
-            o.async_export()                                                            # peer stores
-        for o in ops:                                                                   # (barrier: same stream here)
-            o.async_step(ys[t])
+        for phase in ("xchg_post", "xchg_stats", ("async_plan", u0, float("nan"), 1), "async_sweep", "async_export", "async_wait",
+                      ("async_step", ys[t])):
+            for o in ops:
+                if isinstance(phase, tuple):
+                    getattr(o, phase[0])(*phase[1:])
+                else:
+                    getattr(o, phase)()
     nres = [o.async_finish() for o in ops]
     assert len(set(nres)) == 1
     cols = [np.concatenate([s.get_state(f) for s in shards]) for f in range(model.state_dim)]
@@ -227,22 +217,14 @@ def test_async_sharded_overflow_is_reported(g):
     shards[1].log_weights = np.full(counts[1], -800.0)            # shard 1 has no weight: all its slots come from shard 0
     for r, o in enumerate(ops):
         o.attach_local(1 - r, ops[1 - r])
+    for r, o in enumerate(ops):
         o.async_setup(K, r, offs, n + 1)
-    stats = [o.stats_tensor(torch) for o in ops]
-    for o in ops:
-        o.weight_max_device()
-    m = torch.stack([st[0:1].view(torch.float64) for st in stats]).max()
-    for st in stats:
-        st[0:1].view(torch.float64).fill_(m)
-    for o in ops:
-        o.weight_sums_device(L.lib().gb_quant_bits(n))
-    gathered = torch.cat(stats).clone()
-    for o in ops:
-        o.async_plan(gathered, 7)
-        o.async_sweep()
-    for o in ops:
-        o.async_export()
-    for o in ops:
-        o.async_step(ys[1])
+    for phase in ("xchg_post", "xchg_stats", ("async_plan", 7, float("nan"), 1), "async_sweep", "async_export", "async_wait",
+                  ("async_step", ys[1])):
+        for o in ops:
+            if isinstance(phase, tuple):
+                getattr(o, phase[0])(*phase[1:])
+            else:
+                getattr(o, phase)()
     with pytest.raises(g.GenB200Error):
         ops[0].async_finish()
