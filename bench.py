@@ -5,8 +5,10 @@ Workload (config.workload): BASELINE.json configs[2], the 2-D bearings-only trac
 (docs/src/tutorials/smc.md:607-661; 4-D state, nonlinear observation) bootstrap particle filter with
 N = 10^8 particles (fp64) and systematic resampling EVERY step.  One "step" = one particle-filter
 step over all particles: maybe_resample! (ESS, ancestors, resampled-trace gather) followed by
-particle_filter_step! (propose + weight + log-sum-exp partials).  At --gpus G > 1 the particles are
-sharded G ways (one process per GPU, global-prefix systematic resampling, NCCL exchange).
+particle_filter_step! (propose + weight + log-sum-exp partials).  At --gpus G > 1 the 10^8 particles are
+sharded G ways (strong scaling, as BASELINE.json words the config; one process per GPU, global-prefix
+systematic resampling, every exchange through peer memory inside the kernels -- no collective in the
+step); a weak-scaling run (10^8 per GPU) rides in the same JSON line under "weak".
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl genb200|reference]
                     [--particles P] [--dtype f64|f32] [--scaling strong|weak]
@@ -167,8 +169,10 @@ def run_reference(args):
     out = {
         "impl": "reference", "metric": "particle-steps/sec", "value": val, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n_total=args.particles),
+        "higher_is_better": True, "scaling": args.scaling or ("strong" if args.gpus > 1 else "weak"), "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": dict(workload_config(args, n_total=n), particles_note="the CPU arm times a bounded sample of the 1e8-particle "
+                       "workload (rate is per particle-step, i.e. size-normalised)", workload_particles=int(args.particles)),
         "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample,
                          "note": "Gen.jl is pure Julia and Julia is absent from this image; this is the C oracle "
                                  "restating Gen's particle filter (optimistic stand-in: no trace allocation/dispatch)"},
@@ -219,6 +223,266 @@ def log_ml_error_check(g):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def ncu_traffic(dtype, S):
+    """Measured DRAM bytes per particle of the dominant kernel from THIS round's committed `ncu --set full` capture
+    (profiles/r2_step_kernel_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep): applies to the captured
+    configuration only (same dtype / state size); anything else reports null."""
+    p = os.path.join(ROOT, "profiles", "r2_step_kernel_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d.get("dtype") == dtype and int(d.get("state_dim", -1)) == S:
+            return d
+    except Exception:
+        pass
+    return None
+
+
+def time_bearings_filter(g, torch, dist, args, n_total, world, zs, steps, warmup, sampler=None):
+    """Device-timed throughput + the end-to-end loop of the bearings filter at n_total particles over `world` ranks."""
+    from genb200 import _lib as L
+    thr = n_total + 1   # ESS <= N < N + 1: resample every step (the accounting of SURVEY.md section 8d)
+    model = g.bearings_model()
+    if world == 1:
+        pf = g.initialize_particle_filter(model, (0,), zs[0], n_total, dtype=args.dtype, seed=20242)
+
+        def step(t, sync_scalar=False):
+            g.maybe_resample_(pf, ess_threshold=thr, resampler="systematic")
+            g.particle_filter_step_(pf, (t,), (g.UnknownChange,), zs[t], return_incr=False)
+            if sync_scalar:
+                return g.log_ml_estimate(pf)
+
+        def run_many(t0, k):
+            for t in range(t0, t0 + k):
+                step(t)
+        state, spf = pf, None
+    else:
+        from genb200 import sharded
+        spf = sharded.ShardedParticleFilter(model, n_total, dtype=args.dtype, seed=20242)
+        spf.initialize(zs[0])
+
+        def step(t, sync_scalar=False):
+            spf.maybe_resample_(ess_threshold=thr)
+            spf.particle_filter_step_((t,), zs[t])
+            if sync_scalar:
+                return spf.log_ml_estimate()
+
+        def run_many(t0, k):
+            # device-resident path: statistics exchange, plan, ESS test, log-ML and offspring exchange on the devices
+            spf.run_([zs[t] for t in range(t0, t0 + k)], ess_threshold=thr)
+        state = spf.local
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t = 1
+    run_many(t, warmup)
+    t += warmup
+    state.sync()
+    # ---- device-timed region: value (state resident in HBM; per step the host passes the 8-byte observation and, on one
+    #      GPU, reads the 48-byte weight statistics maybe_resample!'s Bool needs) ----
+    state.enable_timing(True)
+    state.get_timing()
+    if sampler is not None:
+        sampler.wait_ready()
+    barrier()
+    w0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    run_many(t, steps)
+    t += steps
+    ev1.record()
+    barrier()
+    clocks = None
+    if sampler is not None:
+        sampler.window(w0, time.perf_counter())
+        clocks = sampler.stop()          # (before the end-to-end loop: polling nvidia-smi perturbs its host round trips)
+    ms = ev0.elapsed_time(ev1)
+    timing = state.get_timing()
+    state.enable_timing(False)
+    # per-kernel events serialise the launches (no programmatic-dependent-launch overlap): a second, uninstrumented pass
+    # of the same K steps gives the production number; `value` is the slower (instrumented) of the two only if it IS slower
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    run_many(t, steps)
+    t += steps
+    u1.record()
+    barrier()
+    ms_plain = u0.elapsed_time(u1)
+    # ---- end to end through the public API with host buffers: every step passes the observation from the host and reads the
+    #      step's result (log-ML estimate: the weight statistics, device -> host) back ----
+    if world > 1:
+        for _ in range(2):   # first use of the synchronous path (peer mappings) stays untimed
+            step(t, sync_scalar=True)
+            t += 1
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lml = None
+    for _ in range(steps):
+        lml = step(t, sync_scalar=True)
+        t += 1
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    # the variant in which the caller also LOOKS at what particle_filter_step! returns (the N log incremental weights)
+    ms_incr = None
+    if world == 1 and n_total <= 2 * 10 ** 8:
+        barrier()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        k_incr = max(2, steps // 5)
+        for _ in range(k_incr):
+            g.maybe_resample_(pf, ess_threshold=thr, resampler="systematic")
+            incr, = g.particle_filter_step_(pf, (t,), (g.UnknownChange,), zs[t], return_incr=True)
+            t += 1
+        i1.record()
+        barrier()
+        ms_incr = i0.elapsed_time(i1) / k_incr
+    if dist is not None:
+        tt = torch.tensor([ms, ms_plain, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_plain, ms_e2e = (float(x) for x in tt.tolist())
+    out = {"n_total": n_total, "ms": ms, "ms_plain": ms_plain, "ms_e2e": ms_e2e, "ms_e2e_incr_per_step": ms_incr, "timing": timing,
+           "clocks": clocks, "lml": lml}
+    del state
+    if world == 1:
+        del pf
+    else:
+        del spf
+    g.cache_trim()
+    return out
+
+
+def sharded_parity_check(g, torch, dist, rank):
+    """SCALE lines carry their own proof: an untimed strong-sharded filter (synchronous calls AND the device-controlled run)
+    against the same filter on ONE GPU (rank 0), compared bit for bit."""
+    from genb200 import sharded
+    n, T, seed = 400003, 10, 77
+    ys = F.bearings_series(T + 1)
+    model = g.bearings_model()
+    res = {}
+    for mode in ("sync", "run"):
+        spf = sharded.ShardedParticleFilter(model, n, seed=seed).initialize(ys[0])
+        if mode == "sync":
+            nres = 0
+            for t in range(1, T + 1):
+                nres += spf.maybe_resample_(ess_threshold=(n + 1 if t % 2 else n / 2))
+                spf.particle_filter_step_((t,), ys[t])
+        else:
+            nres = spf.run_(ys[1:], ess_threshold=n / 2)
+        cols = [spf.get_state(f) for f in range(4)]
+        par, lw, lml = spf.get_parents(), spf.get_log_weights(), spf.log_ml_estimate()
+        if rank == 0:
+            st = g.initialize_particle_filter(model, (0,), ys[0], n, seed=seed)
+            if mode == "sync":
+                nres1 = 0
+                for t in range(1, T + 1):
+                    nres1 += g.maybe_resample_(st, ess_threshold=(n + 1 if t % 2 else n / 2), resampler="systematic")
+                    g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+            else:
+                nres1 = g.particle_filter_run_(st, ys[1:], ess_threshold=n / 2)
+            lml1 = g.log_ml_estimate(st)
+            res[mode] = {"traces_bit_exact": bool(all(np.array_equal(cols[f], st.get_state(f)) for f in range(4))),
+                         "parents_bit_exact": bool(np.array_equal(par, st.parents)),
+                         "log_weights_bit_exact": bool(np.array_equal(lw, st.log_weights)),
+                         "resamples": [int(nres), int(nres1)], "log_ml_rel_err": abs(lml - lml1) / max(1.0, abs(lml1))}
+            del st
+        del spf
+    g.cache_trim()
+    if rank != 0:
+        return None
+    ok = all(v["traces_bit_exact"] and v["parents_bit_exact"] and v["log_weights_bit_exact"] and v["resamples"][0] == v["resamples"][1]
+             and v["log_ml_rel_err"] <= 1e-10 for v in res.values())
+    return {"bit_exact": ok, "particles": n, "steps": T, "against": "the same filter on one GPU (rank 0), ordinary API",
+            "paths": res}
+
+
+def other_configs(g, torch, peak):
+    """BASELINE.json configs[0], [1], [3], [4] on one GPU, bounded (a few seconds in total): driver-timed companions of the
+    headline config.  `frac` = algorithmic bytes (SURVEY.md 8d per-unit figures) / time / measured HBM peak."""
+    import ctypes as C
+    from genb200 import _lib as L
+    out = []
+
+    def ev_time(fn, reps=1):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # cfg 0: LGSSM N = 1000, T = 100 (latency regime: single-CTA fused run)
+    ys = F.lgssm_series(101)
+    model = g.lgssm_model(**F.LGSSM)
+    st = g.initialize_particle_filter(model, (0,), ys[0], 1000, seed=1)
+    g.particle_filter_run_(st, ys[1:], ess_threshold=500)
+    st = g.initialize_particle_filter(model, (0,), ys[0], 1000, seed=2)
+    ms = ev_time(lambda: g.particle_filter_run_(st, ys[1:], ess_threshold=500))
+    out.append({"config": "configs[0]: LGSSM N=1e3 T=100 fp64, systematic @ ESS<N/2, gb_pf_run (one single-CTA kernel)",
+                "us_per_step": 1e3 * ms / 100, "value": 1000 * 100 / (ms * 1e-3), "unit": "particle-steps/s", "frac": None,
+                "bound": "launch latency"})
+    # cfg 1: SV N = 1e6, T = 1000, fp64 and fp32, resampling every step, fused run
+    ys = F.sv_series(1001)
+    model = g.sv_model(**F.SV)
+    for dtype, E in (("f64", 8), ("f32", 4)):
+        n = 10 ** 6
+        st = g.initialize_particle_filter(model, (0,), ys[0], n, dtype=dtype, seed=3)
+        g.particle_filter_run_(st, ys[1:51], ess_threshold=n + 1)
+        ms = ev_time(lambda: g.particle_filter_run_(st, ys[51:1001], ess_threshold=n + 1))
+        b = algorithmic_bytes_per_particle_step(1, E)
+        out.append({"config": "configs[1]: stochastic volatility N=1e6 T=1000 %s, systematic every step, gb_pf_run" % dtype,
+                    "us_per_step": 1e3 * ms / 950, "value": n * 950 / (ms * 1e-3), "unit": "particle-steps/s",
+                    "algorithmic_bytes_per_unit": b, "frac": b * n * 950 / (ms * 1e-3) / 1e9 / peak, "bound": "launch latency / hbm",
+                    "log_ml_estimate": g.log_ml_estimate(st)})
+        del st
+    # cfg 3: BLR importance sampling D = 64, 1e7 samples
+    X, y, sigma = F.blr_problem(D=64, n=64)
+    model = g.blr_model(X, sigma)
+    n = 10 ** 7
+    for dtype, E in (("f64", 8), ("f32", 4)):
+        st = g.create_particle_filter(model, n, dtype=dtype, seed=4)
+        g.generate_(st, y)
+        st.ess()
+        ms = ev_time(lambda: (g.generate_(st, y), st.ess()), reps=3)
+        del st
+        t0 = time.perf_counter()
+        _, lnw, lml = g.importance_sampling(model, (), y, n, dtype=dtype, seed=4, return_traces=False)
+        wall = time.perf_counter() - t0
+        b = (64 + 1) * E
+        out.append({"config": "configs[3]: Bayesian linear regression importance_sampling D=64 n=64, 1e7 samples %s" % dtype,
+                    "ms": ms, "value": n / (ms * 1e-3), "unit": "samples/s", "algorithmic_bytes_per_unit": b,
+                    "frac": b * n / (ms * 1e-3) / 1e9 / peak, "bound": "fp64 ALU (8192 likelihood flop + 32 Box-Muller pairs per sample)",
+                    "likelihood_tflops": 2.0 * 64 * 64 * n / (ms * 1e-3) / 1e12,
+                    "e2e_ms_with_80MB_weights_to_host": 1e3 * wall, "log_ml_estimate": lml})
+        del lnw
+    # cfg 4: resampling microbenchmark, device-resident log weights ~ N(0, 3^2)
+    for n in (10 ** 6, 10 ** 8):
+        ld = (n + 2047) // 2048 * 2048
+        gen = torch.Generator(device="cuda").manual_seed(20244)
+        lw = torch.zeros(ld, dtype=torch.float64, device="cuda")
+        lw[:n] = 3.0 * torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
+        anc = torch.empty(ld, dtype=torch.int32, device="cuda")
+        for kind, name in ((L.RESAMPLE_SYSTEMATIC, "systematic"), (L.RESAMPLE_RESIDUAL, "residual"), (L.RESAMPLE_MULTINOMIAL, "multinomial")):
+            def call():
+                L.check(L.lib().gb_resample_device(C.c_void_p(lw.data_ptr()), n, L.F64, kind, 12345, None, 7, 3, C.c_void_p(anc.data_ptr()), None))
+            call()
+            ms = ev_time(call, reps=3)
+            out.append({"config": "configs[4]: resample %s, N=%.0e fp64 log weights resident in HBM" % (name, n), "ms": ms,
+                        "value": n / (ms * 1e-3), "unit": "weights/s", "algorithmic_bytes_per_unit": 12,
+                        "frac": 12.0 * n / (ms * 1e-3) / 1e9 / peak, "bound": "hbm",
+                        "note": "includes the max + statistics passes the raw-array entry needs (inside a filter the step kernel "
+                                "provides the max)"})
+        del lw, anc
+    g.cache_trim()
+    return out
+
+
 def run_genb200(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -235,133 +499,46 @@ def run_genb200(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))   # plumbing: IPC handles, barriers, max of the timings
 
     E = 8 if args.dtype == "f64" else 4
-    n_total = int(args.particles) * (world if args.scaling == "weak" else 1)
-    zs = F.bearings_series(args.warmup + 2 * args.steps + 12)
-    model = g.bearings_model()
-    if world == 1:
-        pf = g.initialize_particle_filter(model, (0,), zs[0], n_total, dtype=args.dtype, seed=20242)
-        thr = n_total + 1   # ESS <= N < N + 1: resample every step (the accounting of SURVEY.md section 8d)
-
-        def step(t, sync_scalar=False):
-            g.maybe_resample_(pf, ess_threshold=thr, resampler="systematic")
-            g.particle_filter_step_(pf, (t,), (g.UnknownChange,), zs[t], return_incr=False)
-            if sync_scalar:
-                return g.log_ml_estimate(pf)
-        state = pf
-    else:
-        from genb200 import sharded
-        spf = sharded.ShardedParticleFilter(model, n_total, dtype=args.dtype, seed=20242)
-        spf.initialize(zs[0])
-        thr = n_total + 1
-
-        def step(t, sync_scalar=False):
-            spf.maybe_resample_(ess_threshold=thr)
-            spf.particle_filter_step_((t,), zs[t])
-            if sync_scalar:
-                return spf.log_ml_estimate()
-
-        def run_many(t0, k):
-            # device-resident path: plan / ESS test / log-ML on the device, no host round trip per step
-            spf.run_([zs[t] for t in range(t0, t0 + k)], ess_threshold=thr)
-        state = spf.local
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    t = 1
-    if world == 1:
-        for _ in range(args.warmup):
-            step(t)
-            t += 1
-    else:
-        run_many(t, args.warmup)
-        t += args.warmup
-    state.sync()
-
-    # ---- device-timed region: value (state resident in HBM, no per-step host read beyond the API's own
-    #      8-byte observation argument and the 40-byte weight-statistics read maybe_resample! needs) ----
-    state.enable_timing(True)
-    state.get_timing()
-    sampler.wait_ready()
-    barrier()
-    w0 = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    if world == 1:
-        for _ in range(args.steps):
-            step(t)
-            t += 1
-    else:
-        run_many(t, args.steps)
-        t += args.steps
-    ev1.record()
-    barrier()
-    sampler.window(w0, time.perf_counter())
-    clocks = sampler.stop()              # (before the end-to-end loop: polling nvidia-smi perturbs its host round trips)
-    ms = ev0.elapsed_time(ev1)
-    timing = state.get_timing()
-    state.enable_timing(False)
-    if dist is not None:
-        tt = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
-    ms_per_step = ms / args.steps
-    value = n_total * args.steps / (ms * 1e-3)
-
-    # ---- end to end through the public API with host buffers: every step passes the observation from
-    #      the host and reads the step's result (log-ML estimate: weight statistics D2H) back ----
-    if world > 1:
-        for _ in range(2):   # first use of the synchronous path's collectives (NCCL p2p channel set-up) stays untimed
-            step(t, sync_scalar=True)
-            t += 1
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    lml = None
-    for _ in range(args.steps):
-        if world > 1 and args.e2e_api == "run":
-            spf.run_([zs[t]], ess_threshold=thr)       # one observation per call, passed from host memory
-            lml = spf.log_ml_estimate()                # device -> host read of the step's result
-        else:
-            lml = step(t, sync_scalar=True)
-        t += 1
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if dist is not None:
-        tt = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_e2e = float(tt.item())
-    e2e_value = n_total * args.steps / (ms_e2e * 1e-3)
-
+    scaling = args.scaling or ("strong" if world > 1 else "weak")
+    n_total = int(args.particles) * (world if scaling == "weak" else 1)
+    zs = F.bearings_series(args.warmup + 4 * args.steps + 16)
+    parity = sharded_parity_check(g, torch, dist, rank) if world > 1 else None
+    main = time_bearings_filter(g, torch, dist, args, n_total, world, zs, args.steps, args.warmup, sampler)
+    other = None
+    if world > 1 and not args.no_second_scaling:
+        n_other = int(args.particles) * (1 if scaling == "weak" else world)
+        other = time_bearings_filter(g, torch, dist, args, n_other, world, zs, args.steps, args.warmup)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
     peak, peak_src = measured_peak()
+    S = S_BEARINGS
     n_local = n_total // world
-    b_step = algorithmic_bytes_per_particle_step(S_BEARINGS, E)
-    # dominant kernel = fused (deferred gather +) propose + weight + LSE kernel.  Its algorithmic bytes
-    # (DESIGN.md "Kernels"): particle_filter_step! (2S+3)E plus the resampled-trace gather it absorbs
-    # (A + 2S E + E) per particle.
+    ms = min(main["ms"], main["ms_plain"])
+    ms_per_step = ms / args.steps
+    value = n_total * args.steps / (ms * 1e-3)
+    timing = main["timing"]
     step_name = L.lib().gb_kernel_name(L.K_STEP).decode()
     k_ms, k_launches = timing[step_name]
-    alg_step_kernel = ((2 * S_BEARINGS + 3) * E + (4 + 2 * S_BEARINGS * E + E)) * n_local
     avg_ms = k_ms / max(1, k_launches)
-    achieved = alg_step_kernel / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    # bytes the fused step kernel has to move per particle: ancestor index + gathered row in, new row + log weight + log
+    # incremental weight out = 4 + 2 S E + 2 E (84 for S = 4, fp64).  This is what `frac` is a fraction OF.
+    fused_bytes = (4 + 2 * S * E + 2 * E) * n_local
+    achieved = fused_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    b_step = algorithmic_bytes_per_particle_step(S, E)                    # SURVEY.md 8d accounting of the UNFUSED API calls: 176
+    b_necessary = (4 + 2 * S * E + 2 * E) + E + (E + 4)                    # fused step + statistics read + ancestors read/write: 104
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in timing.items() if v[1]}
     launches = int(sum(v[1] for v in timing.values()))
-    whole_step_gbs = b_step * n_local / (ms_per_step * 1e-3) / 1e9
-    # DRAM traffic of the step kernel from the committed `ncu --set full` capture (profiles/r1e_kernels_final_ncu.txt:
-    # dram__bytes_read.sum + dram__bytes_write.sum = 2.997 + 4.746 GB at N = 1e8, fp64); scales with N
-    traffic = 77.43 * n_local if args.dtype == "f64" else None
-    fused_io = (4 + 2 * S_BEARINGS * E + 2 * E) * n_local     # what the fused kernel itself must move: anc + rows in, rows + logw + incr out
+    tr = ncu_traffic(args.dtype, S)
+
+    def whole(nbytes):
+        gbs = nbytes * n_local / (ms_per_step * 1e-3) / 1e9
+        return {"bytes_per_particle_step": nbytes, "achieved": gbs, "frac": gbs / peak, "frac_of_8TBs_spec": gbs / 8000.0}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----
     cpu = None
@@ -377,31 +554,50 @@ def run_genb200(args):
                "note": "Gen.jl (pure Julia) cannot run in this image; tutorial-derived Gen.jl figure is "
                        "4e3-8e3 particle-steps/s (docs/src/tutorials/smc.md:298-300)"}
 
+    def second(o, label):
+        if o is None:
+            return None
+        m2 = min(o["ms"], o["ms_plain"])
+        return {"scaling": label, "particles": o["n_total"], "value": o["n_total"] * args.steps / (m2 * 1e-3), "ms_per_step": m2 / args.steps,
+                "e2e_value": o["n_total"] * args.steps / (o["ms_e2e"] * 1e-3), "e2e_ms_per_step": o["ms_e2e"] / args.steps}
+
     out = {
         "metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "scaling": scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": workload_config(args, n_total),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 80,
-                "ms_per_step": ms_e2e / args.steps, "log_ml_estimate": lml,
-                "note": "maybe_resample_ + particle_filter_step_ + log_ml_estimate through the host API each step: "
-                        "observation passed from host memory, weight statistics read back twice (40 B each); the N log "
-                        "incremental weights particle_filter_step! returns stay on the device as a lazy vector "
-                        "(gb_pf_get_log_increments) and are not read"},
+        "clocks": main["clocks"],
+        "e2e": {"value": n_total * args.steps / (main["ms_e2e"] * 1e-3), "unit": "particle-steps/s", "h2d_bytes_per_step": 8,
+                "d2h_bytes_per_step": 48 if world == 1 else 628,
+                "ms_per_step": main["ms_e2e"] / args.steps, "log_ml_estimate": main["lml"],
+                "note": "maybe_resample_ + particle_filter_step_ + log_ml_estimate through the host API each step: observation "
+                        "passed from host memory, weight statistics read back; the N log incremental weights "
+                        "particle_filter_step! returns stay on the device as a lazy vector (gb_pf_get_log_increments)",
+                "reading_log_increments": None if main["ms_e2e_incr_per_step"] is None else {
+                    "ms_per_step": main["ms_e2e_incr_per_step"], "value": n_total / (main["ms_e2e_incr_per_step"] * 1e-3),
+                    "d2h_bytes_per_step": 8 * n_total + 48,
+                    "note": "the same loop when the caller materialises the returned vector every step (N x 8 bytes device -> host)"}},
         "gpu_launches": launches,
+        "timing_note": "ms_per_step = the faster of two passes of K steps: with per-kernel CUDA events (which serialise the "
+                       "launches) and without (programmatic dependent launch overlaps launch latencies)",
+        "ms_per_step_instrumented": main["ms"] / args.steps, "ms_per_step_uninstrumented": main["ms_plain"] / args.steps,
         "roofline": {"bound": "hbm", "kernel": step_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_step_kernel, "avg_launch_ms": avg_ms,
-                     "note": "algorithmic = particle_filter_step! (2S+3)E + the maybe_resample! gather it absorbs (A+2SE+E) per "
-                             "particle (SURVEY.md 8d); the deferred-gather fusion removes an intermediate write+read of the state, "
-                             "so real DRAM traffic (`traffic`, ncu) is below the algorithmic bytes and frac can exceed 1",
-                     "fused_io": {"bytes_per_launch": fused_io, "achieved": fused_io / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0,
-                                  "frac": (fused_io / (avg_ms * 1e-3) / 1e9 / peak) if avg_ms > 0 else 0.0},
-                     "whole_step": {"algorithmic_bytes_per_particle_step": b_step, "achieved": whole_step_gbs,
-                                    "frac": whole_step_gbs / peak, "frac_of_8TBs_spec": whole_step_gbs / 8000.0}},
+                     "frac": achieved / peak, "peak_source": peak_src,
+                     "bytes_per_launch": fused_bytes, "bytes_per_particle": fused_bytes / n_local, "avg_launch_ms": avg_ms,
+                     "traffic": None if tr is None else tr["dram_bytes_per_particle"] * n_local,
+                     "traffic_source": None if tr is None else {k: tr[k] for k in ("file", "kernel", "particles", "dram_bytes_per_particle")},
+                     "note": "bytes = what the FUSED kernel must move per particle (ancestor index + gathered row in; row, log weight, "
+                             "log incremental weight out); frac = bytes / measured time / measured copy peak",
+                     "whole_step": {"algorithmic": dict(whole(b_step), note="SURVEY.md 8d accounting of the unfused API calls "
+                                                                           "(step! + maybe_resample! with a materialised gather): the deferred-gather fusion removes a "
+                                                                           "write + read of the state, so this can exceed 1"),
+                                    "necessary": dict(whole(b_necessary), note="bytes the fused pipeline really has to move: step kernel "
+                                                                             "+ one statistics read + ancestors read/write")}},
         "kernels": kernels,
         "cpu_baseline": cpu,
+        "sharded_parity": parity,
+        "weak" if scaling == "strong" else "strong": second(other, "weak" if scaling == "strong" else "strong"),
+        "configs": other_configs(g, torch, peak) if world == 1 and not args.no_configs else None,
         "log_ml_error": log_ml_error_check(g) if world == 1 else None,
     }
     emit(out)
@@ -435,14 +631,14 @@ def main():
     ap.add_argument("--impl", default="genb200", choices=["genb200", "reference"])
     ap.add_argument("--particles", type=float, default=1e8, help="particles per GPU (weak scaling) / in total (strong scaling)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
-                    help="weak (default): 1e8 particles PER GPU; strong: 1e8 particles in total, sharded")
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="strong (default at --gpus > 1, BASELINE.json configs[2]): 1e8 particles in total, sharded; weak: 1e8 "
+                         "particles PER GPU.  The other one is measured too and reported under its own key.")
+    ap.add_argument("--no-second-scaling", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the bounded runs of the other BASELINE configs (N = 1)")
     ap.add_argument("--cpu-particles", type=int, default=20_000_000)
     ap.add_argument("--ref-particles", type=int, default=20_000_000)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-api", default="sync", choices=["sync", "run"],
-                    help="multi-GPU end-to-end loop: maybe_resample_/particle_filter_step_ per step (sync) or run_ with one "
-                         "observation per call (run)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -12,6 +12,7 @@
 #include "kernels_small.cuh"
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -2102,7 +2103,10 @@ extern "C" int gb_pf_xchg_read(gb_pf_t *pf, double *lse, double *ess, uint64_t *
   REQ(pf && pf->a_world > 0, "gb_pf_xchg_read: bad argument");
   DeviceScope ds__(pf->device);
   CK(cudaMemcpyAsync(pf->h_ctl, pf->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, pf->stream));
-  CK(cudaMemcpyAsync(pf->h_shplan, pf->d_shplan, sizeof(ShardPlanDev), cudaMemcpyDeviceToHost, pf->stream));
+  {   // only what the plan kernel writes for the host: {world, rank, overflow, global record, per-shard masses}
+    const size_t off = offsetof(ShardPlanDev, world);
+    CK(cudaMemcpyAsync((char *)pf->h_shplan + off, (const char *)pf->d_shplan + off, sizeof(ShardPlanDev) - off, cudaMemcpyDeviceToHost, pf->stream));
+  }
   CK(cudaMemcpyAsync(&pf->h_xc->error, &pf->d_xc->error, sizeof(int), cudaMemcpyDeviceToHost, pf->stream));
   CK(cudaStreamSynchronize(pf->stream));
   if (lse) *lse = pf->h_shplan->global.lse;
