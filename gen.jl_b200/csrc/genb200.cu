@@ -294,9 +294,7 @@ struct gb_pf {
   bool u64_set = false;
   // resampling workspace
   long long ntiles = 0;
-  uint64_t *tile_q = nullptr, *tile_c = nullptr;
-  U128 *tile_r = nullptr;
-  long long *tile_slot = nullptr;
+  uint64_t *tile_q = nullptr;
   unsigned long long *super_q = nullptr, *super_excl = nullptr;
   long long nsuper = 0;
   OverflowEntry *oflow = nullptr;
@@ -404,7 +402,7 @@ static void pf_release(gb_pf *pf) {
   gb_dev_free(pf->parents64); gb_dev_free(pf->ext_parents); gb_dev_free(pf->partials); gb_dev_free(pf->ticket); gb_dev_free(pf->d_stats);
   gb_host_free(pf->h_stats); gb_dev_free(pf->d_normals); gb_dev_free(pf->d_uniforms); gb_dev_free(pf->d_u64);
   gb_dev_free(pf->d_ctl); gb_host_free(pf->h_ctl); gb_dev_free(pf->d_shplan); gb_host_free(pf->h_shplan); gb_dev_free(pf->d_offs); gb_dev_free(pf->super_q); gb_dev_free(pf->super_excl); gb_dev_free(pf->oflow); gb_dev_free(pf->oflow_count);
-  gb_dev_free(pf->tile_q); gb_dev_free(pf->tile_c); gb_dev_free(pf->tile_r); gb_dev_free(pf->tile_slot); gb_dev_free(pf->d_plan);
+  gb_dev_free(pf->tile_q); gb_dev_free(pf->d_plan);
   gb_dev_free(pf->lik); gb_dev_free(pf->guide); gb_dev_free(pf->tile_save);
   gb_host_free(pf->h_plan); gb_dev_free(pf->cdf); gb_dev_free(pf->off_anc); gb_dev_free(pf->d_tab); gb_dev_free(pf->d_ptab);
   for (auto p : pf->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -473,7 +471,6 @@ extern "C" int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_glob
   if (e == cudaSuccess) e = A((void **)&pf->d_stats, sizeof(WeightStats), true);
   if (e == cudaSuccess) e = gb_host_alloc((void **)&pf->h_stats, sizeof(WeightStats));
   if (e == cudaSuccess) e = A((void **)&pf->tile_q, (size_t)(pf->ntiles + 1) * 8, true);
-  if (e == cudaSuccess) e = A((void **)&pf->tile_slot, (size_t)(pf->ntiles + 1) * 8, true);
   if (e == cudaSuccess) e = A((void **)&pf->d_plan, sizeof(ResamplePlan), true);
   if (e == cudaSuccess) e = gb_host_alloc((void **)&pf->h_plan, sizeof(ResamplePlan));
   if (e == cudaSuccess) e = alloc_sys_workspace(pf);
@@ -896,6 +893,7 @@ extern "C" int gb_pf_initialize(const gb_model_t *m, int64_t n, int dtype, uint6
   return GB_OK;
 }
 
+static int copy_out(gb_pf *pf, const void *dsrc, double *out, long long n);
 extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, const double *pargs, int npargs,
                           double *incr_out) {
   REQ(pf, "null handle");
@@ -918,17 +916,7 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
   pf->incr_step = pf->step;
   if (pf->history && (rc = history_record(pf, pf->hist_resampled))) return rc;
   pf->hist_resampled = false;
-  if (incr_out) {
-    if (pf->dtype == GB_F64) {
-      CK(cudaMemcpyAsync(incr_out, pf->incr, (size_t)pf->n * 8, cudaMemcpyDeviceToHost, pf->stream));
-      CK(cudaStreamSynchronize(pf->stream));
-    } else {
-      std::vector<float> tmp(pf->n);
-      CK(cudaMemcpyAsync(tmp.data(), pf->incr, (size_t)pf->n * 4, cudaMemcpyDeviceToHost, pf->stream));
-      CK(cudaStreamSynchronize(pf->stream));
-      for (long long i = 0; i < pf->n; i++) incr_out[i] = tmp[i];
-    }
-  }
+  if (incr_out) return copy_out(pf, pf->incr, incr_out, pf->n);   // staged: pinned chunks + host fan-out (the caller's pages are pageable)
   return GB_OK;
 }
 
@@ -1441,38 +1429,17 @@ extern "C" int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out) {
 // ------------------------------------------------------------------------------------------
 // resampling
 // ------------------------------------------------------------------------------------------
-static int ensure_residual_ws(gb_pf *pf) {
-  if (!pf->tile_c) CK(gb_dev_alloc((void **)&pf->tile_c, (size_t)(pf->ntiles + 1) * 8));
-  if (!pf->tile_r) CK(gb_dev_alloc((void **)&pf->tile_r, (size_t)(pf->ntiles + 1) * sizeof(U128)));
-  return GB_OK;
-}
-
-template <typename R, int SWEEP>
-static int launch_qtotal(gb_pf *pf, const void *logw, double m, int bits, uint64_t q_total) {
-  auto kern = qtotal_kernel<R, SWEEP>;
-  int grid = grid_for(pf, kern, pf->ntiles * kBlock, kBlock);
-  LAUNCH(pf, GB_K_QTOTAL, kern<<<grid, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->n_global, q_total,
-                                                                 pf->tile_q, pf->tile_c, pf->tile_r));
+// inclusive integer CDF of the current weights into pf->cdf (needs valid tile totals: run_wstats); tile_q becomes its prefix
+template <typename R>
+static int launch_cdf(gb_pf *pf, const void *logw, double m) {
+  const int bits = quant_bits(pf->n_global);
+  if (!pf->cdf) CK(gb_dev_alloc((void **)&pf->cdf, (size_t)pf->ld * 8));
+  LAUNCH(pf, GB_K_TILESCAN, tilescan_cdf_kernel<<<1, 1024, 0, pf->stream>>>(pf->ntiles, pf->tile_q, pf->d_plan, pf->n_global));
   CK(cudaGetLastError());
-  return GB_OK;
-}
-template <int SWEEP>
-static int launch_tilescan(gb_pf *pf, uint64_t q_offset, uint64_t q_total, uint32_t u0, int write) {
-  LAUNCH(pf, GB_K_TILESCAN, tilescan_kernel<SWEEP><<<1, 1024, 0, pf->stream>>>(pf->ntiles, pf->tile_q, pf->tile_c, pf->tile_r,
-                                                                                pf->tile_slot, pf->d_plan, q_offset, q_total,
-                                                                                pf->n_global, u0, write));
+  LAUNCH(pf, GB_K_ANCESTORS, cdf_kernel<R><<<(unsigned)pf->ntiles, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->tile_q, pf->cdf));
   CK(cudaGetLastError());
-  return GB_OK;
-}
-template <typename R, int SWEEP>
-static int launch_ancestors(gb_pf *pf, const void *logw, double m, int bits, long long over_base, long long n_over,
-                            int *anc, long long anc_base) {
-  auto kern = ancestors_kernel<R, SWEEP>;
-  long long grid = pf->ntiles + n_over;
-  LAUNCH(pf, GB_K_ANCESTORS, kern<<<(unsigned)grid, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->tile_q, pf->tile_c,
-                                                                              pf->tile_r, pf->tile_slot, pf->d_plan, pf->ntiles,
-                                                                              over_base, anc, anc_base, pf->cdf));
-  CK(cudaGetLastError());
+  pf->tiles_valid = false;
+  pf->ws_clean = false;
   return GB_OK;
 }
 
@@ -1507,36 +1474,22 @@ static int launch_systematic(gb_pf *pf, const void *logw, double m, uint64_t q_o
 template <typename R>
 static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, uint32_t u0, const uint64_t *d_u64,
                              uint64_t seed, uint32_t step, int *anc) {
-  const int bits = quant_bits(pf->n_global);
-  const long long n_over = (pf->n_global + kChunk - 1) / kChunk;
   int rc;
-  if (kind == GB_RESAMPLE_SYSTEMATIC) {
+  if (kind == GB_RESAMPLE_SYSTEMATIC || kind == GB_RESAMPLE_RESIDUAL) {
+    // residual resampling (deterministic copies + a systematic sweep over the residual masses, same u0) IS systematic
+    // resampling in the exact integer spec: kernels_resample.cuh "RESIDUAL == SYSTEMATIC"
     if (!pf->tiles_valid && (rc = run_wstats(pf, logw, m, false))) return rc;
     return launch_systematic<R>(pf, logw, m, 0, 0, u0, AncOut{anc, 0, pf->n_global, nullptr, 0, 0});
   }
-  if (kind == GB_RESAMPLE_RESIDUAL) {
-    if ((rc = ensure_residual_ws(pf))) return rc;
-    if (!pf->tiles_valid && (rc = run_wstats(pf, logw, m, false))) return rc;
-    const uint64_t qn = pf->h_stats->q_total;
-    pf->tiles_valid = false;   // tile_q is about to be overwritten by the residual tile scan
-    if ((rc = launch_qtotal<R, SWEEP_RESIDUAL>(pf, logw, m, bits, qn))) return rc;
-    if ((rc = launch_tilescan<SWEEP_RESIDUAL>(pf, 0, qn, u0, 1))) return rc;
-    return launch_ancestors<R, SWEEP_RESIDUAL>(pf, logw, m, bits, 0, n_over, anc, 0);
-  }
   if (kind == GB_RESAMPLE_MULTINOMIAL) {
-    if (!pf->cdf) CK(gb_dev_alloc((void **)&pf->cdf, (size_t)pf->ld * 8));
     if (!pf->tiles_valid && (rc = run_wstats(pf, logw, m, false))) return rc;
-    pf->tiles_valid = false;   // tile_q becomes its exclusive prefix
     // guide table first: the systematic sweep for u0 = 0 consumes (and zeroes) the tile totals, so they are parked meanwhile
     if (!pf->guide) CK(gb_dev_alloc((void **)&pf->guide, (size_t)pf->ld * 4));
     if (!pf->tile_save) CK(gb_dev_alloc((void **)&pf->tile_save, (size_t)(pf->ntiles + 1) * 8));
     CK(cudaMemcpyAsync(pf->tile_save, pf->tile_q, (size_t)(pf->ntiles + 1) * 8, cudaMemcpyDeviceToDevice, pf->stream));
     if ((rc = launch_systematic<R>(pf, logw, m, 0, 0, 0u, AncOut{pf->guide, 0, pf->n_global, nullptr, 0, 0}))) return rc;
     CK(cudaMemcpyAsync(pf->tile_q, pf->tile_save, (size_t)(pf->ntiles + 1) * 8, cudaMemcpyDeviceToDevice, pf->stream));
-    pf->ws_clean = false;
-    pf->tiles_valid = false;
-    if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, u0, 1))) return rc;
-    if ((rc = launch_ancestors<R, SWEEP_CDF>(pf, logw, m, bits, 0, 0, anc, 0))) return rc;
+    if ((rc = launch_cdf<R>(pf, logw, m))) return rc;
     int grid = grid_for(pf, multinomial_guided_kernel, pf->n, kBlock);
     LAUNCH(pf, GB_K_ANCESTORS, multinomial_guided_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->cdf, pf->guide, pf->n, pf->d_plan, d_u64, seed,
                                                                                           step, pf->n, anc, (unsigned)PK_MULTI));
@@ -1589,12 +1542,7 @@ extern "C" int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t 
   const double m = pf->h_stats->m;
   if (!(m > -INFINITY)) return fail(GB_ESTATE, "gb_pf_sample_unweighted: all log weights are -Inf or NaN");
   if (!pf->tiles_valid && (rc = run_wstats(pf, pf->logw, m, false))) return rc;
-  if (!pf->cdf) CK(gb_dev_alloc((void **)&pf->cdf, (size_t)pf->ld * 8));
-  const int bits = quant_bits(pf->n_global);
-  pf->tiles_valid = false;   // tile_q becomes its exclusive prefix
-  if ((rc = launch_tilescan<SWEEP_CDF>(pf, 0, 0, 0, 1))) return rc;
-  rc = pf->dtype == GB_F64 ? launch_ancestors<double, SWEEP_CDF>(pf, pf->logw, m, bits, 0, 0, nullptr, 0)
-                           : launch_ancestors<float, SWEEP_CDF>(pf, pf->logw, m, bits, 0, 0, nullptr, 0);
+  rc = pf->dtype == GB_F64 ? launch_cdf<double>(pf, pf->logw, m) : launch_cdf<float>(pf, pf->logw, m);
   if (rc) return rc;
   int *d_idx = nullptr;
   long long *d_idx1 = nullptr;
@@ -2356,7 +2304,6 @@ static int raw_workspace(long long n, int dtype, cudaStream_t stream, gb_pf **ou
   if (e == cudaSuccess) e = cudaMemset(pf->d_stats, 0, sizeof(WeightStats));     // (xc = nullptr: not a sharded filter)
   if (e == cudaSuccess) e = gb_host_alloc((void **)&pf->h_stats, sizeof(WeightStats));
   if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->tile_q, (size_t)(pf->ntiles + 1) * 8);
-  if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->tile_slot, (size_t)(pf->ntiles + 1) * 8);
   if (e == cudaSuccess) e = gb_dev_alloc((void **)&pf->d_plan, sizeof(ResamplePlan));
   if (e == cudaSuccess) e = gb_host_alloc((void **)&pf->h_plan, sizeof(ResamplePlan));
   if (e != cudaSuccess) { pf_release(pf); return fail(GB_ECUDA, std::string("raw workspace: ") + cudaGetErrorString(e)); }

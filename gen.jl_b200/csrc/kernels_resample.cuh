@@ -7,75 +7,30 @@
 // the tiling, of the launch geometry and of how particles are sharded over GPUs, and bit-identical to
 // the sequential oracle.
 //
-// Passes (all HBM-streaming, tiles of kTile = 2048 particles, 256 threads x 8 items):
-//   qtotal    : read lw            -> per-tile sum of q                       (E bytes / particle)
-//   tilescan  : per-tile sums      -> exclusive tile CDF + first output slot of every tile (tiny)
-//   ancestors : read lw, block scan, per-particle offspring range by exact 128/64-bit division,
-//               merge-path style fill of the tile's output slots            (E + 4 bytes / particle)
-//   gather    : read ancestors + ancestor rows (monotone => near-coalesced), write rows, zero lw
+// RESIDUAL == SYSTEMATIC.  Appendix B defines residual resampling as c_j = floor(N q_j / Q) deterministic copies plus
+// a systematic sweep, with the same offset u0, over the residual masses r_j = N q_j - c_j Q.  In exact integers the two
+// coincide: residual slot k lies before the end of particle j iff floor((k 2^32 + u0) Q / 2^32) < N C_j - Q Cc_j
+// (C = inclusive CDF of q, Cc = running count of copies), i.e. iff ((k + Cc_j) 2^32 + u0) Q < 2^32 N C_j, i.e. iff the
+// SYSTEMATIC threshold tau_{k + Cc_j} < C_j; and every slot k' < Cc_j satisfies tau_k' < C_j because Cc_j Q <= N C_j.
+// So the offspring range of particle j ends at the same slot under both definitions (the "residual systematic
+// resampling" identity of Bolic et al., here exact).  GB_RESAMPLE_RESIDUAL therefore runs the systematic pipeline; the
+// oracle keeps the definitional two-stage restatement and the parity tests compare against THAT
+// (tests/test_gpu_parity.py::test_resamplers_bit_exact, tests/test_oracle_golden.py::test_residual_equals_systematic).
+//
+// Passes (all HBM-streaming, tiles of kTile = 2048 particles, 256 threads x 8 items): see "Systematic resampling,
+// production pipeline" below; the CDF materialisation + guided search right below serve the multinomial draws.
 #pragma once
 #include "kernels_step.cuh"
 
 namespace gb {
 
-struct U128 { uint64_t lo, hi; };
-GB_HD U128 u128_add(U128 a, U128 b) {
-  U128 r;
-  r.lo = a.lo + b.lo;
-  r.hi = a.hi + b.hi + (r.lo < a.lo ? 1 : 0);
-  return r;
-}
-GB_HD U128 u128_make(uint64_t lo) { return U128{lo, 0}; }
-
-enum { SWEEP_SYSTEMATIC = 0, SWEEP_RESIDUAL = 1, SWEEP_CDF = 2 };
-
-// ---- 64-bit / 128-bit block primitives built on warp shuffles ----
+// ---- 64-bit block primitives built on warp shuffles ----
 GB_D uint64_t shfl_u64(uint64_t v, int src) {
   uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
   uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
   return ((uint64_t)hi << 32) | lo;
 }
-// exclusive block scan of one U128 per thread; returns the exclusive prefix, *total = block sum
-GB_D U128 block_exclusive_scan(U128 v, U128 *s_warp /* kBlock/32 + 1 */, U128 *total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  U128 inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    U128 o;
-    o.lo = shfl_up_u64(inc.lo, d);
-    o.hi = shfl_up_u64(inc.hi, d);
-    if (lane >= d) inc = u128_add(inc, o);
-  }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    U128 w = lane < kBlock / 32 ? s_warp[lane] : U128{0, 0};
-    U128 winc = w;
-#pragma unroll
-    for (int d = 1; d < kBlock / 32; d <<= 1) {
-      U128 o;
-      o.lo = shfl_up_u64(winc.lo, d);
-      o.hi = shfl_up_u64(winc.hi, d);
-      if (lane >= d) winc = u128_add(winc, o);
-    }
-    if (lane < kBlock / 32) {
-      // exclusive warp offset = inclusive - own
-      U128 ex;
-      ex.lo = winc.lo - w.lo;
-      ex.hi = winc.hi - w.hi - (winc.lo < w.lo ? 1 : 0);
-      s_warp[lane] = ex;
-    }
-    if (lane == kBlock / 32 - 1) s_warp[kBlock / 32] = winc;
-  }
-  __syncthreads();
-  U128 woff = s_warp[warp];
-  *total = s_warp[kBlock / 32];
-  U128 ex;
-  ex.lo = inc.lo - v.lo;
-  ex.hi = inc.hi - v.hi - (inc.lo < v.lo ? 1 : 0);
-  return u128_add(woff, ex);
-}
-// 64-bit flavour (systematic / multinomial CDF never exceeds 2^62)
+// exclusive block scan of one u64 per thread (the CDF never exceeds 2^62); *total = block sum
 GB_D uint64_t block_exclusive_scan(uint64_t v, uint64_t *s_warp /* kBlock/32 + 1 */, uint64_t *total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t inc = v;
@@ -102,284 +57,77 @@ GB_D uint64_t block_exclusive_scan(uint64_t v, uint64_t *s_warp /* kBlock/32 + 1
   return s_warp[warp] + (inc - v);
 }
 
-// residual resampling: deterministic copies c = floor(N q / Q) and residual mass r = N q - c Q
-GB_D void residual_split(uint64_t q, long long n_global, uint64_t q_total, uint64_t &c, uint64_t &r) {
-  uint64_t nq = (uint64_t)n_global * q;   // <= 2^62 by the choice of the quantisation width
-  c = nq / q_total;
-  r = nq - c * q_total;
-}
-
-// ---- K4a: per-tile totals ----
-template <typename R, int SWEEP>
-__global__ void __launch_bounds__(kBlock) qtotal_kernel(const R *__restrict__ logw, long long n, double m, int bits,
-                                                        long long n_global, uint64_t q_total,
-                                                        uint64_t *__restrict__ tile_q, uint64_t *__restrict__ tile_c,
-                                                        U128 *__restrict__ tile_r) {
-  __shared__ U128 s_warp[kBlock / 32 + 1];
-  __shared__ uint64_t s_warp64[kBlock / 32 + 1];
-  const long long ntiles = (n + kTile - 1) / kTile;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    double lw[kItems];
-    load_items<R>(logw, tile * kTile, n, lw);
-    uint64_t sq = 0, sc = 0;
-    U128 sr = {0, 0};
-#pragma unroll
-    for (int j = 0; j < kItems; j++) {
-      uint64_t q = quantize_k(lw[j] - m, bits);
-      if (SWEEP == SWEEP_RESIDUAL) {
-        uint64_t c, r;
-        residual_split(q, n_global, q_total, c, r);
-        sc += c;
-        sr = u128_add(sr, u128_make(r));
-      } else {
-        sq += q;
-      }
-    }
-    // block reduction through the scan helper (total only)
-    if (SWEEP == SWEEP_RESIDUAL) {
-      U128 tot, tot2;
-      block_exclusive_scan(sr, s_warp, &tot);
-      __syncthreads();
-      block_exclusive_scan(u128_make(sc), s_warp, &tot2);
-      if (threadIdx.x == 0) { tile_r[tile] = tot; tile_c[tile] = tot2.lo; }
-    } else {
-      uint64_t tot;
-      block_exclusive_scan(sq, s_warp64, &tot);
-      if (threadIdx.x == 0) tile_q[tile] = tot;
-    }
-    __syncthreads();
-  }
-}
-
-// ---- tilescan: exclusive scan of the tile totals + first output slot of every tile ----
-// One CTA of 1024 threads (ntiles <= 2^31 / 2048 = 2^20, i.e. at most 1024 entries per thread).
-// tile_q/tile_c/tile_r are overwritten with their exclusive prefixes (ntiles + 1 entries each);
-// tile_slot[i] = first global output slot produced by tile i (ntiles + 1 entries).
-template <int SWEEP>
-__global__ void __launch_bounds__(1024) tilescan_kernel(long long ntiles, uint64_t *tile_q, uint64_t *tile_c, U128 *tile_r,
-                                                        long long *tile_slot, ResamplePlan *plan, uint64_t q_offset,
-                                                        uint64_t q_total_given, long long n_global, uint32_t u0, int write) {
-  __shared__ U128 s_part[1024 / 32 + 1];
-  __shared__ U128 s_part2[1024 / 32 + 1];
-  __shared__ SweepParams s_sp;
+// ---- inclusive integer CDF, materialised (multinomial draws, sample_unweighted_traces) ----
+// tilescan_cdf : one CTA of 1024 threads turns the per-tile totals (wstats) into exclusive tile prefixes (ntiles + 1 entries)
+// cdf_kernel   : one CTA per tile: block scan of the quantised weights on top of the tile prefix -> cdf_out[i]
+__global__ void __launch_bounds__(1024) tilescan_cdf_kernel(long long ntiles, uint64_t *tile_q, ResamplePlan *plan, long long n_global) {
+  __shared__ uint64_t s_w[33];
   const int T = 1024;
   const long long per = (ntiles + T - 1) / T;
   const long long lo = (long long)threadIdx.x * per, hi = lo + per < ntiles ? lo + per : ntiles;
-  U128 a = {0, 0};
-  uint64_t ac = 0;
-  for (long long i = lo; i < hi; i++) {
-    if (SWEEP == SWEEP_RESIDUAL) { a = u128_add(a, tile_r[i]); ac += tile_c[i]; }
-    else a = u128_add(a, u128_make(tile_q[i]));
-  }
-  // block scan over 1024 thread sums (two-level: warp shuffles + shared)
+  uint64_t a = 0;
+  for (long long i = lo; i < hi; i++) a += tile_q[i];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  auto scan1024 = [&](U128 v, U128 *sh, U128 *total) -> U128 {
-    U128 inc = v;
+  uint64_t inc = a;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t o = shfl_up_u64(inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t w = s_w[lane], winc = w;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      U128 o;
-      o.lo = shfl_up_u64(inc.lo, d);
-      o.hi = shfl_up_u64(inc.hi, d);
-      if (lane >= d) inc = u128_add(inc, o);
+      uint64_t o = shfl_up_u64(winc, d);
+      if (lane >= d) winc += o;
     }
-    if (lane == 31) sh[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      U128 w = sh[lane];
-      U128 winc = w;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        U128 o;
-        o.lo = shfl_up_u64(winc.lo, d);
-        o.hi = shfl_up_u64(winc.hi, d);
-        if (lane >= d) winc = u128_add(winc, o);
-      }
-      U128 ex;
-      ex.lo = winc.lo - w.lo;
-      ex.hi = winc.hi - w.hi - (winc.lo < w.lo ? 1 : 0);
-      sh[lane] = ex;
-      if (lane == 31) sh[32] = winc;
-    }
-    __syncthreads();
-    *total = sh[32];
-    U128 ex;
-    ex.lo = inc.lo - v.lo;
-    ex.hi = inc.hi - v.hi - (inc.lo < v.lo ? 1 : 0);
-    return u128_add(sh[warp], ex);
-  };
-  U128 tot, totc;
-  U128 ex = scan1024(a, s_part, &tot);
-  U128 exc = scan1024(u128_make(ac), s_part2, &totc);
+    s_w[lane] = winc - w;
+    if (lane == 31) s_w[32] = winc;
+  }
+  __syncthreads();
+  uint64_t run = s_w[warp] + (inc - a);
+  const uint64_t total = s_w[32];
+  for (long long i = lo; i < hi; i++) {
+    const uint64_t v = tile_q[i];
+    tile_q[i] = run;
+    run += v;
+  }
   if (threadIdx.x == 0) {
+    tile_q[ntiles] = total;
     SweepParams sp;
-    if (SWEEP == SWEEP_RESIDUAL) sp.q_total = q_total_given;           // Q_N of the quantised weights
-    else sp.q_total = q_total_given ? q_total_given : tot.lo;          // single shard: Q_N = local total
-    sp.q_inv = 1.0 / (double)sp.q_total;
+    sp.q_total = total;
+    sp.q_inv = 1.0 / (double)total;
     sp.dscale = (uint64_t)n_global << 32;
-    sp.ratio = (double)n_global / (double)sp.q_total;
-    sp.u0 = u0;
-    s_sp = sp;
-  }
-  __syncthreads();
-  const SweepParams sp = s_sp;
-  auto slot_of = [&](const U128 &r, uint64_t c) -> long long {
-    if (SWEEP == SWEEP_RESIDUAL) return (long long)c + slots_below_residual(r.hi, r.lo, sp);
-    if (SWEEP == SWEEP_SYSTEMATIC) return slots_below(q_offset + r.lo, sp);
-    return 0;
-  };
-  if (write) {
-    U128 run = ex;
-    uint64_t runc = exc.lo;
-    for (long long i = lo; i < hi; i++) {
-      U128 val;
-      uint64_t valc = 0;
-      if (SWEEP == SWEEP_RESIDUAL) { val = tile_r[i]; valc = tile_c[i]; tile_r[i] = run; tile_c[i] = runc; }
-      else { val = u128_make(tile_q[i]); tile_q[i] = (SWEEP == SWEEP_CDF ? q_offset : 0) + run.lo; }
-      tile_slot[i] = slot_of(run, runc);
-      run = u128_add(run, val);
-      runc += valc;
-    }
-    if (threadIdx.x == 0) {
-      if (SWEEP == SWEEP_RESIDUAL) { tile_r[ntiles] = tot; tile_c[ntiles] = totc.lo; }
-      else tile_q[ntiles] = (SWEEP == SWEEP_CDF ? q_offset : 0) + tot.lo;
-      tile_slot[ntiles] = slot_of(tot, totc.lo);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+    sp.ratio = (double)n_global / (double)total;
+    sp.u0 = 0;
     plan->sp = sp;
-    plan->q_offset = q_offset;
+    plan->q_offset = 0;
     plan->n_global = n_global;
-    if (SWEEP == SWEEP_SYSTEMATIC) {
-      plan->slot_lo = slots_below(q_offset, sp);
-      plan->slot_hi = slots_below(q_offset + tot.lo, sp);
-    } else if (SWEEP == SWEEP_RESIDUAL) {
-      plan->slot_lo = 0;
-      plan->slot_hi = (long long)totc.lo + slots_below_residual(tot.hi, tot.lo, sp);
-    } else {
-      plan->slot_lo = 0;
-      plan->slot_hi = n_global;
-    }
+    plan->slot_lo = 0;
+    plan->slot_hi = n_global;
   }
 }
-
-// ---- K4b: per-tile scan -> offspring ranges -> ancestor fill ----
-// CTAs [0, ntiles) own one input tile each and fill at most kChunk of its output slots; CTAs
-// [ntiles, ntiles + n_over) own one kChunk-aligned range of output slots each and fill the part of it
-// that belongs to a heavy tile's overflow (at most one tile per range), so a degenerate weight vector
-// (one particle taking every slot) is still spread over the whole GPU.
-template <typename R, int SWEEP>
-__global__ void __launch_bounds__(kBlock) ancestors_kernel(const R *__restrict__ logw, long long n, double m, int bits,
-                                                           const uint64_t *__restrict__ tile_q,
-                                                           const uint64_t *__restrict__ tile_c,
-                                                           const U128 *__restrict__ tile_r,
-                                                           const long long *__restrict__ tile_slot,
-                                                           const ResamplePlan *__restrict__ plan, long long ntiles,
-                                                           long long over_base, int *__restrict__ anc, long long anc_base,
-                                                           uint64_t *__restrict__ cdf_out) {
-  __shared__ U128 s_warp[kBlock / 32 + 1];
+template <typename R>
+__global__ void __launch_bounds__(kBlock) cdf_kernel(const R *__restrict__ logw, long long n, double m, int bits,
+                                                     const uint64_t *__restrict__ tile_q, uint64_t *__restrict__ cdf_out) {
   __shared__ uint64_t s_warp64[kBlock / 32 + 1];
-  __shared__ uint32_t s_kend[kTile];
-  __shared__ long long s_tile, s_lo, s_hi;
-  const SweepParams sp = plan->sp;
-  const uint64_t q_offset = plan->q_offset;
-  const long long n_global = plan->n_global;
-
-  if (threadIdx.x == 0) {
-    long long tile, lo, hi;
-    if ((long long)blockIdx.x < ntiles) {
-      tile = blockIdx.x;
-      lo = tile_slot[tile];
-      hi = tile_slot[tile + 1];
-      if (hi > lo + kChunk) hi = lo + kChunk;
-    } else {
-      const long long a0 = over_base + ((long long)blockIdx.x - ntiles) * kChunk;
-      // tile whose slot range contains a0: last i with tile_slot[i] <= a0
-      long long l = 0, h = ntiles;      // invariant: tile_slot[l] <= a0 (or l == 0), tile_slot[h] > a0 (or h == ntiles)
-      if (a0 < tile_slot[0] || a0 >= tile_slot[ntiles]) { tile = 0; lo = hi = 0; }
-      else {
-        while (h - l > 1) {
-          long long mid = (l + h) >> 1;
-          if (tile_slot[mid] <= a0) l = mid; else h = mid;
-        }
-        tile = l;
-        lo = tile_slot[tile] + kChunk;
-        if (lo < a0) lo = a0;
-        hi = tile_slot[tile + 1];
-        if (hi > a0 + kChunk) hi = a0 + kChunk;
-      }
-    }
-    s_tile = tile; s_lo = lo; s_hi = hi;
-  }
-  __syncthreads();
-  const long long tile = s_tile, lo = s_lo, hi = s_hi;
-  if (SWEEP != SWEEP_CDF && lo >= hi) return;
-
+  const long long tile = blockIdx.x;
   double lw[kItems];
   load_items<R>(logw, tile * kTile, n, lw);
-  const long long slot0 = tile_slot[tile];
-  if (SWEEP == SWEEP_RESIDUAL) {
-    uint64_t c[kItems];
-    U128 r[kItems];
-    uint64_t tc = 0;
-    U128 tr = {0, 0};
+  uint64_t c[kItems];
+  uint64_t t = 0;
 #pragma unroll
-    for (int j = 0; j < kItems; j++) {
-      uint64_t q = quantize_k(lw[j] - m, bits), rr;
-      residual_split(q, n_global, sp.q_total, c[j], rr);
-      tc += c[j];
-      tr = u128_add(tr, u128_make(rr));
-      c[j] = tc;
-      r[j] = tr;
-    }
-    U128 dummy;
-    uint64_t dummy64;
-    U128 exr = block_exclusive_scan(tr, s_warp, &dummy);
-    uint64_t exc = block_exclusive_scan(tc, s_warp64, &dummy64);
-    const U128 base_r = u128_add(tile_r[tile], exr);
-    const uint64_t base_c = tile_c[tile] + exc;
-#pragma unroll
-    for (int j = 0; j < kItems; j++) {
-      U128 C = u128_add(base_r, r[j]);
-      long long kend = (long long)(base_c + c[j]) + slots_below_residual(C.hi, C.lo, sp);
-      s_kend[threadIdx.x * kItems + j] = (uint32_t)(kend - slot0);
-    }
-  } else {
-    uint64_t c[kItems];
-    uint64_t t = 0;
-#pragma unroll
-    for (int j = 0; j < kItems; j++) {
-      t += quantize_k(lw[j] - m, bits);
-      c[j] = t;
-    }
-    uint64_t dummy64;
-    uint64_t ex = block_exclusive_scan(t, s_warp64, &dummy64);
-    const uint64_t base = tile_q[tile] + ex + (SWEEP == SWEEP_CDF ? 0 : q_offset);
-    if (SWEEP == SWEEP_CDF) {
-      // multinomial: materialise the inclusive integer CDF (tile_q already carries q_offset)
-      const long long i0 = tile * kTile + (long long)threadIdx.x * kItems;
-#pragma unroll
-      for (int j = 0; j < kItems; j++) cdf_out[i0 + j] = base + c[j];
-      return;
-    }
-#pragma unroll
-    for (int j = 0; j < kItems; j++) {
-      long long kend = slots_below(base + c[j], sp);
-      s_kend[threadIdx.x * kItems + j] = (uint32_t)(kend - slot0);
-    }
+  for (int j = 0; j < kItems; j++) {
+    t += quantize_k(lw[j] - m, bits);
+    c[j] = t;
   }
-  __syncthreads();
-  // merge-path fill: slot k belongs to the first particle whose offspring range ends beyond k
-  const int base_particle = (int)(tile * kTile);
-  for (long long k = lo + threadIdx.x; k < hi; k += kBlock) {
-    const uint32_t rel = (uint32_t)(k - slot0);
-    int l = 0, h = kTile - 1;   // smallest j with s_kend[j] > rel (exists: s_kend[kTile-1] = tile slot count > rel)
-    while (l < h) {
-      int mid = (l + h) >> 1;
-      if (s_kend[mid] > rel) h = mid; else l = mid + 1;
-    }
-    anc[k - anc_base] = base_particle + l;
-  }
+  uint64_t total;
+  const uint64_t base = tile_q[tile] + block_exclusive_scan(t, s_warp64, &total);
+  const long long i0 = tile * kTile + (long long)threadIdx.x * kItems;
+#pragma unroll
+  for (int j = 0; j < kItems; j++) cdf_out[i0 + j] = base + c[j];
 }
 
 // ---- multinomial (reference semantics: N iid categorical draws in slot order) ----
