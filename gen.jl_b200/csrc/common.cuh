@@ -104,8 +104,8 @@ GB_D void philox_uniform_pair(uint64_t seed, uint64_t pid, uint32_t step, uint32
 }
 
 // ------------------------------------------------------------------------------------------
-// Integer-CDF weight quantisation (oracle go_dexp/go_quantize).  Only rint,
-// fma, * and exact power-of-two scaling are used, so host gcc and device produce identical bits.
+// Integer-CDF weight quantisation (oracle go_dexp/go_quantize): helpers; the
+// exponential itself is gbmath.cuh wexp_parts.
 // ------------------------------------------------------------------------------------------
 GB_HD double dmul(double a, double b) {
 #ifdef __CUDA_ARCH__
@@ -113,27 +113,6 @@ GB_HD double dmul(double a, double b) {
 #else
   return a * b;
 #endif
-}
-GB_HD double dexp_parts(double x, int &kout) {
-  double kd = rint(dmul(x, 1.4426950408889634074));
-  double r = fma(kd, -6.93147180369123816490e-01, x);
-  r = fma(kd, -1.90821492927058770002e-10, r);
-  double p = 1.0 / 6227020800.0;
-  p = fma(p, r, 1.0 / 479001600.0);
-  p = fma(p, r, 1.0 / 39916800.0);
-  p = fma(p, r, 1.0 / 3628800.0);
-  p = fma(p, r, 1.0 / 362880.0);
-  p = fma(p, r, 1.0 / 40320.0);
-  p = fma(p, r, 1.0 / 5040.0);
-  p = fma(p, r, 1.0 / 720.0);
-  p = fma(p, r, 1.0 / 120.0);
-  p = fma(p, r, 1.0 / 24.0);
-  p = fma(p, r, 1.0 / 6.0);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  kout = (int)kd;
-  return p;
 }
 GB_HD double pow2i(int e) {
   uint64_t bits = (uint64_t)(e + 1023) << 52;
@@ -144,16 +123,6 @@ GB_HD double pow2i(int e) {
   memcpy(&d, &bits, 8);
   return d;
 #endif
-}
-// floor(exp(x) * 2^b) for x = lw - max <= 0; NaN / -Inf / tiny -> 0
-GB_HD uint64_t quantize(double x, int b) {
-  if (!(x > -708.0)) return 0;
-  if (x > 0.0) x = 0.0;
-  int k;
-  double p = dexp_parts(x, k);
-  int e = k + b;
-  if (e < 0) return 0;
-  return (uint64_t)dmul(p, pow2i(e));
 }
 #ifndef __CUDACC_RTC__
 inline __host__ int quant_bits(int64_t n) {

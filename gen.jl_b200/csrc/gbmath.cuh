@@ -36,7 +36,7 @@ GB_DECL_COEFFS(cos, 6, 4.16666666666666019037e-02, -1.38888888888741095749e-03, 
 GB_DECL_COEFFS(log1p, 6, -0.5, 1.0 / 3.0, -0.25, 0.2, -1.0 / 6.0, 1.0 / 7.0)
 // atan(t), |t| <= 1/128: t - t^3/3 + t^5/5 - t^7/7 + t^9/9
 GB_DECL_COEFFS(atan, 4, -1.0 / 3.0, 0.2, -1.0 / 7.0, 1.0 / 9.0)
-// exp(r), |r| <= ln2/2: Taylor to r^13 (same values as oracle go_dexp: bit-identical quantisation)
+// exp(r), |r| <= ln2/2: Taylor to r^13 (general gb_exp; the weight quantiser has its own table-driven form below)
 GB_DECL_COEFFS(exp, 12, 1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
                1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5)
 GB_DECL_COEFFS(misc, 10, GB_LN2_HI, GB_LN2_LO, GB_PI_HI, GB_PI_LO, GB_PIO2_HI, GB_PIO2_LO,
@@ -154,7 +154,7 @@ GB_HD void gb_sincos2pi(double u, double &s, double &c) {
   c = ((q + 1) & 2) ? -cc : cc;
 }
 
-// exp(x) for |x| < 700 (same reduction and coefficients as the weight quantiser)
+// exp(x) for |x| < 700
 GB_HD double gb_exp_parts(double x, int &kout) {
   const double kd = rint(dmul(x, KC(misc, MI_LOG2E)));
   double r = fma(kd, KC(misc, MI_NLN2_HI), x);
@@ -175,30 +175,71 @@ GB_HD double gb_exp(double x) {
   return p * pow2i(k);
 }
 
-// floor(exp(x) 2^b) for x = lw - max: bit-identical to common.cuh quantize() / oracle go_quantize(), but
-// branch-free and with every coefficient read from the constant bank (the v0 ancestors kernel spent 14%
-// of its issue slots on UMOVs rebuilding these immediates)
-GB_HD uint64_t quantize_k(double x, int b) {
-  const bool dead = !(x > -708.0);            // NaN, -Inf, below the representable floor
-  double xc = dead ? -708.0 : x;
-  xc = xc > 0.0 ? 0.0 : xc;
-  int k;
-  const double p = gb_exp_parts(xc, k);
-  const int e = k + b;
-  const uint64_t q = (uint64_t)dmul(p, pow2i(e < 0 ? 0 : e));
-  return (dead || e < 0) ? 0 : q;
+// ---- the weight exponential of the integer-CDF quantiser (shared bit for bit with the oracle) ----
+// exp(x) for -708 < x <= 0:  x = j ln2/64 + r,  j = rint(x 64/ln2),  |r| <= ln2/128:
+//     exp(x) = 2^(j >> 6) * T[j & 63] * (1 + r + r^2/2 + r^3/6 + r^4/24 + r^5/120)          (truncation < 4e-17)
+// T = 2^(i/64) correctly rounded (64 doubles, staged in shared memory: every lane reads its own entry).  Six fp64
+// operations in a dependency chain four deep, against the 14-deep Horner chain of the general gb_exp: the statistics
+// kernel spent half of its stall samples waiting on that chain (profiles/r2j).  Only rint, fma, * and exact
+// power-of-two scaling, so host, device and oracle produce identical bits.
+__constant__ double c_wexp_tab[64] = {GB_WEXP_TAB_VALUES};
+static const double h_wexp_tab[64] = {GB_WEXP_TAB_VALUES};
+GB_DECL_COEFFS(wexp, 7, GB_WEXP_SCALE, GB_WEXP_NL_HI, GB_WEXP_NL_LO, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5)
+GB_D const double *stage_wexp_table(double *smem /* 64 */) {   // call from every thread of the CTA, then __syncthreads()
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) smem[i] = c_wexp_tab[i];
+  return smem;
 }
-// exp(x) and floor(exp(x) 2^b) from ONE polynomial evaluation (weight statistics pass)
-GB_HD void exp_and_quantize(double x, int b, double &ex, uint64_t &q) {
-  const bool dead = !(x > -708.0);
-  double xc = dead ? -708.0 : x;
-  xc = xc > 0.0 ? 0.0 : xc;
+GB_HD double wexp_parts(double x, int &kout, const double *__restrict__ tab) {
+  const double jd = rint(dmul(x, KC(wexp, 0)));
+  const int j = (int)jd;
+  double r = fma(jd, KC(wexp, 1), x);
+  r = fma(jd, KC(wexp, 2), r);
+  const double r2 = dmul(r, r);
+  const double a = fma(r, KC(wexp, 3), KC(wexp, 4));
+  const double b = fma(r, KC(wexp, 5), KC(wexp, 6));
+  const double c = fma(r2, a, b);
+  const double poly = fma(r2, c, r);
+  const double t = tab[j & 63];
+  kout = j >> 6;
+  return fma(t, poly, t);
+}
+// Arguments of the weight kernels are x = lw - max: -708 < x <= -0.0 or x == +0.0 for every particle that carries weight.
+// Anything else (NaN, -Inf, below the representable floor, or x > 0 when a caller passes a reference below the max) is
+// rare and takes a branch instead of being folded into every evaluation as selects (the selects were 12 of the 65
+// instructions per particle of the statistics kernel).  Integer test on the high word: for x <= -0.0 the magnitude
+// ordering is the unsigned ordering of the bits.
+GB_HD bool wx_regular(double x) {
+  const uint32_t hi = (uint32_t)(dbits(x) >> 32);
+  return ((hi ^ 0x80000000u) < 0x40862000u /* high word of 708.0 (low word 0): -708 < x <= -0.0 */) || x == 0.0;
+}
+// floor(exp(x) 2^b) for x = lw - max: bit-identical to the oracle's go_quantize()
+GB_HD uint64_t quantize_k(double x, int b, const double *__restrict__ wt) {
   int k;
-  const double p = gb_exp_parts(xc, k);
-  const int e = k + b;
-  const uint64_t qq = (uint64_t)dmul(p, pow2i(e < 0 ? 0 : e));
-  q = (dead || e < 0) ? 0 : qq;
-  ex = dead ? 0.0 : p * pow2i(k);
+  if (wx_regular(x)) {
+    const double p = wexp_parts(x, k, wt);
+    const int e = k + b;
+    const uint64_t q = (uint64_t)dmul(p, pow2i(e < 0 ? 0 : e));
+    return e < 0 ? 0 : q;
+  }
+  if (!(x > -708.0)) return 0;                // NaN, -Inf, below the representable floor
+  const double p = wexp_parts(0.0, k, wt);    // x > 0: clamped to 0
+  return (uint64_t)dmul(p, pow2i(k + b));
+}
+// exp(x) and floor(exp(x) 2^b) from ONE evaluation (weight statistics pass)
+GB_HD void exp_and_quantize(double x, int b, double &ex, uint64_t &q, const double *__restrict__ wt) {
+  int k;
+  if (wx_regular(x)) {
+    const double p = wexp_parts(x, k, wt);
+    const int e = k + b;
+    const uint64_t qq = (uint64_t)dmul(p, pow2i(e < 0 ? 0 : e));
+    q = e < 0 ? 0 : qq;
+    ex = p * pow2i(k);
+    return;
+  }
+  if (!(x > -708.0)) { q = 0; ex = 0.0; return; }
+  const double p = wexp_parts(0.0, k, wt);
+  q = (uint64_t)dmul(p, pow2i(k + b));
+  ex = p * pow2i(k);
 }
 
 // atan2(y, x) for finite arguments whose exponents are within +-1000 (anything else: libm)

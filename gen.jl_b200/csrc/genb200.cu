@@ -295,6 +295,7 @@ struct gb_pf {
   // resampling workspace
   long long ntiles = 0;
   uint64_t *tile_q = nullptr;
+  unsigned long long *qbuf = nullptr;   // quantised weights of the last statistics pass (ld entries): what the sweeps scan
   unsigned long long *super_q = nullptr, *super_excl = nullptr;
   long long nsuper = 0;
   OverflowEntry *oflow = nullptr;
@@ -402,7 +403,7 @@ static void pf_release(gb_pf *pf) {
   gb_dev_free(pf->parents64); gb_dev_free(pf->ext_parents); gb_dev_free(pf->partials); gb_dev_free(pf->ticket); gb_dev_free(pf->d_stats);
   gb_host_free(pf->h_stats); gb_dev_free(pf->d_normals); gb_dev_free(pf->d_uniforms); gb_dev_free(pf->d_u64);
   gb_dev_free(pf->d_ctl); gb_host_free(pf->h_ctl); gb_dev_free(pf->d_shplan); gb_host_free(pf->h_shplan); gb_dev_free(pf->d_offs); gb_dev_free(pf->super_q); gb_dev_free(pf->super_excl); gb_dev_free(pf->oflow); gb_dev_free(pf->oflow_count);
-  gb_dev_free(pf->tile_q); gb_dev_free(pf->d_plan);
+  gb_dev_free(pf->tile_q); gb_dev_free(pf->qbuf); gb_dev_free(pf->d_plan);
   gb_dev_free(pf->lik); gb_dev_free(pf->guide); gb_dev_free(pf->tile_save);
   gb_host_free(pf->h_plan); gb_dev_free(pf->cdf); gb_dev_free(pf->off_anc); gb_dev_free(pf->d_tab); gb_dev_free(pf->d_ptab);
   for (auto p : pf->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -1142,22 +1143,26 @@ static int run_wstats(gb_pf *pf, const void *logw, double m_arg, bool from_devic
   memset(&fp, 0, sizeof(fp));
   if (fused) fp = *fused;
   const int bits = quant_bits(pf->n_global);
+  if (!pf->qbuf) CK(gb_dev_alloc((void **)&pf->qbuf, (size_t)pf->ntiles * kTile * 8));
   if (!pf->ws_clean) {       // the systematic sweep leaves both accumulators zeroed; other paths do not
     CK(cudaMemsetAsync(pf->super_q, 0, (size_t)(pf->nsuper + 1) * 8, pf->stream));
     CK(cudaMemsetAsync(pf->tile_q, 0, (size_t)(pf->ntiles + 1) * 8, pf->stream));
   }
   pf->ws_clean = false;
-  if (pf->dtype == GB_F64) {
-    auto kern = wstats_kernel<double>;
-    int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
-    LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const double *)logw, pf->n, m_arg, exchange ? 2 : (from_device ? 1 : 0), bits,
-                                      (unsigned long long *)pf->tile_q, pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl, fp));
-  } else {
-    auto kern = wstats_kernel<float>;
-    int grid = grid_for(pf, kern, pf->ntiles * (kTile / 8), kBlock);
-    LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const float *)logw, pf->n, m_arg, exchange ? 2 : (from_device ? 1 : 0), bits,
-                                      (unsigned long long *)pf->tile_q, pf->super_q, pf->partials, pf->ticket, pf->d_stats, ctl, fp));
+  // large filters: a warp owns whole tiles (plain stores of the tile totals); otherwise 256/512-particle batches + atomics
+  const bool whole = pf->ntiles >= (long long)pf->num_sms * 8 * 4;
+  const int mode = exchange ? 2 : (from_device ? 1 : 0);
+#define GO(R, W)                                                                                                               \
+  {                                                                                                                            \
+    auto kern = wstats_kernel<R, W>;                                                                                           \
+    const long long units = pf->ntiles * (W ? 1 : kTile / (32 * VecOf<R>::V * 4));                                             \
+    int grid = grid_for(pf, kern, units * 32, kBlock);                                                                         \
+    LAUNCH(pf, GB_K_FINALIZE, klaunch(kern, grid, kBlock, pf->stream, (const R *)logw, pf->n, m_arg, mode, bits,                \
+                                      (unsigned long long *)pf->tile_q, pf->super_q, pf->qbuf, pf->partials, pf->ticket, pf->d_stats, ctl, fp)); \
   }
+  if (pf->dtype == GB_F64) { if (whole) GO(double, true) else GO(double, false) }
+  else { if (whole) GO(float, true) else GO(float, false) }
+#undef GO
   CK(cudaGetLastError());
   if (sync_host) {
     CK(cudaMemcpyAsync(pf->h_stats, pf->d_stats, kStatsRecordBytes, cudaMemcpyDeviceToHost, pf->stream));
@@ -1430,13 +1435,11 @@ extern "C" int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out) {
 // resampling
 // ------------------------------------------------------------------------------------------
 // inclusive integer CDF of the current weights into pf->cdf (needs valid tile totals: run_wstats); tile_q becomes its prefix
-template <typename R>
-static int launch_cdf(gb_pf *pf, const void *logw, double m) {
-  const int bits = quant_bits(pf->n_global);
+static int launch_cdf(gb_pf *pf) {
   if (!pf->cdf) CK(gb_dev_alloc((void **)&pf->cdf, (size_t)pf->ld * 8));
   LAUNCH(pf, GB_K_TILESCAN, tilescan_cdf_kernel<<<1, 1024, 0, pf->stream>>>(pf->ntiles, pf->tile_q, pf->d_plan, pf->n_global));
   CK(cudaGetLastError());
-  LAUNCH(pf, GB_K_ANCESTORS, cdf_kernel<R><<<(unsigned)pf->ntiles, kBlock, 0, pf->stream>>>((const R *)logw, pf->n, m, bits, pf->tile_q, pf->cdf));
+  LAUNCH(pf, GB_K_ANCESTORS, cdf_kernel<<<(unsigned)pf->ntiles, kBlock, 0, pf->stream>>>(pf->qbuf, pf->tile_q, pf->cdf));
   CK(cudaGetLastError());
   pf->tiles_valid = false;
   pf->ws_clean = false;
@@ -1454,15 +1457,13 @@ static int launch_systematic(gb_pf *pf, const void *logw, double m, uint64_t q_o
                                       pf->n_global, u0, pf->oflow_count, plan_preset));
   }
   CK(cudaGetLastError());
-  auto kern = ancestors_sys_kernel<R>;
-  LAUNCH(pf, GB_K_ANCESTORS, klaunch(kern, (unsigned)pf->ntiles, kBlock, pf->stream, (const R *)logw, pf->n, m, bits, (const uint64_t *)pf->tile_q,
-                                     (const unsigned long long *)pf->super_excl, (const ResamplePlan *)pf->d_plan, ao, pf->oflow, pf->oflow_count, ctl,
-                                     (const WeightStats *)pf->d_stats));
+  LAUNCH(pf, GB_K_ANCESTORS, klaunch(ancestors_sys_kernel, (unsigned)pf->ntiles, kBlock, pf->stream, (const unsigned long long *)pf->qbuf,
+                                     (const uint64_t *)pf->tile_q, (const unsigned long long *)pf->super_excl, (const ResamplePlan *)pf->d_plan, ao,
+                                     pf->oflow, pf->oflow_count, ctl));
   CK(cudaGetLastError());
-  auto okern = overflow_sys_kernel<R>;
-  LAUNCH(pf, GB_K_ANCESTORS, klaunch(okern, (unsigned)pf->num_sms * 4, kBlock, pf->stream, (const R *)logw, pf->n, m, bits, (const ResamplePlan *)pf->d_plan, ao,
-                                     (const OverflowEntry *)pf->oflow, (const unsigned int *)pf->oflow_count, (unsigned long long *)pf->tile_q, pf->ntiles, ctl,
-                                     (const WeightStats *)pf->d_stats));
+  LAUNCH(pf, GB_K_ANCESTORS, klaunch(overflow_sys_kernel, (unsigned)pf->num_sms * 4, kBlock, pf->stream, (const unsigned long long *)pf->qbuf,
+                                     (const ResamplePlan *)pf->d_plan, ao, (const OverflowEntry *)pf->oflow, (const unsigned int *)pf->oflow_count,
+                                     (unsigned long long *)pf->tile_q, pf->ntiles, ctl));
   CK(cudaGetLastError());
   pf->tiles_valid = false;   // superscan / overflow zeroed the accumulators for the next statistics pass
   pf->ws_clean = true;
@@ -1489,7 +1490,7 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
     CK(cudaMemcpyAsync(pf->tile_save, pf->tile_q, (size_t)(pf->ntiles + 1) * 8, cudaMemcpyDeviceToDevice, pf->stream));
     if ((rc = launch_systematic<R>(pf, logw, m, 0, 0, 0u, AncOut{pf->guide, 0, pf->n_global, nullptr, 0, 0}))) return rc;
     CK(cudaMemcpyAsync(pf->tile_q, pf->tile_save, (size_t)(pf->ntiles + 1) * 8, cudaMemcpyDeviceToDevice, pf->stream));
-    if ((rc = launch_cdf<R>(pf, logw, m))) return rc;
+    if ((rc = launch_cdf(pf))) return rc;
     int grid = grid_for(pf, multinomial_guided_kernel, pf->n, kBlock);
     LAUNCH(pf, GB_K_ANCESTORS, multinomial_guided_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->cdf, pf->guide, pf->n, pf->d_plan, d_u64, seed,
                                                                                           step, pf->n, anc, (unsigned)PK_MULTI));
@@ -1542,8 +1543,7 @@ extern "C" int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t 
   const double m = pf->h_stats->m;
   if (!(m > -INFINITY)) return fail(GB_ESTATE, "gb_pf_sample_unweighted: all log weights are -Inf or NaN");
   if (!pf->tiles_valid && (rc = run_wstats(pf, pf->logw, m, false))) return rc;
-  rc = pf->dtype == GB_F64 ? launch_cdf<double>(pf, pf->logw, m) : launch_cdf<float>(pf, pf->logw, m);
-  if (rc) return rc;
+  if ((rc = launch_cdf(pf))) return rc;
   int *d_idx = nullptr;
   long long *d_idx1 = nullptr;
   double *d_rows = nullptr;
@@ -2463,7 +2463,7 @@ extern "C" int64_t gb_selftest_slots_below_residual(uint64_t chi, uint64_t clo, 
   return slots_below_residual(chi, clo, sp);
 }
 extern "C" uint64_t gb_selftest_div128(uint64_t ahi, uint64_t alo, uint64_t d) { return div128_64(ahi, alo, d, 1.0 / (double)d); }
-extern "C" uint64_t gb_selftest_quantize(double x, int bits) { return quantize_k(x, bits) == quantize(x, bits) ? quantize_k(x, bits) : ~0ull; }
+extern "C" uint64_t gb_selftest_quantize(double x, int bits) { return quantize_k(x, bits, h_wexp_tab); }
 // fn: 0 log(a), 1 sin(2 pi a), 2 cos(2 pi a), 3 atan2(a, b), 4 exp(a), 5 u52_fast(hi = a, lo = b)
 extern "C" double gb_selftest_math(int fn, double a, double b) {
   MathTables T = host_math_tables();

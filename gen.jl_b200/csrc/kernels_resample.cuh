@@ -109,23 +109,20 @@ __global__ void __launch_bounds__(1024) tilescan_cdf_kernel(long long ntiles, ui
     plan->slot_hi = n_global;
   }
 }
-template <typename R>
-__global__ void __launch_bounds__(kBlock) cdf_kernel(const R *__restrict__ logw, long long n, double m, int bits,
-                                                     const uint64_t *__restrict__ tile_q, uint64_t *__restrict__ cdf_out) {
+__global__ void __launch_bounds__(kBlock) cdf_kernel(const unsigned long long *__restrict__ qbuf, const uint64_t *__restrict__ tile_q,
+                                                     uint64_t *__restrict__ cdf_out) {
   __shared__ uint64_t s_warp64[kBlock / 32 + 1];
   const long long tile = blockIdx.x;
-  double lw[kItems];
-  load_items<R>(logw, tile * kTile, n, lw);
+  const long long i0 = tile * kTile + (long long)threadIdx.x * kItems;
   uint64_t c[kItems];
   uint64_t t = 0;
 #pragma unroll
   for (int j = 0; j < kItems; j++) {
-    t += quantize_k(lw[j] - m, bits);
+    t += __ldcs(qbuf + i0 + j);
     c[j] = t;
   }
   uint64_t total;
   const uint64_t base = tile_q[tile] + block_exclusive_scan(t, s_warp64, &total);
-  const long long i0 = tile * kTile + (long long)threadIdx.x * kItems;
 #pragma unroll
   for (int j = 0; j < kItems; j++) cdf_out[i0 + j] = base + c[j];
 }
@@ -349,8 +346,8 @@ struct AncOut {
   long long spill_cap;      // entries in the spill buffer (writes beyond it are dropped: the plan flags the overflow)
 };
 
-constexpr int kHeavyCap = 16;                       // offspring a thread writes itself; more => CTA-cooperative fill
-constexpr int kHeavyMax = kChunk / (kHeavyCap + 1) + 2;
+constexpr int kBlk = 8;                             // output slots per fill block: two 128-bit stores per thread
+constexpr int kEndSlots = kChunk + 2 * kBlk;        // histogram entries of one window (+ alignment slack)
 
 // number of slots below CDF value C: double-precision estimate, exact only when the estimate is within
 // 2^-17 slots of a boundary; `slow` is set instead of branching so callers can batch the rare fix-ups
@@ -366,32 +363,81 @@ GB_D int slots_estimate(uint64_t C, double ratio, double u0term, bool &slow) {
 // Shared-memory scratch of one ancestors CTA
 struct TileSmem {
   uint64_t warp64[kBlock / 32 + 1];
-  int slot[kChunk];
-  int kend_last[kBlock];
-  int3 heavy[kHeavyMax];      // (particle, first slot, end slot) of particles with many offspring
-  int nheavy;
+  // ends[ends_index(x)] = number of particles whose offspring range ends at window slot x - sh.  One padding word per 8
+  // entries: consecutive lanes add at positions ~8 apart (one offspring per particle on average), which would be an 8-way
+  // bank conflict on every reduction in a dense array; with the padding they -- and the block-wise reads, stride 9 -- spread
+  // over all 32 banks.
+  __align__(16) int ends[kEndSlots + kEndSlots / 8];
+  int warp32[kBlock / 32 + 1];
   uint64_t cbase;
-  long long slot0;
+  long long slot0, slot_end;
 };
+GB_D int ends_index(int x) { return x + (x >> 3); }
+GB_D void tile_smem_clear(TileSmem &sm) {   // the histogram must be all zero on entry of tile_fill
+  int4 *z = reinterpret_cast<int4 *>(sm.ends);
+  for (int i = threadIdx.x; i < (kEndSlots + kEndSlots / 8) / 4; i += kBlock) z[i] = make_int4(0, 0, 0, 0);
+  __syncthreads();
+}
+// the 8 counts of fill block B (read and cleared)
+GB_D void ends_take(TileSmem &sm, int B, int (&v)[kBlk]) {
+  int *p = sm.ends + 9 * B;
+#pragma unroll
+  for (int e = 0; e < kBlk; e++) { v[e] = p[e]; p[e] = 0; }
+}
+// exclusive block scan of one int per thread
+GB_D int block_exclusive_scan_i32(int v, int *s_warp /* kBlock/32 + 1 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = lane < kBlock / 32 ? s_warp[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int d = 1; d < kBlock / 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += o;
+    }
+    if (lane < kBlock / 32) s_warp[lane] = winc - w;
+  }
+  __syncthreads();
+  return s_warp[warp] + (inc - v);
+}
 
 // Scan one tile and fill the ancestors of the output slots [lo, hi) (hi - lo <= kChunk) that belong to it.
 //   PREFIX = true : regular CTA.  cbase (integer CDF mass before the tile) is produced by warp 0 from the
 //                   super-tile prefix while the other warps already quantise; [lo, hi) = the tile's first
 //                   kChunk slots; returns the tile's slot range through slot0_out / slot_end_out.
 //   PREFIX = false: overflow CTA.  cbase / slot0 / [lo, hi) are given.
-// Fill: every particle writes its own (usually 0-2) offspring slots into a shared window; particles with
-// more than kHeavyCap offspring are queued and their ranges filled by the whole CTA; the window is then
-// copied out with coalesced stores.  (v1 used head flags + a max-scan: 127 of its 162 instructions per
-// particle were fill bookkeeping, profiles/r1_ancestors.md.)
-template <typename R, bool PREFIX>
-GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits, const SweepParams &sp, long long tile,
+// Fill (r2): the ancestor of window slot i is the number of particles of the tile whose offspring range ends at or before
+// i.  So every particle adds ONE count at its end slot (a shared-memory reduction, whatever its number of offspring), a
+// block-wide prefix sum over the window turns the counts into ancestors, and every thread writes its 8 consecutive
+// slots -- aligned to the destination array -- with two 128-bit stores.  Work is proportional to particles + slots and
+// every memory operation is independent of the others.  (The r1 fill let every particle write its own slots into a
+// shared-memory window: the per-lane loops over 3+ offspring ran in lock step to the LONGEST range of the warp and were
+// 24% of the kernel's instructions, profiles/r2f; a walk over sorted end slots per 8-slot block removed the loops but
+// serialised on shared-memory latency and was slower still, 0.66 vs 0.48 ms.)  sm.ends is all zero on entry and on exit.
+template <bool PREFIX>
+GB_D void tile_fill(const unsigned long long *__restrict__ qbuf, const SweepParams &sp, long long tile,
                     const uint64_t *__restrict__ tile_q, const unsigned long long *__restrict__ super_excl, uint64_t q_offset,
                     uint64_t cbase_in, long long slot0_in, long long lo_in, long long hi_in, const AncOut &ao,
                     long long spill_base, TileSmem &sm, long long *slot0_out, long long *slot_end_out) {
-  double lw[kItems];
-  load_items<R>(logw, tile * kTile, n, lw);
+  // the quantised weights of the tile as the statistics pass left them (q = 0 beyond n): no second exp per particle
+  uint64_t qv[kItems];
+  {
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(qbuf + tile * kTile + (long long)threadIdx.x * kItems);
+#pragma unroll
+    for (int j = 0; j < kItems; j += 2) {
+      const ulonglong2 t2 = __ldcs(src + j / 2);
+      qv[j] = t2.x; qv[j + 1] = t2.y;
+    }
+  }
   const double u0term = -(double)sp.u0 * 0x1p-32;
-  if (threadIdx.x == 0) sm.nheavy = 0;
   if (PREFIX && threadIdx.x < 32) {
     // CDF mass before this tile: super-tile prefix + the (<= 63) tile totals before it inside the super-tile
     const long long sbase = (tile / kSuper) * kSuper;
@@ -404,7 +450,7 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
   uint64_t t = 0;
 #pragma unroll
   for (int j = 0; j < kItems; j++) {
-    t += quantize_k(lw[j] - m, bits);
+    t += qv[j];
     c[j] = t;
   }
   uint64_t total;
@@ -424,7 +470,7 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
     for (int j = 0; j < kItems; j++)
       if (slow & (1u << j)) kend[j] = (int)slots_below(cbase + ex + c[j], sp);
   }
-  sm.kend_last[threadIdx.x] = kend[kItems - 1];
+  if (threadIdx.x == kBlock - 1) sm.slot_end = kend[kItems - 1];
   if (PREFIX && threadIdx.x == 0) {
     bool sl;
     int s0 = slots_estimate(cbase, sp.ratio, u0term, sl);
@@ -433,72 +479,110 @@ GB_D void tile_fill(const R *__restrict__ logw, long long n, double m, int bits,
   }
   __syncthreads();
   const long long slot0 = PREFIX ? sm.slot0 : slot0_in;
-  const long long slot_end = sm.kend_last[kBlock - 1];
+  const long long slot_end = sm.slot_end;
   if (PREFIX) { *slot0_out = slot0; *slot_end_out = slot_end; }
   const long long lo = PREFIX ? slot0 : lo_in;
   long long hi = PREFIX ? slot_end : hi_in;
   if (PREFIX && hi > lo + kChunk) hi = lo + kChunk;
   const int cnt = (int)(hi - lo);
   if (cnt <= 0) return;                       // uniform across the CTA
-  // particle j owns slots [kstart_j, kend_j)
-  int kstart = threadIdx.x == 0 ? (int)slot0 : sm.kend_last[threadIdx.x - 1];
-  const int ilo = (int)lo, ihi = (int)hi;
+  // fill blocks are aligned to the destination: window slot i goes to own[d0 + i] and sits at histogram position
+  // x = i + sh, sh = d0 mod 8; block B covers x in [8 B, 8 B + 8)
+  const long long d0 = lo - ao.own_lo;
+  const int sh = (int)(d0 & (kBlk - 1));
+  const int ilo = (int)lo;
 #pragma unroll
   for (int j = 0; j < kItems; j++) {
-    const int a0 = (kstart > ilo ? kstart : ilo) - ilo, a1 = (kend[j] < ihi ? kend[j] : ihi) - ilo;
-    const int id = threadIdx.x * kItems + j;
-    const int cnt_j = a1 - a0;
-    if (cnt_j > kHeavyCap) {
-      sm.heavy[atomicAdd(&sm.nheavy, 1)] = make_int3(id, a0, a1);
-    } else {
-      // 0, 1 or 2 offspring is the common case after regular resampling: two predicated stores, no loop
-      if (cnt_j > 0) sm.slot[a0] = id;
-      if (cnt_j > 1) sm.slot[a0 + 1] = id;
-      for (int k = a0 + 2; k < a1; k++) sm.slot[k] = id;
-    }
-    kstart = kend[j];
+    int x = kend[j] - ilo;                    // the particle's range ends at window slot x: it precedes the owners of slots >= x
+    x = x < 0 ? 0 : x;                        // (overflow pieces: ended before the window)
+    if (x < cnt) atomicAdd(&sm.ends[ends_index(x + sh)], 1);
   }
   __syncthreads();
-  const int nh = sm.nheavy;
-  for (int e = 0; e < nh; e++) {
-    const int3 h = sm.heavy[e];
-    for (int k = h.y + threadIdx.x; k < h.z; k += kBlock) sm.slot[k] = h.x;
-  }
-  if (nh) __syncthreads();
-  // coalesced copy-out
   const int tile_base = (int)(tile * kTile);
-  if (lo >= ao.own_lo && hi <= ao.own_hi) {     // the usual case (always, on a single shard): every slot is this shard's own
-    int *__restrict__ dst = ao.own + (lo - ao.own_lo);
-    for (int i = threadIdx.x; i < cnt; i += kBlock) __stcs(dst + i, tile_base + sm.slot[i]);
+  const int nblk = ((cnt - 1 + sh) >> 3) + 1;
+  const int per = (nblk + kBlock - 1) / kBlock;            // consecutive blocks per thread: 1, unless the tile owns > 2048 slots
+  const bool owned = lo >= ao.own_lo && hi <= ao.own_hi;   // the usual case (always, on a single shard): every slot is this shard's own
+  int run;
+  if (per == 1) {
+    const int B = threadIdx.x;
+    int v[kBlk] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (B < nblk) ends_take(sm, B, v);                      // (leaves the histogram clean)
+#pragma unroll
+    for (int e = 1; e < kBlk; e++) v[e] += v[e - 1];
+    run = tile_base + block_exclusive_scan_i32(v[kBlk - 1], sm.warp32);
+    if (B < nblk) {
+      const int s = (B << 3) - sh;                          // window slot of element 0 (< 0 only for block 0)
+      if (owned && s >= 0 && s + kBlk <= cnt) {
+        int4 *dst = reinterpret_cast<int4 *>(ao.own + (d0 + s));
+        __stcs(dst, make_int4(run + v[0], run + v[1], run + v[2], run + v[3]));
+        __stcs(dst + 1, make_int4(run + v[4], run + v[5], run + v[6], run + v[7]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < kBlk; e++) {
+          const int i = s + e;
+          if (i < 0 || i >= cnt) continue;
+          const long long k = lo + i;
+          if (k >= ao.own_lo && k < ao.own_hi) __stcs(ao.own + (k - ao.own_lo), run + v[e]);
+          else if (k - spill_base >= 0 && k - spill_base < ao.spill_cap) __stcs(ao.spill + (k - spill_base), run + v[e]);
+        }
+      }
+    }
     return;
   }
-  for (int i = threadIdx.x; i < cnt; i += kBlock) {
-    const long long k = lo + i;
-    if (k >= ao.own_lo && k < ao.own_hi) __stcs(ao.own + (k - ao.own_lo), tile_base + sm.slot[i]);
-    else if (k - spill_base < ao.spill_cap) __stcs(ao.spill + (k - spill_base), tile_base + sm.slot[i]);
+  // heavy tile (more than 2048 slots in the window): `per` consecutive blocks per thread, two passes over them
+  const int B0 = threadIdx.x * per;
+  int tot = 0;
+  for (int q = 0; q < per; q++) {
+    const int B = B0 + q;
+    if (B >= nblk) break;
+    const int *src = sm.ends + 9 * B;
+#pragma unroll
+    for (int e = 0; e < kBlk; e++) tot += src[e];
+  }
+  run = tile_base + block_exclusive_scan_i32(tot, sm.warp32);
+  for (int q = 0; q < per; q++) {
+    const int B = B0 + q;
+    if (B >= nblk) break;
+    int v[kBlk];
+    ends_take(sm, B, v);
+#pragma unroll
+    for (int e = 1; e < kBlk; e++) v[e] += v[e - 1];
+    const int s = (B << 3) - sh;
+    if (owned && s >= 0 && s + kBlk <= cnt) {
+      int4 *dst = reinterpret_cast<int4 *>(ao.own + (d0 + s));
+      __stcs(dst, make_int4(run + v[0], run + v[1], run + v[2], run + v[3]));
+      __stcs(dst + 1, make_int4(run + v[4], run + v[5], run + v[6], run + v[7]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < kBlk; e++) {
+        const int i = s + e;
+        if (i < 0 || i >= cnt) continue;
+        const long long k = lo + i;
+        if (k >= ao.own_lo && k < ao.own_hi) __stcs(ao.own + (k - ao.own_lo), run + v[e]);
+        else if (k - spill_base >= 0 && k - spill_base < ao.spill_cap) __stcs(ao.spill + (k - spill_base), run + v[e]);
+      }
+    }
+    run += v[kBlk - 1];
   }
 }
 
-template <typename R>
-__global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const R *__restrict__ logw, long long n, double m, int bits,
+__global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const unsigned long long *__restrict__ qbuf,
                                                                const uint64_t *__restrict__ tile_q,
                                                                const unsigned long long *__restrict__ super_excl,
                                                                const ResamplePlan *__restrict__ plan, const AncOut ao,
                                                                OverflowEntry *__restrict__ oflow,
                                                                unsigned int *__restrict__ oflow_count,
-                                                               const RunCtl *__restrict__ ctl, const WeightStats *__restrict__ dstats) {
+                                                               const RunCtl *__restrict__ ctl) {
   __shared__ TileSmem sm;
   pdl_trigger();
+  tile_smem_clear(sm);             // (constant work: overlaps the predecessor's tail)
   pdl_wait();
-  if (ctl) {                       // fused multi-step run: decision and reference max live on the device
-    if (!ctl->do_resample) return;
-    m = dstats->m;
-  }
+  if (ctl && !ctl->do_resample) return;      // fused multi-step run: the decision lives on the device
   const SweepParams sp = plan->sp;
   const long long tile = blockIdx.x;
   long long slot0, slot_end;
   const long long spill_base = ao.spill_base >= 0 ? ao.spill_base : plan->slot_lo;
-  tile_fill<R, true>(logw, n, m, bits, sp, tile, tile_q, super_excl, plan->q_offset, 0, 0, 0, 0, ao, spill_base, sm, &slot0, &slot_end);
+  tile_fill<true>(qbuf, sp, tile, tile_q, super_excl, plan->q_offset, 0, 0, 0, 0, ao, spill_base, sm, &slot0, &slot_end);
   if (slot_end > slot0 + kChunk && threadIdx.x == 0) {
     const unsigned int e = atomicAdd(oflow_count, 1u);
     oflow[e] = OverflowEntry{tile, slot0, slot0 + kChunk, slot_end, sm.cbase};
@@ -507,17 +591,16 @@ __global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const R *__restri
 
 // Remaining slots of heavy tiles: work unit = (queue entry, kChunk-sized piece); units are dealt
 // round-robin to the CTAs of a fixed-size grid.
-template <typename R>
-__global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restrict__ logw, long long n, double m, int bits,
+__global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const unsigned long long *__restrict__ qbuf,
                                                               const ResamplePlan *__restrict__ plan, const AncOut ao,
                                                               const OverflowEntry *__restrict__ oflow,
                                                               const unsigned int *__restrict__ oflow_count,
                                                               unsigned long long *__restrict__ tile_q, long long ntiles,
-                                                              const RunCtl *__restrict__ ctl, const WeightStats *__restrict__ dstats) {
+                                                              const RunCtl *__restrict__ ctl) {
   __shared__ TileSmem sm;
   pdl_trigger();
+  tile_smem_clear(sm);
   pdl_wait();
-  if (ctl) m = dstats->m;
   // the sweep is done with the per-tile totals: leave the accumulator clean for the next statistics pass
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < ntiles; i += (long long)gridDim.x * kBlock) tile_q[i] = 0;
   const unsigned int ne = *oflow_count;
@@ -534,7 +617,7 @@ __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const R *__restric
       long long hi = lo + kChunk;
       if (hi > en.slot_hi) hi = en.slot_hi;
       __syncthreads();
-      tile_fill<R, false>(logw, n, m, bits, sp, en.tile, nullptr, nullptr, 0, en.cbase, en.slot0, lo, hi, ao,
+      tile_fill<false>(qbuf, sp, en.tile, nullptr, nullptr, 0, en.cbase, en.slot0, lo, hi, ao,
                           ao.spill_base >= 0 ? ao.spill_base : plan->slot_lo, sm, nullptr, nullptr);
     }
     unit0 += pieces;

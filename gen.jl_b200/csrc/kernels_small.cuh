@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(kSmallThreads, 1) small_run_kernel(const Small
   __shared__ uint64_t s_u[kSmallThreads / 32 + 1];
   __shared__ int3 s_heavy[kSmallMax / kSmallHeavyCap + 1];
   __shared__ int s_nheavy;
+  __shared__ double s_wexp[64];
   const MathTables T = stage_math_tables(s_tab);
+  const double *wt = stage_wexp_table(s_wexp);
   __syncthreads();
   const int n = (int)a.n;
   const int per = (n + kSmallThreads - 1) / kSmallThreads;       // particles per thread (blocked layout): <= P
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) small_run_kernel(const Small
     for (int j = 0; j < P; j++) {
       double e = 0.0;
       uint64_t q = 0;
-      if (j < per && i0 + j < n) exp_and_quantize((double)lw[j] - m, a.bits, e, q);
+      if (j < per && i0 + j < n) exp_and_quantize((double)lw[j] - m, a.bits, e, q, wt);
       s1 += e;
       s2 = fma(e, e, s2);
       qt += q;

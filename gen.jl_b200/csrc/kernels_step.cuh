@@ -232,6 +232,19 @@ __global__ void xchg_post_max_kernel(WeightStats *stats) {
 #ifndef GB_STEP_MINB
 #define GB_STEP_MINB 3
 #endif
+// Shared-memory staging of the deferred gather: every thread copies the ancestor rows of its NEXT iteration into its own
+// shared-memory slots with asynchronous copies (cp.async: global -> shared without passing through registers, a deep
+// queue per SM) while the current iteration computes, and reads them back one iteration later.  0: the r1 scheme (L2
+// prefetch of the next rows, ld.global.nc at the point of use).
+#ifndef GB_STEP_STAGE
+#define GB_STEP_STAGE 0
+#endif
+template <int BYTES> GB_D void cp_async(void *smem_dst, const void *gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+GB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> GB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 template <typename R, int KIND, int PK, bool INIT, bool PREDRAWN, int GATHER /* 0 no, 1 yes, 2 ctl->do_resample */>
 __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepArgs a) {
   // R is the STORAGE type (traces, log weights, noise); the transition itself (propose + logpdf) is always evaluated in
@@ -265,9 +278,22 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
     else { int4 t = __ldcs(reinterpret_cast<const int4 *>(a.anc + ivx * V)); dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w; }
   };
   const bool gather = GATHER == 2 ? (a.ctl->do_resample != 0) : (GATHER == 1);
+  // staged gather: [stage][field][v][thread] -- a thread only ever touches its own column, so the asynchronous copies
+  // need no barrier, just cp.async.wait_group
+  constexpr bool STAGE = GB_STEP_STAGE && !INIT && GATHER != 0 && S > 0 && (2 * (S > 0 ? S : 1) * V * (int)sizeof(R) * kBlock <= 40 * 1024);
+  __shared__ __align__(16) R s_stage[STAGE ? 2 : 1][STAGE ? S : 1][STAGE ? V : 1][STAGE ? kBlock : 1];
+  auto stage_rows = [&](int st, const int (&src)[V]) {
+#pragma unroll
+    for (int s = 0; s < S; s++)
+#pragma unroll
+      for (int v = 0; v < V; v++) cp_async<(int)sizeof(R)>(&s_stage[STAGE ? st : 0][STAGE ? s : 0][STAGE ? v : 0][STAGE ? threadIdx.x : 0], sin + (long long)s * a.ld + src[v]);
+    cp_async_commit();
+  };
+  int stage = 0;
   if (!INIT && gather) {
     if (iv < nvec) load_anc(iv, src_cur);
     if (iv + stride < nvec) load_anc(iv + stride, src_nxt);
+    if (STAGE && iv < nvec) stage_rows(0, src_cur);
   }
   for (; iv < nvec; iv += stride) {
     const long long i0 = iv * V;
@@ -277,21 +303,37 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
       if (gather) {
         // deferred maybe_resample! gather (particle_filter.jl:264-267): slot k continues the trace of
         // ancestor anc[k]; its log weight was reset to exactly 0.0
-#pragma unroll
-        for (int s = 0; s < S; s++)
-#pragma unroll
-          for (int v = 0; v < V; v++) prev[s][v] = __ldg(sin + (long long)s * a.ld + src_cur[v]);
-#pragma unroll
-        for (int v = 0; v < V; v++) lw_old[v] = R(0);
-        if (iv + stride < nvec) {
+        if constexpr (STAGE) {
+          const bool more = iv + stride < nvec;
+          if (more) stage_rows(stage ^ 1, src_nxt);          // the next iteration's rows start flowing now
+          if (more) cp_async_wait<1>(); else cp_async_wait<0>();   // this iteration's rows (committed one iteration ago) are in
 #pragma unroll
           for (int s = 0; s < S; s++)
 #pragma unroll
-            for (int v = 0; v < V; v++) prefetch_l2(sin + (long long)s * a.ld + src_nxt[v]);
+            for (int v = 0; v < V; v++) prev[s][v] = s_stage[stage][s][v][threadIdx.x];
+          stage ^= 1;
+          if (more) {
 #pragma unroll
-          for (int v = 0; v < V; v++) src_cur[v] = src_nxt[v];
-          if (iv + 2 * stride < nvec) load_anc(iv + 2 * stride, src_nxt);
+            for (int v = 0; v < V; v++) src_cur[v] = src_nxt[v];
+            if (iv + 2 * stride < nvec) load_anc(iv + 2 * stride, src_nxt);
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < S; s++)
+#pragma unroll
+            for (int v = 0; v < V; v++) prev[s][v] = __ldg(sin + (long long)s * a.ld + src_cur[v]);
+          if (iv + stride < nvec) {
+#pragma unroll
+            for (int s = 0; s < S; s++)
+#pragma unroll
+              for (int v = 0; v < V; v++) prefetch_l2(sin + (long long)s * a.ld + src_nxt[v]);
+#pragma unroll
+            for (int v = 0; v < V; v++) src_cur[v] = src_nxt[v];
+            if (iv + 2 * stride < nvec) load_anc(iv + 2 * stride, src_nxt);
+          }
         }
+#pragma unroll
+        for (int v = 0; v < V; v++) lw_old[v] = R(0);
       } else {
 #pragma unroll
         for (int s = 0; s < S; s++) svload<R, V>(sin + (long long)s * a.ld + i0, prev[s]);
@@ -513,22 +555,35 @@ GB_D uint64_t block_sum_u64(uint64_t v, uint64_t *smem /* kBlock/32 */) {
   return r;  // valid in every thread
 }
 
-// Each WARP owns 256-particle segments (no CTA barrier in the streaming loop): striped 128-bit loads,
-// one exp per particle, 64-bit shuffle reduction of the quantised mass, two integer atomics per segment
-// (tile_q / super_q must be zeroed by the caller).
-template <typename R>
-__global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ logw, long long n, double m_arg, int m_from_device,
+// Each WARP owns whole 2048-particle tiles (no CTA barrier and no atomics on the tile totals in the streaming loop):
+// striped 128-bit loads in batches of four per lane, the next batch in flight while the current one is evaluated, one exp
+// per particle, ONE 64-bit shuffle reduction of the quantised mass per tile.  (r1: 256-particle segments with a shuffle
+// reduction + two atomics each and bounds selects on every element: 65 instructions per particle, 13% of them the selects.)
+// WHOLE = false: the unit of work of a warp is one batch (256 fp64 / 512 fp32 particles) and the tile totals are
+// accumulated with atomics (tile_q zeroed by the caller) -- mid-size filters, where whole tiles would leave SMs idle.
+// (98 registers unconstrained = 2 CTAs/SM; 3 CTAs/SM measured fastest: 0.224 vs 0.236 ms at N = 1e8, 4 CTAs/SM 0.235)
+#ifndef GB_WSTATS_MINB
+#define GB_WSTATS_MINB 3
+#endif
+template <typename R, bool WHOLE>
+__global__ void __launch_bounds__(kBlock, GB_WSTATS_MINB) wstats_kernel(const R *__restrict__ logw, long long n, double m_arg, int m_from_device,
                                                         int bits, unsigned long long *__restrict__ tile_q,
-                                                        unsigned long long *__restrict__ super_q, double2 *partials,
-                                                        unsigned int *ticket, WeightStats *stats, RunCtl *ctl, const FusedPlan fp) {
+                                                        unsigned long long *__restrict__ super_q, unsigned long long *__restrict__ qout,
+                                                        double2 *partials, unsigned int *ticket, WeightStats *stats, RunCtl *ctl,
+                                                        const FusedPlan fp) {
   constexpr int V = VecOf<R>::V;
-  constexpr int kSeg = 256, kPerLane = kSeg / 32, kLoads = kPerLane / V;
+  constexpr int kB = 4;                              // loads per lane and batch
+  constexpr int kPerTile = kTile / (32 * V * kB);    // batches per tile: 8 (fp64) / 4 (fp32)
+  constexpr int kNB = WHOLE ? kPerTile : 1;          // batches per unit of work
   __shared__ uint64_t s_u64[kBlock / 32];
   __shared__ uint64_t s_u64_33[33];
   __shared__ double2 s_d2[kBlock / 32];
   __shared__ bool s_last;
   __shared__ double s_m;
+  __shared__ double s_wexp[64];
   pdl_trigger();
+  const double *wt = stage_wexp_table(s_wexp);       // constants only: overlaps the predecessor's tail
+  __syncthreads();
   pdl_wait();
   double m = m_from_device ? __ldcg(&stats->m) : m_arg;
   XchgCtl *xc = m_from_device == 2 ? stats->xc : nullptr;
@@ -548,49 +603,82 @@ __global__ void __launch_bounds__(kBlock) wstats_kernel(const R *__restrict__ lo
     m = s_m;
   }
   const long long ntiles = (n + kTile - 1) / kTile;
-  const long long nseg = ntiles * (kTile / kSeg);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double s1 = 0.0, s2 = 0.0;
-  // register double buffering: the next segment's four 128-bit loads are in flight while this one is
-  // evaluated (v1 was 41% long-scoreboard: one segment of loads per warp at a time)
-  const long long sstride = (long long)gridDim.x * (kBlock / 32);
-  long long seg = (long long)blockIdx.x * (kBlock / 32) + warp;
-  R cur[kLoads][V], nxt[kLoads][V];
-  if (seg < nseg) {
+  // units of work: unit u covers batches [u * kNB, (u + 1) * kNB) of the flat batch sequence; batch g lives in tile
+  // g / kPerTile at element offset ((g % kPerTile) * kB + l) * 32 * V + lane * V   (arrays are padded to whole tiles)
+  const long long nunits = ntiles * (kPerTile / kNB);
+  const long long ustride = (long long)gridDim.x * (kBlock / 32);
+  long long unit = (long long)blockIdx.x * (kBlock / 32) + warp;
+  int bi = 0;
+  R cur[kB][V], nxt[kB][V];
+  auto load_batch = [&](long long g, R (&dst)[kB][V]) {
+    const long long off = (g / kPerTile) * kTile + (long long)(g % kPerTile) * (kB * 32 * V);
 #pragma unroll
-    for (int j = 0; j < kLoads; j++) vload_keep<R>(logw + seg * kSeg + (long long)(j * 32 + lane) * V, cur[j]);
-  }
-  for (; seg < nseg; seg += sstride) {
-    const long long base = seg * kSeg;
-    const bool full = base + kSeg <= n;
-    if (seg + sstride < nseg) {
+    for (int l = 0; l < kB; l++) vload_keep<R>(logw + off + (long long)(l * 32 + lane) * V, dst[l]);
+  };
+  if (unit < nunits) load_batch(unit * kNB, cur);
+  uint64_t sq = 0;
+  while (unit < nunits) {
+    long long nunit = unit;
+    int nbi = bi + 1;
+    if (nbi == kNB) { nbi = 0; nunit += ustride; }
+    if (nunit < nunits) load_batch(nunit * kNB + nbi, nxt);
+    const long long g = unit * kNB + bi;
+    const long long tile = g / kPerTile;
+    const long long base = tile * kTile + (long long)(g % kPerTile) * (kB * 32 * V);
+    // the quantised weights are kept (8 B per particle, 0 beyond n): the ancestors pass scans THEM instead of evaluating the
+    // exponential a second time -- it was issue-bound with a third of its instructions in that exp (profiles/r2j)
+    unsigned long long *qdst = qout + base + (long long)lane * V;
+    if (base + kB * 32 * V <= n) {                   // warp-uniform: whole batch inside the array, no bounds selects
 #pragma unroll
-      for (int j = 0; j < kLoads; j++) vload_keep<R>(logw + (seg + sstride) * kSeg + (long long)(j * 32 + lane) * V, nxt[j]);
-    }
-    uint64_t sq = 0;
+      for (int l = 0; l < kB; l++) {
+        uint64_t qv[V];
 #pragma unroll
-    for (int j = 0; j < kLoads; j++) {
-      const long long i0 = base + (long long)(j * 32 + lane) * V;   // padded arrays: always in bounds
+        for (int k = 0; k < V; k++) {
+          double e;
+          exp_and_quantize((double)cur[l][k] - m, bits, e, qv[k], wt);
+          s1 += e;
+          s2 = fma(e, e, s2);
+          sq += qv[k];
+        }
 #pragma unroll
-      for (int k = 0; k < V; k++) {
-        double e;
-        uint64_t q;
-        const double lw = (full || i0 + k < n) ? (double)cur[j][k] : -INFINITY;
-        exp_and_quantize(lw - m, bits, e, q);
-        s1 += e;
-        s2 = fma(e, e, s2);
-        sq += q;
+        for (int k = 0; k < V; k += 2)
+          *reinterpret_cast<ulonglong2 *>(qdst + (long long)l * 32 * V + k) = make_ulonglong2(qv[k], qv[k + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int l = 0; l < kB; l++) {
+        uint64_t qv[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) {
+          double e;
+          const long long i = base + (long long)(l * 32 + lane) * V + k;
+          exp_and_quantize(i < n ? (double)cur[l][k] - m : -INFINITY, bits, e, qv[k], wt);
+          s1 += e;
+          s2 = fma(e, e, s2);
+          sq += qv[k];
+        }
+#pragma unroll
+        for (int k = 0; k < V; k += 2)
+          *reinterpret_cast<ulonglong2 *>(qdst + (long long)l * 32 * V + k) = make_ulonglong2(qv[k], qv[k + 1]);
       }
     }
-    sq = warp_sum_u64(sq);
-    if (lane == 0) {
-      atomicAdd(tile_q + seg / (kTile / kSeg), (unsigned long long)sq);
-      atomicAdd(super_q + seg / (kTile / kSeg) / kSuper, (unsigned long long)sq);
+    if (bi == kNB - 1) {                             // unit done: its integer CDF mass
+      sq = warp_sum_u64(sq);
+      if (lane == 0) {
+        if (WHOLE) tile_q[tile] = (unsigned long long)sq;
+        else atomicAdd(tile_q + tile, (unsigned long long)sq);
+        atomicAdd(super_q + tile / kSuper, (unsigned long long)sq);
+      }
+      sq = 0;
     }
 #pragma unroll
-    for (int j = 0; j < kLoads; j++)
+    for (int l = 0; l < kB; l++)
 #pragma unroll
-      for (int k = 0; k < V; k++) cur[j][k] = nxt[j][k];
+      for (int k = 0; k < V; k++) cur[l][k] = nxt[l][k];
+    unit = nunit;
+    bi = nbi;
   }
   // CTA partial sums (fixed order => deterministic for a fixed grid)
 #pragma unroll

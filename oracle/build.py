@@ -14,7 +14,8 @@ OUT = os.path.join(HERE, "libgenoracle.so")
 
 def build(force: bool = False) -> str:
     if (not force and os.path.exists(OUT)
-            and os.path.getmtime(OUT) >= max(os.path.getmtime(SRC), os.path.getmtime(SRC[:-2] + ".h"))):
+            and os.path.getmtime(OUT) >= max(os.path.getmtime(SRC), os.path.getmtime(SRC[:-2] + ".h"),
+                                             os.path.getmtime(os.path.join(HERE, "wexp_table.inc")))):
         return OUT
     cmd = ["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared", "-std=gnu11",
            "-Wall", "-Wextra", "-o", OUT, SRC, "-lm"]

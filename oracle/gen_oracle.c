@@ -281,28 +281,25 @@ double go_random_gamma_philox(double shape, double scale, uint64_t seed, uint64_
 /* Integer-CDF resamplers                       */
 /* ------------------------------------------------------------------ */
 
-/* Deterministic exp(x), x <= 0: only rint, fma, * and exact power-of-two scaling, so the
- * CUDA restatement produces identical bits.  ~1 ulp; not libm. */
+/* Deterministic exp(x), -708 < x <= 0: only rint, fma, * and exact power-of-two scaling, so the CUDA restatement
+ * (csrc/gbmath.cuh wexp_parts) produces identical bits.  x = j ln2/64 + r, j = rint(x 64/ln2), |r| <= ln2/128:
+ * exp(x) = 2^(j >> 6) * T[j & 63] * (1 + r + r^2/2 + r^3/6 + r^4/24 + r^5/120); T = 2^(i/64) correctly rounded
+ * (oracle/wexp_table.inc, generated by tools/gen_math_tables.py together with the engine's copy).  ~1.5 ulp; not libm. */
+#include "wexp_table.inc"
+static const double wexp_tab[64] = {GB_WEXP_TAB_VALUES};
 static double dexp_parts(double x, int *kout) {
-  double kd = rint(x * 1.4426950408889634074);
-  double r = fma(kd, -6.93147180369123816490e-01, x);
-  r = fma(kd, -1.90821492927058770002e-10, r);
-  double p = 1.0 / 6227020800.0;            /* 1/13! */
-  p = fma(p, r, 1.0 / 479001600.0);
-  p = fma(p, r, 1.0 / 39916800.0);
-  p = fma(p, r, 1.0 / 3628800.0);
-  p = fma(p, r, 1.0 / 362880.0);
-  p = fma(p, r, 1.0 / 40320.0);
-  p = fma(p, r, 1.0 / 5040.0);
-  p = fma(p, r, 1.0 / 720.0);
-  p = fma(p, r, 1.0 / 120.0);
-  p = fma(p, r, 1.0 / 24.0);
-  p = fma(p, r, 1.0 / 6.0);
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  *kout = (int)kd;
-  return p;
+  double jd = rint(x * GB_WEXP_SCALE);
+  int j = (int)jd;
+  double r = fma(jd, GB_WEXP_NL_HI, x);
+  r = fma(jd, GB_WEXP_NL_LO, r);
+  double r2 = r * r;
+  double a = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  double b = fma(r, 1.0 / 6.0, 0.5);
+  double c = fma(r2, a, b);
+  double poly = fma(r2, c, r);
+  double t = wexp_tab[j & 63];
+  *kout = j >> 6; /* arithmetic shift: floor(j / 64) */
+  return fma(t, poly, t);
 }
 static double pow2i(int e) { /* exact 2^e for -1022 <= e <= 1023 */
   uint64_t bits = (uint64_t)(e + 1023) << 52;

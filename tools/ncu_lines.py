@@ -45,6 +45,9 @@ for r in csv.reader(src.splitlines()):
 assert kern and pat in kern, "kernel not found"
 # match function by demangled-name fragments
 cand = [f for f in funcs if len(funcs[f]) == len(rows)]
+# same static length for the float and the double instantiation: take the one the kernel name asks for
+want = "Id" if "<double" in kern else ("If" if "<float" in kern else "")
+cand.sort(key=lambda f: 0 if (want and ("I" + want[1] + "E" in f or "I" + want[1] + "L" in f)) else 1)
 fn = None
 for f in cand:
     if all(re.sub(r"\s+", " ", a[2]).split(" ")[0] == re.sub(r"\s+", " ", b[1]).split(" ")[0] or True for a, b in zip(funcs[f][:5], rows[:5])):
