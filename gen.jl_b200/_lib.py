@@ -131,6 +131,8 @@ SIGNATURES = {
     "gb_pf_import_rows": (i, [vp, i64, i64, vp]),
     "gb_pf_commit_resample": (i, [vp, d]),
     "gb_importance_sampling": (i, [vp, i64, i, u64, dp, i, i, dp, i, dp, i, dp, i, dp, dp, vpp]),
+    "gb_importance_resampling": (i, [vp, i64, i, u64, dp, i, i, dp, i, i64, dp, dp]),
+    "gb_enumerative_normalize": (i, [dp, dp, i64, i, dp, dp]),
     "gb_resample": (i, [dp, i64, i, i, u32, u64p, u64, u32, i64p]),
     "gb_resample_device": (i, [vp, i64, i, i, u32, vp, u64, u32, vp, vp]),
     "gb_logsumexp": (i, [dp, i64, i, dp, dp]),

@@ -201,6 +201,28 @@ class SpecProgram:
     def logpdf(self, dist, x, a, b=None):
         return self._emit(42, self._new(), a, a if b is None else b, imm=_DISTS[dist] + 100 * x)
 
+    # mvnormal(mu, cov) (mvnormal.jl:12-33): vectors are k CONSECUTIVE registers; cov = k*k model parameters (row-major)
+    def vector(self, regs):
+        """Copy `regs` into k fresh consecutive registers (x + 0) and return the first."""
+        if getattr(self, "_zero", None) is None:
+            self._zero = self.const(0.0)
+        zero = self._zero
+        first = None
+        for r in regs:
+            d = self.add(r, zero)
+            first = d if first is None else first
+        return first
+
+    def sample_mvnormal(self, mu_first, cov_param_offset, k):
+        """k consecutive registers ~ mvnormal(regs mu_first .. mu_first+k-1, params[offset : offset + k*k]); returns the first."""
+        first = self.nreg
+        for _ in range(int(k)):
+            self._new()
+        return self._emit(43, first, mu_first, int(cov_param_offset), imm=int(k))
+
+    def observe_mvnormal(self, x_first, mu_first, cov_param_offset, k):
+        self._emit(44, x_first, mu_first, int(cov_param_offset), imm=int(k))
+
 
 def spec_model(state_dim, params, num_obs, generate_program, step_program=None, name="spec"):
     """A model of the supported class from its declarative specification: `generate_program` is the static-IR
@@ -575,14 +597,25 @@ def sample_unweighted_traces(state, num_samples, draw=0):
     return idx, rows.T.copy()
 
 
-def importance_resampling(model, model_args, observations, *rest, verbose=False, dtype="f64", seed=0):
+def importance_resampling(model, model_args, observations, *rest, verbose=False, dtype="f64", seed=0, chunk=0):
     """(trace, lml_est) = importance_resampling(model, model_args, observations, [proposal, proposal_args,] num_samples)
-    (importance.jl:77-122).  The reference streams the N proposals and keeps one by a running Bernoulli swap, which is
-    a single draw from Categorical(normalised weights); here the N samples are generated in one launch and one index is
-    drawn on the device."""
-    traces, lnw, lml = importance_sampling(model, model_args, observations, *rest, dtype=dtype, seed=seed)
-    idx, rows = sample_unweighted_traces(traces._state, 1, draw=0xFFFF)
-    return rows[0], lml
+    (importance.jl:77-122), streaming: the proposals are generated and reduced chunk by chunk on the device (O(chunk)
+    memory for any num_samples) and folded by the reference's running logsumexp(x1, x2) + Bernoulli swap
+    (include/genb200.h gb_importance_resampling).  `trace` is the kept particle's state row."""
+    if len(rest) == 1:
+        proposal, proposal_args, n = None, (), rest[0]
+    elif len(rest) == 3:
+        proposal, proposal_args, n = rest
+    else:
+        raise TypeError("importance_resampling(model, model_args, observations, [proposal, proposal_args,] num_samples)")
+    obs = _flatten_obs(observations)
+    pk, pargs = _proposal(proposal, proposal_args)
+    pa, pp, npa = _darr(pargs)
+    row = np.empty(model.state_dim, dtype=np.float64)
+    lml = C.c_double()
+    L.check(L.lib().gb_importance_resampling(model._h, int(n), _DTYPES[dtype], int(seed), obs.ctypes.data_as(L.dp), obs.size, pk, pp, npa,
+                                             int(chunk), row.ctypes.data_as(L.dp), C.byref(lml)))
+    return row, lml.value
 
 
 def importance_sampling(model, model_args, observations, *rest, verbose=False, dtype="f64", seed=0,
@@ -647,7 +680,7 @@ def effective_sample_size_from_logw(arr, dtype="f64"):
 _DISTS = {"normal": L.DIST_NORMAL, "gamma": L.DIST_GAMMA, "bernoulli": L.DIST_BERNOULLI,
           "categorical": L.DIST_CATEGORICAL, "mvnormal": L.DIST_MVNORMAL, "uniform": 6, "exponential": 7, "laplace": 8,
           "cauchy": 9, "inv_gamma": 10, "beta": 11, "poisson": 12, "geometric": 13, "binom": 14, "neg_binom": 15,
-          "uniform_discrete": 16}
+          "uniform_discrete": 16, "broadcasted_normal": 17, "dirichlet": 18, "piecewise_uniform": 19, "beta_uniform": 20}
 
 
 def logpdf(dist, x, a, b=None, dtype="f64"):
@@ -657,20 +690,31 @@ def logpdf(dist, x, a, b=None, dtype="f64"):
     x = np.ascontiguousarray(x, dtype=np.float64)
     a = np.ascontiguousarray(a, dtype=np.float64)
     bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
-    if k == L.DIST_MVNORMAL:
+    if k in (L.DIST_MVNORMAL, 18):                 # mvnormal(mu, cov) / dirichlet(alpha): x is [n][len]
         ln = a.size
         n = x.size // ln
         ast = bst = 0
     elif k == L.DIST_CATEGORICAL:
         ln, n, ast, bst = a.size, x.size, 0, 0
+    elif k == 19:                                  # piecewise_uniform(bounds, probs)
+        ln, n, ast, bst = bb.size, x.size, 0, 0
+        if a.size != ln + 1:
+            raise L.GenB200Error(L.EINVAL, "Dimension mismatch")       # piecewise_uniform.jl:13-17
+    elif k == 20:                                  # beta_uniform(theta, alpha, beta): b = (alpha, beta) pairs
+        ln, n = 0, x.size
+        ast = 0 if a.size == 1 else 1
+        bst = 0 if bb.size == 2 else 1
     else:
         ln, n = 0, x.size
         ast = 0 if a.size == 1 else 1
         bst = 0 if (bb is None or bb.size == 1) else 1
-    out = np.empty(n, dtype=np.float64)
+        if k == 17 and n == 1 and (a.size > 1 or (bb is not None and bb.size > 1)):      # scalar x against array parameters
+            n = max(a.size, 1 if bb is None else bb.size)
+            x = np.full(n, float(x.ravel()[0]))
+    out = np.empty(1 if k == 17 else n, dtype=np.float64)
     L.check(L.lib().gb_dist_logpdf(k, _DTYPES[dtype], n, x.ctypes.data_as(L.dp), a.ctypes.data_as(L.dp), ast,
                                    None if bb is None else bb.ctypes.data_as(L.dp), bst, ln, out.ctypes.data_as(L.dp)))
-    return out
+    return float(out[0]) if k == 17 else out
 
 
 def random(dist, n, a, b=None, dtype="f64", seed=0, step=0):
@@ -678,17 +722,33 @@ def random(dist, n, a, b=None, dtype="f64", seed=0, step=0):
     k = _DISTS[dist]
     a = np.ascontiguousarray(a, dtype=np.float64)
     bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
-    if k in (L.DIST_MVNORMAL, L.DIST_CATEGORICAL):
+    if k in (L.DIST_MVNORMAL, L.DIST_CATEGORICAL, 18):
         ln, ast, bst = a.size, 0, 0
+    elif k == 19:
+        ln, ast, bst = bb.size, 0, 0
+    elif k == 20:
+        ln, ast, bst = 0, (0 if a.size == 1 else 1), (0 if bb.size == 2 else 1)
     else:
         ln = 0
         ast = 0 if a.size == 1 else 1
         bst = 0 if (bb is None or bb.size == 1) else 1
-    out = np.empty(n * (ln if k == L.DIST_MVNORMAL else 1), dtype=np.float64)
+    rowwise = k in (L.DIST_MVNORMAL, 18)
+    out = np.empty(n * (ln if rowwise else 1), dtype=np.float64)
     L.check(L.lib().gb_dist_random(k, _DTYPES[dtype], n, a.ctypes.data_as(L.dp), ast,
                                    None if bb is None else bb.ctypes.data_as(L.dp), bst, ln, int(seed), int(step),
                                    out.ctypes.data_as(L.dp)))
-    return out.reshape(n, ln) if k == L.DIST_MVNORMAL else out
+    return out.reshape(n, ln) if rowwise else out
+
+
+def enumerative_normalize(log_weights, log_vols=None, dtype="f64"):
+    """(log_normalized_weights, log_total_weight): the tail of enumerative_inference (enumerative.jl:39-46)."""
+    lw = np.ascontiguousarray(log_weights, dtype=np.float64).ravel()
+    lv = None if log_vols is None else np.ascontiguousarray(log_vols, dtype=np.float64).ravel()
+    out = np.empty(lw.size, dtype=np.float64)
+    tot = C.c_double()
+    L.check(L.lib().gb_enumerative_normalize(lw.ctypes.data_as(L.dp), None if lv is None else lv.ctypes.data_as(L.dp), lw.size,
+                                             _DTYPES[dtype], out.ctypes.data_as(L.dp), C.byref(tot)))
+    return out.reshape(np.shape(log_weights)), tot.value
 
 
 def philox_normals(seed, step, pid0, n, ndraw, dtype="f64"):

@@ -151,7 +151,8 @@ GB_D double logpdf_uniform_discrete(double xi, double lo, double hi) {  // unifo
 
 // distribution ids of the scalar built-ins above (== GB_DIST_* of include/genb200.h, static_assert in genb200.cu)
 enum { DIST_UNIFORM = 6, DIST_EXPONENTIAL = 7, DIST_LAPLACE = 8, DIST_CAUCHY = 9, DIST_INV_GAMMA = 10, DIST_BETA = 11,
-       DIST_POISSON = 12, DIST_GEOMETRIC = 13, DIST_BINOM = 14, DIST_NEG_BINOM = 15, DIST_UNIFORM_DISCRETE = 16 };
+       DIST_POISSON = 12, DIST_GEOMETRIC = 13, DIST_BINOM = 14, DIST_NEG_BINOM = 15, DIST_UNIFORM_DISCRETE = 16,
+       DIST_BROADCASTED_NORMAL = 17, DIST_DIRICHLET = 18, DIST_PIECEWISE_UNIFORM = 19, DIST_BETA_UNIFORM = 20 };
 GB_D double logpdf_scalar(int dist, double x, double a, double b) {
   switch (dist) {
     case DIST_UNIFORM: return logpdf_uniform(x, a, b);
@@ -183,6 +184,72 @@ GB_D double random_invcdf(int dist, double p0, double p1, double u) {
     case DIST_UNIFORM_DISCRETE: return p0 + floor((p1 - p0 + 1.0) * u);
   }
   return NAN;
+}
+
+// ---- dirichlet / piecewise_uniform / beta_uniform (the non-scalar-parameter built-ins) ----
+GB_D double logsumexp2(double x1, double x2) {                           // inference.jl:8-11
+  const double m = x1 > x2 ? x1 : x2;
+  return m == -INFINITY ? m : m + log(exp(x1 - m) + exp(x2 - m));
+}
+GB_D double logpdf_dirichlet(const double *__restrict__ x, const double *__restrict__ alpha, int k) {   // dirichlet.jl:12-21
+  double s = 0.0, sa = 0.0, lg = 0.0;
+  bool ok = true;
+  for (int j = 0; j < k; j++) { s += x[j]; ok = ok && x[j] >= 0.0 && alpha[j] >= 0.0; sa += alpha[j]; lg += lgamma(alpha[j]); }
+  // isapprox(sum(x), 1): |s - 1| <= sqrt(eps) * max(|s|, 1)
+  if (!ok || !(fabs(s - 1.0) <= 1.4901161193847656e-08 * fmax(fabs(s), 1.0))) return -INFINITY;
+  double ll = 0.0;
+  for (int j = 0; j < k; j++) ll += (alpha[j] - 1.0) * log(x[j]);
+  return ll - (lg - lgamma(sa));
+}
+GB_D double logpdf_piecewise_uniform(double x, const double *__restrict__ bounds, const double *__restrict__ probs, int nb) {
+  if (x <= bounds[0] || x >= bounds[nb]) return -INFINITY;               // piecewise_uniform.jl:38-44
+  int bin = 0;
+  while (x > bounds[bin + 1]) bin++;                                     // get_bin, :19-27
+  return log(probs[bin]) - log(bounds[bin + 1] - bounds[bin]);
+}
+GB_D double logpdf_beta_uniform(double x, double theta, double a, double b) {   // beta_uniform.jl:10-18
+  if (x < 0.0 || x > 1.0) return -INFINITY;
+  return logsumexp2(log(theta) + logpdf_beta(x, a, b), log(1.0 - theta));
+}
+// Exact inversion for unimodal integer distributions: the uniform is compared against the probability masses in the order
+// mode, mode+1, mode-1, mode+2, ... (each k still receives exactly p_k of the unit interval), so the search takes
+// O(standard deviation) steps for any parameter.  up(k) = p_{k+1} / p_k, down(k) = p_{k-1} / p_k.
+template <typename UP, typename DOWN>
+GB_D double sample_unimodal(double u, long long mode, double p_mode, long long kmin, long long kmax, UP up, DOWN down) {
+  if (u < p_mode) return (double)mode;
+  u -= p_mode;
+  double pu = p_mode, pd = p_mode;
+  long long ku = mode, kd = mode;
+  for (int it = 0; it < (1 << 22); it++) {
+    bool moved = false;
+    if (ku < kmax) { pu *= up(ku); ku++; moved = true; if (u < pu) return (double)ku; u -= pu; }
+    if (kd > kmin) { pd *= down(kd); kd--; moved = true; if (u < pd) return (double)kd; u -= pd; }
+    if (!moved) break;
+  }
+  return (double)ku;     // the rounding leftover of the unit interval (~1e-16) goes to the upper tail
+}
+GB_D double random_poisson(double lambda, double u) {                     // poisson.jl:19-21
+  const long long mode = (long long)floor(lambda);
+  const double pm = exp((double)mode * log(lambda) - lambda - lgamma((double)mode + 1.0));
+  return sample_unimodal(u, mode, pm, 0, (1ll << 62), [=](long long k) { return lambda / (double)(k + 1); },
+                         [=](long long k) { return (double)k / lambda; });
+}
+GB_D double random_binom(double n, double p, double u) {                  // binom.jl:18-20
+  if (p <= 0.0) return 0.0;
+  if (p >= 1.0) return n;
+  long long mode = (long long)floor((n + 1.0) * p);
+  if (mode > (long long)n) mode = (long long)n;
+  const double pm = exp(logpdf_binom((double)mode, n, p));
+  const double odds = p / (1.0 - p);
+  return sample_unimodal(u, mode, pm, 0, (long long)n, [=](long long k) { return (n - (double)k) / ((double)k + 1.0) * odds; },
+                         [=](long long k) { return (double)k / (n - (double)k + 1.0) / odds; });
+}
+GB_D double random_neg_binom(double r, double p, double u) {              // neg_binom.jl:22-24 (failures before r successes)
+  const double q = 1.0 - p;
+  long long mode = r > 1.0 ? (long long)floor((r - 1.0) * q / p) : 0;
+  const double pm = exp(logpdf_neg_binom((double)mode, r, p));
+  return sample_unimodal(u, mode, pm, 0, (1ll << 62), [=](long long k) { return ((double)k + r) / ((double)k + 1.0) * q; },
+                         [=](long long k) { return (double)k / ((double)k - 1.0 + r) / q; });
 }
 
 // mvnormal.jl:12-16: the covariance is shared by all particles, so it is factored ONCE (host, in

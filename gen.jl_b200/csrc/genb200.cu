@@ -91,7 +91,8 @@ static_assert((int)DIST_UNIFORM == (int)GB_DIST_UNIFORM && (int)DIST_EXPONENTIAL
               (int)DIST_INV_GAMMA == (int)GB_DIST_INV_GAMMA && (int)DIST_BETA == (int)GB_DIST_BETA &&
               (int)DIST_POISSON == (int)GB_DIST_POISSON && (int)DIST_GEOMETRIC == (int)GB_DIST_GEOMETRIC &&
               (int)DIST_BINOM == (int)GB_DIST_BINOM && (int)DIST_NEG_BINOM == (int)GB_DIST_NEG_BINOM &&
-              (int)DIST_UNIFORM_DISCRETE == (int)GB_DIST_UNIFORM_DISCRETE, "distribution ids");
+              (int)DIST_UNIFORM_DISCRETE == (int)GB_DIST_UNIFORM_DISCRETE && (int)DIST_BETA_UNIFORM == (int)GB_DIST_BETA_UNIFORM &&
+              (int)DIST_DIRICHLET == (int)GB_DIST_DIRICHLET, "distribution ids");
 
 static int model_state_dim(int kind, const double *p) {
   switch (kind) {
@@ -113,6 +114,7 @@ static int model_num_normals(int kind, const double *p, int is_init) {
 }
 static int model_num_uniforms(int kind) { return kind == MODEL_HMM ? 1 : 0; }
 
+static bool host_cholesky(const double *cov, int k, std::vector<double> &L, double *logdet);
 extern "C" int gb_model_create(int kind, const double *params, int nparams, gb_model_t **out) {
   REQ(out && params && nparams > 0, "gb_model_create: null argument");
   int need = 0;
@@ -192,6 +194,24 @@ extern "C" int gb_model_create(int kind, const double *params, int nparams, gb_m
         case OP_LOGPDF_DIST: {
           const int di = (int)op.imm % 100, xr = (int)op.imm / 100;
           ok = ok && reg(op.a) && reg(op.b) && reg(xr) && di >= DIST_UNIFORM && di <= DIST_UNIFORM_DISCRETE;
+          break;
+        }
+        case OP_SAMPLE_MVNORMAL: case OP_OBSERVE_MVNORMAL: {
+          const int kk = (int)op.imm;
+          ok = kk >= 1 && kk <= kSpecMaxMv && op.dst >= 0 && op.dst + kk <= kSpecRegs && op.a >= 0 && op.a + kk <= kSpecRegs &&
+               op.b >= 0 && op.b + kk * kk <= np_;
+          if (ok) {
+            // mvnormal.jl:14-15 builds MvNormal(mu, Symmetric(cov)) -- a Cholesky factorisation -- at EVERY call; the covariance
+            // is a parameter of the model here, so it is factored once: [L (k*k, row-major lower), logdet] appended to the parameters
+            std::vector<double> Lf;
+            double logdet = 0.0;
+            if (!host_cholesky(params + 5 + op.b, kk, Lf, &logdet)) { delete m; return fail(GB_EINVAL, "SPEC: mvnormal covariance of op #" + std::to_string(k) + " is not positive definite"); }
+            if ((int)m->spec_params.size() + kk * kk + 1 > kSpecMaxParams) { delete m; return fail(GB_EUNSUPPORTED, "SPEC: parameter block full"); }
+            op.b = (int)m->spec_params.size();
+            m->spec_params.insert(m->spec_params.end(), Lf.begin(), Lf.end());
+            m->spec_params.push_back(logdet);
+            if (op.code == OP_SAMPLE_MVNORMAL) m->nn[prog] += kk;
+          }
           break;
         }
         default: ok = false;
@@ -1098,6 +1118,10 @@ static int run_gather(gb_pf *pf);
 static int materialize_pending(gb_pf *pf) { return run_gather(pf); }
 static int run_gather(gb_pf *pf) {   // materialise a deferred resample gather
   if (!pf->pending_gather) return GB_OK;
+  if (pf->xc_on && pf->a_world > 1) {   // sharded: the peers' offspring rows must have landed before they are read
+    LAUNCH(pf, GB_K_MISC, klaunch(xchg_wait_kernel, 1, kMaxWorld, pf->stream, pf->d_stats));
+    CK(cudaGetLastError());
+  }
   const long long nvec = pf->dtype == GB_F64 ? (pf->n + 1) / 2 : (pf->n + 3) / 4;
   if (pf->dtype == GB_F64) {
     auto kern = gather_kernel<double>;
@@ -1966,7 +1990,8 @@ extern "C" int gb_pf_async_export(gb_pf_t *pf) {
   REQ(pf && pf->a_world > 0, "gb_pf_async_export: bad argument");
   if (pf->a_world == 1) return GB_OK;
   DeviceScope ds__(pf->device);
-  const unsigned gx = (unsigned)std::min<long long>(std::max<long long>(pf->n / (64 * kBlock), 1), 64);
+  // rows that change shards are the fluctuation of the shards' weight sums (~sqrt of the shard size): a few CTAs per destination
+  const unsigned gx = (unsigned)std::min<long long>(std::max<long long>(pf->n / (4096 * kBlock), 1), 8);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(gx, (unsigned)pf->a_world, 1);
@@ -1988,12 +2013,10 @@ extern "C" int gb_pf_async_export(gb_pf_t *pf) {
   CK(cudaGetLastError());
   return GB_OK;
 }
+// (kept for drivers written against the first version of the protocol) the wait for the peers' "done" flags now sits at
+// the top of the step kernel itself (xchg_wait_done): one launch less per step
 extern "C" int gb_pf_async_wait(gb_pf_t *pf) {
   REQ(pf && pf->a_world > 0, "gb_pf_async_wait: bad argument");
-  if (pf->a_world == 1) return GB_OK;
-  DeviceScope ds__(pf->device);
-  LAUNCH(pf, GB_K_MISC, klaunch(xchg_wait_kernel, 1, kMaxWorld, pf->stream, pf->d_stats, (const RunCtl *)pf->d_ctl));
-  CK(cudaGetLastError());
   return GB_OK;
 }
 extern "C" int gb_pf_async_step(gb_pf_t *pf, const double *obs, int nobs) {
@@ -2400,6 +2423,64 @@ extern "C" int gb_logsumexp(const double *a, int64_t n, int dtype, double *lse_o
   return GB_OK;
 }
 
+// tail of enumerative_inference (enumerative.jl:39-46): log_weights[i] = log_weight + log_vol; logsumexp; normalise
+extern "C" int gb_enumerative_normalize(const double *log_weights, const double *log_vols, int64_t n, int dtype, double *lognormw_out,
+                                        double *log_total_out) {
+  REQ(log_weights && n >= 1 && log_total_out, "gb_enumerative_normalize: bad argument");
+  std::vector<double> lw(log_weights, log_weights + n);
+  if (log_vols)
+    for (int64_t i = 0; i < n; i++) lw[i] += log_vols[i];                       // :41
+  double lse = 0.0;
+  int rc = gb_logsumexp(lw.data(), n, dtype, &lse, nullptr);                    // :43 (device reduction)
+  if (rc) return rc;
+  *log_total_out = lse;
+  if (lognormw_out)
+    for (int64_t i = 0; i < n; i++) lognormw_out[i] = lw[i] - lse;              // :44
+  return GB_OK;
+}
+
+// importance_resampling (importance.jl:77-122), streaming: O(chunk) device memory for any number of proposals
+extern "C" int gb_importance_resampling(const gb_model_t *m, int64_t n, int dtype, uint64_t seed, const double *obs, int nobs,
+                                        int pk, const double *pargs, int npargs, int64_t chunk, double *row_out, double *lml_out) {
+  REQ(m && n >= 1 && row_out && lml_out, "gb_importance_resampling: bad argument");
+  if (chunk <= 0) chunk = (int64_t)1 << 20;
+  chunk = std::min<int64_t>(std::min<int64_t>(chunk, (int64_t)1 << 22), n);
+  gb_pf_t *pf = nullptr;
+  int rc = gb_pf_create(m, chunk, chunk, 0, dtype, seed, &pf);
+  if (rc) return rc;
+  const int S = pf->S;
+  std::vector<double> row(S), kept(S);
+  double total = -INFINITY;                     // running log total weight (:93, :111)
+  uint64_t draw = 0;
+  for (int64_t off = 0; off < n && !rc; off += chunk, draw++) {
+    const int64_t cnt = std::min<int64_t>(chunk, n - off);
+    // the chunk's proposals: global sample ids [off, off + cnt) of the same Philox stream a one-shot run would use
+    pf->n = cnt; pf->n_global = cnt; pf->pid_offset = off;
+    pf->wstate = W_DIRTY; pf->tiles_valid = false; pf->ws_clean = false;
+    if ((rc = gb_pf_generate(pf, obs, nobs, pk, pargs, npargs))) break;     // (:88-92, :106-110 for every proposal of the chunk)
+    pf->pid_offset = 0;                          // (indices returned below are chunk-local)
+    if ((rc = ensure_stats(pf))) break;
+    const double lse = pf->h_stats->lse;
+    if (!(lse > -INFINITY)) continue;            // a chunk without weight can never supply the kept trace
+    int64_t idx = 0;
+    if ((rc = gb_pf_sample_unweighted(pf, 1, (draw << 8) | 0xA5u, &idx, row.data()))) break;
+    // fold the chunk into the running total: logsumexp(x1, x2) (inference.jl:8-11), keep the chunk's draw with
+    // probability exp(lse - new total) -- the reference's per-proposal Bernoulli swap (:95-103) applied to a block
+    const double mx = std::max(total, lse);
+    const double nt = mx + log(exp(total - mx) + exp(lse - mx));
+    const U4 w = philox_block(seed ^ 0xD1B54A32D192ED03ull, draw, 0u, PK_SAMPLE, 0xFFFFFFu);
+    if (u52(w.x, w.y) < exp(lse - nt)) kept = row;
+    total = nt;
+  }
+  pf->n = chunk; pf->n_global = chunk; pf->pid_offset = 0;
+  pf_release(pf);
+  if (rc) return rc;
+  if (!(total > -INFINITY)) return fail(GB_ESTATE, "gb_importance_resampling: every proposal has zero weight");
+  for (int s = 0; s < S; s++) row_out[s] = kept[s];
+  *lml_out = total - log((double)n);            // :104, :121
+  return GB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // noise export + host-side integer helpers
 // ------------------------------------------------------------------------------------------
@@ -2497,6 +2578,10 @@ __global__ void __launch_bounds__(kBlock) dist_logpdf_kernel(int dist, long long
       case GB_DIST_GAMMA: r = logpdf_gamma<R>((R)x[i], (R)a[i * as], (R)b[i * bs]); break;
       case GB_DIST_BERNOULLI: r = logpdf_bernoulli<R>(x[i] != 0.0, (R)a[i * as]); break;
       case GB_DIST_CATEGORICAL: r = logpdf_categorical<R>((long long)x[i], a, len); break;
+      case GB_DIST_BROADCASTED_NORMAL: r = logpdf_normal<R>((R)x[i], (R)a[i * as], (R)b[i * bs]); break;   // the host sums (normal.jl:66-67)
+      case GB_DIST_DIRICHLET: r = (R)logpdf_dirichlet(x + i * len, a, len); break;
+      case GB_DIST_PIECEWISE_UNIFORM: r = (R)logpdf_piecewise_uniform(x[i], a, b, len); break;
+      case GB_DIST_BETA_UNIFORM: r = (R)logpdf_beta_uniform(x[i], a[i * as], b[2 * i * bs], b[2 * i * bs + 1]); break;
       case GB_DIST_UNIFORM: case GB_DIST_EXPONENTIAL: case GB_DIST_LAPLACE: case GB_DIST_CAUCHY: case GB_DIST_INV_GAMMA:
       case GB_DIST_BETA: case GB_DIST_POISSON: case GB_DIST_GEOMETRIC: case GB_DIST_BINOM: case GB_DIST_NEG_BINOM:
       case GB_DIST_UNIFORM_DISCRETE:
@@ -2548,6 +2633,48 @@ __global__ void __launch_bounds__(kBlock) dist_random_kernel(int dist, long long
         out[i] = v;
         break;
       }
+      case GB_DIST_BROADCASTED_NORMAL: {      // normal.jl:123-126: mu .+ std .* randn(shape)
+        R e0, e1;
+        philox_normal_pair(seed, pid, step, 0u, T, e0, e1);
+        out[i] = (double)random_normal<R>((R)a[i * as], (R)b[i * bs], e0);
+        break;
+      }
+      case GB_DIST_POISSON: case GB_DIST_BINOM: case GB_DIST_NEG_BINOM: {   // exact inversion on one 52-bit uniform
+        double u0, u1;
+        philox_uniform_pair(seed, pid, step, 0u, u0, u1);
+        out[i] = dist == GB_DIST_POISSON ? random_poisson(a[i * as], u0)
+                 : dist == GB_DIST_BINOM ? random_binom(a[i * as], b[i * bs], u0) : random_neg_binom(a[i * as], b[i * bs], u0);
+        break;
+      }
+      case GB_DIST_DIRICHLET: {               // dirichlet.jl:33-35: independent gamma(alpha_j, 1) draws, normalised
+        double tot = 0.0;
+        for (int j = 0; j < len; j++) {
+          const double gj = random_gamma_philox<double>(a[j], 1.0, seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(j + 1)), pid, step);
+          out[i * len + j] = gj;
+          tot += gj;
+        }
+        for (int j = 0; j < len; j++) out[i * len + j] /= tot;
+        break;
+      }
+      case GB_DIST_PIECEWISE_UNIFORM: {       // piecewise_uniform.jl:48-52: bin = categorical(probs); uniform on the bin
+        double u0, u1;
+        philox_uniform_pair(seed, pid, step, 0u, u0, u1);
+        const long long bin = random_categorical<double>(b, len, u0) - 1;
+        out[i] = u1 * (a[bin + 1] - a[bin]) + a[bin];      // uniform_continuous.jl:21-23
+        break;
+      }
+      case GB_DIST_BETA_UNIFORM: {            // beta_uniform.jl:36-42
+        double u0, u1;
+        philox_uniform_pair(seed, pid, step, 0u, u0, u1);
+        if (u0 < a[i * as]) {
+          const double g1 = random_gamma_philox<double>(b[2 * i * bs], 1.0, seed, pid, step);
+          const double g2 = random_gamma_philox<double>(b[2 * i * bs + 1], 1.0, seed ^ 0x9E3779B97F4A7C15ull, pid, step);
+          out[i] = g1 / (g1 + g2);
+        } else {
+          out[i] = u1;
+        }
+        break;
+      }
       case GB_DIST_INV_GAMMA: out[i] = b[i * bs] / random_gamma_philox<double>(a[i * as], 1.0, seed, pid, step); break;
       case GB_DIST_BETA: {
         const double g1 = random_gamma_philox<double>(a[i * as], 1.0, seed, pid, step);
@@ -2597,16 +2724,18 @@ static bool host_cholesky(const double *cov, int k, std::vector<double> &L, doub
 static int dist_common(int dist, int dtype, int64_t n, const double *x, const double *a, int as, const double *b, int bs, int len,
                        bool random, uint64_t seed, uint32_t step, double *out) {
   REQ(out && n >= 1, "bad argument");
-  REQ(dist >= GB_DIST_NORMAL && dist <= GB_DIST_UNIFORM_DISCRETE, "unknown distribution");
-  if (random) REQ(dist != GB_DIST_POISSON && dist != GB_DIST_BINOM && dist != GB_DIST_NEG_BINOM,
-                  "random() of poisson / binom / neg_binom is not implemented on the device yet");
+  REQ(dist >= GB_DIST_NORMAL && dist <= GB_DIST_BETA_UNIFORM, "unknown distribution");
   int rc = require_gpu();
   if (rc) return rc;
   const bool vec = dist == GB_DIST_MVNORMAL;
-  if (dist == GB_DIST_CATEGORICAL || vec) REQ(len >= 1 && (!vec || len <= kBlrMax), "len out of range (mvnormal: k <= 64)");
-  size_t nx = (size_t)n * (vec ? len : 1);
-  size_t na = (dist == GB_DIST_CATEGORICAL || vec) ? (size_t)len : (as ? (size_t)n : 1);
-  size_t nb = vec ? (size_t)len * len : (b ? (bs ? (size_t)n : 1) : 0);
+  const bool dirichlet = dist == GB_DIST_DIRICHLET, pwu = dist == GB_DIST_PIECEWISE_UNIFORM, bu = dist == GB_DIST_BETA_UNIFORM;
+  if (dist == GB_DIST_CATEGORICAL || vec || dirichlet || pwu) REQ(len >= 1 && (!vec || len <= kBlrMax), "len out of range (mvnormal: k <= 64)");
+  if (pwu) REQ(b, "piecewise_uniform needs bounds (a, len + 1 values) and probs (b, len values)");
+  if (bu) REQ(b, "beta_uniform needs b = (alpha, beta)");
+  const bool rowwise = vec || dirichlet;                       // x / the draws are [n][len]
+  size_t nx = (size_t)n * (rowwise ? len : 1);
+  size_t na = (dist == GB_DIST_CATEGORICAL || rowwise) ? (size_t)len : (pwu ? (size_t)len + 1 : (as ? (size_t)n : 1));
+  size_t nb = vec ? (size_t)len * len : (pwu ? (size_t)len : (b ? (bs ? (size_t)n : 1) * (bu ? 2 : 1) : 0));
   std::vector<double> L;
   double logdet = 0.0;
   const double *bsrc = b;
@@ -2615,6 +2744,8 @@ static int dist_common(int dist, int dtype, int64_t n, const double *x, const do
     if (!host_cholesky(b, len, L, &logdet)) return fail(GB_EINVAL, "mvnormal: covariance is not positive definite");
     bsrc = L.data();
   }
+  if (pwu)
+    for (int j = 0; j < len; j++) REQ(a[j] < a[j + 1], "piecewise_uniform: bounds must be strictly increasing");
   double *dx = nullptr, *da = nullptr, *db = nullptr, *dout = nullptr;
   cudaError_t e = cudaSuccess;
   size_t nout = random ? nx : (size_t)n;
@@ -2625,7 +2756,8 @@ static int dist_common(int dist, int dtype, int64_t n, const double *x, const do
   if (e == cudaSuccess) e = gb_dev_alloc((void **)&dout, nout * 8);
   if (e == cudaSuccess) {
     int grid = (int)std::min<long long>((n + kBlock - 1) / kBlock, 148 * 8);
-    const int as_ = (dist == GB_DIST_CATEGORICAL || vec) ? 0 : (as ? 1 : 0), bs_ = vec ? 0 : (bs ? 1 : 0);
+    const bool shared_a = dist == GB_DIST_CATEGORICAL || rowwise || pwu;
+    const int as_ = shared_a ? 0 : (as ? 1 : 0), bs_ = (vec || pwu) ? 0 : (bs ? 1 : 0);
     const double *dbb = db ? db : da;   // bernoulli / categorical have no second parameter
     if (random) {
       if (dtype == GB_F64) dist_random_kernel<double><<<grid, kBlock>>>(dist, n, da, as_, dbb, bs_, len, seed, step, dout);
@@ -2636,7 +2768,17 @@ static int dist_common(int dist, int dtype, int64_t n, const double *x, const do
     }
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cudaMemcpy(out, dout, nout * 8, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) {
+    if (!random && dist == GB_DIST_BROADCASTED_NORMAL) {       // normal.jl:66-67: ONE number, the sum over the broadcast shape
+      std::vector<double> tmp(nout);
+      e = cudaMemcpy(tmp.data(), dout, nout * 8, cudaMemcpyDeviceToHost);
+      double acc = 0.0;
+      for (size_t i = 0; i < nout; i++) acc += tmp[i];
+      out[0] = acc;
+    } else {
+      e = cudaMemcpy(out, dout, nout * 8, cudaMemcpyDeviceToHost);
+    }
+  }
   gb_dev_free(dx); gb_dev_free(da); gb_dev_free(db); gb_dev_free(dout);
   if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_dist: ") + cudaGetErrorString(e));
   return GB_OK;

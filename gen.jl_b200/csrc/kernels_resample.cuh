@@ -632,7 +632,8 @@ __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const unsigned lon
 //   * offspring owned by another shard are written by export_p2p_kernel STRAIGHT INTO THAT SHARD'S MEMORY over NVLink
 //     (peer pointers: same process or CUDA IPC): rows into the extension rows of its current trace buffer, the slot's
 //     ancestor index and the global parent id next to them -- no staging buffer, no all-to-all, traffic = the spill;
-//   * its last CTA posts a "done" flag to every peer (phase C); xchg_wait_kernel holds the next step until all arrived.
+//   * its last CTA posts a "done" flag to every peer (phase C); the next step kernel waits for all of them before it reads
+//     the rows (xchg_wait_done at its top).
 // ==========================================================================================
 struct PeerMem {           // a peer shard's arrays (device pointers valid in THIS process)
   void *state[2];          // its two trace buffers
@@ -763,11 +764,13 @@ __global__ void __launch_bounds__(kBlock) export_p2p_kernel(const R *__restrict_
       pm.anc[dst_slot0 + i] = (int)(ext0 + i);
       pm.ext_parents[sh->ext_off[d] + i] = pid_offset + src + 1;   // Gen's parents are 1-based, global
     }
-    __threadfence_system();                      // this thread's peer stores are ordered before the flag below
   }
   XchgCtl *xc = stats->xc;
   __syncthreads();
   if (threadIdx.x == 0) {
+    // ONE system-scope fence per CTA, after the barrier: it is cumulative over the peer stores of every thread of the CTA
+    // (they happen before it through the barrier), and orders them before the ticket and the flags below
+    if (cnt > 0) __threadfence_system();
     const unsigned int t = atomicAdd(&xc->export_ticket, 1u);
     s_last = (t == gridDim.x * gridDim.y - 1);
   }
@@ -779,13 +782,11 @@ __global__ void __launch_bounds__(kBlock) export_p2p_kernel(const R *__restrict_
   xc->seq_c = seq;
   for (int r = 0; r < xc->world; r++) st_release_sys(&xc->peer[r]->done_seq[xc->rank], seq);
 }
-// phase C wait: every peer's offspring rows have landed in this shard's extension rows
-__global__ void __launch_bounds__(kMaxWorld) xchg_wait_kernel(WeightStats *stats, const RunCtl *__restrict__ ctl) {
+// phase C wait as a kernel of its own, for readers of the extension rows that are not step kernels (the eager gather)
+__global__ void __launch_bounds__(kMaxWorld) xchg_wait_kernel(WeightStats *stats) {
   pdl_trigger();
   pdl_wait();
-  if (!ctl->do_resample) return;
-  XchgCtl *xc = stats->xc;
-  if ((int)threadIdx.x < xc->world) xchg_spin(&xc->mine->done_seq[threadIdx.x], __ldcg(&xc->seq_c), xc);
+  xchg_wait_done(stats);
 }
 
 }  // namespace gb

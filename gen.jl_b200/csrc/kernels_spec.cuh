@@ -21,7 +21,8 @@ enum {
   OP_SAMPLE_NORMAL = 20, OP_OBSERVE_NORMAL = 21, OP_SAMPLE_BERNOULLI = 22, OP_OBSERVE_BERNOULLI = 23,
   OP_SAMPLE_GAMMA = 24, OP_OBSERVE_GAMMA = 25, OP_SAMPLE_CATEGORICAL = 26, OP_OBSERVE_CATEGORICAL = 27,
   OP_STORE = 30, OP_WEIGHT = 31, OP_LOGPDF_NORMAL = 32,
-  OP_SAMPLE_DIST = 40, OP_OBSERVE_DIST = 41, OP_LOGPDF_DIST = 42   // the other scalar built-ins: imm = distribution id (+ 100 * x register)
+  OP_SAMPLE_DIST = 40, OP_OBSERVE_DIST = 41, OP_LOGPDF_DIST = 42,  // the other scalar built-ins: imm = distribution id (+ 100 * x register)
+  OP_SAMPLE_MVNORMAL = 43, OP_OBSERVE_MVNORMAL = 44                // k = (int)imm consecutive registers; b = offset of [L (k*k, row-major), logdet]
 };
 constexpr int kSpecMaxOps = 256, kSpecMaxParams = 2048, kSpecMaxState = 16;
 
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
   const MathTables T = stage_math_tables(s_tab);
   __syncthreads();
   pdl_wait();
+  if (!INIT && GATHER != 0) xchg_wait_done(a.stats);
   const ST *__restrict__ sin = static_cast<const ST *>(a.state_in);
   ST *__restrict__ sout = static_cast<ST *>(a.state_out);
   ST *__restrict__ logw = static_cast<ST *>(a.logw);
@@ -105,6 +107,21 @@ __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
         case OP_STORE: st_stream(sout + (long long)op.dst * a.ld + i, (ST)regs[op.a]); break;
         case OP_WEIGHT: w += regs[op.a]; break;                                     // e.g. minus a proposal score
         case OP_LOGPDF_NORMAL: regs[op.dst] = logpdf_normal<R>(regs[(int)op.imm], regs[op.a], regs[op.b]); break;
+        case OP_SAMPLE_MVNORMAL: {
+          const int kk = (int)op.imm;
+          R ev[kSpecMaxMv];
+          for (int j = 0; j < kk; j++) {
+            ST e;
+            if (PREDRAWN) e = (ST)__ldcs(a.normals + (long long)n_norm * a.ld + i);
+            else if (n_norm & 1) e = spare_n;
+            else philox_normal_pair(a.seed, pid, a.step, (unsigned)(n_norm >> 1), T, e, spare_n);
+            n_norm++;
+            ev[j] = (R)e;
+          }
+          spec_mvnormal_sample<R>(regs + op.dst, regs + op.a, c_spec_params + op.b, ev, kk);
+          break;
+        }
+        case OP_OBSERVE_MVNORMAL: w += spec_mvnormal_logpdf<R>(regs + op.dst, regs + op.a, c_spec_params + op.b, (int)op.imm); break;
         case OP_OBSERVE_DIST: w += (R)logpdf_scalar((int)op.imm, (double)regs[op.dst], (double)regs[op.a], (double)regs[op.b]); break;
         case OP_LOGPDF_DIST:
           regs[op.dst] = (R)logpdf_scalar((int)op.imm % 100, (double)regs[(int)op.imm / 100], (double)regs[op.a], (double)regs[op.b]);

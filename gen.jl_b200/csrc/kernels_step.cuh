@@ -37,7 +37,7 @@ constexpr int kStatsRecordBytes = 48;   // {m, s1, s2, lse, ess, q_total}: what 
 // consuming kernel spins on the G flags of its own (local) mailbox:
 //   phase A  publish_max (tail of the step / max kernel)  -> mx[src]            consumed at the start of wstats
 //   phase B  wstats' last CTA                             -> (s1, s2, q)[src]   consumed by shard_plan_kernel
-//   phase C  export_p2p_kernel's last CTA                 -> done flag          consumed by xchg_wait_kernel before the step
+//   phase C  export_p2p_kernel's last CTA                 -> done flag          consumed at the top of the next step kernel
 // Payload slots alternate with the parity of the sequence number; a shard can never be more than one phase ahead of a
 // peer (each phase consumes what every peer produced in the previous one), so two slots are enough.  Every shard
 // executes the same sequence of kernels (SPMD), so the expected sequence number is the shard's own post counter.
@@ -74,6 +74,17 @@ GB_D void xchg_spin(const unsigned long long *flag, unsigned long long seq, Xchg
     if (clock64() - t0 > xc->timeout_cycles) { xc->error = 1; break; }
     __nanosleep(40);
   }
+}
+// phase C wait, at the top of every kernel that reads a sharded filter's traces (call from all threads of the CTA, after
+// pdl_wait): the offspring rows its peers exported in the resample before this step have landed in this shard's extension
+// rows.  Every peer's "done" counter must have reached this shard's own export count -- all shards export in lock step, and
+// when nothing was exported since the last wait the test passes at once.
+GB_D void xchg_wait_done(WeightStats *stats) {
+  XchgCtl *xc = stats->xc;
+  if (!xc) return;
+  const int world = xc->world;
+  if (world > 1 && (int)threadIdx.x < world) xchg_spin(&xc->mine->done_seq[threadIdx.x], __ldcg(&xc->seq_c), xc);
+  __syncthreads();
 }
 // phase A post (one thread): this shard's max of the log weights into every mailbox
 GB_D void xchg_post_max(XchgCtl *xc, double m) {
@@ -258,6 +269,7 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
   const MathTables T = stage_math_tables(s_tab);   // constants only: overlaps the predecessor's tail
   __syncthreads();
   pdl_wait();
+  if (!INIT && GATHER != 0) xchg_wait_done(a.stats);   // sharded filter: peers' offspring rows are in (no-op otherwise)
   const R *__restrict__ sin = static_cast<const R *>(a.state_in);
   R *__restrict__ sout = static_cast<R *>(a.state_out);
   R *__restrict__ logw = static_cast<R *>(a.logw);

@@ -24,4 +24,26 @@ struct SpecArgs {
   double obs[kSpecMaxObs];            // this call's observations
 };
 
+constexpr int kSpecMaxMv = 8;
+// mvnormal.jl:30-33: mu + L * randn(k) with the Cholesky factor prepared at model creation
+template <typename R> GB_D void spec_mvnormal_sample(R *x, const R *mu, const double *__restrict__ Lf, const R *eps, int k) {
+  for (int i = 0; i < k; i++) {
+    R s = mu[i];
+    for (int c = 0; c <= i; c++) s += (R)Lf[i * k + c] * eps[c];
+    x[i] = s;
+  }
+}
+// mvnormal.jl:12-16: -(k log 2pi + logdet + |L^-1 (x - mu)|^2) / 2
+template <typename R> GB_D R spec_mvnormal_logpdf(const R *x, const R *mu, const double *__restrict__ Lf, int k) {
+  R z[kSpecMaxMv];
+  R quad = R(0);
+  for (int i = 0; i < k; i++) {
+    R s = x[i] - mu[i];
+    for (int p = 0; p < i; p++) s -= (R)Lf[i * k + p] * z[p];
+    z[i] = s / (R)Lf[i * k + i];
+    quad += z[i] * z[i];
+  }
+  return -(R(k) * Math<R>::log2pi() + (R)Lf[k * k] + quad) / R(2);
+}
+
 }  // namespace gb

@@ -49,6 +49,10 @@ enum { GB_MODEL_LGSSM = 1, GB_MODEL_SV = 2, GB_MODEL_BEARINGS = 3, GB_MODEL_HMM 
  *           (uniform, exponential, laplace, cauchy, geometric, uniform_discrete; one draw of the uniform stream)
  *        41 OBSERVE_DIST weight += logpdf(D, reg dst, a, b), D = GB_DIST_UNIFORM .. GB_DIST_UNIFORM_DISCRETE
  *        42 LOGPDF_DIST dst <- logpdf(D, reg x, a, b) with imm = D + 100 * x
+ *        43 SAMPLE_MVNORMAL  regs dst .. dst+k-1 ~ mvnormal(mu = regs a .. a+k-1, cov = params[b : b + k*k] row-major), k = (int)imm
+ *        44 OBSERVE_MVNORMAL weight += logpdf(mvnormal, x = regs dst .. dst+k-1, mu = regs a .. a+k-1, cov = params[b : b + k*k])
+ *           (mvnormal.jl:12-33; 1 <= k <= 8.  The covariance is a model parameter shared by all particles, so it is factored ONCE, at
+ *           gb_model_create -- the reference re-factors it at every logpdf / random call -- and the kernels use L and log det)
  * `sample` ops are unconstrained choices (weight unchanged: static_ir/generate.jl:31-38), `observe` ops constrained ones
  * (weight += logpdf: unfold/update.jl:64-68).  A custom proposal (particle_filter.jl:186-208, trace_translators.jl:854) is
  * written inside the program: sample from the proposal, OBSERVE the model's density of the proposed value, and subtract
@@ -67,7 +71,12 @@ enum { GB_DIST_NORMAL = 1, GB_DIST_GAMMA = 2, GB_DIST_BERNOULLI = 3, GB_DIST_CAT
        GB_DIST_UNIFORM = 6 /* low, high */, GB_DIST_EXPONENTIAL = 7 /* rate */, GB_DIST_LAPLACE = 8 /* loc, scale */,
        GB_DIST_CAUCHY = 9 /* x0, gamma */, GB_DIST_INV_GAMMA = 10 /* shape, scale */, GB_DIST_BETA = 11 /* alpha, beta */,
        GB_DIST_POISSON = 12 /* lambda */, GB_DIST_GEOMETRIC = 13 /* p */, GB_DIST_BINOM = 14 /* n, p */,
-       GB_DIST_NEG_BINOM = 15 /* r, p */, GB_DIST_UNIFORM_DISCRETE = 16 /* low, high */ };
+       GB_DIST_NEG_BINOM = 15 /* r, p */, GB_DIST_UNIFORM_DISCRETE = 16 /* low, high */,
+       /* normal.jl:61-120: x, mu, std broadcast against each other (a scalar or n values each); logpdf is ONE number, the sum */
+       GB_DIST_BROADCASTED_NORMAL = 17,
+       GB_DIST_DIRICHLET = 18 /* a = alpha[len]; x is [n][len] row-major (dirichlet.jl:12-21, :33-35) */,
+       GB_DIST_PIECEWISE_UNIFORM = 19 /* a = bounds[len + 1], b = probs[len] (piecewise_uniform.jl:31-52) */,
+       GB_DIST_BETA_UNIFORM = 20 /* a = theta, b = (alpha, beta) pairs: 2 values, or 2 n (beta_uniform.jl:10-18, :36-42) */ };
 
 typedef struct gb_model gb_model_t;
 typedef struct gb_pf gb_pf_t;
@@ -209,12 +218,13 @@ int gb_pf_weight_sums_device(gb_pf_t *pf, int bits);
  *     same records on every shard, so all agree without talking;
  *   - offspring owned by another shard are written by a kernel STRAIGHT INTO THAT SHARD'S MEMORY: rows into the
  *     extension rows of its current trace buffer, plus the slot's ancestor index and global parent id; its last CTA
- *     posts a "done" flag (phase C) that the peers wait for before their next particle_filter_step! reads the rows.
+ *     posts a "done" flag (phase C) that the peers' next step kernel waits for before it reads the rows.
  *   once   : gb_pf_ipc_export -> exchange of the bundles (any transport) -> gb_pf_async_attach_ipc for every peer in
  *            another process / gb_pf_async_attach_local for peers in this process -> gb_pf_async_setup -> a barrier
  *            across all shards (the set-up resets the mailbox)
  *   per run: gb_pf_async_arm(threshold), then per step gb_pf_async_iterate(obs) = gb_pf_xchg_stats -> gb_pf_async_plan ->
- *            gb_pf_async_sweep -> gb_pf_async_export -> gb_pf_async_wait -> gb_pf_async_step (enqueues only)
+ *            gb_pf_async_sweep -> gb_pf_async_export -> gb_pf_async_step (enqueues only; gb_pf_async_wait is a no-op kept
+ *            for older drivers: the wait sits inside the step kernel)
  *   finish : gb_pf_async_finish, one device->host read (log_ml_est, #resamples, overflow / time-out flags).  Overflow (a
  *            shard's extension rows or spill buffer too small for the weight skew) or a peer that did not answer within
  *            GENB200_XCHG_TIMEOUT_MS (default 20000) invalidates the run: GB_ESTATE.
@@ -338,6 +348,19 @@ int gb_dist_logpdf(int dist, int dtype, int64_t n, const double *x, const double
 /* draws n values with the engine's Philox stream (seed, step, pid = 0..n-1) */
 int gb_dist_random(int dist, int dtype, int64_t n, const double *a, int a_stride, const double *b, int b_stride,
                    int len, uint64_t seed, uint32_t step, double *out);
+
+/* ---- importance_resampling (importance.jl:77-122) and the tail of enumerative_inference (enumerative.jl:39-46) ---- */
+/* Streaming form, O(chunk) memory for any n: the reference keeps ONE trace while it runs over the n proposals, folding each
+ * log weight into a running logsumexp(x1, x2) (inference.jl:8-11) and swapping the kept trace with probability
+ * exp(w - running total) (importance.jl:95-103, :113-120).  Here the proposals are generated chunk by chunk (chunk <= 2^22
+ * particles of device memory), each chunk is reduced on the device (log-sum-exp + one categorical draw from its normalised
+ * weights), and the chunks are folded on the host by the same pairwise rule -- the same distribution over the kept trace.
+ * row_out: S doubles, the kept trace; lml_out: logsumexp of all n log weights - log n (:104, :121). */
+int gb_importance_resampling(const gb_model_t *m, int64_t n, int dtype, uint64_t seed, const double *obs, int nobs,
+                             int proposal_kind, const double *pargs, int npargs, int64_t chunk, double *row_out, double *lml_out);
+/* log_total = logsumexp(log_weights [+ log_vols]); lognormw_out = log_weights [+ log_vols] - log_total (may be NULL) */
+int gb_enumerative_normalize(const double *log_weights, const double *log_vols, int64_t n, int dtype, double *lognormw_out,
+                             double *log_total_out);
 
 /* ---- the engine's counter-based noise, exported so the oracle can consume identical draws ---- */
 int gb_philox_normals(uint64_t seed, uint32_t step, int64_t pid0, int64_t n, int ndraw, int dtype, double *out);

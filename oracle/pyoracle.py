@@ -319,3 +319,93 @@ def importance_sampling(kind, params, n, obs, seed=0, proposal_kind=0, pargs=Non
     lml = lib().go_importance_sampling(kind, pp, pa.size, n, seed, op, proposal_kind, gp, np_, up,
                                        out.ctypes.data_as(_dp), C.byref(ptr))
     return OraclePF(ptr.value, kind, pa), out, lml
+
+
+# ---- the remaining built-in distributions: numpy restatements of the reference formulas ----
+def logpdf_broadcasted_normal(x, mu, std):
+    """normal.jl:61-68: sum over the broadcast shape of the elementwise normal log density."""
+    x, mu, std = np.broadcast_arrays(np.asarray(x, float), np.asarray(mu, float), np.asarray(std, float))
+    z = (x - mu) / std
+    return float(np.sum(-(z * z + np.log(2 * np.pi)) / 2 - np.log(std)))
+
+
+def logpdf_dirichlet(x, alpha):
+    """dirichlet.jl:12-21 (isapprox(sum(x), 1) with Julia's default rtol = sqrt(eps))."""
+    from scipy.special import gammaln
+    x, alpha = np.asarray(x, float), np.asarray(alpha, float)
+    s = x.sum()
+    if len(x) == len(alpha) and abs(s - 1) <= np.sqrt(np.finfo(float).eps) * max(abs(s), 1) and np.all(x >= 0) and np.all(alpha >= 0):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ll = np.sum((alpha - 1) * np.log(x))
+        return float(ll - (np.sum(gammaln(alpha)) - gammaln(alpha.sum())))
+    return -np.inf
+
+
+def logpdf_piecewise_uniform(x, bounds, probs):
+    """piecewise_uniform.jl:19-46."""
+    if x <= bounds[0] or x >= bounds[-1]:
+        return -np.inf
+    b = 0
+    while x > bounds[b + 1]:
+        b += 1
+    return float(np.log(probs[b]) - np.log(bounds[b + 1] - bounds[b]))
+
+
+def logpdf_beta_uniform(x, theta, a, b):
+    """beta_uniform.jl:10-18 with logsumexp(x1, x2) of inference.jl:8-11."""
+    from scipy import stats
+    if x < 0 or x > 1:
+        return -np.inf
+    return logsumexp2(np.log(theta) + stats.beta.logpdf(x, a, b), np.log(1.0 - theta))
+
+
+def logsumexp2(x1, x2):
+    return lib().go_logsumexp2(float(x1), float(x2))
+
+
+def _sample_unimodal(u, mode, p_mode, kmin, kmax, up, down):
+    """This repo's sampler spec for poisson / binom / neg_binom (the reference delegates to Distributions.jl on Julia's
+    global RNG: parity unpinned): exact inversion of ONE uniform against the masses in the order mode, mode+1, mode-1, ..."""
+    if u < p_mode:
+        return mode
+    u -= p_mode
+    pu = pd = p_mode
+    ku = kd = mode
+    while True:
+        moved = False
+        if ku < kmax:
+            pu *= up(ku); ku += 1; moved = True
+            if u < pu:
+                return ku
+            u -= pu
+        if kd > kmin:
+            pd *= down(kd); kd -= 1; moved = True
+            if u < pd:
+                return kd
+            u -= pd
+        if not moved:
+            return ku
+
+
+def random_poisson(lam, u):
+    import math
+    mode = int(math.floor(lam))
+    pm = math.exp(mode * math.log(lam) - lam - math.lgamma(mode + 1.0))
+    return _sample_unimodal(u, mode, pm, 0, 1 << 62, lambda k: lam / (k + 1), lambda k: k / lam)
+
+
+def random_binom(n, p, u):
+    import math
+    from scipy import stats
+    mode = min(int(math.floor((n + 1.0) * p)), int(n))
+    pm = math.exp(math.lgamma(n + 1.0) - math.lgamma(mode + 1.0) - math.lgamma(n - mode + 1.0) + mode * math.log(p) + (n - mode) * math.log1p(-p))
+    odds = p / (1.0 - p)
+    return _sample_unimodal(u, mode, pm, 0, int(n), lambda k: (n - k) / (k + 1.0) * odds, lambda k: k / (n - k + 1.0) / odds)
+
+
+def random_neg_binom(r, p, u):
+    import math
+    q = 1.0 - p
+    mode = int(math.floor((r - 1.0) * q / p)) if r > 1.0 else 0
+    pm = math.exp(math.lgamma(mode + r) - math.lgamma(mode + 1.0) - math.lgamma(r) + r * math.log(p) + mode * math.log1p(-p))
+    return _sample_unimodal(u, mode, pm, 0, 1 << 62, lambda k: (k + r) / (k + 1.0) * q, lambda k: k / (k - 1.0 + r) / q)

@@ -740,8 +740,94 @@ def test_more_builtin_distributions(g):
     assert abs(ig.mean() - 1.5 / 2.5) < 0.01
     be = g.random("beta", m, [2.0], [3.5], seed=8)
     assert abs(be.mean() - 2.0 / 5.5) < 0.005 and abs(be.var() - stats.beta.var(2.0, 3.5)) < 0.003
+    po = g.random("poisson", 10, [4.2])
+    assert po.min() >= 0
+
+
+def test_remaining_builtin_distributions(g, O):
+    """SURVEY.md 8f row 2, the rest of distributions/distributions.jl:1-19: broadcasted_normal, dirichlet, piecewise_uniform,
+    beta_uniform against numpy restatements of the reference formulas (oracle/pyoracle.py), and the integer samplers
+    (poisson, binom, neg_binom) against the oracle's restatement of the sampler spec on the device's own uniforms."""
+    from scipy import stats
+    rng = np.random.default_rng(7)
+    # broadcasted_normal (normal.jl:61-68): array / scalar combinations, ONE number out
+    x, mu, sd = rng.standard_normal(1000), rng.standard_normal(1000), np.exp(0.3 * rng.standard_normal(1000))
+    for xx, mm, ss in ((x, mu, sd), (x, [0.3], sd), (x, mu, [1.7]), (x, [0.3], [1.7]), ([0.2], mu, sd)):
+        got, ref = g.logpdf("broadcasted_normal", xx, mm, ss), O.logpdf_broadcasted_normal(xx, mm, ss)
+        assert abs(got - ref) <= 1e-10 * abs(ref), (got, ref)
+    draws = g.random("broadcasted_normal", 200000, np.tile([0.0, 5.0], 100000), [2.0], seed=3)
+    assert abs(draws[0::2].mean()) < 0.03 and abs(draws[1::2].mean() - 5.0) < 0.03 and abs(draws.std() - math.sqrt(4 + 6.25)) < 0.03
+    # dirichlet (dirichlet.jl:12-21, :33-35)
+    alpha = np.array([0.7, 2.0, 3.5, 1.0])
+    xs = rng.dirichlet(alpha, size=500)
+    xs[0] = [0.5, 0.5, 0.2, 0.1]                    # not on the simplex
+    xs[1] = [1.2, -0.2, 0.0, 0.0]                   # negative entry
+    got = g.logpdf("dirichlet", xs, alpha)
+    ref = np.array([O.logpdf_dirichlet(r, alpha) for r in xs])
+    assert got[0] == -np.inf and got[1] == -np.inf and close(got[2:], ref[2:], 1e-11)
+    assert close(got[2:], stats.dirichlet.logpdf(xs[2:].T, alpha), 1e-10)
+    d = g.random("dirichlet", 100000, alpha, seed=4)
+    assert d.shape == (100000, 4) and np.allclose(d.sum(axis=1), 1.0, atol=1e-12) and d.min() >= 0
+    assert np.allclose(d.mean(axis=0), alpha / alpha.sum(), atol=0.005)
+    assert np.allclose(d.var(axis=0), stats.dirichlet.var(alpha), atol=0.002)
+    # piecewise_uniform (piecewise_uniform.jl:19-52)
+    bounds, probs = np.array([-1.0, 0.0, 0.5, 2.0]), np.array([0.2, 0.5, 0.3])
+    xp = np.concatenate([rng.uniform(-1.5, 2.5, 500), bounds])
+    got = g.logpdf("piecewise_uniform", xp, bounds, probs)
+    ref = np.array([O.logpdf_piecewise_uniform(v, bounds, probs) for v in xp])
+    assert np.array_equal(np.isinf(got), np.isinf(ref)) and close(got[np.isfinite(ref)], ref[np.isfinite(ref)], 1e-12)
+    pw = g.random("piecewise_uniform", 200000, bounds, probs, seed=5)
+    frac = [np.mean((pw > bounds[k]) & (pw <= bounds[k + 1])) for k in range(3)]
+    assert pw.min() > -1.0 and pw.max() < 2.0 and np.allclose(frac, probs, atol=0.005)
     with pytest.raises(g.GenB200Error):
-        g.random("poisson", 10, [4.2])
+        g.logpdf("piecewise_uniform", [0.1], bounds, probs[:2])                       # check_dims (:13-17)
+    # beta_uniform (beta_uniform.jl:10-18, :36-42)
+    xb = np.concatenate([rng.random(500), [-0.1, 1.1, 0.0, 1.0]])
+    got = g.logpdf("beta_uniform", xb, [0.3], [2.0, 5.0])
+    ref = np.array([O.logpdf_beta_uniform(v, 0.3, 2.0, 5.0) for v in xb])
+    assert got[500] == -np.inf and got[501] == -np.inf and close(got[:500], ref[:500], 1e-11)
+    bu = g.random("beta_uniform", 200000, [0.3], [2.0, 5.0], seed=6)
+    assert bu.min() >= 0 and bu.max() <= 1 and abs(bu.mean() - (0.3 * 2 / 7 + 0.7 * 0.5)) < 0.004
+    # integer samplers: exact inversion of the device's own uniform stream (oracle restatement) + moments
+    m = 4000
+    u = g.philox_uniforms(11, 3, 0, m, 1)[0]
+    for lam in (0.3, 4.2, 250.0):
+        got = g.random("poisson", m, [lam], seed=11, step=3)
+        assert np.array_equal(got, [O.random_poisson(lam, float(v)) for v in u]), lam
+    got = g.random("binom", m, [40.0], [0.3], seed=11, step=3)
+    assert np.array_equal(got, [O.random_binom(40.0, 0.3, float(v)) for v in u])
+    got = g.random("neg_binom", m, [3.5], [0.4], seed=11, step=3)
+    assert np.array_equal(got, [O.random_neg_binom(3.5, 0.4, float(v)) for v in u])
+    big = 300000
+    po = g.random("poisson", big, [4.2], seed=1)
+    assert abs(po.mean() - 4.2) < 0.02 and abs(po.var() - 4.2) < 0.05 and po.min() >= 0
+    hist = np.bincount(po.astype(int), minlength=12)[:12] / big
+    assert np.allclose(hist, stats.poisson.pmf(np.arange(12), 4.2), atol=0.003)
+    bi = g.random("binom", big, [40.0], [0.3], seed=2)
+    assert abs(bi.mean() - 12.0) < 0.03 and abs(bi.var() - 8.4) < 0.1 and bi.max() <= 40
+    nb = g.random("neg_binom", big, [3.5], [0.4], seed=3)
+    assert abs(nb.mean() - 3.5 * 0.6 / 0.4) < 0.05 and abs(nb.var() - 3.5 * 0.6 / 0.16) < 0.5
+    # enumerative_inference's tail (enumerative.jl:39-46)
+    lw, lv = rng.standard_normal((7, 9)) * 4, np.log(rng.random((7, 9)))
+    lnw, tot = g.enumerative_normalize(lw, lv)
+    ref_tot = O.logsumexp((lw + lv).ravel())
+    assert abs(tot - ref_tot) <= 1e-12 * abs(ref_tot) and np.allclose(lnw, lw + lv - ref_tot, rtol=0, atol=1e-12)
+    assert abs(O.logsumexp(lnw.ravel())) < 1e-12
+
+
+def test_streaming_importance_resampling_matches_one_shot(g):
+    """importance.jl:77-122: the kept trace is distributed as ONE categorical draw from the normalised weights and the log-ML
+    estimate is logsumexp(all weights) - log n, whatever the chunking (the chunks are folded by logsumexp(x1, x2) and a
+    Bernoulli swap like the reference's per-proposal loop)."""
+    m = g.lgssm_model(**F.LGSSM)
+    n = 20000
+    _, lnw, lml_ref = g.importance_sampling(m, (0,), 0.8, n, seed=5)
+    for chunk in (0, 4096, 333):
+        tr, lml = g.importance_resampling(m, (0,), 0.8, n, seed=5, chunk=chunk)
+        assert abs(lml - lml_ref) <= 1e-10 * abs(lml_ref), (chunk, lml, lml_ref)      # same Philox proposals, same log ML
+    # posterior of x0 | y0 for the conjugate model (prior N(0,1), observation sd 1): N(y/2, 1/2), through small chunks
+    xs = np.array([g.importance_resampling(m, (0,), 0.8, 3000, seed=s, chunk=700)[0][0] for s in range(400)])
+    assert abs(xs.mean() - 0.4) < 4 * math.sqrt(0.5 / 400) + 0.02 and abs(xs.var() - 0.5) < 0.12
 
 
 def test_sample_unweighted_traces_and_importance_resampling(g, O):
@@ -960,6 +1046,85 @@ def test_single_cta_run_degenerate_weights(g):
     assert np.array_equal(a.parents, b.parents) and np.array_equal(a.get_state(0), b.get_state(0))
     cnt = np.bincount(b.parents - 1, minlength=n)
     assert cnt[777] > 0.7 * n and cnt.sum() == n
+
+
+def mvn_lgssm_spec(g, A, Q, H, Rm, m0, P0):
+    """2-D linear-Gaussian state-space model written with mvnormal choices (mvnormal.jl:12-33):
+    x0 ~ mvnormal(m0, P0); x_t ~ mvnormal(A x_{t-1}, Q); y_t ~ mvnormal(H x_t, R) (y observed, 2-D)."""
+    params = np.concatenate([P0.ravel(), Q.ravel(), Rm.ravel()])          # covariances at parameter offsets 0, 4, 8
+    gen, step = g.SpecProgram(), g.SpecProgram()
+
+    def emit(p, prev):
+        if prev is None:
+            mu = p.vector([p.const(m0[0]), p.const(m0[1])])
+            x = p.sample_mvnormal(mu, 0, 2)
+        else:
+            mu = p.vector([p.add(p.mul(p.const(A[0, 0]), prev[0]), p.mul(p.const(A[0, 1]), prev[1])),
+                           p.add(p.mul(p.const(A[1, 0]), prev[0]), p.mul(p.const(A[1, 1]), prev[1]))])
+            x = p.sample_mvnormal(mu, 4, 2)
+        assert np.array_equal(H, np.eye(2))      # (the observation's mean is the sampled vector itself: 32 registers per program)
+        y = p.vector([p.obs(0), p.obs(1)])
+        p.observe_mvnormal(y, x, 8, 2)
+        p.store(0, x)
+        p.store(1, x + 1)
+    emit(gen, None)
+    emit(step, (step.prev(0), step.prev(1)))
+    return g.spec_model(2, params, 2, gen, step, name="mvn_lgssm")
+
+
+@pytest.mark.parametrize("backend", ["1", "0"])
+def test_spec_mvnormal_choices(g, monkeypatch, backend):
+    """mvnormal as a model choice: SAMPLE_MVNORMAL / OBSERVE_MVNORMAL in a spec program, through the
+    NVRTC-specialised kernel and the interpreter.  Per-particle traces and log weights against a numpy restatement of
+    mvnormal.jl:12-33 (mu + L randn(k); -(k log 2pi + logdet + maha)/2) on the device's exported Philox normals; the log-ML
+    estimate against the exact 2-D Kalman filter."""
+    from scipy import stats
+    monkeypatch.setenv("GENB200_SPEC_JIT", backend)
+    A = np.array([[0.9, 0.2], [-0.1, 0.8]]); Q = np.array([[0.3, 0.1], [0.1, 0.2]])
+    H = np.eye(2); Rm = np.array([[0.5, -0.2], [-0.2, 0.4]])
+    m0 = np.array([0.3, -0.2]); P0 = np.array([[1.0, 0.3], [0.3, 0.7]])
+    rng = np.random.default_rng(4)
+    T = 12
+    xs = rng.multivariate_normal(m0, P0)
+    ys = []
+    for t in range(T + 1):
+        if t:
+            xs = rng.multivariate_normal(A @ xs, Q)
+        ys.append(rng.multivariate_normal(H @ xs, Rm))
+    model = mvn_lgssm_spec(g, A, Q, H, Rm, m0, P0)
+    n, seed = 50000, 12
+    st = g.initialize_particle_filter(model, (0,), ys[0], n, seed=seed)
+    assert st.spec_backend == ("nvrtc" if backend == "1" else "interpreter")
+    # t = 0 against numpy on the exported noise
+    eps = g.philox_normals(seed, 0, 0, n, 2)
+    x_ref = m0[:, None] + np.linalg.cholesky(P0) @ eps
+    x_dev = np.stack([st.get_state(0), st.get_state(1)])
+    assert np.allclose(x_dev, x_ref, rtol=0, atol=1e-12)
+    lw_ref = stats.multivariate_normal.logpdf((ys[0][:, None] - H @ x_dev).T, np.zeros(2), Rm)
+    assert close(st.log_weights, lw_ref, 1e-10)
+    # one step without resampling: transition + observation
+    incr, = g.particle_filter_step_(st, (1,), (g.UnknownChange,), ys[1])
+    eps = g.philox_normals(seed, 1, 0, n, 2)
+    x1_ref = A @ x_dev + np.linalg.cholesky(Q) @ eps
+    x1_dev = np.stack([st.get_state(0), st.get_state(1)])
+    assert np.allclose(x1_dev, x1_ref, rtol=0, atol=1e-12)
+    assert close(incr, stats.multivariate_normal.logpdf((ys[1][:, None] - H @ x1_dev).T, np.zeros(2), Rm), 1e-10)
+    # the filter against the exact Kalman log marginal likelihood
+    for t in range(2, T + 1):
+        g.maybe_resample_(st, resampler="systematic")
+        g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+    m, P, exact = m0.copy(), P0.copy(), 0.0
+    for t, y in enumerate(ys):
+        if t:
+            m, P = A @ m, A @ P @ A.T + Q
+        S = H @ P @ H.T + Rm
+        exact += stats.multivariate_normal.logpdf(y, H @ m, S)
+        K = P @ H.T @ np.linalg.inv(S)
+        m, P = m + K @ (y - H @ m), (np.eye(2) - K @ H) @ P
+    assert abs(g.log_ml_estimate(st) - exact) < 0.15, (g.log_ml_estimate(st), exact)
+    # a covariance that is not positive definite is rejected when the model is created
+    with pytest.raises(g.GenB200Error):
+        mvn_lgssm_spec(g, A, np.array([[1.0, 2.0], [2.0, 1.0]]), H, Rm, m0, P0)
 
 
 def test_spec_nvrtc_general_loop_with_gamma_draws(g, monkeypatch):
