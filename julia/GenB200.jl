@@ -19,7 +19,7 @@ module GenB200
 
 using Gen
 import Gen: initialize_particle_filter, particle_filter_step!, maybe_resample!, log_ml_estimate,
-            get_log_weights, get_traces, importance_sampling
+            get_log_weights, get_traces, importance_sampling, importance_resampling
 
 const libgenb200 = get(ENV, "GENB200_LIB", "libgenb200.so")
 
@@ -117,6 +117,23 @@ function Base.copy(s::DeviceParticleFilterState)       # particle_filter.jl:43-5
     c
 end
 
+# Base.:(==) / Base.hash (particle_filter.jl:52-63): field-wise over traces, new_traces (scratch: not compared here),
+# log_weights, log_ml_est, parents.  The columns are read back once per comparison.
+function _columns(s::DeviceParticleFilterState)
+    n, S = getfield(s, :num_particles), getfield(s, :model).state_dim
+    cols = Matrix{Float64}(undef, n, S)
+    for f in 1:S
+        check(ccall((:gb_pf_get_state, libgenb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}), getfield(s, :handle), f - 1, view(cols, :, f)))
+    end
+    cols
+end
+function Base.:(==)(a::DeviceParticleFilterState, b::DeviceParticleFilterState)
+    getfield(a, :num_particles) == getfield(b, :num_particles) && a.log_ml_est == b.log_ml_est &&
+        a.parents == b.parents && isequal(a.log_weights, b.log_weights) && isequal(_columns(a), _columns(b))
+end
+Base.hash(s::DeviceParticleFilterState, h::UInt) =
+    hash(_columns(s), hash(s.log_weights, hash(s.log_ml_est, hash(s.parents, h))))
+
 # ---- Gen's generics ----
 function initialize_particle_filter(model::DeviceModel, model_args::Tuple, observations::ChoiceMap,
                                     proposal, proposal_args::Tuple, num_particles::Int;
@@ -211,6 +228,94 @@ function importance_sampling(model::DeviceModel, model_args::Tuple, observations
 end
 importance_sampling(model::DeviceModel, model_args::Tuple, observations::ChoiceMap, num_samples::Int; kw...) =
     importance_sampling(model, model_args, observations, nothing, (), num_samples; kw...)
+
+# importance_resampling (importance.jl:77-122): (trace, lml_est); streaming on the device, O(chunk) memory for any
+# num_samples (gb_importance_resampling folds chunks by the reference's logsumexp(x1, x2) + Bernoulli swap)
+function importance_resampling(model::DeviceModel, model_args::Tuple, observations::ChoiceMap,
+                               proposal, proposal_args::Tuple, num_samples::Int;
+                               verbose=false, dtype::Int=GB_F64, seed::Integer=rand(UInt64), chunk::Int=0)
+    obs = flatten_obs(observations)
+    pa = flatten_pargs(proposal, proposal_args)
+    row = Vector{Float64}(undef, model.state_dim)
+    lml = Ref{Cdouble}()
+    check(ccall((:gb_importance_resampling, libgenb200), Cint,
+                (Ptr{Cvoid}, Int64, Cint, UInt64, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Cint, Int64, Ptr{Cdouble}, Ref{Cdouble}),
+                model.handle, num_samples, dtype, seed, obs, length(obs), proposal_kind(proposal), pa, length(pa), chunk, row, lml))
+    (row, lml[])
+end
+importance_resampling(model::DeviceModel, model_args::Tuple, observations::ChoiceMap, num_samples::Int; kw...) =
+    importance_resampling(model, model_args, observations, nothing, (), num_samples; kw...)
+
+# tail of enumerative_inference (enumerative.jl:39-46) on the device: (log_normalized_weights, log_total_weight)
+function enumerative_normalize(log_weights::AbstractArray{Float64}, log_vols::Union{AbstractArray{Float64},Nothing}=nothing)
+    lw = vec(collect(log_weights))
+    out = similar(lw)
+    tot = Ref{Cdouble}()
+    check(ccall((:gb_enumerative_normalize, libgenb200), Cint, (Ptr{Cdouble}, Ptr{Cdouble}, Int64, Cint, Ptr{Cdouble}, Ref{Cdouble}),
+                lw, log_vols === nothing ? C_NULL : vec(collect(log_vols)), length(lw), GB_F64, out, tot))
+    (reshape(out, size(log_weights)), tot[])
+end
+
+# ---- ONE filter over several GPUs from this (single) Julia thread: the gb_spf_* entries (no NCCL / MPI; the devices
+#      exchange through peer memory inside the kernels).  Same generics, same results bit for bit as on one GPU. ----
+mutable struct MultiGpuParticleFilterState
+    handle::Ptr{Cvoid}
+    model::DeviceModel
+    num_particles::Int
+    last_t::Union{Int,Nothing}
+    function MultiGpuParticleFilterState(h, model, n, last_t)
+        s = new(h, model, n, last_t)
+        finalizer(x -> ccall((:gb_spf_free, libgenb200), Cvoid, (Ptr{Cvoid},), x.handle), s)
+        s
+    end
+end
+function initialize_particle_filter(model::DeviceModel, model_args::Tuple, observations::ChoiceMap, num_particles::Int,
+                                    devices::Vector{<:Integer}; dtype::Int=GB_F64, seed::Integer=rand(UInt64))
+    obs = flatten_obs(observations)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    dev = Cint.(devices)
+    check(ccall((:gb_spf_initialize, libgenb200), Cint,
+                (Ptr{Cvoid}, Int64, Cint, UInt64, Cint, Ptr{Cint}, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Cint, Ref{Ptr{Cvoid}}),
+                model.handle, num_particles, dtype, seed, length(dev), dev, obs, length(obs), GB_PROPOSAL_DEFAULT, C_NULL, 0, h))
+    last_t = (length(model_args) >= 1 && model_args[1] isa Integer) ? Int(model_args[1]) : nothing
+    MultiGpuParticleFilterState(h[], model, num_particles, last_t)
+end
+function particle_filter_step!(state::MultiGpuParticleFilterState, new_args::Tuple, argdiffs::Tuple, observations::ChoiceMap)
+    if state.last_t !== nothing && length(new_args) >= 1 && new_args[1] != state.last_t + 1
+        error("Choices were updated or deleted inside particle filter step")          # particle_filter.jl:227-229
+    end
+    obs = flatten_obs(observations)
+    check(ccall((:gb_spf_step, libgenb200), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Ptr{Cdouble}, Cint),
+                state.handle, obs, length(obs), GB_PROPOSAL_DEFAULT, C_NULL, 0))
+    length(new_args) >= 1 && (state.last_t = Int(new_args[1]))
+    lazy = Vector{Float64}(undef, 0)     # log incremental weights stay on the devices (gb_spf_get_log_increments reads them)
+    (lazy,)
+end
+function maybe_resample!(state::MultiGpuParticleFilterState; ess_threshold::Real=state.num_particles / 2, verbose=false)
+    did = Ref{Cint}(0)
+    check(ccall((:gb_spf_maybe_resample, libgenb200), Cint, (Ptr{Cvoid}, Cdouble, Ref{Cint}), state.handle, Float64(ess_threshold), did))
+    did[] != 0
+end
+function log_ml_estimate(state::MultiGpuParticleFilterState)
+    r = Ref{Cdouble}()
+    check(ccall((:gb_spf_log_ml_estimate, libgenb200), Cint, (Ptr{Cvoid}, Ref{Cdouble}), state.handle, r))
+    r[]
+end
+function get_log_weights(state::MultiGpuParticleFilterState)
+    out = Vector{Float64}(undef, state.num_particles)
+    check(ccall((:gb_spf_get_log_weights, libgenb200), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), state.handle, out))
+    out
+end
+function particle_filter_run!(state::MultiGpuParticleFilterState, observations::Vector{<:ChoiceMap};
+                              ess_threshold::Real=state.num_particles / 2)
+    obs = reduce(vcat, [flatten_obs(o) for o in observations])
+    nres = Ref{Cint}(0)
+    T = length(observations)
+    check(ccall((:gb_spf_run, libgenb200), Cint, (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Cdouble, Ref{Cint}),
+                state.handle, T, obs, div(length(obs), T), Float64(ess_threshold), nres))
+    state.last_t !== nothing && (state.last_t += T)
+    nres[]
+end
 
 # sample_unweighted_traces (particle_filter.jl:101-109): 1-based indices of num_samples iid draws + their rows
 function sample_unweighted_traces(state::DeviceParticleFilterState, num_samples::Int; draw::Integer=0)
