@@ -51,6 +51,8 @@ SIGNATURES = {
     "gb_pf_get_trajectory": (i, [vp, i, dp]),
     "gb_pf_sample_unweighted": (i, [vp, i64, u64, i64p, dp]),
     "gb_pf_rejuvenate": (i, [vp, i, dp, i, d, i64p, dp]),
+    "gb_pf_enable_window": (i, [vp, i]),
+    "gb_pf_rejuvenate_window": (i, [vp, i, i, dp, i, d, i64p, dp]),
     "gb_pf_run": (i, [vp, i, dp, i, d, ip]),
     "gb_pf_run_mh": (i, [vp, i, dp, i, d, i, d, i, ip, i64p]),
     "gb_cache_trim": (i, []),

@@ -369,6 +369,10 @@ class DeviceParticleFilterState:
             up = u64s.ctypes.data_as(L.u64p)
         L.check(L.lib().gb_pf_set_resample_noise(self._h, 0 if u0 is None else 1, 0 if u0 is None else int(u0), up))
 
+    def enable_window(self, W):
+        """Keep the last W states of every particle's own lineage (sliding-window rejuvenation); before generate."""
+        L.check(L.lib().gb_pf_enable_window(self._h, int(W)))
+
     def enable_history(self, on=True):
         """Keep per-step snapshots + ancestors so that full trajectories can be reconstructed (call before generate)."""
         L.check(L.lib().gb_pf_enable_history(self._h, int(bool(on))))
@@ -541,6 +545,19 @@ def rejuvenate_(state, observations, move="resimulate", drift_std=0.0, return_al
     alpha = np.empty(state.num_particles, dtype=np.float64) if return_alpha else None
     L.check(L.lib().gb_pf_rejuvenate(state._h, mv, obs.ctypes.data_as(L.dp), obs.size, float(drift_std), C.byref(acc),
                                      None if alpha is None else alpha.ctypes.data_as(L.dp)))
+    return (acc.value, alpha) if return_alpha else acc.value
+
+
+def rejuvenate_window_(state, a, b, observations_window, drift_std, return_alpha=False):
+    """The tutorial's sliding-window rejuvenation `for i in 1:N  state.traces[i], _ = perturbation_move(state.traces[i], a, b)`
+    (docs/src/tutorials/smc.md:492-541): one block Gaussian-drift MH move per particle on the latent choices of steps
+    a..b (1 <= a <= b <= current step, at most W steps back: state.enable_window(W) before generate).
+    `observations_window`: the observations of steps a..T.  Returns the number of accepted moves."""
+    obs = np.ascontiguousarray([_flatten_obs(o)[0] for o in observations_window], dtype=np.float64)
+    acc = C.c_int64()
+    alpha = np.empty(state.num_particles, dtype=np.float64) if return_alpha else None
+    L.check(L.lib().gb_pf_rejuvenate_window(state._h, int(a), int(b), obs.ctypes.data_as(L.dp), 1, float(drift_std), C.byref(acc),
+                                            None if alpha is None else alpha.ctypes.data_as(L.dp)))
     return (acc.value, alpha) if return_alpha else acc.value
 
 

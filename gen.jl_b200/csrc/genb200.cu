@@ -290,6 +290,9 @@ struct gb_pf {
   bool hist_resampled = false;      // a resample happened since the last recorded step
   std::vector<void *> hist_state;   // [t] -> S columns x n_pad of the filter dtype (t = 0: after generate)
   std::vector<int *> hist_anc;      // [t] -> ancestors applied BEFORE step t (nullptr: no resample)
+  // optional window of the last W states of every particle's own lineage (sliding-window rejuvenation, kernels_mh.cuh)
+  int win_W = 0, win_len = 0, win_cur = 0;
+  void *win[2] = {nullptr, nullptr};           // [W][S][ld] each, double-buffered like the traces
   RunCtl *d_ctl = nullptr, *h_ctl = nullptr;   // fused multi-step run (gb_pf_run) / asynchronous sharded run
   ShardPlanDev *d_shplan = nullptr, *h_shplan = nullptr;
   XchgMail *mail = nullptr;         // this shard's mailbox of the peer-memory exchange (kernels_step.cuh), written by peers
@@ -418,7 +421,7 @@ static void pf_release(gb_pf *pf) {
   if (!pf) return;
   DeviceScope ds__(pf->device);
   FreeBatch fb__;
-  gb_dev_free(pf->mail); gb_dev_free(pf->d_xc); gb_host_free(pf->h_xc);
+  gb_dev_free(pf->mail); gb_dev_free(pf->d_xc); gb_host_free(pf->h_xc); gb_dev_free(pf->win[0]); gb_dev_free(pf->win[1]);
   gb_dev_free(pf->state[0]); gb_dev_free(pf->state[1]); gb_dev_free(pf->logw); gb_dev_free(pf->incr); gb_dev_free(pf->anc);
   gb_dev_free(pf->parents64); gb_dev_free(pf->ext_parents); gb_dev_free(pf->partials); gb_dev_free(pf->ticket); gb_dev_free(pf->d_stats);
   gb_host_free(pf->h_stats); gb_dev_free(pf->d_normals); gb_dev_free(pf->d_uniforms); gb_dev_free(pf->d_u64);
@@ -834,6 +837,7 @@ static int history_record(gb_pf *pf, bool resampled) {
 extern "C" int gb_pf_enable_history(gb_pf_t *pf, int on) {
   REQ(pf, "null handle");
   REQ(pf->n == pf->n_global, "history is kept for single-shard filters only");
+  REQ(!(on && pf->win_W > 0), "gb_pf_enable_history: not together with gb_pf_enable_window");
   pf->history = on != 0;
   return GB_OK;
 }
@@ -872,6 +876,49 @@ extern "C" int gb_pf_get_trajectory(gb_pf_t *pf, int field, double *out) {
   return GB_OK;
 }
 
+// ---- window of the last W states per particle (sliding-window rejuvenation) ----
+extern "C" int gb_pf_enable_window(gb_pf_t *pf, int W) {
+  REQ(pf, "null handle");
+  REQ(W >= 0 && W <= kWinMax, "gb_pf_enable_window: 0 <= W <= 8");
+  REQ(pf->n == pf->n_global, "gb_pf_enable_window: single-shard filters only");
+  REQ(!(W > 0 && pf->history), "gb_pf_enable_window: not together with gb_pf_enable_history (window moves rewrite the recent past)");
+  DeviceScope ds__(pf->device);
+  {
+    FreeBatch fb__;
+    gb_dev_free(pf->win[0]); gb_dev_free(pf->win[1]);
+  }
+  pf->win[0] = pf->win[1] = nullptr;
+  pf->win_W = W; pf->win_len = 0; pf->win_cur = 0;
+  if (W > 0) {
+    const size_t bytes = (size_t)W * pf->S * pf->ld * pf->esz;
+    CK(gb_dev_alloc(&pf->win[0], bytes));
+    CK(gb_dev_alloc(&pf->win[1], bytes));
+    CK(cudaMemsetAsync(pf->win[0], 0, bytes, pf->stream));
+    CK(cudaMemsetAsync(pf->win[1], 0, bytes, pf->stream));
+  }
+  return GB_OK;
+}
+// shift = 1: after particle_filter_step! (parent = the buffer the step read, through `anc` iff it gathered);
+// shift = 0: the eager resample gather moves the window with the particles
+static int window_update(gb_pf *pf, const void *parent_state, const int *anc, int shift) {
+  if (pf->win_W == 0) return GB_OK;
+  if (pf->dtype == GB_F64) {
+    auto kern = window_shift_kernel<double>;
+    int grid = grid_for(pf, kern, pf->n, kBlock);
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((const double *)parent_state, (const double *)pf->win[pf->win_cur],
+                                                                   (double *)pf->win[pf->win_cur ^ 1], anc, pf->S, pf->win_W, shift, pf->n, pf->ld));
+  } else {
+    auto kern = window_shift_kernel<float>;
+    int grid = grid_for(pf, kern, pf->n, kBlock);
+    LAUNCH(pf, GB_K_GATHER, kern<<<grid, kBlock, 0, pf->stream>>>((const float *)parent_state, (const float *)pf->win[pf->win_cur],
+                                                                   (float *)pf->win[pf->win_cur ^ 1], anc, pf->S, pf->win_W, shift, pf->n, pf->ld));
+  }
+  CK(cudaGetLastError());
+  pf->win_cur ^= 1;
+  if (shift) pf->win_len = std::min(pf->win_len + 1, pf->win_W);
+  return GB_OK;
+}
+
 extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, const double *pargs, int npargs) {
   REQ(pf, "null handle");
   REQ(nobs == pf->model.nobs, "gb_pf_generate: wrong number of observations");
@@ -879,6 +926,7 @@ extern "C" int gb_pf_generate(gb_pf_t *pf, const double *obs, int nobs, int pk, 
   int rc = check_noise(pf, true, &predrawn);
   if (rc) return rc;
   pf->step = 0;
+  pf->win_len = 0;
   pf->log_ml_est = 0.0;               // particle_filter.jl:133,153
   pf->anc_valid = pf->parents64_valid = pf->pending_gather = false;   // parents = collect(1:N)
   if (pf->model.kind == MODEL_BLR) {
@@ -926,6 +974,7 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
   const bool gather = pf->pending_gather;
   rc = launch_model(pf, obs, nobs, pk, pargs, npargs, false, predrawn, gather ? 1 : 0);
   if (rc) return rc;
+  if ((rc = window_update(pf, pf->state[pf->cur], gather ? pf->anc : nullptr, 1))) return rc;
   pf->step += 1;
   pf->cur ^= 1;                       // particle_filter.jl:203-205, :234-237 (swap traces/new_traces)
   pf->pending_gather = false;
@@ -1111,6 +1160,71 @@ extern "C" int gb_pf_rejuvenate(gb_pf_t *pf, int move, const double *obs, int no
   return GB_OK;
 }
 
+// Sliding-window rejuvenation (kernels_mh.cuh window_mh_kernel): one block MH move per particle on the latent choices of
+// steps a..b, 1 <= a <= b <= current step, reaching back at most W steps (gb_pf_enable_window).
+extern "C" int gb_pf_rejuvenate_window(gb_pf_t *pf, int a, int b, const double *obs_window, int nobs, double drift_std,
+                                       int64_t *n_accepted, double *alpha_out) {
+  REQ(pf && obs_window, "gb_pf_rejuvenate_window: null argument");
+  const int kind = pf->model.kind;
+  if (!(kind == MODEL_LGSSM || kind == MODEL_SV || kind == MODEL_BEARINGS))
+    return fail(GB_EUNSUPPORTED, "gb_pf_rejuvenate_window: Gaussian-drift window moves need continuous latent choices (LGSSM, SV, BEARINGS)");
+  REQ(pf->win_W > 0, "gb_pf_rejuvenate_window: call gb_pf_enable_window before initialize");
+  REQ(nobs == 1, "gb_pf_rejuvenate_window: one scalar observation per step");
+  REQ(drift_std > 0.0, "gb_pf_rejuvenate_window: drift_std must be positive");
+  REQ(a >= 1 && a <= b && b <= pf->step, "gb_pf_rejuvenate_window: need 1 <= a <= b <= current step");
+  const int L = pf->step - a + 1;
+  if (L > pf->win_len)
+    return fail(GB_ESTATE, "gb_pf_rejuvenate_window: step a - 1 lies outside the window kept per particle (W = " + std::to_string(pf->win_W) +
+                               ", valid lags " + std::to_string(pf->win_len) + ")");
+  if (pf->pending_gather) return fail(GB_ESTATE, "gb_pf_rejuvenate_window: call it before maybe_resample (docs/src/tutorials/smc.md:518-524)");
+  DeviceScope ds__(pf->device);
+  const int nb = b - a + 1;
+  const int nd = kind == MODEL_BEARINGS ? 2 : 1;
+  const bool predrawn = pf->nn_set > 0 || pf->nu_set > 0;
+  if (predrawn) REQ(pf->nn_set >= nb * nd && pf->nu_set >= 1, "gb_pf_set_noise: a window move consumes (b - a + 1) x (choices per step) normal rows and ONE uniform row");
+  WinMhArgs wa;
+  memset(&wa, 0, sizeof(wa));
+  int rc = fill_model_params(pf, wa.mp, obs_window, 1, PROPOSAL_DEFAULT, nullptr, 0, false);
+  if (rc) return rc;
+  for (int j = 0; j < L; j++) wa.obsw[j] = obs_window[j];
+  unsigned long long *d_acc = nullptr;
+  double *d_alpha = nullptr;
+  CK(gb_dev_alloc((void **)&d_acc, 8));
+  CK(cudaMemsetAsync(d_acc, 0, 8, pf->stream));
+  if (alpha_out) {
+    cudaError_t e = gb_dev_alloc((void **)&d_alpha, (size_t)pf->n * 8);
+    if (e != cudaSuccess) { gb_dev_free(d_acc); return fail(GB_ECUDA, cudaGetErrorString(e)); }
+  }
+  wa.cur = pf->state[pf->cur]; wa.win = pf->win[pf->win_cur];
+  wa.normals = pf->d_normals; wa.uniforms = pf->d_uniforms; wa.alpha_out = d_alpha;
+  wa.n = pf->n; wa.ld = pf->ld; wa.pid_offset = pf->pid_offset; wa.seed = pf->seed;
+  wa.step = (unsigned)pf->step; wa.move = pf->mh_moves;
+  wa.L = L; wa.nb = nb; wa.W = pf->win_W; wa.drift_sd = drift_std; wa.accepted = d_acc;
+  const int grid = (int)std::min<long long>((pf->n + 127) / 128, (long long)pf->num_sms * 8);
+#define GO(R, K)                                                                                              \
+  {                                                                                                           \
+    if (predrawn) LAUNCH(pf, GB_K_MISC, window_mh_kernel<R, K, true><<<grid, 128, 0, pf->stream>>>(wa));      \
+    else LAUNCH(pf, GB_K_MISC, window_mh_kernel<R, K, false><<<grid, 128, 0, pf->stream>>>(wa));              \
+  }
+  const bool f64 = pf->dtype == GB_F64;
+  if (kind == MODEL_LGSSM) { if (f64) GO(double, MODEL_LGSSM) else GO(float, MODEL_LGSSM) }
+  else if (kind == MODEL_SV) { if (f64) GO(double, MODEL_SV) else GO(float, MODEL_SV) }
+  else { if (f64) GO(double, MODEL_BEARINGS) else GO(float, MODEL_BEARINGS) }
+#undef GO
+  unsigned long long acc = 0;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&acc, d_acc, 8, cudaMemcpyDeviceToHost, pf->stream);
+  if (e == cudaSuccess && alpha_out) e = cudaMemcpyAsync(alpha_out, d_alpha, (size_t)pf->n * 8, cudaMemcpyDeviceToHost, pf->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
+  gb_dev_free(d_acc); gb_dev_free(d_alpha);
+  if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_rejuvenate_window: ") + cudaGetErrorString(e));
+  pf->mh_moves += 1;
+  pf->mh_ok = false;             // the latest-step moves keep their parents in the other trace buffer, which this move bypassed
+  pf->nn_set = pf->nu_set = 0;
+  if (n_accepted) *n_accepted = (int64_t)acc;
+  return GB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // weights: stats, materialisation
 // ------------------------------------------------------------------------------------------
@@ -1135,6 +1249,10 @@ static int run_gather(gb_pf *pf) {   // materialise a deferred resample gather
                                                                    pf->ld, pf->S, pf->anc, pf->n, (float *)pf->logw));
   }
   CK(cudaGetLastError());
+  {
+    const int wrc = window_update(pf, nullptr, pf->anc, 0);
+    if (wrc) return wrc;
+  }
   pf->cur ^= 1;                       // particle_filter.jl:270-272
   pf->mh_ok = false;
   pf->pending_gather = false;
@@ -1667,6 +1785,7 @@ static int pf_run_impl(gb_pf *pf, int T, const double *obs, int nobs, double ess
   pf->h_ctl->log_n = log((double)pf->n_global);
   CK(cudaMemcpyAsync(pf->d_ctl, pf->h_ctl, sizeof(RunCtl), cudaMemcpyHostToDevice, pf->stream));
   CK(cudaStreamSynchronize(pf->stream));                // h_ctl is reused for the read-back below
+  pf->win_len = 0;                    // (the fused entries do not maintain the rejuvenation window)
   if (sweeps == 0 && small_run_eligible(pf, T)) return small_run(pf, T, obs, nobs, n_resampled);
   if (sweeps > 0) {
     const int kind = pf->model.kind;

@@ -147,6 +147,19 @@ int gb_pf_sample_unweighted(gb_pf_t *pf, int64_t n_samples, uint64_t draw, int64
 #define GB_MH_DRIFT 1
 int gb_pf_rejuvenate(gb_pf_t *pf, int move, const double *obs, int nobs, double drift_std, int64_t *n_accepted,
                      double *alpha_out);
+/* Sliding-window rejuvenation (docs/src/tutorials/smc.md:492-541): ONE block MH move per particle,
+ *     mh(trace, perturbation_proposal, (a, b)),  {latent choices of step t} ~ normal(current value, drift_std) for a <= t <= b,
+ * accepted with the update weight of src/dynamic/update.jl:46-62 -- the latent choices of steps a..b+1 under their (moved)
+ * parents and the observations of ALL steps a..T -- minus the forward and plus the backward proposal score (mh.jl:37-58).
+ * gb_pf_enable_window(W) (before gb_pf_generate; 1 <= W <= 8; single shard; not with gb_pf_enable_history) makes every
+ * particle carry the last W states of its own lineage (window columns gathered with it at every resample); a move may
+ * reach back to step a >= T - W + 1.  obs_window: the observations of steps a..T (T - a + 1 scalars).  Call between
+ * particle_filter_step! and maybe_resample!, like gb_pf_rejuvenate (which it disables until the next step).  Models: LGSSM,
+ * SV, BEARINGS.  Validation noise (gb_pf_set_noise): (b - a + 1) x (choices per step) normal rows, step-major, and ONE
+ * uniform row (the accept draw).  The fused gb_pf_run* entries do not maintain the window. */
+int gb_pf_enable_window(gb_pf_t *pf, int W);
+int gb_pf_rejuvenate_window(gb_pf_t *pf, int a, int b, const double *obs_window, int nobs, double drift_std,
+                            int64_t *n_accepted, double *alpha_out);
 /* Run-time specialisation of GB_MODEL_SPEC models.  Gen turns a static-IR function into straight-line code per trace
  * type (`@generated` functions, src/static_ir/generate.jl:68-109, update.jl:467-513); here the program that crossed
  * this boundary is lowered to CUDA C++ (one statement per node, parameters as literals) and compiled for sm_100a

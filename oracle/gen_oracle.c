@@ -486,6 +486,8 @@ struct go_pf {
   int64_t *parents;  /* :40, 1-based */
   int mh_ok;         /* new_state still holds the parents of `state` (rows aligned) */
   int storage_f32;   /* GB_F32 storage model: traces, log weights and increments are rounded to float when stored */
+  int win_W, win_len; /* sliding-window rejuvenation: the last win_W states of every particle's own lineage */
+  double *win;       /* [win_W][S][n]: win[k] = the state k+1 steps before the current one */
 };
 
 /* Storage model of the engine's GB_F32 filters (this repo's extension; Gen itself is Float64 only): the per-particle
@@ -683,10 +685,34 @@ int go_pf_step(go_pf_t *pf, const double *obs, int pk, const double *pa, const d
     pf->logw[i] = st_round(pf, pf->logw[i] + incr[i]);            /* :199, :231 */
     incr[i] = st_round(pf, incr[i]);
   }
+  if (pf->win_W > 0) { /* the window follows the trace: the state the step extended becomes lag 1 */
+    const size_t blk = (size_t)pf->S * pf->n;
+    for (int k = pf->win_W - 1; k >= 1; k--) memcpy(pf->win + (size_t)k * blk, pf->win + (size_t)(k - 1) * blk, blk * 8);
+    memcpy(pf->win, pf->state, blk * 8);
+    if (pf->win_len < pf->win_W) pf->win_len++;
+  }
   swap_traces(pf);                                                 /* :203-205, :234-237 */
   pf->mh_ok = 1;
   if (!incr_out) free(incr);
   return 0;
+}
+/* Gen's traces are persistent copies: resampling particle i from ancestor a copies a's whole past.  Here: the window rows. */
+static void window_gather(go_pf_t *pf, const int64_t *anc0 /* 0-based */) {
+  if (pf->win_W == 0) return;
+  const int64_t n = pf->n;
+  const size_t rows = (size_t)pf->win_W * pf->S;
+  double *tmp = (double *)malloc((size_t)n * 8);
+  for (size_t r = 0; r < rows; r++) {
+    double *col = pf->win + r * n;
+    for (int64_t i = 0; i < n; i++) tmp[i] = col[anc0[i]];
+    memcpy(col, tmp, (size_t)n * 8);
+  }
+  free(tmp);
+}
+void go_pf_enable_window(go_pf_t *pf, int W) {
+  free(pf->win);
+  pf->win = W > 0 ? (double *)calloc((size_t)W * pf->S * pf->n, 8) : NULL;
+  pf->win_W = W; pf->win_len = 0;
 }
 /* particle_filter.jl:249-275 */
 int go_pf_maybe_resample(go_pf_t *pf, double ess_threshold, int kind, int use_given_u0, uint32_t u0,
@@ -723,6 +749,7 @@ int go_pf_maybe_resample(go_pf_t *pf, double ess_threshold, int kind, int use_gi
     pf->logw[i] = 0.0;
   }
   swap_traces(pf);                                                 /* :270-272 */
+  window_gather(pf, anc);
   pf->mh_ok = 0;
   free(anc);
   return 1;
@@ -743,6 +770,12 @@ int go_pf_resample_given(go_pf_t *pf, const int64_t *parents) {
     pf->logw[i] = 0.0;
   }
   swap_traces(pf);                                                 /* :270-272 */
+  if (pf->win_W > 0) {
+    int64_t *anc0 = (int64_t *)malloc((size_t)n * 8);
+    for (int64_t i = 0; i < n; i++) anc0[i] = parents[i] - 1;
+    window_gather(pf, anc0);
+    free(anc0);
+  }
   pf->mh_ok = 0;
   return 1;
 }
@@ -863,6 +896,88 @@ int64_t go_pf_rejuvenate(go_pf_t *pf, int move, const double *obs, double drift_
   }
   return total;
 }
+/* Sliding-window block move (docs/src/tutorials/smc.md:492-541): mh(trace, perturbation_proposal, (a, b)) with
+ * {latent choices of step t} ~ normal(current value, drift_std) for a <= t <= b (mh.jl:37-58).  The update weight
+ * (dynamic/update.jl:46-62) sums score' - score over every choice whose value or arguments change: the latent choices of
+ * steps a..T under their parents (unperturbed ones cancel unless their parent moved) and the observations of steps a..T.
+ * Noise: pre-drawn rows (normals [(b-a+1) * choices per step][n], step-major; uniforms [1][n] = the accept draw) or Philox
+ * draw-index block 0x900000 + 64 * move_index (pairs) and pair + 63 for the accept draw.  Returns #accepted, -1 if the
+ * window does not reach back to step a - 1. */
+int64_t go_pf_rejuvenate_window(go_pf_t *pf, int a, int b, const double *obs_window, double drift_std, uint32_t move_index,
+                                const double *normals, const double *uniforms, double *alpha_out, uint8_t *accepted_out) {
+  const int kind = pf->kind, S = pf->S, T = pf->step;
+  const int64_t n = pf->n;
+  const int L = T - a + 1, nb = b - a + 1;
+  if (kind == GO_MODEL_HMM || kind == GO_MODEL_BLR || a < 1 || b < a || b > T || L > pf->win_len) return -1;
+  const uint32_t base = 0x900000u + 64u * move_index;
+  int64_t total = 0;
+#pragma omp parallel for schedule(static) reduction(+ : total) if (g_threads > 1)
+  for (int64_t i = 0; i < n; i++) {
+    double told[9][8], tnew[9][8];
+    for (int j = 0; j <= L; j++) {
+      const int lag = L - j;
+      for (int s = 0; s < S; s++)
+        told[j][s] = lag == 0 ? pf->state[(int64_t)s * n + i] : pf->win[((int64_t)(lag - 1) * S + s) * n + i];
+    }
+    for (int s = 0; s < S; s++) tnew[0][s] = told[0][s];
+    double weight = 0.0, fwd = 0.0, bwd = 0.0;
+    for (int j = 1; j <= L; j++) {
+      const int t = a - 1 + j;
+      const int *cidx;
+      const int nc = model_latent_choices(kind, t, &cidx);
+      double c_new[4], c_old[4];
+      for (int k = 0; k < nc; k++) {
+        c_old[k] = told[j][cidx[k]];
+        if (j <= nb) {
+          const int idx = (j - 1) * nc + k;
+          double e;
+          if (normals) e = normals[(int64_t)idx * n + i];
+          else {
+            double e0, e1;
+            philox_normal_pair(pf->seed, (uint64_t)i, (uint32_t)T, base + (uint32_t)(idx >> 1), &e0, &e1);
+            e = (idx & 1) ? e1 : e0;
+          }
+          c_new[k] = go_random_normal(c_old[k], drift_std, e);                   /* proposal: {addr} ~ normal(choices[addr], std) */
+          fwd += go_logpdf_normal(c_new[k], c_old[k], drift_std);                /* propose: mh.jl:44 */
+        } else {
+          c_new[k] = c_old[k];
+        }
+      }
+      model_state_from_choices(kind, t, tnew[j - 1], c_new, tnew[j]);
+      for (int k = 0; k < nc; k++)                                               /* update.jl:46-50 */
+        weight += model_latent_score(kind, pf->params, t, tnew[j - 1], k, c_new[k]) -
+                  model_latent_score(kind, pf->params, t, told[j - 1], k, c_old[k]);
+      weight += model_obs_logpdf(kind, pf->params, tnew[j], obs_window + (j - 1)) -
+                model_obs_logpdf(kind, pf->params, told[j], obs_window + (j - 1));
+      if (j <= nb)
+        for (int k = 0; k < nc; k++) bwd += go_logpdf_normal(c_old[k], c_new[k], drift_std);   /* assess: mh.jl:48 */
+    }
+    const double alpha = weight - fwd + bwd;                                     /* mh.jl:49 */
+    double ua;
+    if (uniforms) ua = uniforms[i];
+    else {
+      double u0, u1;
+      philox_uniform_pair(pf->seed, (uint64_t)i, (uint32_t)T, base + 63u, &u0, &u1);
+      ua = u0;
+    }
+    const int acc = log(ua) < alpha;                                             /* mh.jl:52 */
+    if (alpha_out) alpha_out[i] = alpha;
+    if (accepted_out) accepted_out[i] = (uint8_t)acc;
+    if (acc) {
+      for (int j = 1; j <= L; j++) {
+        const int lag = L - j;
+        for (int s = 0; s < S; s++) {
+          const double v = st_round(pf, tnew[j][s]);
+          if (lag == 0) pf->state[(int64_t)s * n + i] = v;
+          else pf->win[((int64_t)(lag - 1) * S + s) * n + i] = v;
+        }
+      }
+      total++;
+    }
+  }
+  pf->mh_ok = 0;
+  return total;
+}
 /* particle_filter.jl:91-94 */
 double go_pf_log_ml_estimate(const go_pf_t *pf) {
   return pf->log_ml_est + go_logsumexp(pf->logw, pf->n) - log((double)pf->n);
@@ -884,10 +999,15 @@ go_pf_t *go_pf_copy(const go_pf_t *s) {
   pf->new_state = (double *)malloc(sn); memcpy(pf->new_state, s->new_state, sn);
   pf->logw = (double *)malloc(nn); memcpy(pf->logw, s->logw, nn);
   pf->parents = (int64_t *)malloc(nn); memcpy(pf->parents, s->parents, nn);
+  if (s->win) {
+    const size_t wb = (size_t)s->win_W * sn;
+    pf->win = (double *)malloc(wb); memcpy(pf->win, s->win, wb);
+  }
   return pf;
 }
 void go_pf_free(go_pf_t *pf) {
   if (!pf) return;
+  free(pf->win);
   free(pf->params); free(pf->state); free(pf->new_state); free(pf->logw); free(pf->parents); free(pf);
 }
 /* importance.jl:20-59 */

@@ -103,6 +103,11 @@ int go_pf_resample_given(go_pf_t *pf, const int64_t *parents);
  * move 1 = mh(trace, gaussian-drift proposal, (drift_std,)) (mh.jl:37-58).  Returns #accepted, -1 if unsupported. */
 int64_t go_pf_rejuvenate(go_pf_t *pf, int move, const double *obs, double drift_std, uint32_t move_index,
                          const double *normals, const double *uniforms, double *alpha_out, uint8_t *accepted_out);
+/* sliding-window rejuvenation (docs/src/tutorials/smc.md:492-541): keep the last W states of every particle's lineage
+ * (call right after go_pf_init), then one block drift move mh(trace, perturbation_proposal, (a, b)) per particle */
+void go_pf_enable_window(go_pf_t *pf, int W);
+int64_t go_pf_rejuvenate_window(go_pf_t *pf, int a, int b, const double *obs_window, double drift_std, uint32_t move_index,
+                                const double *normals, const double *uniforms, double *alpha_out, uint8_t *accepted_out);
 double go_pf_log_ml_estimate(const go_pf_t *pf);        /* particle_filter.jl:91-94 */
 const double *go_pf_log_weights(const go_pf_t *pf);     /* :82-84 */
 const int64_t *go_pf_parents(const go_pf_t *pf);        /* 1-based */

@@ -71,6 +71,8 @@ def lib():
             "go_pf_maybe_resample": (i, [vp, d, i, i, u32, _u64p, _dp]),
             "go_pf_resample_given": (i, [vp, _i64p]),
             "go_pf_rejuvenate": (i64, [vp, i, _dp, d, u32, _dp, _dp, _dp, C.POINTER(C.c_uint8)]),
+            "go_pf_enable_window": (None, [vp, i]),
+            "go_pf_rejuvenate_window": (i64, [vp, i, i, _dp, d, u32, _dp, _dp, _dp, C.POINTER(C.c_uint8)]),
             "go_pf_log_ml_estimate": (d, [vp]),
             "go_pf_log_weights": (_dp, [vp]),
             "go_pf_parents": (_i64p, [vp]),
@@ -269,6 +271,23 @@ class OraclePF:
                                    acc.ctypes.data_as(C.POINTER(C.c_uint8)))
         if r < 0:
             raise ValueError("oracle: MH move unsupported in this state / for this model")
+        return r, alpha, acc.astype(bool)
+
+    def enable_window(self, W):
+        lib().go_pf_enable_window(self._p, int(W))
+
+    def rejuvenate_window(self, a, b, obs_window, drift_std, move_index=0, normals=None, uniforms=None):
+        """One block drift move on the latent choices of steps a..b per particle (docs/src/tutorials/smc.md:492-541).
+        Returns (#accepted, log acceptance ratios, accepted flags)."""
+        oa, op = _d(obs_window)
+        na, np_ = _d(normals)
+        ua, up = _d(uniforms)
+        alpha = np.empty(self.n, dtype=np.float64)
+        acc = np.empty(self.n, dtype=np.uint8)
+        r = lib().go_pf_rejuvenate_window(self._p, int(a), int(b), op, float(drift_std), int(move_index), np_, up,
+                                          alpha.ctypes.data_as(_dp), acc.ctypes.data_as(C.POINTER(C.c_uint8)))
+        if r < 0:
+            raise ValueError("oracle: window move unsupported in this state / for this model")
         return r, alpha, acc.astype(bool)
 
     @property

@@ -293,3 +293,113 @@ def test_spec_model_with_inline_proposal_has_no_resimulation_move(g):
     st = g.initialize_particle_filter(g.spec_model(1, [], 1, p), (0,), 0.3, 1000)
     with pytest.raises(g.GenB200Error, match="custom proposal"):
         g.rejuvenate_(st, 0.3)
+
+
+# ---------------------------------------------------------------- sliding-window rejuvenation (smc.md:492-541)
+def _bearings_log_joint(p, traj, zs_window):
+    """log p(latent choices of steps 1..L, observations | step 0) for a bearings trajectory [L+1][4][n] (numpy, independent
+    of the oracle's C code): velocities ~ normal(previous velocity, sqrt(var)); positions accumulate; z ~ normal(atan2(y, x), noise)."""
+    lj = 0.0
+    sdv = math.sqrt(p[8])
+    for j in range(1, len(traj)):
+        lj = lj + npdf(traj[j][2], traj[j - 1][2], sdv) + npdf(traj[j][3], traj[j - 1][3], sdv)
+        lj = lj + npdf(zs_window[j - 1], np.arctan2(traj[j][1], traj[j][0]), p[9])
+    return lj
+
+
+def test_oracle_window_move_is_joint_density_ratio(O):
+    """Gaussian drift is symmetric, so the acceptance ratio of the block move on the velocities of steps a..b is the ratio of
+    the log joint of the whole replayed trajectory a-1..T, positions recomputed from the perturbed velocities."""
+    n, T, W = 300, 6, 5
+    rng = np.random.default_rng(8)
+    zs = F.bearings_series(T + 1)
+    p = F.BEARINGS_PARAMS
+    pf = O.OraclePF.init(O.MODEL_BEARINGS, p, n, [zs[0]], normals=rng.standard_normal((4, n)))
+    pf.enable_window(W)
+    snaps = [np.stack([pf.state(f) for f in range(4)])]
+    for t in range(1, T + 1):
+        pf.step([zs[t]], normals=rng.standard_normal((2, n)))
+        snaps.append(np.stack([pf.state(f) for f in range(4)]))         # no resampling: lineage = identity
+    a, b, sd = 3, 5, 1e-3
+    nb = b - a + 1
+    eps, ua = rng.standard_normal((2 * nb, n)), rng.random((1, n))
+    nacc, alpha, acc = pf.rejuvenate_window(a, b, zs[a:T + 1], sd, normals=eps, uniforms=ua)
+    old = [snaps[t] for t in range(a - 1, T + 1)]
+    new = [old[0]]
+    for j in range(1, len(old)):
+        vx, vy = old[j][2].copy(), old[j][3].copy()
+        if j <= nb:
+            vx = vx + sd * eps[2 * (j - 1)]
+            vy = vy + sd * eps[2 * (j - 1) + 1]
+        new.append(np.stack([new[j - 1][0] + vx, new[j - 1][1] + vy, vx, vy]))
+    ref = _bearings_log_joint(p, new, zs[a:T + 1]) - _bearings_log_joint(p, old, zs[a:T + 1])
+    assert np.allclose(alpha, ref, rtol=1e-8, atol=1e-8)
+    assert np.array_equal(acc, np.log(ua[0]) < alpha) and nacc == acc.sum() and 0 < nacc < n
+    assert np.allclose(pf.state(0), np.where(acc, new[-1][0], old[-1][0]), rtol=0, atol=1e-15)
+    with pytest.raises(ValueError):
+        pf.rejuvenate_window(1, 2, zs[1:T + 1], sd)                     # step 0 lies outside a 5-deep window at T = 6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["bearings", "lgssm", "sv"])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_window_rejuvenation_matches_oracle(g, O, name, dtype):
+    """The tutorial's particle_filter_rejuv loop (smc.md:513-531): block drift moves on the last five steps before every
+    resample.  Pre-drawn noise on both sides: accept decisions, traces (current AND inside the window, checked through the
+    later moves that read them) and ancestors bit-exact, log acceptance ratios to 1e-10; then the Philox-driven move."""
+    from test_gpu_parity import model_zoo, _series
+    model, okind_m, params, _, _, _ = model_zoo(g, O)[name]
+    n, T, W, sd = 6007, 12, 5, (1e-3 if name == "bearings" else 0.2)
+    ys = _series(name, T + 1)
+    rng = np.random.default_rng(5)
+    nn0, nn1 = model.num_normals(True), model.num_normals(False)
+    nd = 2 if name == "bearings" else 1
+    f32 = dtype == "f32"
+    rnd = (lambda *s: rng.standard_normal(s).astype(np.float32).astype(np.float64)) if f32 else (lambda *s: rng.standard_normal(s))
+    st = g.create_particle_filter(model, n, dtype=dtype, seed=3)
+    st.enable_window(W)
+    eps = rnd(nn0, n)
+    st.set_noise(eps)
+    g.generate_(st, ys[0])
+    O.lib().go_set_storage_f32(1 if f32 else 0)
+    try:
+        ref = O.OraclePF.init(okind_m, params, n, [ys[0]], seed=3, normals=eps)
+    finally:
+        O.lib().go_set_storage_f32(0)
+    ref.enable_window(W)
+    tol = 1e-5 if f32 else RTOL64
+    total = 0
+    for t in range(1, T + 1):
+        eps = rnd(nn1, n)
+        st.set_noise(eps)
+        g.particle_filter_step_(st, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+        ref.step([ys[t]], normals=eps)
+        a, b = max(1, t - 4), t                                          # the last five steps (smc.md:524)
+        nb = b - a + 1
+        e2 = rnd(nb * nd, n)
+        ua = rng.random((1, n)).astype(np.float32).astype(np.float64) if f32 else rng.random((1, n))
+        st.set_noise(e2, ua)
+        nacc, alpha = g.rejuvenate_window_(st, a, b, ys[a:t + 1], sd, return_alpha=True)
+        nacc_ref, alpha_ref, acc_ref = ref.rejuvenate_window(a, b, ys[a:t + 1], sd, normals=e2, uniforms=ua)
+        assert nacc == nacc_ref, (t, nacc, nacc_ref)
+        assert np.allclose(alpha, alpha_ref, rtol=tol, atol=tol * 10), (t, np.abs(alpha - alpha_ref).max())
+        for f in range(model.state_dim):
+            assert np.array_equal(st.get_state(f), ref.state(f)), (t, f)
+        total += nacc
+        if t == T and not f32:
+            # production noise (Philox): same counts / traces as the oracle driven by the same counter-based stream
+            nacc = g.rejuvenate_window_(st, T - 2, T, ys[T - 2:T + 1], sd)
+            nacc_ref, _, _ = ref.rejuvenate_window(T - 2, T, ys[T - 2:T + 1], sd, move_index=1)
+            assert nacc == nacc_ref and nacc > 0
+            # (the engine's Box-Muller uses its own table-driven log / sincos: same Philox integers, normals equal to ~1e-16)
+            assert np.allclose(st.get_state(0), ref.state(0), rtol=0, atol=1e-12)
+        u0 = 777 + t
+        st.set_resample_noise(u0=u0)
+        did = g.maybe_resample_(st, ess_threshold=n / 2 if t % 2 else n, resampler="systematic")
+        assert did == ref.maybe_resample(ess_threshold=n / 2 if t % 2 else n, kind=O.RESAMPLE_SYSTEMATIC, u0=u0)
+        if did:
+            assert np.array_equal(st.parents, ref.parents)
+    assert 0 < total < T * n
+    # reaching back beyond the window is refused, not approximated
+    with pytest.raises(g.GenB200Error):
+        g.rejuvenate_window_(st, T - 6, T, ys[T - 6:T + 1], sd)
