@@ -90,6 +90,7 @@ SIGNATURES = {
     "gb_pf_async_cur": (i, [vp, ip]),
     "gb_pf_xchg_post": (i, [vp]),
     "gb_pf_xchg_stats": (i, [vp]),
+    "gb_pf_xchg_stats_plan": (i, [vp, u32]),
     "gb_pf_async_plan": (i, [vp, u32, d, i]),
     "gb_pf_async_sweep": (i, [vp]),
     "gb_pf_async_export": (i, [vp]),

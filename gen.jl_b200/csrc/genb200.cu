@@ -1592,7 +1592,8 @@ static int launch_cdf(gb_pf *pf) {
 // shard's offspring slots; single shard: q_offset = 0, q_total = 0 (= the local total), anc_base = 0.
 template <typename R>
 static int launch_systematic(gb_pf *pf, const void *logw, double m, uint64_t q_offset, uint64_t q_total, uint32_t u0,
-                             const AncOut &ao, const RunCtl *ctl = nullptr, int plan_preset = 0, bool plan_done = false) {
+                             const AncOut &ao, const RunCtl *ctl = nullptr, int plan_preset = 0, bool plan_done = false,
+                             bool export_rows = false) {
   const int bits = quant_bits(pf->n_global);
   if (!plan_done) {   // (fused run: the statistics kernel's last CTA already scanned the super-tiles and wrote the plan)
     LAUNCH(pf, GB_K_TILESCAN, klaunch(superscan_kernel, 1, 1024, pf->stream, pf->nsuper, pf->super_q, pf->super_excl, pf->d_plan, q_offset, q_total,
@@ -1603,9 +1604,20 @@ static int launch_systematic(gb_pf *pf, const void *logw, double m, uint64_t q_o
                                      (const uint64_t *)pf->tile_q, (const unsigned long long *)pf->super_excl, (const ResamplePlan *)pf->d_plan, ao,
                                      pf->oflow, pf->oflow_count, ctl));
   CK(cudaGetLastError());
-  LAUNCH(pf, GB_K_ANCESTORS, klaunch(overflow_sys_kernel, (unsigned)pf->num_sms * 4, kBlock, pf->stream, (const unsigned long long *)pf->qbuf,
-                                     (const ResamplePlan *)pf->d_plan, ao, (const OverflowEntry *)pf->oflow, (const unsigned int *)pf->oflow_count,
-                                     (unsigned long long *)pf->tile_q, pf->ntiles, ctl));
+  ExportArgs ex;
+  memset(&ex, 0, sizeof(ex));
+  if (export_rows) {       // sharded sweep: offspring owned by other shards leave in the same kernel (peer stores over NVLink)
+    ex.sin = pf->state[pf->cur]; ex.ld = pf->ld; ex.S = pf->S; ex.cur = pf->cur; ex.spill = pf->off_anc; ex.sh = pf->d_shplan;
+    ex.offs = pf->d_offs; ex.pid_offset = pf->pid_offset; ex.spill_cap = pf->off_cap; ex.stats = pf->d_stats;
+    ex.grid_barrier = pf->oflow_count + 8;
+  }
+  {
+    auto okern = overflow_sys_kernel<R>;
+    const unsigned ogrid = (unsigned)grid_for(pf, okern, (long long)pf->num_sms * 4 * kBlock, kBlock);   // co-resident by construction
+    LAUNCH(pf, export_rows ? GB_K_GATHER : GB_K_ANCESTORS,
+           klaunch(okern, ogrid, kBlock, pf->stream, (const unsigned long long *)pf->qbuf, (const ResamplePlan *)pf->d_plan, ao,
+                   (const OverflowEntry *)pf->oflow, (const unsigned int *)pf->oflow_count, (unsigned long long *)pf->tile_q, pf->ntiles, ctl, ex));
+  }
   CK(cudaGetLastError());
   pf->tiles_valid = false;   // superscan / overflow zeroed the accumulators for the next statistics pass
   pf->ws_clean = true;
@@ -2083,6 +2095,23 @@ extern "C" int gb_pf_xchg_stats(gb_pf_t *pf) {
   pf->wstate = keep == W_ZERO ? W_ZERO : W_MAX;   // d_stats->m is now the global max: still a valid reference for this shard
   return rc;
 }
+// gb_pf_xchg_stats + gb_pf_async_plan(u0, armed threshold, do_scan = 1) as ONE kernel: the statistics kernel's last CTA waits
+// for the peers' records and computes the plan in its tail.  Only for shards that do not share a device with a peer (the
+// waiting CTA would sit in front of the peer's statistics kernel on a shared stream).
+extern "C" int gb_pf_xchg_stats_plan(gb_pf_t *pf, uint32_t u0) {
+  int rc = gb_pf_xchg_post(pf);
+  if (rc) return rc;
+  if (pf) pf->mh_ok = false;
+  DeviceScope ds__(pf->device);
+  const int keep = pf->wstate;
+  FusedPlan fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.plan = pf->d_plan; fp.super_excl = pf->super_excl; fp.overflow_count = pf->oflow_count; fp.n_global = pf->n_global; fp.u0 = u0;
+  fp.sh = pf->d_shplan; fp.offs = pf->d_offs; fp.spill_cap = pf->off_cap; fp.sh_ctl = pf->d_ctl;
+  rc = run_wstats(pf, pf->logw, 0.0, true, false, nullptr, &fp, true);
+  pf->wstate = keep == W_ZERO ? W_ZERO : W_MAX;
+  return rc;
+}
 // ESS test + log-ML update + exchange plan on the device from the G records in this shard's mailbox.  ess_threshold NaN:
 // the armed threshold.  do_scan != 0 prepares the sweep that follows (consumes the super-tile totals).
 extern "C" int gb_pf_async_plan(gb_pf_t *pf, uint32_t u0, double ess_threshold, int do_scan) {
@@ -2101,35 +2130,14 @@ extern "C" int gb_pf_async_sweep(gb_pf_t *pf) {
   REQ(pf && pf->a_world > 0 && pf->tiles_valid, "gb_pf_async_sweep: statistics pass missing");
   DeviceScope ds__(pf->device);
   const AncOut ao{pf->anc, pf->pid_offset, pf->pid_offset + pf->n, pf->off_anc, -1, pf->off_cap};
-  return pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1, true)
-                             : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1, true);
+  const bool ex = pf->a_world > 1;      // offspring owned by other shards leave with the sweep's second kernel (+ phase C post)
+  return pf->dtype == GB_F64 ? launch_systematic<double>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1, true, ex)
+                             : launch_systematic<float>(pf, pf->logw, 0.0, 0, 0, 0, ao, pf->d_ctl, 1, true, ex);
 }
-// offspring owned by other shards -> their memory (peer stores) + phase C post; gb_pf_async_wait orders them before the step
+// (kept for drivers written against the first version of the protocol) the export of the offspring owned by other shards now
+// rides in the second kernel of gb_pf_async_sweep (overflow_sys_kernel): one launch less per step
 extern "C" int gb_pf_async_export(gb_pf_t *pf) {
   REQ(pf && pf->a_world > 0, "gb_pf_async_export: bad argument");
-  if (pf->a_world == 1) return GB_OK;
-  DeviceScope ds__(pf->device);
-  // rows that change shards are the fluctuation of the shards' weight sums (~sqrt of the shard size): a few CTAs per destination
-  const unsigned gx = (unsigned)std::min<long long>(std::max<long long>(pf->n / (4096 * kBlock), 1), 8);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(gx, (unsigned)pf->a_world, 1);
-  cfg.blockDim = dim3(kBlock, 1, 1);
-  cfg.stream = pf->stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  if (pf->dtype == GB_F64)
-    LAUNCH(pf, GB_K_GATHER, cudaLaunchKernelEx(&cfg, export_p2p_kernel<double>, (const double *)pf->state[pf->cur], pf->ld, pf->S, (const int *)pf->off_anc,
-                                               (const ResamplePlan *)pf->d_plan, (const ShardPlanDev *)pf->d_shplan, (const RunCtl *)pf->d_ctl,
-                                               (const long long *)pf->d_offs, pf->cur, pf->pid_offset, pf->off_cap, pf->d_stats));
-  else
-    LAUNCH(pf, GB_K_GATHER, cudaLaunchKernelEx(&cfg, export_p2p_kernel<float>, (const float *)pf->state[pf->cur], pf->ld, pf->S, (const int *)pf->off_anc,
-                                               (const ResamplePlan *)pf->d_plan, (const ShardPlanDev *)pf->d_shplan, (const RunCtl *)pf->d_ctl,
-                                               (const long long *)pf->d_offs, pf->cur, pf->pid_offset, pf->off_cap, pf->d_stats));
-  CK(cudaGetLastError());
   return GB_OK;
 }
 // (kept for drivers written against the first version of the protocol) the wait for the peers' "done" flags now sits at
@@ -2157,8 +2165,7 @@ extern "C" int gb_pf_async_step(gb_pf_t *pf, const double *obs, int nobs) {
 extern "C" int gb_pf_async_iterate(gb_pf_t *pf, const double *obs, int nobs) {
   REQ(pf && pf->a_world > 0, "gb_pf_async_iterate: call gb_pf_async_setup first");
   const uint32_t u0 = philox_block(pf->seed, 0, (uint32_t)pf->step, PK_RESAMPLE, 0).x;
-  int rc = gb_pf_xchg_stats(pf);
-  if (!rc) rc = gb_pf_async_plan(pf, u0, NAN, 1);
+  int rc = gb_pf_xchg_stats_plan(pf, u0);          // (one shard per process: no peer shares this device)
   if (!rc) rc = gb_pf_async_sweep(pf);
   if (!rc) rc = gb_pf_async_export(pf);
   if (!rc) rc = gb_pf_async_wait(pf);

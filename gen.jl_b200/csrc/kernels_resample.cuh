@@ -589,190 +589,110 @@ __global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const unsigned lo
   }
 }
 
-// Remaining slots of heavy tiles: work unit = (queue entry, kChunk-sized piece); units are dealt
-// round-robin to the CTAs of a fixed-size grid.
-__global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const unsigned long long *__restrict__ qbuf,
-                                                              const ResamplePlan *__restrict__ plan, const AncOut ao,
-                                                              const OverflowEntry *__restrict__ oflow,
-                                                              const unsigned int *__restrict__ oflow_count,
-                                                              unsigned long long *__restrict__ tile_q, long long ntiles,
-                                                              const RunCtl *__restrict__ ctl) {
-  __shared__ TileSmem sm;
-  pdl_trigger();
-  tile_smem_clear(sm);
-  pdl_wait();
-  // the sweep is done with the per-tile totals: leave the accumulator clean for the next statistics pass
-  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < ntiles; i += (long long)gridDim.x * kBlock) tile_q[i] = 0;
-  const unsigned int ne = *oflow_count;
-  if (ne == 0 || (ctl && !ctl->do_resample)) return;
-  const SweepParams sp = plan->sp;
-  long long unit0 = 0;
-  for (unsigned int e = 0; e < ne; e++) {
-    const OverflowEntry en = oflow[e];
-    const long long pieces = (en.slot_hi - en.slot_lo + kChunk - 1) / kChunk;
-    // first piece of this entry handled by this CTA (units are dealt round-robin over the grid)
-    long long first = ((long long)blockIdx.x - unit0 % gridDim.x + gridDim.x) % gridDim.x;
-    for (long long pc = first; pc < pieces; pc += gridDim.x) {
-      const long long lo = en.slot_lo + pc * kChunk;
-      long long hi = lo + kChunk;
-      if (hi > en.slot_hi) hi = en.slot_hi;
-      __syncthreads();
-      tile_fill<false>(qbuf, sp, en.tile, nullptr, nullptr, 0, en.cbase, en.slot0, lo, hi, ao,
-                          ao.spill_base >= 0 ? ao.spill_base : plan->slot_lo, sm, nullptr, nullptr);
-    }
-    unit0 += pieces;
-  }
-}
-
 // ==========================================================================================
 // Sharded resample without a host round trip and without collectives (one shard per GPU):
 //   * the global max / the per-shard sums travel through the peer-memory mailboxes of kernels_step.cuh (phases A, B);
 //   * shard_plan_kernel turns them into the ESS test, the log-ML update and the exchange plan ON THE DEVICE (every shard
 //     evaluates the same arithmetic on the same G records, so all agree without talking), then scans the super-tiles;
-//   * offspring owned by another shard are written by export_p2p_kernel STRAIGHT INTO THAT SHARD'S MEMORY over NVLink
+//   * offspring owned by another shard are written by the sweep's second kernel STRAIGHT INTO THAT SHARD'S MEMORY over NVLink
 //     (peer pointers: same process or CUDA IPC): rows into the extension rows of its current trace buffer, the slot's
 //     ancestor index and the global parent id next to them -- no staging buffer, no all-to-all, traffic = the spill;
 //   * its last CTA posts a "done" flag to every peer (phase C); the next step kernel waits for all of them before it reads
 //     the rows (xchg_wait_done at its top).
 // ==========================================================================================
-struct PeerMem {           // a peer shard's arrays (device pointers valid in THIS process)
-  void *state[2];          // its two trace buffers
-  int *anc;
-  long long *ext_parents;
-  long long ld, n_pad, ext_cap;
+// Second kernel of the sweep.  (1) leaves the per-tile accumulator clean for the next statistics pass; (2) remaining slots
+// of heavy tiles: work unit = (queue entry, kChunk-sized piece), dealt round-robin to the CTAs of the grid (normally the
+// queue is empty); (3) sharded filters: the offspring rows of slots owned by OTHER shards go straight into the owners'
+// memory (NVLink peer stores: rows into the extension rows of their current trace buffer, the slot's ancestor index and
+// global parent id next to them), and the last CTA to finish posts this shard's "done" flag (phase C) to every peer.
+// (3) used to be a kernel of its own: ~20 us of launch + fence latency per step, a twentieth of the 8-GPU strong-scaling step.
+struct ExportArgs {
+  const void *sin;                 // current traces (source rows); nullptr: not a sharded sweep
+  long long ld;
+  int S, cur;
+  const int *spill;                // ancestors of the slots this shard produced for other shards
+  const ShardPlanDev *sh;
+  const long long *offs;
+  long long pid_offset, spill_cap;
+  WeightStats *stats;
+  unsigned int *grid_barrier;      // monotone counter (only used when heavy tiles queued work: their slots may be exported)
 };
-struct ShardPlanDev {
-  PeerMem peer[kMaxWorld];
-  long long send_lo[kMaxWorld], send_hi[kMaxWorld];   // global slots produced here that shard d owns
-  long long ext_off[kMaxWorld];                       // first extension row at shard d for the rows sent from here
-  int world, rank;
-  int overflow;                                       // sticky: a capacity was exceeded, results are invalid
-  WeightStats global;                                 // {m, S1, S2, lse, ess, Q} over ALL shards (what the host reads)
-  unsigned long long q_shard[kMaxWorld];              // every shard's integer CDF mass (host-side capacity check)
-};
-
-// One CTA (1024 threads).  Waits for every shard's record (phase B), takes the maybe_resample! decision
-// (particle_filter.jl:256; ess_threshold NaN: the run's own threshold in ctl), updates the log-ML estimate (:263), writes
-// the sweep + exchange plan and, when a sweep follows (do_scan), the exclusive scan of this shard's super-tile totals.
-__global__ void __launch_bounds__(1024) shard_plan_kernel(WeightStats *stats, const long long *__restrict__ offs, long long n_global, uint32_t u0,
-                                                          double ess_threshold, int do_scan, long long spill_cap, RunCtl *ctl,
-                                                          ResamplePlan *plan, ShardPlanDev *sh, long long nsuper,
-                                                          unsigned long long *__restrict__ super_q,
-                                                          unsigned long long *__restrict__ super_excl, unsigned int *overflow_count) {
-  __shared__ SweepParams s_sp;
-  __shared__ unsigned long long s_pref[kMaxWorld + 1];
-  __shared__ long long s_lo[kMaxWorld], s_hi[kMaxWorld];
-  __shared__ int s_do;
-  __shared__ uint64_t s_w[33];
-  pdl_trigger();
-  pdl_wait();
-  XchgCtl *xc = stats->xc;
-  const int world = xc->world, rank = xc->rank;
-  const int r = threadIdx.x;
-  const unsigned long long seq = __ldcg(&xc->seq_b);
-  if (r < world) xchg_spin(&xc->mine->rec_seq[r], seq, xc);
-  __syncthreads();
-  const int slot = (int)(seq & 1);
-  if (r == 0) {
-    const double m = __ldcg(&stats->m);        // the GLOBAL max: wstats folded phase A and left it here
-    double S1 = 0.0, S2 = 0.0;
-    unsigned long long run = 0;
-    for (int k = 0; k < world; k++) {          // fixed rank order: identical on every shard
-      S1 += __ldcg(&xc->mine->s1[slot][k]);
-      S2 += __ldcg(&xc->mine->s2[slot][k]);
-      s_pref[k] = run;
-      const unsigned long long qk = __ldcg(&xc->mine->q[slot][k]);
-      sh->q_shard[k] = qk;
-      run += qk;
-    }
-    s_pref[world] = run;
-    const double lse = (m == -INFINITY) ? -INFINITY : m + log(S1);   // inference.jl:5
-    const double ess = (S1 * S1) / S2;                                // particle_filter.jl:3-6
-    const double thr = ess_threshold == ess_threshold ? ess_threshold : ctl->ess_threshold;
-    const int flag = (ess < thr && run > 0) ? 1 : 0;                  // :256
-    ctl->do_resample = flag;
-    if (flag) { ctl->log_ml_est += lse - ctl->log_n; ctl->n_resampled += 1; }   // :263
-    s_do = flag;
-    sh->global.m = m; sh->global.s1 = S1; sh->global.s2 = S2; sh->global.lse = lse; sh->global.ess = ess; sh->global.q_total = run;
-    SweepParams sp;
-    sp.q_total = run ? run : 1;
-    sp.q_inv = 1.0 / (double)sp.q_total;
-    sp.dscale = (uint64_t)n_global << 32;
-    sp.ratio = (double)n_global / (double)sp.q_total;
-    sp.u0 = u0;
-    s_sp = sp;
-  }
-  __syncthreads();
-  if (r < world) {
-    s_lo[r] = slots_below(s_pref[r], s_sp);
-    s_hi[r] = slots_below(s_pref[r + 1], s_sp);
-  }
-  __syncthreads();
-  if (r == 0) {
-    plan->sp = s_sp;
-    plan->q_offset = s_pref[rank];
-    plan->n_global = n_global;
-    plan->slot_lo = s_lo[rank];
-    plan->slot_hi = s_hi[rank];
-    if (s_do && s_hi[rank] - s_lo[rank] > spill_cap) sh->overflow = 1;
-  }
-  if (r < world) {
-    // rows going from this shard to shard r, and where they start in r's extension rows: after the rows r receives
-    // from lower-ranked sources (every shard evaluates the same arithmetic, so all agree)
-    long long a = s_lo[rank] > offs[r] ? s_lo[rank] : offs[r], b = s_hi[rank] < offs[r + 1] ? s_hi[rank] : offs[r + 1];
-    if (b < a) b = a;
-    long long before = 0, total = 0;
-    for (int k = 0; k < world; k++) {
-      if (k == r) continue;
-      long long c = s_lo[k] > offs[r] ? s_lo[k] : offs[r], d = s_hi[k] < offs[r + 1] ? s_hi[k] : offs[r + 1];
-      const long long cnt = d > c ? d - c : 0;
-      if (k < rank) before += cnt;
-      total += cnt;
-    }
-    if (r != rank && s_do && total > sh->peer[r].ext_cap) { sh->overflow = 1; b = a; }   // r cannot park its incoming rows
-    sh->send_lo[r] = a; sh->send_hi[r] = b;
-    sh->ext_off[r] = before;
-  }
-  if (do_scan) {
-    __syncthreads();
-    superscan_block(nsuper, super_q, super_excl, plan, 0, 0, n_global, u0, overflow_count, 1, s_w);
-  }
-}
-
-// blockIdx.y = destination shard d: the rows of the slots d owns go straight into d's memory (NVLink peer stores).
-// The last CTA of the grid to finish posts this shard's "done" flag (phase C) to every peer.
 template <typename R>
-__global__ void __launch_bounds__(kBlock) export_p2p_kernel(const R *__restrict__ sin, long long ld, int S, const int *__restrict__ spill,
-                                                            const ResamplePlan *__restrict__ plan, const ShardPlanDev *__restrict__ sh,
-                                                            const RunCtl *__restrict__ ctl, const long long *__restrict__ offs,
-                                                            int cur, long long pid_offset, long long spill_cap, WeightStats *stats) {
+__global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const unsigned long long *__restrict__ qbuf,
+                                                              const ResamplePlan *__restrict__ plan, const AncOut ao,
+                                                              const OverflowEntry *__restrict__ oflow,
+                                                              const unsigned int *__restrict__ oflow_count,
+                                                              unsigned long long *__restrict__ tile_q, long long ntiles,
+                                                              const RunCtl *__restrict__ ctl, const ExportArgs ex) {
+  __shared__ TileSmem sm;
   __shared__ bool s_last;
   pdl_trigger();
+  tile_smem_clear(sm);
   pdl_wait();
-  if (!ctl->do_resample) return;               // uniform over the grid and over the shards: nobody posts, nobody waits
-  const int d = blockIdx.y;
-  const long long cnt = d == sh->rank ? 0 : sh->send_hi[d] - sh->send_lo[d];
-  if (cnt > 0) {
-    const PeerMem pm = sh->peer[d];
-    R *__restrict__ dst = static_cast<R *>(pm.state[cur]);
-    const long long base = sh->send_lo[d] - plan->slot_lo;       // index into this shard's spill buffer
-    const long long dst_slot0 = sh->send_lo[d] - offs[d];        // local slot at the destination
-    const long long ext0 = pm.n_pad + sh->ext_off[d];
-    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < cnt; i += (long long)gridDim.x * kBlock) {
-      const int src = (base + i < spill_cap) ? spill[base + i] : 0;
-      for (int s = 0; s < S; s++) dst[(long long)s * pm.ld + ext0 + i] = __ldg(sin + (long long)s * ld + src);
-      pm.anc[dst_slot0 + i] = (int)(ext0 + i);
-      pm.ext_parents[sh->ext_off[d] + i] = pid_offset + src + 1;   // Gen's parents are 1-based, global
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < ntiles; i += (long long)gridDim.x * kBlock) tile_q[i] = 0;
+  if (ctl && !ctl->do_resample) return;        // uniform over the grid and over the shards: nobody posts, nobody waits
+  const unsigned int ne = *oflow_count;
+  if (ne) {
+    const SweepParams sp = plan->sp;
+    long long unit0 = 0;
+    for (unsigned int e = 0; e < ne; e++) {
+      const OverflowEntry en = oflow[e];
+      const long long pieces = (en.slot_hi - en.slot_lo + kChunk - 1) / kChunk;
+      // first piece of this entry handled by this CTA (units are dealt round-robin over the grid)
+      long long first = ((long long)blockIdx.x - unit0 % gridDim.x + gridDim.x) % gridDim.x;
+      for (long long pc = first; pc < pieces; pc += gridDim.x) {
+        const long long lo = en.slot_lo + pc * kChunk;
+        long long hi = lo + kChunk;
+        if (hi > en.slot_hi) hi = en.slot_hi;
+        __syncthreads();
+        tile_fill<false>(qbuf, sp, en.tile, nullptr, nullptr, 0, en.cbase, en.slot0, lo, hi, ao,
+                         ao.spill_base >= 0 ? ao.spill_base : plan->slot_lo, sm, nullptr, nullptr);
+      }
+      unit0 += pieces;
     }
   }
-  XchgCtl *xc = stats->xc;
-  __syncthreads();
+  if (!ex.sin) return;
+  const ShardPlanDev *__restrict__ sh = ex.sh;
+  XchgCtl *xc = ex.stats->xc;
+  if (ne) {
+    // heavy tiles wrote spill ancestors in THIS kernel: every CTA must be past that before any row is exported (the grid is
+    // sized to be co-resident, so a counter barrier is safe; only taken in this rare case)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int t = atomicAdd(ex.grid_barrier, 1u);
+      const unsigned int target = (t / gridDim.x + 1u) * gridDim.x;
+      while (*((volatile unsigned int *)ex.grid_barrier) < target) __nanosleep(100);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  const R *__restrict__ sin = static_cast<const R *>(ex.sin);
+  bool wrote = false;
+  for (int d = 0; d < sh->world; d++) {
+    if (d == sh->rank) continue;
+    const long long cnt = sh->send_hi[d] - sh->send_lo[d];
+    if (cnt <= 0) continue;
+    const PeerMem pm = sh->peer[d];
+    R *__restrict__ dst = static_cast<R *>(pm.state[ex.cur]);
+    const long long base = sh->send_lo[d] - plan->slot_lo;       // index into this shard's spill buffer
+    const long long dst_slot0 = sh->send_lo[d] - ex.offs[d];     // local slot at the destination
+    const long long ext0 = pm.n_pad + sh->ext_off[d];
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < cnt; i += (long long)gridDim.x * kBlock) {
+      const int src = (base + i < ex.spill_cap) ? ex.spill[base + i] : 0;
+      for (int s = 0; s < ex.S; s++) dst[(long long)s * pm.ld + ext0 + i] = __ldg(sin + (long long)s * ex.ld + src);
+      pm.anc[dst_slot0 + i] = (int)(ext0 + i);
+      pm.ext_parents[sh->ext_off[d] + i] = ex.pid_offset + src + 1;   // Gen's parents are 1-based, global
+      wrote = true;
+    }
+  }
+  const int any = __syncthreads_or(wrote ? 1 : 0);
   if (threadIdx.x == 0) {
     // ONE system-scope fence per CTA, after the barrier: it is cumulative over the peer stores of every thread of the CTA
     // (they happen before it through the barrier), and orders them before the ticket and the flags below
-    if (cnt > 0) __threadfence_system();
+    if (any) __threadfence_system();
     const unsigned int t = atomicAdd(&xc->export_ticket, 1u);
-    s_last = (t == gridDim.x * gridDim.y - 1);
+    s_last = (t == gridDim.x - 1);
   }
   __syncthreads();
   if (!s_last || threadIdx.x != 0) return;

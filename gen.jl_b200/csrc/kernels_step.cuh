@@ -502,6 +502,119 @@ GB_D void superscan_block(long long nsuper, unsigned long long *__restrict__ sup
   }
 }
 
+struct PeerMem {           // a peer shard's arrays (device pointers valid in THIS process)
+  void *state[2];          // its two trace buffers
+  int *anc;
+  long long *ext_parents;
+  long long ld, n_pad, ext_cap;
+};
+struct ShardPlanDev {
+  PeerMem peer[kMaxWorld];
+  long long send_lo[kMaxWorld], send_hi[kMaxWorld];   // global slots produced here that shard d owns
+  long long ext_off[kMaxWorld];                       // first extension row at shard d for the rows sent from here
+  int world, rank;
+  int overflow;                                       // sticky: a capacity was exceeded, results are invalid
+  WeightStats global;                                 // {m, S1, S2, lse, ess, Q} over ALL shards (what the host reads)
+  unsigned long long q_shard[kMaxWorld];              // every shard's integer CDF mass (host-side capacity check)
+};
+
+// Waits for every shard's record (phase B), takes the maybe_resample! decision (particle_filter.jl:256; ess_threshold NaN: the
+// run's own threshold in ctl), updates the log-ML estimate (:263), writes the sweep + exchange plan and, when a sweep follows
+// (do_scan), the exclusive scan of this shard's super-tile totals.  One CTA (any multiple of 32 threads, >= kMaxWorld): its own
+// kernel (shard_plan_kernel, synchronous callers) or the tail of the statistics kernel's last CTA (device-controlled run: one
+// launch and one kernel boundary less per step).
+GB_D void shard_plan_block(WeightStats *stats, const long long *__restrict__ offs, long long n_global, uint32_t u0,
+                           double ess_threshold, int do_scan, long long spill_cap, RunCtl *ctl,
+                           ResamplePlan *plan, ShardPlanDev *sh, long long nsuper,
+                           unsigned long long *__restrict__ super_q,
+                           unsigned long long *__restrict__ super_excl, unsigned int *overflow_count) {
+  __shared__ SweepParams s_sp;
+  __shared__ unsigned long long s_pref[kMaxWorld + 1];
+  __shared__ long long s_lo[kMaxWorld], s_hi[kMaxWorld];
+  __shared__ int s_do;
+  __shared__ uint64_t s_w[33];
+  XchgCtl *xc = stats->xc;
+  const int world = xc->world, rank = xc->rank;
+  const int r = threadIdx.x;
+  const unsigned long long seq = __ldcg(&xc->seq_b);
+  if (r < world) xchg_spin(&xc->mine->rec_seq[r], seq, xc);
+  __syncthreads();
+  const int slot = (int)(seq & 1);
+  if (r == 0) {
+    const double m = __ldcg(&stats->m);        // the GLOBAL max: wstats folded phase A and left it here
+    double S1 = 0.0, S2 = 0.0;
+    unsigned long long run = 0;
+    for (int k = 0; k < world; k++) {          // fixed rank order: identical on every shard
+      S1 += __ldcg(&xc->mine->s1[slot][k]);
+      S2 += __ldcg(&xc->mine->s2[slot][k]);
+      s_pref[k] = run;
+      const unsigned long long qk = __ldcg(&xc->mine->q[slot][k]);
+      sh->q_shard[k] = qk;
+      run += qk;
+    }
+    s_pref[world] = run;
+    const double lse = (m == -INFINITY) ? -INFINITY : m + log(S1);   // inference.jl:5
+    const double ess = (S1 * S1) / S2;                                // particle_filter.jl:3-6
+    const double thr = ess_threshold == ess_threshold ? ess_threshold : ctl->ess_threshold;
+    const int flag = (ess < thr && run > 0) ? 1 : 0;                  // :256
+    ctl->do_resample = flag;
+    if (flag) { ctl->log_ml_est += lse - ctl->log_n; ctl->n_resampled += 1; }   // :263
+    s_do = flag;
+    sh->global.m = m; sh->global.s1 = S1; sh->global.s2 = S2; sh->global.lse = lse; sh->global.ess = ess; sh->global.q_total = run;
+    SweepParams sp;
+    sp.q_total = run ? run : 1;
+    sp.q_inv = 1.0 / (double)sp.q_total;
+    sp.dscale = (uint64_t)n_global << 32;
+    sp.ratio = (double)n_global / (double)sp.q_total;
+    sp.u0 = u0;
+    s_sp = sp;
+  }
+  __syncthreads();
+  if (r < world) {
+    s_lo[r] = slots_below(s_pref[r], s_sp);
+    s_hi[r] = slots_below(s_pref[r + 1], s_sp);
+  }
+  __syncthreads();
+  if (r == 0) {
+    plan->sp = s_sp;
+    plan->q_offset = s_pref[rank];
+    plan->n_global = n_global;
+    plan->slot_lo = s_lo[rank];
+    plan->slot_hi = s_hi[rank];
+    if (s_do && s_hi[rank] - s_lo[rank] > spill_cap) sh->overflow = 1;
+  }
+  if (r < world) {
+    // rows going from this shard to shard r, and where they start in r's extension rows: after the rows r receives
+    // from lower-ranked sources (every shard evaluates the same arithmetic, so all agree)
+    long long a = s_lo[rank] > offs[r] ? s_lo[rank] : offs[r], b = s_hi[rank] < offs[r + 1] ? s_hi[rank] : offs[r + 1];
+    if (b < a) b = a;
+    long long before = 0, total = 0;
+    for (int k = 0; k < world; k++) {
+      if (k == r) continue;
+      long long c = s_lo[k] > offs[r] ? s_lo[k] : offs[r], d = s_hi[k] < offs[r + 1] ? s_hi[k] : offs[r + 1];
+      const long long cnt = d > c ? d - c : 0;
+      if (k < rank) before += cnt;
+      total += cnt;
+    }
+    if (r != rank && s_do && total > sh->peer[r].ext_cap) { sh->overflow = 1; b = a; }   // r cannot park its incoming rows
+    sh->send_lo[r] = a; sh->send_hi[r] = b;
+    sh->ext_off[r] = before;
+  }
+  if (do_scan) {
+    __syncthreads();
+    superscan_block(nsuper, super_q, super_excl, plan, 0, 0, n_global, u0, overflow_count, 1, s_w);
+  }
+}
+__global__ void __launch_bounds__(1024) shard_plan_kernel(WeightStats *stats, const long long *__restrict__ offs, long long n_global, uint32_t u0,
+                                                          double ess_threshold, int do_scan, long long spill_cap, RunCtl *ctl,
+                                                          ResamplePlan *plan, ShardPlanDev *sh, long long nsuper,
+                                                          unsigned long long *__restrict__ super_q,
+                                                          unsigned long long *__restrict__ super_excl, unsigned int *overflow_count) {
+  pdl_trigger();
+  pdl_wait();
+  shard_plan_block(stats, offs, n_global, u0, ess_threshold, do_scan, spill_cap, ctl, plan, sh, nsuper, super_q, super_excl, overflow_count);
+}
+
 // the sweep plan computed in the tail of the statistics kernel (plan == nullptr: not fused)
 struct FusedPlan {
   ResamplePlan *plan;
@@ -509,6 +622,11 @@ struct FusedPlan {
   unsigned int *overflow_count;
   long long n_global;
   uint32_t u0;
+  // sharded filter (device-controlled run): the cross-shard plan instead of the local one
+  ShardPlanDev *sh;
+  const long long *offs;
+  long long spill_cap;
+  RunCtl *sh_ctl;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -760,7 +878,11 @@ __global__ void __launch_bounds__(kBlock, GB_WSTATS_MINB) wstats_kernel(const R 
     }
     *ticket = 0;
   }
-  if (fp.plan) {   // fused multi-step run: the super-tile scan + sweep plan ride on this CTA (one launch less per step)
+  if (fp.sh) {     // sharded device-controlled run: wait for the peers' records, ESS test, exchange plan, super-tile scan
+    __syncthreads();
+    shard_plan_block(stats, fp.offs, fp.n_global, fp.u0, NAN, 1, fp.spill_cap, fp.sh_ctl, fp.plan, fp.sh, nsuper, super_q, fp.super_excl,
+                     fp.overflow_count);
+  } else if (fp.plan) {   // fused multi-step run: the super-tile scan + sweep plan ride on this CTA (one launch less per step)
     __syncthreads();
     superscan_block(nsuper, super_q, fp.super_excl, fp.plan, 0, 0, fp.n_global, fp.u0, fp.overflow_count, 0, s_u64_33);
   }

@@ -235,9 +235,10 @@ int gb_pf_weight_sums_device(gb_pf_t *pf, int bits);
  *   once   : gb_pf_ipc_export -> exchange of the bundles (any transport) -> gb_pf_async_attach_ipc for every peer in
  *            another process / gb_pf_async_attach_local for peers in this process -> gb_pf_async_setup -> a barrier
  *            across all shards (the set-up resets the mailbox)
- *   per run: gb_pf_async_arm(threshold), then per step gb_pf_async_iterate(obs) = gb_pf_xchg_stats -> gb_pf_async_plan ->
- *            gb_pf_async_sweep -> gb_pf_async_export -> gb_pf_async_step (enqueues only; gb_pf_async_wait is a no-op kept
- *            for older drivers: the wait sits inside the step kernel)
+ *   per run: gb_pf_async_arm(threshold), then per step gb_pf_async_iterate(obs) = gb_pf_xchg_stats_plan (or gb_pf_xchg_stats ->
+ *            gb_pf_async_plan) -> gb_pf_async_sweep -> gb_pf_async_step: four kernels per shard and step, enqueues only.
+ *            (gb_pf_async_export / gb_pf_async_wait are no-ops kept for older drivers: the export rides in the sweep's second
+ *            kernel, the wait sits at the top of the step kernel.)
  *   finish : gb_pf_async_finish, one device->host read (log_ml_est, #resamples, overflow / time-out flags).  Overflow (a
  *            shard's extension rows or spill buffer too small for the weight skew) or a peer that did not answer within
  *            GENB200_XCHG_TIMEOUT_MS (default 20000) invalidates the run: GB_ESTATE.
@@ -253,6 +254,9 @@ int gb_pf_async_arm(gb_pf_t *pf, double ess_threshold);
 int gb_pf_async_cur(const gb_pf_t *pf, int *cur);
 int gb_pf_xchg_post(gb_pf_t *pf);    /* phase A only (no-op when the producing kernel already posted); implied by gb_pf_xchg_stats */
 int gb_pf_xchg_stats(gb_pf_t *pf);
+/* gb_pf_xchg_stats + gb_pf_async_plan(u0, NaN, 1) fused into one kernel (the plan rides in the statistics kernel's tail);
+ * only when no peer shard shares this shard's device */
+int gb_pf_xchg_stats_plan(gb_pf_t *pf, uint32_t u0);
 /* ess_threshold NaN: the armed one; do_scan != 0 when a sweep follows */
 int gb_pf_async_plan(gb_pf_t *pf, uint32_t u0, double ess_threshold, int do_scan);
 int gb_pf_async_sweep(gb_pf_t *pf);
