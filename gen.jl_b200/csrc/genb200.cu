@@ -12,6 +12,8 @@
 #include "kernels_small.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
@@ -84,7 +86,7 @@ struct gb_model {
   int nn[2] = {0, 0}, nu[2] = {0, 0};   // normal / uniform draws of the step [0] and generate [1] programs
   long long spec_id = 0;
 };
-static long long g_spec_next_id = 1;
+static std::atomic<long long> g_spec_next_id{1};
 static long long g_spec_loaded[64] = {0};   // per device: id of the program currently in the interpreter's constant memory
 static_assert((int)DIST_UNIFORM == (int)GB_DIST_UNIFORM && (int)DIST_EXPONENTIAL == (int)GB_DIST_EXPONENTIAL &&
               (int)DIST_LAPLACE == (int)GB_DIST_LAPLACE && (int)DIST_CAUCHY == (int)GB_DIST_CAUCHY &&
@@ -740,7 +742,10 @@ static int launch_spec(gb_pf *pf, const double *obs, int nobs, bool predrawn, in
   int spec_dev = 0;
   cudaGetDevice(&spec_dev);
   spec_dev = spec_dev >= 0 && spec_dev < 64 ? spec_dev : 0;
+  static std::mutex spec_mu;                          // (the interpreter's program lives in ONE __constant__ array per device)
+  std::lock_guard<std::mutex> spec_lk(spec_mu);
   if (g_spec_loaded[spec_dev] != m.spec_id) {
+    CK(cudaDeviceSynchronize());                      // another handle's kernels may still be reading the previous program
     CK(cudaMemcpyToSymbolAsync(c_spec_ops, m.ops.data(), m.ops.size() * sizeof(SpecOp), 0, cudaMemcpyHostToDevice, pf->stream));
     if (!m.spec_params.empty())
       CK(cudaMemcpyToSymbolAsync(c_spec_params, m.spec_params.data(), m.spec_params.size() * 8, 0, cudaMemcpyHostToDevice, pf->stream));
@@ -2532,7 +2537,8 @@ extern "C" int gb_logsumexp(const double *a, int64_t n, int dtype, double *lse_o
   if (rc) return rc;
   void *d = nullptr;
   const size_t esz = dtype == GB_F64 ? 8 : 4;
-  CK(gb_dev_alloc(&d, (size_t)n * esz));
+  // (the statistics pass loads whole 2048-element tiles and masks by index: the array is padded like the engine's own)
+  CK(gb_dev_alloc(&d, (size_t)ws->ld * esz));
   cudaError_t e;
   if (dtype == GB_F64) e = cudaMemcpy(d, a, (size_t)n * 8, cudaMemcpyHostToDevice);
   else {

@@ -89,13 +89,18 @@ __global__ void __launch_bounds__(kBlock) spec_kernel(const SpecArgs a) {
           n_unif++;
           if (op.code == OP_SAMPLE_DIST) regs[op.dst] = (R)random_invcdf((int)op.imm, (double)regs[op.a], (double)regs[op.b], (double)u);
           else if (op.code == OP_SAMPLE_BERNOULLI) regs[op.dst] = random_bernoulli<R>(regs[op.a], (R)u) ? R(1) : R(0);   // bernoulli.jl:19
-          else regs[op.dst] = (R)random_categorical<R>(c_spec_params + (int)regs[op.a], op.b, (R)u);                  // categorical.jl:20-22
+          else {                                                                                                     // categorical.jl:20-22
+            const int off = spec_table_offset((double)regs[op.a], op.b, kSpecMaxParams);
+            regs[op.dst] = off < 0 ? (R)NAN : (R)random_categorical<R>(c_spec_params + off, op.b, (R)u);
+          }
           break;
         }
         case OP_OBSERVE_BERNOULLI: w += logpdf_bernoulli<R>(regs[op.dst] != R(0), regs[op.a]); break;             // bernoulli.jl:10-12
         case OP_OBSERVE_CATEGORICAL: {                                                                            // categorical.jl:10-12
           const long long x = (long long)regs[op.dst];
-          w += (x > 0 && x <= op.b) ? Math<R>::log_((R)c_spec_params[(int)regs[op.a] + (int)x - 1]) : Math<R>::neg_inf();
+          const int off = spec_table_offset((double)regs[op.a], op.b, kSpecMaxParams);
+          if (off < 0) w += (R)NAN;
+          else w += (x > 0 && x <= op.b) ? Math<R>::log_((R)c_spec_params[off + (int)x - 1]) : Math<R>::neg_inf();
           break;
         }
         case OP_SAMPLE_GAMMA:                                                                                     // gamma.jl:29-31

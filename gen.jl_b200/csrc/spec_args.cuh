@@ -24,6 +24,13 @@ struct SpecArgs {
   double obs[kSpecMaxObs];            // this call's observations
 };
 
+// A categorical table's offset into the parameter block is a RUN-TIME register value: [off, off + len) must lie inside the
+// block (np entries), otherwise the choice is poisoned (NaN value / NaN weight) instead of reading out of bounds.
+GB_D int spec_table_offset(double v, int len, int np) {
+  const int o = (int)v;
+  return (v == v && o >= 0 && o + len <= np) ? o : -1;
+}
+
 constexpr int kSpecMaxMv = 8;
 // mvnormal.jl:30-33: mu + L * randn(k) with the Cholesky factor prepared at model creation
 template <typename R> GB_D void spec_mvnormal_sample(R *x, const R *mu, const double *__restrict__ Lf, const R *eps, int k) {

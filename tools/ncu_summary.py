@@ -23,6 +23,11 @@ for r in rows[2:]:
         if k in hdr:
             i = hdr.index(k)
             print("  %-75s %s %s" % (k, r[i][:30], units[i]))
+    # warp stall reasons (warps stalled per issue slot), largest first
+    pre, suf = "smsp__average_warps_issue_stalled_", "_per_issue_active.ratio"
+    st = sorted(((float(r[i]), hdr[i][len(pre):-len(suf)]) for i in range(len(hdr)) if hdr[i].startswith(pre) and r[i]), reverse=True)
+    if st:
+        print("  stalls (warps per issue-active cycle): " + ", ".join("%s %.2f" % (n, v) for v, n in st[:7]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 cur = None
 tally = {}
