@@ -10,6 +10,7 @@
 #include "kernels_spec.cuh"
 #include "kernels_mh.cuh"
 #include "kernels_small.cuh"
+#include "kernels_mid.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -321,6 +322,8 @@ struct gb_pf {
   long long ntiles = 0;
   uint64_t *tile_q = nullptr;
   unsigned long long *qbuf = nullptr;   // quantised weights of the last statistics pass (ld entries): what the sweeps scan
+  void *mid_ws = nullptr;               // persistent run (kernels_mid.cuh): per-CTA partials + the grid barrier counter
+  int mid_grid = 0;
   unsigned long long *super_q = nullptr, *super_excl = nullptr;
   long long nsuper = 0;
   OverflowEntry *oflow = nullptr;
@@ -428,7 +431,7 @@ static void pf_release(gb_pf *pf) {
   gb_dev_free(pf->parents64); gb_dev_free(pf->ext_parents); gb_dev_free(pf->partials); gb_dev_free(pf->ticket); gb_dev_free(pf->d_stats);
   gb_host_free(pf->h_stats); gb_dev_free(pf->d_normals); gb_dev_free(pf->d_uniforms); gb_dev_free(pf->d_u64);
   gb_dev_free(pf->d_ctl); gb_host_free(pf->h_ctl); gb_dev_free(pf->d_shplan); gb_host_free(pf->h_shplan); gb_dev_free(pf->d_offs); gb_dev_free(pf->super_q); gb_dev_free(pf->super_excl); gb_dev_free(pf->oflow); gb_dev_free(pf->oflow_count);
-  gb_dev_free(pf->tile_q); gb_dev_free(pf->qbuf); gb_dev_free(pf->d_plan);
+  gb_dev_free(pf->tile_q); gb_dev_free(pf->qbuf); gb_dev_free(pf->d_plan); gb_dev_free(pf->mid_ws);
   gb_dev_free(pf->lik); gb_dev_free(pf->guide); gb_dev_free(pf->tile_save);
   gb_host_free(pf->h_plan); gb_dev_free(pf->cdf); gb_dev_free(pf->off_anc); gb_dev_free(pf->d_tab); gb_dev_free(pf->d_ptab);
   for (auto p : pf->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -1525,6 +1528,10 @@ static int ensure_parents64(gb_pf *pf) {
   if (!pf->parents64) CK(gb_dev_alloc((void **)&pf->parents64, (size_t)pf->ld * 8));
   if (pf->parents64_valid) return GB_OK;
   if (pf->anc_valid) {
+    if (pf->xc_on && pf->a_world > 1) {   // sharded: ancestors / parent ids of imported slots arrive by peer stores (phase C)
+      LAUNCH(pf, GB_K_MISC, klaunch(xchg_wait_kernel, 1, kMaxWorld, pf->stream, pf->d_stats));
+      CK(cudaGetLastError());
+    }
     int grid = grid_for(pf, parents_from_anc_kernel, pf->n, kBlock);
     LAUNCH(pf, GB_K_MISC, parents_from_anc_kernel<<<grid, kBlock, 0, pf->stream>>>(pf->anc, pf->parents64, pf->n, pf->pid_offset,
                                                                                        pf->ext_used ? pf->n_pad : (long long)1 << 40, pf->ext_parents));
@@ -1780,6 +1787,101 @@ static int small_run(gb_pf *pf, int T, const double *obs, int nobs, int *n_resam
   return GB_OK;
 }
 
+// ---- mid-size particle counts: the whole T-step loop in one persistent co-resident kernel (kernels_mid.cuh) ----
+static long long mid_run_max_particles() {
+  static const long long v = [] { const char *e = getenv("GENB200_MID_RUN_MAX"); return e ? atoll(e) : 2000000ll; }();
+  return v;     // beyond this the working set leaves the L2 and the HBM-streaming kernels win (0 disables the path)
+}
+static bool mid_run_eligible(const gb_pf *pf, int T) {
+  const int k = pf->model.kind;
+  return T > 0 && pf->n > kSmallMax && pf->n <= mid_run_max_particles() && pf->n == pf->n_global && pf->pid_offset == 0 && !pf->history &&
+         (k == MODEL_LGSSM || k == MODEL_SV || k == MODEL_BEARINGS || k == MODEL_HMM);
+}
+static int mid_run(gb_pf *pf, int T, const double *obs, int nobs, int *n_resampled) {
+  MidRunArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = GB_OK;
+  for (int t = 0; t < T && !rc; t++)   // per-step argument checks (HMM: observation in 1..M), parameters from the last one
+    rc = fill_model_params(pf, a.mp, obs + (size_t)t * nobs, nobs, PROPOSAL_DEFAULT, nullptr, 0, false);
+  if (rc) return rc;
+  const void *kern = nullptr;
+  const bool f64 = pf->dtype == GB_F64;
+#define PICK(K, B) kern = f64 ? (const void *)mid_run_kernel<double, K, B> : (const void *)mid_run_kernel<float, K, B>
+  switch (pf->model.kind) {
+    case MODEL_LGSSM: PICK(MODEL_LGSSM, 4); break;
+    case MODEL_SV: PICK(MODEL_SV, 4); break;
+    case MODEL_BEARINGS: PICK(MODEL_BEARINGS, 3); break;
+    default: PICK(MODEL_HMM, 4); break;
+  }
+#undef PICK
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, 0));
+  REQ(occ >= 1, "gb_pf_run: the persistent kernel does not fit on an SM");
+  // co-resident grid, every SM equally full: the step phase deals the particles evenly over the CTAs, whatever the tile count
+  // (small filters: no more CTAs than eight per tile, a CTA needs a few hundred particles to be worth a barrier seat)
+  int grid = pf->num_sms * occ;
+  while (grid > pf->num_sms && (long long)grid > pf->ntiles * 8) grid -= pf->num_sms;
+  if (!pf->mid_ws || pf->mid_grid < grid) {
+    gb_dev_free(pf->mid_ws);
+    pf->mid_ws = nullptr;
+    CK(gb_dev_alloc(&pf->mid_ws, 256 + (size_t)grid * 8 + 256 + (size_t)grid * sizeof(MidPartial)));
+    pf->mid_grid = grid;
+  }
+  const size_t bar_bytes = (256 + (size_t)grid * 8 + 255) / 256 * 256;      // release word (own line) + arrival words
+  if (!pf->qbuf) CK(gb_dev_alloc((void **)&pf->qbuf, (size_t)pf->ntiles * kTile * 8));
+  double *d_obs = nullptr;
+  CK(gb_dev_alloc((void **)&d_obs, (size_t)T * nobs * 8));
+  cudaError_t e = cudaMemcpyAsync(d_obs, obs, (size_t)T * nobs * 8, cudaMemcpyHostToDevice, pf->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(pf->mid_ws, 0, bar_bytes, pf->stream);
+  a.obs = d_obs; a.T = T; a.nobs = nobs;
+  a.state[0] = pf->state[0]; a.state[1] = pf->state[1]; a.cur = pf->cur;
+  a.logw = pf->logw; a.incr = pf->incr; a.anc = pf->anc;
+  a.qbuf = pf->qbuf;
+  a.barrier.release = (unsigned long long *)pf->mid_ws;
+  a.barrier.arrive = (unsigned long long *)((char *)pf->mid_ws + 256);
+  a.part = (MidPartial *)((char *)pf->mid_ws + bar_bytes);
+  a.n = pf->n; a.ld = pf->ld; a.ntiles = pf->ntiles; a.seed = pf->seed; a.step = (unsigned)pf->step;
+  a.bits = quant_bits(pf->n_global);
+  a.ctl = pf->d_ctl; a.stats = pf->d_stats;
+  static const bool dbg = [] { const char *v = getenv("GENB200_MID_DEBUG"); return v && v[0] == '1'; }();
+  unsigned long long *d_dbg = nullptr;
+  if (dbg && e == cudaSuccess) {
+    e = gb_dev_alloc((void **)&d_dbg, (size_t)T * 64);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_dbg, 0, (size_t)T * 64, pf->stream);
+    a.dbg = d_dbg;
+  }
+  if (e == cudaSuccess) {
+    void *params[] = {(void *)&a};
+    LAUNCH(pf, GB_K_STEP, e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(kBlock), params, 0, pf->stream));
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pf->h_ctl, pf->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, pf->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(pf->stream);
+  if (d_dbg && e == cudaSuccess) {      // phase breakdown of CTA 0 (ns per step, averaged over the run)
+    std::vector<unsigned long long> h((size_t)T * 8);
+    e = cudaMemcpy(h.data(), d_dbg, (size_t)T * 64, cudaMemcpyDeviceToHost);
+    double ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < T; t++) {
+      for (int k = 0; k < 6; k++) ph[k] += (double)(h[(size_t)t * 8 + k + 1] - h[(size_t)t * 8 + k]);
+      ph[7] += (double)(h[(size_t)t * 8 + 7] - h[(size_t)t * 8 + 6]);
+      if (t + 1 < T) ph[6] += (double)(h[(size_t)(t + 1) * 8] - h[(size_t)t * 8 + 7]);
+    }
+    fprintf(stderr, "[genb200 persistent run] grid %d x %d, n %lld, T %d; ns/step: stats %.0f | barrier %.0f | ancestors %.0f | barrier %.0f | step %.0f | "
+                    "barrier %.0f | (bare barrier %.0f) | max fold %.0f\n", grid, kBlock, pf->n, T, ph[0] / T, ph[1] / T, ph[2] / T, ph[3] / T, ph[4] / T,
+            ph[5] / T, ph[7] / T, ph[6] / std::max(T - 1, 1));
+  }
+  gb_dev_free(d_dbg);
+  gb_dev_free(d_obs);
+  if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_pf_run (persistent path): ") + cudaGetErrorString(e));
+  pf->log_ml_est = pf->h_ctl->log_ml_est;
+  pf->step += T;
+  pf->cur ^= (T & 1);
+  pf->incr_step = pf->step;
+  if (pf->h_ctl->n_resampled > 0) { pf->anc_valid = true; pf->parents64_valid = false; pf->ext_used = false; }
+  pf->wstate = W_MAX; pf->tiles_valid = false; pf->pending_gather = false;
+  if (n_resampled) *n_resampled = pf->h_ctl->n_resampled;
+  return GB_OK;
+}
+
 // T x { maybe_resample!; particle_filter_step!; [sweeps x mh on the latest latents] } without a host round trip
 static int pf_run_impl(gb_pf *pf, int T, const double *obs, int nobs, double ess_threshold, int move, double drift_std, int sweeps,
                        int *n_resampled, int64_t *n_accepted) {
@@ -1804,6 +1906,7 @@ static int pf_run_impl(gb_pf *pf, int T, const double *obs, int nobs, double ess
   CK(cudaStreamSynchronize(pf->stream));                // h_ctl is reused for the read-back below
   pf->win_len = 0;                    // (the fused entries do not maintain the rejuvenation window)
   if (sweeps == 0 && small_run_eligible(pf, T)) return small_run(pf, T, obs, nobs, n_resampled);
+  if (sweeps == 0 && mid_run_eligible(pf, T)) return mid_run(pf, T, obs, nobs, n_resampled);
   if (sweeps > 0) {
     const int kind = pf->model.kind;
     REQ(move == MH_RESIMULATE || move == MH_DRIFT, "gb_pf_run_mh: unknown move");

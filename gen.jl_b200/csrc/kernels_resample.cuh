@@ -426,7 +426,8 @@ template <bool PREFIX>
 GB_D void tile_fill(const unsigned long long *__restrict__ qbuf, const SweepParams &sp, long long tile,
                     const uint64_t *__restrict__ tile_q, const unsigned long long *__restrict__ super_excl, uint64_t q_offset,
                     uint64_t cbase_in, long long slot0_in, long long lo_in, long long hi_in, const AncOut &ao,
-                    long long spill_base, TileSmem &sm, long long *slot0_out, long long *slot_end_out) {
+                    long long spill_base, TileSmem &sm, long long *slot0_out, long long *slot_end_out,
+                    uint64_t *total_out = nullptr) {
   // the quantised weights of the tile as the statistics pass left them (q = 0 beyond n): no second exp per particle
   uint64_t qv[kItems];
   {
@@ -439,12 +440,14 @@ GB_D void tile_fill(const unsigned long long *__restrict__ qbuf, const SweepPara
   }
   const double u0term = -(double)sp.u0 * 0x1p-32;
   if (PREFIX && threadIdx.x < 32) {
-    // CDF mass before this tile: super-tile prefix + the (<= 63) tile totals before it inside the super-tile
-    const long long sbase = (tile / kSuper) * kSuper;
-    uint64_t v = 0;
-    for (long long i = sbase + threadIdx.x; i < tile; i += 32) v += tile_q[i];
-    v = warp_sum_u64(v);
-    if (threadIdx.x == 0) sm.cbase = q_offset + super_excl[tile / kSuper] + v;
+    if (tile_q) {
+      // CDF mass before this tile: super-tile prefix + the (<= 63) tile totals before it inside the super-tile
+      const long long sbase = (tile / kSuper) * kSuper;
+      uint64_t v = 0;
+      for (long long i = sbase + threadIdx.x; i < tile; i += 32) v += tile_q[i];
+      v = warp_sum_u64(v);
+      if (threadIdx.x == 0) sm.cbase = q_offset + super_excl[tile / kSuper] + v;
+    } else if (threadIdx.x == 0) sm.cbase = cbase_in;     // (persistent run: the caller carries the prefix itself)
   }
   uint64_t c[kItems];
   uint64_t t = 0;
@@ -455,6 +458,7 @@ GB_D void tile_fill(const unsigned long long *__restrict__ qbuf, const SweepPara
   }
   uint64_t total;
   const uint64_t ex = block_exclusive_scan(t, sm.warp64, &total);   // two barriers: sm.cbase is visible after it
+  if (total_out) *total_out = total;
   const uint64_t cbase = PREFIX ? sm.cbase : cbase_in;
   // offspring end of every particle; rare exact fix-ups batched after the unrolled loop
   int kend[kItems];
@@ -700,7 +704,7 @@ __global__ void __launch_bounds__(kBlock) overflow_sys_kernel(const unsigned lon
   xc->export_ticket = 0;
   const unsigned long long seq = xc->seq_c + 1;
   xc->seq_c = seq;
-  for (int r = 0; r < xc->world; r++) st_release_sys(&xc->peer[r]->done_seq[xc->rank], seq);
+  for (int r = 0; r < xc->world; r++) st_relaxed_sys(&xc->peer[r]->done_seq[xc->rank], seq);
 }
 // phase C wait as a kernel of its own, for readers of the extension rows that are not step kernels (the eager gather)
 __global__ void __launch_bounds__(kMaxWorld) xchg_wait_kernel(WeightStats *stats) {

@@ -67,13 +67,25 @@ GB_D unsigned long long ld_acquire_sys(const unsigned long long *p) {
 GB_D void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// flag traffic of the exchange: ONE system-scope fence orders a shard's payload stores before its G flag stores, and one
+// after the spin orders the flag before the payload loads -- the flags themselves are relaxed accesses.  (A release store per
+// peer and an acquire load per probe put a system-scope fence on every one of them: G fences per post, one per probe.)
+GB_D void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+GB_D unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 // wait until *flag >= seq (flag lives in this shard's own memory; a peer writes it)
 GB_D void xchg_spin(const unsigned long long *flag, unsigned long long seq, XchgCtl *xc) {
   const long long t0 = clock64();
-  while (ld_acquire_sys(flag) < seq) {
+  while (ld_relaxed_sys(flag) < seq) {
     if (clock64() - t0 > xc->timeout_cycles) { xc->error = 1; break; }
-    __nanosleep(40);
+    __nanosleep(20);
   }
+  __threadfence_system();
 }
 // phase C wait, at the top of every kernel that reads a sharded filter's traces (call from all threads of the CTA, after
 // pdl_wait): the offspring rows its peers exported in the resample before this step have landed in this shard's extension
@@ -93,7 +105,7 @@ GB_D void xchg_post_max(XchgCtl *xc, double m) {
   const int slot = (int)(seq & 1), me = xc->rank;
   for (int r = 0; r < xc->world; r++) xc->peer[r]->mx[slot][me] = m;
   __threadfence_system();
-  for (int r = 0; r < xc->world; r++) st_release_sys(&xc->peer[r]->mx_seq[me], seq);
+  for (int r = 0; r < xc->world; r++) st_relaxed_sys(&xc->peer[r]->mx_seq[me], seq);
 }
 
 // Device-side control block of the fused multi-step entry (gb_pf_run): the ESS test of maybe_resample!
@@ -269,7 +281,11 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
   const MathTables T = stage_math_tables(s_tab);   // constants only: overlaps the predecessor's tail
   __syncthreads();
   pdl_wait();
-  if (!INIT && GATHER != 0) xchg_wait_done(a.stats);   // sharded filter: peers' offspring rows are in (no-op otherwise)
+  // sharded filter: peers' offspring rows are in (no-op otherwise).  (A lazy variant -- only the warps whose slots another
+  // shard's sweep produced wait, right before their first ancestor load -- hides nothing: the particles are dealt to the
+  // threads statically, so a warp that starts late finishes late by the same amount, and the extra live registers made the
+  // fp64 bearings instantiation spill: 2-GPU step kernel 0.756 -> 0.834 ms, profiles/README.md r2v.)
+  if (!INIT && GATHER != 0) xchg_wait_done(a.stats);
   const R *__restrict__ sin = static_cast<const R *>(a.state_in);
   R *__restrict__ sout = static_cast<R *>(a.state_out);
   R *__restrict__ logw = static_cast<R *>(a.logw);
@@ -866,7 +882,7 @@ __global__ void __launch_bounds__(kBlock, GB_WSTATS_MINB) wstats_kernel(const R 
         pm->s1[slot][me] = t1; pm->s2[slot][me] = t2; pm->q[slot][me] = qtot;
       }
       __threadfence_system();
-      for (int r = 0; r < xc->world; r++) st_release_sys(&xc->peer[r]->rec_seq[me], seq);
+      for (int r = 0; r < xc->world; r++) st_relaxed_sys(&xc->peer[r]->rec_seq[me], seq);
     }
     if (ctl) {   // maybe_resample! decision + log-ML update on the device (particle_filter.jl:256, :263)
       const int flag = stats->ess < ctl->ess_threshold ? 1 : 0;

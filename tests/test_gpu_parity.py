@@ -1030,6 +1030,60 @@ def test_single_cta_run_equals_api_loop(g, O, name, dtype, n):
     assert np.array_equal(a.get_state(0), b.get_state(0)) and np.array_equal(a.parents, b.parents)
 
 
+@pytest.mark.parametrize("name", ["lgssm", "sv", "bearings", "hmm"])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("n", [4097, 70001, 1000000])
+def test_persistent_run_equals_api_loop(g, O, name, dtype, n):
+    """4096 < N <= 2e6: gb_pf_run executes the whole loop in one persistent co-resident kernel with grid barriers between
+    the phases (kernels_mid.cuh).  Same per-particle arithmetic as the multi-kernel path: states, ancestors and log weights
+    are bit-identical to the API loop; lse / ESS are reduced in a different order, so log_ml_est agrees to rounding."""
+    if n == 1000000 and name not in ("sv", "bearings"):
+        pytest.skip("full-size case kept for the config-2 model and the 4-D one")
+    model, _, _, ys, _, _ = model_zoo(g, O)[name]
+    thr = n / 2 if name != "hmm" else n + 1
+    a = g.initialize_particle_filter(model, (0,), ys[0], n, dtype=dtype, seed=13)
+    b = g.initialize_particle_filter(model, (0,), ys[0], n, dtype=dtype, seed=13)
+    nres_a = 0
+    for t in range(1, len(ys)):
+        nres_a += g.maybe_resample_(a, ess_threshold=thr, resampler="systematic")
+        g.particle_filter_step_(a, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+    nres_b = g.particle_filter_run_(b, ys[1:], ess_threshold=thr)
+    assert nres_a == nres_b and nres_b >= 1
+    for f in range(model.state_dim):
+        assert np.array_equal(a.get_state(f), b.get_state(f))
+    assert np.array_equal(a.parents, b.parents) and np.array_equal(a.log_weights, b.log_weights)
+    assert np.array_equal(a.log_incremental_weights, b.log_incremental_weights)
+    tol = 1e-12 if dtype == "f64" else 1e-6
+    assert abs(a.log_ml_est - b.log_ml_est) <= tol * max(1.0, abs(a.log_ml_est))
+    assert abs(g.log_ml_estimate(a) - g.log_ml_estimate(b)) <= tol * max(1.0, abs(g.log_ml_estimate(a)))
+    # and the filter carries on through the ordinary entries afterwards
+    for st in (a, b):
+        g.maybe_resample_(st, ess_threshold=n + 0.5, resampler="systematic")
+        g.particle_filter_step_(st, (len(ys),), (g.UnknownChange,), ys[-1], return_incr=False)
+    assert np.array_equal(a.get_state(0), b.get_state(0)) and np.array_equal(a.parents, b.parents)
+    # a second run on the same handle (workspace reuse, barrier counter reset)
+    assert g.particle_filter_run_(a, ys[1:4], ess_threshold=thr) == g.particle_filter_run_(b, ys[1:4], ess_threshold=thr)
+    assert np.array_equal(a.get_state(0), b.get_state(0)) and np.array_equal(a.log_weights, b.log_weights)
+
+
+def test_persistent_run_degenerate_weights(g):
+    """One particle owns (almost) every offspring: a tile that fills many slot windows, in the persistent kernel."""
+    n = 300000
+    model = g.lgssm_model(**F.LGSSM)
+    a = g.initialize_particle_filter(model, (0,), 0.3, n, seed=2)
+    lw = np.full(n, -80.0)
+    lw[77777] = 0.0
+    lw[5] = -1.0
+    a.log_weights = lw
+    b = a.copy()
+    assert g.maybe_resample_(a, ess_threshold=n / 2, resampler="systematic")
+    g.particle_filter_step_(a, (1,), (g.UnknownChange,), 0.1, return_incr=False)
+    assert g.particle_filter_run_(b, [0.1], ess_threshold=n / 2) == 1
+    assert np.array_equal(a.parents, b.parents) and np.array_equal(a.get_state(0), b.get_state(0))
+    cnt = np.bincount(b.parents - 1, minlength=n)
+    assert cnt[77777] > 0.7 * n and cnt.sum() == n
+
+
 def test_single_cta_run_degenerate_weights(g):
     """One particle owns (almost) every offspring: the CTA-cooperative fill of heavy particles."""
     n = 2048
