@@ -526,12 +526,16 @@ def run_genb200(args):
     step_name = L.lib().gb_kernel_name(L.K_STEP).decode()
     k_ms, k_launches = timing[step_name]
     avg_ms = k_ms / max(1, k_launches)
-    # bytes the fused step kernel has to move per particle: ancestor index + gathered row in, new row + log weight + log
-    # incremental weight out = 4 + 2 S E + 2 E (84 for S = 4, fp64).  This is what `frac` is a fraction OF.
-    fused_bytes = (4 + 2 * S * E + 2 * E) * n_local
+    # bytes the fused step kernel has to move per particle: ancestor index + gathered row in, new row + log weight out
+    # = 4 + 2 S E + E (76 for S = 4, fp64).  After a resample the log weights restart from exactly 0.0, so the step's log
+    # incremental weights ARE its new log weights: they are stored once and gb_pf_get_log_increments reads that column (up
+    # to r2t the kernel wrote both, 84 B).  This is what `frac` is a fraction OF.
+    fused_bytes = (4 + 2 * S * E + E) * n_local
     achieved = fused_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     b_step = algorithmic_bytes_per_particle_step(S, E)                    # SURVEY.md 8d accounting of the UNFUSED API calls: 176
-    b_necessary = (4 + 2 * S * E + 2 * E) + E + (E + 4)                    # fused step + statistics read + ancestors read/write: 104
+    # fused step (76) + statistics: log weights in, quantised weights out (2 E) + ancestors: quantised weights in, indices out
+    # (E + 4): 104 for S = 4, fp64
+    b_necessary = (4 + 2 * S * E + E) + 2 * E + (E + 4)
     kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in timing.items() if v[1]}
     launches = int(sum(v[1] for v in timing.values()))
     tr = ncu_traffic(args.dtype, S)
@@ -586,13 +590,15 @@ def run_genb200(args):
                      "bytes_per_launch": fused_bytes, "bytes_per_particle": fused_bytes / n_local, "avg_launch_ms": avg_ms,
                      "traffic": None if tr is None else tr["dram_bytes_per_particle"] * n_local,
                      "traffic_source": None if tr is None else {k: tr[k] for k in ("file", "kernel", "particles", "dram_bytes_per_particle")},
-                     "note": "bytes = what the FUSED kernel must move per particle (ancestor index + gathered row in; row, log weight, "
-                             "log incremental weight out); frac = bytes / measured time / measured copy peak",
+                     "note": "bytes = what the FUSED kernel must move per particle (ancestor index + gathered row in; row + log weight "
+                             "out; the log incremental weights equal the new log weights after a resample and share their column); "
+                             "frac = bytes / measured time / measured copy peak",
                      "whole_step": {"algorithmic": dict(whole(b_step), note="SURVEY.md 8d accounting of the unfused API calls "
                                                                            "(step! + maybe_resample! with a materialised gather): the deferred-gather fusion removes a "
                                                                            "write + read of the state, so this can exceed 1"),
-                                    "necessary": dict(whole(b_necessary), note="bytes the fused pipeline really has to move: step kernel "
-                                                                             "+ one statistics read + ancestors read/write")}},
+                                    "necessary": dict(whole(b_necessary), note="bytes the fused pipeline really moves: step kernel + "
+                                                                             "statistics pass (log weights in, quantised weights out) + "
+                                                                             "ancestors pass (quantised weights in, indices out)")}},
         "kernels": kernels,
         "cpu_baseline": cpu,
         "sharded_parity": parity,

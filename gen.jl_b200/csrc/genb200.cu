@@ -281,6 +281,8 @@ struct gb_pf {
   void *lik = nullptr;            // GB_MODEL_SPEC rejuvenation: score of every particle's constrained choices (kernels_mh.cuh)
   int lik_step = -1;              // step index `lik` belongs to
   int incr_step = -1;             // step index whose log incremental weights `incr` holds
+  int incr_where = 0;             // ... and where they are: 0 = `incr`; 1 = `logw` (gathered step: logw was reset to 0, so logw == incr);
+                                  // 2 = ask the device (d_stats->incr_in_logw: the step's gather decision was taken there)
   int spec_backend = -1;          // GB_MODEL_SPEC: 1 = NVRTC-specialised kernel, 0 = interpreter (last launch)      // rejuvenation sweeps applied since the last step (Philox draw-index block)
   long long *parents64 = nullptr; // global 1-based parents (sharded path)
   bool parents64_valid = false;
@@ -807,6 +809,7 @@ static int launch_model(gb_pf *pf, const double *obs, int nobs, int pk, const do
   if (pf->model.kind == MODEL_SPEC) {
     REQ(pk == PROPOSAL_DEFAULT, "SPEC models carry their proposal inside the program (default proposal only)");
     REQ(init || pf->model.n_step_ops > 0, "this SPEC model has no step program");
+    if (!init) pf->incr_where = 0;      // (the SPEC kernels always store the increments in their own column)
     if (pf->dtype == GB_F64) return init ? launch_spec<double, true>(pf, obs, nobs, predrawn, 0) : launch_spec<double, false>(pf, obs, nobs, predrawn, gather);
     return init ? launch_spec<float, true>(pf, obs, nobs, predrawn, 0) : launch_spec<float, false>(pf, obs, nobs, predrawn, gather);
   }
@@ -823,7 +826,10 @@ static int launch_model(gb_pf *pf, const double *obs, int nobs, int pk, const do
   a.seed = pf->seed; a.step = init ? 0u : (unsigned)(pf->step + 1);
   a.partials = (double *)pf->partials; a.ticket = pf->ticket; a.stats = pf->d_stats;
   if (init) return pf->dtype == GB_F64 ? launch_step_k<double, true>(pf, a, pk, predrawn, 0) : launch_step_k<float, true>(pf, a, pk, predrawn, 0);
-  return pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, pk, predrawn, gather) : launch_step_k<float, false>(pf, a, pk, predrawn, gather);
+  a.share_incr = 1;
+  rc = pf->dtype == GB_F64 ? launch_step_k<double, false>(pf, a, pk, predrawn, gather) : launch_step_k<float, false>(pf, a, pk, predrawn, gather);
+  if (!rc) pf->incr_where = gather;      // 0: own column; 1: shared with logw; 2: decided on the device (d_stats->incr_in_logw)
+  return rc;
 }
 
 // snapshot of the current trace columns (+ the ancestors that were applied on the way into this step)
@@ -971,6 +977,27 @@ extern "C" int gb_pf_initialize(const gb_model_t *m, int64_t n, int dtype, uint6
 }
 
 static int copy_out(gb_pf *pf, const void *dsrc, double *out, long long n);
+// where the log incremental weights of the last step live (see gb_pf::incr_where)
+static int incr_source(gb_pf *pf, const void **src) {
+  if (pf->incr_where == 2) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, &pf->d_stats->incr_in_logw, sizeof(int), cudaMemcpyDeviceToHost, pf->stream));
+    CK(cudaStreamSynchronize(pf->stream));
+    pf->incr_where = flag ? 1 : 0;
+  }
+  *src = pf->incr_where == 1 ? pf->logw : pf->incr;
+  return GB_OK;
+}
+// call before anything other than a step overwrites logw: the shared copy moves to its own column
+static int unshare_incr(gb_pf *pf) {
+  if (pf->incr_where == 0 || pf->step < 1 || pf->incr_step != pf->step) { pf->incr_where = 0; return GB_OK; }
+  const void *src = nullptr;
+  int rc = incr_source(pf, &src);
+  if (rc) return rc;
+  if (src != pf->incr) CK(cudaMemcpyAsync(pf->incr, pf->logw, (size_t)pf->ld * pf->esz, cudaMemcpyDeviceToDevice, pf->stream));
+  pf->incr_where = 0;
+  return GB_OK;
+}
 extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, const double *pargs, int npargs,
                           double *incr_out) {
   REQ(pf, "null handle");
@@ -994,7 +1021,11 @@ extern "C" int gb_pf_step(gb_pf_t *pf, const double *obs, int nobs, int pk, cons
   pf->incr_step = pf->step;
   if (pf->history && (rc = history_record(pf, pf->hist_resampled))) return rc;
   pf->hist_resampled = false;
-  if (incr_out) return copy_out(pf, pf->incr, incr_out, pf->n);   // staged: pinned chunks + host fan-out (the caller's pages are pageable)
+  if (incr_out) {
+    const void *src = nullptr;
+    if ((rc = incr_source(pf, &src))) return rc;
+    return copy_out(pf, src, incr_out, pf->n);   // staged: pinned chunks + host fan-out (the caller's pages are pageable)
+  }
   return GB_OK;
 }
 
@@ -1051,7 +1082,9 @@ static int spec_rejuvenate(gb_pf *pf, int move, const double *obs, int nobs, int
   if (!pf->lik) CK(gb_dev_alloc(&pf->lik, (size_t)pf->ld * pf->esz));
   if (pf->lik_step != pf->step) {   // scores of the current traces = what the last generate / step added to the weights
     if (!init && pf->incr_step != pf->step) return fail(GB_ESTATE, "gb_pf_rejuvenate: the step's log incremental weights are gone");
-    CK(cudaMemcpyAsync(pf->lik, init ? pf->logw : pf->incr, (size_t)pf->n * pf->esz, cudaMemcpyDeviceToDevice, pf->stream));
+    const void *isrc = pf->logw;
+    if (!init) { const int irc = incr_source(pf, &isrc); if (irc) return irc; }
+    CK(cudaMemcpyAsync(pf->lik, isrc, (size_t)pf->n * pf->esz, cudaMemcpyDeviceToDevice, pf->stream));
     pf->lik_step = pf->step;
   }
   MhArgs a;
@@ -1238,8 +1271,10 @@ extern "C" int gb_pf_rejuvenate_window(gb_pf_t *pf, int a, int b, const double *
 // ------------------------------------------------------------------------------------------
 static int run_gather(gb_pf *pf);
 static int materialize_pending(gb_pf *pf) { return run_gather(pf); }
+static int unshare_incr(gb_pf *pf);
 static int run_gather(gb_pf *pf) {   // materialise a deferred resample gather
   if (!pf->pending_gather) return GB_OK;
+  { const int urc = unshare_incr(pf); if (urc) return urc; }     // (the gather kernel resets logw to 0)
   if (pf->xc_on && pf->a_world > 1) {   // sharded: the peers' offspring rows must have landed before they are read
     LAUNCH(pf, GB_K_MISC, klaunch(xchg_wait_kernel, 1, kMaxWorld, pf->stream, pf->d_stats));
     CK(cudaGetLastError());
@@ -1497,12 +1532,16 @@ extern "C" int gb_pf_get_log_increments(gb_pf_t *pf, double *out) {
   REQ(pf && out, "null argument");
   if (pf->step < 1 || pf->incr_step != pf->step)
     return fail(GB_ESTATE, "gb_pf_get_log_increments: no particle_filter_step has produced increments for the current step");
-  return copy_out(pf, pf->incr, out, pf->n);
+  const void *src = nullptr;
+  int rc = incr_source(pf, &src);
+  if (rc) return rc;
+  return copy_out(pf, src, out, pf->n);
 }
 extern "C" int gb_pf_set_log_weights(gb_pf_t *pf, const double *in) {
   REQ(pf && in, "null argument");
   int rc = materialize(pf);
   if (rc) return rc;
+  if ((rc = unshare_incr(pf))) return rc;
   if (pf->dtype == GB_F64) {
     CK(cudaMemcpyAsync(pf->logw, in, (size_t)pf->n * 8, cudaMemcpyHostToDevice, pf->stream));
   } else {
@@ -1554,6 +1593,7 @@ extern "C" int gb_pf_clone(gb_pf_t *pf, gb_pf_t **out) {
   REQ(pf && out, "null argument");
   int rc = materialize(pf);
   if (rc) return rc;
+  if ((rc = unshare_incr(pf))) return rc;
   rc = ensure_stats(pf);
   if (rc) return rc;
   if ((rc = ensure_parents64(pf))) return rc;
@@ -1781,6 +1821,7 @@ static int small_run(gb_pf *pf, int T, const double *obs, int nobs, int *n_resam
   pf->step += T;
   pf->cur ^= (T & 1);
   pf->incr_step = pf->step;
+  pf->incr_where = 0;
   if (pf->h_ctl->n_resampled > 0) { pf->anc_valid = true; pf->parents64_valid = false; pf->ext_used = false; }
   pf->wstate = W_MAX; pf->tiles_valid = false; pf->pending_gather = false;
   if (n_resampled) *n_resampled = pf->h_ctl->n_resampled;
@@ -1789,8 +1830,8 @@ static int small_run(gb_pf *pf, int T, const double *obs, int nobs, int *n_resam
 
 // ---- mid-size particle counts: the whole T-step loop in one persistent co-resident kernel (kernels_mid.cuh) ----
 static long long mid_run_max_particles() {
-  static const long long v = [] { const char *e = getenv("GENB200_MID_RUN_MAX"); return e ? atoll(e) : 2000000ll; }();
-  return v;     // beyond this the working set leaves the L2 and the HBM-streaming kernels win (0 disables the path)
+  const char *e = getenv("GENB200_MID_RUN_MAX");      // (read per call: the tests pin either path)
+  return e ? atoll(e) : 2000000ll;     // beyond this the HBM-streaming kernels win: N = 2e6 55 vs 59 us/step, 4e6 101 vs 102 (fp32 88 vs 84)
 }
 static bool mid_run_eligible(const gb_pf *pf, int T) {
   const int k = pf->model.kind;
@@ -1876,6 +1917,7 @@ static int mid_run(gb_pf *pf, int T, const double *obs, int nobs, int *n_resampl
   pf->step += T;
   pf->cur ^= (T & 1);
   pf->incr_step = pf->step;
+  pf->incr_where = 0;
   if (pf->h_ctl->n_resampled > 0) { pf->anc_valid = true; pf->parents64_valid = false; pf->ext_used = false; }
   pf->wstate = W_MAX; pf->tiles_valid = false; pf->pending_gather = false;
   if (n_resampled) *n_resampled = pf->h_ctl->n_resampled;
@@ -2446,6 +2488,7 @@ extern "C" int gb_pf_import_rows(gb_pf_t *pf, int64_t dst_lo, int64_t count, con
 extern "C" int gb_pf_commit_resample(gb_pf_t *pf, double log_ml_increment) {
   if (pf) pf->mh_ok = false;
   REQ(pf, "null handle");
+  { const int urc = unshare_incr(pf); if (urc) return urc; }     // (logw is zeroed below)
   pf->cur ^= 1;
   pf->log_ml_est += log_ml_increment;
   pf->wstate = W_ZERO;

@@ -25,6 +25,7 @@ struct WeightStats {
   double lse, ess;    // m + log s1 ; s1^2 / s2
   unsigned long long q_total;   // sum of the quantised weights (wstats)
   XchgCtl *xc;        // sharded filters: the peer-memory exchange below (nullptr: single shard).  NOT part of the record.
+  int incr_in_logw;   // device-decided steps (GATHER == 2): 1 = the last step kernel left its log incremental weights in logw
 };
 constexpr int kStatsRecordBytes = 48;   // {m, s1, s2, lse, ess, q_total}: what is copied to the host / to a clone
 
@@ -199,6 +200,10 @@ struct StepArgs {
   double *partials;       // one running max per CTA
   unsigned int *ticket;
   WeightStats *stats;     // stats->m receives the max of the new log weights
+  // After a resample the log weights are reset to exactly 0.0 (particle_filter.jl:266), so the step's new log weights ARE its
+  // log incremental weights (0.0 + w == w): with share_incr the gathered step stores them once (logw) and the host reads
+  // gb_pf_get_log_increments from there -- 8 of the kernel's 84 bytes per particle.
+  int share_incr;
   ModelParams mp;
 };
 
@@ -413,8 +418,9 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
 #pragma unroll
     for (int s = 0; s < S; s++) svstore<R, V>(sout + (long long)s * a.ld + i0, next[s]);
     svstore_keep<R, V>(logw + i0, lw_new);
-    if (!INIT) svstore<R, V>(incr + i0, w);
+    if (!INIT && !(gather && a.share_incr)) svstore<R, V>(incr + i0, w);
   }
+  if (!INIT && GATHER == 2 && blockIdx.x == 0 && threadIdx.x == 0) a.stats->incr_in_logw = (gather && a.share_incr) ? 1 : 0;
   publish_max(acc, a.partials, a.ticket, a.stats);
 }
 

@@ -669,9 +669,11 @@ def test_determinism(g):
 
 @pytest.mark.parametrize("name", ["lgssm", "sv", "bearings", "hmm"])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_fused_multi_step_run_equals_api_loop(g, O, name, dtype):
+def test_fused_multi_step_run_equals_api_loop(g, O, name, dtype, monkeypatch):
     """gb_pf_run (device-side ESS test / log-ML / gather choice, no host round trip per step) is bit-identical
-    to calling maybe_resample! + particle_filter_step! T times."""
+    to calling maybe_resample! + particle_filter_step! T times.  (The multi-kernel form of the run, which is what filters
+    beyond 2e6 particles get: the persistent kernel of test_persistent_run_equals_api_loop is switched off.)"""
+    monkeypatch.setenv("GENB200_MID_RUN_MAX", "0")
     model, _, _, ys, _, _ = model_zoo(g, O)[name]
     n, seed = 70001, 12
     for thr in (n / 2, n + 1, 0.0):            # ESS-triggered, always, never
@@ -1028,6 +1030,43 @@ def test_single_cta_run_equals_api_loop(g, O, name, dtype, n):
         g.maybe_resample_(st, ess_threshold=n + 0.5, resampler="systematic")
         g.particle_filter_step_(st, (len(ys),), (g.UnknownChange,), ys[-1], return_incr=False)
     assert np.array_equal(a.get_state(0), b.get_state(0)) and np.array_equal(a.parents, b.parents)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("lazy", [True, False])
+def test_log_increments_share_the_log_weight_column(g, O, dtype, lazy):
+    """After a resample the log weights restart from exactly 0.0 (particle_filter.jl:266), so the step that follows stores its
+    log incremental weights only once, in the log-weight column.  What particle_filter_step! returns / gb_pf_get_log_increments
+    reads must not notice: compared with the oracle, and kept intact when the log weights are overwritten afterwards."""
+    model, omodel, _, ys, _, _ = model_zoo(g, O)["bearings"]
+    n = 5003
+    a = g.initialize_particle_filter(model, (0,), ys[0], n, dtype=dtype, seed=7)
+    a.set_lazy_gather(lazy)
+    ref = g.initialize_particle_filter(model, (0,), ys[0], n, dtype=dtype, seed=7)
+    ref.set_lazy_gather(lazy)
+    for t in range(1, 7):
+        resample = t in (2, 3, 5)
+        for st in (a, ref):
+            did = g.maybe_resample_(st, ess_threshold=(n + 1) if resample else 0.0, resampler="systematic")
+            assert did == resample
+        inc_ref, = g.particle_filter_step_(ref, (t,), (g.UnknownChange,), ys[t], return_incr=True)     # copied out at once
+        g.particle_filter_step_(a, (t,), (g.UnknownChange,), ys[t], return_incr=False)                   # read later
+        lw = a.log_weights
+        assert np.array_equal(a.log_incremental_weights, inc_ref)
+        if resample:
+            assert np.array_equal(lw, inc_ref)                     # 0.0 + w == w
+        if t == 3:      # overwriting the log weights must not disturb the increments that shared their column
+            a.log_weights = lw - 1.0
+            assert np.array_equal(a.log_incremental_weights, inc_ref)
+            a.log_weights = lw
+        if t == 5:      # neither must a copy, nor the resample that follows
+            b = a.copy()
+            assert np.array_equal(b.log_incremental_weights, inc_ref)
+            assert g.maybe_resample_(b, ess_threshold=n + 1, resampler="systematic")
+            assert np.array_equal(b.log_incremental_weights, inc_ref)
+            b.get_state(0)                                          # materialises the gather (resets the log weights)
+            assert np.array_equal(b.log_incremental_weights, inc_ref)
+    assert np.array_equal(a.log_weights, ref.log_weights)
 
 
 @pytest.mark.parametrize("name", ["lgssm", "sv", "bearings", "hmm"])
