@@ -57,6 +57,29 @@ GB_D uint64_t block_exclusive_scan(uint64_t v, uint64_t *s_warp /* kBlock/32 + 1
   return s_warp[warp] + (inc - v);
 }
 
+// the same with ONE barrier: every thread folds the kBlock/32 warp totals itself (broadcast shared-memory reads).  The
+// caller must not reuse s_warp before its next barrier.
+GB_D uint64_t block_exclusive_scan_1b(uint64_t v, uint64_t *s_warp /* kBlock/32 */, uint64_t *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t o = shfl_up_u64(inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint64_t base = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < kBlock / 32; k++) {
+    const uint64_t w = s_warp[k];
+    base += k < warp ? w : 0;
+    tot += w;
+  }
+  *total = tot;
+  return base + (inc - v);
+}
+
 // ---- inclusive integer CDF, materialised (multinomial draws, sample_unweighted_traces) ----
 // tilescan_cdf : one CTA of 1024 threads turns the per-tile totals (wstats) into exclusive tile prefixes (ntiles + 1 entries)
 // cdf_kernel   : one CTA per tile: block scan of the quantised weights on top of the tile prefix -> cdf_out[i]
@@ -348,6 +371,7 @@ struct AncOut {
 
 constexpr int kBlk = 8;                             // output slots per fill block: two 128-bit stores per thread
 constexpr int kEndSlots = kChunk + 2 * kBlk;        // histogram entries of one window (+ alignment slack)
+constexpr int kEndWords = ((kEndSlots / 2 + kEndSlots / 8) + 3) / 4 * 4;   // two 16-bit entries per word + one padding word per four
 
 // number of slots below CDF value C: double-precision estimate, exact only when the estimate is within
 // 2^-17 slots of a boundary; `slow` is set instead of branching so callers can batch the rare fix-ups
@@ -363,26 +387,43 @@ GB_D int slots_estimate(uint64_t C, double ratio, double u0term, bool &slow) {
 // Shared-memory scratch of one ancestors CTA
 struct TileSmem {
   uint64_t warp64[kBlock / 32 + 1];
-  // ends[ends_index(x)] = number of particles whose offspring range ends at window slot x - sh.  One padding word per 8
-  // entries: consecutive lanes add at positions ~8 apart (one offspring per particle on average), which would be an 8-way
-  // bank conflict on every reduction in a dense array; with the padding they -- and the block-wise reads, stride 9 -- spread
-  // over all 32 banks.
-  __align__(16) int ends[kEndSlots + kEndSlots / 8];
+  // Histogram of the window: the number of particles whose offspring range ends at window slot x - sh, as a 16-bit count
+  // (a tile has 2048 particles) -- two slots per word, so the window of kChunk slots costs 20 KB instead of 37 KB of shared
+  // memory and a fifth CTA fits on the SM (the kernel is bound by the latency of its load -> scan -> histogram -> scan ->
+  // store chain, i.e. by the number of tiles in flight).  One padding word per 4 words: consecutive lanes add at positions
+  // ~8 slots = 4 words apart, which would be an 8-way bank conflict in a dense array; with the padding they -- and the
+  // block-wise reads, stride 5 words -- spread over all 32 banks.
+  __align__(16) unsigned int ends[kEndWords];
   int warp32[kBlock / 32 + 1];
   uint64_t cbase;
-  long long slot0, slot_end;
 };
-GB_D int ends_index(int x) { return x + (x >> 3); }
+GB_D void ends_add(TileSmem &sm, int x) {
+  const int w = x >> 1;
+  atomicAdd(&sm.ends[w + (w >> 2)], 1u << ((x & 1) * 16));
+}
 GB_D void tile_smem_clear(TileSmem &sm) {   // the histogram must be all zero on entry of tile_fill
-  int4 *z = reinterpret_cast<int4 *>(sm.ends);
-  for (int i = threadIdx.x; i < (kEndSlots + kEndSlots / 8) / 4; i += kBlock) z[i] = make_int4(0, 0, 0, 0);
+  uint4 *z = reinterpret_cast<uint4 *>(sm.ends);
+  for (int i = threadIdx.x; i < kEndWords / 4; i += kBlock) z[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
 }
 // the 8 counts of fill block B (read and cleared)
 GB_D void ends_take(TileSmem &sm, int B, int (&v)[kBlk]) {
-  int *p = sm.ends + 9 * B;
+  unsigned int *p = sm.ends + 5 * B;
 #pragma unroll
-  for (int e = 0; e < kBlk; e++) { v[e] = p[e]; p[e] = 0; }
+  for (int e = 0; e < kBlk / 2; e++) {
+    const unsigned int w = p[e];
+    p[e] = 0u;
+    v[2 * e] = (int)(w & 0xffffu);
+    v[2 * e + 1] = (int)(w >> 16);
+  }
+}
+// their sum (not cleared)
+GB_D int ends_sum(const TileSmem &sm, int B) {
+  const unsigned int *p = sm.ends + 5 * B;
+  int t = 0;
+#pragma unroll
+  for (int e = 0; e < kBlk / 2; e++) t += (int)(p[e] & 0xffffu) + (int)(p[e] >> 16);
+  return t;
 }
 // exclusive block scan of one int per thread
 GB_D int block_exclusive_scan_i32(int v, int *s_warp /* kBlock/32 + 1 */) {
@@ -407,6 +448,22 @@ GB_D int block_exclusive_scan_i32(int v, int *s_warp /* kBlock/32 + 1 */) {
   }
   __syncthreads();
   return s_warp[warp] + (inc - v);
+}
+
+GB_D int block_exclusive_scan_i32_1b(int v, int *s_warp /* kBlock/32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  int base = 0;
+#pragma unroll
+  for (int k = 0; k < kBlock / 32; k++) base += k < warp ? s_warp[k] : 0;
+  return base + (inc - v);
 }
 
 // Scan one tile and fill the ancestors of the output slots [lo, hi) (hi - lo <= kChunk) that belong to it.
@@ -457,7 +514,7 @@ GB_D void tile_fill(const unsigned long long *__restrict__ qbuf, const SweepPara
     c[j] = t;
   }
   uint64_t total;
-  const uint64_t ex = block_exclusive_scan(t, sm.warp64, &total);   // two barriers: sm.cbase is visible after it
+  const uint64_t ex = block_exclusive_scan_1b(t, sm.warp64, &total);   // one barrier: sm.cbase is visible after it
   if (total_out) *total_out = total;
   const uint64_t cbase = PREFIX ? sm.cbase : cbase_in;
   // offspring end of every particle; rare exact fix-ups batched after the unrolled loop
@@ -474,16 +531,20 @@ GB_D void tile_fill(const unsigned long long *__restrict__ qbuf, const SweepPara
     for (int j = 0; j < kItems; j++)
       if (slow & (1u << j)) kend[j] = (int)slots_below(cbase + ex + c[j], sp);
   }
-  if (threadIdx.x == kBlock - 1) sm.slot_end = kend[kItems - 1];
-  if (PREFIX && threadIdx.x == 0) {
+  // the tile's slot range, by every thread itself (same inputs, same bits as the last particle's end / the first one's
+  // start): saves a shared-memory exchange and its barrier
+  long long slot0 = slot0_in, slot_end;
+  {
     bool sl;
-    int s0 = slots_estimate(cbase, sp.ratio, u0term, sl);
-    if (sl) s0 = (int)slots_below(cbase, sp);
-    sm.slot0 = s0;
+    int se = slots_estimate(cbase + total, sp.ratio, u0term, sl);
+    if (sl) se = (int)slots_below(cbase + total, sp);
+    slot_end = se;
+    if (PREFIX) {
+      int s0 = slots_estimate(cbase, sp.ratio, u0term, sl);
+      if (sl) s0 = (int)slots_below(cbase, sp);
+      slot0 = s0;
+    }
   }
-  __syncthreads();
-  const long long slot0 = PREFIX ? sm.slot0 : slot0_in;
-  const long long slot_end = sm.slot_end;
   if (PREFIX) { *slot0_out = slot0; *slot_end_out = slot_end; }
   const long long lo = PREFIX ? slot0 : lo_in;
   long long hi = PREFIX ? slot_end : hi_in;
@@ -499,7 +560,7 @@ GB_D void tile_fill(const unsigned long long *__restrict__ qbuf, const SweepPara
   for (int j = 0; j < kItems; j++) {
     int x = kend[j] - ilo;                    // the particle's range ends at window slot x: it precedes the owners of slots >= x
     x = x < 0 ? 0 : x;                        // (overflow pieces: ended before the window)
-    if (x < cnt) atomicAdd(&sm.ends[ends_index(x + sh)], 1);
+    if (x < cnt) ends_add(sm, x + sh);
   }
   __syncthreads();
   const int tile_base = (int)(tile * kTile);
@@ -513,7 +574,7 @@ GB_D void tile_fill(const unsigned long long *__restrict__ qbuf, const SweepPara
     if (B < nblk) ends_take(sm, B, v);                      // (leaves the histogram clean)
 #pragma unroll
     for (int e = 1; e < kBlk; e++) v[e] += v[e - 1];
-    run = tile_base + block_exclusive_scan_i32(v[kBlk - 1], sm.warp32);
+    run = tile_base + block_exclusive_scan_i32_1b(v[kBlk - 1], sm.warp32);
     if (B < nblk) {
       const int s = (B << 3) - sh;                          // window slot of element 0 (< 0 only for block 0)
       if (owned && s >= 0 && s + kBlk <= cnt) {
@@ -539,9 +600,7 @@ GB_D void tile_fill(const unsigned long long *__restrict__ qbuf, const SweepPara
   for (int q = 0; q < per; q++) {
     const int B = B0 + q;
     if (B >= nblk) break;
-    const int *src = sm.ends + 9 * B;
-#pragma unroll
-    for (int e = 0; e < kBlk; e++) tot += src[e];
+    tot += ends_sum(sm, B);
   }
   run = tile_base + block_exclusive_scan_i32(tot, sm.warp32);
   for (int q = 0; q < per; q++) {
@@ -570,7 +629,10 @@ GB_D void tile_fill(const unsigned long long *__restrict__ qbuf, const SweepPara
   }
 }
 
-__global__ void __launch_bounds__(kBlock) ancestors_sys_kernel(const unsigned long long *__restrict__ qbuf,
+#ifndef GB_ANC_MINB
+#define GB_ANC_MINB 5
+#endif
+__global__ void __launch_bounds__(kBlock, GB_ANC_MINB) ancestors_sys_kernel(const unsigned long long *__restrict__ qbuf,
                                                                const uint64_t *__restrict__ tile_q,
                                                                const unsigned long long *__restrict__ super_excl,
                                                                const ResamplePlan *__restrict__ plan, const AncOut ao,
