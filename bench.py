@@ -276,6 +276,22 @@ def time_bearings_filter(g, torch, dist, args, n_total, world, zs, steps, warmup
             dist.barrier()
         torch.cuda.synchronize()
 
+    # NCCL calls inside the timed regions, counted (the device-controlled run exchanges through peer memory: zero expected)
+    coll = {"n": 0}
+    coll_names = ("all_reduce", "all_gather", "all_gather_into_tensor", "all_to_all", "all_to_all_single", "broadcast", "reduce",
+                  "reduce_scatter", "reduce_scatter_tensor", "send", "recv", "isend", "irecv", "batch_isend_irecv", "barrier")
+    coll_orig = {}
+    if dist is not None:
+        def counted(fn):
+            def w(*a, **k):
+                coll["n"] += 1
+                return fn(*a, **k)
+            return w
+        for nm in coll_names:
+            if hasattr(dist, nm):
+                coll_orig[nm] = getattr(dist, nm)
+                setattr(dist, nm, counted(coll_orig[nm]))
+
     t = 1
     run_many(t, warmup)
     t += warmup
@@ -306,7 +322,9 @@ def time_bearings_filter(g, torch, dist, args, n_total, world, zs, steps, warmup
     barrier()
     u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     u0.record()
+    coll["n"] = 0
     run_many(t, steps)
+    coll_run = coll["n"]
     t += steps
     u1.record()
     barrier()
@@ -321,12 +339,16 @@ def time_bearings_filter(g, torch, dist, args, n_total, world, zs, steps, warmup
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     lml = None
+    coll["n"] = 0
     for _ in range(steps):
         lml = step(t, sync_scalar=True)
         t += 1
+    coll_e2e = coll["n"]
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    for nm, fn in coll_orig.items():
+        setattr(dist, nm, fn)
     # the variant in which the caller also LOOKS at what particle_filter_step! returns (the N log incremental weights)
     ms_incr = None
     if world == 1 and n_total <= 2 * 10 ** 8:
@@ -346,7 +368,12 @@ def time_bearings_filter(g, torch, dist, args, n_total, world, zs, steps, warmup
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_plain, ms_e2e = (float(x) for x in tt.tolist())
     out = {"n_total": n_total, "ms": ms, "ms_plain": ms_plain, "ms_e2e": ms_e2e, "ms_e2e_incr_per_step": ms_incr, "timing": timing,
-           "clocks": clocks, "lml": lml}
+           "clocks": clocks, "lml": lml,
+           "collectives": None if dist is None else {
+               "torch_distributed_calls_in_timed_region": coll_run, "per_step_in_e2e_region": coll_e2e / max(1, steps),
+               "how": "every torch.distributed collective / point-to-point entry wrapped with a counter; the timed region is K steps of "
+                      "the device-controlled run (max, weight sums and offspring rows travel through peer memory written by the "
+                      "filter's own kernels); the barriers that bracket the region are outside the count"}}
     del state
     if world == 1:
         del pf
@@ -602,6 +629,7 @@ def run_genb200(args):
         "kernels": kernels,
         "cpu_baseline": cpu,
         "sharded_parity": parity,
+        "collectives": main.get("collectives"),
         "weak" if scaling == "strong" else "strong": second(other, "weak" if scaling == "strong" else "strong"),
         "configs": other_configs(g, torch, peak) if world == 1 and not args.no_configs else None,
         "log_ml_error": log_ml_error_check(g) if world == 1 else None,

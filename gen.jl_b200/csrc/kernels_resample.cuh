@@ -209,9 +209,23 @@ __global__ void __launch_bounds__(kBlock) multinomial_guided_kernel(const uint64
     j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
     long long a = __ldg(guide + j);
     long long b = j + 3 < n ? (long long)__ldg(guide + j + 3) : n - 1;
-    while (a < b) {
-      const long long mid = (a + b) >> 1;
-      if (__ldg(cdf + mid) > tau) b = mid; else a = mid + 1;
+    // the bracket [a, b] holds ~4 particles: its CDF entries are fetched with INDEPENDENT loads (one or two sectors in
+    // flight at once) and counted, instead of a chain of three dependent probes -- the kernel is bound by the latency of
+    // its random accesses, not by their bytes.  The answer is the first index in [a, b] whose CDF exceeds tau (b if none
+    // before it does: the bracket always contains it), i.e. a + #{i in [a, b) : cdf[i] <= tau} because the CDF is monotone.
+    if (b - a <= 8) {
+      uint64_t c[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) c[e] = a + e < b ? __ldg(cdf + a + e) : ~0ull;
+      int below = 0;
+#pragma unroll
+      for (int e = 0; e < 8; e++) below += c[e] <= tau ? 1 : 0;
+      a += below;
+    } else {
+      while (a < b) {
+        const long long mid = (a + b) >> 1;
+        if (__ldg(cdf + mid) > tau) b = mid; else a = mid + 1;
+      }
     }
     anc[k] = (int)a;
   }
