@@ -264,8 +264,13 @@ __global__ void xchg_post_max_kernel(WeightStats *stats) {
 // shared-memory slots with asynchronous copies (cp.async: global -> shared without passing through registers, a deep
 // queue per SM) while the current iteration computes, and reads them back one iteration later.  0: the r1 scheme (L2
 // prefetch of the next rows, ld.global.nc at the point of use).
+// Measured (profiles/README.md, r2i / r2ai / r2aj): with the 84-byte kernel of r2i the staged form was 1 % SLOWER (1.5515 vs
+// 1.5345 ms at N = 1e8); once the gathered step stopped writing the increments twice (76 bytes) it is faster for every model
+// and dtype -- N = 2e7: bearings 0.281 vs 0.291 ms (fp32 0.242 vs 0.259), SV 0.222 vs 0.227 (0.174 vs 0.183), LGSSM 0.185 vs
+// 0.191 (0.144 vs 0.151); N = 1e8 bearings fp64 1.39 vs 1.41 ms.  ncu: the long-scoreboard stall (1.66 warps per issue slot)
+// is gone, what is left is the fixed-latency dependency chain of the fp64 transition ("wait" 3.0) at 64 % issue-active.
 #ifndef GB_STEP_STAGE
-#define GB_STEP_STAGE 0
+#define GB_STEP_STAGE 1
 #endif
 template <int BYTES> GB_D void cp_async(void *smem_dst, const void *gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
