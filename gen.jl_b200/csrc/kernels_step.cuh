@@ -278,24 +278,21 @@ template <int BYTES> GB_D void cp_async(void *smem_dst, const void *gmem_src) {
 }
 GB_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> GB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-template <typename R, int KIND, int PK, bool INIT, bool PREDRAWN, int GATHER /* 0 no, 1 yes, 2 ctl->do_resample */>
-__global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepArgs a) {
+// The body of the step kernel, specialised on whether the step reads through the ancestors (GATHER 1) or not (0).  DEVCTL:
+// the choice was taken from the device flag by the kernel below (it is then recorded for the host, see share_incr).
+template <typename R, int KIND, int PK, bool INIT, bool PREDRAWN, int GATHER /* 0 no, 1 yes */, bool DEVCTL>
+GB_D void step_body(const StepArgs &a, const MathTables &T) {
   // R is the STORAGE type (traces, log weights, noise); the transition itself (propose + logpdf) is always evaluated in
   // fp64 on the widened values (models.cuh "Arith"), so a GB_F32 filter differs from the fp64 one only by the rounding of
   // what it stores.
   typedef typename Arith<R>::type A;
   typedef Transition<A, KIND, PK, INIT> Tr;
   constexpr int V = StepV<R>::V, S = Tr::S, NN = Tr::NN, NU = Tr::NU;
-  __shared__ double s_tab[kMathTabDoubles];
-  pdl_trigger();
-  const MathTables T = stage_math_tables(s_tab);   // constants only: overlaps the predecessor's tail
-  __syncthreads();
-  pdl_wait();
   // sharded filter: peers' offspring rows are in (no-op otherwise).  (A lazy variant -- only the warps whose slots another
   // shard's sweep produced wait, right before their first ancestor load -- hides nothing: the particles are dealt to the
   // threads statically, so a warp that starts late finishes late by the same amount, and the extra live registers made the
   // fp64 bearings instantiation spill: 2-GPU step kernel 0.756 -> 0.834 ms, profiles/README.md r2v.)
-  if (!INIT && GATHER != 0) xchg_wait_done(a.stats);
+  if (!INIT && (GATHER != 0 || DEVCTL)) xchg_wait_done(a.stats);
   const R *__restrict__ sin = static_cast<const R *>(a.state_in);
   R *__restrict__ sout = static_cast<R *>(a.state_out);
   R *__restrict__ logw = static_cast<R *>(a.logw);
@@ -315,7 +312,7 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
     else if constexpr (V == 2) { int2 t = __ldcs(reinterpret_cast<const int2 *>(a.anc + ivx * V)); dst[0] = t.x; dst[1] = t.y; }
     else { int4 t = __ldcs(reinterpret_cast<const int4 *>(a.anc + ivx * V)); dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w; }
   };
-  const bool gather = GATHER == 2 ? (a.ctl->do_resample != 0) : (GATHER == 1);
+  constexpr bool gather = GATHER == 1;
   // staged gather: [stage][field][v][thread] -- a thread only ever touches its own column, so the asynchronous copies
   // need no barrier, just cp.async.wait_group
   constexpr bool STAGE = GB_STEP_STAGE && !INIT && GATHER != 0 && S > 0 && (2 * (S > 0 ? S : 1) * V * (int)sizeof(R) * kBlock <= 40 * 1024);
@@ -425,8 +422,26 @@ __global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepAr
     svstore_keep<R, V>(logw + i0, lw_new);
     if (!INIT && !(gather && a.share_incr)) svstore<R, V>(incr + i0, w);
   }
-  if (!INIT && GATHER == 2 && blockIdx.x == 0 && threadIdx.x == 0) a.stats->incr_in_logw = (gather && a.share_incr) ? 1 : 0;
+  if (!INIT && DEVCTL && blockIdx.x == 0 && threadIdx.x == 0) a.stats->incr_in_logw = (gather && a.share_incr) ? 1 : 0;
   publish_max(acc, a.partials, a.ticket, a.stats);
+}
+// GATHER 2: gathered iff ctl->do_resample, decided on the device (fused / sharded runs).  The kernel branches ONCE into one of
+// the two specialised bodies: with the flag as a run-time predicate inside a single body, the fp64 bearings kernel was 12 %
+// slower than the GATHER 1 instantiation (N = 5e7: 0.752 vs 0.674 ms, tools/step_probe.py) -- the reason the sharded step
+// kernel did not follow the single-GPU one when that got faster.
+template <typename R, int KIND, int PK, bool INIT, bool PREDRAWN, int GATHER /* 0 no, 1 yes, 2 ctl->do_resample */>
+__global__ void __launch_bounds__(kBlock, GB_STEP_MINB) step_kernel(const StepArgs a) {
+  __shared__ double s_tab[kMathTabDoubles];
+  pdl_trigger();
+  const MathTables T = stage_math_tables(s_tab);   // constants only: overlaps the predecessor's tail
+  __syncthreads();
+  pdl_wait();
+  if constexpr (GATHER == 2) {
+    if (a.ctl->do_resample != 0) step_body<R, KIND, PK, INIT, PREDRAWN, 1, true>(a, T);
+    else step_body<R, KIND, PK, INIT, PREDRAWN, 0, true>(a, T);
+  } else {
+    step_body<R, KIND, PK, INIT, PREDRAWN, GATHER, false>(a, T);
+  }
 }
 
 // max of an existing log-weight array (after gb_pf_set_log_weights, clone, raw-array entries): 128-bit

@@ -28,4 +28,10 @@ for name, (model, ys) in zoo.items():
         st.sync()
         tm = st.get_timing()
         print("N=%d %-8s %s: " % (n, name, dtype) + ", ".join("%s %.4f ms" % (k.split("(")[0], ms / ln) for k, (ms, ln) in tm.items() if ln))
+        # the device-controlled run (gather decided on the device: the GATHER == 2 instantiation of the step kernel)
+        st.get_timing()
+        g.particle_filter_run_(st, ys[16:16 + T], ess_threshold=n + 1)
+        st.sync()
+        tm = st.get_timing()
+        print("   run_: " + ", ".join("%s %.4f ms" % (k.split("(")[0], ms / ln) for k, (ms, ln) in tm.items() if ln))
         del st
