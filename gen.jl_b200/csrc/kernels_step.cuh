@@ -291,7 +291,9 @@ GB_D void step_body(const StepArgs &a, const MathTables &T) {
   // sharded filter: peers' offspring rows are in (no-op otherwise).  (A lazy variant -- only the warps whose slots another
   // shard's sweep produced wait, right before their first ancestor load -- hides nothing: the particles are dealt to the
   // threads statically, so a warp that starts late finishes late by the same amount, and the extra live registers made the
-  // fp64 bearings instantiation spill: 2-GPU step kernel 0.756 -> 0.834 ms, profiles/README.md r2v.)
+  // fp64 bearings instantiation spill: 2-GPU step kernel 0.756 -> 0.834 ms, profiles/README.md r2v.  Rotating the iteration
+  // order of the affected warps so that their wait falls at the END of their work was tried too, r2an: the modular iteration
+  // index costs the whole kernel 5-8 % on ONE GPU -- 1.39 -> 1.49 ms at N = 1e8 -- far more than the wait it would hide.)
   if (!INIT && (GATHER != 0 || DEVCTL)) xchg_wait_done(a.stats);
   const R *__restrict__ sin = static_cast<const R *>(a.state_in);
   R *__restrict__ sout = static_cast<R *>(a.state_out);
@@ -575,6 +577,11 @@ GB_D void shard_plan_block(WeightStats *stats, const long long *__restrict__ off
   __shared__ long long s_lo[kMaxWorld], s_hi[kMaxWorld];
   __shared__ int s_do;
   __shared__ uint64_t s_w[33];
+  // the scan of this shard's own super-tile totals needs nothing from the peers: it runs while their records are in flight
+  if (do_scan) {
+    superscan_block(nsuper, super_q, super_excl, plan, 0, 0, n_global, u0, overflow_count, 1, s_w);
+    __syncthreads();
+  }
   XchgCtl *xc = stats->xc;
   const int world = xc->world, rank = xc->rank;
   const int r = threadIdx.x;
@@ -582,17 +589,26 @@ GB_D void shard_plan_block(WeightStats *stats, const long long *__restrict__ off
   if (r < world) xchg_spin(&xc->mine->rec_seq[r], seq, xc);
   __syncthreads();
   const int slot = (int)(seq & 1);
+  // the G records are fetched by G threads at once (one L2 round trip instead of 3 G dependent ones on thread 0) ...
+  __shared__ double s_s1[kMaxWorld], s_s2[kMaxWorld];
+  __shared__ unsigned long long s_qk[kMaxWorld];
+  if (r < world) {
+    s_s1[r] = __ldcg(&xc->mine->s1[slot][r]);
+    s_s2[r] = __ldcg(&xc->mine->s2[slot][r]);
+    const unsigned long long qk = __ldcg(&xc->mine->q[slot][r]);
+    s_qk[r] = qk;
+    sh->q_shard[r] = qk;
+  }
+  __syncthreads();
   if (r == 0) {
     const double m = __ldcg(&stats->m);        // the GLOBAL max: wstats folded phase A and left it here
     double S1 = 0.0, S2 = 0.0;
     unsigned long long run = 0;
-    for (int k = 0; k < world; k++) {          // fixed rank order: identical on every shard
-      S1 += __ldcg(&xc->mine->s1[slot][k]);
-      S2 += __ldcg(&xc->mine->s2[slot][k]);
+    for (int k = 0; k < world; k++) {          // ... and summed in fixed rank order: identical on every shard
+      S1 += s_s1[k];
+      S2 += s_s2[k];
       s_pref[k] = run;
-      const unsigned long long qk = __ldcg(&xc->mine->q[slot][k]);
-      sh->q_shard[k] = qk;
-      run += qk;
+      run += s_qk[k];
     }
     s_pref[world] = run;
     const double lse = (m == -INFINITY) ? -INFINITY : m + log(S1);   // inference.jl:5
@@ -641,10 +657,6 @@ GB_D void shard_plan_block(WeightStats *stats, const long long *__restrict__ off
     if (r != rank && s_do && total > sh->peer[r].ext_cap) { sh->overflow = 1; b = a; }   // r cannot park its incoming rows
     sh->send_lo[r] = a; sh->send_hi[r] = b;
     sh->ext_off[r] = before;
-  }
-  if (do_scan) {
-    __syncthreads();
-    superscan_block(nsuper, super_q, super_excl, plan, 0, 0, n_global, u0, overflow_count, 1, s_w);
   }
 }
 __global__ void __launch_bounds__(1024) shard_plan_kernel(WeightStats *stats, const long long *__restrict__ offs, long long n_global, uint32_t u0,
@@ -764,11 +776,15 @@ __global__ void __launch_bounds__(kBlock, GB_WSTATS_MINB) wstats_kernel(const R 
     // taken in rank order by every CTA (identical bits everywhere)
     const unsigned long long seq = __ldcg(&xc->seq_a);
     const int world = xc->world;
-    if ((int)threadIdx.x < world) xchg_spin(&xc->mine->mx_seq[threadIdx.x], seq, xc);
+    __shared__ double s_mx[kMaxWorld];
+    if ((int)threadIdx.x < world) {            // (each waiting thread also fetches the value: one round trip, not G in a row)
+      xchg_spin(&xc->mine->mx_seq[threadIdx.x], seq, xc);
+      s_mx[threadIdx.x] = __ldcg(&xc->mine->mx[seq & 1][threadIdx.x]);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       double g = -INFINITY;
-      for (int r = 0; r < world; r++) g = max_nan(g, __ldcg(&xc->mine->mx[seq & 1][r]));
+      for (int r = 0; r < world; r++) g = max_nan(g, s_mx[r]);
       s_m = g;
     }
     __syncthreads();
