@@ -495,7 +495,9 @@ def other_configs(g, torch, peak):
         lw = torch.zeros(ld, dtype=torch.float64, device="cuda")
         lw[:n] = 3.0 * torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
         anc = torch.empty(ld, dtype=torch.int32, device="cuda")
-        for kind, name in ((L.RESAMPLE_SYSTEMATIC, "systematic"), (L.RESAMPLE_RESIDUAL, "residual"), (L.RESAMPLE_MULTINOMIAL, "multinomial")):
+        for kind, name in ((L.RESAMPLE_SYSTEMATIC, "systematic"), (L.RESAMPLE_RESIDUAL, "residual"),
+                           (L.RESAMPLE_MULTINOMIAL, "multinomial (reference semantics: iid draws in slot order)"),
+                           (L.RESAMPLE_MULTINOMIAL_SORTED, "multinomial_sorted (the same draws' distribution, sorted by ancestor)")):
             def call():
                 L.check(L.lib().gb_resample_device(C.c_void_p(lw.data_ptr()), n, L.F64, kind, 12345, None, 7, 3, C.c_void_p(anc.data_ptr()), None))
             call()

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("GENB200_LIB") or os.path.join(_HERE, "libgenb200.so")
 OK, EINVAL, ENOGPU, ECUDA, EUNSUPPORTED, ESTATE = range(6)
 MODEL_LGSSM, MODEL_SV, MODEL_BEARINGS, MODEL_HMM, MODEL_BLR, MODEL_SPEC = 1, 2, 3, 4, 5, 6
 PROPOSAL_DEFAULT, PROPOSAL_AFFINE_NORMAL, PROPOSAL_CATEGORICAL_TABLE = 0, 1, 2
-RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL = 0, 1, 2
+RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL, RESAMPLE_MULTINOMIAL_SORTED = 0, 1, 2, 3
 MH_RESIMULATE, MH_DRIFT = 0, 1
 F64, F32 = 0, 1
 DIST_NORMAL, DIST_GAMMA, DIST_BERNOULLI, DIST_CATEGORICAL, DIST_MVNORMAL = 1, 2, 3, 4, 5
@@ -61,6 +61,7 @@ SIGNATURES = {
     "gb_spec_jit_compile": (i, [vp, i, i64p]),
     "gb_pf_spec_backend": (i, [vp, ip]),
     "gb_pf_set_resample_noise": (i, [vp, i, u32, u64p]),
+    "gb_pf_set_resample_spacings": (i, [vp, u64p]),
     "gb_pf_log_ml_estimate": (i, [vp, dp]),
     "gb_pf_get_log_weights": (i, [vp, dp]),
     "gb_pf_get_log_increments": (i, [vp, dp]),
@@ -145,6 +146,7 @@ SIGNATURES = {
     "gb_philox_uniforms": (i, [u64, u32, i64, i64, i, i, dp]),
     "gb_philox_resample_u0": (u32, [u64, u32]),
     "gb_philox_multinomial_u64": (i, [u64, u32, i64, i64, u64p]),
+    "gb_philox_sorted_spacings": (i, [u64, u32, i64, i64, u64p]),
     "gb_quant_bits": (i, [i64]),
     "gb_pf_enable_timing": (i, [vp, i]),
     "gb_pf_get_timing": (i, [vp, dp, i64p]),

@@ -23,7 +23,7 @@ UnknownChange = "UnknownChange"
 NoChange = "NoChange"
 
 _RESAMPLERS = {"multinomial": L.RESAMPLE_MULTINOMIAL, "systematic": L.RESAMPLE_SYSTEMATIC,
-               "residual": L.RESAMPLE_RESIDUAL}
+               "residual": L.RESAMPLE_RESIDUAL, "multinomial_sorted": L.RESAMPLE_MULTINOMIAL_SORTED}
 _DTYPES = {"f64": L.F64, "float64": L.F64, "fp64": L.F64, np.float64: L.F64,
            "f32": L.F32, "float32": L.F32, "fp32": L.F32, np.float32: L.F32}
 
@@ -368,6 +368,15 @@ class DeviceParticleFilterState:
             u64s = np.ascontiguousarray(u64s, dtype=np.uint64)
             up = u64s.ctypes.data_as(L.u64p)
         L.check(L.lib().gb_pf_set_resample_noise(self._h, 0 if u0 is None else 1, 0 if u0 is None else int(u0), up))
+
+    def set_resample_spacings(self, spacings):
+        """Validation mode of the sorted multinomial resampler: n + 1 integer spacings for the next resample."""
+        sp = None
+        if spacings is not None:
+            spacings = np.ascontiguousarray(spacings, dtype=np.uint64)
+            assert spacings.size == self.num_particles + 1, "n + 1 spacings"
+            sp = spacings.ctypes.data_as(L.u64p)
+        L.check(L.lib().gb_pf_set_resample_spacings(self._h, sp))
 
     def enable_window(self, W):
         """Keep the last W states of every particle's own lineage (sliding-window rejuvenation); before generate."""
@@ -784,6 +793,13 @@ def philox_uniforms(seed, step, pid0, n, ndraw, dtype="f64"):
 
 def philox_resample_u0(seed, step):
     return int(L.lib().gb_philox_resample_u0(int(seed), int(step)))
+
+
+def philox_sorted_spacings(seed, step, k0, n):
+    """The integer exponential spacings the sorted multinomial resampler derives from Philox (computed on the device)."""
+    out = np.empty(n, dtype=np.uint64)
+    L.check(L.lib().gb_philox_sorted_spacings(int(seed), int(step), int(k0), int(n), out.ctypes.data_as(L.u64p)))
+    return out
 
 
 def philox_multinomial_u64(seed, step, k0, n):

@@ -46,7 +46,7 @@ constexpr double kLog2Pi = 1.8378770664093454835606594728112;  // log(2*pi)
 // function of (seed, step, global particle id, draw index) and so independent of sharding and of the
 // launch geometry.  Same integer spec as the oracle (oracle/gen_oracle.c go_philox4x32_10).
 // ------------------------------------------------------------------------------------------
-enum { PK_NORMAL = 1, PK_UNIFORM = 2, PK_RESAMPLE = 3, PK_MULTI = 4, PK_GAMMA = 5, PK_SAMPLE = 6 };
+enum { PK_NORMAL = 1, PK_UNIFORM = 2, PK_RESAMPLE = 3, PK_MULTI = 4, PK_GAMMA = 5, PK_SAMPLE = 6, PK_SORTED = 7 };
 
 struct U4 { uint32_t x, y, z, w; };
 

@@ -11,6 +11,7 @@
 #include "kernels_mh.cuh"
 #include "kernels_small.cuh"
 #include "kernels_mid.cuh"
+#include "kernels_msort.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -320,6 +321,12 @@ struct gb_pf {
   uint32_t u0 = 0;
   uint64_t *d_u64 = nullptr;
   bool u64_set = false;
+  // sorted multinomial (kernels_msort.cuh): spacings e[0..n] (padded to whole tiles), slot-tile sums + prefixes, particle-tile
+  // CDF, slot-tile -> particle-tile partition, totals
+  unsigned long long *ms_e = nullptr, *ms_st = nullptr, *ms_tcdf = nullptr;
+  int *ms_pt = nullptr;
+  MsortPlan *ms_plan = nullptr;
+  bool ms_e_set = false;            // ms_e holds caller-supplied spacings (gb_pf_set_resample_spacings)
   // resampling workspace
   long long ntiles = 0;
   uint64_t *tile_q = nullptr;
@@ -432,6 +439,7 @@ static void pf_release(gb_pf *pf) {
   gb_dev_free(pf->state[0]); gb_dev_free(pf->state[1]); gb_dev_free(pf->logw); gb_dev_free(pf->incr); gb_dev_free(pf->anc);
   gb_dev_free(pf->parents64); gb_dev_free(pf->ext_parents); gb_dev_free(pf->partials); gb_dev_free(pf->ticket); gb_dev_free(pf->d_stats);
   gb_host_free(pf->h_stats); gb_dev_free(pf->d_normals); gb_dev_free(pf->d_uniforms); gb_dev_free(pf->d_u64);
+  gb_dev_free(pf->ms_e); gb_dev_free(pf->ms_st); gb_dev_free(pf->ms_tcdf); gb_dev_free(pf->ms_pt); gb_dev_free(pf->ms_plan);
   gb_dev_free(pf->d_ctl); gb_host_free(pf->h_ctl); gb_dev_free(pf->d_shplan); gb_host_free(pf->h_shplan); gb_dev_free(pf->d_offs); gb_dev_free(pf->super_q); gb_dev_free(pf->super_excl); gb_dev_free(pf->oflow); gb_dev_free(pf->oflow_count);
   gb_dev_free(pf->tile_q); gb_dev_free(pf->qbuf); gb_dev_free(pf->d_plan); gb_dev_free(pf->mid_ws);
   gb_dev_free(pf->lik); gb_dev_free(pf->guide); gb_dev_free(pf->tile_save);
@@ -592,6 +600,29 @@ extern "C" int gb_pf_set_resample_noise(gb_pf_t *pf, int use_u0, uint32_t u0, co
     CK(cudaStreamSynchronize(pf->stream));
     pf->u64_set = true;
   }
+  return GB_OK;
+}
+
+static long long msort_slot_tiles(const gb_pf *pf) { return (pf->n + 1 + kTile - 1) / kTile; }   // tiles covering e[0..n]
+static int msort_workspace(gb_pf *pf) {
+  const long long nst = msort_slot_tiles(pf);
+  if (!pf->ms_e) CK(gb_dev_alloc((void **)&pf->ms_e, (size_t)nst * kTile * 8));
+  if (!pf->ms_st) CK(gb_dev_alloc((void **)&pf->ms_st, (size_t)(2 * nst + 4) * 8));
+  if (!pf->ms_tcdf) CK(gb_dev_alloc((void **)&pf->ms_tcdf, (size_t)(pf->ntiles + 2) * 8));
+  if (!pf->ms_pt) CK(gb_dev_alloc((void **)&pf->ms_pt, (size_t)(nst + 2) * 4));
+  if (!pf->ms_plan) CK(gb_dev_alloc((void **)&pf->ms_plan, sizeof(MsortPlan)));
+  return GB_OK;
+}
+// validation mode of GB_RESAMPLE_MULTINOMIAL_SORTED: the n + 1 integer spacings (each >= 1, sum < 2^63) in place of Philox
+extern "C" int gb_pf_set_resample_spacings(gb_pf_t *pf, const uint64_t *spacings) {
+  REQ(pf, "null handle");
+  pf->ms_e_set = false;
+  if (!spacings) return GB_OK;
+  int rc = msort_workspace(pf);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(pf->ms_e, spacings, (size_t)(pf->n + 1) * 8, cudaMemcpyHostToDevice, pf->stream));
+  CK(cudaStreamSynchronize(pf->stream));
+  pf->ms_e_set = true;
   return GB_OK;
 }
 
@@ -1703,6 +1734,36 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
     CK(cudaGetLastError());
     return GB_OK;
   }
+  if (kind == GB_RESAMPLE_MULTINOMIAL_SORTED) {
+    // sorted multinomial: exponential spacings -> sorted thresholds -> one merge with the integer CDF (kernels_msort.cuh).
+    // d_u64: n + 1 caller-supplied spacings on the device (raw-array entry), or ms_e already holds them (ms_e_set)
+    if (!pf->tiles_valid && (rc = run_wstats(pf, logw, m, false))) return rc;
+    if ((rc = msort_workspace(pf))) return rc;
+    const long long nst = msort_slot_tiles(pf), nslot = (pf->n + kTile - 1) / kTile;
+    unsigned long long *st_sum = pf->ms_st, *st_pref = pf->ms_st + nst + 1;
+    if (d_u64) CK(cudaMemcpyAsync(pf->ms_e, d_u64, (size_t)(pf->n + 1) * 8, cudaMemcpyDeviceToDevice, pf->stream));
+    const bool given = d_u64 || pf->ms_e_set;
+    {
+      const int grid = (int)std::min<long long>(nst, (long long)pf->num_sms * 8);
+      if (given)
+        LAUNCH(pf, GB_K_MISC, msort_spacing_kernel<false><<<grid, kBlock, 0, pf->stream>>>(pf->ms_e, pf->n, nst, 0ull, 0u, 0ll, st_sum));
+      else
+        LAUNCH(pf, GB_K_MISC, msort_spacing_kernel<true><<<grid, kBlock, 0, pf->stream>>>(pf->ms_e, pf->n, nst, seed, step, 0ll, st_sum));
+    }
+    LAUNCH(pf, GB_K_TILESCAN, msort_scan_kernel<<<1, 1024, 0, pf->stream>>>(st_sum, st_pref, nst, (const unsigned long long *)pf->tile_q, pf->ms_tcdf,
+                                                                             pf->ntiles, pf->ms_plan));
+    {
+      const int grid = (int)std::min<long long>((nst + 1 + kBlock - 1) / kBlock, (long long)pf->num_sms * 8);
+      LAUNCH(pf, GB_K_TILESCAN, msort_partition_kernel<<<grid, kBlock, 0, pf->stream>>>(st_pref, nst, pf->ms_tcdf, pf->ntiles, pf->ms_plan, pf->ms_pt));
+    }
+    LAUNCH(pf, GB_K_ANCESTORS, msort_fill_kernel<<<(unsigned)nslot, kBlock, 0, pf->stream>>>(pf->ms_e, st_pref, (const unsigned long long *)pf->qbuf,
+                                                                                           pf->ms_tcdf, pf->ntiles, pf->ms_pt, pf->ms_plan, pf->n, anc));
+    CK(cudaGetLastError());
+    pf->tiles_valid = false;      // (the tile totals were only read: the next statistics pass clears them itself)
+    pf->ws_clean = false;
+    pf->ms_e_set = false;
+    return GB_OK;
+  }
   return fail(GB_EINVAL, "unknown resampler kind");
 }
 
@@ -2651,9 +2712,10 @@ extern "C" int gb_resample(const double *logw, int64_t n, int dtype, int kind, u
   cudaError_t e = gb_dev_alloc(&d_lw, (size_t)ld * esz);
   if (e == cudaSuccess) e = cudaMemset(d_lw, 0xFF, (size_t)ld * esz);   // padding = NaN, masked by index anyway
   if (e == cudaSuccess) e = gb_dev_alloc((void **)&d_anc, (size_t)ld * 4);
-  if (e == cudaSuccess && u64s) {
-    e = gb_dev_alloc((void **)&d_u, (size_t)ld * 8);
-    if (e == cudaSuccess) e = cudaMemcpy(d_u, u64s, (size_t)n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && u64s) {      // (sorted multinomial: n + 1 spacings instead of n draws)
+    const size_t nu = (size_t)n + (kind == GB_RESAMPLE_MULTINOMIAL_SORTED ? 1 : 0);
+    e = gb_dev_alloc((void **)&d_u, ((size_t)ld + kTile) * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(d_u, u64s, nu * 8, cudaMemcpyHostToDevice);
   }
   if (e == cudaSuccess) {
     if (dtype == GB_F64) e = cudaMemcpy(d_lw, logw, (size_t)n * 8, cudaMemcpyHostToDevice);
@@ -2805,6 +2867,26 @@ extern "C" int gb_philox_multinomial_u64(uint64_t seed, uint32_t step, int64_t k
     U4 w = philox_block(seed, (uint64_t)(k0 + i), step, PK_MULTI, 0);
     out[i] = ((uint64_t)w.x << 32) | w.y;
   }
+  return GB_OK;
+}
+// the integer exponential spacings GB_RESAMPLE_MULTINOMIAL_SORTED derives from Philox (slots k0 .. k0 + n - 1 of resample
+// `step`), computed by the device kernel itself: what the tests hand to the oracle
+extern "C" int gb_philox_sorted_spacings(uint64_t seed, uint32_t step, int64_t k0, int64_t n, uint64_t *out) {
+  REQ(out && n >= 1 && k0 >= 0, "gb_philox_sorted_spacings: bad argument");
+  int rc = require_gpu();
+  if (rc) return rc;
+  const long long nst = (n + kTile - 1) / kTile;
+  unsigned long long *d = nullptr;
+  CK(gb_dev_alloc((void **)&d, (size_t)nst * kTile * 8));
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)std::min<long long>(nst, (long long)(sms > 0 ? sms : 1) * 8);
+  msort_spacing_kernel<true><<<grid, kBlock>>>(d, n - 1, nst, seed, step, (long long)k0, nullptr);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(out, d, (size_t)n * 8, cudaMemcpyDeviceToHost);
+  gb_dev_free(d);
+  if (e != cudaSuccess) return fail(GB_ECUDA, std::string("gb_philox_sorted_spacings: ") + cudaGetErrorString(e));
   return GB_OK;
 }
 extern "C" int gb_quant_bits(int64_t n_global) { return quant_bits(n_global); }

@@ -63,7 +63,11 @@ enum { GB_MODEL_LGSSM = 1, GB_MODEL_SV = 2, GB_MODEL_BEARINGS = 3, GB_MODEL_HMM 
 enum { GB_PROPOSAL_DEFAULT = 0, GB_PROPOSAL_AFFINE_NORMAL = 1, GB_PROPOSAL_CATEGORICAL_TABLE = 2 };
 /* particle_filter.jl:261-262 is multinomial; systematic / residual are the north-star extensions
  * (exact integer-CDF definitions shared with the oracle). */
-enum { GB_RESAMPLE_MULTINOMIAL = 0, GB_RESAMPLE_SYSTEMATIC = 1, GB_RESAMPLE_RESIDUAL = 2 };
+enum { GB_RESAMPLE_MULTINOMIAL = 0, GB_RESAMPLE_SYSTEMATIC = 1, GB_RESAMPLE_RESIDUAL = 2,
+       /* multinomial resampling with the draws SORTED by ancestor (production mode; not in the reference): the order statistics
+        * of N iid uniforms through exponential spacings, merged with the integer CDF in one streaming pass.  Same multiset
+        * distribution as GB_RESAMPLE_MULTINOMIAL (particle_filter.jl:261-262), different slot order.  Single shard. */
+       GB_RESAMPLE_MULTINOMIAL_SORTED = 3 };
 enum { GB_F64 = 0, GB_F32 = 1 };
 /* distributions for the batched logpdf/random entries (modeling_library/distributions/<name>.jl) */
 enum { GB_DIST_NORMAL = 1, GB_DIST_GAMMA = 2, GB_DIST_BERNOULLI = 3, GB_DIST_CATEGORICAL = 4, GB_DIST_MVNORMAL = 5,
@@ -185,6 +189,9 @@ int gb_pf_run_mh(gb_pf_t *pf, int T, const double *obs, int nobs, double ess_thr
                  int *n_resampled, int64_t *n_accepted);
 /* validation mode for the resampler: u0 for systematic/residual, n u64 for multinomial (NULL clears) */
 int gb_pf_set_resample_noise(gb_pf_t *pf, int use_u0, uint32_t u0, const uint64_t *u64s);
+/* validation mode of GB_RESAMPLE_MULTINOMIAL_SORTED: n + 1 integer spacings (each >= 1, sum < 2^63) in place of the Philox
+ * ones, consumed by the next resample (NULL clears).  gb_resample / gb_resample_device take them through their u64 argument. */
+int gb_pf_set_resample_spacings(gb_pf_t *pf, const uint64_t *spacings);
 int gb_pf_log_ml_estimate(gb_pf_t *pf, double *out);                 /* particle_filter.jl:91-94 */
 int gb_pf_get_log_weights(gb_pf_t *pf, double *out_n);               /* :82-84 (unnormalised) */
 /* The return value of the last particle_filter_step! (:199-207, :231-239), read on demand: gb_pf_step(..., NULL) leaves
@@ -384,6 +391,7 @@ int gb_philox_normals(uint64_t seed, uint32_t step, int64_t pid0, int64_t n, int
 int gb_philox_uniforms(uint64_t seed, uint32_t step, int64_t pid0, int64_t n, int ndraw, int dtype, double *out);
 uint32_t gb_philox_resample_u0(uint64_t seed, uint32_t step);         /* host-side integer, no GPU */
 int gb_philox_multinomial_u64(uint64_t seed, uint32_t step, int64_t k0, int64_t n, uint64_t *out);
+int gb_philox_sorted_spacings(uint64_t seed, uint32_t step, int64_t k0, int64_t n, uint64_t *out);   /* needs a GPU */
 int gb_quant_bits(int64_t n_global);                                   /* host-side, no GPU */
 
 /* ---- instrumentation for bench.py: per-kernel CUDA-event timings on the handle's stream ---- */

@@ -25,7 +25,7 @@ const libgenb200 = get(ENV, "GENB200_LIB", "libgenb200.so")
 
 const GB_MODEL_LGSSM, GB_MODEL_SV, GB_MODEL_BEARINGS, GB_MODEL_HMM, GB_MODEL_BLR = 1, 2, 3, 4, 5
 const GB_PROPOSAL_DEFAULT, GB_PROPOSAL_AFFINE_NORMAL, GB_PROPOSAL_CATEGORICAL_TABLE = 0, 1, 2
-const GB_RESAMPLE_MULTINOMIAL, GB_RESAMPLE_SYSTEMATIC, GB_RESAMPLE_RESIDUAL = 0, 1, 2
+const GB_RESAMPLE_MULTINOMIAL, GB_RESAMPLE_SYSTEMATIC, GB_RESAMPLE_RESIDUAL, GB_RESAMPLE_MULTINOMIAL_SORTED = 0, 1, 2, 3
 const GB_F64, GB_F32 = 0, 1
 
 # every entry returns a status; the message replaces Julia's error(...) (particle_filter.jl:227-229)

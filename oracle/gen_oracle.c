@@ -382,6 +382,33 @@ int go_resample_multinomial(const double *logw, int64_t n, const uint64_t *u, in
   free(cdf);
   return 0;
 }
+/* sorted multinomial (production mode, not in the reference): the ORDER STATISTICS of N iid uniforms on [0, Q_N) through
+ * exponential spacings -- U_(k) = (E_0 + ... + E_k) / (E_0 + ... + E_N) for iid exponential E_j, a classical identity
+ * (e.g. Devroye 1986, ch. V.3) -- so the draws come out sorted by ancestor and one merge with the integer CDF replaces N
+ * binary searches.  The spacings are INTEGERS e[0..n] (>= 1; the engine derives them from Philox, the tests pass them
+ * in), everything below is exact:  T_k = e_0 + ... + e_k,  T = T_n,
+ *     a_k = min{ j : C_j * T > T_k * Q_N }      (C = inclusive CDF of the quantised weights; T_k < T, so a_k exists).
+ * As a multiset the ancestors have the distribution of particle_filter.jl:261-262's N iid categorical draws (up to the
+ * 2^-30 resolution of the spacings); slot order differs (sorted instead of iid), which Gen's particle filter never
+ * looks at: traces are exchangeable after a resample. */
+int go_resample_multinomial_sorted(const double *logw, int64_t n, const uint64_t *e, int64_t *anc) {
+  double m = array_max(logw, n);
+  if (m == -INFINITY || isnan(m)) return -1;
+  int b = go_quant_bits(n);
+  uint64_t *q = (uint64_t *)malloc((size_t)n * 8);
+  uint64_t qn = go_quantized_weights(logw, n, m, b, q);
+  u128 total = 0;
+  for (int64_t k = 0; k <= n; k++) total += e[k];
+  int64_t j = 0;
+  u128 cdf = q[0], t = 0;
+  for (int64_t k = 0; k < n; k++) {
+    t += e[k];
+    while (!(cdf * total > t * qn)) { j++; cdf += q[j]; }
+    anc[k] = j;
+  }
+  free(q);
+  return 0;
+}
 /* residual: c_j = floor(N q_j / Q_N) copies; R = N - sum c_j slots by systematic resampling on
  * r_j = N q_j - c_j Q_N (sum r_j = R * Q_N).  Output sorted by ancestor. */
 int go_resample_residual(const double *logw, int64_t n, uint32_t u0, int64_t *anc) {
@@ -731,7 +758,10 @@ int go_pf_maybe_resample(go_pf_t *pf, double ess_threshold, int kind, int use_gi
   int rc = 0;
   if (kind == GO_RESAMPLE_SYSTEMATIC) rc = go_resample_systematic(pf->logw, n, u, anc);
   else if (kind == GO_RESAMPLE_RESIDUAL) rc = go_resample_residual(pf->logw, n, u, anc);
-  else {
+  else if (kind == GO_RESAMPLE_MULTINOMIAL_SORTED) {
+    /* u64s = the n + 1 integer spacings (required: the engine's come from its own table-driven log, exported to the tests) */
+    rc = u64s ? go_resample_multinomial_sorted(pf->logw, n, u64s, anc) : -2;
+  } else {
     uint64_t *tmp = NULL;
     if (!u64s) {
       tmp = (uint64_t *)malloc((size_t)n * 8);

@@ -29,7 +29,7 @@ extern "C" {
 /* model kinds / proposal kinds / resampler kinds: numeric values match include/genb200.h */
 enum { GO_MODEL_LGSSM = 1, GO_MODEL_SV = 2, GO_MODEL_BEARINGS = 3, GO_MODEL_HMM = 4, GO_MODEL_BLR = 5 };
 enum { GO_PROPOSAL_DEFAULT = 0, GO_PROPOSAL_AFFINE_NORMAL = 1, GO_PROPOSAL_CATEGORICAL_TABLE = 2 };
-enum { GO_RESAMPLE_MULTINOMIAL = 0, GO_RESAMPLE_SYSTEMATIC = 1, GO_RESAMPLE_RESIDUAL = 2 };
+enum { GO_RESAMPLE_MULTINOMIAL = 0, GO_RESAMPLE_SYSTEMATIC = 1, GO_RESAMPLE_RESIDUAL = 2, GO_RESAMPLE_MULTINOMIAL_SORTED = 3 };
 
 /* ---- distributions (src/modeling_library/distributions/{normal,gamma,...}.jl) ---- */
 double go_logpdf_normal(double x, double mu, double std);
@@ -65,6 +65,7 @@ uint64_t go_quantized_weights(const double *logw, int64_t n, double m, int b, ui
 /* ancestors are 0-based here; callers add 1 for Gen's `parents` */
 int go_resample_systematic(const double *logw, int64_t n, uint32_t u0, int64_t *anc);
 int go_resample_multinomial(const double *logw, int64_t n, const uint64_t *u, int64_t *anc);
+int go_resample_multinomial_sorted(const double *logw, int64_t n, const uint64_t *e /* n + 1 spacings */, int64_t *anc);
 int go_resample_residual(const double *logw, int64_t n, uint32_t u0, int64_t *anc);
 
 /* ---- exact log-ML oracles ---- */

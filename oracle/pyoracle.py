@@ -16,7 +16,7 @@ import build as _build  # noqa: E402
 
 MODEL_LGSSM, MODEL_SV, MODEL_BEARINGS, MODEL_HMM, MODEL_BLR = 1, 2, 3, 4, 5
 PROPOSAL_DEFAULT, PROPOSAL_AFFINE_NORMAL, PROPOSAL_CATEGORICAL_TABLE = 0, 1, 2
-RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL = 0, 1, 2
+RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC, RESAMPLE_RESIDUAL, RESAMPLE_MULTINOMIAL_SORTED = 0, 1, 2, 3
 
 _lib = None
 _dp = C.POINTER(C.c_double)
@@ -55,6 +55,7 @@ def lib():
             "go_quantized_weights": (u64, [_dp, i64, d, i, _u64p]),
             "go_resample_systematic": (i, [_dp, i64, u32, _i64p]),
             "go_resample_multinomial": (i, [_dp, i64, _u64p, _i64p]),
+            "go_resample_multinomial_sorted": (i, [_dp, i64, _u64p, _i64p]),
             "go_resample_residual": (i, [_dp, i64, u32, _i64p]),
             "go_kalman_logml": (d, [d, d, d, d, d, _dp, i]),
             "go_hmm_forward": (d, [_dp, _dp, _dp, i, i, _i64p, i]),
@@ -177,6 +178,10 @@ def resample(kind, logw, u0=0, u64s=None):
         rc = lib().go_resample_systematic(p, a.size, u0, ap)
     elif kind == RESAMPLE_RESIDUAL:
         rc = lib().go_resample_residual(p, a.size, u0, ap)
+    elif kind == RESAMPLE_MULTINOMIAL_SORTED:
+        e = np.ascontiguousarray(u64s, dtype=np.uint64)            # the n + 1 integer spacings
+        assert e.size == a.size + 1, "sorted multinomial takes n + 1 spacings"
+        rc = lib().go_resample_multinomial_sorted(p, a.size, e.ctypes.data_as(_u64p), ap)
     else:
         u = np.ascontiguousarray(u64s, dtype=np.uint64)
         rc = lib().go_resample_multinomial(p, a.size, u.ctypes.data_as(_u64p), ap)

@@ -141,6 +141,71 @@ def test_resamplers_bit_exact(g, O, n, shape):
     assert np.array_equal(got, O.resample(O.RESAMPLE_MULTINOMIAL, lw, u64s=O.philox_multinomial_u64(17, 3, 0, n)))
 
 
+@pytest.mark.parametrize("n", [1, 2, 7, 2047, 2048, 2049, 4095, 8193, 100003, 1 << 20])
+@pytest.mark.parametrize("shape", ["normal", "equal", "onehot", "ramp"])
+def test_sorted_multinomial_bit_exact(g, O, n, shape):
+    """GB_RESAMPLE_MULTINOMIAL_SORTED (kernels_msort.cuh): sorted thresholds from integer exponential spacings, one merge with
+    the integer CDF.  Bit-exact against the oracle's two-pointer restatement (exact 128-bit rational comparisons), for
+    caller-supplied spacings and for the Philox-derived ones exported from the device."""
+    if shape == "ramp":            # weights falling over 60 orders of magnitude: slot tiles that span many particle tiles
+        lw = -140.0 * np.arange(n) / max(n - 1, 1)
+    else:
+        lw = F.resample_logw(n, shape)
+        if shape == "onehot" and n > 3:
+            lw = np.roll(lw, n // 3)
+    rng = np.random.default_rng(n + 1)
+    e = rng.integers(1, 2 ** 31, size=n + 1, dtype=np.uint64)
+    got = g.resample(lw, "multinomial_sorted", u64s=e)
+    exp = O.resample(O.RESAMPLE_MULTINOMIAL_SORTED, lw, u64s=e)
+    assert np.array_equal(got, exp), np.flatnonzero(got != exp)[:5]
+    assert np.all(np.diff(got) >= 0)
+    e = g.philox_sorted_spacings(17, 3, 0, n + 1)
+    assert e.min() >= 1 and abs(np.log2(e.astype(np.float64).mean()) - 30.0) < (0.05 if n > 10000 else 8.0)
+    got = g.resample(lw, "multinomial_sorted", seed=17, step=3)
+    assert np.array_equal(got, O.resample(O.RESAMPLE_MULTINOMIAL_SORTED, lw, u64s=e))
+    assert np.array_equal(g.philox_sorted_spacings(17, 3, 5, 3), e[5:8]) if n >= 7 else True
+
+
+def test_sorted_multinomial_properties_large(g, O):
+    """N = 10^7: sorted, unbiased (counts ~ multinomial: |count - N w| within 6 sd for the heavy particles, total N), and
+    spacings that ARE exponential (mean 2^30, variance = mean^2)."""
+    n = 10 ** 7
+    lw = F.resample_logw(n, "normal")
+    anc = g.resample(lw, "multinomial_sorted", seed=5, step=9)
+    assert anc.min() >= 0 and anc.max() < n and np.all(np.diff(anc) >= 0)
+    w = np.exp(lw - O.logsumexp(lw))
+    cnt = np.bincount(anc, minlength=n)
+    top = np.argsort(w)[-2000:]
+    z = (cnt[top] - n * w[top]) / np.sqrt(n * w[top] * (1 - w[top]))
+    assert np.abs(z).max() < 6.0 and abs(z.mean()) < 0.15 and abs(z.std() - 1.0) < 0.1
+    e = g.philox_sorted_spacings(5, 9, 0, 10 ** 6).astype(np.float64) / 2.0 ** 30
+    assert abs(e.mean() - 1.0) < 0.005 and abs(e.var() - 1.0) < 0.02
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_particle_filter_with_sorted_multinomial(g, O, dtype):
+    """maybe_resample!(resampler = sorted multinomial) inside the filter loop, lazy and eager gather, against the oracle filter
+    fed with the device's exported spacings: ancestors and states bit-exact."""
+    model, okind_m, params, ys, _, _ = model_zoo(g, O)["bearings"]
+    n, seed = 30011, 21
+    for lazy in (True, False):
+        st = g.initialize_particle_filter(model, (0,), ys[0], n, dtype=dtype, seed=seed)
+        st.set_lazy_gather(lazy)
+        ref = g.initialize_particle_filter(model, (0,), ys[0], n, dtype=dtype, seed=seed)
+        for t in range(1, 6):
+            e = g.philox_sorted_spacings(seed, t - 1, 0, n + 1)
+            assert g.maybe_resample_(st, ess_threshold=n + 1, resampler="multinomial_sorted")
+            exp = O.resample(O.RESAMPLE_MULTINOMIAL_SORTED, ref.log_weights, u64s=e)
+            assert np.array_equal(st.parents - 1, exp)
+            # the reference filter resamples with pre-drawn spacings: same ancestors through the validation entry
+            ref.set_resample_spacings(e)
+            assert g.maybe_resample_(ref, ess_threshold=n + 1, resampler="multinomial_sorted")
+            assert np.array_equal(ref.parents, st.parents)
+            for f in (st, ref):
+                g.particle_filter_step_(f, (t,), (g.UnknownChange,), ys[t], return_incr=False)
+            assert np.array_equal(st.get_state(0), ref.get_state(0)) and np.array_equal(st.log_weights, ref.log_weights)
+
+
 @pytest.mark.parametrize("n", [5, 4099, 1 << 18])
 def test_resamplers_fp32_weights(g, O, n):
     lw = F.resample_logw(n, "normal").astype(np.float32).astype(np.float64)

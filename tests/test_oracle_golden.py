@@ -227,6 +227,30 @@ def test_resamplers_against_python_bigint_definition(O):
             tau = ((k << 32) + u0) * Q >> 32
             cnt[next(j for j in range(n) if rc[j] > tau)] += 1
         assert list(anc) == [j for j in range(n) for _ in range(cnt[j])]
+        # sorted multinomial: thresholds T_k Q / T from integer spacings, exact rational comparison
+        e = [int(v) for v in rng.integers(1, 2 ** 36, size=n + 1, dtype=np.uint64)]
+        anc = O.resample(O.RESAMPLE_MULTINOMIAL_SORTED, lw, u64s=np.array(e, dtype=np.uint64))
+        T, run, exp = sum(e), 0, []
+        for k in range(n):
+            run += e[k]
+            exp.append(next(j for j in range(n) if cdf[j] * T > run * Q))
+        assert list(anc) == exp and exp == sorted(exp)
+
+
+def test_sorted_multinomial_is_multinomial_in_distribution(O):
+    # exponential spacings give the order statistics of iid uniforms: with exponential integer spacings the offspring counts
+    # are multinomial(N, w) -- mean N w_j and variance N w_j (1 - w_j) over repetitions (systematic would have variance < 1/4)
+    rng = np.random.default_rng(8)
+    n, reps = 200, 400
+    lw = 1.5 * rng.standard_normal(n)
+    w = np.exp(lw - O.logsumexp(lw))
+    counts = np.zeros((reps, n))
+    for r in range(reps):
+        e = np.floor(rng.exponential(size=n + 1) * 2.0 ** 30).astype(np.uint64) + 1
+        counts[r] = np.bincount(O.resample(O.RESAMPLE_MULTINOMIAL_SORTED, lw, u64s=e), minlength=n)
+    big = w > 0.01
+    assert np.allclose(counts.mean(axis=0)[big], n * w[big], rtol=0.08)
+    assert np.allclose(counts.var(axis=0)[big], (n * w * (1 - w))[big], rtol=0.3)
 
 
 def test_resampler_statistics(O):

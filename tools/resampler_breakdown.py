@@ -1,4 +1,4 @@
-"""Per-kernel time of maybe_resample! for the three resamplers at N = 1e8 (LGSSM filter, weights after one step)."""
+"""Per-kernel time of maybe_resample! for the resamplers at N = 1e8 (LGSSM filter, weights after one step)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -6,7 +6,7 @@ import __graft_entry__ as entry, fixtures as F
 g = entry.load_package()
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10 ** 8
 ys = F.lgssm_series(8)
-for kind in ("systematic", "residual", "multinomial"):
+for kind in ("systematic", "residual", "multinomial", "multinomial_sorted"):
     st = g.initialize_particle_filter(g.lgssm_model(**F.LGSSM), (0,), ys[0], n, seed=1)
     for t in (1, 2):
         g.maybe_resample_(st, ess_threshold=n + 1, resampler=kind)
