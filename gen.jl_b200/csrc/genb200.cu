@@ -1756,8 +1756,17 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
       const int grid = (int)std::min<long long>((nst + 1 + kBlock - 1) / kBlock, (long long)pf->num_sms * 8);
       LAUNCH(pf, GB_K_TILESCAN, msort_partition_kernel<<<grid, kBlock, 0, pf->stream>>>(st_pref, nst, pf->ms_tcdf, pf->ntiles, pf->ms_plan, pf->ms_pt));
     }
-    LAUNCH(pf, GB_K_ANCESTORS, msort_fill_kernel<<<(unsigned)nslot, kBlock, 0, pf->stream>>>(pf->ms_e, st_pref, (const unsigned long long *)pf->qbuf,
-                                                                                           pf->ms_tcdf, pf->ntiles, pf->ms_pt, pf->ms_plan, pf->n, anc));
+    {
+      const size_t smem = (size_t)2 * kMsPad * sizeof(uint64_t);      // CDF x T of two particle tiles (hi / lo): 73.7 KB
+      static bool attr_set[64] = {false};
+      const int dv = pf->device >= 0 && pf->device < 64 ? pf->device : 0;
+      if (!attr_set[dv]) {
+        CK(cudaFuncSetAttribute(msort_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dv] = true;
+      }
+      LAUNCH(pf, GB_K_ANCESTORS, msort_fill_kernel<<<(unsigned)nslot, kBlock, smem, pf->stream>>>(pf->ms_e, st_pref, (const unsigned long long *)pf->qbuf,
+                                                                                                 pf->ms_tcdf, pf->ntiles, pf->ms_pt, pf->ms_plan, pf->n, anc));
+    }
     CK(cudaGetLastError());
     pf->tiles_valid = false;      // (the tile totals were only read: the next statistics pass clears them itself)
     pf->ws_clean = false;

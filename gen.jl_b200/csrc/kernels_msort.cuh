@@ -31,14 +31,21 @@ GB_D bool gt128(const U128 &x, const U128 &y) { return x.hi > y.hi || (x.hi == y
 
 struct MsortPlan { uint64_t T, Q; };   // total of the spacings, total of the quantised weights
 
-// exponential spacing of slot j, integer, >= 1 (mean 2^30: N <= 2^31 slots sum to < 2^62)
-GB_D uint64_t spacing_from_philox(unsigned long long seed, unsigned long long j, unsigned int step, const MathTables &T) {
-  const U4 w = philox_block(seed, j, step, PK_SORTED, 0);
-  const double u = u52(w.x, w.y);                     // in (0, 1)
-  return (uint64_t)(-gb_log(u, T) * 0x1p30) + 1ull;
+// exponential spacings, integers >= 1 (mean 2^30: N <= 2^31 slots sum to < 2^62).  One Philox block (counter = J / 2) serves
+// the two slots J = 2m and 2m + 1: words (x, y) and (z, w).
+GB_D uint64_t spacing_from_u52(double u, const MathTables &T) { return (uint64_t)(-gb_log(u, T) * 0x1p30) + 1ull; }
+GB_D void spacing_pair(unsigned long long seed, unsigned long long m, unsigned int step, const MathTables &T, uint64_t &e0, uint64_t &e1) {
+  const U4 w = philox_block(seed, m, step, PK_SORTED, 0);
+  e0 = spacing_from_u52(u52(w.x, w.y), T);
+  e1 = spacing_from_u52(u52(w.z, w.w), T);
+}
+GB_D uint64_t spacing_one(unsigned long long seed, unsigned long long J, unsigned int step, const MathTables &T) {
+  const U4 w = philox_block(seed, J >> 1, step, PK_SORTED, 0);
+  return (J & 1) ? spacing_from_u52(u52(w.z, w.w), T) : spacing_from_u52(u52(w.x, w.y), T);
 }
 
-// e[j] for j in [0, n] (GEN: generated and written; otherwise read), zero beyond; st_sum[s] = sum over slot tile s
+// e[j] for j in [0, n] (GEN: generated for global slot j0 + j and written; otherwise read), zero beyond; st_sum[s] = sum
+// over slot tile s
 template <bool GEN>
 __global__ void __launch_bounds__(kBlock) msort_spacing_kernel(unsigned long long *__restrict__ e, long long n, long long nst,
                                                                unsigned long long seed, unsigned int step, long long j0,
@@ -49,13 +56,25 @@ __global__ void __launch_bounds__(kBlock) msort_spacing_kernel(unsigned long lon
   __syncthreads();
   for (long long s = blockIdx.x; s < nst; s += gridDim.x) {
     uint64_t sum = 0;
+    if (GEN && (j0 & 1) == 0) {                     // two consecutive slots per thread and Philox block, 128-bit stores
 #pragma unroll
-    for (int i = 0; i < kItems; i++) {
-      const long long j = s * kTile + (long long)i * kBlock + threadIdx.x;
-      uint64_t v = 0;
-      if (j <= n) v = GEN ? spacing_from_philox(seed, (unsigned long long)(j0 + j), step, T) : e[j];
-      if (GEN || j > n) e[j] = v;
-      sum += v;
+      for (int i = 0; i < kItems / 2; i++) {
+        const long long j = s * kTile + (long long)i * (2 * kBlock) + 2 * threadIdx.x;
+        uint64_t v0 = 0, v1 = 0;
+        if (j <= n) spacing_pair(seed, (unsigned long long)(j0 + j) >> 1, step, T, v0, v1);
+        if (j + 1 > n) v1 = 0;
+        *reinterpret_cast<ulonglong2 *>(e + j) = make_ulonglong2(v0, v1);
+        sum += v0 + v1;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kItems; i++) {
+        const long long j = s * kTile + (long long)i * kBlock + threadIdx.x;
+        uint64_t v = 0;
+        if (j <= n) v = GEN ? spacing_one(seed, (unsigned long long)(j0 + j), step, T) : e[j];
+        if (GEN || j > n) e[j] = v;
+        sum += v;
+      }
     }
     sum = block_sum_u64(sum, s_w);
     if (threadIdx.x == 0 && st_sum) st_sum[s] = sum;
@@ -63,43 +82,49 @@ __global__ void __launch_bounds__(kBlock) msort_spacing_kernel(unsigned long lon
   }
 }
 
-// exclusive scan of in[0..n) into out[0..n], out[n] = total; one CTA of 1024 threads (contiguous chunk per thread)
+// exclusive scan of in[0..n) into out[0..n], out[n] = total; one CTA of 1024 threads walking the array in chunks of 4096
+// (four consecutive elements per thread: coalesced), carry in a register.  (First version: one contiguous chunk of n / 1024
+// elements per thread -- every load instruction of a warp touched 32 different sectors, 0.2 ms for two arrays of 49 k entries.)
 GB_D uint64_t msort_scan_array(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out, long long n, uint64_t *s_w /* 33 */) {
-  const int Tn = blockDim.x;
-  const long long per = (n + Tn - 1) / Tn;
-  const long long lo = (long long)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
-  uint64_t a = 0;
-  for (long long i = lo; i < hi; i++) a += __ldcg(in + i);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = Tn >> 5;
-  uint64_t inc = a;
+  const int Tn = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = Tn >> 5;
+  uint64_t carry = 0;
+  for (long long base = 0; base < n; base += (long long)Tn * 4) {
+    const long long i0 = base + (long long)threadIdx.x * 4;
+    uint64_t v[4];
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint64_t o = shfl_up_u64(inc, d);
-    if (lane >= d) inc += o;
-  }
-  __syncthreads();
-  if (lane == 31) s_w[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint64_t w = lane < nwarp ? s_w[lane] : 0, winc = w;
+    for (int k = 0; k < 4; k++) v[k] = i0 + k < n ? __ldcg(in + i0 + k) : 0;
+    const uint64_t a = v[0] + v[1] + v[2] + v[3];
+    uint64_t inc = a;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      uint64_t o = shfl_up_u64(winc, d);
-      if (lane >= d) winc += o;
+      uint64_t o = shfl_up_u64(inc, d);
+      if (lane >= d) inc += o;
     }
-    s_w[lane] = winc - w;
-    if (lane == 31) s_w[32] = winc;
+    __syncthreads();                                   // (s_w of the previous chunk has been read)
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint64_t w = lane < nwarp ? s_w[lane] : 0, winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint64_t o = shfl_up_u64(winc, d);
+        if (lane >= d) winc += o;
+      }
+      s_w[lane] = winc - w;
+      if (lane == 31) s_w[32] = winc;
+    }
+    __syncthreads();
+    uint64_t run = carry + s_w[warp] + (inc - a);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i0 + k < n) out[i0 + k] = run;
+      run += v[k];
+    }
+    carry += s_w[32];
   }
   __syncthreads();
-  uint64_t run = s_w[warp] + (inc - a);
-  const uint64_t total = s_w[32];
-  for (long long i = lo; i < hi; i++) {
-    const uint64_t v = __ldcg(in + i);
-    out[i] = run;
-    run += v;
-  }
-  if (threadIdx.x == 0) out[n] = total;
-  return total;
+  if (threadIdx.x == 0) out[n] = carry;
+  return carry;
 }
 __global__ void __launch_bounds__(1024) msort_scan_kernel(const unsigned long long *__restrict__ st_sum, unsigned long long *__restrict__ st_pref,
                                                           long long nst, const unsigned long long *__restrict__ tile_q,
@@ -128,19 +153,28 @@ __global__ void __launch_bounds__(kBlock) msort_partition_kernel(const unsigned 
 }
 
 // one CTA per slot tile s: ancestors of slots [2048 s, 2048 s + 2048) below n.
-// The particle tile's CDF goes to shared memory ALREADY MULTIPLIED by T (128-bit, hi / lo arrays): a probe of the search is
-// then two shared-memory loads and a compare instead of a 64 x 64 -> 128-bit multiply (the first version multiplied in every
-// probe and searched every slot from scratch: 4.4 ms per 1e8 slots).  A thread's 8 slots are consecutive sorted thresholds,
-// so after the first one (binary search) the next ancestor is a few particles further: linear probes, binary only as fallback.
-constexpr int kMsPad = kTile + kTile / 8;            // one padding entry per 8: the blocked stores spread over the banks
+// The CDF of the particle tiles the slot tile reaches into goes to shared memory ALREADY MULTIPLIED by T (128-bit, hi / lo
+// arrays): a probe of the search is then two shared-memory loads and a compare instead of a 64 x 64 -> 128-bit multiply.
+// Three CTAs per SM (77 registers, a few spilled words: 1.89 vs 2.46 ms at two).  TWO particle tiles per pass (a slot tile
+// usually straddles two): one build phase and one search phase in which every
+// thread has work, instead of one pass per tile with half of the CTA waiting at the barriers (first version, profiles/
+// r2as: barrier 7.9 warps per issue slot).  A thread's 8 slots are consecutive sorted thresholds, so after the first one
+// (binary search) the next ancestor is a few particles further: linear probes, binary only as fallback.
+#ifndef GB_MSORT_MINB
+#define GB_MSORT_MINB 3
+#endif
+constexpr int kMsTiles = 2;                                        // particle tiles per pass
+constexpr int kMsEntries = kMsTiles * kTile;
+constexpr int kMsPad = kMsEntries + kMsEntries / 8;                // one padding entry per 8: the blocked stores spread over the banks
 GB_D int ms_idx(int i) { return i + (i >> 3); }
-__global__ void __launch_bounds__(kBlock, 2) msort_fill_kernel(const unsigned long long *__restrict__ e, const unsigned long long *__restrict__ st_pref,
+__global__ void __launch_bounds__(kBlock, GB_MSORT_MINB) msort_fill_kernel(const unsigned long long *__restrict__ e, const unsigned long long *__restrict__ st_pref,
                                                                const unsigned long long *__restrict__ qbuf,
                                                                const unsigned long long *__restrict__ tile_cdf, long long ntiles,
                                                                const int *__restrict__ pt_lo, const MsortPlan *__restrict__ plan, long long n,
                                                                int *__restrict__ anc) {
-  __shared__ uint64_t s_hi[kMsPad], s_lo[kMsPad];
-  __shared__ uint64_t s_w1[kBlock / 32], s_w2[kBlock / 32];
+  extern __shared__ __align__(16) unsigned char ms_smem[];
+  uint64_t *s_hi = reinterpret_cast<uint64_t *>(ms_smem), *s_lo = s_hi + kMsPad;
+  __shared__ uint64_t s_w1[kBlock / 32], s_w2[kMsTiles][kBlock / 32];
   const long long s = blockIdx.x;
   const uint64_t T = plan->T, Q = plan->Q;
   const long long k0 = s * kTile + (long long)threadIdx.x * kItems;       // first slot of this thread
@@ -168,45 +202,47 @@ __global__ void __launch_bounds__(kBlock, 2) msort_fill_kernel(const unsigned lo
   const int p_lo = pt_lo[s];
   int p_hi = pt_lo[s + 1];
   if (p_hi > ntiles - 1) p_hi = (int)(ntiles - 1);
-  for (int p = p_lo; p <= p_hi; p++) {
-    // inclusive CDF of particle tile p, times T, in shared memory
-    {
-      const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(qbuf + (long long)p * kTile + (long long)threadIdx.x * kItems);
-      uint64_t c[kItems], run = 0;
+  for (int p = p_lo; p <= p_hi; p += kMsTiles) {
+    const int nt = p_hi - p + 1 < kMsTiles ? p_hi - p + 1 : kMsTiles;     // particle tiles in this pass
+    // inclusive CDF of the pass's particle tiles, times T, in shared memory
 #pragma unroll
-      for (int i = 0; i < kItems; i += 2) {
-        const ulonglong2 v = __ldg(src + i / 2);
-        run += v.x; c[i] = run;
-        run += v.y; c[i + 1] = run;
-      }
-      uint64_t total;
-      const uint64_t ex = block_exclusive_scan_1b(run, s_w2, &total) + __ldg(tile_cdf + p);
+    for (int tt = 0; tt < kMsTiles; tt++) {
+      if (tt < nt) {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(qbuf + (long long)(p + tt) * kTile + (long long)threadIdx.x * kItems);
+        uint64_t c[kItems], run = 0;
 #pragma unroll
-      for (int i = 0; i < kItems; i++) {
-        const U128 pr = mul128(ex + c[i], T);
-        const int ix = ms_idx(threadIdx.x * kItems + i);
-        s_hi[ix] = pr.hi;
-        s_lo[ix] = pr.lo;
+        for (int i = 0; i < kItems; i += 2) {
+          const ulonglong2 v = __ldg(src + i / 2);
+          run += v.x; c[i] = run;
+          run += v.y; c[i + 1] = run;
+        }
+        uint64_t total;
+        const uint64_t ex = block_exclusive_scan_1b(run, s_w2[tt], &total) + __ldg(tile_cdf + p + tt);
+#pragma unroll
+        for (int i = 0; i < kItems; i++) {
+          const U128 pr = mul128(ex + c[i], T);
+          const int ix = ms_idx(tt * kTile + threadIdx.x * kItems + i);
+          s_hi[ix] = pr.hi;
+          s_lo[ix] = pr.lo;
+        }
       }
     }
     __syncthreads();
-    const U128 end_t = U128{s_hi[ms_idx(kTile - 1)], s_lo[ms_idx(kTile - 1)]};     // the tile's last CDF value times T
-    int pos = -1;                                             // (-1: no slot of this thread resolved in this tile yet)
+    const int last = nt * kTile - 1;
+    const U128 end_t = U128{s_hi[ms_idx(last)], s_lo[ms_idx(last)]};      // the pass's last CDF value times T
+    int pos = -1;                                             // (-1: no slot of this thread resolved in this pass yet)
     bool open = true;
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
       if (open && i >= i_cur && i < nvalid) {
         const U128 tq = mul128(tk[i], Q);
-        if (gt128(end_t, tq)) {                              // the ancestor lies in this tile: first index whose C * T > T_k * Q
-          int lo = pos < 0 ? 0 : pos, hi = kTile - 1;
+        if (gt128(end_t, tq)) {                              // the ancestor lies in this pass: first index whose C * T > T_k * Q
+          int lo = pos < 0 ? 0 : pos, hi = last;
           bool found = false;
           if (pos >= 0) {                                    // sorted thresholds: a few particles further than the last one
-#pragma unroll
-            for (int st = 0; st < 4; st++) {
-              if (!found) {
-                const int ix = ms_idx(lo);
-                if (gt128(U128{s_hi[ix], s_lo[ix]}, tq)) found = true; else lo++;
-              }
+            for (int st = 0; st < 4 && !found; st++) {
+              const int ix = ms_idx(lo);
+              if (gt128(U128{s_hi[ix], s_lo[ix]}, tq)) found = true; else lo++;
             }
           }
           if (!found) {
@@ -224,7 +260,7 @@ __global__ void __launch_bounds__(kBlock, 2) msort_fill_kernel(const unsigned lo
         }
       }
     }
-    __syncthreads();                                         // the shared arrays are rebuilt for the next tile
+    __syncthreads();                                         // the shared arrays are rebuilt for the next pass
   }
   if (nvalid == kItems) {
     int4 *dst = reinterpret_cast<int4 *>(anc + k0);
