@@ -528,7 +528,17 @@ extern "C" int gb_pf_create(const gb_model_t *m, int64_t n_local, int64_t n_glob
   return GB_OK;
 }
 
-extern "C" int gb_pf_set_stream(gb_pf_t *pf, void *s) { REQ(pf, "null handle"); pf->stream = (cudaStream_t)s; return GB_OK; }
+// Work enqueued so far (creation-time fills on the stream the handle had, e.g. the legacy default stream) must not be
+// overtaken by kernels on the new stream -- a non-blocking stream does not order itself after the default one, and a handle
+// built from recycled blocks holds stale bytes (an old exchange pointer in d_stats) until its memsets have run.
+extern "C" int gb_pf_set_stream(gb_pf_t *pf, void *s) {
+  REQ(pf, "null handle");
+  DeviceScope ds__(pf->device);
+  CK(cudaStreamSynchronize(pf->stream));
+  CK(cudaDeviceSynchronize());
+  pf->stream = (cudaStream_t)s;
+  return GB_OK;
+}
 extern "C" int gb_pf_sync(gb_pf_t *pf) { REQ(pf, "null handle"); CK(cudaStreamSynchronize(pf->stream)); return GB_OK; }
 extern "C" int gb_pf_set_lazy_gather(gb_pf_t *pf, int lazy) { REQ(pf, "null handle"); pf->lazy = lazy != 0; return GB_OK; }
 extern "C" int gb_pf_num_particles(const gb_pf_t *pf, int64_t *nl, int64_t *ng) {
