@@ -37,8 +37,10 @@ constexpr int kStatsRecordBytes = 48;   // {m, s1, s2, lse, ess, q_total}: what 
 // last CTA peer-stores its 8..24 byte contribution into EVERY shard's mailbox, followed by a sequence flag, and the
 // consuming kernel spins on the G flags of its own (local) mailbox:
 //   phase A  publish_max (tail of the step / max kernel)  -> mx[src]            consumed at the start of wstats
-//   phase B  wstats' last CTA                             -> (s1, s2, q)[src]   consumed by shard_plan_kernel
-//   phase C  export_p2p_kernel's last CTA                 -> done flag          consumed at the top of the next step kernel
+//   phase B  wstats' last CTA                             -> (s1, s2, q)[src]   consumed by shard_plan_block (the same CTA's tail,
+//                                                                               or shard_plan_kernel for synchronous callers)
+//   phase C  overflow_sys_kernel's last CTA (after the     -> done flag          consumed at the top of the next step kernel
+//            offspring export)
 // Payload slots alternate with the parity of the sequence number; a shard can never be more than one phase ahead of a
 // peer (each phase consumes what every peer produced in the previous one), so two slots are enough.  Every shard
 // executes the same sequence of kernels (SPMD), so the expected sequence number is the shard's own post counter.
