@@ -1767,7 +1767,7 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
       LAUNCH(pf, GB_K_TILESCAN, msort_partition_kernel<<<grid, kBlock, 0, pf->stream>>>(st_pref, nst, pf->ms_tcdf, pf->ntiles, pf->ms_plan, pf->ms_pt));
     }
     {
-      const size_t smem = (size_t)2 * kMsPad * sizeof(uint64_t);      // CDF x T of two particle tiles (hi / lo): 73.7 KB
+      const size_t smem = (size_t)kMsPad * sizeof(uint64_t);          // the CDF of kMsTiles particle tiles: 36.9 KB for two
       static bool attr_set[64] = {false};
       const int dv = pf->device >= 0 && pf->device < 64 ? pf->device : 0;
       if (!attr_set[dv]) {

@@ -153,17 +153,22 @@ __global__ void __launch_bounds__(kBlock) msort_partition_kernel(const unsigned 
 }
 
 // one CTA per slot tile s: ancestors of slots [2048 s, 2048 s + 2048) below n.
-// The CDF of the particle tiles the slot tile reaches into goes to shared memory ALREADY MULTIPLIED by T (128-bit, hi / lo
-// arrays): a probe of the search is then two shared-memory loads and a compare instead of a 64 x 64 -> 128-bit multiply.
-// Three CTAs per SM (77 registers, a few spilled words: 1.89 vs 2.46 ms at two).  TWO particle tiles per pass (a slot tile
-// usually straddles two): one build phase and one search phase in which every
-// thread has work, instead of one pass per tile with half of the CTA waiting at the barriers (first version, profiles/
-// r2as: barrier 7.9 warps per issue slot).  A thread's 8 slots are consecutive sorted thresholds, so after the first one
-// (binary search) the next ancestor is a few particles further: linear probes, binary only as fallback.
+// Every threshold is converted to CDF units once -- tau_k = floor(T_k * Q / T), one exact 128/64-bit division (div128_64,
+// common.cuh: double-precision estimates + exact remainder fix-up) -- because for an integer C,  C * T > T_k * Q  <=>
+// C > tau_k.  The particle tiles' CDF then sits in shared memory as plain 64-bit values and a probe of the search is one load
+// and one compare.  (Versions before this one kept C * T as 128-bit products in shared memory: 16 multiplies per thread and
+// pass, twice the shared memory; before that, one multiply per probe -- profiles/README.md r2as.)
+// kMsTiles particle tiles per pass (a slot tile usually straddles two): one build phase and one search phase in which every
+// thread has work, instead of one pass per tile with half of the CTA waiting at the barriers.  A thread's 8 slots are
+// consecutive sorted thresholds, so after the first one (binary search) the next ancestor is a few particles further: linear
+// probes, binary only as fallback.
 #ifndef GB_MSORT_MINB
-#define GB_MSORT_MINB 3
+#define GB_MSORT_MINB 5
 #endif
-constexpr int kMsTiles = 2;                                        // particle tiles per pass
+#ifndef GB_MSORT_TILES
+#define GB_MSORT_TILES 2
+#endif
+constexpr int kMsTiles = GB_MSORT_TILES;                           // particle tiles per pass
 constexpr int kMsEntries = kMsTiles * kTile;
 constexpr int kMsPad = kMsEntries + kMsEntries / 8;                // one padding entry per 8: the blocked stores spread over the banks
 GB_D int ms_idx(int i) { return i + (i >> 3); }
@@ -173,26 +178,30 @@ __global__ void __launch_bounds__(kBlock, GB_MSORT_MINB) msort_fill_kernel(const
                                                                const int *__restrict__ pt_lo, const MsortPlan *__restrict__ plan, long long n,
                                                                int *__restrict__ anc) {
   extern __shared__ __align__(16) unsigned char ms_smem[];
-  uint64_t *s_hi = reinterpret_cast<uint64_t *>(ms_smem), *s_lo = s_hi + kMsPad;
+  uint64_t *s_cs = reinterpret_cast<uint64_t *>(ms_smem);
   __shared__ uint64_t s_w1[kBlock / 32], s_w2[kMsTiles][kBlock / 32];
   const long long s = blockIdx.x;
   const uint64_t T = plan->T, Q = plan->Q;
+  const double t_inv = 1.0 / (double)T;
   const long long k0 = s * kTile + (long long)threadIdx.x * kItems;       // first slot of this thread
-  // T_k of this thread's 8 consecutive slots
-  uint64_t tk[kItems];
+  // tau_k of this thread's 8 consecutive slots
+  uint64_t tau[kItems];
   {
     const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(e + k0);
     uint64_t run = 0;
 #pragma unroll
     for (int i = 0; i < kItems; i += 2) {
       const ulonglong2 v = __ldcs(src + i / 2);
-      run += v.x; tk[i] = run;
-      run += v.y; tk[i + 1] = run;
+      run += v.x; tau[i] = run;
+      run += v.y; tau[i + 1] = run;
     }
     uint64_t total;
     const uint64_t ex = block_exclusive_scan_1b(run, s_w1, &total) + __ldg(st_pref + s);
 #pragma unroll
-    for (int i = 0; i < kItems; i++) tk[i] += ex;
+    for (int i = 0; i < kItems; i++) {
+      const uint64_t tk = tau[i] + ex;                     // T_k <= T
+      tau[i] = div128_64(mulhi64(tk, Q), tk * Q, T, t_inv);
+    }
   }
   const int nvalid = n - k0 >= kItems ? kItems : (n - k0 > 0 ? (int)(n - k0) : 0);
   int a[kItems];
@@ -204,7 +213,7 @@ __global__ void __launch_bounds__(kBlock, GB_MSORT_MINB) msort_fill_kernel(const
   if (p_hi > ntiles - 1) p_hi = (int)(ntiles - 1);
   for (int p = p_lo; p <= p_hi; p += kMsTiles) {
     const int nt = p_hi - p + 1 < kMsTiles ? p_hi - p + 1 : kMsTiles;     // particle tiles in this pass
-    // inclusive CDF of the pass's particle tiles, times T, in shared memory
+    // inclusive CDF of the pass's particle tiles in shared memory
 #pragma unroll
     for (int tt = 0; tt < kMsTiles; tt++) {
       if (tt < nt) {
@@ -219,37 +228,30 @@ __global__ void __launch_bounds__(kBlock, GB_MSORT_MINB) msort_fill_kernel(const
         uint64_t total;
         const uint64_t ex = block_exclusive_scan_1b(run, s_w2[tt], &total) + __ldg(tile_cdf + p + tt);
 #pragma unroll
-        for (int i = 0; i < kItems; i++) {
-          const U128 pr = mul128(ex + c[i], T);
-          const int ix = ms_idx(tt * kTile + threadIdx.x * kItems + i);
-          s_hi[ix] = pr.hi;
-          s_lo[ix] = pr.lo;
-        }
+        for (int i = 0; i < kItems; i++) s_cs[ms_idx(tt * kTile + threadIdx.x * kItems + i)] = ex + c[i];
       }
     }
     __syncthreads();
     const int last = nt * kTile - 1;
-    const U128 end_t = U128{s_hi[ms_idx(last)], s_lo[ms_idx(last)]};      // the pass's last CDF value times T
+    const uint64_t end_c = s_cs[ms_idx(last)];                // the pass's last CDF value
     int pos = -1;                                             // (-1: no slot of this thread resolved in this pass yet)
     bool open = true;
 #pragma unroll
     for (int i = 0; i < kItems; i++) {
       if (open && i >= i_cur && i < nvalid) {
-        const U128 tq = mul128(tk[i], Q);
-        if (gt128(end_t, tq)) {                              // the ancestor lies in this pass: first index whose C * T > T_k * Q
+        const uint64_t t = tau[i];
+        if (end_c > t) {                                     // the ancestor lies in this pass: first index whose C > tau_k
           int lo = pos < 0 ? 0 : pos, hi = last;
           bool found = false;
           if (pos >= 0) {                                    // sorted thresholds: a few particles further than the last one
             for (int st = 0; st < 4 && !found; st++) {
-              const int ix = ms_idx(lo);
-              if (gt128(U128{s_hi[ix], s_lo[ix]}, tq)) found = true; else lo++;
+              if (s_cs[ms_idx(lo)] > t) found = true; else lo++;
             }
           }
           if (!found) {
             while (lo < hi) {
               const int mid = (lo + hi) >> 1;
-              const int ix = ms_idx(mid);
-              if (gt128(U128{s_hi[ix], s_lo[ix]}, tq)) hi = mid; else lo = mid + 1;
+              if (s_cs[ms_idx(mid)] > t) hi = mid; else lo = mid + 1;
             }
           }
           a[i] = p * kTile + lo;
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(kBlock, GB_MSORT_MINB) msort_fill_kernel(const
         }
       }
     }
-    __syncthreads();                                         // the shared arrays are rebuilt for the next pass
+    __syncthreads();                                         // the shared array is rebuilt for the next pass
   }
   if (nvalid == kItems) {
     int4 *dst = reinterpret_cast<int4 *>(anc + k0);
