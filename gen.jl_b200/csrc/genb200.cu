@@ -1760,7 +1760,7 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
       else
         LAUNCH(pf, GB_K_MISC, msort_spacing_kernel<true><<<grid, kBlock, 0, pf->stream>>>(pf->ms_e, pf->n, nst, seed, step, 0ll, st_sum));
     }
-    LAUNCH(pf, GB_K_TILESCAN, msort_scan_kernel<<<1, 1024, 0, pf->stream>>>(st_sum, st_pref, nst, (const unsigned long long *)pf->tile_q, pf->ms_tcdf,
+    LAUNCH(pf, GB_K_TILESCAN, msort_scan_kernel<<<2, 1024, 0, pf->stream>>>(st_sum, st_pref, nst, (const unsigned long long *)pf->tile_q, pf->ms_tcdf,
                                                                              pf->ntiles, pf->ms_plan));
     {
       const int grid = (int)std::min<long long>((nst + 1 + kBlock - 1) / kBlock, (long long)pf->num_sms * 8);

@@ -15,7 +15,7 @@
 //
 // Passes (tiles of 2048, as everywhere):
 //   msort_spacing    e_j (generated, or read) and the sum of every SLOT tile
-//   msort_scan       one CTA: exclusive scan of the slot-tile sums (-> T) and of the PARTICLE-tile totals tile_q (-> Q)
+//   msort_scan       two CTAs: exclusive scan of the slot-tile sums (-> T) / of the PARTICLE-tile totals tile_q (-> Q)
 //   msort_partition  one thread per slot-tile boundary X: the particle tile that contains threshold X (binary search over
 //                    the 49 k tile prefixes, L2 resident)
 //   msort_fill       one CTA per slot tile: T_k of its 2048 slots by a block scan, then for every particle tile in its
@@ -130,10 +130,13 @@ __global__ void __launch_bounds__(1024) msort_scan_kernel(const unsigned long lo
                                                           long long nst, const unsigned long long *__restrict__ tile_q,
                                                           unsigned long long *__restrict__ tile_cdf, long long ntiles, MsortPlan *plan) {
   __shared__ uint64_t s_w[33];
-  const uint64_t T = msort_scan_array(st_sum, st_pref, nst, s_w);
-  __syncthreads();
-  const uint64_t Q = msort_scan_array(tile_q, tile_cdf, ntiles, s_w);
-  if (threadIdx.x == 0) { plan->T = T; plan->Q = Q; }
+  if (blockIdx.x == 0) {                      // (two CTAs: the two scans are independent)
+    const uint64_t T = msort_scan_array(st_sum, st_pref, nst, s_w);
+    if (threadIdx.x == 0) plan->T = T;
+  } else {
+    const uint64_t Q = msort_scan_array(tile_q, tile_cdf, ntiles, s_w);
+    if (threadIdx.x == 0) plan->Q = Q;
+  }
 }
 
 // pt_lo[s] = the particle tile p with tile_cdf[p] * T <= st_pref[s] * Q < tile_cdf[p + 1] * T   (s = 0 .. nst)
