@@ -327,6 +327,11 @@ struct gb_pf {
   int *ms_pt = nullptr;
   MsortPlan *ms_plan = nullptr;
   bool ms_e_set = false;            // ms_e holds caller-supplied spacings (gb_pf_set_resample_spacings)
+  // the Philox spacings depend on (seed, step) only, not on the weights: the raw-array entry generates them on a second
+  // stream while the max and statistics passes run (an issue-bound kernel next to two bandwidth-bound ones)
+  cudaStream_t ms_aux = nullptr;
+  cudaEvent_t ms_fork = nullptr, ms_join = nullptr;
+  bool ms_e_async = false;          // ms_e / the slot-tile sums are being produced on ms_aux: wait for ms_join, skip the spacing pass
   // resampling workspace
   long long ntiles = 0;
   uint64_t *tile_q = nullptr;
@@ -439,6 +444,7 @@ static void pf_release(gb_pf *pf) {
   gb_dev_free(pf->state[0]); gb_dev_free(pf->state[1]); gb_dev_free(pf->logw); gb_dev_free(pf->incr); gb_dev_free(pf->anc);
   gb_dev_free(pf->parents64); gb_dev_free(pf->ext_parents); gb_dev_free(pf->partials); gb_dev_free(pf->ticket); gb_dev_free(pf->d_stats);
   gb_host_free(pf->h_stats); gb_dev_free(pf->d_normals); gb_dev_free(pf->d_uniforms); gb_dev_free(pf->d_u64);
+  if (pf->ms_aux) { cudaStreamSynchronize(pf->ms_aux); cudaStreamDestroy(pf->ms_aux); cudaEventDestroy(pf->ms_fork); cudaEventDestroy(pf->ms_join); }
   gb_dev_free(pf->ms_e); gb_dev_free(pf->ms_st); gb_dev_free(pf->ms_tcdf); gb_dev_free(pf->ms_pt); gb_dev_free(pf->ms_plan);
   gb_dev_free(pf->d_ctl); gb_host_free(pf->h_ctl); gb_dev_free(pf->d_shplan); gb_host_free(pf->h_shplan); gb_dev_free(pf->d_offs); gb_dev_free(pf->super_q); gb_dev_free(pf->super_excl); gb_dev_free(pf->oflow); gb_dev_free(pf->oflow_count);
   gb_dev_free(pf->tile_q); gb_dev_free(pf->qbuf); gb_dev_free(pf->d_plan); gb_dev_free(pf->mid_ws);
@@ -621,6 +627,25 @@ static int msort_workspace(gb_pf *pf) {
   if (!pf->ms_tcdf) CK(gb_dev_alloc((void **)&pf->ms_tcdf, (size_t)(pf->ntiles + 2) * 8));
   if (!pf->ms_pt) CK(gb_dev_alloc((void **)&pf->ms_pt, (size_t)(nst + 2) * 4));
   if (!pf->ms_plan) CK(gb_dev_alloc((void **)&pf->ms_plan, sizeof(MsortPlan)));
+  return GB_OK;
+}
+// spacing pass of GB_RESAMPLE_MULTINOMIAL_SORTED on the auxiliary stream, ordered after everything enqueued on pf->stream so far
+static int msort_prelaunch_spacings(gb_pf *pf, uint64_t seed, uint32_t step) {
+  int rc = msort_workspace(pf);
+  if (rc) return rc;
+  if (!pf->ms_aux) {
+    CK(cudaStreamCreateWithFlags(&pf->ms_aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&pf->ms_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&pf->ms_join, cudaEventDisableTiming));
+  }
+  const long long nst = msort_slot_tiles(pf);
+  CK(cudaEventRecord(pf->ms_fork, pf->stream));
+  CK(cudaStreamWaitEvent(pf->ms_aux, pf->ms_fork, 0));
+  const int grid = (int)std::min<long long>(nst, (long long)pf->num_sms * 8);
+  msort_spacing_kernel<true><<<grid, kBlock, 0, pf->ms_aux>>>(pf->ms_e, pf->n, nst, seed, step, 0ll, pf->ms_st);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(pf->ms_join, pf->ms_aux));
+  pf->ms_e_async = true;
   return GB_OK;
 }
 // validation mode of GB_RESAMPLE_MULTINOMIAL_SORTED: the n + 1 integer spacings (each >= 1, sum < 2^63) in place of Philox
@@ -1753,7 +1778,10 @@ static int compute_ancestors(gb_pf *pf, const void *logw, double m, int kind, ui
     unsigned long long *st_sum = pf->ms_st, *st_pref = pf->ms_st + nst + 1;
     if (d_u64) CK(cudaMemcpyAsync(pf->ms_e, d_u64, (size_t)(pf->n + 1) * 8, cudaMemcpyDeviceToDevice, pf->stream));
     const bool given = d_u64 || pf->ms_e_set;
-    {
+    if (pf->ms_e_async) {            // spacings + slot-tile sums were started on the auxiliary stream: join
+      CK(cudaStreamWaitEvent(pf->stream, pf->ms_join, 0));
+      pf->ms_e_async = false;
+    } else {
       const int grid = (int)std::min<long long>(nst, (long long)pf->num_sms * 8);
       if (given)
         LAUNCH(pf, GB_K_MISC, msort_spacing_kernel<false><<<grid, kBlock, 0, pf->stream>>>(pf->ms_e, pf->n, nst, 0ull, 0u, 0ll, st_sum));
@@ -2709,9 +2737,14 @@ extern "C" int gb_resample_device(const void *dev_logw, int64_t n, int dtype, in
   gb_pf *ws = nullptr;
   int rc = raw_workspace(n, dtype, (cudaStream_t)cuda_stream, &ws);
   if (rc) return rc;
+  ws->ms_e_async = false;
+  if (kind == GB_RESAMPLE_MULTINOMIAL_SORTED && !dev_u64 && (rc = msort_prelaunch_spacings(ws, seed, step))) return rc;
   if ((rc = raw_stats(ws, dev_logw))) return rc;
   const double m = ws->h_stats->m;
-  if (!(m > -INFINITY)) return fail(GB_ESTATE, "gb_resample: all log weights are -Inf or NaN");
+  if (!(m > -INFINITY)) {
+    if (ws->ms_e_async) { cudaStreamSynchronize(ws->ms_aux); ws->ms_e_async = false; }
+    return fail(GB_ESTATE, "gb_resample: all log weights are -Inf or NaN");
+  }
   return dtype == GB_F64 ? compute_ancestors<double>(ws, dev_logw, m, kind, u0, (const uint64_t *)dev_u64, seed, step, (int *)dev_anc)
                          : compute_ancestors<float>(ws, dev_logw, m, kind, u0, (const uint64_t *)dev_u64, seed, step, (int *)dev_anc);
 }
