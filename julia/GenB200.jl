@@ -190,6 +190,15 @@ function maybe_resample!(state::DeviceParticleFilterState; ess_threshold::Real=s
     did[] != 0
 end
 
+# Resampler of the next maybe_resample! calls: :multinomial (Gen's semantics, particle_filter.jl:261-262), :systematic,
+# :residual, or :multinomial_sorted (the same draws' distribution, returned sorted by ancestor: one streaming merge on the
+# device instead of N searches; traces are exchangeable after a resample, so nothing downstream can tell the difference).
+function set_resampler!(state::DeviceParticleFilterState, kind::Symbol)
+    state.resampler = Dict(:multinomial => GB_RESAMPLE_MULTINOMIAL, :systematic => GB_RESAMPLE_SYSTEMATIC,
+                           :residual => GB_RESAMPLE_RESIDUAL, :multinomial_sorted => GB_RESAMPLE_MULTINOMIAL_SORTED)[kind]
+    state
+end
+
 function log_ml_estimate(state::DeviceParticleFilterState)
     r = Ref{Cdouble}()
     check(ccall((:gb_pf_log_ml_estimate, libgenb200), Cint, (Ptr{Cvoid}, Ref{Cdouble}), state.handle, r))
